@@ -1,0 +1,86 @@
+"""ctypes binding of libb200ir.so (include/b200ir.h).  No fallback: if the library is missing the import of
+any compute path raises, and on a box without an sm_100 GPU every entry point returns an error."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libb200ir.so')
+
+MAX_TAPS = 16
+MAX_VIEWS = 4
+
+
+class View(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('c', C.c_int32), ('w', C.c_int32), ('h', C.c_int32), ('b', C.c_int32),
+                ('stride_w', C.c_int64), ('stride_h', C.c_int64), ('stride_b', C.c_int64)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ('a', View * MAX_VIEWS), ('num_views', C.c_int32),
+        ('weight', C.c_void_p), ('cin', C.c_int32), ('cout', C.c_int32), ('num_taps', C.c_int32),
+        ('tap_view', C.c_int8 * MAX_TAPS), ('tap_dx', C.c_int8 * MAX_TAPS), ('tap_dy', C.c_int8 * MAX_TAPS),
+        ('m_w', C.c_int32), ('m_h', C.c_int32), ('m_b', C.c_int32),
+        ('tile_w', C.c_int32), ('tile_h', C.c_int32), ('tile_b', C.c_int32), ('block_n', C.c_int32),
+        ('out', C.c_void_p), ('out_fp32', C.c_int32),
+        ('out_stride_x', C.c_int64), ('out_stride_y', C.c_int64), ('out_stride_b', C.c_int64),
+        ('out_c_off', C.c_int32), ('out_x_mul', C.c_int32), ('out_x_off', C.c_int32),
+        ('out_y_mul', C.c_int32), ('out_y_off', C.c_int32),
+        ('bias', C.c_void_p), ('demod', C.c_void_p), ('noise', C.c_void_p), ('noise_gain', C.c_void_p),
+        ('noise_stride_b', C.c_int64), ('noise_stride_y', C.c_int64),
+        ('act', C.c_int32), ('res_mode', C.c_int32), ('res', C.c_void_p),
+        ('res_stride_x', C.c_int64), ('res_stride_y', C.c_int64), ('res_stride_b', C.c_int64),
+        ('res_w', C.c_int32), ('res_h', C.c_int32), ('res_scale', C.c_float), ('max_ctas', C.c_int32),
+    ]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes (return type is int unless listed in _RESTYPES); mirrors include/b200ir.h one to one
+SIGNATURES = {
+    'b200ir_last_error': [],
+    'b200ir_abi_version': [],
+    'b200ir_launch_count': [],
+    'b200ir_device_check': [],
+    'b200ir_conv_igemm': [C.POINTER(ConvDesc), _P],
+    'b200ir_first_conv': [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_fir_pad22': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'b200ir_fir_down2': [_P, _P, _I, _I, _I, _I, _P],
+    'b200ir_bilinear_up2': [_P, _P, _I, _I, _I, _I, _P],
+    'b200ir_add': [_P, _P, _P, _L, _P],
+    'b200ir_upfir_act': [_P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P, _P, _I, _P, _P],
+    'b200ir_to_rgb': [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    'b200ir_modulate_const': [_P, _P, _P, _I, _I, _I, _P],
+    'b200ir_mod_linear': [_P, _I, _I, _I, _P, _P, _F, _P, _I, _I, _P],
+    'b200ir_demod': [_P, _P, _F, _P, _I, _I, _I, _P],
+    'b200ir_nhwc_to_nchw_f32': [_P, _P, _I, _I, _I, _P],
+    'b200ir_degrade': [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
+}
+_RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built: there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} not found: build it with `python -m image_restoration_b200.build` '
+                               '(or __graft_entry__.build()); image_restoration_b200 has no fallback path')
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = handle
+    return _lib
+
+
+class B200irError(RuntimeError):
+    pass
+
+
+def check(status, what=''):
+    if status != 0:
+        raise B200irError(f'{what}: {lib().b200ir_last_error().decode()}')

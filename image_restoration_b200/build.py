@@ -1,0 +1,51 @@
+"""Builds libb200ir.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+Usage: python -m image_restoration_b200.build [--force]
+The .so lands next to this file so it travels with the repo snapshot to the GPU box.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libb200ir.so')
+SOURCES = ['api.cu', 'conv_igemm.cu', 'pointwise.cu', 'degrade.cu']
+HEADERS = ['ptx.cuh', 'host_common.h', os.path.join('..', '..', 'include', 'b200ir.h')]
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    objs = []
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    for s in SOURCES:
+        obj = os.path.join(HERE, 'build', s.replace('.cu', '.o'))
+        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, s), '-o', obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(' '.join(cmd) + '\n' + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {s}')
+        objs.append(obj)
+    cmd = [nvcc, '-shared', '-o', LIB, *objs, '-lcudart_static', '-ldl', '-lrt', '-lpthread']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('link failed')
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose=True))

@@ -1,0 +1,225 @@
+"""Host-side operator layer over the C ABI: builds b200ir_conv_desc records and launches the kernels on torch's
+current CUDA stream.  torch is used for device memory and streams only; all arithmetic happens in libb200ir.so.
+
+Naming follows the reference operators these replace (EqualConv2d / ModulatedConv2d / ConvUpLayer /
+upfirdn2d / fused_leaky_relu — see include/b200ir.h for file:line).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, View, check
+
+SQRT2 = math.sqrt(2.0)
+INV_SQRT2 = 1.0 / SQRT2
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _req(t, dtype, name):
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f'{name}: expected contiguous CUDA {dtype}, got {t.dtype} on {t.device}')
+
+
+def pick_tile(m_w, m_h, m_b):
+    """Choose (tile_w, tile_h, tile_b), powers of two with product 128, minimising the number of tiles."""
+    best = None
+    for lw in range(8):
+        for lh in range(8 - lw):
+            tw, th, tb = 1 << lw, 1 << lh, 1 << (7 - lw - lh)
+            tiles = -(-m_w // tw) * -(-m_h // th) * -(-m_b // tb)
+            key = (tiles, -tw, -th)
+            if best is None or key < best[0]:
+                best = (key, (tw, th, tb))
+    return best[1]
+
+
+def pick_block_n(cout):
+    for n in (256, 128, 64, 32, 16):
+        if cout % n == 0:
+            return n
+    raise ValueError(f'cout={cout} must be a multiple of 16')
+
+
+def nhwc_view(t, ch=None):
+    """b200ir_view of a contiguous NHWC tensor [B,H,W,C]."""
+    b, h, w, c = t.shape
+    return View(t.data_ptr(), ch or c, w, h, b, c, w * c, h * w * c)
+
+
+class ConvOp:
+    """One prepared b200ir_conv_igemm launch (descriptor built once, launched many times)."""
+
+    def __init__(self, views, weight, cin, cout, taps, m_whb, out, out_strides, *, out_fp32=False, out_c_off=0,
+                 out_mul_off=(1, 0, 1, 0), bias=None, demod=None, noise=None, noise_gain=None, noise_strides=(0, 0),
+                 act=False, res=None, res_mode=0, res_strides=(0, 0, 0), res_wh=(0, 0), res_scale=1.0, block_n=None,
+                 tile=None, max_ctas=0):
+        d = ConvDesc()
+        assert 1 <= len(views) <= _lib.MAX_VIEWS and 1 <= len(taps) <= _lib.MAX_TAPS
+        for i, v in enumerate(views):
+            d.a[i] = v
+        d.num_views = len(views)
+        _req(weight, torch.float16, 'weight')
+        assert weight.shape == (cout, len(taps) * cin), (weight.shape, cout, len(taps), cin)
+        d.weight = weight.data_ptr()
+        d.cin, d.cout, d.num_taps = cin, cout, len(taps)
+        for i, (v, dx, dy) in enumerate(taps):
+            d.tap_view[i], d.tap_dx[i], d.tap_dy[i] = v, dx, dy
+        d.m_w, d.m_h, d.m_b = m_whb
+        d.tile_w, d.tile_h, d.tile_b = tile or pick_tile(*m_whb)
+        d.block_n = block_n or pick_block_n(cout)
+        d.out = out.data_ptr()
+        d.out_fp32 = 1 if out_fp32 else 0
+        d.out_stride_x, d.out_stride_y, d.out_stride_b = out_strides
+        d.out_c_off = out_c_off
+        d.out_x_mul, d.out_x_off, d.out_y_mul, d.out_y_off = out_mul_off
+        for name, t in (('bias', bias), ('demod', demod), ('noise', noise), ('noise_gain', noise_gain)):
+            if t is not None:
+                _req(t, torch.float32, name)
+                setattr(d, name, t.data_ptr())
+        d.noise_stride_b, d.noise_stride_y = noise_strides
+        d.act = 1 if act else 0
+        d.res_mode = res_mode
+        if res is not None:
+            _req(res, torch.float16, 'res')
+            d.res = res.data_ptr()
+        d.res_stride_x, d.res_stride_y, d.res_stride_b = res_strides
+        d.res_w, d.res_h = res_wh
+        d.res_scale = res_scale
+        d.max_ctas = max_ctas
+        self.desc = d
+        # keep every tensor alive as long as the op exists
+        self._keep = (weight, out, bias, demod, noise, noise_gain, res)
+        self._fn = _lib.lib().b200ir_conv_igemm
+
+    def __call__(self):
+        check(self._fn(C.byref(self.desc), _stream()), 'b200ir_conv_igemm')
+
+
+def taps_3x3():
+    return [(0, kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
+
+
+def conv_same(x, weight, out, ksize, **kw):
+    """Stride-1 'same' conv (k = 1 or 3) of NHWC x [B,H,W,Cin] into NHWC out [B,H,W,Ctot] (channel offset via
+    out_c_off).  EqualConv2d / plain ModulatedConv2d / ConvUpLayer conv."""
+    b, h, w, cin = x.shape
+    cout = weight.shape[0]
+    taps = taps_3x3() if ksize == 3 else [(0, 0, 0)]
+    oc = out.shape[3]
+    return ConvOp([nhwc_view(x)], weight, cin, cout, taps, (w, h, b), out, (oc, w * oc, h * w * oc), **kw)
+
+
+def conv3x3_s2(p, h, w, weight, out, **kw):
+    """3x3 stride-2 conv over the FIR-smoothed buffer p [B,H+2,W+2,C] (valid (H+1)x(W+1)) -> out [B,H/2,W/2,Cout].
+    EqualConv2d(stride=2, padding=0) after UpFirDnSmooth, stylegan2_ocr_arch.py:685-697."""
+    b, hp, wp, c = p.shape
+    assert hp == h + 2 and wp == w + 2 and h % 2 == 0 and w % 2 == 0
+    cout = weight.shape[0]
+    views = []
+    for py in range(2):
+        for px in range(2):
+            views.append(View(p.data_ptr() + 2 * (py * wp + px) * c, c, wp // 2, hp // 2, b, 2 * c, 2 * wp * c,
+                              hp * wp * c))
+    taps = [((kh % 2) * 2 + (kw % 2), kw // 2, kh // 2) for kh in range(3) for kw in range(3)]
+    oh, ow = h // 2, w // 2
+    return ConvOp(views, weight, c, cout, taps, (ow, oh, b), out, (cout, ow * cout, oh * ow * cout), **kw)
+
+
+CONVT_PHASES = [(py, px) for py in range(2) for px in range(2)]
+
+
+def convt_phase_taps(py, px):
+    """Taps (kh, kw) of a 3x3 stride-2 transposed conv that land on output rows 2i+py / cols 2j+px."""
+    khs = (0, 2) if py == 0 else (1,)
+    kws = (0, 2) if px == 0 else (1,)
+    return [(kh, kw) for kh in khs for kw in kws]
+
+
+def convt_s2_phase(x, weight_phase, py, px, raw, **kw):
+    """One output phase of conv_transpose2d(stride 2, padding 0, 3x3) (stylegan2_ocr_arch.py:265): x [B,h,w,Cin] ->
+    raw[b, 2i+py, 2j+px, :] for the (2h+1)x(2w+1) valid region of raw [B,RH,RW,Cout]."""
+    b, h, w, cin = x.shape
+    _, rh, rw, cout = raw.shape
+    taps = [(0, -(kwi // 2), -(khi // 2)) for (khi, kwi) in convt_phase_taps(py, px)]
+    m_h = h + 1 if py == 0 else h
+    m_w = w + 1 if px == 0 else w
+    return ConvOp([nhwc_view(x)], weight_phase, cin, cout, taps, (m_w, m_h, b), raw,
+                  (cout, rw * cout, rh * rw * cout), out_mul_off=(2, px, 2, py), **kw)
+
+
+def linear_as_conv(x2d, weight, out, **kw):
+    """EqualLinear as a 1x1 conv over a [B,1,1,K] view; out fp32 [B,N]."""
+    b, k = x2d.shape
+    n = weight.shape[0]
+    v = View(x2d.data_ptr(), k, 1, 1, b, k, k, k)
+    return ConvOp([v], weight, k, n, [(0, 0, 0)], (1, 1, b), out, (n, n, n), out_fp32=True, tile=(1, 1, 128), **kw)
+
+
+# ------------------------------------------------------------------------------------------ memory-bound stages
+def first_conv(x, w, bias, out):
+    b, _, h, wd = x.shape
+    check(_lib.lib().b200ir_first_conv(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), b, h, wd, w.shape[0], _stream()),
+          'first_conv')
+
+
+def fir_pad22(x, out):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_fir_pad22(_ptr(x), _ptr(out), b, h, w, c, out.shape[1], out.shape[2], _stream()),
+          'fir_pad22')
+
+
+def fir_down2(x, out):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_fir_down2(_ptr(x), _ptr(out), b, h, w, c, _stream()), 'fir_down2')
+
+
+def bilinear_up2(x, out):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_bilinear_up2(_ptr(x), _ptr(out), b, h, w, c, _stream()), 'bilinear_up2')
+
+
+def add(a, b, out):
+    check(_lib.lib().b200ir_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), 'add')
+
+
+def upfir_act(raw, out, noise, noise_stride_b, noise_gain, bias, scale, shift, c_sft, s_next):
+    b, h2, w2, c = out.shape
+    check(_lib.lib().b200ir_upfir_act(_ptr(raw), _ptr(out), b, h2, w2, c, raw.shape[1], raw.shape[2], _ptr(noise),
+                                      noise_stride_b, _ptr(noise_gain), _ptr(bias), _ptr(scale), _ptr(shift), c_sft,
+                                      _ptr(s_next), _stream()), 'upfir_act')
+
+
+def to_rgb(x, wrgb, s, bias, skip, rgb, s_next=None, xs_out=None):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_to_rgb(_ptr(x), b, h, w, c, _ptr(wrgb), _ptr(s), _ptr(bias), _ptr(skip), _ptr(rgb),
+                                   _ptr(s_next), _ptr(xs_out), _stream()), 'to_rgb')
+
+
+def modulate_const(cst, s, out):
+    b, h, w, c = out.shape
+    check(_lib.lib().b200ir_modulate_const(_ptr(cst), _ptr(s), _ptr(out), b, h * w, c, _stream()), 'modulate_const')
+
+
+def mod_linear(latent, lat_idx, w, bias, wscale, s):
+    b, L, f = latent.shape
+    check(_lib.lib().b200ir_mod_linear(_ptr(latent), L, f, lat_idx, _ptr(w), _ptr(bias), wscale, _ptr(s), b,
+                                       w.shape[0], _stream()), 'mod_linear')
+
+
+def demod(s, wsq, scale2, d):
+    b, cin = s.shape
+    check(_lib.lib().b200ir_demod(_ptr(s), _ptr(wsq), scale2, _ptr(d), b, cin, wsq.shape[0], _stream()), 'demod')
+
+
+def nhwc_to_nchw_f32(x, out):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_nhwc_to_nchw_f32(_ptr(x), _ptr(out), b, h * w, c, _stream()), 'nhwc_to_nchw_f32')

@@ -1,0 +1,184 @@
+/* b200ir.h — C ABI of libb200ir.so: the B200 (sm_100a) kernels behind the GFPGANv1OCR forward pass
+ * and the pyblur degradation of ChuRuaNh0/Image_Restoration (Car_Plate-Restoration).
+ *
+ * This is the drop-in native boundary.  The reference's own native boundary on this path is two
+ * pybind11 modules:
+ *   fused_act_ext.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *       -> basicsr/ops/fused_act/src/fused_bias_act.cpp:14-26, kernel fused_bias_act_kernel.cu:20-50
+ *   upfirdn2d_ext.upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+ *       -> basicsr/ops/upfirdn2d/src/upfirdn2d.cpp:13-24, kernels upfirdn2d_kernel.cu:51-208
+ * plus the library calls (F.conv2d / F.conv_transpose2d / F.linear / F.interpolate) made from
+ * basicsr/archs/stylegan2_ocr_arch.py and basicsr/archs/gfpganv1_ocr_arch.py, and scipy.signal.convolve2d /
+ * cv2.resize made from pyblur/ and basicsr/data/ffhq_degradation_dataset.py.  Each entry point below names
+ * the reference call it replaces.
+ *
+ * Conventions (same as the reference ops: asynchronous, ordered on the caller's stream, no hidden sync):
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; 0 is the legacy default stream;
+ *   - every function returns 0 on success, non-zero on error; b200ir_last_error() gives the message of the
+ *     last failing call on the calling thread;
+ *   - activations are NHWC fp16 (`__half`), i.e. [B][H][W][C] with C contiguous, unless stated otherwise;
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU every compute entry point returns an error.
+ */
+#ifndef B200IR_H_
+#define B200IR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200IR_ABI_VERSION 1
+#define B200IR_MAX_TAPS 16
+#define B200IR_MAX_VIEWS 4
+
+const char* b200ir_last_error(void);
+int b200ir_abi_version(void);
+/* Number of kernels this library has launched since load (all entry points, all threads). */
+uint64_t b200ir_launch_count(void);
+/* 0 if the current device can run the sm_100a kernels, else non-zero (+ last_error). */
+int b200ir_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ *
+ * Replaces, on the GFPGANv1OCR path: F.conv2d of EqualConv2d.forward (stylegan2_ocr_arch.py:639-648),
+ * the grouped F.conv2d / F.conv_transpose2d of ModulatedConv2d.forward (:261-277), F.conv2d of
+ * ConvUpLayer.forward (gfpganv1_ocr_arch.py:192-198), F.linear of EqualLinear.forward
+ * (stylegan2_ocr_arch.py:165-175, as a 1x1 conv over a [B,1,1,K] view), with the FusedLeakyReLU
+ * (fused_bias_act_kernel.cu:27-48), demodulation (:253-257), noise injection (:326-330) and the residual
+ * merges of ResBlock / ResUpBlock (:733, gfpganv1_ocr_arch.py:224) fused into the epilogue.
+ *
+ * GEMM view: M = output positions (b, y, x) over extents (m_b, m_h, m_w), tiled (tile_b, tile_h, tile_w) with
+ * tile_b*tile_h*tile_w == 128; N = cout tiled by block_n; K = num_taps * cin.
+ * Tap t reads input view tap_view[t] at (b, y + tap_dy[t], x + tap_dx[t], :); out-of-range reads are zero
+ * (TMA out-of-bounds fill), which implements the zero padding of every conv on this path.
+ * Weights are fp16 [cout][num_taps*cin] (K contiguous, tap-major).
+ *
+ * Epilogue, per output element (fp32 math):
+ *   v = acc * (demod ? demod[b*cout + n] : 1)
+ *     + (noise ? noise_gain[0] * noise[b*noise_stride_b + yo*out_w_full + xo] : 0) + (bias ? bias[n] : 0)
+ *   if (act) v = (v > 0 ? v : 0.2 v) * sqrt(2)
+ *   if (res_mode == 1) v = (v + res[b, yo, xo, n]) * res_scale
+ *   if (res_mode == 2) v = (v + bilinear_up2(res_lowres)[b, yo, xo, n]) * res_scale   (align_corners=False)
+ *   out[b, yo, xo, out_c_off + n] = v      with yo = y*out_y_mul + out_y_off, xo = x*out_x_mul + out_x_off
+ */
+typedef struct {
+  const void* ptr; /* fp16, element (b,y,x,c) at ptr[b*stride_b + y*stride_h + x*stride_w + c] */
+  int32_t c, w, h, b;
+  int64_t stride_w, stride_h, stride_b; /* in elements; multiples of 8 */
+} b200ir_view;
+
+typedef struct {
+  b200ir_view a[B200IR_MAX_VIEWS];
+  int32_t num_views;
+  const void* weight; /* fp16 [cout][num_taps*cin] */
+  int32_t cin, cout;
+  int32_t num_taps;
+  int8_t tap_view[B200IR_MAX_TAPS], tap_dx[B200IR_MAX_TAPS], tap_dy[B200IR_MAX_TAPS];
+  int32_t m_w, m_h, m_b;
+  int32_t tile_w, tile_h, tile_b;
+  int32_t block_n; /* 16..256, multiple of 16, divides cout */
+  /* output */
+  void* out;
+  int32_t out_fp32; /* 0: fp16, 1: fp32 */
+  int64_t out_stride_x, out_stride_y, out_stride_b; /* elements */
+  int32_t out_c_off;
+  int32_t out_x_mul, out_x_off, out_y_mul, out_y_off;
+  /* epilogue */
+  const float* bias;       /* [cout] or NULL */
+  const float* demod;      /* [m_b][cout] or NULL */
+  const float* noise;      /* fp32 plane(s) indexed [b*noise_stride_b + yo*noise_stride_y + xo] or NULL */
+  const float* noise_gain; /* device scalar (StyleConv.weight) */
+  int64_t noise_stride_b, noise_stride_y;
+  int32_t act;      /* 0 none, 1 leaky-relu(0.2)*sqrt(2) */
+  int32_t res_mode; /* 0 none, 1 same resolution, 2 bilinear x2 of a half-resolution tensor */
+  const void* res;  /* fp16 NHWC */
+  int64_t res_stride_x, res_stride_y, res_stride_b;
+  int32_t res_w, res_h; /* extents of the residual tensor (for the clamp of mode 2) */
+  float res_scale;
+  int32_t max_ctas; /* 0: one CTA per SM */
+} b200ir_conv_desc;
+
+int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Memory-bound stages (128-bit NHWC access).  FIR = outer([1,3,3,1])/64 (make_resample_kernel,
+ * stylegan2_ocr_arch.py:26-40) evaluated as upfirdn2d does (upfirdn2d.py:162-192; zero padding).
+ */
+
+/* conv_body_first: ConvLayer(3, cout, 1) = EqualConv2d 1x1 + FusedLeakyReLU (stylegan2_ocr_arch.py:658-705).
+ * x: fp32 NCHW [B][3][H][W]; w: fp32 [cout][3] (already scaled by 1/sqrt(3)); bias fp32 [cout]; out NHWC fp16. */
+int b200ir_first_conv(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int cout,
+                      void* stream);
+
+/* UpFirDnSmooth before a stride-2 3x3 conv (pad (2,2), ConvLayer downsample=True, k=3):
+ * in [B][H][W][C] -> out rows/cols 0..H / 0..W of a [B][out_h][out_w][C] buffer (out_h >= H+1, out_w >= W+1). */
+int b200ir_fir_pad22(const void* in, void* out, int B, int H, int W, int C, int out_h, int out_w, void* stream);
+
+/* UpFirDnSmooth (pad (1,1)) followed by the stride-2 sampling of the 1x1 skip conv (ResBlock.skip):
+ * in [B][H][W][C] -> out [B][H/2][W/2][C]. */
+int b200ir_fir_down2(const void* in, void* out, int B, int H, int W, int C, void* stream);
+
+/* F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) (gfpganv1_ocr_arch.py:190). */
+int b200ir_bilinear_up2(const void* in, void* out, int B, int h, int w, int C, void* stream);
+
+/* out = a + b (fp16, n elements, n % 8 == 0): the U-Net skip add, gfpganv1_ocr_arch.py:368. */
+int b200ir_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* Tail of an upsampling StyleConv (stylegan2_ocr_arch.py:261-267,323-333) + SFT (gfpganv1_ocr_arch.py:118-125):
+ * raw: demodulated transposed-conv output, [B][raw_h][raw_w][C] buffer holding (2h+1)x(2w+1) valid samples;
+ * y = FIR*4 with pad (1,1) -> [B][2h][2w][C]; y += noise_gain*noise + bias; y = lrelu(y)*sqrt2;
+ * channels c >= C - c_sft: y = y*scale[..., c-(C-c_sft)] + shift[...]  (scale/shift NHWC fp16 with c_sft channels);
+ * if s_next: y *= s_next[b*C + c]   (modulation of the next conv, stylegan2_ocr_arch.py:247-251). */
+int b200ir_upfir_act(const void* raw, void* out, int B, int h2, int w2, int C, int raw_h, int raw_w, const float* noise,
+                     int64_t noise_stride_b, const float* noise_gain, const float* bias, const void* scale,
+                     const void* shift, int c_sft, const float* s_next, void* stream);
+
+/* ToRGB.forward (stylegan2_ocr_arch.py:357-374): rgb[b,o,y,x] = sum_c w[o][c]*s[b][c]*x[b,y,x,c] + bias[o]
+ *   (+ upfirdn2d(skip, FIR*4, up=2, pad=(2,1)) when skip != NULL, skip is fp32 NCHW [B][3][h/2][w/2]).
+ * w: fp32 [3][C] pre-scaled by 1/sqrt(C); s: fp32 [B][C] or NULL (plain EqualConv2d toRGB, gfpganv1_ocr_arch.py:290-292).
+ * rgb: fp32 NCHW [B][3][h][w].  If xs_out: xs_out = x * s_next[b][c] (NHWC fp16; input of the next modulated conv). */
+int b200ir_to_rgb(const void* x, int B, int h, int w, int C, const float* wrgb, const float* s, const float* bias,
+                  const float* skip, float* rgb, const float* s_next, void* xs_out, void* stream);
+
+/* ConstantInput.forward (stylegan2_ocr_arch.py:389-391) fused with the first modulation:
+ * out[b,p,c] = cst[p*C + c] * s[b*C + c];  cst NHWC fp16 [P][C]. */
+int b200ir_modulate_const(const void* cst, const float* s, void* out, int B, int P, int C, void* stream);
+
+/* EqualLinear modulation (stylegan2_ocr_arch.py:247, 165-175): s[b][i] = sum_f w[i][f]*latent[b][lat_idx][f]*wscale + bias[i].
+ * latent fp32 [B][L][F]. */
+int b200ir_mod_linear(const float* latent, int L, int F, int lat_idx, const float* w, const float* bias, float wscale,
+                      float* s, int B, int cin, void* stream);
+
+/* Demodulation coefficients (stylegan2_ocr_arch.py:253-257): d[b][o] = rsqrt(scale2 * sum_i s[b][i]^2 * wsq[o][i] + 1e-8),
+ * wsq[o][i] = sum_k W[o][i][k]^2 (fp32). */
+int b200ir_demod(const float* s, const float* wsq, float scale2, float* d, int B, int cin, int cout, void* stream);
+
+/* NHWC fp16 [B][P][C] -> fp32 matrix [B][P*C] is a reinterpretation; this converts fp32 NCHW image batches to the
+ * caller-facing layout when needed: out_nchw[b][c][p] = in_nhwc[b][p][c] (fp16 -> fp32). */
+int b200ir_nhwc_to_nchw_f32(const void* in, float* out, int B, int P, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused degradation (pyblur blur -> cv2.resize down -> Gaussian noise -> clip -> cv2.resize up -> round/clip ->
+ * normalize), one launch per batch of crops.  Replaces random_pyblur (degradations.py:363-366; pyblur/*.py
+ * convolve2d(mode='same', fillvalue=255).astype(uint8)), the two cv2.resize(INTER_LINEAR) calls and
+ * random_add_gaussian_noise + round/clip/normalize of FFHQDegradationDataset.__getitem__
+ * (ffhq_degradation_dataset.py:244-272,307-311; degradations.py:660-669).
+ *
+ * gt:     uint8 [B][H][W][3] (the uint8 image random_pyblur builds: np.array(img*255, dtype=uint8))
+ * taps:   fp32 [B][kmax][kmax] blur kernels, zero padded, centred; ksize[b] odd (0 = no blur)
+ * lr_w/lr_h: int32 [B] low-resolution size per crop; noise: fp32 [B][lr_hmax][lr_wmax][3] (already sigma/255-scaled)
+ * out:    fp32 NCHW [B][3][H][W], (x-0.5)/0.5-normalised, channel order reversed if bgr2rgb.
+ * blur_out (optional): uint8 [B][H][W][3] blurred image (pyblur output) for parity checks.
+ */
+int b200ir_degrade(const uint8_t* gt, const float* taps, const int32_t* ksize, int kmax, const int32_t* lr_w,
+                   const int32_t* lr_h, const float* noise, int lr_wmax, int lr_hmax, float* out, uint8_t* blur_out,
+                   int B, int H, int W, int bgr2rgb, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200IR_H_ */

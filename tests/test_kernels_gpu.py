@@ -1,0 +1,293 @@
+"""GPU parity tests of the individual kernels (through the C ABI) against plain torch fp32 restatements of the
+reference operators, computed from the same fp16-rounded inputs.  Tolerances: outputs are stored in fp16
+(rel 2^-11) after fp32 accumulation, so |err| <= 4e-3 * scale is expected; asserted at 1e-2 * scale."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+
+
+def setup_module(module):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _ops():
+    from image_restoration_b200 import ops
+    return ops
+
+
+def nhwc16(t):  # NCHW fp32 -> NHWC fp16 contiguous
+    return t.permute(0, 2, 3, 1).contiguous().half()
+
+
+def nchw32(t):  # NHWC fp16 -> NCHW fp32
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def pack3x3(w):  # (cout,cin,kh,kw) -> [cout][(kh*kw)*cin]
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().half()
+
+
+def check_close(got, ref, tol=1e-2, what=''):
+    scale = ref.abs().max().item() + 1e-6
+    err = (got - ref).abs().max().item()
+    print(f'{what}: max|err|={err:.3e} scale={scale:.3e} rel={err / scale:.3e}')
+    assert math.isfinite(err) and err <= tol * scale, f'{what}: err {err} vs scale {scale}'
+
+
+def fir_k(dev):
+    k = torch.tensor([1., 3., 3., 1.], device=dev)
+    k = k[None] * k[:, None]
+    return k / k.sum()
+
+
+def upfirdn_ref(x, k, up=1, down=1, pad=(0, 0)):
+    b, c, h, w = x.shape
+    if up > 1:
+        z = x.new_zeros(b, c, h, up, w, up)
+        z[:, :, :, 0, :, 0] = x
+        x = z.view(b, c, h * up, w * up)
+    x = F.pad(x, [pad[0], pad[1], pad[0], pad[1]])
+    y = F.conv2d(x.reshape(b * c, 1, *x.shape[2:]), torch.flip(k, [0, 1])[None, None])
+    return y.view(b, c, *y.shape[2:])[:, :, ::down, ::down]
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout,k', [
+    (2, 32, 96, 256, 256, 3),
+    (1, 128, 384, 32, 32, 3),
+    (3, 16, 48, 512, 512, 3),
+    (2, 64, 192, 64, 64, 3),
+    (5, 4, 12, 256, 256, 3),
+    (3, 8, 24, 512, 512, 3),
+    (2, 32, 96, 256, 64, 1),
+    (2, 64, 192, 128, 128, 3),
+    (1, 32, 32, 16, 16, 3),
+])
+def test_conv_same_bias_act(B, H, W, cin, cout, k):
+    ops = _ops()
+    torch.manual_seed(0)
+    x = torch.randn(B, cin, H, W, device=DEV)
+    w = torch.randn(cout, cin, k, k, device=DEV) / math.sqrt(cin * k * k)
+    bias = torch.randn(cout, device=DEV) * 0.1
+    xh, wh = nhwc16(x), pack3x3(w)
+    out = torch.empty(B, H, W, cout, device=DEV, dtype=torch.float16)
+    op = ops.conv_same(xh, wh, out, k, bias=bias, act=True)
+    op()
+    torch.cuda.synchronize()
+    wr = wh.float().view(cout, k, k, cin).permute(0, 3, 1, 2)
+    ref = F.leaky_relu(F.conv2d(nchw32(xh), wr, bias, padding=k // 2), 0.2) * math.sqrt(2)
+    check_close(nchw32(out), ref, what=f'conv{k}x{k} {cin}->{cout} @{H}x{W} B{B}')
+
+
+def test_conv_residual_and_channel_offset():
+    ops = _ops()
+    torch.manual_seed(1)
+    B, H, W, cin, cout = 2, 16, 48, 256, 256
+    x = torch.randn(B, cin, H, W, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    res = torch.randn(B, cout, H, W, device=DEV)
+    xh, wh, rh = nhwc16(x), pack3x3(w), nhwc16(res)
+    out = torch.zeros(B, H, W, 2 * cout, device=DEV, dtype=torch.float16)
+    ops.conv_same(xh, wh, out, 3, out_c_off=cout, res=rh, res_mode=1,
+                  res_strides=(cout, W * cout, H * W * cout), res_wh=(W, H), res_scale=1 / math.sqrt(2))()
+    torch.cuda.synchronize()
+    wr = wh.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    ref = (F.conv2d(nchw32(xh), wr, padding=1) + nchw32(rh)) / math.sqrt(2)
+    got = nchw32(out)
+    check_close(got[:, cout:], ref, what='conv+res into channel slice')
+    assert got[:, :cout].abs().max().item() == 0
+
+
+def test_conv_bilinear_residual():
+    ops = _ops()
+    torch.manual_seed(2)
+    B, H, W, cin, cout = 2, 16, 48, 256, 64
+    x = torch.randn(B, cin, H, W, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    lo = torch.randn(B, cout, H // 2, W // 2, device=DEV)
+    xh, wh, lh = nhwc16(x), pack3x3(w), nhwc16(lo)
+    out = torch.empty(B, H, W, cout, device=DEV, dtype=torch.float16)
+    ops.conv_same(xh, wh, out, 3, res=lh, res_mode=2, res_strides=(cout, (W // 2) * cout, (H // 2) * (W // 2) * cout),
+                  res_wh=(W // 2, H // 2), res_scale=1 / math.sqrt(2))()
+    torch.cuda.synchronize()
+    wr = wh.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    up = F.interpolate(nchw32(lh), scale_factor=2, mode='bilinear', align_corners=False)
+    ref = (F.conv2d(nchw32(xh), wr, padding=1) + up) / math.sqrt(2)
+    check_close(nchw32(out), ref, what='conv+bilinear residual')
+
+
+def test_modulated_epilogue_demod_noise():
+    ops = _ops()
+    torch.manual_seed(3)
+    B, H, W, cin, cout = 3, 8, 24, 512, 512
+    x = torch.randn(B, cin, H, W, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    demod = torch.rand(B, cout, device=DEV) + 0.5
+    noise = torch.randn(1, 1, H, W, device=DEV)
+    gain = torch.tensor([0.3], device=DEV)
+    bias = torch.randn(cout, device=DEV) * 0.1
+    xh, wh = nhwc16(x), pack3x3(w)
+    out = torch.empty(B, H, W, cout, device=DEV, dtype=torch.float16)
+    ops.conv_same(xh, wh, out, 3, bias=bias, demod=demod, noise=noise, noise_gain=gain, noise_strides=(0, W), act=True)()
+    torch.cuda.synchronize()
+    wr = wh.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    y = F.conv2d(nchw32(xh), wr, padding=1) * demod[:, :, None, None] + gain * noise + bias[None, :, None, None]
+    ref = F.leaky_relu(y, 0.2) * math.sqrt(2)
+    check_close(nchw32(out), ref, what='modconv epilogue')
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout', [(2, 32, 96, 64, 256), (1, 128, 384, 32, 64), (3, 8, 24, 256, 256)])
+def test_fir_then_stride2_conv(B, H, W, cin, cout):
+    ops = _ops()
+    torch.manual_seed(4)
+    x = torch.randn(B, cin, H, W, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    bias = torch.randn(cout, device=DEV) * 0.1
+    xh, wh = nhwc16(x), pack3x3(w)
+    p = torch.zeros(B, H + 2, W + 2, cin, device=DEV, dtype=torch.float16)
+    ops.fir_pad22(xh, p)
+    torch.cuda.synchronize()
+    pref = upfirdn_ref(nchw32(xh), fir_k(DEV), pad=(2, 2))
+    check_close(nchw32(p)[:, :, :H + 1, :W + 1], pref, what='fir_pad22')
+    out = torch.empty(B, H // 2, W // 2, cout, device=DEV, dtype=torch.float16)
+    ops.conv3x3_s2(p, H, W, wh, out, bias=bias, act=True)()
+    torch.cuda.synchronize()
+    wr = wh.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    ref = F.leaky_relu(F.conv2d(nchw32(p)[:, :, :H + 1, :W + 1], wr, bias, stride=2), 0.2) * math.sqrt(2)
+    check_close(nchw32(out), ref, what=f'conv3x3 s2 {cin}->{cout} @{H}x{W}')
+
+
+def test_fir_down2_and_bilinear_and_add():
+    ops = _ops()
+    torch.manual_seed(5)
+    B, H, W, C = 2, 32, 96, 64
+    xh = nhwc16(torch.randn(B, C, H, W, device=DEV))
+    out = torch.empty(B, H // 2, W // 2, C, device=DEV, dtype=torch.float16)
+    ops.fir_down2(xh, out)
+    ref = upfirdn_ref(nchw32(xh), fir_k(DEV), pad=(1, 1))[:, :, ::2, ::2]
+    check_close(nchw32(out), ref, what='fir_down2')
+    up = torch.empty(B, 2 * H, 2 * W, C, device=DEV, dtype=torch.float16)
+    ops.bilinear_up2(xh, up)
+    check_close(nchw32(up), F.interpolate(nchw32(xh), scale_factor=2, mode='bilinear', align_corners=False),
+                what='bilinear_up2')
+    s = torch.empty_like(xh)
+    ops.add(xh, xh, s)
+    check_close(s.float(), 2 * xh.float(), what='add')
+
+
+@pytest.mark.parametrize('B,h,w,cin,cout,sft', [(2, 4, 12, 512, 512, True), (2, 32, 96, 512, 128, True),
+                                                 (1, 64, 192, 128, 64, False)])
+def test_transposed_conv_phases_and_tail(B, h, w, cin, cout, sft):
+    ops = _ops()
+    torch.manual_seed(6)
+    x = torch.randn(B, cin, h, w, device=DEV)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    demod = torch.rand(B, cout, device=DEV) + 0.5
+    xh = nhwc16(x)
+    wh = wt.half()
+    raw = torch.zeros(B, 2 * h + 2, 2 * w + 2, cout, device=DEV, dtype=torch.float16)
+    for (py, px) in ops.CONVT_PHASES:
+        taps = ops.convt_phase_taps(py, px)
+        wp = torch.cat([wh[:, :, kh, kw] for kh, kw in taps], dim=1).contiguous()
+        ops.convt_s2_phase(xh, wp, py, px, raw, demod=demod)()
+    torch.cuda.synchronize()
+    ref_raw = F.conv_transpose2d(nchw32(xh), wh.float().transpose(0, 1), stride=2) * demod[:, :, None, None]
+    check_close(nchw32(raw)[:, :, :2 * h + 1, :2 * w + 1], ref_raw, what='convT phases')
+    # tail
+    h2, w2 = 2 * h, 2 * w
+    noise = torch.randn(B, 1, h2, w2, device=DEV)
+    gain = torch.tensor([0.2], device=DEV)
+    bias = torch.randn(cout, device=DEV) * 0.1
+    c_sft = cout // 2 if sft else cout
+    scale = nhwc16(torch.randn(B, c_sft, h2, w2, device=DEV))
+    shift = nhwc16(torch.randn(B, c_sft, h2, w2, device=DEV))
+    s_next = torch.rand(B, cout, device=DEV) + 0.5
+    out = torch.empty(B, h2, w2, cout, device=DEV, dtype=torch.float16)
+    ops.upfir_act(raw, out, noise, h2 * w2, gain, bias, scale, shift, c_sft, s_next)
+    torch.cuda.synchronize()
+    y = upfirdn_ref(nchw32(raw)[:, :, :2 * h + 1, :2 * w + 1], fir_k(DEV) * 4, pad=(1, 1))
+    y = F.leaky_relu(y + gain * noise + bias[None, :, None, None], 0.2) * math.sqrt(2)
+    keep = cout - c_sft
+    y = torch.cat([y[:, :keep], y[:, keep:] * nchw32(scale) + nchw32(shift)], 1) * s_next[:, :, None, None]
+    check_close(nchw32(out), y, what='upfir_act')
+
+
+def test_linear_as_conv():
+    ops = _ops()
+    torch.manual_seed(7)
+    B, K, N = 5, 12288, 3072
+    x = (torch.randn(B, K, device=DEV)).half()
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).half()
+    bias = torch.randn(N, device=DEV)
+    out = torch.empty(B, N, device=DEV, dtype=torch.float32)
+    ops.linear_as_conv(x, w, out, bias=bias, block_n=64)()
+    torch.cuda.synchronize()
+    check_close(out, x.float() @ w.float().t() + bias, tol=2e-3, what='linear 12288->3072')
+
+
+def test_style_path_and_to_rgb():
+    ops = _ops()
+    torch.manual_seed(8)
+    B, L, Fd, cin, cout = 3, 12, 256, 512, 128
+    latent = torch.randn(B, L, Fd, device=DEV)
+    wm = torch.randn(cin, Fd, device=DEV)
+    bm = torch.ones(cin, device=DEV)
+    s = torch.empty(B, cin, device=DEV)
+    ops.mod_linear(latent, 5, wm, bm, 1 / math.sqrt(Fd), s)
+    sref = latent[:, 5] @ wm.t() / math.sqrt(Fd) + bm
+    check_close(s, sref, tol=1e-5, what='mod_linear')
+    wconv = torch.randn(cout, cin, 3, 3, device=DEV)
+    wsq = wconv.pow(2).sum([2, 3]).contiguous()
+    d = torch.empty(B, cout, device=DEV)
+    scale2 = 1.0 / (cin * 9)
+    ops.demod(s, wsq, scale2, d)
+    wmod = (1 / math.sqrt(cin * 9)) * wconv[None] * sref[:, None, :, None, None]
+    dref = torch.rsqrt(wmod.pow(2).sum([2, 3, 4]) + 1e-8)
+    check_close(d, dref, tol=1e-4, what='demod')
+    cst = nhwc16(torch.randn(1, cin, 4, 12, device=DEV))
+    xs = torch.empty(B, 4, 12, cin, device=DEV, dtype=torch.float16)
+    ops.modulate_const(cst, s, xs)
+    check_close(nchw32(xs), nchw32(cst) * sref[:, :, None, None], what='modulate_const')
+    # to_rgb with skip upsample and xs by-product
+    h, w, C = 16, 48, 128
+    x = nhwc16(torch.randn(B, C, h, w, device=DEV))
+    wrgb = torch.randn(3, C, device=DEV) / math.sqrt(C)
+    srgb = torch.rand(B, C, device=DEV) + 0.5
+    snext = torch.rand(B, C, device=DEV) + 0.5
+    brgb = torch.randn(3, device=DEV)
+    skip = torch.randn(B, 3, h // 2, w // 2, device=DEV)
+    rgb = torch.empty(B, 3, h, w, device=DEV)
+    xs2 = torch.empty_like(x)
+    ops.to_rgb(x, wrgb, srgb, brgb, skip, rgb, snext, xs2)
+    torch.cuda.synchronize()
+    ref = torch.einsum('bchw,oc,bc->bohw', nchw32(x), wrgb, srgb) + brgb[None, :, None, None]
+    ref = ref + upfirdn_ref(skip, fir_k(DEV) * 4, up=2, pad=(2, 1))
+    check_close(rgb, ref, tol=1e-4, what='to_rgb')
+    check_close(nchw32(xs2), nchw32(x) * snext[:, :, None, None], what='to_rgb xs by-product')
+    for Cc in (64, 512):
+        x = nhwc16(torch.randn(B, Cc, 8, 24, device=DEV))
+        wr = torch.randn(3, Cc, device=DEV) / math.sqrt(Cc)
+        rgb = torch.empty(B, 3, 8, 24, device=DEV)
+        ops.to_rgb(x, wr, None, brgb, None, rgb)
+        check_close(rgb, torch.einsum('bchw,oc->bohw', nchw32(x), wr) + brgb[None, :, None, None], tol=1e-4,
+                    what=f'plain toRGB C={Cc}')
+
+
+def test_first_conv():
+    ops = _ops()
+    torch.manual_seed(9)
+    B, H, W, cout = 2, 128, 384, 32
+    x = torch.rand(B, 3, H, W, device=DEV) * 2 - 1
+    w = torch.randn(cout, 3, device=DEV) / math.sqrt(3)
+    bias = torch.randn(cout, device=DEV) * 0.1
+    out = torch.empty(B, H, W, cout, device=DEV, dtype=torch.float16)
+    ops.first_conv(x, w, bias, out)
+    ref = F.leaky_relu(F.conv2d(x, w[:, :, None, None], bias), 0.2) * math.sqrt(2)
+    check_close(nchw32(out), ref, what='first_conv')
