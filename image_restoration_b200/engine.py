@@ -1,0 +1,360 @@
+"""Execution engine of the B200 GFPGANv1OCR: weight pre-packing + per-batch-size launch plans over libb200ir.so.
+
+Data layout in HBM: every activation is NHWC fp16 ([B][H][W][C], C contiguous) so that a 3x3 tap of a 128-position
+tile is one TMA box; weights are packed once as fp16 [Cout][taps*Cin] (K contiguous) with the equalised-lr scale
+folded in; style vectors, demodulation tables, biases, noise and the RGB skip chain stay fp32.
+
+Follows the data flow of GFPGANv1OCR.forward (gfpganv1_ocr_arch.py:341-393) and
+StyleGAN2OCRGeneratorSFT.forward (:50-136); identities used (verified in tests):
+  * modulated conv == shared-weight conv of (x * s[b,:]) scaled by demod[b,o] in the epilogue;
+  * conv_transpose2d(stride 2) == 4 output-phase GEMMs with 4/2/2/1 taps;
+  * bilinear x2 commutes with the 1x1 skip conv of ResUpBlock; FIR-then-sample commutes with the 1x1 skip of ResBlock.
+"""
+import math
+
+import torch
+
+from . import ops
+
+F16 = torch.float16
+F32 = torch.float32
+
+
+def _pack_conv(w, scale):
+    """(cout, cin, kh, kw) fp32 -> fp16 [cout][(kh*kw)*cin], scale folded."""
+    co, ci, kh, kw = w.shape
+    return (w.float() * scale).permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous().to(F16)
+
+
+class _Packed:
+    """Weights of one module instance, packed for the kernels (built once per parameter version)."""
+
+    def __init__(self, net):
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        dev = next(net.parameters()).device
+        self.dev = dev
+        L = net.log_size - 2
+        self.L = L
+        g = lambda k: sd[k].to(dev)  # noqa: E731
+
+        def eq(wkey):
+            w = g(wkey)
+            return _pack_conv(w, 1.0 / math.sqrt(w.shape[1] * w.shape[2] * w.shape[3]))
+
+        def f32(key):
+            return g(key).float().contiguous()
+
+        # encoder
+        w0 = g('conv_body_first.0.weight').float()
+        self.first_w = (w0[:, :, 0, 0] / math.sqrt(3.0)).contiguous()
+        self.first_b = f32('conv_body_first.1.bias')
+        self.down = []
+        for i in range(L):
+            p = f'conv_body_down.{i}'
+            self.down.append(dict(w1=eq(f'{p}.conv1.0.weight'), b1=f32(f'{p}.conv1.1.bias'),
+                                  w2=eq(f'{p}.conv2.1.weight'), b2=f32(f'{p}.conv2.2.bias'),
+                                  ws=eq(f'{p}.skip.1.weight')))
+        self.final_w = eq('final_conv.0.weight')
+        self.final_b = f32('final_conv.1.bias')
+        # final_linear: reference flattens NCHW (c*P + p); our activations are NHWC (p*C + c)
+        wl = g('final_linear.weight').float()
+        n_out, k_in = wl.shape
+        c4 = self.final_w.shape[0]
+        P = k_in // c4
+        wl = wl.view(n_out, c4, P).permute(0, 2, 1).reshape(n_out, k_in) * (1.0 / math.sqrt(k_in))
+        self.lin_w = wl.contiguous().to(F16)
+        self.lin_b = f32('final_linear.bias')
+        # decoder (U-Net up path) + SFT heads + plain toRGB
+        self.up = []
+        for i in range(L):
+            p = f'conv_body_up.{i}'
+            cs, ch = f'condition_scale.{i}', f'condition_shift.{i}'
+            wrgb = g(f'toRGB.{i}.weight').float()
+            self.up.append(dict(
+                w1=eq(f'{p}.conv1.0.weight'), b1=f32(f'{p}.conv1.1.bias'),
+                w2=eq(f'{p}.conv2.weight'), b2=f32(f'{p}.conv2.activation.bias'), ws=eq(f'{p}.skip.weight'),
+                wh0=torch.cat([eq(f'{cs}.0.weight'), eq(f'{ch}.0.weight')], 0).contiguous(),
+                bh0=torch.cat([f32(f'{cs}.0.bias'), f32(f'{ch}.0.bias')]).contiguous(),
+                wsc=eq(f'{cs}.2.weight'), bsc=f32(f'{cs}.2.bias'), wsh=eq(f'{ch}.2.weight'), bsh=f32(f'{ch}.2.bias'),
+                wrgb=(wrgb[:, :, 0, 0] / math.sqrt(wrgb.shape[1])).contiguous(), brgb=f32(f'toRGB.{i}.bias')))
+        # StyleGAN decoder
+        D = 'stylegan_decoder'
+        cst = g(f'{D}.constant_input.weight').float()[0]                       # (C, 4, 4r)
+        self.const = cst.permute(1, 2, 0).contiguous().to(F16)                 # [4][4r][C]
+
+        def style_conv(p, upsample):
+            w = g(f'{p}.modulated_conv.weight').float()[0]                     # (cout, cin, 3, 3)
+            cout, cin = w.shape[:2]
+            scale = 1.0 / math.sqrt(cin * 9)
+            d = dict(cin=cin, cout=cout, scale2=scale * scale, wsq=w.pow(2).sum([2, 3]).contiguous(),
+                     mod_w=f32(f'{p}.modulated_conv.modulation.weight'), mod_b=f32(f'{p}.modulated_conv.modulation.bias'),
+                     gain=f32(f'{p}.weight'), bias=f32(f'{p}.activate.bias'))
+            if upsample:
+                ws = (w * scale).to(F16)
+                d['w_phase'] = [torch.cat([ws[:, :, kh, kw] for kh, kw in ops.convt_phase_taps(py, px)], 1).contiguous()
+                                for py, px in ops.CONVT_PHASES]
+            else:
+                d['w'] = _pack_conv(w, scale)
+            return d
+
+        def rgb(p):
+            w = g(f'{p}.modulated_conv.weight').float()[0, :, :, 0, 0]         # (3, cin)
+            return dict(w=(w / math.sqrt(w.shape[1])).contiguous(), bias=f32(f'{p}.bias').reshape(3).contiguous(),
+                        mod_w=f32(f'{p}.modulated_conv.modulation.weight'),
+                        mod_b=f32(f'{p}.modulated_conv.modulation.bias'))
+
+        self.sc1 = style_conv(f'{D}.style_conv1', False)
+        self.rgb1 = rgb(f'{D}.to_rgb1')
+        self.sconv = [style_conv(f'{D}.style_convs.{j}', j % 2 == 0) for j in range(2 * L)]
+        self.rgbs = [rgb(f'{D}.to_rgbs.{i}') for i in range(L)]
+        self.stored_noise = [f32(f'{D}.noises.noise{j}') for j in range(2 * L + 1)]
+        self.mod_wscale = 1.0 / math.sqrt(net.num_style_feat)
+
+
+class _Plan:
+    """All buffers and prepared launches for one batch size."""
+
+    def __init__(self, eng, B):
+        net, pk = eng.net, eng.packed
+        dev = pk.dev
+        self.B = B
+        L = pk.L
+        H, W = net.input_height, net.input_width
+        nf = net.num_style_feat
+        steps = []          # list of zero-arg callables, in launch order
+        self.steps = steps
+        e16 = lambda *s: torch.empty(*s, device=dev, dtype=F16)  # noqa: E731
+        z16 = lambda *s: torch.zeros(*s, device=dev, dtype=F16)  # noqa: E731
+        e32 = lambda *s: torch.empty(*s, device=dev, dtype=F32)  # noqa: E731
+        inv = ops.INV_SQRT2
+
+        self.x_in = e32(B, 3, H, W)
+        c0 = pk.first_w.shape[0]
+        feat = e16(B, H, W, c0)
+        steps.append(lambda o=feat: ops.first_conv(self.x_in, pk.first_w, pk.first_b, o))
+        # ---------------- encoder: ResBlock x L (stylegan2_ocr_arch.py:729-734)
+        skips = []
+        h, w = H, W
+        for i in range(L):
+            d = pk.down[i]
+            cin, cout = d['w1'].shape[0], d['w2'].shape[0]
+            t1 = e16(B, h, w, cin)
+            steps.append(ops.conv_same(feat, d['w1'], t1, 3, bias=d['b1'], act=True))
+            p = z16(B, h + 2, w + 2, cin)
+            steps.append(lambda a=t1, o=p: ops.fir_pad22(a, o))
+            sk_in = e16(B, h // 2, w // 2, cin)
+            steps.append(lambda a=feat, o=sk_in: ops.fir_down2(a, o))
+            sk = e16(B, h // 2, w // 2, cout)
+            steps.append(ops.conv_same(sk_in, d['ws'], sk, 1))
+            nxt = e16(B, h // 2, w // 2, cout)
+            oh, ow = h // 2, w // 2
+            steps.append(ops.conv3x3_s2(p, h, w, d['w2'], nxt, bias=d['b2'], act=True, res=sk, res_mode=1,
+                                        res_strides=(cout, ow * cout, oh * ow * cout), res_wh=(ow, oh), res_scale=inv))
+            feat = nxt
+            skips.insert(0, feat)
+            h, w = oh, ow
+        # ---------------- final conv + style code (gfpganv1_ocr_arch.py:358-363)
+        c4 = pk.final_w.shape[0]
+        g = e16(B, h, w, c4)
+        steps.append(ops.conv_same(feat, pk.final_w, g, 3, bias=pk.final_b, act=True))
+        n_lin = pk.lin_w.shape[0]
+        self.style_code = e32(B, n_lin)
+        steps.append(ops.linear_as_conv(g.view(B, -1), pk.lin_w, self.style_code, bias=pk.lin_b,
+                                        block_n=64 if n_lin % 64 == 0 else None))
+        if net.different_w:
+            self.num_latent = n_lin // nf
+            self.latent = self.style_code.view(B, self.num_latent, nf)
+        else:
+            self.num_latent = 1
+            self.latent = self.style_code.view(B, 1, nf)
+
+        def lat(i):
+            return i if net.different_w else 0
+
+        # ---------------- U-Net decoder with SFT heads (gfpganv1_ocr_arch.py:366-378)
+        self.cond = []      # (scale, shift) per level, NHWC fp16
+        self.out_rgbs = []
+        self.rgb_steps = []
+        feat = g
+        for i in range(L):
+            d = pk.up[i]
+            cin, cout = d['w1'].shape[0], d['w2'].shape[0]
+            a = e16(B, h, w, cin)
+            steps.append(lambda x=feat, y=skips[i], o=a: ops.add(x, y, o))
+            t1 = e16(B, h, w, cin)
+            steps.append(ops.conv_same(a, d['w1'], t1, 3, bias=d['b1'], act=True))
+            u = e16(B, 2 * h, 2 * w, cin)
+            steps.append(lambda x=t1, o=u: ops.bilinear_up2(x, o))
+            sl = e16(B, h, w, cout)
+            steps.append(ops.conv_same(a, d['ws'], sl, 1))
+            h2, w2 = 2 * h, 2 * w
+            feat = e16(B, h2, w2, cout)
+            steps.append(ops.conv_same(u, d['w2'], feat, 3, bias=d['b2'], act=True, res=sl, res_mode=2,
+                                       res_strides=(cout, w * cout, h * w * cout), res_wh=(w, h), res_scale=inv))
+            hid = e16(B, h2, w2, 2 * cout)
+            steps.append(ops.conv_same(feat, d['wh0'], hid, 3, bias=d['bh0'], act=True))
+            c_sft = d['wsc'].shape[0]
+            sc, sh = e16(B, h2, w2, c_sft), e16(B, h2, w2, c_sft)
+            for half, wk, bk, dst in ((0, 'wsc', 'bsc', sc), (1, 'wsh', 'bsh', sh)):
+                v = ops.View(hid.data_ptr() + 2 * half * cout, cout, w2, h2, B, 2 * cout, w2 * 2 * cout,
+                             h2 * w2 * 2 * cout)
+                steps.append(ops.ConvOp([v], d[wk], cout, c_sft, ops.taps_3x3(), (w2, h2, B), dst,
+                                        (c_sft, w2 * c_sft, h2 * w2 * c_sft), bias=d[bk]))
+            self.cond.append((sc, sh))
+            rgb = e32(B, 3, h2, w2)
+            self.out_rgbs.append(rgb)
+            self.rgb_steps.append(lambda x=feat, dd=d, o=rgb: ops.to_rgb(x, dd['wrgb'], None, dd['brgb'], None, o))
+            steps.append(('rgb', len(self.rgb_steps) - 1))
+            h, w = h2, w2
+        self._hid_keep = None
+
+        # ---------------- style modulation vectors and demodulation tables (hoisted: depend on the latent only)
+        def mod(layer, lat_idx):
+            s = e32(B, layer['mod_w'].shape[0])
+            steps.append(lambda l=layer, i=lat(lat_idx), o=s: ops.mod_linear(self.latent, i, l['mod_w'], l['mod_b'],
+                                                                              pk.mod_wscale, o))
+            return s
+
+        def dem(layer, s):
+            dd = e32(B, layer['cout'])
+            steps.append(lambda l=layer, ss=s, o=dd: ops.demod(ss, l['wsq'], l['scale2'], o))
+            return dd
+
+        s_sc1 = mod(pk.sc1, 0)
+        d_sc1 = dem(pk.sc1, s_sc1)
+        s_rgb1 = mod(pk.rgb1, 1)
+        s_conv, d_conv, s_rgb = [], [], []
+        for lvl in range(L):
+            i = 1 + 2 * lvl
+            s1 = mod(pk.sconv[2 * lvl], i)
+            s2 = mod(pk.sconv[2 * lvl + 1], i + 1)
+            s_conv += [s1, s2]
+            d_conv += [dem(pk.sconv[2 * lvl], s1), dem(pk.sconv[2 * lvl + 1], s2)]
+            s_rgb.append(mod(pk.rgbs[lvl], i + 2))
+
+        # ---------------- StyleGAN2 decoder with SFT (gfpganv1_ocr_arch.py:108-129)
+        self.noise = [None] * (2 * L + 1)   # fp32 [nb,1,h,w] buffers the kernels read; filled per call
+        self.noise_shapes = []
+        ratio = int(W / H)
+        h, w = 4, 4 * ratio
+        cch = pk.sc1['cin']
+        self.noise_shapes.append((h, w))
+        self.noise[0] = e32(B, 1, h, w)
+        xs = e16(B, h, w, cch)
+        steps.append(lambda o=xs: ops.modulate_const(pk.const, s_sc1, o))
+        out = e16(B, h, w, pk.sc1['cout'])
+        steps.append(ops.conv_same(xs, pk.sc1['w'], out, 3, bias=pk.sc1['bias'], demod=d_sc1, noise=self.noise[0],
+                                   noise_gain=pk.sc1['gain'], noise_strides=(h * w, w), act=True))
+        skip = e32(B, 3, h, w)
+        xs = e16(B, h, w, pk.sc1['cout'])
+        steps.append(lambda x=out, o=skip, xo=xs: ops.to_rgb(x, pk.rgb1['w'], s_rgb1, pk.rgb1['bias'], None, o,
+                                                             s_conv[0] if L > 0 else None, xo if L > 0 else None))
+        for lvl in range(L):
+            c1, c2 = pk.sconv[2 * lvl], pk.sconv[2 * lvl + 1]
+            cout = c1['cout']
+            h2, w2 = 2 * h, 2 * w
+            raw = z16(B, h2 + 2, w2 + 2, cout)
+            for pi, (py, px) in enumerate(ops.CONVT_PHASES):
+                steps.append(ops.convt_s2_phase(xs, c1['w_phase'][pi], py, px, raw, demod=d_conv[2 * lvl]))
+            n1 = e32(B, 1, h2, w2)
+            n2 = e32(B, 1, h2, w2)
+            self.noise[2 * lvl + 1], self.noise[2 * lvl + 2] = n1, n2
+            self.noise_shapes += [(h2, w2), (h2, w2)]
+            sc, sh = self.cond[lvl]
+            xs2 = e16(B, h2, w2, cout)
+            steps.append(lambda r=raw, o=xs2, n=n1, c=c1, a=sc, b_=sh, sn=s_conv[2 * lvl + 1]:
+                         ops.upfir_act(r, o, n, o.shape[1] * o.shape[2], c['gain'], c['bias'], a, b_, a.shape[3], sn))
+            out = e16(B, h2, w2, cout)
+            steps.append(ops.conv_same(xs2, c2['w'], out, 3, bias=c2['bias'], demod=d_conv[2 * lvl + 1], noise=n2,
+                                       noise_gain=c2['gain'], noise_strides=(h2 * w2, w2), act=True))
+            nskip = e32(B, 3, h2, w2)
+            last = lvl == L - 1
+            xs = None if last else e16(B, h2, w2, cout)
+            steps.append(lambda x=out, r=pk.rgbs[lvl], s=s_rgb[lvl], sk=skip, o=nskip, xo=xs,
+                         sn=(None if last else s_conv[2 * lvl + 2]): ops.to_rgb(x, r['w'], s, r['bias'], sk, o, sn, xo))
+            skip = nskip
+            h, w = h2, w2
+        self.image = skip
+        self.graphs = {}
+
+    def launch(self, return_rgb):
+        for st in self.steps:
+            if isinstance(st, tuple):
+                if return_rgb:
+                    self.rgb_steps[st[1]]()
+            else:
+                st()
+
+
+class OcrEngine:
+    def __init__(self, net):
+        if net.input_is_latent is False:
+            raise NotImplementedError('input_is_latent=False (style MLP path) is not built yet; every shipped '
+                                      'reference config uses input_is_latent=True')
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('image_restoration_b200 needs the module on a CUDA B200 (no CPU path)')
+        from . import _lib
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().b200ir_device_check(), 'device check')
+        self.net = net
+        self._sig = self._signature()
+        with torch.cuda.device(dev), torch.no_grad():
+            self.packed = _Packed(net)
+        self.plans = {}
+        self.use_graphs = True
+
+    def _signature(self):
+        ps = list(self.net.parameters()) + list(self.net.buffers())
+        return (tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+
+    def stale(self):
+        return self._sig != self._signature()
+
+    def plan(self, B):
+        if B not in self.plans:
+            self.plans[B] = _Plan(self, B)
+        return self.plans[B]
+
+    @torch.no_grad()
+    def forward(self, x, return_rgb=True, randomize_noise=True, save_feat_path=None, load_feat_path=None,
+                noise=None):
+        net = self.net
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != (3, net.input_height, net.input_width):
+            raise ValueError(f'expected input (B,3,{net.input_height},{net.input_width}), got {tuple(x.shape)}')
+        dev = self.packed.dev
+        with torch.cuda.device(dev):
+            plan = self.plan(B)
+            plan.x_in.copy_(x)
+            pk = self.packed
+            for j, buf in enumerate(plan.noise):
+                if noise is not None:
+                    buf.copy_(noise[j].expand_as(buf))
+                elif randomize_noise:
+                    buf.normal_()
+                else:
+                    buf.copy_(pk.stored_noise[j].expand_as(buf))
+            if load_feat_path is not None or save_feat_path is not None or not self.use_graphs:
+                self._run_eager(plan, return_rgb, save_feat_path, load_feat_path)
+            else:
+                key = bool(return_rgb)
+                gr = plan.graphs.get(key)
+                if gr is None:
+                    plan.launch(return_rgb)          # warm-up (also surfaces launch errors outside capture)
+                    torch.cuda.synchronize()
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        plan.launch(return_rgb)
+                    plan.graphs[key] = gr
+                gr.replay()
+            image = plan.image.clone()
+            rgbs = [t.clone() for t in plan.out_rgbs] if return_rgb else []
+        return image.to(x.dtype) if x.dtype != F32 else image, rgbs
+
+    def _run_eager(self, plan, return_rgb, save_feat_path, load_feat_path):
+        if load_feat_path is None and save_feat_path is None:
+            plan.launch(return_rgb)
+            return
+        # conditions are produced by the first half of the step list; split at the first modulation step
+        raise NotImplementedError('save_feat_path / load_feat_path are not wired in the B200 engine yet')

@@ -1,0 +1,100 @@
+"""Whole-network parity on the GPU: B200 engine (through the C ABI) vs the CPU fp32 oracle restatement of the
+reference forward, on the same seeded random-init weights and synthetic crops.
+Contract (BASELINE.json north_star): after to01 (= tensor2img's clamp to [-1,1] -> [0,1]) max-abs <= 2e-2 and
+PSNR >= 45 dB.  Operands are fp16 with fp32 accumulation (bf16 operands do not meet this bar: SURVEY.md App. D)."""
+import pytest
+import torch
+
+from oracle.gfpgan_ocr_oracle import OcrNetConfig, gfpgan_ocr_forward, psnr01, to01
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(num_style_feat=256, channel_multiplier=0.5, num_mlp=4, input_is_latent=True, different_w=True, narrow=1,
+          sft_half=True)
+MAX_ABS, MIN_PSNR = 2e-2, 45.0
+
+
+def build(W, H, seed, perturb=True, **over):
+    from image_restoration_b200 import GFPGANv1OCR
+    kw = dict(KW, **over)
+    torch.manual_seed(seed)
+    net = GFPGANv1OCR(input_width=W, input_height=H, decoder_load_path=None, fix_decoder=True, **kw).eval()
+    if perturb:  # make biases and noise gains non-trivial so every epilogue term is exercised
+        g = torch.Generator().manual_seed(seed + 100)
+        sd = net.state_dict()
+        for k, v in sd.items():
+            if k.endswith('bias') or (k.endswith('.weight') and v.numel() == 1):
+                v.add_(torch.randn(v.shape, generator=g) * 0.2)
+        net.load_state_dict(sd)
+    cfg = OcrNetConfig(input_width=W, input_height=H, **kw)
+    return net, cfg
+
+
+def compare(net, cfg, x, return_rgb=True, what=''):
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    ref, ref_rgbs = gfpgan_ocr_forward(sd, cfg, x, return_rgb)
+    net = net.cuda()
+    got, rgbs = net(x.cuda(), return_rgb=return_rgb, randomize_noise=False)
+    got = got.float().cpu()
+    a, b = to01(got), to01(ref)
+    max_abs = (a - b).abs().max().item()
+    psnr = psnr01(a, b)
+    raw_rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    print(f'{what}: max-abs[0,1]={max_abs:.4e} psnr={psnr:.2f} dB raw rel-rms={raw_rel:.3e} '
+          f'sat={(ref.abs() > 1).float().mean().item():.2f}')
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert max_abs <= MAX_ABS and psnr >= MIN_PSNR
+    assert raw_rel < 5e-3
+    assert len(rgbs) == len(ref_rgbs)
+    for i, (r, rr) in enumerate(zip(rgbs, ref_rgbs)):
+        rel = ((r.float().cpu() - rr).abs().max() / (rr.abs().max() + 1e-6)).item()
+        print(f'   out_rgbs[{i}] {tuple(r.shape)} rel-max={rel:.3e}')
+        assert r.shape == rr.shape and rel < 2e-2
+    return got
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+def test_forward_128x384(seed):
+    net, cfg = build(384, 128, seed)
+    torch.manual_seed(seed)
+    x = torch.rand(2, 3, 128, 384) * 2 - 1
+    compare(net, cfg, x, True, f'128x384 seed {seed}')
+
+
+def test_forward_stock_init_single_crop():
+    """BASELINE config 1: stock random init (noise gains 0, biases 0/1), one 3x128x384 crop, return_rgb=False."""
+    net, cfg = build(384, 128, 0, perturb=False)
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 128, 384) * 2 - 1
+    compare(net, cfg, x, False, 'stock init B=1')
+
+
+@pytest.mark.parametrize('W,H', [(48, 16), (32, 32), (256, 64)])
+def test_forward_other_geometries(W, H):
+    net, cfg = build(W, H, 3)
+    torch.manual_seed(3)
+    x = torch.rand(3, 3, H, W) * 2 - 1
+    compare(net, cfg, x, True, f'{H}x{W}')
+
+
+def test_forward_sft_full_channels():
+    net, cfg = build(96, 32, 4, sft_half=False)
+    torch.manual_seed(4)
+    x = torch.rand(2, 3, 32, 96) * 2 - 1
+    compare(net, cfg, x, True, 'sft_half=False 32x96')
+
+
+def test_batch_consistency_and_noise_modes():
+    """Crops are independent: row b of a batch-8 forward equals the batch-1 forward of crop b (bit-exact, the kernels
+    are deterministic); randomize_noise=True changes nothing while the noise gains are zero."""
+    net, cfg = build(384, 128, 5, perturb=False)
+    net = net.cuda()
+    torch.manual_seed(5)
+    x = (torch.rand(8, 3, 128, 384) * 2 - 1).cuda()
+    y8, _ = net(x, return_rgb=False, randomize_noise=False)
+    y1, _ = net(x[3:4], return_rgb=False, randomize_noise=False)
+    assert torch.equal(y8[3:4], y1)
+    yr, _ = net(x, return_rgb=False, randomize_noise=True)
+    assert torch.equal(yr, y8)
+    y8b, _ = net(x, return_rgb=False, randomize_noise=False)
+    assert torch.equal(y8b, y8)
