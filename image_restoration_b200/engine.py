@@ -121,7 +121,7 @@ class _Plan:
         L = pk.L
         H, W = net.input_height, net.input_width
         nf = net.num_style_feat
-        steps = []          # list of zero-arg callables, in launch order
+        steps = []          # launch list: zero-arg callables (ConvOp or closure) or ('rgb', i) markers
         self.steps = steps
         e16 = lambda *s: torch.empty(*s, device=dev, dtype=F16)  # noqa: E731
         z16 = lambda *s: torch.zeros(*s, device=dev, dtype=F16)  # noqa: E731

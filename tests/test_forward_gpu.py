@@ -110,3 +110,27 @@ def test_batch_consistency_and_noise_modes():
     assert torch.equal(yr, y8)
     y8b, _ = net(x, return_rgb=False, randomize_noise=False)
     assert torch.equal(y8b, y8)
+
+
+def test_engine_matches_reference_goldens():
+    """Parity anchored in the reference itself: fixtures in tests/golden/ were produced by the unmodified reference
+    GFPGANv1OCR (tests/golden/make_golden.py); the B200 engine must reproduce them within the contract."""
+    import os
+    from tests.helpers import golden_files, load_golden
+    n = 0
+    for path in golden_files():
+        fx, net = load_golden(path)
+        if net is None:
+            continue
+        n += 1
+        x = torch.from_numpy(fx['x'])
+        ref = torch.from_numpy(fx['image'])
+        got, rgbs = net.cuda()(x.cuda(), return_rgb=True, randomize_noise=False)
+        a, b = to01(got.float().cpu()), to01(ref)
+        max_abs, psnr = (a - b).abs().max().item(), psnr01(a, b)
+        print(f'{os.path.basename(path)}: max-abs={max_abs:.4e} psnr={psnr:.2f} dB')
+        assert max_abs <= MAX_ABS and psnr >= MIN_PSNR
+        for i, r in enumerate(rgbs):
+            rr = torch.from_numpy(fx[f'rgb{i}'])
+            assert ((r.float().cpu() - rr).abs().max() / (rr.abs().max() + 1e-6)).item() < 2e-2
+    assert n > 0, 'no golden fixture could be reproduced from its seed'
