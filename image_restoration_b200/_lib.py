@@ -54,7 +54,7 @@ SIGNATURES = {
     'b200ir_mod_linear': [_P, _I, _I, _I, _P, _P, _F, _P, _I, _I, _P],
     'b200ir_demod': [_P, _P, _F, _P, _I, _I, _I, _P],
     'b200ir_nhwc_to_nchw_f32': [_P, _P, _I, _I, _I, _P],
-    'b200ir_degrade': [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_degrade': [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64}
 

@@ -1,11 +1,234 @@
-// Fused per-crop degradation kernel (pyblur blur -> resize down -> noise -> clip -> resize up -> round -> normalize).
+// Fused per-crop degradation: pyblur blur -> cv2.resize(INTER_LINEAR) down -> + Gaussian noise -> clip ->
+// cv2.resize(INTER_LINEAR) up -> clamp/round to the 8-bit grid -> normalize to [-1,1] -> NCHW fp32.
+// One CTA per crop; the blur is evaluated only at the (separable) set of source rows/cols the down-resize samples.
+//
+// Reference semantics (see include/b200ir.h for file:line):
+//   blur   : scipy.signal.convolve2d(img_f32[:,:,c], K, mode='same', boundary='fill', fillvalue=255).astype(uint8)
+//            out[y,x] = sum_{i,j} K[i,j] * img[y + ci - i, x + cj - j], fp32 accumulation in (i,j) ascending order,
+//            then truncation to uint8, then /255 in fp32 (degradations.py:363-366)
+//   resize : OpenCV INTER_LINEAR on float32: src = (dst+0.5)*scale-0.5 (double), floor, clamp, horizontal pass then
+//            vertical pass in fp32
+//   noise  : clip(img + noise, 0, 1) (degradations.py:660-669; noise already scaled by sigma/255)
+//   tail   : clamp(round(x*255), 0, 255)/255 then (x-0.5)/0.5 (ffhq_degradation_dataset.py:307-311), BGR->RGB
 #include "host_common.h"
+
+namespace b200ir {
+
+static constexpr int kDegThreads = 512;
+
+struct ResizeAxis {
+  int i0, i1;
+  float w0, w1;
+};
+
+// shared-memory layout (every region 16-byte aligned):
+//   taps | row taps (lr_hmax) | col taps (lr_wmax) | LR image (lh*lw*3 f32) | sampled blur (2lh*2lw*3 u8) | [GT u8]
+struct DegLayout {
+  size_t row, col, lr, samp, gt;
+};
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline DegLayout deg_layout(int kmax, int lr_wmax, int lr_hmax) {
+  DegLayout l;
+  l.row = align16((size_t)kmax * kmax * 4);
+  l.col = l.row + (size_t)lr_hmax * sizeof(ResizeAxis);
+  l.lr = l.col + (size_t)lr_wmax * sizeof(ResizeAxis);
+  l.samp = align16(l.lr + (size_t)lr_hmax * lr_wmax * 3 * 4);
+  l.gt = align16(l.samp + (size_t)2 * lr_hmax * 2 * lr_wmax * 3);
+  return l;
+}
+
+// OpenCV's linear-resize tap for destination index d: resize from `src_n` to `dst_n` samples.
+__device__ __forceinline__ ResizeAxis cv_linear_tap(int d, int src_n, int dst_n) {
+  const double inv_scale = (double)dst_n / (double)src_n;
+  const double scale = 1.0 / inv_scale;
+  float f = (float)((d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (s < 0) {
+    f = 0.f;
+    s = 0;
+  }
+  if (s >= src_n - 1) {
+    f = 0.f;
+    s = src_n - 1;
+  }
+  ResizeAxis a;
+  a.i0 = s;
+  a.i1 = min(s + 1, src_n - 1);
+  a.w0 = __fsub_rn(1.f, f);
+  a.w1 = f;
+  return a;
+}
+
+__device__ __forceinline__ float blur_at(const uint8_t* __restrict__ img, int H, int W, int y, int x, int c,
+                                         const float* __restrict__ taps, int kmax, int ksz) {
+  // taps: kmax x kmax, the ksz x ksz kernel centred; zero taps contribute nothing and are skipped
+  const int cm = (kmax - 1) >> 1;
+  const int r = (ksz - 1) >> 1;
+  float s = 0.f;
+  for (int i = cm - r; i <= cm + r; ++i) {
+    const int iy = y + cm - i;
+    const bool yin = (iy >= 0) && (iy < H);
+    for (int j = cm - r; j <= cm + r; ++j) {
+      const float t = taps[i * kmax + j];
+      if (t == 0.f) continue;
+      const int ix = x + cm - j;
+      const float v = (yin && ix >= 0 && ix < W) ? (float)img[(iy * W + ix) * 3 + c] : 255.f;
+      s = __fadd_rn(s, __fmul_rn(t, v));
+    }
+  }
+  return s;
+}
+
+__device__ __forceinline__ uint8_t trunc_u8(float s) {
+  s = fminf(fmaxf(s, 0.f), 255.f);
+  return (uint8_t)s;  // truncation toward zero, as ndarray.astype(uint8)
+}
+
+template <bool kStage>
+__global__ void __launch_bounds__(kDegThreads, 1)
+degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_all, const int* __restrict__ ksize,
+               int kmax, const int* __restrict__ lr_w, const int* __restrict__ lr_h, const float* __restrict__ noise,
+               int lr_wmax, int lr_hmax, float* __restrict__ out, int H, int W, int bgr2rgb) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lw = lr_w[b], lh = lr_h[b];
+  const int ksz = ksize[b];
+  const DegLayout lay = deg_layout(kmax, lr_wmax, lr_hmax);
+  float* s_taps = reinterpret_cast<float*>(smem);
+  ResizeAxis* s_row = reinterpret_cast<ResizeAxis*>(smem + lay.row);
+  ResizeAxis* s_col = reinterpret_cast<ResizeAxis*>(smem + lay.col);
+  float* s_lr = reinterpret_cast<float*>(smem + lay.lr);
+  uint8_t* s_samp = smem + lay.samp;
+  uint8_t* s_gt = smem + lay.gt;
+  const uint8_t* g_img = gt + (size_t)b * H * W * 3;
+
+  for (int i = tid; i < kmax * kmax; i += kDegThreads) s_taps[i] = taps_all[(size_t)b * kmax * kmax + i];
+  for (int i = tid; i < lh; i += kDegThreads) s_row[i] = cv_linear_tap(i, H, lh);
+  for (int i = tid; i < lw; i += kDegThreads) s_col[i] = cv_linear_tap(i, W, lw);
+  if (kStage) {
+    const int n16 = (H * W * 3) >> 4;  // H*W*3 is a multiple of 16 whenever W % 16 == 0 (checked on the host)
+    const uint4* src = reinterpret_cast<const uint4*>(g_img);
+    uint4* dst = reinterpret_cast<uint4*>(s_gt);
+    for (int i = tid; i < n16; i += kDegThreads) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const uint8_t* img = kStage ? s_gt : g_img;
+
+  // 1a. blurred uint8 samples on the separable grid {row i0/i1} x {col i0/i1}
+  const int nr = 2 * lh, nc = 2 * lw;
+  for (int it = tid; it < nr * nc * 3; it += kDegThreads) {
+    const int c = it % 3;
+    const int q = (it / 3) % nc;
+    const int r = it / (3 * nc);
+    const int y = (r & 1) ? s_row[r >> 1].i1 : s_row[r >> 1].i0;
+    const int x = (q & 1) ? s_col[q >> 1].i1 : s_col[q >> 1].i0;
+    uint8_t v;
+    if (ksz > 0) v = trunc_u8(blur_at(img, H, W, y, x, c, s_taps, kmax, ksz));
+    else v = img[(y * W + x) * 3 + c];
+    s_samp[it] = v;
+  }
+  __syncthreads();
+  // 1b. down-resize (horizontal then vertical), add noise, clip
+  for (int it = tid; it < lh * lw * 3; it += kDegThreads) {
+    const int c = it % 3;
+    const int lx = (it / 3) % lw;
+    const int ly = it / (3 * lw);
+    const ResizeAxis ry = s_row[ly], rx = s_col[lx];
+    const float p00 = __fdiv_rn((float)s_samp[((2 * ly) * nc + 2 * lx) * 3 + c], 255.f);
+    const float p01 = __fdiv_rn((float)s_samp[((2 * ly) * nc + 2 * lx + 1) * 3 + c], 255.f);
+    const float p10 = __fdiv_rn((float)s_samp[((2 * ly + 1) * nc + 2 * lx) * 3 + c], 255.f);
+    const float p11 = __fdiv_rn((float)s_samp[((2 * ly + 1) * nc + 2 * lx + 1) * 3 + c], 255.f);
+    const float h0 = __fadd_rn(__fmul_rn(p00, rx.w0), __fmul_rn(p01, rx.w1));
+    const float h1 = __fadd_rn(__fmul_rn(p10, rx.w0), __fmul_rn(p11, rx.w1));
+    float v = __fadd_rn(__fmul_rn(h0, ry.w0), __fmul_rn(h1, ry.w1));
+    if (noise != nullptr) v = __fadd_rn(v, noise[(((size_t)b * lr_hmax + ly) * lr_wmax + lx) * 3 + c]);
+    s_lr[it] = fminf(fmaxf(v, 0.f), 1.f);
+  }
+  __syncthreads();
+  // 2. up-resize to (H, W), 8-bit grid, normalize, NCHW (optionally BGR->RGB)
+  float* o = out + (size_t)b * 3 * H * W;
+  for (int it = tid; it < H * W; it += kDegThreads) {
+    const int x = it % W, y = it / W;
+    const ResizeAxis ry = cv_linear_tap(y, lh, H), rx = cv_linear_tap(x, lw, W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float p00 = s_lr[(ry.i0 * lw + rx.i0) * 3 + c], p01 = s_lr[(ry.i0 * lw + rx.i1) * 3 + c];
+      const float p10 = s_lr[(ry.i1 * lw + rx.i0) * 3 + c], p11 = s_lr[(ry.i1 * lw + rx.i1) * 3 + c];
+      const float h0 = __fadd_rn(__fmul_rn(p00, rx.w0), __fmul_rn(p01, rx.w1));
+      const float h1 = __fadd_rn(__fmul_rn(p10, rx.w0), __fmul_rn(p11, rx.w1));
+      float v = __fadd_rn(__fmul_rn(h0, ry.w0), __fmul_rn(h1, ry.w1));
+      v = fminf(fmaxf(v, 0.f), 1.f);
+      v = fminf(fmaxf(rintf(__fmul_rn(v, 255.f)), 0.f), 255.f);
+      v = __fdiv_rn(v, 255.f);
+      v = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+      const int co = bgr2rgb ? 2 - c : c;
+      o[(size_t)co * H * W + it] = v;
+    }
+  }
+}
+
+// Full-resolution blur dump for parity tests (uint8 after truncation and/or fp32 before it).
+__global__ void blur_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_all,
+                                 const int* __restrict__ ksize, int kmax, uint8_t* __restrict__ blur_u8,
+                                 float* __restrict__ blur_f32, int B, int H, int W) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * H * W * 3;
+  if (idx >= total) return;
+  const int c = (int)(idx % 3);
+  size_t r = idx / 3;
+  const int x = (int)(r % W);
+  r /= W;
+  const int y = (int)(r % H);
+  const int b = (int)(r / H);
+  const uint8_t* img = gt + (size_t)b * H * W * 3;
+  const int ksz = ksize[b];
+  float s = (ksz > 0) ? blur_at(img, H, W, y, x, c, taps_all + (size_t)b * kmax * kmax, kmax, ksz)
+                      : (float)img[(y * W + x) * 3 + c];
+  if (blur_f32) blur_f32[idx] = s;
+  if (blur_u8) blur_u8[idx] = trunc_u8(s);
+}
+
+}  // namespace b200ir
 
 using namespace b200ir;
 
 extern "C" int b200ir_degrade(const uint8_t* gt, const float* taps, const int32_t* ksize, int kmax, const int32_t* lr_w,
                               const int32_t* lr_h, const float* noise, int lr_wmax, int lr_hmax, float* out,
-                              uint8_t* blur_out, int B, int H, int W, int bgr2rgb, void* stream) {
-  set_error("degrade: not built yet");
-  return 1;
+                              uint8_t* blur_u8_out, float* blur_f32_out, int B, int H, int W, int bgr2rgb,
+                              void* stream) {
+  B200IR_REQUIRE(gt && taps && ksize && lr_w && lr_h && out, "degrade: null pointer");
+  B200IR_REQUIRE(B > 0 && H > 0 && W > 0 && kmax > 0 && (kmax & 1) && lr_wmax > 0 && lr_hmax > 0,
+                 "degrade: bad sizes (kmax must be odd)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0, smem_optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+    set_error("degrade: no CUDA device");
+    return 1;
+  }
+  const size_t base = deg_layout(kmax, lr_wmax, lr_hmax).gt;
+  const size_t staged = base + (size_t)H * W * 3;
+  const bool stage = (staged <= (size_t)smem_optin) && ((H * W * 3) % 16 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(gt) & 15) == 0);
+  B200IR_REQUIRE(base <= (size_t)smem_optin, "degrade: low-resolution image %dx%d does not fit shared memory", lr_wmax,
+                 lr_hmax);
+  if (stage) {
+    cudaFuncSetAttribute(degrade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
+    degrade_kernel<true><<<B, kDegThreads, staged, st>>>(gt, taps, ksize, kmax, lr_w, lr_h, noise, lr_wmax, lr_hmax,
+                                                        out, H, W, bgr2rgb);
+  } else {
+    cudaFuncSetAttribute(degrade_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+    degrade_kernel<false><<<B, kDegThreads, base, st>>>(gt, taps, ksize, kmax, lr_w, lr_h, noise, lr_wmax, lr_hmax,
+                                                        out, H, W, bgr2rgb);
+  }
+  if (check_launch("degrade")) return 1;
+  if (blur_u8_out || blur_f32_out) {
+    const size_t n = (size_t)B * H * W * 3;
+    blur_full_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gt, taps, ksize, kmax, blur_u8_out, blur_f32_out, B,
+                                                                  H, W);
+    if (check_launch("degrade(blur dump)")) return 1;
+  }
+  return 0;
 }

@@ -172,11 +172,12 @@ int b200ir_nhwc_to_nchw_f32(const void* in, float* out, int B, int P, int C, voi
  * taps:   fp32 [B][kmax][kmax] blur kernels, zero padded, centred; ksize[b] odd (0 = no blur)
  * lr_w/lr_h: int32 [B] low-resolution size per crop; noise: fp32 [B][lr_hmax][lr_wmax][3] (already sigma/255-scaled)
  * out:    fp32 NCHW [B][3][H][W], (x-0.5)/0.5-normalised, channel order reversed if bgr2rgb.
- * blur_out (optional): uint8 [B][H][W][3] blurred image (pyblur output) for parity checks.
+ * blur_u8_out / blur_f32_out (optional, parity checks): the full blurred image [B][H][W][3] as pyblur returns it
+ *         (uint8, truncated) and the fp32 convolution result before the truncation.
  */
 int b200ir_degrade(const uint8_t* gt, const float* taps, const int32_t* ksize, int kmax, const int32_t* lr_w,
-                   const int32_t* lr_h, const float* noise, int lr_wmax, int lr_hmax, float* out, uint8_t* blur_out,
-                   int B, int H, int W, int bgr2rgb, void* stream);
+                   const int32_t* lr_h, const float* noise, int lr_wmax, int lr_hmax, float* out, uint8_t* blur_u8_out,
+                   float* blur_f32_out, int B, int H, int W, int bgr2rgb, void* stream);
 
 #ifdef __cplusplus
 }
