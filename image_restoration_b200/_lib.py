@@ -31,6 +31,7 @@ class ConvDesc(C.Structure):
         ('act', C.c_int32), ('res_mode', C.c_int32), ('res', C.c_void_p),
         ('res_stride_x', C.c_int64), ('res_stride_y', C.c_int64), ('res_stride_b', C.c_int64),
         ('res_w', C.c_int32), ('res_h', C.c_int32), ('res_scale', C.c_float), ('max_ctas', C.c_int32),
+        ('row_mode', C.c_int32),
     ]
 
 

@@ -16,7 +16,11 @@
 namespace b200ir {
 
 static constexpr int kBlockM = 128;
-static constexpr int kThreads = 192;
+static constexpr int kEpiWarps = 8;                         // two per TMEM lane quarter
+static constexpr int kEpiThreads = kEpiWarps * 32;
+static constexpr int kThreads = 64 + kEpiThreads;       // warp 0 producer, warp 1 MMA, warps 2.. epilogue
+static constexpr int kDemodTable = 2048;                   // floats per buffer of the per-tile demod table
+static constexpr int kMaxBias = 512;
 static constexpr int kMaxStages = 8;
 static constexpr int kAccStages = 2;
 
@@ -30,6 +34,10 @@ struct alignas(64) ConvParams {
   int stages;
   uint32_t idesc;
   uint32_t tmem_cols;
+  // row mode (conv_row_kernel): 3x3 stride-1 conv, tile = 128 consecutive pixels of one row, weights resident in
+  // shared memory, each input row segment loaded once (with a 1-pixel halo) and reused for 3 kw shifts x 3 output rows
+  int row_R, row_chunks, row_items, row_slots, row_slot_bytes, row_w_bytes, desc_mode;
+  int smem_demod;  // 1: per-tile demod table staged in shared memory
   int8_t tap_view[B200IR_MAX_TAPS], tap_dx[B200IR_MAX_TAPS], tap_dy[B200IR_MAX_TAPS];
   // epilogue
   void* out;
@@ -69,252 +77,153 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
   return t;
 }
 
-__device__ __forceinline__ void load_half16(const __half* ptr, float (&f)[16]) {
-  const uint4* q = reinterpret_cast<const uint4*>(ptr);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
-  const __half2* ha = reinterpret_cast<const __half2*>(&a);
-  const __half2* hb = reinterpret_cast<const __half2*>(&b);
+__device__ __forceinline__ void unpack_half8(const uint4& q, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 x = __half22float2(ha[i]);
-    float2 y = __half22float2(hb[i]);
+    const float2 x = __half22float2(h[i]);
     f[2 * i] = x.x;
     f[2 * i + 1] = x.y;
-    f[8 + 2 * i] = y.x;
-    f[8 + 2 * i + 1] = y.y;
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
-  uint8_t* smem = smem_raw + pad;
+// Per-thread addressing of one output position, computed (and the noise value fetched) BEFORE the accumulator is
+// ready so that none of it sits on the MMA -> epilogue critical path.
+struct EpiRow {
+  long long out_off;
+  float nz;
+  const __half* r00;
+  const __half* r01;
+  const __half* r10;
+  const __half* r11;
+  float wy0, wy1, wx0, wx1;
+};
 
-  const uint32_t row_bytes = p.block_k * 2;
-  const uint32_t a_bytes = kBlockM * row_bytes;
-  const uint32_t b_bytes = p.block_n * row_bytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kMaxStages;
-  uint64_t* tmem_full = bars + 2 * kMaxStages;
-  uint64_t* tmem_empty = bars + 2 * kMaxStages + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kAccStages);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < kAccStages; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
-    }
-    fence_barrier_init();
+__device__ __forceinline__ EpiRow epi_setup(const ConvParams& p, int x, int y, int b, int n0, bool valid, float gain) {
+  EpiRow r;
+  const int xo = x * p.out_x_mul + p.out_x_off;
+  const int yo = y * p.out_y_mul + p.out_y_off;
+  r.out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx + p.out_c_off + n0;
+  r.nz = 0.f;
+  if (valid && p.noise != nullptr) r.nz = gain * __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);
+  r.r00 = r.r01 = r.r10 = r.r11 = nullptr;
+  r.wy0 = r.wy1 = r.wx0 = r.wx1 = 0.f;
+  if (valid && p.res_mode == 1) {
+    r.r00 = p.res + (long long)b * p.res_sb + (long long)yo * p.res_sy + (long long)xo * p.res_sx + n0;
+  } else if (valid && p.res_mode == 2) {
+    // F.interpolate(scale 2, bilinear, align_corners=False): even 2k -> .25*x[k-1] + .75*x[k], odd 2k+1 ->
+    // .75*x[k] + .25*x[k+1], indices clamped to the tensor.
+    const int ky = yo >> 1, kx = xo >> 1;
+    int ya, yb, xa, xb;
+    if (yo & 1) { ya = ky; yb = min(ky + 1, p.res_h - 1); r.wy0 = 0.75f; r.wy1 = 0.25f; }
+    else        { ya = max(ky - 1, 0); yb = ky; r.wy0 = 0.25f; r.wy1 = 0.75f; }
+    if (xo & 1) { xa = kx; xb = min(kx + 1, p.res_w - 1); r.wx0 = 0.75f; r.wx1 = 0.25f; }
+    else        { xa = max(kx - 1, 0); xb = kx; r.wx0 = 0.25f; r.wx1 = 0.75f; }
+    const __half* rb = p.res + (long long)b * p.res_sb + n0;
+    r.r00 = rb + (long long)ya * p.res_sy + (long long)xa * p.res_sx;
+    r.r01 = rb + (long long)ya * p.res_sy + (long long)xb * p.res_sx;
+    r.r10 = rb + (long long)yb * p.res_sy + (long long)xa * p.res_sx;
+    r.r11 = rb + (long long)yb * p.res_sy + (long long)xb * p.res_sx;
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
+  return r;
+}
+
+// Drains this thread's row of one 128 x block_n accumulator tile, 16 columns at a time (columns c_begin, c_begin +
+// c_step, ...: two warps share a TMEM lane quarter).  Per chunk the TMEM load is issued first, the operands that do not
+// depend on it (bias / demod from shared memory, residual from global) are fetched while it is in flight.
+//   s_bias  : shared memory, bias[n0 ...] (zeros when the layer has no bias)
+//   s_demod : shared memory, demod[b][n0 ...] for this row's image, or nullptr
+//   g_demod : global fallback for demod (used when the per-tile table does not fit), or nullptr
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
+                                              uint32_t full_phase, const EpiRow& r, bool valid, const float* s_bias,
+                                              const float* s_demod, const float* g_demod, int c_begin, int c_step) {
+  mbar_wait(full_bar, full_phase);
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int num_kb = p.num_taps * p.k_chunks;
-
-  if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      for (int v = 0; v < B200IR_MAX_VIEWS; ++v) tma_prefetch_desc(&p.tmap_a[v]);
-      tma_prefetch_desc(&p.tmap_b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          const int view = p.tap_view[tap];
-          const int cx = t.x0 + p.tap_dx[tap];
-          const int cy = t.y0 + p.tap_dy[tap];
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sa = smem + stage * stage_bytes;
-            uint8_t* sb = sa + a_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-            tma_load_4d(sa, &p.tmap_a[view], &full_bar[stage], kc * p.block_k, cx, cy, t.b0);
-            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], (tap * p.k_chunks + kc) * p.block_k, t.n0);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
+  for (int c0 = c_begin; c0 < p.block_n; c0 += c_step) {
+    uint32_t raw[16];
+    tmem_ld16(taddr + c0, raw);
+    float4 bs[4], dm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bs[j] = reinterpret_cast<const float4*>(s_bias + c0)[j];
+    if (s_demod != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = reinterpret_cast<const float4*>(s_demod + c0)[j];
+    } else if (g_demod != nullptr && valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = __ldg(reinterpret_cast<const float4*>(g_demod + c0) + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+    uint4 ra[2], rb[2], rc[2], rd[2];
+    if (valid && p.res_mode != 0) {
+      ra[0] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0));
+      ra[1] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0) + 1);
+      if (p.res_mode == 2) {
+        rb[0] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0));
+        rb[1] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0) + 1);
+        rc[0] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0));
+        rc[1] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0) + 1);
+        rd[0] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0));
+        rd[1] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0) + 1);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      const int k_steps = p.block_k / 16;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * p.block_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          for (int k = 0; k < k_steps; ++k) {
-            const uint64_t da = make_kmajor_desc(sa + k * 32, row_bytes);
-            const uint64_t db = make_kmajor_desc(sb + k * 32, row_bytes);
-            umma_f16(tmem_d, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+    tmem_ld_wait16(raw);
+    if (valid) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[4 * j] = __uint_as_float(raw[4 * j]) * dm[j].x + bs[j].x + r.nz;
+        v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) * dm[j].y + bs[j].y + r.nz;
+        v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) * dm[j].z + bs[j].z + r.nz;
+        v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) * dm[j].w + bs[j].w + r.nz;
+      }
+      if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (v[j] > 0.f ? v[j] : 0.2f * v[j]) * 1.4142135623730951f;
+      }
+      if (p.res_mode == 1) {
+        float f[16];
+        unpack_half8(ra[0], f);
+        unpack_half8(ra[1], f + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (v[j] + f[j]) * p.res_scale;
+      } else if (p.res_mode == 2) {
+        float fa[16], fb[16], fc[16], fd[16];
+        unpack_half8(ra[0], fa); unpack_half8(ra[1], fa + 8);
+        unpack_half8(rb[0], fb); unpack_half8(rb[1], fb + 8);
+        unpack_half8(rc[0], fc); unpack_half8(rc[1], fc + 8);
+        unpack_half8(rd[0], fd); unpack_half8(rd[1], fd + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float up = r.wy0 * (r.wx0 * fa[j] + r.wx1 * fb[j]) + r.wy1 * (r.wx0 * fc[j] + r.wx1 * fd[j]);
+          v[j] = (v[j] + up) * p.res_scale;
         }
       }
-    }
-  } else {
-    // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int xx = row % p.tile_w;
-    const int yy = (row / p.tile_w) % p.tile_h;
-    const int bi = row / (p.tile_w * p.tile_h);
-    const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) : 0.f;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const TileCoord t = decode_tile(p, tile);
-      const int x = t.x0 + xx, y = t.y0 + yy, b = t.b0 + bi;
-      const bool valid = (x < p.m_w) && (y < p.m_h) && (b < p.m_b);
-      const int xo = x * p.out_x_mul + p.out_x_off;
-      const int yo = y * p.out_y_mul + p.out_y_off;
-      const long long out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx +
-                                p.out_c_off + t.n0;
-      float nz = 0.f;
-      if (valid && p.noise != nullptr) nz = gain * __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);
-      // residual source addressing
-      const __half* r00 = nullptr;
-      const __half* r01 = nullptr;
-      const __half* r10 = nullptr;
-      const __half* r11 = nullptr;
-      float wy0 = 0.f, wy1 = 0.f, wx0 = 0.f, wx1 = 0.f;
-      if (valid && p.res_mode == 1) {
-        r00 = p.res + (long long)b * p.res_sb + (long long)yo * p.res_sy + (long long)xo * p.res_sx + t.n0;
-      } else if (valid && p.res_mode == 2) {
-        // F.interpolate(scale 2, bilinear, align_corners=False): even 2k -> .25*x[k-1] + .75*x[k], odd 2k+1 ->
-        // .75*x[k] + .25*x[k+1], indices clamped to the tensor.
-        const int ky = yo >> 1, kx = xo >> 1;
-        int ya, yb, xa, xb;
-        if (yo & 1) { ya = ky; yb = min(ky + 1, p.res_h - 1); wy0 = 0.75f; wy1 = 0.25f; }
-        else        { ya = max(ky - 1, 0); yb = ky; wy0 = 0.25f; wy1 = 0.75f; }
-        if (xo & 1) { xa = kx; xb = min(kx + 1, p.res_w - 1); wx0 = 0.75f; wx1 = 0.25f; }
-        else        { xa = max(kx - 1, 0); xb = kx; wx0 = 0.25f; wx1 = 0.75f; }
-        const __half* rb = p.res + (long long)b * p.res_sb + t.n0;
-        r00 = rb + (long long)ya * p.res_sy + (long long)xa * p.res_sx;
-        r01 = rb + (long long)ya * p.res_sy + (long long)xb * p.res_sx;
-        r10 = rb + (long long)yb * p.res_sy + (long long)xa * p.res_sx;
-        r11 = rb + (long long)yb * p.res_sy + (long long)xb * p.res_sx;
-      }
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + c0, raw);
-        tmem_ld_wait();
-        if (valid) {
-          float v[16];
+      if (p.out_fp32) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r.out_off + c0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-          const int n = t.n0 + c0;
-          if (p.demod != nullptr) {
-            const float4* dp = reinterpret_cast<const float4*>(p.demod + (long long)b * p.cout + n);
+        for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+        uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 d = __ldg(dp + j);
-              v[4 * j] *= d.x; v[4 * j + 1] *= d.y; v[4 * j + 2] *= d.z; v[4 * j + 3] *= d.w;
-            }
-          }
-          if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 d = __ldg(bp + j);
-              v[4 * j] += d.x; v[4 * j + 1] += d.y; v[4 * j + 2] += d.z; v[4 * j + 3] += d.w;
-            }
-          }
-          if (p.noise != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += nz;
-          }
-          if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (v[j] > 0.f ? v[j] : 0.2f * v[j]) * 1.4142135623730951f;
-          }
-          if (p.res_mode == 1) {
-            float r[16];
-            load_half16(r00 + c0, r);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (v[j] + r[j]) * p.res_scale;
-          } else if (p.res_mode == 2) {
-            float ra[16], rb[16], rc[16], rd[16];
-            load_half16(r00 + c0, ra);
-            load_half16(r01 + c0, rb);
-            load_half16(r10 + c0, rc);
-            load_half16(r11 + c0, rd);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float up = wy0 * (wx0 * ra[j] + wx1 * rb[j]) + wy1 * (wx0 * rc[j] + wx1 * rd[j]);
-              v[j] = (v[j] + up) * p.res_scale;
-            }
-          }
-          if (p.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + out_off + c0);
-            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
+        for (int j = 0; j < 8; ++j) {
+          __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
         }
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + r.out_off + c0);
+        op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
     }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
+
+}  // namespace b200ir
+
+#include "conv_kernels.cuh"
+
+namespace b200ir {
 
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -383,6 +292,19 @@ int device_check_impl() { return init_device_info(); }
 
 using namespace b200ir;
 
+template <typename K>
+static int configure_smem(K kernel, int slot) {
+  static bool done[8] = {false, false, false, false, false, false, false, false};
+  if (done[slot]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+  if (e != cudaSuccess) {
+    set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  done[slot] = true;
+  return 0;
+}
+
 extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   B200IR_REQUIRE(d != nullptr, "conv_igemm: null desc");
   if (init_device_info()) return 1;
@@ -440,13 +362,16 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
     p.tap_view[t] = d->tap_view[t]; p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t];
   }
   p.idesc = make_idesc_f16(kBlockM, d->block_n, false);
+  p.smem_demod = (d->demod != nullptr && d->tile_b * d->block_n <= kDemodTable) ? 1 : 0;
+  B200IR_REQUIRE(d->cout <= kMaxBias || d->bias != nullptr, "conv_igemm: cout=%d > %d needs a bias vector", d->cout,
+                 kMaxBias);
   uint32_t cols = 32;
   while (cols < (uint32_t)(kAccStages * d->block_n)) cols <<= 1;
   p.tmem_cols = cols;
 
   const int row_bytes = p.block_k * 2;
   const int stage_bytes = kBlockM * row_bytes + d->block_n * row_bytes;
-  const int tail = (2 * kMaxStages + 2 * kAccStages) * 8 + 16;
+  const int tail = kTailBytes;
   int stages = (g_smem_optin - 1024 - tail) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   B200IR_REQUIRE(stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
@@ -464,17 +389,72 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   p.res_sx = d->res_stride_x; p.res_sy = d->res_stride_y; p.res_sb = d->res_stride_b;
   p.res_w = d->res_w; p.res_h = d->res_h; p.res_scale = d->res_scale;
 
-  static int configured_smem = 0;
-  if (smem_bytes > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    if (e != cudaSuccess) {
-      set_error("conv_igemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return 1;
+  // ---- row mode eligibility: plain 3x3 stride-1 conv on one view, 128-pixel row tiles, weights fit in smem
+  {
+    bool row_ok = d->num_views == 1 && d->num_taps == 9 && d->tile_w == 128 && d->tile_h == 1 && d->tile_b == 1 &&
+                  d->block_n == d->cout && d->out_x_mul == 1 && d->out_y_mul == 1 && d->out_x_off == 0 &&
+                  d->out_y_off == 0 && d->row_mode != 0;
+    for (int t = 0; row_ok && t < 9; ++t)
+      row_ok = d->tap_view[t] == 0 && d->tap_dx[t] == (t % 3) - 1 && d->tap_dy[t] == (t / 3) - 1;
+    if (row_ok) {
+      const int w_bytes = 9 * p.k_chunks * d->block_n * row_bytes;
+      const int slot_bytes = 136 * row_bytes;
+      const int tail_r = kTailBytes;
+      int slots = (g_smem_optin - 1024 - tail_r - w_bytes) / slot_bytes;
+      if (slots > kMaxStages) slots = kMaxStages;
+      if (slots >= 3 * p.k_chunks + 1) {
+        // re-encode the activation map with the 130-pixel halo box
+        const b200ir_view& a = d->a[0];
+        cuuint64_t dims[4] = {(cuuint64_t)a.c, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)a.b};
+        cuuint64_t strides[3] = {(cuuint64_t)a.stride_w * 2, (cuuint64_t)a.stride_h * 2, (cuuint64_t)a.stride_b * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.block_k, 130u, 1u, 1u};
+        if (encode_map(&p.tmap_a[0], a.ptr, 4, dims, strides, box, swz, "activation(row)")) return 1;
+        int R = d->m_h;
+        while ((long long)d->m_b * p.tiles_w * ((d->m_h + R - 1) / R) < 4LL * g_num_sms && R > 8) R = (R + 1) / 2;
+        p.row_R = R;
+        p.row_chunks = (d->m_h + R - 1) / R;
+        p.row_items = d->m_b * p.tiles_w * p.row_chunks;
+        row_ok = p.row_items >= 2 * g_num_sms;  // too little parallelism at small batch: generic tiles are faster
+        p.row_slots = slots;
+        p.row_slot_bytes = slot_bytes;
+        p.row_w_bytes = w_bytes;
+        p.desc_mode = d->row_mode == 2 ? 1 : 0;
+        const int smem_row = w_bytes + slots * slot_bytes + tail_r + 1024;
+        if (row_ok) {
+          int grid_r = p.row_items < g_num_sms ? p.row_items : g_num_sms;
+          if (d->max_ctas > 0 && grid_r > d->max_ctas) grid_r = d->max_ctas;
+          cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+          if (p.block_k == 64) {
+            if (configure_smem(conv_row_kernel<64>, 3)) return 1;
+            conv_row_kernel<64><<<grid_r, kThreads, smem_row, st>>>(p);
+          } else if (p.block_k == 32) {
+            if (configure_smem(conv_row_kernel<32>, 4)) return 1;
+            conv_row_kernel<32><<<grid_r, kThreads, smem_row, st>>>(p);
+          } else {
+            if (configure_smem(conv_row_kernel<16>, 5)) return 1;
+            conv_row_kernel<16><<<grid_r, kThreads, smem_row, st>>>(p);
+          }
+          return check_launch("conv_row");
+        }
+        // not taken: restore the generic activation map (box = tile)
+        cuuint32_t box_g[4] = {(cuuint32_t)p.block_k, (cuuint32_t)d->tile_w, (cuuint32_t)d->tile_h, (cuuint32_t)d->tile_b};
+        if (encode_map(&p.tmap_a[0], a.ptr, 4, dims, strides, box_g, swz, "activation")) return 1;
+      }
     }
-    configured_smem = g_smem_optin;
   }
+
   int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.block_k == 64) {
+    if (configure_smem(conv_igemm_kernel<64>, 0)) return 1;
+    conv_igemm_kernel<64><<<grid, kThreads, smem_bytes, st>>>(p);
+  } else if (p.block_k == 32) {
+    if (configure_smem(conv_igemm_kernel<32>, 1)) return 1;
+    conv_igemm_kernel<32><<<grid, kThreads, smem_bytes, st>>>(p);
+  } else {
+    if (configure_smem(conv_igemm_kernel<16>, 2)) return 1;
+    conv_igemm_kernel<16><<<grid, kThreads, smem_bytes, st>>>(p);
+  }
   return check_launch("conv_igemm");
 }

@@ -198,8 +198,9 @@ class _Plan:
             for half, wk, bk, dst in ((0, 'wsc', 'bsc', sc), (1, 'wsh', 'bsh', sh)):
                 v = ops.View(hid.data_ptr() + 2 * half * cout, cout, w2, h2, B, 2 * cout, w2 * 2 * cout,
                              h2 * w2 * 2 * cout)
+                rk = dict(tile=(128, 1, 1), row_mode=1, block_n=c_sft) if ops.row_mode_ok(B, h2, w2, cout, c_sft) else {}
                 steps.append(ops.ConvOp([v], d[wk], cout, c_sft, ops.taps_3x3(), (w2, h2, B), dst,
-                                        (c_sft, w2 * c_sft, h2 * w2 * c_sft), bias=d[bk]))
+                                        (c_sft, w2 * c_sft, h2 * w2 * c_sft), bias=d[bk], **rk))
             self.cond.append((sc, sh))
             rgb = e32(B, 3, h2, w2)
             self.out_rgbs.append(rgb)

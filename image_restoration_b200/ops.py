@@ -61,7 +61,7 @@ class ConvOp:
     def __init__(self, views, weight, cin, cout, taps, m_whb, out, out_strides, *, out_fp32=False, out_c_off=0,
                  out_mul_off=(1, 0, 1, 0), bias=None, demod=None, noise=None, noise_gain=None, noise_strides=(0, 0),
                  act=False, res=None, res_mode=0, res_strides=(0, 0, 0), res_wh=(0, 0), res_scale=1.0, block_n=None,
-                 tile=None, max_ctas=0):
+                 tile=None, max_ctas=0, row_mode=0):
         d = ConvDesc()
         assert 1 <= len(views) <= _lib.MAX_VIEWS and 1 <= len(taps) <= _lib.MAX_TAPS
         for i, v in enumerate(views):
@@ -95,6 +95,7 @@ class ConvOp:
         d.res_w, d.res_h = res_wh
         d.res_scale = res_scale
         d.max_ctas = max_ctas
+        d.row_mode = row_mode
         self.desc = d
         # keep every tensor alive as long as the op exists
         self._keep = (weight, out, bias, demod, noise, noise_gain, res)
@@ -108,6 +109,23 @@ def taps_3x3():
     return [(0, kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
 
 
+NUM_SMS = 148
+
+
+def row_mode_ok(b, h, w, cin, cout):
+    """Mirror of the eligibility test of the row-sliding conv variant in b200ir_conv_igemm: low channel counts at
+    high resolution (L2-bound with generic tiles), weights resident in shared memory, enough work items."""
+    if cin > 128 or cout > 256 or cout % 16 or w < 128:
+        return False
+    block_k = 64 if cin % 64 == 0 else (32 if cin % 32 == 0 else 16)
+    kc = cin // block_k
+    w_bytes = 9 * kc * cout * block_k * 2
+    slots = (232448 - 1024 - (256 + 512 * 4 + 2 * 2048 * 4) - w_bytes) // (136 * block_k * 2)
+    if slots < 3 * kc + 1:
+        return False
+    return b * -(-w // 128) * -(-h // 8) >= 2 * NUM_SMS
+
+
 def conv_same(x, weight, out, ksize, **kw):
     """Stride-1 'same' conv (k = 1 or 3) of NHWC x [B,H,W,Cin] into NHWC out [B,H,W,Ctot] (channel offset via
     out_c_off).  EqualConv2d / plain ModulatedConv2d / ConvUpLayer conv."""
@@ -115,6 +133,8 @@ def conv_same(x, weight, out, ksize, **kw):
     cout = weight.shape[0]
     taps = taps_3x3() if ksize == 3 else [(0, 0, 0)]
     oc = out.shape[3]
+    if ksize == 3 and 'tile' not in kw and 'row_mode' not in kw and row_mode_ok(b, h, w, cin, cout):
+        kw.update(tile=(128, 1, 1), row_mode=1, block_n=cout)
     return ConvOp([nhwc_view(x)], weight, cin, cout, taps, (w, h, b), out, (oc, w * oc, h * w * oc), **kw)
 
 

@@ -100,6 +100,8 @@ typedef struct {
   int32_t res_w, res_h; /* extents of the residual tensor (for the clamp of mode 2) */
   float res_scale;
   int32_t max_ctas; /* 0: one CTA per SM */
+  int32_t row_mode; /* 0: generic tiles; 1: allow the row-sliding variant (3x3 stride 1, tile 128x1x1, weights resident
+                       in shared memory; picked only when eligible and the batch gives enough work items) */
 } b200ir_conv_desc;
 
 int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
