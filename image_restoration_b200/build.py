@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libb200ir.so')
 SOURCES = ['api.cu', 'conv_igemm.cu', 'pointwise.cu', 'degrade.cu']
-HEADERS = ['ptx.cuh', 'host_common.h', os.path.join('..', '..', 'include', 'b200ir.h')]
+HEADERS = ['ptx.cuh', 'host_common.h', 'conv_kernels.cuh', os.path.join('..', '..', 'include', 'b200ir.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -21,6 +21,7 @@ def _stale():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC)]          # any new header counts too
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

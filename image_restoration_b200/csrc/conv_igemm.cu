@@ -22,7 +22,7 @@ static constexpr int kThreads = 64 + kEpiThreads;       // warp 0 producer, warp
 static constexpr int kDemodTable = 2048;                   // floats per buffer of the per-tile demod table
 static constexpr int kMaxBias = 512;
 static constexpr int kMaxStages = 8;
-static constexpr int kAccStages = 2;
+static constexpr int kMaxAccStages = 8;  // TMEM accumulator ring: as many 128 x block_n tiles as fit in 512 columns
 
 struct alignas(64) ConvParams {
   CUtensorMap tmap_a[B200IR_MAX_VIEWS];
@@ -34,10 +34,13 @@ struct alignas(64) ConvParams {
   int stages;
   uint32_t idesc;
   uint32_t tmem_cols;
+  int acc_stages, acc_shift;
   // row mode (conv_row_kernel): 3x3 stride-1 conv, tile = 128 consecutive pixels of one row, weights resident in
   // shared memory, each input row segment loaded once (with a 1-pixel halo) and reused for 3 kw shifts x 3 output rows
   int row_R, row_chunks, row_items, row_slots, row_slot_bytes, row_w_bytes, desc_mode;
   int smem_demod;  // 1: per-tile demod table staged in shared memory
+  int st256;       // 1: fp16 output rows are 32-byte aligned -> 256-bit stores
+  float act_gain;  // sqrt(2) when act is set (folded into the bias / demod / noise terms), else 1
   int8_t tap_view[B200IR_MAX_TAPS], tap_dx[B200IR_MAX_TAPS], tap_dy[B200IR_MAX_TAPS];
   // epilogue
   void* out;
@@ -105,7 +108,7 @@ __device__ __forceinline__ EpiRow epi_setup(const ConvParams& p, int x, int y, i
   const int yo = y * p.out_y_mul + p.out_y_off;
   r.out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx + p.out_c_off + n0;
   r.nz = 0.f;
-  if (valid && p.noise != nullptr) r.nz = gain * __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);
+  if (valid && p.noise != nullptr) r.nz = gain * __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);  // gain includes act_gain
   r.r00 = r.r01 = r.r10 = r.r11 = nullptr;
   r.wy0 = r.wy1 = r.wx0 = r.wx1 = 0.f;
   if (valid && p.res_mode == 1) {
@@ -150,10 +153,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
       for (int j = 0; j < 4; ++j) dm[j] = reinterpret_cast<const float4*>(s_demod + c0)[j];
     } else if (g_demod != nullptr && valid) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dm[j] = __ldg(reinterpret_cast<const float4*>(g_demod + c0) + j);
+      for (int j = 0; j < 4; ++j) {
+        dm[j] = __ldg(reinterpret_cast<const float4*>(g_demod + c0) + j);
+        dm[j].x *= p.act_gain; dm[j].y *= p.act_gain; dm[j].z *= p.act_gain; dm[j].w *= p.act_gain;
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dm[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+      for (int j = 0; j < 4; ++j) dm[j] = make_float4(p.act_gain, p.act_gain, p.act_gain, p.act_gain);
     }
     uint4 ra[2], rb[2], rc[2], rd[2];
     if (valid && p.res_mode != 0) {
@@ -170,17 +176,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
     }
     tmem_ld_wait16(raw);
     if (valid) {
+      // bias / demod / noise arrive pre-multiplied by the activation gain (sqrt 2) when act is set, so the
+      // leaky-ReLU is just max(v, 0.2 v)
       float v[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        v[4 * j] = __uint_as_float(raw[4 * j]) * dm[j].x + bs[j].x + r.nz;
-        v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) * dm[j].y + bs[j].y + r.nz;
-        v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) * dm[j].z + bs[j].z + r.nz;
-        v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) * dm[j].w + bs[j].w + r.nz;
+        v[4 * j] = __uint_as_float(raw[4 * j]) * dm[j].x + (bs[j].x + r.nz);
+        v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) * dm[j].y + (bs[j].y + r.nz);
+        v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) * dm[j].z + (bs[j].z + r.nz);
+        v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) * dm[j].w + (bs[j].w + r.nz);
       }
       if (p.act) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (v[j] > 0.f ? v[j] : 0.2f * v[j]) * 1.4142135623730951f;
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
       }
       if (p.res_mode == 1) {
         float f[16];
@@ -211,9 +219,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
           __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
           pk[j] = *reinterpret_cast<uint32_t*>(&h);
         }
-        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + r.out_off + c0);
-        op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        __half* op = reinterpret_cast<__half*>(p.out) + r.out_off + c0;
+        if (p.st256) {  // one full 32-byte sector per thread and instruction (no partial-sector writes in L2)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]),
+                       "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
+        } else {
+          reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
       }
     }
   }
@@ -363,10 +377,21 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   }
   p.idesc = make_idesc_f16(kBlockM, d->block_n, false);
   p.smem_demod = (d->demod != nullptr && d->tile_b * d->block_n <= kDemodTable) ? 1 : 0;
-  B200IR_REQUIRE(d->cout <= kMaxBias || d->bias != nullptr, "conv_igemm: cout=%d > %d needs a bias vector", d->cout,
-                 kMaxBias);
+  p.st256 = (!d->out_fp32 && d->out_c_off % 16 == 0 && d->out_stride_x % 16 == 0 && d->out_stride_y % 16 == 0 &&
+             d->out_stride_b % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 31) == 0) ? 1 : 0;
+  B200IR_REQUIRE(d->cout <= kMaxBias || (d->bias != nullptr && !d->act),
+                 "conv_igemm: cout=%d > %d needs a bias vector and no activation", d->cout, kMaxBias);
+  // accumulator ring depth: the epilogue latency of a tile is hidden behind the main loops of the next
+  // (acc_stages - 1) tiles; small tiles (short main loops) need a deeper ring
+  int acc_stages = 2, acc_shift = 1;
+  while (acc_stages < kMaxAccStages && 2 * acc_stages * d->block_n <= 512) {
+    acc_stages *= 2;
+    ++acc_shift;
+  }
+  p.acc_stages = acc_stages;
+  p.acc_shift = acc_shift;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(kAccStages * d->block_n)) cols <<= 1;
+  while (cols < (uint32_t)(acc_stages * d->block_n)) cols <<= 1;
   p.tmem_cols = cols;
 
   const int row_bytes = p.block_k * 2;
@@ -385,7 +410,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   p.cout = d->cout;
   p.bias = d->bias; p.demod = d->demod; p.noise = d->noise; p.noise_gain = d->noise_gain;
   p.noise_sb = d->noise_stride_b; p.noise_sy = d->noise_stride_y;
-  p.act = d->act; p.res_mode = d->res_mode; p.res = reinterpret_cast<const __half*>(d->res);
+  p.act = d->act; p.act_gain = d->act ? 1.4142135623730951f : 1.f; p.res_mode = d->res_mode; p.res = reinterpret_cast<const __half*>(d->res);
   p.res_sx = d->res_stride_x; p.res_sy = d->res_stride_y; p.res_sb = d->res_stride_b;
   p.res_w = d->res_w; p.res_h = d->res_h; p.res_scale = d->res_scale;
 

@@ -21,8 +21,8 @@ struct KernelSmem {
   uint8_t* base;        // 1024-byte aligned
   uint64_t* full_bar;   // [kMaxStages]
   uint64_t* empty_bar;  // [kMaxStages]
-  uint64_t* tmem_full;  // [kAccStages]
-  uint64_t* tmem_empty; // [kAccStages]
+  uint64_t* tmem_full;  // [kMaxAccStages]
+  uint64_t* tmem_empty; // [kMaxAccStages]
   uint64_t* w_bar;      // row mode: resident weights landed
   uint32_t* tmem_slot;
   float* bias;          // [kMaxBias] bias of all output channels (zeros when the layer has none)
@@ -30,9 +30,12 @@ struct KernelSmem {
 };
 
 // bytes after the pipeline buffers: barriers + TMEM slot + bias + demod tables
-static constexpr int kTailBytes = 256 + kMaxBias * 4 + 2 * kDemodTable * 4;
+static constexpr int kTailBytes = 512 + kMaxBias * 4 + 2 * kDemodTable * 4;
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+// the two epilogue warp groups (4 warps each) drain alternate tiles; each group syncs on its own named barrier
+__device__ __forceinline__ void epi_group_sync(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
 
 __device__ __forceinline__ KernelSmem carve_smem(uint8_t* smem_raw, uint32_t data_bytes) {
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -43,10 +46,10 @@ __device__ __forceinline__ KernelSmem carve_smem(uint8_t* smem_raw, uint32_t dat
   s.full_bar = bars;
   s.empty_bar = bars + kMaxStages;
   s.tmem_full = bars + 2 * kMaxStages;
-  s.tmem_empty = bars + 2 * kMaxStages + kAccStages;
-  s.w_bar = bars + 2 * kMaxStages + 2 * kAccStages;
+  s.tmem_empty = bars + 2 * kMaxStages + kMaxAccStages;
+  s.w_bar = bars + 2 * kMaxStages + 2 * kMaxAccStages;
   s.tmem_slot = reinterpret_cast<uint32_t*>(s.w_bar + 1);
-  s.bias = reinterpret_cast<float*>(s.base + data_bytes + 256);
+  s.bias = reinterpret_cast<float*>(s.base + data_bytes + 512);
   s.demod = s.bias + kMaxBias;
   return s;
 }
@@ -57,15 +60,16 @@ __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const K
       mbar_init(&s.full_bar[i], 1);
       mbar_init(&s.empty_bar[i], 1);
     }
-    for (int i = 0; i < kAccStages; ++i) {
+    for (int i = 0; i < p.acc_stages; ++i) {
       mbar_init(&s.tmem_full[i], 1);
-      mbar_init(&s.tmem_empty[i], kEpiThreads);
+      mbar_init(&s.tmem_empty[i], 128);
     }
     mbar_init(s.w_bar, 1);
     fence_barrier_init();
   }
   if (p.cout <= kMaxBias)
-    for (int i = threadIdx.x; i < p.cout; i += kThreads) s.bias[i] = (p.bias != nullptr) ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.cout; i += kThreads)
+      s.bias[i] = (p.bias != nullptr) ? p.bias[i] * p.act_gain : 0.f;
   if (warp == 1) {
     tmem_alloc(s.tmem_slot, p.tmem_cols);
     tmem_relinquish();
@@ -140,8 +144,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      mbar_wait(&s.tmem_empty[acc], ((it >> 1) & 1) ^ 1u);
+      const int acc = it & (p.acc_stages - 1);
+      mbar_wait(&s.tmem_empty[acc], ((it >> p.acc_shift) & 1) ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * p.block_n;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -164,18 +168,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
     }
   } else {
-    // ---------------- epilogue: 8 warps, TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
+    // ---------------- epilogue: two groups of 4 warps drain alternate tiles; TMEM lane quarter = warp % 4
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;
+    const int group = (warp - 2) >> 2;
+    const int gt = (threadIdx.x - 64) & 127;
     const int row = q * 32 + lane;
     const int xx = row % p.tile_w;
     const int yy = (row / p.tile_w) % p.tile_h;
     const int bi = row / (p.tile_w * p.tile_h);
-    const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) : 0.f;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
+    const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) * p.act_gain : 0.f;
+    int it = group;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int acc = it & (p.acc_stages - 1);
       const TileCoord t = decode_tile(p, tile);
       const int x = t.x0 + xx, y = t.y0 + yy, b = t.b0 + bi;
       const bool valid = (x < p.m_w) && (y < p.m_h) && (b < p.m_b);
@@ -184,20 +188,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const float* g_dm = nullptr;
       if (p.demod != nullptr) {
         if (p.smem_demod) {
-          float* tab = s.demod + (it & 1) * kDemodTable;
-          for (int i = et; i < p.tile_b * p.block_n; i += kEpiThreads) {
+          float* tab = s.demod + group * kDemodTable;
+          epi_group_sync(group);  // previous tile of this group fully drained
+          for (int i = gt; i < p.tile_b * p.block_n; i += 128) {
             const int bb = t.b0 + i / p.block_n;
-            tab[i] = (bb < p.m_b) ? __ldg(p.demod + (long long)bb * p.cout + t.n0 + (i % p.block_n)) : 0.f;
+            tab[i] = (bb < p.m_b) ? __ldg(p.demod + (long long)bb * p.cout + t.n0 + (i % p.block_n)) * p.act_gain : 0.f;
           }
-          epi_bar_sync();
+          epi_group_sync(group);
           s_dm = tab + bi * p.block_n;
         } else {
           g_dm = p.demod + (long long)b * p.cout + t.n0;
         }
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-      const float* bias_ptr = (p.cout <= kMaxBias) ? s.bias + t.n0 : p.bias + t.n0;  // wide layers: global (L1-cached)
-      epilogue_tile(p, taddr, &s.tmem_full[acc], (it >> 1) & 1, r, valid, bias_ptr, s_dm, g_dm, half * 16, 32);
+      const float* bias_ptr = (p.cout <= kMaxBias) ? s.bias + t.n0 : p.bias + t.n0;  // wide layers: global, act == 0
+      epilogue_tile(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, r, valid, bias_ptr, s_dm, g_dm, 0, 16);
       tc_fence_before();
       mbar_arrive(&s.tmem_empty[acc]);
     }
@@ -300,8 +305,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_cons
           }
           ++rows_waited;
         }
-        const int acc = it & 1;
-        mbar_wait(&s.tmem_empty[acc], ((it >> 1) & 1) ^ 1u);
+        const int acc = it & (p.acc_stages - 1);
+        mbar_wait(&s.tmem_empty[acc], ((it >> p.acc_shift) & 1) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tmem_d = tmem_base + acc * p.block_n;
@@ -340,34 +345,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_cons
       if (row_slot >= nslots) row_slot -= nslots;
     }
   } else {
-    // ---------------- epilogue: 8 warps, TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
+    // ---------------- epilogue: two groups of 4 warps drain alternate output rows
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;
+    const int group = (warp - 2) >> 2;
+    const int gt = (threadIdx.x - 64) & 127;
     const int row = q * 32 + lane;
-    const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) : 0.f;
-    int it = 0, item_no = 0;
-    for (int item = blockIdx.x; item < p.row_items; item += gridDim.x, ++item_no) {
+    const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) * p.act_gain : 0.f;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.row_items; item += gridDim.x) {
       const RowItem w = decode_item(p, item);
       const int x = w.seg * 128 + row;
       const bool valid = x < p.m_w;
       const float* s_dm = nullptr;
-      if (p.demod != nullptr) {  // one image per item: stage its demod row once (block_n == cout <= kDemodTable)
-        float* tab = s.demod + (item_no & 1) * kDemodTable;
-        for (int i = et; i < p.block_n; i += kEpiThreads) tab[i] = __ldg(p.demod + (long long)w.b * p.cout + i);
-        epi_bar_sync();
+      if (p.demod != nullptr) {  // one image per item: each group stages that image's demod row once
+        float* tab = s.demod + group * kDemodTable;
+        epi_group_sync(group);
+        for (int i = gt; i < p.block_n; i += 128) tab[i] = __ldg(p.demod + (long long)w.b * p.cout + i) * p.act_gain;
+        epi_group_sync(group);
         s_dm = tab;
       }
-      EpiRow r = epi_setup(p, x, w.y0, w.b, 0, valid, gain);
       for (int j = 0; j < w.rows_out; ++j, ++it) {
-        const int acc = it & 1;
-        // prefetch the next row's addressing / noise while this row's accumulator is being produced
-        const EpiRow rn = (j + 1 < w.rows_out) ? epi_setup(p, x, w.y0 + j + 1, w.b, 0, valid, gain) : r;
+        if ((it & 1) != group) continue;
+        const int acc = it & (p.acc_stages - 1);
+        const EpiRow r = epi_setup(p, x, w.y0 + j, w.b, 0, valid, gain);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-        epilogue_tile(p, taddr, &s.tmem_full[acc], (it >> 1) & 1, r, valid, s.bias, s_dm, nullptr, half * 16, 32);
+        epilogue_tile(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, r, valid, s.bias, s_dm, nullptr, 0, 16);
         tc_fence_before();
         mbar_arrive(&s.tmem_empty[acc]);
-        r = rn;
       }
     }
   }
