@@ -35,6 +35,15 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ModLayer(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('bias', C.c_void_p), ('s', C.c_void_p), ('lat_idx', C.c_int32), ('cin', C.c_int32)]
+
+
+class DemodLayer(C.Structure):
+    _fields_ = [('s', C.c_void_p), ('wsq', C.c_void_p), ('d', C.c_void_p), ('scale2', C.c_float),
+                ('cin', C.c_int32), ('cout', C.c_int32)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> argtypes (return type is int unless listed in _RESTYPES); mirrors include/b200ir.h one to one
@@ -54,6 +63,8 @@ SIGNATURES = {
     'b200ir_modulate_const': [_P, _P, _P, _I, _I, _I, _P],
     'b200ir_mod_linear': [_P, _I, _I, _I, _P, _P, _F, _P, _I, _I, _P],
     'b200ir_demod': [_P, _P, _F, _P, _I, _I, _I, _P],
+    'b200ir_mod_linear_multi': [_P, _I, _I, _P, _I, _I, _F, _I, _P],
+    'b200ir_demod_multi': [_P, _I, _I, _I, _P],
     'b200ir_nhwc_to_nchw_f32': [_P, _P, _I, _I, _I, _P],
     'b200ir_degrade': [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
 }

@@ -64,13 +64,81 @@ __global__ void first_conv_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------ FIR family
-// in [B][H][W][C]; out position (y, x) = sum_{a,b} k[a]k[b]/64 * in[y*sy + a - py][x*sx + b - px], zero outside.
-__global__ void fir4_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C,
-                            int OH, int OW, int out_h, int out_w, int step, int pad) {
+// 4x4 FIR outer(k,k), k = kscale*[1,3,3,1], evaluated for FOUR horizontally adjacent outputs per thread (8 channels):
+// 4 rows x 7 columns of 16-byte loads feed 4 outputs (7 loads per output instead of 16); separable per row.
+//   out(y, x0+o) = sum_{a,b} k[a] k[b] * in(y + a - pad, x0 + o + b - pad), zero outside [0,Hv) x [0,Wv).
+__device__ __forceinline__ void fir_quad(const __half* __restrict__ base, int pitch_w, int C, int Hv, int Wv, int y_in0,
+                                         int x_in0, float kscale, float (&acc)[4][8]) {
+  const float k[4] = {kscale, 3.f * kscale, 3.f * kscale, kscale};
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int iy = y_in0 + a;
+    if (iy < 0 || iy >= Hv) continue;
+    float hrow[4][8];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hrow[o][j] = 0.f;
+    const __half* rowp = base + (long long)iy * pitch_w * C;
+#pragma unroll
+    for (int col = 0; col < 7; ++col) {
+      const int ix = x_in0 + col;
+      if (ix < 0 || ix >= Wv) continue;
+      const H8 v = ld8(rowp + (long long)ix * C);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int bb = col - o;
+        if (bb >= 0 && bb < 4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hrow[o][j] += k[bb] * v.v[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o][j] += k[a] * hrow[o][j];
+  }
+}
+
+// UpFirDnSmooth with pad (2,2): in [B][H][W][C] -> out rows 0..H, cols 0..W of [B][out_h][out_w][C]
+__global__ void fir_pad22_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C,
+                                 int out_h, int out_w) {
   const int cg = C >> 3;
+  const int OW = W + 1, OH = H + 1;
+  const int xg = (OW + 3) >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * OH * OW * cg;
-  if (idx >= total) return;
+  if (idx >= (long long)B * OH * xg * cg) return;
+  const int c = (int)(idx % cg) * 8;
+  long long r = idx / cg;
+  const int x0 = (int)(r % xg) * 4;
+  r /= xg;
+  const int y = (int)(r % OH);
+  const int b = (int)(r / OH);
+  float acc[4][8];
+  fir_quad(in + (long long)b * H * W * C + c, W, C, H, W, y - 2, x0 - 2, 0.125f, acc);
+  __half* op = out + (((long long)b * out_h + y) * out_w + x0) * C + c;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    if (x0 + o < OW) {
+      H8 v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = acc[o][j];
+      st8(op + (long long)o * C, v);
+    }
+  }
+}
+
+// pad (1,1) + stride-2 sampling (ResBlock.skip): out(y,x) = sum k[a]k[b] in(2y + a - 1, 2x + b - 1)
+__global__ void fir_down2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C) {
+  const int cg = C >> 3;
+  const int OH = H >> 1, OW = W >> 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * OH * OW * cg) return;
   const int c = (int)(idx % cg) * 8;
   long long r = idx / cg;
   const int x = (int)(r % OW);
@@ -81,11 +149,11 @@ __global__ void fir4_kernel(const __half* __restrict__ in, __half* __restrict__ 
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const int iy = y * step + a - pad;
+    const int iy = 2 * y + a - 1;
     if (iy < 0 || iy >= H) continue;
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) {
-      const int ix = x * step + bb - pad;
+      const int ix = 2 * x + bb - 1;
       if (ix < 0 || ix >= W) continue;
       const H8 v = ld8(in + (((long long)b * H + iy) * W + ix) * C + c);
       const float wgt = k[a] * k[bb];
@@ -96,40 +164,51 @@ __global__ void fir4_kernel(const __half* __restrict__ in, __half* __restrict__ 
   H8 o;
 #pragma unroll
   for (int j = 0; j < 8; ++j) o.v[j] = acc[j];
-  st8(out + (((long long)b * out_h + y) * out_w + x) * C + c, o);
+  st8(out + idx * 8, o);
 }
 
 // ------------------------------------------------------------------------------------------ bilinear x2
+// One thread produces the 2x2 outputs fed by input pixel (k,l): 3x3 loads per 4 outputs.
 __global__ void bilinear_up2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int h, int w,
                                     int C) {
   const int cg = C >> 3;
-  const int OH = 2 * h, OW = 2 * w;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * OH * OW * cg;
-  if (idx >= total) return;
+  if (idx >= (long long)B * h * w * cg) return;
   const int c = (int)(idx % cg) * 8;
   long long r = idx / cg;
-  const int x = (int)(r % OW);
-  r /= OW;
-  const int y = (int)(r % OH);
-  const int b = (int)(r / OH);
-  const int ky = y >> 1, kx = x >> 1;
-  int ya, yb, xa, xb;
-  float wy0, wy1, wx0, wx1;
-  if (y & 1) { ya = ky; yb = min(ky + 1, h - 1); wy0 = 0.75f; wy1 = 0.25f; }
-  else       { ya = max(ky - 1, 0); yb = ky; wy0 = 0.25f; wy1 = 0.75f; }
-  if (x & 1) { xa = kx; xb = min(kx + 1, w - 1); wx0 = 0.75f; wx1 = 0.25f; }
-  else       { xa = max(kx - 1, 0); xb = kx; wx0 = 0.25f; wx1 = 0.75f; }
+  const int l = (int)(r % w);
+  r /= w;
+  const int k = (int)(r % h);
+  const int b = (int)(r / h);
+  const int ys[3] = {max(k - 1, 0), k, min(k + 1, h - 1)};
+  const int xs[3] = {max(l - 1, 0), l, min(l + 1, w - 1)};
   const __half* base = in + (long long)b * h * w * C + c;
-  const H8 v00 = ld8(base + ((long long)ya * w + xa) * C);
-  const H8 v01 = ld8(base + ((long long)ya * w + xb) * C);
-  const H8 v10 = ld8(base + ((long long)yb * w + xa) * C);
-  const H8 v11 = ld8(base + ((long long)yb * w + xb) * C);
+  float lo[3][8], hi[3][8];  // horizontal pass: lo -> output col 2l, hi -> output col 2l+1
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const __half* rp = base + (long long)ys[a] * w * C;
+    const H8 v0 = ld8(rp + (long long)xs[0] * C), v1 = ld8(rp + (long long)xs[1] * C), v2 = ld8(rp + (long long)xs[2] * C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      lo[a][j] = 0.25f * v0.v[j] + 0.75f * v1.v[j];
+      hi[a][j] = 0.75f * v1.v[j] + 0.25f * v2.v[j];
+    }
+  }
+  const int OW = 2 * w;
+  __half* op = out + (((long long)b * 2 * h + 2 * k) * OW + 2 * l) * C + c;
   H8 o;
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    o.v[j] = wy0 * (wx0 * v00.v[j] + wx1 * v01.v[j]) + wy1 * (wx0 * v10.v[j] + wx1 * v11.v[j]);
-  st8(out + idx * 8, o);
+  for (int j = 0; j < 8; ++j) o.v[j] = 0.25f * lo[0][j] + 0.75f * lo[1][j];
+  st8(op, o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o.v[j] = 0.25f * hi[0][j] + 0.75f * hi[1][j];
+  st8(op + C, o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o.v[j] = 0.75f * lo[1][j] + 0.25f * lo[2][j];
+  st8(op + (long long)OW * C, o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o.v[j] = 0.75f * hi[1][j] + 0.25f * hi[2][j];
+  st8(op + (long long)OW * C + C, o);
 }
 
 __global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out,
@@ -144,122 +223,138 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
 }
 
 // ------------------------------------------------------------------------------------------ upsample-StyleConv tail
+// Four adjacent outputs per thread (w2 is a multiple of 4 on this path).
 __global__ void upfir_act_kernel(const __half* __restrict__ raw, __half* __restrict__ out, int B, int h2, int w2, int C,
                                  int raw_h, int raw_w, const float* __restrict__ noise, long long noise_sb,
                                  const float* __restrict__ noise_gain, const float* __restrict__ bias,
                                  const __half* __restrict__ scale, const __half* __restrict__ shift, int c_sft,
                                  const float* __restrict__ s_next) {
   const int cg = C >> 3;
+  const int xg = w2 >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * h2 * w2 * cg;
-  if (idx >= total) return;
+  if (idx >= (long long)B * h2 * xg * cg) return;
   const int c = (int)(idx % cg) * 8;
   long long r = idx / cg;
-  const int x = (int)(r % w2);
-  r /= w2;
+  const int x0 = (int)(r % xg) * 4;
+  r /= xg;
   const int y = (int)(r % h2);
   const int b = (int)(r / h2);
-  // FIR*4 with pad (1,1) over the (2h+1)x(2w+1) = (h2+1)x(w2+1) valid raw samples
-  const float k[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float acc[4][8];
+  // FIR*4 (k = [1,3,3,1]/4 per axis) with pad (1,1) over the (h2+1) x (w2+1) valid raw samples
+  fir_quad(raw + (long long)b * raw_h * raw_w * C + c, raw_w, C, h2 + 1, w2 + 1, y - 1, x0 - 1, 0.25f, acc);
+  float bs[8], sn[8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int iy = y + a - 1;
-    if (iy < 0 || iy > h2) continue;
-#pragma unroll
-    for (int bb = 0; bb < 4; ++bb) {
-      const int ix = x + bb - 1;
-      if (ix < 0 || ix > w2) continue;
-      const H8 v = ld8(raw + (((long long)b * raw_h + iy) * raw_w + ix) * C + c);
-      const float wgt = k[a] * k[bb];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += wgt * v.v[j];
-    }
+  for (int j = 0; j < 8; ++j) {
+    bs[j] = __ldg(bias + c + j);
+    sn[j] = (s_next != nullptr) ? __ldg(s_next + (long long)b * C + c + j) : 1.f;
   }
-  float nz = 0.f;
-  if (noise != nullptr) nz = __ldg(noise_gain) * __ldg(noise + b * noise_sb + (long long)y * w2 + x);
-  H8 o;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o.v[j] = lrelu_s(acc[j] + nz + __ldg(bias + c + j));
+  const float g = (noise != nullptr) ? __ldg(noise_gain) : 0.f;
   const int c_keep = C - c_sft;
-  if (scale != nullptr && c >= c_keep) {
-    const long long po = (((long long)b * h2 + y) * w2 + x) * c_sft + (c - c_keep);
-    const H8 sc = ld8(scale + po), sh = ld8(shift + po);
+  const bool sft = (scale != nullptr) && (c >= c_keep);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = o.v[j] * sc.v[j] + sh.v[j];
-  }
-  if (s_next != nullptr) {
+  for (int o = 0; o < 4; ++o) {
+    const int x = x0 + o;
+    const float nz = (noise != nullptr) ? g * __ldg(noise + b * noise_sb + (long long)y * w2 + x) : 0.f;
+    H8 v;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] *= __ldg(s_next + (long long)b * C + c + j);
+    for (int j = 0; j < 8; ++j) v.v[j] = lrelu_s(acc[o][j] + nz + bs[j]);
+    const long long pix = ((long long)b * h2 + y) * w2 + x;
+    if (sft) {
+      const long long po = pix * c_sft + (c - c_keep);
+      const H8 sc = ld8(scale + po), sh = ld8(shift + po);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = v.v[j] * sc.v[j] + sh.v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] *= sn[j];
+    st8(out + pix * C + c, v);
   }
-  st8(out + idx * 8, o);
 }
 
 // ------------------------------------------------------------------------------------------ toRGB
-// A group of `lanes` consecutive lanes handles one pixel; each lane covers 8 channels per iteration.
-__global__ void to_rgb_kernel(const __half* __restrict__ x, int B, int h, int w, int C, const float* __restrict__ wrgb,
+// grid (pixel blocks, B): a block works on kRgbPix pixels of ONE image, so every thread keeps its channel group's
+// modulated RGB weights (w[o][c]*s[b][c]) and next-layer modulation in registers across all its pixels.
+// `lanes` consecutive lanes share a pixel (8 channels each, G = C / (8*lanes) groups per lane).
+static constexpr int kRgbPix = 256;
+template <int G>
+__global__ void to_rgb_kernel(const __half* __restrict__ x, int HW, int w, int C, const float* __restrict__ wrgb,
                               const float* __restrict__ s, const float* __restrict__ bias,
                               const float* __restrict__ skip, float* __restrict__ rgb,
                               const float* __restrict__ s_next, __half* __restrict__ xs_out, int lanes) {
-  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pix = gtid / lanes;
-  const int sub = (int)(gtid % lanes);
-  const long long npix = (long long)B * h * w;
-  const bool active = pix < npix;
-  const long long pc = active ? pix : (npix - 1);
-  const int b = (int)(pc / ((long long)h * w));
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int c = sub * 8; c < C; c += lanes * 8) {
-    H8 v = ld8(x + pc * C + c);
-    float m[8];
+  const int b = blockIdx.y;
+  const int sub = threadIdx.x % lanes;
+  const int pslot = threadIdx.x / lanes;
+  const int pstep = blockDim.x / lanes;
+  float wm[G][3][8], sn[G][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = (s != nullptr) ? v.v[j] * __ldg(s + (long long)b * C + c + j) : v.v[j];
+  for (int g = 0; g < G; ++g) {
+    const int c = (g * lanes + sub) * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a0 += m[j] * __ldg(wrgb + c + j);
-      a1 += m[j] * __ldg(wrgb + C + c + j);
-      a2 += m[j] * __ldg(wrgb + 2 * C + c + j);
-    }
-    if (xs_out != nullptr && active) {
-      H8 o;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = v.v[j] * __ldg(s_next + (long long)b * C + c + j);
-      st8(xs_out + pc * C + c, o);
+      const float sv = (s != nullptr) ? __ldg(s + (long long)b * C + c + j) : 1.f;
+      wm[g][0][j] = __ldg(wrgb + c + j) * sv;
+      wm[g][1][j] = __ldg(wrgb + C + c + j) * sv;
+      wm[g][2][j] = __ldg(wrgb + 2 * C + c + j) * sv;
+      sn[g][j] = (s_next != nullptr) ? __ldg(s_next + (long long)b * C + c + j) : 1.f;
     }
   }
-  for (int off = lanes >> 1; off > 0; off >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, off);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
-  }
-  if (!active || sub != 0) return;
-  const int p = (int)(pc % ((long long)h * w));
-  const int y = p / w, xq = p % w;
-  float o[3] = {a0 + __ldg(bias), a1 + __ldg(bias + 1), a2 + __ldg(bias + 2)};
-  if (skip != nullptr) {
-    // upfirdn2d(skip, FIR*4, up=2, pad=(2,1)): even 2k -> .25*s[k-1] + .75*s[k]; odd 2k+1 -> .75*s[k] + .25*s[k+1];
-    // zero (not clamped) outside.
-    const int hh = h >> 1, ww = w >> 1;
-    int ya, yb, xa, xb;
-    float wy0, wy1, wx0, wx1;
-    if (y & 1) { ya = y >> 1; yb = ya + 1; wy0 = 0.75f; wy1 = 0.25f; }
-    else       { yb = y >> 1; ya = yb - 1; wy0 = 0.25f; wy1 = 0.75f; }
-    if (xq & 1) { xa = xq >> 1; xb = xa + 1; wx0 = 0.75f; wx1 = 0.25f; }
-    else        { xb = xq >> 1; xa = xb - 1; wx0 = 0.25f; wx1 = 0.75f; }
-    if (ya < 0) wy0 = 0.f;
-    if (yb >= hh) wy1 = 0.f;
-    if (xa < 0) wx0 = 0.f;
-    if (xb >= ww) wx1 = 0.f;
-    ya = max(ya, 0); yb = min(yb, hh - 1); xa = max(xa, 0); xb = min(xb, ww - 1);
+  const int h = HW / w;
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * kRgbPix);
+  for (int p0 = blockIdx.x * kRgbPix; p0 < p_end; p0 += pstep) {
+    const int p = p0 + pslot;
+    const bool active = p < p_end;
+    const long long pix = (long long)b * HW + (active ? p : p_end - 1);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      const float* sp = skip + ((long long)b * 3 + ch) * hh * ww;
-      o[ch] += wy0 * (wx0 * __ldg(sp + ya * ww + xa) + wx1 * __ldg(sp + ya * ww + xb)) +
-               wy1 * (wx0 * __ldg(sp + yb * ww + xa) + wx1 * __ldg(sp + yb * ww + xb));
+    for (int g = 0; g < G; ++g) {
+      const int c = (g * lanes + sub) * 8;
+      const H8 v = ld8(x + pix * C + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0 += v.v[j] * wm[g][0][j];
+        a1 += v.v[j] * wm[g][1][j];
+        a2 += v.v[j] * wm[g][2][j];
+      }
+      if (xs_out != nullptr && active) {
+        H8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = v.v[j] * sn[g][j];
+        st8(xs_out + pix * C + c, o);
+      }
     }
-  }
+    for (int off = lanes >> 1; off > 0; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (!active || sub != 0) continue;
+    const int y = p / w, xq = p % w;
+    float o[3] = {a0 + __ldg(bias), a1 + __ldg(bias + 1), a2 + __ldg(bias + 2)};
+    if (skip != nullptr) {
+      // upfirdn2d(skip, FIR*4, up=2, pad=(2,1)): even 2k -> .25*s[k-1] + .75*s[k]; odd 2k+1 -> .75*s[k] + .25*s[k+1];
+      // zero (not clamped) outside.
+      const int hh = h >> 1, ww = w >> 1;
+      int ya, yb, xa, xb;
+      float wy0, wy1, wx0, wx1;
+      if (y & 1) { ya = y >> 1; yb = ya + 1; wy0 = 0.75f; wy1 = 0.25f; }
+      else       { yb = y >> 1; ya = yb - 1; wy0 = 0.25f; wy1 = 0.75f; }
+      if (xq & 1) { xa = xq >> 1; xb = xa + 1; wx0 = 0.75f; wx1 = 0.25f; }
+      else        { xb = xq >> 1; xa = xb - 1; wx0 = 0.25f; wx1 = 0.75f; }
+      if (ya < 0) wy0 = 0.f;
+      if (yb >= hh) wy1 = 0.f;
+      if (xa < 0) wx0 = 0.f;
+      if (xb >= ww) wx1 = 0.f;
+      ya = max(ya, 0); yb = min(yb, hh - 1); xa = max(xa, 0); xb = min(xb, ww - 1);
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch) rgb[((long long)b * 3 + ch) * h * w + p] = o[ch];
+      for (int ch = 0; ch < 3; ++ch) {
+        const float* sp = skip + ((long long)b * 3 + ch) * hh * ww;
+        o[ch] += wy0 * (wx0 * __ldg(sp + ya * ww + xa) + wx1 * __ldg(sp + ya * ww + xb)) +
+                 wy1 * (wx0 * __ldg(sp + yb * ww + xa) + wx1 * __ldg(sp + yb * ww + xb));
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) rgb[((long long)b * 3 + ch) * HW + p] = o[ch];
+  }
 }
 
 // ------------------------------------------------------------------------------------------ style path
@@ -313,6 +408,39 @@ __global__ void demod_kernel(const float* __restrict__ s, const float* __restric
   if (lane == 0) d[(long long)b * cout + o] = rsqrtf(scale2 * acc + 1e-8f);
 }
 
+// all modulation linears of a forward in one launch: blockIdx.y = layer, one warp per (b, i)
+__global__ void mod_linear_multi_kernel(const float* __restrict__ latent, int L, int F, const b200ir_mod_layer* layers,
+                                        float wscale, int B) {
+  const b200ir_mod_layer ly = layers[blockIdx.y];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * ly.cin) return;
+  const int b = warp / ly.cin, i = warp % ly.cin;
+  const float* lp = latent + ((long long)b * L + ly.lat_idx) * F;
+  const float* wp = ly.w + (long long)i * F;
+  float acc = 0.f;
+  for (int f = lane; f < F; f += 32) acc += __ldg(wp + f) * __ldg(lp + f);
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) ly.s[(long long)b * ly.cin + i] = acc * wscale + __ldg(ly.bias + i);
+}
+
+__global__ void demod_multi_kernel(const b200ir_demod_layer* layers, int B) {
+  const b200ir_demod_layer ly = layers[blockIdx.y];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * ly.cout) return;
+  const int b = warp / ly.cout, o = warp % ly.cout;
+  const float* sp = ly.s + (long long)b * ly.cin;
+  const float* wp = ly.wsq + (long long)o * ly.cin;
+  float acc = 0.f;
+  for (int i = lane; i < ly.cin; i += 32) {
+    const float sv = __ldg(sp + i);
+    acc += sv * sv * __ldg(wp + i);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) ly.d[(long long)b * ly.cout + o] = rsqrtf(ly.scale2 * acc + 1e-8f);
+}
+
 __global__ void nhwc_to_nchw_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, int B, int P, int C) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * P * C) return;
@@ -341,23 +469,21 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
 extern "C" int b200ir_fir_pad22(const void* in, void* out, int B, int H, int W, int C, int out_h, int out_w,
                                 void* stream) {
   B200IR_REQUIRE(in && out && C % 8 == 0 && out_h >= H + 1 && out_w >= W + 1, "fir_pad22: bad arguments");
-  const long long n = (long long)B * (H + 1) * (W + 1) * (C / 8);
-  fir4_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, H, W, C, H + 1, W + 1, out_h,
-                                                      out_w, 1, 2);
+  const long long n = (long long)B * (H + 1) * ((W + 4) / 4) * (C / 8);
+  fir_pad22_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, H, W, C, out_h, out_w);
   return check_launch("fir_pad22");
 }
 
 extern "C" int b200ir_fir_down2(const void* in, void* out, int B, int H, int W, int C, void* stream) {
   B200IR_REQUIRE(in && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "fir_down2: bad arguments");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
-  fir4_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, H, W, C, H / 2, W / 2, H / 2,
-                                                      W / 2, 2, 1);
+  fir_down2_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, H, W, C);
   return check_launch("fir_down2");
 }
 
 extern "C" int b200ir_bilinear_up2(const void* in, void* out, int B, int h, int w, int C, void* stream) {
   B200IR_REQUIRE(in && out && C % 8 == 0, "bilinear_up2: bad arguments");
-  const long long n = (long long)B * 4 * h * w * (C / 8);
+  const long long n = (long long)B * h * w * (C / 8);
   bilinear_up2_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, h, w, C);
   return check_launch("bilinear_up2");
 }
@@ -376,7 +502,8 @@ extern "C" int b200ir_upfir_act(const void* raw, void* out, int B, int h2, int w
   B200IR_REQUIRE((scale == nullptr) == (shift == nullptr), "upfir_act: scale/shift must come together");
   B200IR_REQUIRE(scale == nullptr || (c_sft % 8 == 0 && c_sft <= C && (C - c_sft) % 8 == 0), "upfir_act: c_sft=%d",
                  c_sft);
-  const long long n = (long long)B * h2 * w2 * (C / 8);
+  B200IR_REQUIRE(w2 % 4 == 0, "upfir_act: w2=%d must be a multiple of 4", w2);
+  const long long n = (long long)B * h2 * (w2 / 4) * (C / 8);
   upfir_act_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)raw, (__half*)out, B, h2, w2, C, raw_h, raw_w,
                                                            noise, noise_stride_b, noise_gain, bias,
                                                            (const __half*)scale, (const __half*)shift, c_sft, s_next);
@@ -394,9 +521,18 @@ extern "C" int b200ir_to_rgb(const void* x, int B, int h, int w, int C, const fl
   int pw = 1;
   while (pw * 2 <= lanes) pw *= 2;
   lanes = pw;
-  const long long n = (long long)B * h * w * lanes;
-  to_rgb_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)x, B, h, w, C, wrgb, s, bias, skip, rgb, s_next,
-                                                        (__half*)xs_out, lanes);
+  const int G = C / (8 * lanes);
+  B200IR_REQUIRE(G * lanes * 8 == C && (G == 1 || G == 2 || G == 3), "to_rgb: C=%d unsupported", C);
+  dim3 grid((h * w + kRgbPix - 1) / kRgbPix, B);
+  if (G == 1)
+    to_rgb_kernel<1><<<grid, kPwThreads, 0, STREAM>>>((const __half*)x, h * w, w, C, wrgb, s, bias, skip, rgb, s_next,
+                                                      (__half*)xs_out, lanes);
+  else if (G == 2)
+    to_rgb_kernel<2><<<grid, kPwThreads, 0, STREAM>>>((const __half*)x, h * w, w, C, wrgb, s, bias, skip, rgb, s_next,
+                                                      (__half*)xs_out, lanes);
+  else
+    to_rgb_kernel<3><<<grid, kPwThreads, 0, STREAM>>>((const __half*)x, h * w, w, C, wrgb, s, bias, skip, rgb, s_next,
+                                                      (__half*)xs_out, lanes);
   return check_launch("to_rgb");
 }
 
@@ -421,6 +557,22 @@ extern "C" int b200ir_demod(const float* s, const float* wsq, float scale2, floa
   const long long n = (long long)B * cout * 32;
   demod_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>(s, wsq, scale2, d, B, cin, cout);
   return check_launch("demod");
+}
+
+extern "C" int b200ir_mod_linear_multi(const float* latent, int L, int F, const b200ir_mod_layer* layers_dev,
+                                       int n_layers, int max_cin, float wscale, int B, void* stream) {
+  B200IR_REQUIRE(latent && layers_dev && n_layers > 0 && max_cin > 0, "mod_linear_multi: bad arguments");
+  dim3 grid(grid_for((long long)B * max_cin * 32), n_layers);
+  mod_linear_multi_kernel<<<grid, kPwThreads, 0, STREAM>>>(latent, L, F, layers_dev, wscale, B);
+  return check_launch("mod_linear_multi");
+}
+
+extern "C" int b200ir_demod_multi(const b200ir_demod_layer* layers_dev, int n_layers, int max_cout, int B,
+                                  void* stream) {
+  B200IR_REQUIRE(layers_dev && n_layers > 0 && max_cout > 0, "demod_multi: bad arguments");
+  dim3 grid(grid_for((long long)B * max_cout * 32), n_layers);
+  demod_multi_kernel<<<grid, kPwThreads, 0, STREAM>>>(layers_dev, B);
+  return check_launch("demod_multi");
 }
 
 extern "C" int b200ir_nhwc_to_nchw_f32(const void* in, float* out, int B, int P, int C, void* stream) {

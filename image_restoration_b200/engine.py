@@ -210,15 +210,16 @@ class _Plan:
         self._hid_keep = None
 
         # ---------------- style modulation vectors and demodulation tables (hoisted: depend on the latent only)
+        mod_layers, demod_layers = [], []
+
         def mod(layer, lat_idx):
             s = e32(B, layer['mod_w'].shape[0])
-            steps.append(lambda l=layer, i=lat(lat_idx), o=s: ops.mod_linear(self.latent, i, l['mod_w'], l['mod_b'],
-                                                                              pk.mod_wscale, o))
+            mod_layers.append((layer['mod_w'], layer['mod_b'], lat(lat_idx), s))
             return s
 
         def dem(layer, s):
             dd = e32(B, layer['cout'])
-            steps.append(lambda l=layer, ss=s, o=dd: ops.demod(ss, l['wsq'], l['scale2'], o))
+            demod_layers.append((s, layer['wsq'], layer['scale2'], dd))
             return dd
 
         s_sc1 = mod(pk.sc1, 0)
@@ -232,6 +233,8 @@ class _Plan:
             s_conv += [s1, s2]
             d_conv += [dem(pk.sconv[2 * lvl], s1), dem(pk.sconv[2 * lvl + 1], s2)]
             s_rgb.append(mod(pk.rgbs[lvl], i + 2))
+        steps.append(ops.ModLinearMulti(self.latent, mod_layers, pk.mod_wscale))
+        steps.append(ops.DemodMulti(demod_layers))
 
         # ---------------- StyleGAN2 decoder with SFT (gfpganv1_ocr_arch.py:108-129)
         self.noise = [None] * (2 * L + 1)   # fp32 [nb,1,h,w] buffers the kernels read; filled per call

@@ -240,6 +240,47 @@ def demod(s, wsq, scale2, d):
     check(_lib.lib().b200ir_demod(_ptr(s), _ptr(wsq), scale2, _ptr(d), b, cin, wsq.shape[0], _stream()), 'demod')
 
 
+def _device_records(records, dev):
+    """ctypes structure array -> device byte tensor (the *_multi kernels read their layer tables from HBM)."""
+    arr = (type(records[0]) * len(records))(*records)
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+
+
+class ModLinearMulti:
+    """All modulation linears of one forward (ModulatedConv2d.modulation, stylegan2_ocr_arch.py:229-234,249) in one
+    launch.  layers: list of (weight [cin,F], bias [cin], lat_idx, s_out [B,cin])."""
+
+    def __init__(self, latent, layers, wscale):
+        self.latent, self.wscale = latent, wscale
+        self.keep = layers
+        recs = [_lib.ModLayer(w.data_ptr(), b.data_ptr(), s.data_ptr(), li, w.shape[0]) for (w, b, li, s) in layers]
+        self.table = _device_records(recs, latent.device)
+        self.n = len(recs)
+        self.max_cin = max(w.shape[0] for (w, _, _, _) in layers)
+
+    def __call__(self):
+        b, L, f = self.latent.shape
+        check(_lib.lib().b200ir_mod_linear_multi(_ptr(self.latent), L, f, _ptr(self.table), self.n, self.max_cin,
+                                                 self.wscale, b, _stream()), 'mod_linear_multi')
+
+
+class DemodMulti:
+    """All demodulation tables of one forward (stylegan2_ocr_arch.py:253-257) in one launch.
+    layers: list of (s [B,cin], wsq [cout,cin], scale2, d_out [B,cout])."""
+
+    def __init__(self, layers):
+        self.keep = layers
+        recs = [_lib.DemodLayer(s.data_ptr(), wsq.data_ptr(), d.data_ptr(), sc2, wsq.shape[1], wsq.shape[0])
+                for (s, wsq, sc2, d) in layers]
+        self.table = _device_records(recs, layers[0][0].device)
+        self.n = len(recs)
+        self.max_cout = max(wsq.shape[0] for (_, wsq, _, _) in layers)
+        self.b = layers[0][0].shape[0]
+
+    def __call__(self):
+        check(_lib.lib().b200ir_demod_multi(_ptr(self.table), self.n, self.max_cout, self.b, _stream()), 'demod_multi')
+
+
 def nhwc_to_nchw_f32(x, out):
     b, h, w, c = x.shape
     check(_lib.lib().b200ir_nhwc_to_nchw_f32(_ptr(x), _ptr(out), b, h * w, c, _stream()), 'nhwc_to_nchw_f32')

@@ -159,6 +159,25 @@ int b200ir_mod_linear(const float* latent, int L, int F, int lat_idx, const floa
  * wsq[o][i] = sum_k W[o][i][k]^2 (fp32). */
 int b200ir_demod(const float* s, const float* wsq, float scale2, float* d, int B, int cin, int cout, void* stream);
 
+/* All modulation linears / demodulation tables of one forward in a single launch each (same arithmetic as
+ * b200ir_mod_linear / b200ir_demod); `layers_dev` is a DEVICE array of n_layers records. */
+typedef struct {
+  const float* w;    /* [cin][F] */
+  const float* bias; /* [cin] */
+  float* s;          /* out [B][cin] */
+  int32_t lat_idx, cin;
+} b200ir_mod_layer;
+typedef struct {
+  const float* s;   /* [B][cin] */
+  const float* wsq; /* [cout][cin] */
+  float* d;         /* out [B][cout] */
+  float scale2;
+  int32_t cin, cout;
+} b200ir_demod_layer;
+int b200ir_mod_linear_multi(const float* latent, int L, int F, const b200ir_mod_layer* layers_dev, int n_layers,
+                            int max_cin, float wscale, int B, void* stream);
+int b200ir_demod_multi(const b200ir_demod_layer* layers_dev, int n_layers, int max_cout, int B, void* stream);
+
 /* NHWC fp16 [B][P][C] -> fp32 matrix [B][P*C] is a reinterpretation; this converts fp32 NCHW image batches to the
  * caller-facing layout when needed: out_nchw[b][c][p] = in_nhwc[b][p][c] (fp16 -> fp32). */
 int b200ir_nhwc_to_nchw_f32(const void* in, float* out, int B, int P, int C, void* stream);

@@ -291,3 +291,28 @@ def test_first_conv():
     ops.first_conv(x, w, bias, out)
     ref = F.leaky_relu(F.conv2d(x, w[:, :, None, None], bias), 0.2) * math.sqrt(2)
     check_close(nchw32(out), ref, what='first_conv')
+
+
+def test_style_path_multi_launch():
+    """All modulation linears / demod tables of a forward in one launch each == the per-layer kernels."""
+    ops = _ops()
+    torch.manual_seed(10)
+    B, L, Fd = 5, 12, 256
+    latent = torch.randn(B, L, Fd, device=DEV)
+    dims = [(512, 512), (512, 3), (128, 64), (64, 64)]
+    mods, dems, refs = [], [], []
+    for j, (cin, cout) in enumerate(dims):
+        wm, bm = torch.randn(cin, Fd, device=DEV), torch.randn(cin, device=DEV)
+        s = torch.empty(B, cin, device=DEV)
+        wsq = torch.rand(cout, cin, device=DEV) * 9
+        d = torch.empty(B, cout, device=DEV)
+        mods.append((wm, bm, j + 2, s))
+        dems.append((s, wsq, 1.0 / (cin * 9), d))
+        sref = latent[:, j + 2] @ wm.t() / math.sqrt(Fd) + bm
+        refs.append((sref, torch.rsqrt(sref.pow(2) @ wsq.t() / (cin * 9) + 1e-8)))
+    ops.ModLinearMulti(latent, mods, 1 / math.sqrt(Fd))()
+    ops.DemodMulti(dems)()
+    torch.cuda.synchronize()
+    for (wm, bm, li, s), (_, _, _, d), (sref, dref) in zip(mods, dems, refs):
+        check_close(s, sref, tol=1e-5, what='mod_linear_multi')
+        check_close(d, dref, tol=1e-4, what='demod_multi')

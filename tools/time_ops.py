@@ -29,6 +29,8 @@ def label(st):
         return (f'conv taps={d.num_taps} {d.cin}->{d.cout} M=({d.m_b},{d.m_h},{d.m_w}) tile=({d.tile_b},{d.tile_h},'
                 f'{d.tile_w}) bn={d.block_n} ep[{"b" if d.bias else ""}{"d" if d.demod else ""}{"n" if d.noise else ""}'
                 f'{"a" if d.act else ""}r{d.res_mode}]')
+    if not hasattr(st, '__code__'):
+        return type(st).__name__
     names = [n for n in st.__code__.co_names if n not in ('ops', 'self', 'shape')]
     t = [v for v in (st.__defaults__ or ()) if torch.is_tensor(v)]
     return f'{names[0] if names else "?"} ' + ' '.join(str(tuple(v.shape)) for v in t[:2])
@@ -56,7 +58,7 @@ for st in plan.steps:
         by = 2.0 * (d.m_b * d.m_h * d.m_w * (d.cin + d.cout))
         extra = f'{fl / ms / 1e9:8.1f} TF/s  {by / ms / 1e6:8.1f} GB/s(in+out)'
     else:
-        t = [v for v in (st.__defaults__ or ()) if torch.is_tensor(v)]
+        t = [v for v in (getattr(st, '__defaults__', None) or ()) if torch.is_tensor(v)]
         by = sum(v.numel() * v.element_size() for v in t)
         extra = f'{"":8s}       {by / ms / 1e6:8.1f} GB/s(listed tensors)'
     rows.append((ms, label(st), extra))
