@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libb200ir.so')
-SOURCES = ['api.cu', 'conv_igemm.cu', 'pointwise.cu', 'degrade.cu']
+SOURCES = ['api.cu', 'conv_igemm.cu', 'pointwise.cu', 'fir_tma.cu', 'degrade.cu']
 HEADERS = ['ptx.cuh', 'host_common.h', 'conv_kernels.cuh', os.path.join('..', '..', 'include', 'b200ir.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v']

@@ -258,8 +258,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                      const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+               const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return 1;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -301,6 +301,8 @@ static int init_device_info() {
 }
 
 int device_check_impl() { return init_device_info(); }
+int num_sms() { return init_device_info() ? 0 : g_num_sms; }
+int smem_optin() { return init_device_info() ? 0 : g_smem_optin; }
 
 }  // namespace b200ir
 

@@ -469,6 +469,16 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
 extern "C" int b200ir_fir_pad22(const void* in, void* out, int B, int H, int W, int C, int out_h, int out_w,
                                 void* stream) {
   B200IR_REQUIRE(in && out && C % 8 == 0 && out_h >= H + 1 && out_w >= W + 1, "fir_pad22: bad arguments");
+  {
+    FirLaunch a = {};
+    a.in = (const __half*)in; a.B = B; a.Hv = H; a.Wv = W;
+    a.in_sw = C; a.in_sh = (long long)W * C; a.in_sb = (long long)H * W * C;
+    a.C = C; a.OH = H + 1; a.OW = W + 1; a.pad = 2; a.kscale = 0.125f;
+    a.out = (__half*)out; a.out_sy = (long long)out_w * C; a.out_sb = (long long)out_h * out_w * C;
+    a.post = false;
+    const int r = fir_stream_launch(a, STREAM, "fir_pad22");
+    if (r >= 0) return r;
+  }
   const long long n = (long long)B * (H + 1) * ((W + 4) / 4) * (C / 8);
   fir_pad22_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, H, W, C, out_h, out_w);
   return check_launch("fir_pad22");
@@ -502,6 +512,18 @@ extern "C" int b200ir_upfir_act(const void* raw, void* out, int B, int h2, int w
   B200IR_REQUIRE((scale == nullptr) == (shift == nullptr), "upfir_act: scale/shift must come together");
   B200IR_REQUIRE(scale == nullptr || (c_sft % 8 == 0 && c_sft <= C && (C - c_sft) % 8 == 0), "upfir_act: c_sft=%d",
                  c_sft);
+  {
+    FirLaunch a = {};
+    a.in = (const __half*)raw; a.B = B; a.Hv = h2 + 1; a.Wv = w2 + 1;
+    a.in_sw = C; a.in_sh = (long long)raw_w * C; a.in_sb = (long long)raw_h * raw_w * C;
+    a.C = C; a.OH = h2; a.OW = w2; a.pad = 1; a.kscale = 0.25f;
+    a.out = (__half*)out; a.out_sy = (long long)w2 * C; a.out_sb = (long long)h2 * w2 * C;
+    a.post = true;
+    a.noise = noise; a.noise_sb = noise_stride_b; a.noise_gain = noise_gain; a.bias = bias;
+    a.scale = (const __half*)scale; a.shift = (const __half*)shift; a.c_sft = c_sft; a.s_next = s_next;
+    const int r = fir_stream_launch(a, STREAM, "upfir_act");
+    if (r >= 0) return r;
+  }
   B200IR_REQUIRE(w2 % 4 == 0, "upfir_act: w2=%d must be a multiple of 4", w2);
   const long long n = (long long)B * h2 * (w2 / 4) * (C / 8);
   upfir_act_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)raw, (__half*)out, B, h2, w2, C, raw_h, raw_w,

@@ -316,3 +316,56 @@ def test_style_path_multi_launch():
     for (wm, bm, li, s), (_, _, _, d), (sref, dref) in zip(mods, dems, refs):
         check_close(s, sref, tol=1e-5, what='mod_linear_multi')
         check_close(d, dref, tol=1e-4, what='demod_multi')
+
+
+@pytest.mark.parametrize('B,h2,w2,C,c_sft,with_noise', [
+    (3, 128, 384, 64, 32, True),     # CC=64 chunk straddles the SFT boundary (32 SFT channels per pixel)
+    (2, 64, 192, 128, 64, True),
+    (2, 32, 96, 512, 256, False),    # OW=96: one output per thread variant
+    (5, 8, 24, 512, 256, True),
+    (2, 16, 48, 32, 16, True),       # 32-channel chunks
+    (2, 40, 72, 64, 64, True),       # sft_half=False: every channel modulated; ragged strips / row chunks
+    (1, 16, 16, 96, 0, True),        # no SFT, C % 64 != 0
+])
+def test_upfir_act_streaming(B, h2, w2, C, c_sft, with_noise):
+    """TMA-fed streaming FIR tail vs upfirdn2d restatement; the unused last row/col of `raw` is poisoned to prove the
+    kernel reads only the (h2+1)x(w2+1) valid samples (zero padding comes from the TMA out-of-bounds fill)."""
+    ops = _ops()
+    torch.manual_seed(11)
+    raw = nhwc16(torch.randn(B, C, h2 + 2, w2 + 2, device=DEV))
+    raw[:, h2 + 1, :, :] = 1000.0
+    raw[:, :, w2 + 1, :] = -1000.0
+    noise = torch.randn(B, 1, h2, w2, device=DEV) if with_noise else None
+    gain = torch.tensor([0.3], device=DEV)
+    bias = torch.randn(C, device=DEV) * 0.1
+    scale = nhwc16(torch.randn(B, c_sft, h2, w2, device=DEV)) if c_sft else None
+    shift = nhwc16(torch.randn(B, c_sft, h2, w2, device=DEV)) if c_sft else None
+    s_next = torch.rand(B, C, device=DEV) + 0.5
+    out = torch.empty(B, h2, w2, C, device=DEV, dtype=torch.float16)
+    ops.upfir_act(raw, out, noise, h2 * w2, gain, bias, scale, shift, c_sft, s_next)
+    torch.cuda.synchronize()
+    y = upfirdn_ref(nchw32(raw)[:, :, :h2 + 1, :w2 + 1], fir_k(DEV) * 4, pad=(1, 1))
+    y = y + bias[None, :, None, None]
+    if with_noise:
+        y = y + gain * noise
+    y = F.leaky_relu(y, 0.2) * math.sqrt(2)
+    keep = C - c_sft
+    if c_sft:
+        y = torch.cat([y[:, :keep], y[:, keep:] * nchw32(scale) + nchw32(shift)], 1)
+    y = y * s_next[:, :, None, None]
+    check_close(nchw32(out), y, what=f'upfir_act streaming C={C} {h2}x{w2}')
+
+
+@pytest.mark.parametrize('B,H,W,C', [(2, 128, 384, 32), (3, 64, 192, 64), (2, 32, 96, 256), (4, 8, 24, 256),
+                                     (1, 20, 36, 64), (2, 16, 16, 16)])
+def test_fir_pad22_streaming(B, H, W, C):
+    ops = _ops()
+    torch.manual_seed(12)
+    xh = nhwc16(torch.randn(B, C, H, W, device=DEV))
+    p = torch.full((B, H + 2, W + 2, C), 7.0, device=DEV, dtype=torch.float16)
+    ops.fir_pad22(xh, p)
+    torch.cuda.synchronize()
+    pref = upfirdn_ref(nchw32(xh), fir_k(DEV), pad=(2, 2))
+    got = nchw32(p)
+    check_close(got[:, :, :H + 1, :W + 1], pref, what=f'fir_pad22 streaming C={C} {H}x{W}')
+    assert (got[:, :, H + 1] == 7.0).all() and (got[:, :, :, W + 1] == 7.0).all()   # nothing written past (H+1)x(W+1)
