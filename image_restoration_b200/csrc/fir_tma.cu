@@ -12,6 +12,7 @@
 // warps run the separable filter: one horizontal pass per input row out of shared memory (128-bit, conflict-free), the
 // vertical pass over a register window of the last 4 filtered rows.  Every input element is read from L2/HBM once per
 // item (+3 halo rows per R), every output written once with 128-bit stores.
+#include <stdlib.h>
 #include <string.h>
 
 #include "host_common.h"
@@ -19,8 +20,6 @@
 
 namespace b200ir {
 
-static constexpr int kFirConsumers = 256;
-static constexpr int kFirThreads = kFirConsumers + 32;
 static constexpr int kFirMaxStages = 8;
 
 struct alignas(64) FirParams {
@@ -68,13 +67,21 @@ __device__ __forceinline__ FirItem fir_decode(const FirParams& p, int item) {
   return t;
 }
 
-// CC: channels per chunk (TMA box inner extent); XP: horizontally adjacent outputs per thread; SR: input rows per stage
-template <int CC, int XP, int SR, bool POST>
-__global__ void __launch_bounds__(kFirThreads, 1) fir_stream_kernel(const __grid_constant__ FirParams p) {
+// horizontally filtered row (unscaled taps 1,3,3,1) of this thread's XP outputs x 8 channels
+template <int XP>
+struct FirRow {
+  float v[XP][8];
+};
+
+// CC: channels per chunk (TMA box inner extent); XP: horizontally adjacent outputs per thread; SR: input rows per stage;
+// NT: consumer threads.  SFT (when present) is uniform per chunk: the host requires c_keep % CC == 0.
+template <int CC, int XP, int SR, int NT, bool POST>
+__global__ void __launch_bounds__(NT + 32, (NT == 256 && !(POST && XP == 2)) ? 2 : 1) fir_stream_kernel(const __grid_constant__ FirParams p) {
   constexpr int CG = CC / 8;
-  constexpr int XQ = kFirConsumers / CG;
+  constexpr int XQ = NT / CG;
   constexpr int TW = XQ * XP;
   constexpr int IW = TW + 3;
+  static_assert(SR == 2 || SR == 4, "the register window rotates with period 4");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad_bytes = ((raw_addr + 127u) & ~127u) - raw_addr;
@@ -85,16 +92,16 @@ __global__ void __launch_bounds__(kFirThreads, 1) fir_stream_kernel(const __grid
   if (tid == 0) {
     for (int i = 0; i < p.NS; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], kFirConsumers);
+      mbar_init(&empty_bar[i], NT);
     }
     fence_barrier_init();
   }
   __syncthreads();
   const int my_items = (p.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (tid >= kFirConsumers) {
+  if (tid >= NT) {
     // ---------------- producer warp
-    if (tid == kFirConsumers) {
+    if (tid == NT) {
       tma_prefetch_desc(&p.tmap_in);
       if (POST && p.has_sft) {
         tma_prefetch_desc(&p.tmap_scale);
@@ -105,8 +112,7 @@ __global__ void __launch_bounds__(kFirThreads, 1) fir_stream_kernel(const __grid
       for (int it = 0; it < my_items; ++it) {
         const FirItem t = fir_decode(p, blockIdx.x + it * gridDim.x);
         const int c0 = t.chunk * CC;
-        const bool sft = POST && p.has_sft && (c0 + CC > p.c_keep);
-        const int cs0 = max(c0, p.c_keep) - p.c_keep;
+        const bool sft = POST && p.has_sft && (c0 >= p.c_keep);
         const uint32_t bytes = p.in_bytes + (sft ? 2 * p.sft_bytes : 0);
         for (int k = 0; k < p.KS; ++k) {
           mbar_wait(&empty_bar[slot], phase ^ 1u);
@@ -114,8 +120,9 @@ __global__ void __launch_bounds__(kFirThreads, 1) fir_stream_kernel(const __grid
           mbar_arrive_expect_tx(&full_bar[slot], bytes);
           tma_load_4d(st, &p.tmap_in, &full_bar[slot], c0, t.strip * TW - p.pad, t.y0 - p.pad + k * SR, t.b);
           if (sft) {
-            tma_load_4d(st + p.in_bytes, &p.tmap_scale, &full_bar[slot], cs0, t.strip * TW, t.y0 + k * SR - 3, t.b);
-            tma_load_4d(st + p.in_bytes + p.sft_bytes, &p.tmap_shift, &full_bar[slot], cs0, t.strip * TW,
+            tma_load_4d(st + p.in_bytes, &p.tmap_scale, &full_bar[slot], c0 - p.c_keep, t.strip * TW,
+                        t.y0 + k * SR - 3, t.b);
+            tma_load_4d(st + p.in_bytes + p.sft_bytes, &p.tmap_shift, &full_bar[slot], c0 - p.c_keep, t.strip * TW,
                         t.y0 + k * SR - 3, t.b);
           }
           if (++slot == p.NS) {
@@ -132,100 +139,80 @@ __global__ void __launch_bounds__(kFirThreads, 1) fir_stream_kernel(const __grid
   const int cg = tid % CG;
   const int xq = tid / CG;
   const int xl = xq * XP;  // first output column of this thread inside the strip
-  const uint32_t base_addr = smem_u32(base);
-  float win[3][XP][8];  // horizontally filtered rows y-3, y-2, y-1 (unscaled taps 1,3,3,1)
+  const uint32_t thr_in = smem_u32(base) + (xl * CC + cg * 8) * 2;       // this thread's first input pixel, row 0
+  const uint32_t thr_sft = smem_u32(base) + p.in_bytes + (xl * CC + cg * 8) * 2;
+  FirRow<XP> w0, w1, w2, w3;  // rotating window of the last four horizontally filtered rows
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+  for (int j = 0; j < XP; ++j)
 #pragma unroll
-    for (int j = 0; j < XP; ++j)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) win[a][j][e] = 0.f;
+    for (int e = 0; e < 8; ++e) w0.v[j][e] = w1.v[j][e] = w2.v[j][e] = w3.v[j][e] = 0.f;
   const float gain = (POST && p.noise != nullptr) ? __ldg(p.noise_gain) * 1.4142135623730951f : 0.f;
+  const float ks2 = p.kscale2;
   int slot = 0;
   uint32_t phase = 0;
+  int g = 0;  // stages consumed so far (window rotation phase for SR == 2)
   for (int it = 0; it < my_items; ++it) {
     const FirItem t = fir_decode(p, blockIdx.x + it * gridDim.x);
     const int c0 = t.chunk * CC;
     const int c = c0 + cg * 8;
     const int x0 = t.strip * TW + xl;
     const int y_end = min(t.y0 + p.R, p.OH);
+    bool xv[XP];
+#pragma unroll
+    for (int j = 0; j < XP; ++j) xv[j] = x0 + j < p.OW;
     float bs[8], sn[8];
-    bool sft = false;
-    uint32_t sft_off = 0;  // byte offset of this thread's 8 channels inside a scale/shift pixel
-    uint32_t sft_pix = 0;  // bytes per scale/shift pixel in shared memory
+    const bool sft = POST && p.has_sft && (c0 >= p.c_keep);
     if (POST) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         bs[e] = __ldg(p.bias + c + e) * 1.4142135623730951f;
         sn[e] = (p.s_next != nullptr) ? __ldg(p.s_next + (long long)t.b * p.C + c + e) : 1.f;
       }
-      if (p.has_sft && c >= p.c_keep) {
-        sft = true;
-        sft_off = (uint32_t)(c - max(c0, p.c_keep)) * 2u;
-        sft_pix = (uint32_t)(c0 + CC - max(c0, p.c_keep)) * 2u;
-      }
     }
-    __half* out_b = p.out + (long long)t.b * p.out_sb + c;
-    for (int k = 0; k < p.KS; ++k) {
+    // row pointers advance by one output row per input row; the first three rows of an item only prime the window
+    __half* out_row = p.out + (long long)t.b * p.out_sb + (long long)(t.y0 - 3) * p.out_sy + (long long)x0 * p.C + c;
+    const float* nz_row = (POST && p.noise != nullptr) ? p.noise + t.b * p.noise_sb + (long long)(t.y0 - 3) * p.OW + x0
+                                                       : nullptr;
+    int oy = t.y0 - 3;
+    for (int k = 0; k < p.KS; ++k, ++g) {
       // noise of the output rows this stage completes (independent of the TMA data: fetched before the wait)
       float nz[SR][XP];
-      if (POST) {
 #pragma unroll
-        for (int r = 0; r < SR; ++r) {
-          const int oy = t.y0 + k * SR + r - 3;
+      for (int r = 0; r < SR; ++r)
 #pragma unroll
-          for (int j = 0; j < XP; ++j) {
-            nz[r][j] = 0.f;
-            if (p.noise != nullptr && oy >= t.y0 && oy < y_end && x0 + j < p.OW)
-              nz[r][j] = gain * __ldg(p.noise + t.b * p.noise_sb + (long long)oy * p.OW + x0 + j);
-          }
+        for (int j = 0; j < XP; ++j) {
+          nz[r][j] = 0.f;
+          if (POST && nz_row != nullptr && oy + r >= t.y0 && oy + r < y_end && xv[j])
+            nz[r][j] = gain * __ldg(nz_row + (long long)r * p.OW + j);
         }
-      }
       mbar_wait(&full_bar[slot], phase);
-      const uint32_t st = base_addr + slot * p.stage_bytes;
+      const uint32_t st_off = slot * p.stage_bytes;
+
+      // one input row: horizontal pass into D, then (if the output row exists) vertical pass over A, B, C, D
+      auto do_row = [&](const FirRow<XP>& A, const FirRow<XP>& B, const FirRow<XP>& C, FirRow<XP>& D, int r) {
+        float f[XP + 3][8];
 #pragma unroll
-      for (int r = 0; r < SR; ++r) {
-        // horizontal pass of input row r: taps (1,3,3,1) over columns xl + j .. xl + j + 3
-        float h[XP][8];
+        for (int col = 0; col < XP + 3; ++col) unpack8(lds128(thr_in + st_off + (r * IW + col) * CC * 2), f[col]);
 #pragma unroll
         for (int j = 0; j < XP; ++j)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) h[j][e] = 0.f;
-        const uint32_t row_addr = st + ((r * IW + xl) * CC + cg * 8) * 2;
-#pragma unroll
-        for (int col = 0; col < XP + 3; ++col) {
-          const uint4 q = lds128(row_addr + col * CC * 2);
-          float f[8];
-          unpack8(q, f);
+          for (int e = 0; e < 8; ++e) D.v[j][e] = fmaf(3.f, f[j + 1][e] + f[j + 2][e], f[j][e] + f[j + 3][e]);
+        const int y = oy + r;
+        if (y >= t.y0 && y < y_end) {
 #pragma unroll
           for (int j = 0; j < XP; ++j) {
-            const int tap = col - j;
-            if (tap == 0 || tap == 3) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) h[j][e] += f[e];
-            } else if (tap == 1 || tap == 2) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) h[j][e] = fmaf(3.f, f[e], h[j][e]);
-            }
-          }
-        }
-        const int oy = t.y0 + k * SR + r - 3;
-        if (oy >= t.y0 && oy < y_end) {
-#pragma unroll
-          for (int j = 0; j < XP; ++j) {
-            if (x0 + j < p.OW) {
+            if (xv[j]) {
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                v[e] = ((win[0][j][e] + h[j][e]) + 3.f * (win[1][j][e] + win[2][j][e])) * p.kscale2;
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(3.f, B.v[j][e] + C.v[j][e], A.v[j][e] + D.v[j][e]);
               if (POST) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  const float a = v[e] + (nz[r][j] + bs[e]);  // kscale2 / noise / bias carry the sqrt(2) gain
+                  const float a = fmaf(v[e], ks2, nz[r][j] + bs[e]);  // ks2 / noise / bias carry the sqrt(2) gain
                   v[e] = fmaxf(a, 0.2f * a);
                 }
                 if (sft) {
-                  const uint32_t sa = st + p.in_bytes + (r * TW + xl + j) * sft_pix + sft_off;
+                  const uint32_t sa = thr_sft + st_off + ((r * TW + j) * CC) * 2;
                   float sc[8], sh[8];
                   unpack8(lds128(sa), sc);
                   unpack8(lds128(sa + p.sft_bytes), sh);
@@ -234,37 +221,47 @@ __global__ void __launch_bounds__(kFirThreads, 1) fir_stream_kernel(const __grid
                 }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] *= sn[e];
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] *= ks2;
               }
               uint4 o;
               __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
               for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-              *reinterpret_cast<uint4*>(out_b + (long long)oy * p.out_sy + (long long)(x0 + j) * p.C) = o;
+              *reinterpret_cast<uint4*>(out_row + (long long)r * p.out_sy + (long long)j * p.C) = o;
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < XP; ++j)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            win[0][j][e] = win[1][j][e];
-            win[1][j][e] = win[2][j][e];
-            win[2][j][e] = h[j][e];
-          }
+      };
+      if (SR == 4) {
+        do_row(w0, w1, w2, w3, 0);
+        do_row(w1, w2, w3, w0, 1);
+        do_row(w2, w3, w0, w1, 2);
+        do_row(w3, w0, w1, w2, 3);
+      } else if (g & 1) {
+        do_row(w2, w3, w0, w1, 0);
+        do_row(w3, w0, w1, w2, 1);
+      } else {
+        do_row(w0, w1, w2, w3, 0);
+        do_row(w1, w2, w3, w0, 1);
       }
       mbar_arrive(&empty_bar[slot]);
       if (++slot == p.NS) {
         slot = 0;
         phase ^= 1u;
       }
+      oy += SR;
+      out_row += (long long)SR * p.out_sy;
+      if (nz_row != nullptr) nz_row += (long long)SR * p.OW;
     }
   }
 }
 
-
-template <int CC, int XP, int SR, bool POST>
+template <int CC, int XP, int SR, int NT, bool POST>
 static int fir_launch_variant(const FirLaunch& a, cudaStream_t st, const char* what) {
-  constexpr int CG = CC / 8, XQ = kFirConsumers / CG, TW = XQ * XP, IW = TW + 3;
+  constexpr int CG = CC / 8, XQ = NT / CG, TW = XQ * XP, IW = TW + 3;
+  constexpr int kThreads = NT + 32;
   FirParams p;
   memset(&p, 0, sizeof(p));
   p.B = a.B; p.OH = a.OH; p.OW = a.OW; p.C = a.C; p.pad = a.pad;
@@ -273,6 +270,7 @@ static int fir_launch_variant(const FirLaunch& a, cudaStream_t st, const char* w
   const int sms = num_sms();
   if (sms == 0) return 1;
   int R = 32;
+  if (const char* e = getenv("B200IR_FIR_R")) R = atoi(e) > 0 ? atoi(e) : R;
   while (R > 8 && (long long)a.B * p.strips * p.chunks * ((a.OH + R - 1) / R) < 4LL * sms) R /= 2;
   if (R > a.OH) R = a.OH;
   p.R = R;
@@ -283,12 +281,9 @@ static int fir_launch_variant(const FirLaunch& a, cudaStream_t st, const char* w
   static_assert((SR * IW * CC * 2) % 128 == 0, "stage sub-buffers must stay 128-byte aligned");
   p.has_sft = (POST && a.scale != nullptr) ? 1 : 0;
   p.c_keep = a.C - a.c_sft;
-  int cs = 0;
   if (p.has_sft) {
-    cs = a.c_sft < CC ? a.c_sft : CC;
-    B200IR_REQUIRE(a.c_sft % cs == 0 && p.c_keep % cs == 0 && (cs * 2) % 16 == 0, "%s: c_sft=%d unsupported (C=%d)",
-                   what, a.c_sft, a.C);
-    p.sft_bytes = SR * TW * cs * 2;
+    B200IR_REQUIRE(a.c_sft % CC == 0 && p.c_keep % CC == 0, "%s: c_sft=%d unsupported (C=%d)", what, a.c_sft, a.C);
+    p.sft_bytes = SR * TW * CC * 2;
   }
   p.stage_bytes = p.in_bytes + 2 * p.sft_bytes;
   const int smem_max = smem_optin();
@@ -300,8 +295,8 @@ static int fir_launch_variant(const FirLaunch& a, cudaStream_t st, const char* w
   if (ns >= 4) {
     const int ns2 = ns / 2 > 4 ? 4 : ns / 2;
     int occ = 0;
-    cudaFuncSetAttribute(fir_stream_kernel<CC, XP, SR, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fir_stream_kernel<CC, XP, SR, POST>, kFirThreads,
+    cudaFuncSetAttribute(fir_stream_kernel<CC, XP, SR, NT, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fir_stream_kernel<CC, XP, SR, NT, POST>, kThreads,
                                                       ns2 * p.stage_bytes + 256 + 128) == cudaSuccess && occ >= 2) {
       ns = ns2;
       ctas_per_sm = 2;
@@ -321,14 +316,14 @@ static int fir_launch_variant(const FirLaunch& a, cudaStream_t st, const char* w
     cuuint64_t dims[4] = {(cuuint64_t)a.c_sft, (cuuint64_t)a.OW, (cuuint64_t)a.OH, (cuuint64_t)a.B};
     cuuint64_t strides[3] = {(cuuint64_t)a.c_sft * 2, (cuuint64_t)a.OW * a.c_sft * 2,
                              (cuuint64_t)a.OH * a.OW * a.c_sft * 2};
-    cuuint32_t box[4] = {(cuuint32_t)cs, (cuuint32_t)TW, (cuuint32_t)SR, 1u};
+    cuuint32_t box[4] = {(cuuint32_t)CC, (cuuint32_t)TW, (cuuint32_t)SR, 1u};
     if (encode_map(&p.tmap_scale, a.scale, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, what)) return 1;
     if (encode_map(&p.tmap_shift, a.shift, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, what)) return 1;
   }
   const int smem_bytes = p.NS * p.stage_bytes + 256 + 128;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fir_stream_kernel<CC, XP, SR, POST>,
+    cudaError_t e = cudaFuncSetAttribute(fir_stream_kernel<CC, XP, SR, NT, POST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
@@ -338,30 +333,50 @@ static int fir_launch_variant(const FirLaunch& a, cudaStream_t st, const char* w
   }
   int grid = ctas_per_sm * sms;
   if (grid > p.num_items) grid = p.num_items;
-  fir_stream_kernel<CC, XP, SR, POST><<<grid, kFirThreads, smem_bytes, st>>>(p);
+  fir_stream_kernel<CC, XP, SR, NT, POST><<<grid, kThreads, smem_bytes, st>>>(p);
   return check_launch(what);
 }
 
-// strips * TW / OW: fraction of the x slots that fall on real outputs (inverse); smaller is better
+// strips * TW / OW: x slots per real output; smaller is better
 static inline double fir_waste(int ow, int tw) { return (double)((ow + tw - 1) / tw) * tw / ow; }
+
+template <int CC, bool POST>
+static int fir_dispatch(const FirLaunch& a, cudaStream_t st, const char* what) {
+  // candidates: (XP, NT) -> TW = NT / (CC/8) * XP; POST stages carry scale/shift tiles, so they use SR = 2 when XP = 2
+  constexpr int CG = CC / 8;
+  int force_xp = 0, force_nt = 0;
+  if (const char* e = getenv("B200IR_FIR_XP")) force_xp = atoi(e);
+  if (const char* e = getenv("B200IR_FIR_NT")) force_nt = atoi(e);
+  int best_xp = 0, best_nt = 0;
+  double best = 1e30;
+  for (int nt = 384; nt >= 256; nt -= 128)
+    for (int xp = 2; xp >= 1; --xp) {
+      if ((force_xp && xp != force_xp) || (force_nt && nt != force_nt)) continue;
+      // preference at equal waste: more consumer warps, then two outputs per thread (fewer conversions per output)
+      const double w = fir_waste(a.OW, nt / CG * xp);
+      if (w < best - 1e-9) {
+        best = w;
+        best_xp = xp;
+        best_nt = nt;
+      }
+    }
+  if (best_nt == 384)
+    return best_xp == 2 ? fir_launch_variant<CC, 2, POST ? 2 : 4, 384, POST>(a, st, what)
+                        : fir_launch_variant<CC, 1, 4, 384, POST>(a, st, what);
+  return best_xp == 2 ? fir_launch_variant<CC, 2, POST ? 2 : 4, 256, POST>(a, st, what)
+                      : fir_launch_variant<CC, 1, 4, 256, POST>(a, st, what);
+}
 
 // returns -1 when the shape is not eligible for the streaming kernels (caller falls back to the direct kernels)
 int fir_stream_launch(const FirLaunch& a, cudaStream_t st, const char* what) {
   if (a.C % 32 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || a.in_sw % 8 || a.in_sh % 8 || a.in_sb % 8)
     return -1;
-  if (a.post && a.scale != nullptr) {
-    const int cc = (a.C % 64 == 0) ? 64 : 32;
-    const int cs = a.c_sft < cc ? a.c_sft : cc;
-    if (cs <= 0 || a.c_sft % cs || (a.C - a.c_sft) % cs || cs % 8) return -1;
-  }
-  if (a.C % 64 == 0) {
-    const bool xp2 = fir_waste(a.OW, 64) <= fir_waste(a.OW, 32);
-    if (a.post) return xp2 ? fir_launch_variant<64, 2, 2, true>(a, st, what) : fir_launch_variant<64, 1, 4, true>(a, st, what);
-    return xp2 ? fir_launch_variant<64, 2, 4, false>(a, st, what) : fir_launch_variant<64, 1, 4, false>(a, st, what);
-  }
-  const bool xp2 = fir_waste(a.OW, 128) <= fir_waste(a.OW, 64);
-  if (a.post) return xp2 ? fir_launch_variant<32, 2, 2, true>(a, st, what) : fir_launch_variant<32, 1, 4, true>(a, st, what);
-  return xp2 ? fir_launch_variant<32, 2, 4, false>(a, st, what) : fir_launch_variant<32, 1, 4, false>(a, st, what);
+  const bool sft = a.post && a.scale != nullptr;
+  if (sft && (a.c_sft % 32 != 0 || (a.C - a.c_sft) % 32 != 0)) return -1;
+  // 64-channel chunks unless the SFT boundary (or C) only aligns to 32: SFT must be uniform per chunk
+  const bool cc64 = a.C % 64 == 0 && (!sft || (a.c_sft % 64 == 0 && (a.C - a.c_sft) % 64 == 0));
+  if (cc64) return a.post ? fir_dispatch<64, true>(a, st, what) : fir_dispatch<64, false>(a, st, what);
+  return a.post ? fir_dispatch<32, true>(a, st, what) : fir_dispatch<32, false>(a, st, what);
 }
 
 }  // namespace b200ir
