@@ -32,6 +32,8 @@ class ConvDesc(C.Structure):
         ('res_stride_x', C.c_int64), ('res_stride_y', C.c_int64), ('res_stride_b', C.c_int64),
         ('res_w', C.c_int32), ('res_h', C.c_int32), ('res_scale', C.c_float), ('max_ctas', C.c_int32),
         ('row_mode', C.c_int32),
+        ('out_scale', C.c_void_p), ('rgb_w', C.c_void_p), ('rgb_part', C.c_void_p),
+        ('rgb_w_px', C.c_int32), ('rgb_h', C.c_int32), ('no_store', C.c_int32),
     ]
 
 
@@ -60,6 +62,8 @@ SIGNATURES = {
     'b200ir_add': [_P, _P, _P, _L, _P],
     'b200ir_upfir_act': [_P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P, _P, _P, _I, _P, _P],
     'b200ir_to_rgb': [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    'b200ir_rgb_combine': [_P, _I, _P, _P, _P, _I, _I, _I, _P],
+    'b200ir_rgb_wmod': [_P, _P, _P, _I, _I, _P],
     'b200ir_modulate_const': [_P, _P, _P, _I, _I, _I, _P],
     'b200ir_mod_linear': [_P, _I, _I, _I, _P, _P, _F, _P, _I, _I, _P],
     'b200ir_demod': [_P, _P, _F, _P, _I, _I, _I, _P],

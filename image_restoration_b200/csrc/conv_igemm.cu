@@ -59,6 +59,12 @@ struct alignas(64) ConvParams {
   long long res_sx, res_sy, res_sb;
   int res_w, res_h;
   float res_scale;
+  const float* out_scale;
+  const float* rgb_w;
+  float* rgb_part;
+  long long rgb_plane, rgb_image;  // rgb_h*rgb_w_px, m_b*3*rgb_plane
+  int rgb_w_px;
+  int no_store;
 };
 
 struct TileCoord {
@@ -94,6 +100,9 @@ __device__ __forceinline__ void unpack_half8(const uint4& q, float* f) {
 // ready so that none of it sits on the MMA -> epilogue critical path.
 struct EpiRow {
   long long out_off;
+  long long chan_off;  // b * cout + n0: row of the per-image tables (out_scale)
+  long long rgbw_off;  // b * 3 * cout + n0
+  long long rgb_off;   // offset of (n-tile, b, 0, yo, xo) in rgb_part
   float nz;
   const __half* r00;
   const __half* r01;
@@ -107,6 +116,9 @@ __device__ __forceinline__ EpiRow epi_setup(const ConvParams& p, int x, int y, i
   const int xo = x * p.out_x_mul + p.out_x_off;
   const int yo = y * p.out_y_mul + p.out_y_off;
   r.out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx + p.out_c_off + n0;
+  r.chan_off = (long long)b * p.cout + n0;
+  r.rgbw_off = (long long)b * 3 * p.cout + n0;
+  r.rgb_off = (long long)(n0 / p.block_n) * p.rgb_image + (long long)b * 3 * p.rgb_plane + (long long)yo * p.rgb_w_px + xo;
   r.nz = 0.f;
   if (valid && p.noise != nullptr) r.nz = gain * __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);  // gain includes act_gain
   r.r00 = r.r01 = r.r10 = r.r11 = nullptr;
@@ -142,6 +154,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                                               const float* s_demod, const float* g_demod, int c_begin, int c_step) {
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
+  float rgb_acc[3] = {0.f, 0.f, 0.f};
   for (int c0 = c_begin; c0 < p.block_n; c0 += c_step) {
     uint32_t raw[16];
     tmem_ld16(taddr + c0, raw);
@@ -208,7 +221,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
           v[j] = (v[j] + up) * p.res_scale;
         }
       }
-      if (p.out_fp32) {
+      if (p.rgb_w != nullptr) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const float4* wp = reinterpret_cast<const float4*>(p.rgb_w + r.rgbw_off + (long long)o * p.cout + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 w4 = __ldg(wp + j);
+            rgb_acc[o] = fmaf(v[4 * j], w4.x, rgb_acc[o]);
+            rgb_acc[o] = fmaf(v[4 * j + 1], w4.y, rgb_acc[o]);
+            rgb_acc[o] = fmaf(v[4 * j + 2], w4.z, rgb_acc[o]);
+            rgb_acc[o] = fmaf(v[4 * j + 3], w4.w, rgb_acc[o]);
+          }
+        }
+      }
+      if (p.out_scale != nullptr) {
+        const float4* sp = reinterpret_cast<const float4*>(p.out_scale + r.chan_off + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 s4 = __ldg(sp + j);
+          v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+        }
+      }
+      if (p.no_store) {
+      } else if (p.out_fp32) {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r.out_off + c0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -230,6 +266,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
         }
       }
     }
+  }
+  if (p.rgb_w != nullptr && valid) {
+#pragma unroll
+    for (int o = 0; o < 3; ++o) p.rgb_part[r.rgb_off + o * p.rgb_plane] = rgb_acc[o];
   }
 }
 
@@ -332,12 +372,15 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
                  "conv_igemm: block_n=%d invalid for cout=%d", d->block_n, d->cout);
   B200IR_REQUIRE(d->num_taps >= 1 && d->num_taps <= B200IR_MAX_TAPS, "conv_igemm: num_taps=%d", d->num_taps);
   B200IR_REQUIRE(d->num_views >= 1 && d->num_views <= B200IR_MAX_VIEWS, "conv_igemm: num_views=%d", d->num_views);
-  B200IR_REQUIRE(d->out != nullptr && d->weight != nullptr, "conv_igemm: null out/weight");
+  B200IR_REQUIRE((d->out != nullptr || d->no_store) && d->weight != nullptr, "conv_igemm: null out/weight");
   B200IR_REQUIRE(d->m_w > 0 && d->m_h > 0 && d->m_b > 0, "conv_igemm: empty M extents");
   B200IR_REQUIRE((d->out_c_off % 8) == 0 && (d->out_stride_x % 8) == 0, "conv_igemm: output not 16B aligned");
   B200IR_REQUIRE(d->res_mode >= 0 && d->res_mode <= 2, "conv_igemm: res_mode");
   B200IR_REQUIRE(d->res_mode == 0 || d->res != nullptr, "conv_igemm: res_mode set but res is NULL");
   B200IR_REQUIRE(d->noise == nullptr || d->noise_gain != nullptr, "conv_igemm: noise without noise_gain");
+  B200IR_REQUIRE(d->rgb_w == nullptr || (d->rgb_part != nullptr && d->rgb_w_px > 0 && d->rgb_h > 0),
+                 "conv_igemm: rgb_w needs rgb_part and the plane extents");
+  B200IR_REQUIRE(!d->no_store || d->rgb_w != nullptr, "conv_igemm: no_store without a fused ToRGB leaves no output");
 
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -415,6 +458,9 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   p.act = d->act; p.act_gain = d->act ? 1.4142135623730951f : 1.f; p.res_mode = d->res_mode; p.res = reinterpret_cast<const __half*>(d->res);
   p.res_sx = d->res_stride_x; p.res_sy = d->res_stride_y; p.res_sb = d->res_stride_b;
   p.res_w = d->res_w; p.res_h = d->res_h; p.res_scale = d->res_scale;
+  p.out_scale = d->out_scale; p.rgb_w = d->rgb_w; p.rgb_part = d->rgb_part; p.no_store = d->no_store;
+  p.rgb_w_px = d->rgb_w_px; p.rgb_plane = (long long)d->rgb_h * d->rgb_w_px;
+  p.rgb_image = (long long)d->m_b * 3 * p.rgb_plane;
 
   // ---- row mode eligibility: plain 3x3 stride-1 conv on one view, 128-pixel row tiles, weights fit in smem
   {

@@ -357,6 +357,58 @@ __global__ void to_rgb_kernel(const __half* __restrict__ x, int HW, int w, int C
   }
 }
 
+// second half of the fused ToRGB: bias + partial planes written by the conv epilogues + up-sampled skip
+__global__ void rgb_combine_kernel(const float* __restrict__ part, int n_parts, const float* __restrict__ bias,
+                                   const float* __restrict__ skip, float* __restrict__ rgb, int B, int h, int w) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long HW = (long long)h * w;
+  if (idx >= B * HW) return;
+  const int b = (int)(idx / HW);
+  const int p = (int)(idx % HW);
+  const int y = p / w, xq = p % w;
+  float o[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float a = 0.f;
+    for (int t = 0; t < n_parts; ++t) a += __ldg(part + (((long long)t * B + b) * 3 + ch) * HW + p);
+    o[ch] = a + __ldg(bias + ch);
+  }
+  if (skip != nullptr) {
+    // upfirdn2d(skip, FIR*4, up=2, pad=(2,1)): even 2k -> .25*s[k-1] + .75*s[k]; odd 2k+1 -> .75*s[k] + .25*s[k+1];
+    // zero (not clamped) outside.
+    const int hh = h >> 1, ww = w >> 1;
+    int ya, yb, xa, xb;
+    float wy0, wy1, wx0, wx1;
+    if (y & 1) { ya = y >> 1; yb = ya + 1; wy0 = 0.75f; wy1 = 0.25f; }
+    else       { yb = y >> 1; ya = yb - 1; wy0 = 0.25f; wy1 = 0.75f; }
+    if (xq & 1) { xa = xq >> 1; xb = xa + 1; wx0 = 0.75f; wx1 = 0.25f; }
+    else        { xb = xq >> 1; xa = xb - 1; wx0 = 0.25f; wx1 = 0.75f; }
+    if (ya < 0) wy0 = 0.f;
+    if (yb >= hh) wy1 = 0.f;
+    if (xa < 0) wx0 = 0.f;
+    if (xb >= ww) wx1 = 0.f;
+    ya = max(ya, 0); yb = min(yb, hh - 1); xa = max(xa, 0); xb = min(xb, ww - 1);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float* sp = skip + ((long long)b * 3 + ch) * hh * ww;
+      o[ch] += wy0 * (wx0 * __ldg(sp + ya * ww + xa) + wx1 * __ldg(sp + ya * ww + xb)) +
+               wy1 * (wx0 * __ldg(sp + yb * ww + xa) + wx1 * __ldg(sp + yb * ww + xb));
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) rgb[((long long)b * 3 + ch) * HW + p] = o[ch];
+}
+
+__global__ void rgb_wmod_kernel(const float* __restrict__ w, const float* __restrict__ s, float* __restrict__ wm, int B,
+                                int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 3 * C) return;
+  const int c = idx % C;
+  const int o = (idx / C) % 3;
+  const int b = idx / (3 * C);
+  wm[idx] = __ldg(w + o * C + c) * (s != nullptr ? __ldg(s + (long long)b * C + c) : 1.f);
+}
+
 // ------------------------------------------------------------------------------------------ style path
 __global__ void modulate_const_kernel(const __half* __restrict__ cst, const float* __restrict__ s,
                                       __half* __restrict__ out, int B, int P, int C) {
@@ -556,6 +608,20 @@ extern "C" int b200ir_to_rgb(const void* x, int B, int h, int w, int C, const fl
     to_rgb_kernel<3><<<grid, kPwThreads, 0, STREAM>>>((const __half*)x, h * w, w, C, wrgb, s, bias, skip, rgb, s_next,
                                                       (__half*)xs_out, lanes);
   return check_launch("to_rgb");
+}
+
+extern "C" int b200ir_rgb_combine(const float* part, int n_parts, const float* bias, const float* skip, float* rgb,
+                                  int B, int h, int w, void* stream) {
+  B200IR_REQUIRE(part && bias && rgb && n_parts >= 1 && (skip == nullptr || (h % 2 == 0 && w % 2 == 0)),
+                 "rgb_combine: bad arguments");
+  rgb_combine_kernel<<<grid_for((long long)B * h * w), kPwThreads, 0, STREAM>>>(part, n_parts, bias, skip, rgb, B, h, w);
+  return check_launch("rgb_combine");
+}
+
+extern "C" int b200ir_rgb_wmod(const float* w, const float* s, float* wm, int B, int C, void* stream) {
+  B200IR_REQUIRE(w && wm && B > 0 && C > 0, "rgb_wmod: bad arguments");
+  rgb_wmod_kernel<<<grid_for((long long)B * 3 * C), kPwThreads, 0, STREAM>>>(w, s, wm, B, C);
+  return check_launch("rgb_wmod");
 }
 
 extern "C" int b200ir_modulate_const(const void* cst, const float* s, void* out, int B, int P, int C, void* stream) {

@@ -244,15 +244,29 @@ class _Plan:
         cch = pk.sc1['cin']
         self.noise_shapes.append((h, w))
         self.noise[0] = e32(B, 1, h, w)
+        # per-image ToRGB weights w[o][c] * s_rgb[b][c] for the conv epilogues that fuse ToRGB
+        def rgb_weights(layer, s):
+            wm = e32(B, 3, layer['w'].shape[1])
+            steps.append(lambda l=layer, ss=s, o=wm: ops.rgb_wmod(l['w'], ss, o))
+            return wm
+
+        wm_rgb1 = rgb_weights(pk.rgb1, s_rgb1)
+        wm_rgbs = [rgb_weights(pk.rgbs[lvl], s_rgb[lvl]) for lvl in range(L)]
+
         xs = e16(B, h, w, cch)
         steps.append(lambda o=xs: ops.modulate_const(pk.const, s_sc1, o))
-        out = e16(B, h, w, pk.sc1['cout'])
-        steps.append(ops.conv_same(xs, pk.sc1['w'], out, 3, bias=pk.sc1['bias'], demod=d_sc1, noise=self.noise[0],
-                                   noise_gain=pk.sc1['gain'], noise_strides=(h * w, w), act=True))
+        # style_conv1 + to_rgb1 (gfpganv1_ocr_arch.py:108-110): the conv epilogue accumulates the ToRGB dot products
+        # and writes its output already multiplied by the modulation of the next conv
+        last = L == 0
+        xs_next = None if last else e16(B, h, w, pk.sc1['cout'])
+        op = ops.conv_same(xs, pk.sc1['w'], xs_next, 3, bias=pk.sc1['bias'], demod=d_sc1, noise=self.noise[0],
+                           noise_gain=pk.sc1['gain'], noise_strides=(h * w, w), act=True,
+                           out_scale=None if last else s_conv[0])
+        part = op.attach_rgb(wm_rgb1, (h, w), no_store=last)
+        steps.append(op)
         skip = e32(B, 3, h, w)
-        xs = e16(B, h, w, pk.sc1['cout'])
-        steps.append(lambda x=out, o=skip, xo=xs: ops.to_rgb(x, pk.rgb1['w'], s_rgb1, pk.rgb1['bias'], None, o,
-                                                             s_conv[0] if L > 0 else None, xo if L > 0 else None))
+        steps.append(lambda pt=part, o=skip: ops.rgb_combine(pt, pk.rgb1['bias'], None, o))
+        xs = xs_next
         for lvl in range(L):
             c1, c2 = pk.sconv[2 * lvl], pk.sconv[2 * lvl + 1]
             cout = c1['cout']
@@ -268,14 +282,15 @@ class _Plan:
             xs2 = e16(B, h2, w2, cout)
             steps.append(lambda r=raw, o=xs2, n=n1, c=c1, a=sc, b_=sh, sn=s_conv[2 * lvl + 1]:
                          ops.upfir_act(r, o, n, o.shape[1] * o.shape[2], c['gain'], c['bias'], a, b_, a.shape[3], sn))
-            out = e16(B, h2, w2, cout)
-            steps.append(ops.conv_same(xs2, c2['w'], out, 3, bias=c2['bias'], demod=d_conv[2 * lvl + 1], noise=n2,
-                                       noise_gain=c2['gain'], noise_strides=(h2 * w2, w2), act=True))
-            nskip = e32(B, 3, h2, w2)
             last = lvl == L - 1
             xs = None if last else e16(B, h2, w2, cout)
-            steps.append(lambda x=out, r=pk.rgbs[lvl], s=s_rgb[lvl], sk=skip, o=nskip, xo=xs,
-                         sn=(None if last else s_conv[2 * lvl + 2]): ops.to_rgb(x, r['w'], s, r['bias'], sk, o, sn, xo))
+            op = ops.conv_same(xs2, c2['w'], xs, 3, bias=c2['bias'], demod=d_conv[2 * lvl + 1], noise=n2,
+                               noise_gain=c2['gain'], noise_strides=(h2 * w2, w2), act=True,
+                               out_scale=None if last else s_conv[2 * lvl + 2])
+            part = op.attach_rgb(wm_rgbs[lvl], (h2, w2), no_store=last)
+            steps.append(op)
+            nskip = e32(B, 3, h2, w2)
+            steps.append(lambda pt=part, r=pk.rgbs[lvl], sk=skip, o=nskip: ops.rgb_combine(pt, r['bias'], sk, o))
             skip = nskip
             h, w = h2, w2
         self.image = skip

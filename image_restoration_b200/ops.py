@@ -61,7 +61,8 @@ class ConvOp:
     def __init__(self, views, weight, cin, cout, taps, m_whb, out, out_strides, *, out_fp32=False, out_c_off=0,
                  out_mul_off=(1, 0, 1, 0), bias=None, demod=None, noise=None, noise_gain=None, noise_strides=(0, 0),
                  act=False, res=None, res_mode=0, res_strides=(0, 0, 0), res_wh=(0, 0), res_scale=1.0, block_n=None,
-                 tile=None, max_ctas=0, row_mode=0):
+                 tile=None, max_ctas=0, row_mode=0, out_scale=None, rgb_w=None, rgb_part=None, rgb_hw=(0, 0),
+                 no_store=False):
         d = ConvDesc()
         assert 1 <= len(views) <= _lib.MAX_VIEWS and 1 <= len(taps) <= _lib.MAX_TAPS
         for i, v in enumerate(views):
@@ -76,7 +77,7 @@ class ConvOp:
         d.m_w, d.m_h, d.m_b = m_whb
         d.tile_w, d.tile_h, d.tile_b = tile or pick_tile(*m_whb)
         d.block_n = block_n or pick_block_n(cout)
-        d.out = out.data_ptr()
+        d.out = out.data_ptr() if out is not None else None
         d.out_fp32 = 1 if out_fp32 else 0
         d.out_stride_x, d.out_stride_y, d.out_stride_b = out_strides
         d.out_c_off = out_c_off
@@ -96,10 +97,31 @@ class ConvOp:
         d.res_scale = res_scale
         d.max_ctas = max_ctas
         d.row_mode = row_mode
+        for name, t in (('out_scale', out_scale), ('rgb_w', rgb_w), ('rgb_part', rgb_part)):
+            if t is not None:
+                _req(t, torch.float32, name)
+                setattr(d, name, t.data_ptr())
+        if rgb_w is not None:
+            assert rgb_part is not None and rgb_part.shape[0] == cout // d.block_n, (rgb_part.shape, cout, d.block_n)
+        d.rgb_h, d.rgb_w_px = rgb_hw
+        d.no_store = 1 if no_store else 0
         self.desc = d
         # keep every tensor alive as long as the op exists
-        self._keep = (weight, out, bias, demod, noise, noise_gain, res)
+        self._keep = (weight, out, bias, demod, noise, noise_gain, res, out_scale, rgb_w, rgb_part)
         self._fn = _lib.lib().b200ir_conv_igemm
+
+    def attach_rgb(self, rgb_w, hw, no_store=False):
+        """Fuse ToRGB into this conv's epilogue: rgb_w fp32 [B][3][cout]; returns the partial-plane buffer
+        [cout/block_n][B][3][h][w] that b200ir_rgb_combine reduces."""
+        d = self.desc
+        _req(rgb_w, torch.float32, 'rgb_w')
+        assert rgb_w.shape == (d.m_b, 3, d.cout), rgb_w.shape
+        part = torch.empty(d.cout // d.block_n, d.m_b, 3, hw[0], hw[1], device=rgb_w.device, dtype=torch.float32)
+        d.rgb_w, d.rgb_part = rgb_w.data_ptr(), part.data_ptr()
+        d.rgb_h, d.rgb_w_px = hw
+        d.no_store = 1 if no_store else 0
+        self._keep = self._keep + (rgb_w, part)
+        return part
 
     def __call__(self):
         check(self._fn(C.byref(self.desc), _stream()), 'b200ir_conv_igemm')
@@ -132,7 +154,7 @@ def conv_same(x, weight, out, ksize, **kw):
     b, h, w, cin = x.shape
     cout = weight.shape[0]
     taps = taps_3x3() if ksize == 3 else [(0, 0, 0)]
-    oc = out.shape[3]
+    oc = out.shape[3] if out is not None else cout
     if ksize == 3 and 'tile' not in kw and 'row_mode' not in kw and row_mode_ok(b, h, w, cin, cout):
         kw.update(tile=(128, 1, 1), row_mode=1, block_n=cout)
     return ConvOp([nhwc_view(x)], weight, cin, cout, taps, (w, h, b), out, (oc, w * oc, h * w * oc), **kw)
@@ -222,6 +244,19 @@ def to_rgb(x, wrgb, s, bias, skip, rgb, s_next=None, xs_out=None):
     b, h, w, c = x.shape
     check(_lib.lib().b200ir_to_rgb(_ptr(x), b, h, w, c, _ptr(wrgb), _ptr(s), _ptr(bias), _ptr(skip), _ptr(rgb),
                                    _ptr(s_next), _ptr(xs_out), _stream()), 'to_rgb')
+
+
+def rgb_combine(part, bias, skip, rgb):
+    """rgb = bias + sum of the partial planes the conv epilogues wrote (+ up-sampled skip): second half of ToRGB."""
+    b, _, h, w = rgb.shape
+    check(_lib.lib().b200ir_rgb_combine(_ptr(part), part.shape[0], _ptr(bias), _ptr(skip), _ptr(rgb), b, h, w,
+                                        _stream()), 'rgb_combine')
+
+
+def rgb_wmod(w, s, wm):
+    """wm[b][o][c] = w[o][c] * s[b][c]: per-image ToRGB weights (ModulatedConv2d without demodulation)."""
+    b, _, c = wm.shape
+    check(_lib.lib().b200ir_rgb_wmod(_ptr(w), _ptr(s), _ptr(wm), b, c, _stream()), 'rgb_wmod')
 
 
 def modulate_const(cst, s, out):

@@ -63,7 +63,14 @@ int b200ir_device_check(void);
  *   if (act) v = (v > 0 ? v : 0.2 v) * sqrt(2)
  *   if (res_mode == 1) v = (v + res[b, yo, xo, n]) * res_scale
  *   if (res_mode == 2) v = (v + bilinear_up2(res_lowres)[b, yo, xo, n]) * res_scale   (align_corners=False)
- *   out[b, yo, xo, out_c_off + n] = v      with yo = y*out_y_mul + out_y_off, xo = x*out_x_mul + out_x_off
+ *   if (rgb_w)  rgb_part[nt][b][o][yo][xo] = sum_{n in N-tile nt} v * rgb_w[b][o][n]   (o = 0..2; ToRGB fused, see below)
+ *   if (out_scale) v *= out_scale[b*cout + n]      (modulation of the NEXT modulated conv, stylegan2_ocr_arch.py:247-251)
+ *   if (!no_store) out[b, yo, xo, out_c_off + n] = v      with yo = y*out_y_mul + out_y_off, xo = x*out_x_mul + out_x_off
+ *
+ * Fused ToRGB (stylegan2_ocr_arch.py:357-374): the 1x1 modulated conv to 3 channels reads exactly the tensor this
+ * conv produces, so each epilogue thread (one output position, block_n channels) accumulates the three dot products
+ * with rgb_w[b][o][n] = w[o][n]/sqrt(cout) * s_rgb[b][n] and writes them as fp32 NCHW partial planes, one per N-tile
+ * (rgb_part is [cout/block_n][m_b][3][rgb_h][rgb_w_px]); b200ir_rgb_combine adds bias, the partials and the up-sampled skip.
  */
 typedef struct {
   const void* ptr; /* fp16, element (b,y,x,c) at ptr[b*stride_b + y*stride_h + x*stride_w + c] */
@@ -102,6 +109,11 @@ typedef struct {
   int32_t max_ctas; /* 0: one CTA per SM */
   int32_t row_mode; /* 0: generic tiles; 1: allow the row-sliding variant (3x3 stride 1, tile 128x1x1, weights resident
                        in shared memory; picked only when eligible and the batch gives enough work items) */
+  const float* out_scale; /* [m_b][cout] or NULL */
+  const float* rgb_w;     /* [m_b][3][cout] or NULL */
+  float* rgb_part;        /* [cout/block_n][m_b][3][rgb_h][rgb_w_px] fp32, required with rgb_w */
+  int32_t rgb_w_px, rgb_h;
+  int32_t no_store;       /* 1: do not write `out` (the tensor is only consumed by the fused ToRGB) */
 } b200ir_conv_desc;
 
 int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
@@ -145,6 +157,13 @@ int b200ir_upfir_act(const void* raw, void* out, int B, int h2, int w2, int C, i
  * rgb: fp32 NCHW [B][3][h][w].  If xs_out: xs_out = x * s_next[b][c] (NHWC fp16; input of the next modulated conv). */
 int b200ir_to_rgb(const void* x, int B, int h, int w, int C, const float* wrgb, const float* s, const float* bias,
                   const float* skip, float* rgb, const float* s_next, void* xs_out, void* stream);
+
+/* Second half of the fused ToRGB (see b200ir_conv_igemm): rgb[b][o][y][x] = bias[o] + sum_t part[t][b][o][y][x]
+ *   (+ upfirdn2d(skip, FIR*4, up=2, pad=(2,1)) when skip != NULL; skip fp32 NCHW [B][3][h/2][w/2]).
+ * rgb_wmod builds the per-image weights the conv epilogue uses: wm[b][o][c] = w[o][c] * s[b][c]. */
+int b200ir_rgb_combine(const float* part, int n_parts, const float* bias, const float* skip, float* rgb, int B, int h,
+                       int w, void* stream);
+int b200ir_rgb_wmod(const float* w, const float* s, float* wm, int B, int C, void* stream);
 
 /* ConstantInput.forward (stylegan2_ocr_arch.py:389-391) fused with the first modulation:
  * out[b,p,c] = cst[p*C + c] * s[b*C + c];  cst NHWC fp16 [P][C]. */

@@ -369,3 +369,43 @@ def test_fir_pad22_streaming(B, H, W, C):
     got = nchw32(p)
     check_close(got[:, :, :H + 1, :W + 1], pref, what=f'fir_pad22 streaming C={C} {H}x{W}')
     assert (got[:, :, H + 1] == 7.0).all() and (got[:, :, :, W + 1] == 7.0).all()   # nothing written past (H+1)x(W+1)
+
+
+@pytest.mark.parametrize('B,H,W,C,no_store,with_skip', [(2, 16, 48, 512, False, True), (3, 64, 192, 64, True, True),
+                                                        (64, 4, 12, 512, False, False), (2, 128, 384, 64, True, True)])
+def test_conv_fused_to_rgb_and_next_modulation(B, H, W, C, no_store, with_skip):
+    """StyleConv (plain) + ToRGB fused: conv epilogue writes out * s_next and the three ToRGB dot products as partial
+    planes; rgb_combine adds bias, partials and the up-sampled skip (stylegan2_ocr_arch.py:323-333,357-374)."""
+    ops = _ops()
+    torch.manual_seed(13)
+    x = torch.randn(B, C, H, W, device=DEV)
+    w = torch.randn(C, C, 3, 3, device=DEV) / math.sqrt(C * 9)
+    xh, wh = nhwc16(x), pack3x3(w)
+    bias = torch.randn(C, device=DEV) * 0.1
+    demod = torch.rand(B, C, device=DEV) + 0.5
+    noise = torch.randn(B, 1, H, W, device=DEV)
+    gain = torch.tensor([0.1], device=DEV)
+    s_next = torch.rand(B, C, device=DEV) + 0.5
+    wrgb = torch.randn(3, C, device=DEV) / math.sqrt(C)
+    s_rgb = torch.rand(B, C, device=DEV) + 0.5
+    brgb = torch.randn(3, device=DEV)
+    wm = torch.empty(B, 3, C, device=DEV)
+    ops.rgb_wmod(wrgb, s_rgb, wm)
+    out = None if no_store else torch.empty(B, H, W, C, device=DEV, dtype=torch.float16)
+    op = ops.conv_same(xh, wh, out, 3, bias=bias, demod=demod, noise=noise, noise_gain=gain,
+                       noise_strides=(H * W, W), act=True, out_scale=s_next)
+    part = op.attach_rgb(wm, (H, W), no_store=no_store)
+    op()
+    skip = torch.randn(B, 3, H // 2, W // 2, device=DEV) if with_skip else None
+    rgb = torch.empty(B, 3, H, W, device=DEV)
+    ops.rgb_combine(part, brgb, skip, rgb)
+    torch.cuda.synchronize()
+    wr = wh.float().view(C, 3, 3, C).permute(0, 3, 1, 2)
+    y = F.conv2d(nchw32(xh), wr, padding=1) * demod[:, :, None, None] + gain * noise + bias[None, :, None, None]
+    y = F.leaky_relu(y, 0.2) * math.sqrt(2)
+    ref_rgb = torch.einsum('bchw,oc,bc->bohw', y, wrgb, s_rgb) + brgb[None, :, None, None]
+    if with_skip:
+        ref_rgb = ref_rgb + upfirdn_ref(skip, fir_k(DEV) * 4, up=2, pad=(2, 1))
+    check_close(rgb, ref_rgb, tol=2e-3, what=f'fused toRGB C={C} {H}x{W}')
+    if not no_store:
+        check_close(nchw32(out), y * s_next[:, :, None, None], what='conv out * s_next')
