@@ -183,26 +183,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const TileCoord t = decode_tile(p, tile);
       const int x = t.x0 + xx, y = t.y0 + yy, b = t.b0 + bi;
       const bool valid = (x < p.m_w) && (y < p.m_h) && (b < p.m_b);
-      const EpiRow r = epi_setup(p, x, y, b, t.n0, valid, gain);
-      const float* s_dm = nullptr;
+      uint32_t s_dm = 0, s_aux = 0;
       const float* g_dm = nullptr;
-      if (p.demod != nullptr) {
-        if (p.smem_demod) {
-          float* tab = s.demod + group * kDemodTable;
-          epi_group_sync(group);  // previous tile of this group fully drained
-          for (int i = gt; i < p.tile_b * p.block_n; i += 128) {
-            const int bb = t.b0 + i / p.block_n;
-            tab[i] = (bb < p.m_b) ? __ldg(p.demod + (long long)bb * p.cout + t.n0 + (i % p.block_n)) * p.act_gain : 0.f;
+      const int tab_n = p.tile_b * p.block_n;
+      if ((p.demod != nullptr && p.smem_demod) || p.smem_aux) {
+        float* tab = s.demod + group * kDemodTable;
+        epi_group_sync(group);  // previous tile of this group fully drained
+        for (int i = gt; i < tab_n; i += 128) {
+          const int bb = t.b0 + i / p.block_n;
+          const long long ch = (long long)bb * p.cout + t.n0 + (i % p.block_n);
+          const bool in = bb < p.m_b;
+          if (p.smem_demod) tab[i] = in ? __ldg(p.demod + ch) * p.act_gain : 0.f;
+          if (p.smem_aux) {
+            tab[tab_n + i] = (in && p.out_scale != nullptr) ? __ldg(p.out_scale + ch) : 1.f;
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+              tab[(2 + o) * tab_n + i] =
+                  (in && p.rgb_w != nullptr) ? __ldg(p.rgb_w + ((long long)bb * 3 + o) * p.cout + t.n0 + (i % p.block_n)) : 0.f;
           }
-          epi_group_sync(group);
-          s_dm = tab + bi * p.block_n;
-        } else {
-          g_dm = p.demod + (long long)b * p.cout + t.n0;
         }
+        epi_group_sync(group);
+        if (p.smem_demod) s_dm = smem_u32(tab + bi * p.block_n);
+        if (p.smem_aux) s_aux = smem_u32(tab + tab_n + bi * p.block_n);
       }
+      if (p.demod != nullptr && !p.smem_demod) g_dm = p.demod + (long long)b * p.cout + t.n0;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-      const float* bias_ptr = (p.cout <= kMaxBias) ? s.bias + t.n0 : p.bias + t.n0;  // wide layers: global, act == 0
-      epilogue_tile(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, r, valid, bias_ptr, s_dm, g_dm, 0, 16);
+      const uint32_t s_bias = (p.cout <= kMaxBias) ? smem_u32(s.bias + t.n0) : 0u;  // wide layers: global, act == 0
+      epilogue_dispatch(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, y, b, t.n0, valid, gain, s_bias, s_dm,
+                        g_dm, s_aux, tab_n);
       tc_fence_before();
       mbar_arrive(&s.tmem_empty[acc]);
     }
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_cons
     const uint32_t ring_lo = smem_u32(s_ring) >> 4;
     const uint32_t wtile_lo = wtile_bytes >> 4;
     constexpr uint32_t slot_lo = slot_bytes >> 4;
-    constexpr uint32_t px_lo = row_bytes >> 4;  // one pixel (one smem row) in descriptor units
+    const uint32_t px_lo = p.dbg_noshift ? 0u : (row_bytes >> 4);  // one pixel (one smem row) in descriptor units
     int wait_slot = 0;        // next ring fill to wait for (producer order)
     uint32_t wait_phase = 0;
     int row_slot = 0;         // slot of (input row j, kc 0) of the current output row
@@ -356,20 +364,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_cons
       const RowItem w = decode_item(p, item);
       const int x = w.seg * 128 + row;
       const bool valid = x < p.m_w;
-      const float* s_dm = nullptr;
-      if (p.demod != nullptr) {  // one image per item: each group stages that image's demod row once
+      uint32_t s_dm = 0, s_aux = 0;
+      if (p.demod != nullptr || p.smem_aux) {  // one image per item: each group stages that image's table rows once
         float* tab = s.demod + group * kDemodTable;
         epi_group_sync(group);
-        for (int i = gt; i < p.block_n; i += 128) tab[i] = __ldg(p.demod + (long long)w.b * p.cout + i) * p.act_gain;
+        for (int i = gt; i < p.block_n; i += 128) {
+          const long long ch = (long long)w.b * p.cout + i;
+          if (p.demod != nullptr) tab[i] = __ldg(p.demod + ch) * p.act_gain;
+          if (p.smem_aux) {
+            tab[p.block_n + i] = (p.out_scale != nullptr) ? __ldg(p.out_scale + ch) : 1.f;
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+              tab[(2 + o) * p.block_n + i] =
+                  (p.rgb_w != nullptr) ? __ldg(p.rgb_w + ((long long)w.b * 3 + o) * p.cout + i) : 0.f;
+          }
+        }
         epi_group_sync(group);
-        s_dm = tab;
+        if (p.demod != nullptr) s_dm = smem_u32(tab);
+        if (p.smem_aux) s_aux = smem_u32(tab + p.block_n);
       }
       for (int j = 0; j < w.rows_out; ++j, ++it) {
         if ((it & 1) != group) continue;
         const int acc = it & (p.acc_stages - 1);
-        const EpiRow r = epi_setup(p, x, w.y0 + j, w.b, 0, valid, gain);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-        epilogue_tile(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, r, valid, s.bias, s_dm, nullptr, 0, 16);
+        epilogue_dispatch(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, w.y0 + j, w.b, 0, valid, gain,
+                          smem_u32(s.bias), s_dm, nullptr, s_aux, p.block_n);
         tc_fence_before();
         mbar_arrive(&s.tmem_empty[acc]);
       }
