@@ -295,6 +295,7 @@ class _Plan:
             h, w = h2, w2
         self.image = skip
         self.graphs = {}
+        self.noise_state = None
 
     def launch(self, return_rgb):
         for st in self.steps:
@@ -347,13 +348,17 @@ class OcrEngine:
             plan = self.plan(B)
             plan.x_in.copy_(x)
             pk = self.packed
-            for j, buf in enumerate(plan.noise):
-                if noise is not None:
-                    buf.copy_(noise[j].expand_as(buf))
-                elif randomize_noise:
-                    buf.normal_()
-                else:
-                    buf.copy_(pk.stored_noise[j].expand_as(buf))
+            if noise is None and not randomize_noise and plan.noise_state == 'stored':
+                pass                                  # buffers already hold the registered noise planes
+            else:
+                for j, buf in enumerate(plan.noise):
+                    if noise is not None:
+                        buf.copy_(noise[j].expand_as(buf))
+                    elif randomize_noise:
+                        buf.normal_()
+                    else:
+                        buf.copy_(pk.stored_noise[j].expand_as(buf))
+                plan.noise_state = 'stored' if (noise is None and not randomize_noise) else 'other'
             if load_feat_path is not None or save_feat_path is not None or not self.use_graphs:
                 self._run_eager(plan, return_rgb, save_feat_path, load_feat_path)
             else:

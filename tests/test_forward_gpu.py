@@ -134,3 +134,27 @@ def test_engine_matches_reference_goldens():
             rr = torch.from_numpy(fx[f'rgb{i}'])
             assert ((r.float().cpu() - rr).abs().max() / (rr.abs().max() + 1e-6)).item() < 2e-2
     assert n > 0, 'no golden fixture could be reproduced from its seed'
+
+
+def test_host_pipeline_matches_direct_call():
+    """Host-buffer front end (pinned in / pinned out, copies overlapped with compute) returns exactly what the module
+    call returns, for several jobs in flight and for a synchronous chunked call."""
+    from image_restoration_b200 import GFPGANv1OCR
+    from image_restoration_b200.host_io import HostPipeline, restore_host
+    torch.manual_seed(0)
+    kw = dict(input_width=96, input_height=32, num_style_feat=256, channel_multiplier=0.5, num_mlp=4,
+              input_is_latent=True, different_w=True, narrow=1, sft_half=True)
+    net = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **kw).eval().cuda()
+    xs = [(torch.rand(4, 3, 32, 96) * 2 - 1).pin_memory() for _ in range(5)]
+    ys = [torch.empty(4, 3, 32, 96).pin_memory() for _ in range(5)]
+    pipe = HostPipeline(net, depth=2)
+    tickets = [pipe.submit(x, y) for x, y in zip(xs, ys)]
+    for t in tickets:
+        pipe.wait(t)
+    for x, y in zip(xs, ys):
+        ref = net(x.cuda(), return_rgb=False, randomize_noise=False)[0].cpu()
+        assert torch.equal(y, ref)
+    y2 = restore_host(net, xs[0], chunks=2)
+    ref = torch.cat([net(xs[0][:2].cuda(), return_rgb=False, randomize_noise=False)[0],
+                     net(xs[0][2:].cuda(), return_rgb=False, randomize_noise=False)[0]]).cpu()
+    assert torch.equal(y2, ref)
