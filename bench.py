@@ -42,7 +42,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clock / power / throttle reasons of one GPU through NVML while the timed region runs
+    (nvidia-smi as a fallback)."""
 
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
@@ -51,30 +52,52 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        return (float(sm), float(mx), pw, bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4))
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+        p = [s.strip() for s in out.strip().split(',')]
+        act = [s.lower().startswith('active') for s in p[3:7]]
+        return (float(p[0]), float(p[1]), float(p[2]), *act)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(',')]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                self.samples.append(self._sample_nvml() if self.nvml else self._sample_smi())
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02 if self.nvml else 0.1)
 
     def summary(self):
         if not self.samples:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
-        sm = sorted(float(s[0]) for s in self.samples)
+        sm = sorted(s[0] for s in self.samples)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]),
-                'power_w_max': max(float(s[2]) for s in self.samples), 'samples': len(self.samples),
-                'reasons': reasons}
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i] for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_min_mhz': sm[0], 'sm_max_mhz': self.samples[0][1],
+                'power_w_max': max(s[2] for s in self.samples), 'samples': len(self.samples),
+                'source': 'nvml' if self.nvml else 'nvidia-smi', 'reasons': reasons}
 
 
 def cpu_oracle_rate(seconds_budget=20.0, threads=None):
@@ -227,6 +250,23 @@ def main():
             op()
     ms_conv = timed(conv_only, args.steps, warmup)
 
+    # memory-bound kernels: every launch of each kind, back to back, against its algorithmic bytes
+    from image_restoration_b200.engine import PwOp
+    pw_groups = {}
+    for st in plan.steps:
+        if isinstance(st, PwOp):
+            pw_groups.setdefault(st.name, []).append(st)
+    pw_report = []
+    if world == 1:
+        for name, group in pw_groups.items():
+            def run_group(g=group):
+                for op in g:
+                    op()
+            ms = timed(run_group, args.steps, 3) / args.steps
+            nbytes = sum(op.nbytes for op in group)
+            pw_report.append({'kernel': name, 'launches_per_step': len(group), 'algorithmic_mb_per_step': nbytes / 1e6,
+                              'ms_per_step': ms, 'achieved_gbs': nbytes / ms / 1e6})
+
     if rank == 0:
         tf_peak, hbm_peak, src = peaks()
         crops = B * world * args.steps
@@ -258,6 +298,22 @@ def main():
                          'whole_net_frac': value / world * GFLOP_PER_CROP * 1e9 / 1e12 / tf_peak},
             'clocks': sampler.summary(),
         }
+        traffic_file = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as f:
+                tr = json.load(f)
+            line['roofline']['traffic'] = tr.get('dram_bytes_per_launch')
+            line['roofline']['traffic_source'] = tr.get('source')
+            line['roofline']['algorithmic_bytes_per_launch'] = tr.get('algorithmic_bytes_per_launch')
+        for r in pw_report:
+            r['frac_of_hbm_peak'] = r['achieved_gbs'] / hbm_peak
+        pw_report.sort(key=lambda r: -r['ms_per_step'])
+        line['memory_bound_kernels'] = pw_report
+        if pw_report:
+            top = pw_report[0]
+            line['roofline_hbm'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_gbs'],
+                                    'peak': hbm_peak, 'unit': 'GB/s', 'frac': top['achieved_gbs'] / hbm_peak,
+                                    'traffic': None, 'peak_source': f'{src} hbm_gbs'}
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_oracle_rate()
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}

@@ -460,37 +460,86 @@ __global__ void demod_kernel(const float* __restrict__ s, const float* __restric
   if (lane == 0) d[(long long)b * cout + o] = rsqrtf(scale2 * acc + 1e-8f);
 }
 
-// all modulation linears of a forward in one launch: blockIdx.y = layer, one warp per (b, i)
-__global__ void mod_linear_multi_kernel(const float* __restrict__ latent, int L, int F, const b200ir_mod_layer* layers,
-                                        float wscale, int B) {
-  const b200ir_mod_layer ly = layers[blockIdx.y];
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= B * ly.cin) return;
-  const int b = warp / ly.cin, i = warp % ly.cin;
-  const float* lp = latent + ((long long)b * L + ly.lat_idx) * F;
-  const float* wp = ly.w + (long long)i * F;
-  float acc = 0.f;
-  for (int f = lane; f < F; f += 32) acc += __ldg(wp + f) * __ldg(lp + f);
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) ly.s[(long long)b * ly.cin + i] = acc * wscale + __ldg(ly.bias + i);
+// All modulation linears / demodulation tables of a forward in one launch each.  Both are small row-dot products
+//   out[b][o] = post( sum_c W[o][c] * f(X[b][c]) )
+// grid (output blocks of kRdOut, layer, batch groups of kRdBatch).  A block stages f(X) of its kRdBatch images in shared
+// memory as [c][kRdBatch]; each thread owns one output o and walks over c: one weight load + kRdBatch/4 broadcast
+// LDS.128 + kRdBatch FMAs per c, no cross-lane reduction.  (The first version re-read a weight row per image and spent
+// ~90 us per launch on L2 traffic.)
+static constexpr int kRdBatch = 16;
+static constexpr int kRdOut = 128;
+static constexpr int kRdMaxC = 512;
+
+template <bool SQUARE>
+__device__ __forceinline__ void rowdot_block(const float* __restrict__ W, int n_out, int C, const float* X,
+                                             long long x_stride, int B, float* acc_out /*[kRdBatch]*/, int o,
+                                             float* sx /*[C][kRdBatch]*/) {
+  const int b0 = blockIdx.z * kRdBatch;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // coalesced over c, kRdBatch independent loads in flight
+    float v[kRdBatch];
+#pragma unroll
+    for (int j = 0; j < kRdBatch; ++j) v[j] = (b0 + j < B) ? X[(long long)(b0 + j) * x_stride + c] : 0.f;
+#pragma unroll
+    for (int q = 0; q < kRdBatch / 4; ++q) {
+      float4 x4 = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      if (SQUARE) x4 = make_float4(x4.x * x4.x, x4.y * x4.y, x4.z * x4.z, x4.w * x4.w);
+      reinterpret_cast<float4*>(sx + c * kRdBatch)[q] = x4;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kRdBatch; ++j) acc_out[j] = 0.f;
+  if (o >= n_out) return;
+  const float4* wp = reinterpret_cast<const float4*>(W + (long long)o * C);  // C % 4 == 0 (checked by the launcher)
+#pragma unroll 2
+  for (int c4 = 0; c4 < C / 4; ++c4) {
+    const float4 w4 = __ldg(wp + c4);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4* xp = reinterpret_cast<const float4*>(sx + (4 * c4 + k) * kRdBatch);
+#pragma unroll
+      for (int q = 0; q < kRdBatch / 4; ++q) {
+        const float4 x4 = xp[q];
+        acc_out[4 * q] = fmaf(wv[k], x4.x, acc_out[4 * q]);
+        acc_out[4 * q + 1] = fmaf(wv[k], x4.y, acc_out[4 * q + 1]);
+        acc_out[4 * q + 2] = fmaf(wv[k], x4.z, acc_out[4 * q + 2]);
+        acc_out[4 * q + 3] = fmaf(wv[k], x4.w, acc_out[4 * q + 3]);
+      }
+    }
+  }
 }
 
-__global__ void demod_multi_kernel(const b200ir_demod_layer* layers, int B) {
-  const b200ir_demod_layer ly = layers[blockIdx.y];
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= B * ly.cout) return;
-  const int b = warp / ly.cout, o = warp % ly.cout;
-  const float* sp = ly.s + (long long)b * ly.cin;
-  const float* wp = ly.wsq + (long long)o * ly.cin;
-  float acc = 0.f;
-  for (int i = lane; i < ly.cin; i += 32) {
-    const float sv = __ldg(sp + i);
-    acc += sv * sv * __ldg(wp + i);
+__global__ void __launch_bounds__(kRdOut) mod_linear_multi_kernel(const float* __restrict__ latent, int L, int F,
+                                                                  const b200ir_mod_layer* layers, float wscale, int B) {
+  __shared__ __align__(16) float sx[kRdMaxC * kRdBatch];
+  const b200ir_mod_layer ly = layers[blockIdx.y];
+  if (blockIdx.x * kRdOut >= ly.cin) return;
+  const int o = blockIdx.x * kRdOut + threadIdx.x;
+  float acc[kRdBatch];
+  rowdot_block<false>(ly.w, ly.cin, F, latent + (long long)ly.lat_idx * F, (long long)L * F, B, acc, o, sx);
+  if (o >= ly.cin) return;
+  const float bias = __ldg(ly.bias + o);
+#pragma unroll
+  for (int j = 0; j < kRdBatch; ++j) {
+    const int b = blockIdx.z * kRdBatch + j;
+    if (b < B) ly.s[(long long)b * ly.cin + o] = acc[j] * wscale + bias;
   }
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) ly.d[(long long)b * ly.cout + o] = rsqrtf(ly.scale2 * acc + 1e-8f);
+}
+
+__global__ void __launch_bounds__(kRdOut) demod_multi_kernel(const b200ir_demod_layer* layers, int B) {
+  __shared__ __align__(16) float sx[kRdMaxC * kRdBatch];
+  const b200ir_demod_layer ly = layers[blockIdx.y];
+  if (blockIdx.x * kRdOut >= ly.cout) return;
+  const int o = blockIdx.x * kRdOut + threadIdx.x;
+  float acc[kRdBatch];
+  rowdot_block<true>(ly.wsq, ly.cout, ly.cin, ly.s, ly.cin, B, acc, o, sx);
+  if (o >= ly.cout) return;
+#pragma unroll
+  for (int j = 0; j < kRdBatch; ++j) {
+    const int b = blockIdx.z * kRdBatch + j;
+    if (b < B) ly.d[(long long)b * ly.cout + o] = rsqrtf(ly.scale2 * acc[j] + 1e-8f);
+  }
 }
 
 __global__ void nhwc_to_nchw_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, int B, int P, int C) {
@@ -649,17 +698,18 @@ extern "C" int b200ir_demod(const float* s, const float* wsq, float scale2, floa
 
 extern "C" int b200ir_mod_linear_multi(const float* latent, int L, int F, const b200ir_mod_layer* layers_dev,
                                        int n_layers, int max_cin, float wscale, int B, void* stream) {
-  B200IR_REQUIRE(latent && layers_dev && n_layers > 0 && max_cin > 0, "mod_linear_multi: bad arguments");
-  dim3 grid(grid_for((long long)B * max_cin * 32), n_layers);
-  mod_linear_multi_kernel<<<grid, kPwThreads, 0, STREAM>>>(latent, L, F, layers_dev, wscale, B);
+  B200IR_REQUIRE(latent && layers_dev && n_layers > 0 && max_cin > 0 && F <= kRdMaxC && F % 4 == 0,
+                 "mod_linear_multi: bad arguments (F=%d)", F);
+  dim3 grid((max_cin + kRdOut - 1) / kRdOut, n_layers, (B + kRdBatch - 1) / kRdBatch);
+  mod_linear_multi_kernel<<<grid, kRdOut, 0, STREAM>>>(latent, L, F, layers_dev, wscale, B);
   return check_launch("mod_linear_multi");
 }
 
 extern "C" int b200ir_demod_multi(const b200ir_demod_layer* layers_dev, int n_layers, int max_cout, int B,
                                   void* stream) {
   B200IR_REQUIRE(layers_dev && n_layers > 0 && max_cout > 0, "demod_multi: bad arguments");
-  dim3 grid(grid_for((long long)B * max_cout * 32), n_layers);
-  demod_multi_kernel<<<grid, kPwThreads, 0, STREAM>>>(layers_dev, B);
+  dim3 grid((max_cout + kRdOut - 1) / kRdOut, n_layers, (B + kRdBatch - 1) / kRdBatch);
+  demod_multi_kernel<<<grid, kRdOut, 0, STREAM>>>(layers_dev, B);
   return check_launch("demod_multi");
 }
 

@@ -111,6 +111,18 @@ class _Packed:
         self.mod_wscale = 1.0 / math.sqrt(net.num_style_feat)
 
 
+class PwOp:
+    """One prepared launch of a memory-bound kernel: callable + the tensors it reads / writes once (algorithmic HBM
+    bytes for the roofline report of bench.py)."""
+
+    def __init__(self, name, fn, *tensors):
+        self.name, self.fn = name, fn
+        self.nbytes = sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
+    def __call__(self):
+        self.fn()
+
+
 class _Plan:
     """All buffers and prepared launches for one batch size."""
 
@@ -131,7 +143,7 @@ class _Plan:
         self.x_in = e32(B, 3, H, W)
         c0 = pk.first_w.shape[0]
         feat = e16(B, H, W, c0)
-        steps.append(lambda o=feat: ops.first_conv(self.x_in, pk.first_w, pk.first_b, o))
+        steps.append(PwOp('first_conv', lambda o=feat: ops.first_conv(self.x_in, pk.first_w, pk.first_b, o), self.x_in, feat))
         # ---------------- encoder: ResBlock x L (stylegan2_ocr_arch.py:729-734)
         skips = []
         h, w = H, W
@@ -141,9 +153,9 @@ class _Plan:
             t1 = e16(B, h, w, cin)
             steps.append(ops.conv_same(feat, d['w1'], t1, 3, bias=d['b1'], act=True))
             p = z16(B, h + 2, w + 2, cin)
-            steps.append(lambda a=t1, o=p: ops.fir_pad22(a, o))
+            steps.append(PwOp('fir_pad22', lambda a=t1, o=p: ops.fir_pad22(a, o), t1, p))
             sk_in = e16(B, h // 2, w // 2, cin)
-            steps.append(lambda a=feat, o=sk_in: ops.fir_down2(a, o))
+            steps.append(PwOp('fir_down2', lambda a=feat, o=sk_in: ops.fir_down2(a, o), feat, sk_in))
             sk = e16(B, h // 2, w // 2, cout)
             steps.append(ops.conv_same(sk_in, d['ws'], sk, 1))
             nxt = e16(B, h // 2, w // 2, cout)
@@ -180,11 +192,11 @@ class _Plan:
             d = pk.up[i]
             cin, cout = d['w1'].shape[0], d['w2'].shape[0]
             a = e16(B, h, w, cin)
-            steps.append(lambda x=feat, y=skips[i], o=a: ops.add(x, y, o))
+            steps.append(PwOp('add', lambda x=feat, y=skips[i], o=a: ops.add(x, y, o), feat, skips[i], a))
             t1 = e16(B, h, w, cin)
             steps.append(ops.conv_same(a, d['w1'], t1, 3, bias=d['b1'], act=True))
             u = e16(B, 2 * h, 2 * w, cin)
-            steps.append(lambda x=t1, o=u: ops.bilinear_up2(x, o))
+            steps.append(PwOp('bilinear_up2', lambda x=t1, o=u: ops.bilinear_up2(x, o), t1, u))
             sl = e16(B, h, w, cout)
             steps.append(ops.conv_same(a, d['ws'], sl, 1))
             h2, w2 = 2 * h, 2 * w
@@ -204,7 +216,8 @@ class _Plan:
             self.cond.append((sc, sh))
             rgb = e32(B, 3, h2, w2)
             self.out_rgbs.append(rgb)
-            self.rgb_steps.append(lambda x=feat, dd=d, o=rgb: ops.to_rgb(x, dd['wrgb'], None, dd['brgb'], None, o))
+            self.rgb_steps.append(PwOp('to_rgb', lambda x=feat, dd=d, o=rgb: ops.to_rgb(x, dd['wrgb'], None, dd['brgb'], None, o),
+                                       feat, rgb))
             steps.append(('rgb', len(self.rgb_steps) - 1))
             h, w = h2, w2
         self._hid_keep = None
@@ -247,14 +260,14 @@ class _Plan:
         # per-image ToRGB weights w[o][c] * s_rgb[b][c] for the conv epilogues that fuse ToRGB
         def rgb_weights(layer, s):
             wm = e32(B, 3, layer['w'].shape[1])
-            steps.append(lambda l=layer, ss=s, o=wm: ops.rgb_wmod(l['w'], ss, o))
+            steps.append(PwOp('rgb_wmod', lambda l=layer, ss=s, o=wm: ops.rgb_wmod(l['w'], ss, o), s, wm))
             return wm
 
         wm_rgb1 = rgb_weights(pk.rgb1, s_rgb1)
         wm_rgbs = [rgb_weights(pk.rgbs[lvl], s_rgb[lvl]) for lvl in range(L)]
 
         xs = e16(B, h, w, cch)
-        steps.append(lambda o=xs: ops.modulate_const(pk.const, s_sc1, o))
+        steps.append(PwOp('modulate_const', lambda o=xs: ops.modulate_const(pk.const, s_sc1, o), xs))
         # style_conv1 + to_rgb1 (gfpganv1_ocr_arch.py:108-110): the conv epilogue accumulates the ToRGB dot products
         # and writes its output already multiplied by the modulation of the next conv
         last = L == 0
@@ -265,7 +278,7 @@ class _Plan:
         part = op.attach_rgb(wm_rgb1, (h, w), no_store=last)
         steps.append(op)
         skip = e32(B, 3, h, w)
-        steps.append(lambda pt=part, o=skip: ops.rgb_combine(pt, pk.rgb1['bias'], None, o))
+        steps.append(PwOp('rgb_combine', lambda pt=part, o=skip: ops.rgb_combine(pt, pk.rgb1['bias'], None, o), part, skip))
         xs = xs_next
         for lvl in range(L):
             c1, c2 = pk.sconv[2 * lvl], pk.sconv[2 * lvl + 1]
@@ -280,8 +293,9 @@ class _Plan:
             self.noise_shapes += [(h2, w2), (h2, w2)]
             sc, sh = self.cond[lvl]
             xs2 = e16(B, h2, w2, cout)
-            steps.append(lambda r=raw, o=xs2, n=n1, c=c1, a=sc, b_=sh, sn=s_conv[2 * lvl + 1]:
-                         ops.upfir_act(r, o, n, o.shape[1] * o.shape[2], c['gain'], c['bias'], a, b_, a.shape[3], sn))
+            steps.append(PwOp('upfir_act', lambda r=raw, o=xs2, n=n1, c=c1, a=sc, b_=sh, sn=s_conv[2 * lvl + 1]:
+                              ops.upfir_act(r, o, n, o.shape[1] * o.shape[2], c['gain'], c['bias'], a, b_, a.shape[3], sn),
+                              raw, xs2, n1, sc, sh))
             last = lvl == L - 1
             xs = None if last else e16(B, h2, w2, cout)
             op = ops.conv_same(xs2, c2['w'], xs, 3, bias=c2['bias'], demod=d_conv[2 * lvl + 1], noise=n2,
@@ -290,7 +304,8 @@ class _Plan:
             part = op.attach_rgb(wm_rgbs[lvl], (h2, w2), no_store=last)
             steps.append(op)
             nskip = e32(B, 3, h2, w2)
-            steps.append(lambda pt=part, r=pk.rgbs[lvl], sk=skip, o=nskip: ops.rgb_combine(pt, r['bias'], sk, o))
+            steps.append(PwOp('rgb_combine', lambda pt=part, r=pk.rgbs[lvl], sk=skip, o=nskip: ops.rgb_combine(pt, r['bias'], sk, o),
+                              part, skip, nskip))
             skip = nskip
             h, w = h2, w2
         self.image = skip

@@ -310,6 +310,7 @@ class DemodMulti:
         self.table = _device_records(recs, layers[0][0].device)
         self.n = len(recs)
         self.max_cout = max(wsq.shape[0] for (_, wsq, _, _) in layers)
+        assert all(wsq.shape[1] <= 512 for (_, wsq, _, _) in layers), 'demod_multi keeps a wsq row in registers: cin <= 512'
         self.b = layers[0][0].shape[0]
 
     def __call__(self):

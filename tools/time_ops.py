@@ -29,6 +29,8 @@ def label(st):
         return (f'conv taps={d.num_taps} {d.cin}->{d.cout} M=({d.m_b},{d.m_h},{d.m_w}) tile=({d.tile_b},{d.tile_h},'
                 f'{d.tile_w}) bn={d.block_n} ep[{"b" if d.bias else ""}{"d" if d.demod else ""}{"n" if d.noise else ""}'
                 f'{"a" if d.act else ""}r{d.res_mode}]')
+    if hasattr(st, 'nbytes'):
+        return st.name
     if not hasattr(st, '__code__'):
         return type(st).__name__
     names = [n for n in st.__code__.co_names if n not in ('ops', 'self', 'shape')]
@@ -58,9 +60,8 @@ for st in plan.steps:
         by = 2.0 * (d.m_b * d.m_h * d.m_w * (d.cin + d.cout))
         extra = f'{fl / ms / 1e9:8.1f} TF/s  {by / ms / 1e6:8.1f} GB/s(in+out)'
     else:
-        t = [v for v in (getattr(st, '__defaults__', None) or ()) if torch.is_tensor(v)]
-        by = sum(v.numel() * v.element_size() for v in t)
-        extra = f'{"":8s}       {by / ms / 1e6:8.1f} GB/s(listed tensors)'
+        by = getattr(st, 'nbytes', 0)
+        extra = f'{"":8s}       {by / ms / 1e6:8.1f} GB/s(algorithmic)'
     rows.append((ms, label(st), extra))
     print(f'{ms * 1e3:9.1f} us  {extra}  {label(st)}')
 print(f'total {tot:.3f} ms for B={B} -> {B / tot * 1e3:.0f} crops/s (serialised, no overlap)')
