@@ -23,7 +23,7 @@ static constexpr int kThreads = 64 + kEpiThreads;       // warp 0 producer, warp
 static constexpr int kDemodTable = 2560;  // floats per epilogue group: per-tile tables [demod | out_scale | rgb_w x3]
 static constexpr int kMaxBias = 512;
 static constexpr int kMaxStages = 8;
-static constexpr int kMaxAccStages = 8;  // TMEM accumulator ring: as many 128 x block_n tiles as fit in 512 columns
+static constexpr int kMaxAccStages = 16;  // TMEM accumulator ring: as many 128 x block_n tiles as fit in 512 columns
 
 struct alignas(64) ConvParams {
   CUtensorMap tmap_a[B200IR_MAX_VIEWS];
@@ -34,6 +34,7 @@ struct alignas(64) ConvParams {
   int m_w, m_h, m_b;
   int stages;
   uint32_t idesc;
+  uint32_t idesc_n[3];  // row mode: instruction descriptors for N = 1, 2, 3 x block_n
   uint32_t tmem_cols;
   int acc_stages, acc_shift;
   // row mode (conv_row_kernel): 3x3 stride-1 conv, tile = 128 consecutive pixels of one row, weights resident in
@@ -70,7 +71,6 @@ struct alignas(64) ConvParams {
   long long rgb_plane, rgb_image;  // rgb_h*rgb_w_px, m_b*3*rgb_plane
   int rgb_w_px;
   int no_store;
-  int dbg_noshift;   // profiling aid (env B200IR_DBG_NOSHIFT): row kernel reads all kw taps at the aligned address
   int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
 };
 
@@ -389,6 +389,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
                                               uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride) {
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
+  if (p.dbg_skip_epi) return;
   const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
   const float ag = p.act_gain, slope = p.slope;
   float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
@@ -709,9 +710,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
     static int dbg = -1;
     if (dbg < 0) dbg = (getenv("B200IR_DBG_SKIP_EPI") != nullptr) ? 1 : 0;
     p.dbg_skip_epi = dbg;
-    static int dbg2 = -1;
-    if (dbg2 < 0) dbg2 = (getenv("B200IR_DBG_NOSHIFT") != nullptr) ? 1 : 0;
-    p.dbg_noshift = dbg2;
+
   }
   // ---- specialised epilogue selection
   {
@@ -742,7 +741,8 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   {
     bool row_ok = d->num_views == 1 && d->num_taps == 9 && d->tile_w == 128 && d->tile_h == 1 && d->tile_b == 1 &&
                   d->block_n == d->cout && d->out_x_mul == 1 && d->out_y_mul == 1 && d->out_x_off == 0 &&
-                  d->out_y_off == 0 && d->row_mode != 0;
+                  d->out_y_off == 0 && d->row_mode != 0 &&
+                  (d->cout == 16 || d->cout == 32 || d->cout == 64);  // N = 3*cout <= 256, ring of 512/cout slots
     for (int t = 0; row_ok && t < 9; ++t)
       row_ok = d->tap_view[t] == 0 && d->tap_dx[t] == (t % 3) - 1 && d->tap_dy[t] == (t / 3) - 1;
     if (row_ok) {
@@ -751,7 +751,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
       const int tail_r = kTailBytes;
       int slots = (g_smem_optin - 1024 - tail_r - w_bytes) / slot_bytes;
       if (slots > kMaxStages) slots = kMaxStages;
-      if (slots >= 3 * p.k_chunks + 1) {
+      if (slots >= 2 * p.k_chunks) {
         // re-encode the activation map with the 130-pixel halo box
         const b200ir_view& a = d->a[0];
         cuuint64_t dims[4] = {(cuuint64_t)a.c, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)a.b};
@@ -763,11 +763,13 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
         p.row_R = R;
         p.row_chunks = (d->m_h + R - 1) / R;
         p.row_items = d->m_b * p.tiles_w * p.row_chunks;
-        row_ok = p.row_items >= 2 * g_num_sms;  // too little parallelism at small batch: generic tiles are faster
+        // too little parallelism at small batch: generic tiles are faster (row_mode == 2 forces the variant: tests)
+        row_ok = p.row_items >= 2 * g_num_sms || d->row_mode == 2;
         p.row_slots = slots;
         p.row_slot_bytes = slot_bytes;
         p.row_w_bytes = w_bytes;
-        p.desc_mode = d->row_mode == 2 ? 1 : 0;
+        p.desc_mode = 0;
+        for (int n = 1; n <= 3; ++n) p.idesc_n[n - 1] = make_idesc_f16(kBlockM, n * d->block_n, false);
         const int smem_row = w_bytes + slots * slot_bytes + tail_r + 1024;
         if (row_ok) {
           int grid_r = p.row_items < g_num_sms ? p.row_items : g_num_sms;

@@ -221,10 +221,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 // ================================================================================================ row mode
 // 3x3 stride-1 conv for low channel counts at high resolution.  A work item is (image b, 128-pixel column segment,
 // chunk of R output rows).  Every input row segment (130 pixels: 1-pixel halo each side, TMA zero fill outside the
-// image) is loaded ONCE into a ring slot; the three kw taps read it through descriptors whose start address is shifted
-// by kw pixels (measured on B200: the swizzle XOR uses absolute shared-memory address bits, so row-shifted start
-// addresses work with the matrix-base-offset field left at 0 — tools/try_row_mode.py), the three kh taps reuse it for
-// three consecutive output rows.  All 9 tap weight tiles stay resident in shared memory for the whole kernel.
+// image) is loaded ONCE into a ring slot and consumed ONCE: input row i of an item contributes to the output rows
+// i-2 (kh = 2), i-1 (kh = 1) and i (kh = 0), whose accumulators sit side by side in the TMEM ring, so one MMA with
+// N = 3*cout and the B tile [W(kh=2) | W(kh=1) | W(kh=0)] updates all three.  Per input row that is 3 (kw) x Cin/16
+// MMAs of N = 3*cout instead of 9 x Cin/16 MMAs of N = cout: the A operand (128 x 16 fp16 = 4 KB per MMA) is read from
+// shared memory 3x less often, and with N <= 64 that read, not the tensor pipe, set the MMA rate (measured: 70 cycles
+// per N=64 MMA against a 32-cycle pipe floor).  The three kw taps read the row through descriptors whose start address
+// is shifted by kw pixels (measured on B200: the swizzle XOR uses absolute shared-memory address bits, so row-shifted
+// start addresses work with the matrix-base-offset field left at 0 -- tools/try_row_mode.py).
+// The newest target (output row i) has no partial sum yet: the first MMA of an input row is split so that this slice
+// runs with accumulate = 0; a target run that wraps around the TMEM ring is split in two as well.
+// All 9 tap weight tiles stay resident in shared memory for the whole kernel, grouped per (kw, k-chunk) in kh order 2,1,0.
 struct RowItem {
   int b, seg, y0, rows_out;
 };
@@ -261,7 +268,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_cons
       tma_prefetch_desc(&p.tmap_a[0]);
       tma_prefetch_desc(&p.tmap_b);
       mbar_arrive_expect_tx(s.w_bar, 9 * kc_n * wtile_bytes);
-      for (int t = 0; t < 9 * kc_n; ++t) tma_load_2d(s_w + t * wtile_bytes, &p.tmap_b, s.w_bar, t * kBlockK, 0);
+      const int cin = kc_n * kBlockK;
+      for (int kw = 0; kw < 3; ++kw)
+        for (int kc = 0; kc < kc_n; ++kc)
+          for (int khi = 0; khi < 3; ++khi)  // kh = 2 - khi: ascending output row inside the merged B tile
+            tma_load_2d(s_w + ((kw * kc_n + kc) * 3 + khi) * wtile_bytes, &p.tmap_b, s.w_bar,
+                        ((2 - khi) * 3 + kw) * cin + kc * kBlockK, 0);
     }
     __syncwarp();
     int slot = 0;
@@ -294,63 +306,64 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_cons
     const uint32_t ring_lo = smem_u32(s_ring) >> 4;
     const uint32_t wtile_lo = wtile_bytes >> 4;
     constexpr uint32_t slot_lo = slot_bytes >> 4;
-    const uint32_t px_lo = p.dbg_noshift ? 0u : (row_bytes >> 4);  // one pixel (one smem row) in descriptor units
-    int wait_slot = 0;        // next ring fill to wait for (producer order)
-    uint32_t wait_phase = 0;
-    int row_slot = 0;         // slot of (input row j, kc 0) of the current output row
-    int it = 0;
+    constexpr uint32_t px_lo = row_bytes >> 4;  // one pixel (one smem row) in descriptor units
+    const int ring = p.acc_stages;               // accumulator slots (power of two)
+    int slot = 0;                                // ring slot of (current input row, kc 0)
+    uint32_t phase = 0;
+    int it_base = 0;                             // output rows issued before this item
     for (int item = blockIdx.x; item < p.row_items; item += gridDim.x) {
       const RowItem w = decode_item(p, item);
-      int rows_waited = 0;
-      for (int j = 0; j < w.rows_out; ++j, ++it) {
-        while (rows_waited < j + 3) {  // input rows j .. j+2 must have landed
-          for (int kc = 0; kc < kc_n; ++kc) {
-            mbar_wait(&s.full_bar[wait_slot], wait_phase);
-            if (++wait_slot == nslots) {
-              wait_slot = 0;
-              wait_phase ^= 1u;
-            }
+      for (int i = 0; i < w.rows_out + 2; ++i) {
+        const int row_slot = slot;
+        for (int kc = 0; kc < kc_n; ++kc) {  // this input row has landed (all its k-chunks)
+          mbar_wait(&s.full_bar[slot], phase);
+          if (++slot == nslots) {
+            slot = 0;
+            phase ^= 1u;
           }
-          ++rows_waited;
         }
-        const int acc = it & (p.acc_stages - 1);
-        mbar_wait(&s.tmem_empty[acc], ((it >> p.acc_shift) & 1) ^ 1u);
+        const bool fresh = i < w.rows_out;  // output row i receives its first contribution (kh = 0) from this input row
+        if (fresh) {
+          const int it = it_base + i;
+          mbar_wait(&s.tmem_empty[it & (ring - 1)], ((it >> p.acc_shift) & 1) ^ 1u);
+        }
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t tmem_d = tmem_base + acc * p.block_n;
+          const int j_lo = max(i - 2, 0), j_hi = min(i, w.rows_out - 1);
+          // one accumulating run over output rows [ja, jb] (split where the accumulator ring wraps)
+          auto run = [&](int ja, int jb, uint64_t a_desc, uint32_t tile_lo, uint32_t accumulate) {
+            const int n = jb - ja + 1;
+            const int sa = (it_base + ja) & (ring - 1);
+            const int n1 = min(n, ring - sa);
+            const uint32_t b_lo = tile_lo + (ja - (i - 2)) * wtile_lo;
+            umma_f16(tmem_base + sa * p.block_n, a_desc, desc64(b_lo, hi), p.idesc_n[n1 - 1], accumulate);
+            if (n1 < n) umma_f16(tmem_base, a_desc, desc64(b_lo + n1 * wtile_lo, hi), p.idesc_n[n - n1 - 1], accumulate);
+          };
           int sl = row_slot;
-          uint32_t b_lo = w_lo;
-          for (int kh = 0; kh < 3; ++kh) {
-            for (int kc = 0; kc < kc_n; ++kc) {
-              const uint32_t a_lo = ring_lo + sl * slot_lo;
+          for (int kc = 0; kc < kc_n; ++kc) {
+            const uint32_t a_lo = ring_lo + sl * slot_lo;
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                const uint32_t bt_lo = b_lo + (kw * kc_n) * wtile_lo;  // tap (kh,kw), chunk kc
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t tile_lo = w_lo + (kw * kc_n + kc) * 3 * wtile_lo;
 #pragma unroll
-                for (int k = 0; k < k_steps; ++k)
-                  umma_f16(tmem_d, desc64(a_lo + kw * px_lo + 2 * k, hi), desc64(bt_lo + 2 * k, hi), p.idesc,
-                           (kh > 0 || kc > 0 || kw > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < k_steps; ++k) {
+                const uint64_t a_desc = desc64(a_lo + kw * px_lo + 2 * k, hi);
+                if (fresh && kc == 0 && kw == 0 && k == 0) {
+                  if (j_hi > j_lo) run(j_lo, j_hi - 1, a_desc, tile_lo + 2 * k, 1u);
+                  run(j_hi, j_hi, a_desc, tile_lo + 2 * k, 0u);
+                } else {
+                  run(j_lo, j_hi, a_desc, tile_lo + 2 * k, 1u);
+                }
               }
-              b_lo += wtile_lo;
-              if (++sl == nslots) sl = 0;
             }
-            b_lo += 2 * kc_n * wtile_lo;  // next kh: skip the kw=1,2 tiles of this kh
-          }
-          umma_commit(&s.tmem_full[acc]);
-          // input row j is dead after output row j; the last output row of the item also retires rows j+1, j+2
-          const int retire = ((j == w.rows_out - 1) ? 3 : 1) * kc_n;
-          sl = row_slot;
-          for (int r = 0; r < retire; ++r) {
-            umma_commit(&s.empty_bar[sl]);
+            umma_commit(&s.empty_bar[sl]);  // this (row, kc) slot is consumed once
             if (++sl == nslots) sl = 0;
           }
+          if (i >= 2) umma_commit(&s.tmem_full[(it_base + i - 2) & (ring - 1)]);  // output row i-2 is complete
         }
         __syncwarp();
-        row_slot += kc_n;
-        if (row_slot >= nslots) row_slot -= nslots;
       }
-      row_slot += 2 * kc_n;  // the two extra input rows of the item
-      if (row_slot >= nslots) row_slot -= nslots;
+      it_base += w.rows_out;
     }
   } else {
     // ---------------- epilogue: two groups of 4 warps drain alternate output rows

@@ -137,13 +137,13 @@ NUM_SMS = 148
 def row_mode_ok(b, h, w, cin, cout):
     """Mirror of the eligibility test of the row-sliding conv variant in b200ir_conv_igemm: low channel counts at
     high resolution (L2-bound with generic tiles), weights resident in shared memory, enough work items."""
-    if cin > 128 or cout > 256 or cout % 16 or w < 128:
+    if cin > 128 or cout not in (16, 32, 64) or w < 128:
         return False
     block_k = 64 if cin % 64 == 0 else (32 if cin % 32 == 0 else 16)
     kc = cin // block_k
     w_bytes = 9 * kc * cout * block_k * 2
-    slots = (232448 - 1024 - (512 + 512 * 4 + 2 * 2048 * 4) - w_bytes) // (136 * block_k * 2)
-    if slots < 3 * kc + 1:
+    slots = (232448 - 1024 - (512 + 512 * 4 + 2 * 2560 * 4) - w_bytes) // (136 * block_k * 2)
+    if slots < 2 * kc:
         return False
     return b * -(-w // 128) * -(-h // 8) >= 2 * NUM_SMS
 

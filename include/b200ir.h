@@ -107,8 +107,9 @@ typedef struct {
   int32_t res_w, res_h; /* extents of the residual tensor (for the clamp of mode 2) */
   float res_scale;
   int32_t max_ctas; /* 0: one CTA per SM */
-  int32_t row_mode; /* 0: generic tiles; 1: allow the row-sliding variant (3x3 stride 1, tile 128x1x1, weights resident
-                       in shared memory; picked only when eligible and the batch gives enough work items) */
+  int32_t row_mode; /* 0: generic tiles; 1: allow the row-sliding variant (3x3 stride 1, tile 128x1x1, cout 16/32/64,
+                       weights resident in shared memory; picked only when eligible and the batch gives enough work
+                       items); 2: take it whenever eligible, whatever the batch */
   const float* out_scale; /* [m_b][cout] or NULL */
   const float* rgb_w;     /* [m_b][3][cout] or NULL */
   float* rgb_part;        /* [cout/block_n][m_b][3][rgb_h][rgb_w_px] fp32, required with rgb_w */

@@ -409,3 +409,50 @@ def test_conv_fused_to_rgb_and_next_modulation(B, H, W, C, no_store, with_skip):
     check_close(rgb, ref_rgb, tol=2e-3, what=f'fused toRGB C={C} {H}x{W}')
     if not no_store:
         check_close(nchw32(out), y * s_next[:, :, None, None], what='conv out * s_next')
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout,kind', [
+    (1, 128, 384, 32, 32, 'plain'), (2, 64, 192, 64, 64, 'plain'), (3, 40, 200, 32, 64, 'plain'),
+    (1, 128, 384, 64, 32, 'res2'), (2, 16, 130, 16, 16, 'plain'), (2, 9, 128, 64, 64, 'modrgb'),
+    (2, 33, 256, 64, 64, 'modrgb'), (1, 1, 128, 32, 32, 'plain'), (2, 2, 140, 64, 32, 'plain'),
+    (5, 24, 384, 128, 64, 'plain'),
+])
+def test_row_sliding_conv_forced(B, H, W, cin, cout, kind):
+    """The row-sliding conv variant (one MMA of N = 3*cout per input row and kw tap, accumulator ring in TMEM), forced
+    at small sizes so that ring wrap-around, short row chunks and ragged widths are covered."""
+    ops = _ops()
+    torch.manual_seed(14)
+    x = torch.randn(B, cin, H, W, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    bias = torch.randn(cout, device=DEV) * 0.1
+    xh, wh = nhwc16(x), pack3x3(w)
+    wr = wh.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    out = torch.empty(B, H, W, cout, device=DEV, dtype=torch.float16)
+    kw = dict(bias=bias, act=True, tile=(128, 1, 1), row_mode=2, block_n=cout)
+    y = F.conv2d(nchw32(xh), wr, padding=1)
+    if kind == 'res2':
+        assert H % 2 == 0 and W % 2 == 0
+        lo = nhwc16(torch.randn(B, cout, H // 2, W // 2, device=DEV))
+        kw.update(res=lo, res_mode=2, res_strides=(cout, (W // 2) * cout, (H // 2) * (W // 2) * cout),
+                  res_wh=(W // 2, H // 2), res_scale=1 / math.sqrt(2))
+        ref = (F.leaky_relu(y + bias[None, :, None, None], 0.2) * math.sqrt(2) +
+               F.interpolate(nchw32(lo), scale_factor=2, mode='bilinear', align_corners=False)) / math.sqrt(2)
+    elif kind == 'modrgb':
+        demod = torch.rand(B, cout, device=DEV) + 0.5
+        noise = torch.randn(B, 1, H, W, device=DEV)
+        gain = torch.tensor([0.1], device=DEV)
+        s_next = torch.rand(B, cout, device=DEV) + 0.5
+        wm = torch.randn(B, 3, cout, device=DEV) / math.sqrt(cout)
+        kw.update(demod=demod, noise=noise, noise_gain=gain, noise_strides=(H * W, W), out_scale=s_next)
+        yy = F.leaky_relu(y * demod[:, :, None, None] + gain * noise + bias[None, :, None, None], 0.2) * math.sqrt(2)
+        ref = yy * s_next[:, :, None, None]
+    else:
+        ref = F.leaky_relu(y + bias[None, :, None, None], 0.2) * math.sqrt(2)
+    op = ops.conv_same(xh, wh, out, 3, **kw)
+    part = op.attach_rgb(wm, (H, W)) if kind == 'modrgb' else None
+    op()
+    op()     # a second launch must give the same result (no state left in TMEM / barriers)
+    torch.cuda.synchronize()
+    check_close(nchw32(out), ref, what=f'row conv {cin}->{cout} @{H}x{W} B{B} {kind}')
+    if kind == 'modrgb':
+        check_close(part.sum(0), torch.einsum('bchw,boc->bohw', yy, wm), tol=2e-3, what='row conv fused rgb')
