@@ -10,8 +10,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libb200ir.so')
-SOURCES = ['api.cu', 'conv_igemm.cu', 'pointwise.cu', 'fir_tma.cu', 'degrade.cu']
-HEADERS = ['ptx.cuh', 'host_common.h', 'conv_kernels.cuh', os.path.join('..', '..', 'include', 'b200ir.h')]
+SOURCES = ['api.cu', 'conv_igemm.cu', 'conv_epi_generic.cu', 'conv_epi0.cu', 'conv_epi1.cu', 'conv_epi2.cu', 'conv_epi3.cu',
+           'conv_epi4.cu', 'conv_epi5.cu', 'pointwise.cu', 'fir_tma.cu', 'degrade.cu']
+HEADERS = ['ptx.cuh', 'host_common.h', 'conv_common.cuh', os.path.join('..', '..', 'include', 'b200ir.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -29,16 +30,23 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    objs = []
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
-    for s in SOURCES:
-        obj = os.path.join(HERE, 'build', s.replace('.cu', '.o'))
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, s), '-o', obj]
+
+    def compile_one(src):
+        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
+        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, cmd, r
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:   # one nvcc process per translation unit
+        results = list(ex.map(compile_one, SOURCES))
+    objs = []
+    for src, obj, cmd, r in results:
         if verbose or r.returncode != 0:
             sys.stderr.write(' '.join(cmd) + '\n' + r.stdout + r.stderr)
         if r.returncode != 0:
-            raise RuntimeError(f'nvcc failed on {s}')
+            raise RuntimeError(f'nvcc failed on {src}')
         objs.append(obj)
     cmd = [nvcc, '-shared', '-o', LIB, *objs, '-lcudart_static', '-ldl', '-lrt', '-lpthread']
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,0 +1,975 @@
+// Implicit-GEMM convolution for sm_100a: TMA box loads (im2col by shifted boxes with out-of-bounds zero fill)
+// -> 128B/64B-swizzled shared memory -> tcgen05.mma (M=128, N=block_n, K=16, fp16 x fp16 -> fp32 in TMEM)
+// -> tcgen05.ld epilogue with bias / demodulation / noise / leaky-ReLU / residual fused.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 =
+// epilogue (one TMEM lane quarter each).  Two TMEM accumulator stages let the epilogue of tile i overlap the
+// main loop of tile i+1.
+//
+// Reference semantics implemented here: see include/b200ir.h (b200ir_conv_igemm).
+#pragma once
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace b200ir {
+
+static constexpr int kBlockM = 128;
+static constexpr int kEpiWarps = 8;                         // two per TMEM lane quarter
+static constexpr int kEpiThreads = kEpiWarps * 32;
+static constexpr int kThreads = 64 + kEpiThreads;       // warp 0 producer, warp 1 MMA, warps 2.. epilogue
+static constexpr int kDemodTable = 2560;  // floats per epilogue group: per-tile tables [demod | out_scale | rgb_w x3]
+static constexpr int kMaxBias = 512;
+static constexpr int kMaxStages = 8;
+static constexpr int kMaxAccStages = 16;  // TMEM accumulator ring: as many 128 x block_n tiles as fit in 512 columns
+
+struct alignas(64) ConvParams {
+  CUtensorMap tmap_a[B200IR_MAX_VIEWS];
+  CUtensorMap tmap_b;
+  int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles;
+  int tile_w, tile_h, tile_b;
+  int block_n, block_k, k_chunks, num_taps;
+  int m_w, m_h, m_b;
+  int stages;
+  uint32_t idesc;
+  uint32_t idesc_n[3];  // row mode: instruction descriptors for N = 1, 2, 3 x block_n
+  uint32_t tmem_cols;
+  int acc_stages, acc_shift;
+  // row mode (conv_row_kernel): 3x3 stride-1 conv, tile = 128 consecutive pixels of one row, weights resident in
+  // shared memory, each input row segment loaded once (with a 1-pixel halo) and reused for 3 kw shifts x 3 output rows
+  int row_R, row_chunks, row_items, row_slots, row_slot_bytes, row_w_bytes, desc_mode;
+  int smem_demod;  // 1: per-tile demod table staged in shared memory
+  int smem_aux;    // 1: out_scale / rgb_w tables staged behind it (4 more tables of tile_b * block_n floats)
+  int st256;       // 1: fp16 output rows are 32-byte aligned -> 256-bit stores
+  float act_gain;  // sqrt(2) when act is set (folded into the bias / demod / noise terms), else 1; the specialised
+                   // epilogues (epi >= 0) also fold the residual scale into it
+  float slope;     // leaky-ReLU slope (0.2), 1.0 when the layer has no activation: v = max(v, slope * v)
+  int epi;         // index into kEpiProfiles (compile-time specialised epilogue) or -1 for the run-time generic one
+  int8_t tap_view[B200IR_MAX_TAPS], tap_dx[B200IR_MAX_TAPS], tap_dy[B200IR_MAX_TAPS];
+  // epilogue
+  void* out;
+  int out_fp32;
+  long long out_sx, out_sy, out_sb;
+  int out_c_off, out_x_mul, out_x_off, out_y_mul, out_y_off;
+  int cout;
+  const float* bias;
+  const float* demod;
+  const float* noise;
+  const float* noise_gain;
+  long long noise_sb, noise_sy;
+  int act;
+  int res_mode;
+  const __half* res;
+  long long res_sx, res_sy, res_sb;
+  int res_w, res_h;
+  float res_scale;
+  const float* out_scale;
+  const float* rgb_w;
+  float* rgb_part;
+  long long rgb_plane, rgb_image;  // rgb_h*rgb_w_px, m_b*3*rgb_plane
+  int rgb_w_px;
+  int no_store;
+  int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
+};
+
+struct TileCoord {
+  int x0, y0, b0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord t;
+  int n_tile = tile % p.tiles_n;
+  int m = tile / p.tiles_n;
+  int xw = m % p.tiles_w;
+  m /= p.tiles_w;
+  int yh = m % p.tiles_h;
+  int bb = m / p.tiles_h;
+  t.x0 = xw * p.tile_w;
+  t.y0 = yh * p.tile_h;
+  t.b0 = bb * p.tile_b;
+  t.n0 = n_tile * p.block_n;
+  return t;
+}
+
+__device__ __forceinline__ void unpack_half8(const uint4& q, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 x = __half22float2(h[i]);
+    f[2 * i] = x.x;
+    f[2 * i + 1] = x.y;
+  }
+}
+
+// Per-thread addressing of one output position, computed (and the noise value fetched) BEFORE the accumulator is
+// ready so that none of it sits on the MMA -> epilogue critical path.
+struct EpiRow {
+  long long out_off;
+  long long chan_off;  // b * cout + n0: row of the per-image tables (out_scale)
+  long long rgbw_off;  // b * 3 * cout + n0
+  long long rgb_off;   // offset of (n-tile, b, 0, yo, xo) in rgb_part
+  float nz;
+  const __half* r00;
+  const __half* r01;
+  const __half* r10;
+  const __half* r11;
+  float wy0, wy1, wx0, wx1;
+};
+
+__device__ __forceinline__ EpiRow epi_setup(const ConvParams& p, int x, int y, int b, int n0, bool valid, float gain) {
+  EpiRow r;
+  const int xo = x * p.out_x_mul + p.out_x_off;
+  const int yo = y * p.out_y_mul + p.out_y_off;
+  r.out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx + p.out_c_off + n0;
+  r.chan_off = (long long)b * p.cout + n0;
+  r.rgbw_off = (long long)b * 3 * p.cout + n0;
+  r.rgb_off = (long long)(n0 / p.block_n) * p.rgb_image + (long long)b * 3 * p.rgb_plane + (long long)yo * p.rgb_w_px + xo;
+  r.nz = 0.f;
+  if (valid && p.noise != nullptr) r.nz = __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);  // scaled by the caller later
+  r.r00 = r.r01 = r.r10 = r.r11 = nullptr;
+  r.wy0 = r.wy1 = r.wx0 = r.wx1 = 0.f;
+  if (valid && p.res_mode == 1) {
+    r.r00 = p.res + (long long)b * p.res_sb + (long long)yo * p.res_sy + (long long)xo * p.res_sx + n0;
+  } else if (valid && p.res_mode == 2) {
+    // F.interpolate(scale 2, bilinear, align_corners=False): even 2k -> .25*x[k-1] + .75*x[k], odd 2k+1 ->
+    // .75*x[k] + .25*x[k+1], indices clamped to the tensor.
+    const int ky = yo >> 1, kx = xo >> 1;
+    int ya, yb, xa, xb;
+    if (yo & 1) { ya = ky; yb = min(ky + 1, p.res_h - 1); r.wy0 = 0.75f; r.wy1 = 0.25f; }
+    else        { ya = max(ky - 1, 0); yb = ky; r.wy0 = 0.25f; r.wy1 = 0.75f; }
+    if (xo & 1) { xa = kx; xb = min(kx + 1, p.res_w - 1); r.wx0 = 0.75f; r.wx1 = 0.25f; }
+    else        { xa = max(kx - 1, 0); xb = kx; r.wx0 = 0.25f; r.wx1 = 0.75f; }
+    const __half* rb = p.res + (long long)b * p.res_sb + n0;
+    r.r00 = rb + (long long)ya * p.res_sy + (long long)xa * p.res_sx;
+    r.r01 = rb + (long long)ya * p.res_sy + (long long)xb * p.res_sx;
+    r.r10 = rb + (long long)yb * p.res_sy + (long long)xa * p.res_sx;
+    r.r11 = rb + (long long)yb * p.res_sy + (long long)xb * p.res_sx;
+  }
+  return r;
+}
+
+// Drains this thread's row of one 128 x block_n accumulator tile, 16 columns at a time (columns c_begin, c_begin +
+// c_step, ...: two warps share a TMEM lane quarter).  Per chunk the TMEM load is issued first, the operands that do not
+// depend on it (bias / demod from shared memory, residual from global) are fetched while it is in flight.
+//   s_bias  : shared memory, bias[n0 ...] (zeros when the layer has no bias)
+//   s_demod : shared memory, demod[b][n0 ...] for this row's image, or nullptr
+//   g_demod : global fallback for demod (used when the per-tile table does not fit), or nullptr
+//   s_aux   : shared memory, [out_scale | rgb_w[0] | rgb_w[1] | rgb_w[2]] rows of this row's image, aux_stride floats
+//             apart, or nullptr (then out_scale / rgb_w come from global memory: with ~227 KB of dynamic shared memory
+//             there is almost no L1 left, so every such load is an L2 round trip -- measured as the top stall)
+// All shared-memory tables are passed as 32-bit shared addresses and read with ld.shared: selecting between a shared
+// and a global POINTER makes the compiler emit generic loads, which take the long L1TEX path (measured).
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+//   s_bias  : shared address of bias[n0 ...] (zeros when the layer has no bias); 0 -> g_bias (global, wide layers)
+//   s_demod : shared address of demod[b][n0 ...] for this row's image, or 0
+//   s_aux   : shared address of the [out_scale | rgb_w[0] | rgb_w[1] | rgb_w[2]] rows, aux_stride floats apart, or 0
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
+                                              uint32_t full_phase, EpiRow r, bool valid, float gain, uint32_t s_bias,
+                                              const float* g_bias, uint32_t s_demod, const float* g_demod,
+                                              uint32_t s_aux, int aux_stride, int c_begin, int c_step) {
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+  if (p.dbg_skip_epi) return;
+  r.nz *= gain;  // the noise load was issued in epi_setup, long before this first use
+  float rgb_acc[3] = {0.f, 0.f, 0.f};
+  for (int c0 = c_begin; c0 < p.block_n; c0 += c_step) {
+    uint32_t raw[16];
+    tmem_ld16(taddr + c0, raw);
+    float4 bs[4], dm[4];
+    if (s_bias != 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bs[j] = lds_f4(s_bias + (c0 + 4 * j) * 4);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bs[j] = __ldg(reinterpret_cast<const float4*>(g_bias + c0) + j);
+    }
+    if (s_demod != 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = lds_f4(s_demod + (c0 + 4 * j) * 4);
+    } else if (g_demod != nullptr && valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dm[j] = __ldg(reinterpret_cast<const float4*>(g_demod + c0) + j);
+        dm[j].x *= p.act_gain; dm[j].y *= p.act_gain; dm[j].z *= p.act_gain; dm[j].w *= p.act_gain;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = make_float4(p.act_gain, p.act_gain, p.act_gain, p.act_gain);
+    }
+    uint4 ra[2], rb[2], rc[2], rd[2];
+    if (valid && p.res_mode != 0) {
+      ra[0] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0));
+      ra[1] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0) + 1);
+      if (p.res_mode == 2) {
+        rb[0] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0));
+        rb[1] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0) + 1);
+        rc[0] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0));
+        rc[1] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0) + 1);
+        rd[0] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0));
+        rd[1] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0) + 1);
+      }
+    }
+    tmem_ld_wait16(raw);
+    if (valid) {
+      // bias / demod / noise arrive pre-multiplied by the activation gain (sqrt 2) when act is set, so the
+      // leaky-ReLU is just max(v, 0.2 v)
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[4 * j] = __uint_as_float(raw[4 * j]) * dm[j].x + (bs[j].x + r.nz);
+        v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) * dm[j].y + (bs[j].y + r.nz);
+        v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) * dm[j].z + (bs[j].z + r.nz);
+        v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) * dm[j].w + (bs[j].w + r.nz);
+      }
+      if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+      }
+      if (p.res_mode == 1) {
+        float f[16];
+        unpack_half8(ra[0], f);
+        unpack_half8(ra[1], f + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (v[j] + f[j]) * p.res_scale;
+      } else if (p.res_mode == 2) {
+        float fa[16], fb[16], fc[16], fd[16];
+        unpack_half8(ra[0], fa); unpack_half8(ra[1], fa + 8);
+        unpack_half8(rb[0], fb); unpack_half8(rb[1], fb + 8);
+        unpack_half8(rc[0], fc); unpack_half8(rc[1], fc + 8);
+        unpack_half8(rd[0], fd); unpack_half8(rd[1], fd + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float up = r.wy0 * (r.wx0 * fa[j] + r.wx1 * fb[j]) + r.wy1 * (r.wx0 * fc[j] + r.wx1 * fd[j]);
+          v[j] = (v[j] + up) * p.res_scale;
+        }
+      }
+      if (p.rgb_w != nullptr) {
+        if (s_aux != 0) {
+#pragma unroll
+          for (int o = 0; o < 3; ++o) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 w4 = lds_f4(s_aux + ((1 + o) * aux_stride + c0 + 4 * j) * 4);
+              rgb_acc[o] = fmaf(v[4 * j], w4.x, rgb_acc[o]);
+              rgb_acc[o] = fmaf(v[4 * j + 1], w4.y, rgb_acc[o]);
+              rgb_acc[o] = fmaf(v[4 * j + 2], w4.z, rgb_acc[o]);
+              rgb_acc[o] = fmaf(v[4 * j + 3], w4.w, rgb_acc[o]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int o = 0; o < 3; ++o) {
+            const float4* wp = reinterpret_cast<const float4*>(p.rgb_w + r.rgbw_off + (long long)o * p.cout + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 w4 = __ldg(wp + j);
+              rgb_acc[o] = fmaf(v[4 * j], w4.x, rgb_acc[o]);
+              rgb_acc[o] = fmaf(v[4 * j + 1], w4.y, rgb_acc[o]);
+              rgb_acc[o] = fmaf(v[4 * j + 2], w4.z, rgb_acc[o]);
+              rgb_acc[o] = fmaf(v[4 * j + 3], w4.w, rgb_acc[o]);
+            }
+          }
+        }
+      }
+      if (p.out_scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 s4 = (s_aux != 0) ? lds_f4(s_aux + (c0 + 4 * j) * 4)
+                                         : __ldg(reinterpret_cast<const float4*>(p.out_scale + r.chan_off + c0) + j);
+          v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+        }
+      }
+      if (p.no_store) {
+      } else if (p.out_fp32) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r.out_off + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        __half* op = reinterpret_cast<__half*>(p.out) + r.out_off + c0;
+        if (p.st256) {  // one full 32-byte sector per thread and instruction (no partial-sector writes in L2)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]),
+                       "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
+        } else {
+          reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+  }
+  if (p.rgb_w != nullptr && valid) {
+#pragma unroll
+    for (int o = 0; o < 3; ++o) p.rgb_part[r.rgb_off + o * p.rgb_plane] = rgb_acc[o];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ specialised epilogues
+// The generic epilogue above tests every feature flag per 16-column chunk (measured: ~550 SASS instructions per chunk,
+// which made the epilogue -- not the MMA main loop -- the pace setter of every layer with K <= 1152).  The layers of
+// the network use six feature combinations; each gets an epilogue with the flags as template constants.
+enum : int { F_DEMOD = 1, F_NOISE = 2, F_RES1 = 4, F_RES2 = 8, F_RGB = 16, F_NOSTORE = 32 };
+static constexpr int kNumEpiProfiles = 6;
+__host__ __device__ constexpr int epi_profile_flags(int i) {
+  return i == 0   ? 0
+         : i == 1 ? F_RES1
+         : i == 2 ? F_RES2
+         : i == 3 ? F_DEMOD
+         : i == 4 ? (F_DEMOD | F_NOISE | F_RGB)
+                  : (F_DEMOD | F_NOISE | F_RGB | F_NOSTORE);
+}
+
+struct FastRow {
+  __half* out;  // output row of this position, first channel of the N-tile
+  float* rgb;   // partial ToRGB plane element of this position (channel 0)
+  float nz;
+  const __half* r00;
+  const __half* r01;
+  const __half* r10;
+  const __half* r11;
+  float w00, w01, w10, w11;  // bilinear weights x residual scale
+};
+
+template <int F>
+__device__ __forceinline__ FastRow fast_setup(const ConvParams& p, int x, int y, int b, int n0, bool valid) {
+  FastRow r;
+  const int xo = x * p.out_x_mul + p.out_x_off;
+  const int yo = y * p.out_y_mul + p.out_y_off;
+  r.out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_sb + (long long)yo * p.out_sy +
+          (long long)xo * p.out_sx + p.out_c_off + n0;
+  r.rgb = nullptr;
+  if (F & F_RGB)
+    r.rgb = p.rgb_part + (long long)(n0 / p.block_n) * p.rgb_image + (long long)b * 3 * p.rgb_plane +
+            (long long)yo * p.rgb_w_px + xo;
+  r.nz = 0.f;
+  if ((F & F_NOISE) && valid) r.nz = __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);
+  r.r00 = r.r01 = r.r10 = r.r11 = nullptr;
+  r.w00 = r.w01 = r.w10 = r.w11 = 0.f;
+  if ((F & F_RES1) && valid) {
+    r.r00 = p.res + (long long)b * p.res_sb + (long long)yo * p.res_sy + (long long)xo * p.res_sx + n0;
+    r.w00 = p.res_scale;
+  }
+  if ((F & F_RES2) && valid) {
+    const int ky = yo >> 1, kx = xo >> 1;
+    int ya, yb, xa, xb;
+    float wy0, wy1, wx0, wx1;
+    if (yo & 1) { ya = ky; yb = min(ky + 1, p.res_h - 1); wy0 = 0.75f; wy1 = 0.25f; }
+    else        { ya = max(ky - 1, 0); yb = ky; wy0 = 0.25f; wy1 = 0.75f; }
+    if (xo & 1) { xa = kx; xb = min(kx + 1, p.res_w - 1); wx0 = 0.75f; wx1 = 0.25f; }
+    else        { xa = max(kx - 1, 0); xb = kx; wx0 = 0.25f; wx1 = 0.75f; }
+    const __half* rb = p.res + (long long)b * p.res_sb + n0;
+    r.r00 = rb + (long long)ya * p.res_sy + (long long)xa * p.res_sx;
+    r.r01 = rb + (long long)ya * p.res_sy + (long long)xb * p.res_sx;
+    r.r10 = rb + (long long)yb * p.res_sy + (long long)xa * p.res_sx;
+    r.r11 = rb + (long long)yb * p.res_sy + (long long)xb * p.res_sx;
+    wy0 *= p.res_scale;
+    wy1 *= p.res_scale;
+    r.w00 = wy0 * wx0; r.w01 = wy0 * wx1; r.w10 = wy1 * wx0; r.w11 = wy1 * wx1;
+  }
+  return r;
+}
+
+// fp16 NHWC output with 32-byte aligned rows, bias (and demod / aux tables) in shared memory, gains pre-folded:
+//   v = acc * (demod*g | g) + (bias*g + noise*gain*g);  v = max(v, slope*v);  v += res * w (w carries the residual scale)
+template <int F>
+__device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
+                                              uint32_t full_phase, const FastRow& r, bool valid, float gain,
+                                              uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride) {
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+  if (p.dbg_skip_epi) return;
+  const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
+  const float ag = p.act_gain, slope = p.slope;
+  float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+    uint32_t raw[16];
+    tmem_ld16(taddr + c0, raw);
+    float4 bs[4], dm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bs[j] = lds_f4(s_bias + (c0 + 4 * j) * 4);
+    if (F & F_DEMOD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = lds_f4(s_demod + (c0 + 4 * j) * 4);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = make_float4(ag, ag, ag, ag);
+    }
+    uint4 ra[2], rb[2], rc[2], rd[2];
+    if ((F & (F_RES1 | F_RES2)) && valid) {
+      ra[0] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0));
+      ra[1] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0) + 1);
+      if (F & F_RES2) {
+        rb[0] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0));
+        rb[1] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0) + 1);
+        rc[0] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0));
+        rc[1] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0) + 1);
+        rd[0] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0));
+        rd[1] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0) + 1);
+      }
+    }
+    tmem_ld_wait16(raw);
+    if (!valid) continue;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), dm[j].x, bs[j].x + nz);
+      v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), dm[j].y, bs[j].y + nz);
+      v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), dm[j].z, bs[j].z + nz);
+      v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), dm[j].w, bs[j].w + nz);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+    if (F & F_RES1) {
+      float f[16];
+      unpack_half8(ra[0], f);
+      unpack_half8(ra[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
+    }
+    if (F & F_RES2) {
+      float f[16];
+      unpack_half8(ra[0], f); unpack_half8(ra[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
+      unpack_half8(rb[0], f); unpack_half8(rb[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w01, v[j]);
+      unpack_half8(rc[0], f); unpack_half8(rc[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w10, v[j]);
+      unpack_half8(rd[0], f); unpack_half8(rd[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w11, v[j]);
+    }
+    if (F & F_RGB) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w0 = lds_f4(s_aux + (aux_stride + c0 + 4 * j) * 4);
+        const float4 w1 = lds_f4(s_aux + (2 * aux_stride + c0 + 4 * j) * 4);
+        const float4 w2 = lds_f4(s_aux + (3 * aux_stride + c0 + 4 * j) * 4);
+        rgb0 = fmaf(v[4 * j], w0.x, rgb0); rgb1 = fmaf(v[4 * j], w1.x, rgb1); rgb2 = fmaf(v[4 * j], w2.x, rgb2);
+        rgb0 = fmaf(v[4 * j + 1], w0.y, rgb0); rgb1 = fmaf(v[4 * j + 1], w1.y, rgb1); rgb2 = fmaf(v[4 * j + 1], w2.y, rgb2);
+        rgb0 = fmaf(v[4 * j + 2], w0.z, rgb0); rgb1 = fmaf(v[4 * j + 2], w1.z, rgb1); rgb2 = fmaf(v[4 * j + 2], w2.z, rgb2);
+        rgb0 = fmaf(v[4 * j + 3], w0.w, rgb0); rgb1 = fmaf(v[4 * j + 3], w1.w, rgb1); rgb2 = fmaf(v[4 * j + 3], w2.w, rgb2);
+      }
+      if (!(F & F_NOSTORE)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 s4 = lds_f4(s_aux + (c0 + 4 * j) * 4);
+          v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+        }
+      }
+    }
+    if (!(F & F_NOSTORE)) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(r.out + c0), "r"(pk[0]), "r"(pk[1]),
+                   "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                   : "memory");
+    }
+  }
+  if ((F & F_RGB) && valid) {
+    r.rgb[0] = rgb0;
+    r.rgb[p.rgb_plane] = rgb1;
+    r.rgb[2 * p.rgb_plane] = rgb2;
+  }
+}
+
+// One tile through the epilogue this kernel instantiation was compiled for: EPI = index into epi_profile_flags (flags are
+// template constants) or -1 for the run-time generic one.  Every (block_k, EPI) pair is its own kernel, compiled in its
+// own translation unit (conv_epi*.cu): with all variants inlined behind a switch the register allocator spilled
+// loop-carried state of the tile loops (a local-memory load per tile showed up as the second largest stall).
+template <int EPI>
+__device__ __forceinline__ void epilogue_one(const ConvParams& p, uint32_t taddr, uint64_t* full_bar, uint32_t full_phase,
+                                             int x, int y, int b, int n0, bool valid, float gain, uint32_t s_bias,
+                                             uint32_t s_dm, const float* g_dm, uint32_t s_aux, int aux_stride) {
+  if constexpr (EPI >= 0) {
+    constexpr int F = epi_profile_flags(EPI);
+    const FastRow fr = fast_setup<F>(p, x, y, b, n0, valid);
+    epilogue_fast<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride);
+  } else {
+    const EpiRow r = epi_setup(p, x, y, b, n0, valid, gain);
+    epilogue_tile(p, taddr, full_bar, full_phase, r, valid, gain, s_bias, p.bias + n0, s_dm, g_dm, s_aux, aux_stride, 0, 16);
+  }
+}
+
+}  // namespace b200ir
+
+// Device code of the two tcgen05 convolution kernels (included by conv_igemm.cu after ConvParams / epilogue_tile).
+//
+// Both kernels are persistent and warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+// warps 2..5 = epilogue.  The producer and MMA warps run warp-uniform control flow and let ONE elected lane issue the
+// TMA / tcgen05 instructions: a single thread issues dependent instructions only every few cycles, so those loops are
+// kept as short as possible (descriptor words precomputed, only 32-bit adds per MMA, no divisions) — measured: with
+// ~1000 scalar instructions per output tile the issuing thread, not the tensor pipe or memory, set the pace.
+
+namespace b200ir {
+
+// hi word of a K-major shared-memory descriptor (SBO, version, swizzle layout); lo word = (addr >> 4)
+__device__ __forceinline__ uint32_t desc_hi_word(uint32_t row_bytes) {
+  return static_cast<uint32_t>(make_kmajor_desc(0, row_bytes) >> 32);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+struct KernelSmem {
+  uint8_t* base;        // 1024-byte aligned
+  uint64_t* full_bar;   // [kMaxStages]
+  uint64_t* empty_bar;  // [kMaxStages]
+  uint64_t* tmem_full;  // [kMaxAccStages]
+  uint64_t* tmem_empty; // [kMaxAccStages]
+  uint64_t* w_bar;      // row mode: resident weights landed
+  uint32_t* tmem_slot;
+  float* bias;          // [kMaxBias] bias of all output channels (zeros when the layer has none)
+  float* demod;         // [2][kDemodTable] per-tile demodulation table, double buffered
+};
+
+// bytes after the pipeline buffers: barriers + TMEM slot + bias + demod tables
+static constexpr int kTailBytes = 512 + kMaxBias * 4 + 2 * kDemodTable * 4;
+
+// the two epilogue warp groups (4 warps each) drain alternate tiles; each group syncs on its own named barrier
+__device__ __forceinline__ void epi_group_sync(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+__device__ __forceinline__ KernelSmem carve_smem(uint8_t* smem_raw, uint32_t data_bytes) {
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  KernelSmem s;
+  s.base = smem_raw + pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.base + data_bytes);
+  s.full_bar = bars;
+  s.empty_bar = bars + kMaxStages;
+  s.tmem_full = bars + 2 * kMaxStages;
+  s.tmem_empty = bars + 2 * kMaxStages + kMaxAccStages;
+  s.w_bar = bars + 2 * kMaxStages + 2 * kMaxAccStages;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.w_bar + 1);
+  s.bias = reinterpret_cast<float*>(s.base + data_bytes + 512);
+  s.demod = s.bias + kMaxBias;
+  return s;
+}
+
+__device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const KernelSmem& s, int nslots, int warp) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nslots; ++i) {
+      mbar_init(&s.full_bar[i], 1);
+      mbar_init(&s.empty_bar[i], 1);
+    }
+    for (int i = 0; i < p.acc_stages; ++i) {
+      mbar_init(&s.tmem_full[i], 1);
+      mbar_init(&s.tmem_empty[i], 128);
+    }
+    mbar_init(s.w_bar, 1);
+    fence_barrier_init();
+  }
+  if (p.cout <= kMaxBias)
+    for (int i = threadIdx.x; i < p.cout; i += kThreads)
+      s.bias[i] = (p.bias != nullptr) ? p.bias[i] * p.act_gain : 0.f;
+  if (warp == 1) {
+    tmem_alloc(s.tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *s.tmem_slot;
+}
+
+__device__ __forceinline__ void kernel_epilogue(const ConvParams& p, uint32_t tmem_base, int warp) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ================================================================================================ generic tiles
+template <int kBlockK, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t row_bytes = kBlockK * 2;
+  constexpr uint32_t a_bytes = kBlockM * row_bytes;
+  constexpr int k_steps = kBlockK / 16;
+  const uint32_t b_bytes = p.block_n * row_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const KernelSmem s = carve_smem(smem_raw, p.stages * stage_bytes);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_base = kernel_prologue(p, s, p.stages, warp);
+  const int num_kb = p.num_taps * p.k_chunks;
+
+  if (warp == 0) {
+    // ---------------- TMA producer
+    if (lane == 0) {
+      for (int v = 0; v < B200IR_MAX_VIEWS; ++v) tma_prefetch_desc(&p.tmap_a[v]);
+      tma_prefetch_desc(&p.tmap_b);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      int kb = 0;
+      for (int tap = 0; tap < p.num_taps; ++tap) {
+        const int view = p.tap_view[tap];
+        const int cx = t.x0 + p.tap_dx[tap];
+        const int cy = t.y0 + p.tap_dy[tap];
+        for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
+          mbar_wait(&s.empty_bar[stage], phase ^ 1u);
+          if (elect_one()) {
+            uint8_t* sa = s.base + stage * stage_bytes;
+            mbar_arrive_expect_tx(&s.full_bar[stage], stage_bytes);
+            tma_load_4d(sa, &p.tmap_a[view], &s.full_bar[stage], kc * kBlockK, cx, cy, t.b0);
+            tma_load_2d(sa + a_bytes, &p.tmap_b, &s.full_bar[stage], kb * kBlockK, t.n0);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    const uint32_t hi = desc_hi_word(row_bytes);
+    const uint32_t base_lo = smem_u32(s.base) >> 4;
+    const uint32_t stage_lo = stage_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & (p.acc_stages - 1);
+      mbar_wait(&s.tmem_empty[acc], ((it >> p.acc_shift) & 1) ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * p.block_n;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&s.full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = base_lo + stage * stage_lo;
+          const uint32_t b_lo = a_lo + (a_bytes >> 4);
+#pragma unroll
+          for (int k = 0; k < k_steps; ++k)
+            umma_f16(tmem_d, desc64(a_lo + 2 * k, hi), desc64(b_lo + 2 * k, hi), p.idesc, (k > 0 || kb > 0) ? 1u : 0u);
+          umma_commit(&s.empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&s.tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: two groups of 4 warps drain alternate tiles; TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    const int group = (warp - 2) >> 2;
+    const int gt = (threadIdx.x - 64) & 127;
+    const int row = q * 32 + lane;
+    const int xx = row % p.tile_w;
+    const int yy = (row / p.tile_w) % p.tile_h;
+    const int bi = row / (p.tile_w * p.tile_h);
+    const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) * p.act_gain : 0.f;
+    int it = group;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int acc = it & (p.acc_stages - 1);
+      const TileCoord t = decode_tile(p, tile);
+      const int x = t.x0 + xx, y = t.y0 + yy, b = t.b0 + bi;
+      const bool valid = (x < p.m_w) && (y < p.m_h) && (b < p.m_b);
+      uint32_t s_dm = 0, s_aux = 0;
+      const float* g_dm = nullptr;
+      const int tab_n = p.tile_b * p.block_n;
+      if ((p.demod != nullptr && p.smem_demod) || p.smem_aux) {
+        float* tab = s.demod + group * kDemodTable;
+        epi_group_sync(group);  // previous tile of this group fully drained
+        for (int i = gt; i < tab_n; i += 128) {
+          const int bb = t.b0 + i / p.block_n;
+          const long long ch = (long long)bb * p.cout + t.n0 + (i % p.block_n);
+          const bool in = bb < p.m_b;
+          if (p.smem_demod) tab[i] = in ? __ldg(p.demod + ch) * p.act_gain : 0.f;
+          if (p.smem_aux) {
+            tab[tab_n + i] = (in && p.out_scale != nullptr) ? __ldg(p.out_scale + ch) : 1.f;
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+              tab[(2 + o) * tab_n + i] =
+                  (in && p.rgb_w != nullptr) ? __ldg(p.rgb_w + ((long long)bb * 3 + o) * p.cout + t.n0 + (i % p.block_n)) : 0.f;
+          }
+        }
+        epi_group_sync(group);
+        if (p.smem_demod) s_dm = smem_u32(tab + bi * p.block_n);
+        if (p.smem_aux) s_aux = smem_u32(tab + tab_n + bi * p.block_n);
+      }
+      if (p.demod != nullptr && !p.smem_demod) g_dm = p.demod + (long long)b * p.cout + t.n0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
+      const uint32_t s_bias = (p.cout <= kMaxBias) ? smem_u32(s.bias + t.n0) : 0u;  // wide layers: global, act == 0
+      epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, y, b, t.n0, valid, gain, s_bias, s_dm,
+                        g_dm, s_aux, tab_n);
+      tc_fence_before();
+      mbar_arrive(&s.tmem_empty[acc]);
+    }
+  }
+  kernel_epilogue(p, tmem_base, warp);
+}
+
+// ================================================================================================ row mode
+// 3x3 stride-1 conv for low channel counts at high resolution.  A work item is (image b, 128-pixel column segment,
+// chunk of R output rows).  Every input row segment (130 pixels: 1-pixel halo each side, TMA zero fill outside the
+// image) is loaded ONCE into a ring slot and consumed ONCE: input row i of an item contributes to the output rows
+// i-2 (kh = 2), i-1 (kh = 1) and i (kh = 0), whose accumulators sit side by side in the TMEM ring, so one MMA with
+// N = 3*cout and the B tile [W(kh=2) | W(kh=1) | W(kh=0)] updates all three.  Per input row that is 3 (kw) x Cin/16
+// MMAs of N = 3*cout instead of 9 x Cin/16 MMAs of N = cout: the A operand (128 x 16 fp16 = 4 KB per MMA) is read from
+// shared memory 3x less often, and with N <= 64 that read, not the tensor pipe, set the MMA rate (measured: 70 cycles
+// per N=64 MMA against a 32-cycle pipe floor).  The three kw taps read the row through descriptors whose start address
+// is shifted by kw pixels (measured on B200: the swizzle XOR uses absolute shared-memory address bits, so row-shifted
+// start addresses work with the matrix-base-offset field left at 0 -- tools/try_row_mode.py).
+// The newest target (output row i) has no partial sum yet: the first MMA of an input row is split so that this slice
+// runs with accumulate = 0; a target run that wraps around the TMEM ring is split in two as well.
+// All 9 tap weight tiles stay resident in shared memory for the whole kernel, grouped per (kw, k-chunk) in kh order 2,1,0.
+struct RowItem {
+  int b, seg, y0, rows_out;
+};
+__device__ __forceinline__ RowItem decode_item(const ConvParams& p, int item) {
+  RowItem r;
+  const int chunk = item % p.row_chunks;
+  const int rest = item / p.row_chunks;
+  r.seg = rest % p.tiles_w;
+  r.b = rest / p.tiles_w;
+  r.y0 = chunk * p.row_R;
+  r.rows_out = min(p.row_R, p.m_h - r.y0);
+  return r;
+}
+
+template <int kBlockK, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t row_bytes = kBlockK * 2;
+  constexpr int k_steps = kBlockK / 16;
+  constexpr uint32_t slot_bytes = 136 * row_bytes;
+  const uint32_t wtile_bytes = p.block_n * row_bytes;  // one (tap, kc) weight tile
+  const KernelSmem s = carve_smem(smem_raw, p.row_w_bytes + p.row_slots * slot_bytes);
+  uint8_t* s_w = s.base;
+  uint8_t* s_ring = s.base + p.row_w_bytes;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kc_n = p.k_chunks;
+  const int nslots = p.row_slots;
+  const uint32_t tmem_base = kernel_prologue(p, s, nslots, warp);
+
+  if (warp == 0) {
+    // ---------------- TMA producer: resident weights once, then one box per (input row, kc)
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmap_a[0]);
+      tma_prefetch_desc(&p.tmap_b);
+      mbar_arrive_expect_tx(s.w_bar, 9 * kc_n * wtile_bytes);
+      const int cin = kc_n * kBlockK;
+      for (int kw = 0; kw < 3; ++kw)
+        for (int kc = 0; kc < kc_n; ++kc)
+          for (int khi = 0; khi < 3; ++khi)  // kh = 2 - khi: ascending output row inside the merged B tile
+            tma_load_2d(s_w + ((kw * kc_n + kc) * 3 + khi) * wtile_bytes, &p.tmap_b, s.w_bar,
+                        ((2 - khi) * 3 + kw) * cin + kc * kBlockK, 0);
+    }
+    __syncwarp();
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < p.row_items; item += gridDim.x) {
+      const RowItem w = decode_item(p, item);
+      const int cx = w.seg * 128 - 1;
+      for (int r = 0; r < w.rows_out + 2; ++r) {
+        for (int kc = 0; kc < kc_n; ++kc) {
+          mbar_wait(&s.empty_bar[slot], phase ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&s.full_bar[slot], 130 * row_bytes);
+            tma_load_4d(s_ring + slot * slot_bytes, &p.tmap_a[0], &s.full_bar[slot], kc * kBlockK, cx, w.y0 - 1 + r,
+                        w.b);
+          }
+          __syncwarp();
+          if (++slot == nslots) {
+            slot = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    mbar_wait(s.w_bar, 0);
+    tc_fence_after();
+    const uint32_t hi = desc_hi_word(row_bytes);
+    const uint32_t w_lo = smem_u32(s_w) >> 4;
+    const uint32_t ring_lo = smem_u32(s_ring) >> 4;
+    const uint32_t wtile_lo = wtile_bytes >> 4;
+    constexpr uint32_t slot_lo = slot_bytes >> 4;
+    constexpr uint32_t px_lo = row_bytes >> 4;  // one pixel (one smem row) in descriptor units
+    const int ring = p.acc_stages;               // accumulator slots (power of two)
+    int slot = 0;                                // ring slot of (current input row, kc 0)
+    uint32_t phase = 0;
+    int it_base = 0;                             // output rows issued before this item
+    for (int item = blockIdx.x; item < p.row_items; item += gridDim.x) {
+      const RowItem w = decode_item(p, item);
+      for (int i = 0; i < w.rows_out + 2; ++i) {
+        const int row_slot = slot;
+        for (int kc = 0; kc < kc_n; ++kc) {  // this input row has landed (all its k-chunks)
+          mbar_wait(&s.full_bar[slot], phase);
+          if (++slot == nslots) {
+            slot = 0;
+            phase ^= 1u;
+          }
+        }
+        const bool fresh = i < w.rows_out;  // output row i receives its first contribution (kh = 0) from this input row
+        if (fresh) {
+          const int it = it_base + i;
+          mbar_wait(&s.tmem_empty[it & (ring - 1)], ((it >> p.acc_shift) & 1) ^ 1u);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const int j_lo = max(i - 2, 0), j_hi = min(i, w.rows_out - 1);
+          // one accumulating run over output rows [ja, jb] (split where the accumulator ring wraps)
+          auto run = [&](int ja, int jb, uint64_t a_desc, uint32_t tile_lo, uint32_t accumulate) {
+            const int n = jb - ja + 1;
+            const int sa = (it_base + ja) & (ring - 1);
+            const int n1 = min(n, ring - sa);
+            const uint32_t b_lo = tile_lo + (ja - (i - 2)) * wtile_lo;
+            umma_f16(tmem_base + sa * p.block_n, a_desc, desc64(b_lo, hi), p.idesc_n[n1 - 1], accumulate);
+            if (n1 < n) umma_f16(tmem_base, a_desc, desc64(b_lo + n1 * wtile_lo, hi), p.idesc_n[n - n1 - 1], accumulate);
+          };
+          int sl = row_slot;
+          for (int kc = 0; kc < kc_n; ++kc) {
+            const uint32_t a_lo = ring_lo + sl * slot_lo;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t tile_lo = w_lo + (kw * kc_n + kc) * 3 * wtile_lo;
+#pragma unroll
+              for (int k = 0; k < k_steps; ++k) {
+                const uint64_t a_desc = desc64(a_lo + kw * px_lo + 2 * k, hi);
+                if (fresh && kc == 0 && kw == 0 && k == 0) {
+                  if (j_hi > j_lo) run(j_lo, j_hi - 1, a_desc, tile_lo + 2 * k, 1u);
+                  run(j_hi, j_hi, a_desc, tile_lo + 2 * k, 0u);
+                } else {
+                  run(j_lo, j_hi, a_desc, tile_lo + 2 * k, 1u);
+                }
+              }
+            }
+            umma_commit(&s.empty_bar[sl]);  // this (row, kc) slot is consumed once
+            if (++sl == nslots) sl = 0;
+          }
+          if (i >= 2) umma_commit(&s.tmem_full[(it_base + i - 2) & (ring - 1)]);  // output row i-2 is complete
+        }
+        __syncwarp();
+      }
+      it_base += w.rows_out;
+    }
+  } else {
+    // ---------------- epilogue: two groups of 4 warps drain alternate output rows
+    const int q = warp & 3;
+    const int group = (warp - 2) >> 2;
+    const int gt = (threadIdx.x - 64) & 127;
+    const int row = q * 32 + lane;
+    const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) * p.act_gain : 0.f;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.row_items; item += gridDim.x) {
+      const RowItem w = decode_item(p, item);
+      const int x = w.seg * 128 + row;
+      const bool valid = x < p.m_w;
+      uint32_t s_dm = 0, s_aux = 0;
+      if (p.demod != nullptr || p.smem_aux) {  // one image per item: each group stages that image's table rows once
+        float* tab = s.demod + group * kDemodTable;
+        epi_group_sync(group);
+        for (int i = gt; i < p.block_n; i += 128) {
+          const long long ch = (long long)w.b * p.cout + i;
+          if (p.demod != nullptr) tab[i] = __ldg(p.demod + ch) * p.act_gain;
+          if (p.smem_aux) {
+            tab[p.block_n + i] = (p.out_scale != nullptr) ? __ldg(p.out_scale + ch) : 1.f;
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+              tab[(2 + o) * p.block_n + i] =
+                  (p.rgb_w != nullptr) ? __ldg(p.rgb_w + ((long long)w.b * 3 + o) * p.cout + i) : 0.f;
+          }
+        }
+        epi_group_sync(group);
+        if (p.demod != nullptr) s_dm = smem_u32(tab);
+        if (p.smem_aux) s_aux = smem_u32(tab + p.block_n);
+      }
+      for (int j = 0; j < w.rows_out; ++j, ++it) {
+        if ((it & 1) != group) continue;
+        const int acc = it & (p.acc_stages - 1);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
+        epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, w.y0 + j, w.b, 0, valid, gain,
+                          smem_u32(s.bias), s_dm, nullptr, s_aux, p.block_n);
+        tc_fence_before();
+        mbar_arrive(&s.tmem_empty[acc]);
+      }
+    }
+  }
+  kernel_epilogue(p, tmem_base, warp);
+}
+
+
+// ------------------------------------------------------------------------------------------ launch (per EPI)
+// Defined as a template here, explicitly instantiated once per EPI in conv_epi*.cu; conv_igemm.cu calls through
+// launch_conv_variant's extern declarations.
+template <int kBlockK, int EPI, bool ROW>
+static int launch_one(const ConvParams& p, int grid, int smem_bytes, int smem_max, cudaStream_t st) {
+  static bool configured = false;
+  if (ROW) {
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<kBlockK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      if (e != cudaSuccess) {
+        set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return 1;
+      }
+      configured = true;
+    }
+    conv_row_kernel<kBlockK, EPI><<<grid, kThreads, smem_bytes, st>>>(p);
+    return check_launch("conv_row");
+  }
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<kBlockK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e != cudaSuccess) {
+      set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  conv_igemm_kernel<kBlockK, EPI><<<grid, kThreads, smem_bytes, st>>>(p);
+  return check_launch("conv_igemm");
+}
+
+// block_k 16 exists only with the generic epilogue (narrow test nets); the host never selects EPI >= 0 for it
+template <int EPI>
+int launch_conv_variant(const ConvParams& p, int block_k, bool row, int grid, int smem_bytes, int smem_max,
+                        cudaStream_t st) {
+  if (row) {
+    if (block_k == 64) return launch_one<64, EPI, true>(p, grid, smem_bytes, smem_max, st);
+    if (block_k == 32) return launch_one<32, EPI, true>(p, grid, smem_bytes, smem_max, st);
+    if constexpr (EPI < 0) return launch_one<16, EPI, true>(p, grid, smem_bytes, smem_max, st);
+  } else {
+    if (block_k == 64) return launch_one<64, EPI, false>(p, grid, smem_bytes, smem_max, st);
+    if (block_k == 32) return launch_one<32, EPI, false>(p, grid, smem_bytes, smem_max, st);
+    if constexpr (EPI < 0) return launch_one<16, EPI, false>(p, grid, smem_bytes, smem_max, st);
+  }
+  set_error("conv: no kernel for block_k=%d with epilogue profile %d", block_k, EPI);
+  return 1;
+}
+
+}  // namespace b200ir

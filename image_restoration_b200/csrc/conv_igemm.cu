@@ -1,528 +1,29 @@
-// Implicit-GEMM convolution for sm_100a: TMA box loads (im2col by shifted boxes with out-of-bounds zero fill)
-// -> 128B/64B-swizzled shared memory -> tcgen05.mma (M=128, N=block_n, K=16, fp16 x fp16 -> fp32 in TMEM)
-// -> tcgen05.ld epilogue with bias / demodulation / noise / leaky-ReLU / residual fused.
-//
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 =
-// epilogue (one TMEM lane quarter each).  Two TMEM accumulator stages let the epilogue of tile i overlap the
-// main loop of tile i+1.
-//
-// Reference semantics implemented here: see include/b200ir.h (b200ir_conv_igemm).
-#include <stdarg.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include "host_common.h"
-#include "ptx.cuh"
+// Host side of the implicit-GEMM convolution: descriptor validation, TMA tensor maps, tile / ring sizing, epilogue
+// profile selection and the launch through the per-profile translation units (conv_epi*.cu).
+// Device code: conv_common.cuh.  Reference semantics: include/b200ir.h (b200ir_conv_igemm).
+#include "conv_common.cuh"
 
 namespace b200ir {
+extern template int launch_conv_variant<-1>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
+extern template int launch_conv_variant<0>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
+extern template int launch_conv_variant<1>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
+extern template int launch_conv_variant<2>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
+extern template int launch_conv_variant<3>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
+extern template int launch_conv_variant<4>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
+extern template int launch_conv_variant<5>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
 
-static constexpr int kBlockM = 128;
-static constexpr int kEpiWarps = 8;                         // two per TMEM lane quarter
-static constexpr int kEpiThreads = kEpiWarps * 32;
-static constexpr int kThreads = 64 + kEpiThreads;       // warp 0 producer, warp 1 MMA, warps 2.. epilogue
-static constexpr int kDemodTable = 2560;  // floats per epilogue group: per-tile tables [demod | out_scale | rgb_w x3]
-static constexpr int kMaxBias = 512;
-static constexpr int kMaxStages = 8;
-static constexpr int kMaxAccStages = 16;  // TMEM accumulator ring: as many 128 x block_n tiles as fit in 512 columns
-
-struct alignas(64) ConvParams {
-  CUtensorMap tmap_a[B200IR_MAX_VIEWS];
-  CUtensorMap tmap_b;
-  int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles;
-  int tile_w, tile_h, tile_b;
-  int block_n, block_k, k_chunks, num_taps;
-  int m_w, m_h, m_b;
-  int stages;
-  uint32_t idesc;
-  uint32_t idesc_n[3];  // row mode: instruction descriptors for N = 1, 2, 3 x block_n
-  uint32_t tmem_cols;
-  int acc_stages, acc_shift;
-  // row mode (conv_row_kernel): 3x3 stride-1 conv, tile = 128 consecutive pixels of one row, weights resident in
-  // shared memory, each input row segment loaded once (with a 1-pixel halo) and reused for 3 kw shifts x 3 output rows
-  int row_R, row_chunks, row_items, row_slots, row_slot_bytes, row_w_bytes, desc_mode;
-  int smem_demod;  // 1: per-tile demod table staged in shared memory
-  int smem_aux;    // 1: out_scale / rgb_w tables staged behind it (4 more tables of tile_b * block_n floats)
-  int st256;       // 1: fp16 output rows are 32-byte aligned -> 256-bit stores
-  float act_gain;  // sqrt(2) when act is set (folded into the bias / demod / noise terms), else 1; the specialised
-                   // epilogues (epi >= 0) also fold the residual scale into it
-  float slope;     // leaky-ReLU slope (0.2), 1.0 when the layer has no activation: v = max(v, slope * v)
-  int epi;         // index into kEpiProfiles (compile-time specialised epilogue) or -1 for the run-time generic one
-  int8_t tap_view[B200IR_MAX_TAPS], tap_dx[B200IR_MAX_TAPS], tap_dy[B200IR_MAX_TAPS];
-  // epilogue
-  void* out;
-  int out_fp32;
-  long long out_sx, out_sy, out_sb;
-  int out_c_off, out_x_mul, out_x_off, out_y_mul, out_y_off;
-  int cout;
-  const float* bias;
-  const float* demod;
-  const float* noise;
-  const float* noise_gain;
-  long long noise_sb, noise_sy;
-  int act;
-  int res_mode;
-  const __half* res;
-  long long res_sx, res_sy, res_sb;
-  int res_w, res_h;
-  float res_scale;
-  const float* out_scale;
-  const float* rgb_w;
-  float* rgb_part;
-  long long rgb_plane, rgb_image;  // rgb_h*rgb_w_px, m_b*3*rgb_plane
-  int rgb_w_px;
-  int no_store;
-  int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
-};
-
-struct TileCoord {
-  int x0, y0, b0, n0;
-};
-
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
-  TileCoord t;
-  int n_tile = tile % p.tiles_n;
-  int m = tile / p.tiles_n;
-  int xw = m % p.tiles_w;
-  m /= p.tiles_w;
-  int yh = m % p.tiles_h;
-  int bb = m / p.tiles_h;
-  t.x0 = xw * p.tile_w;
-  t.y0 = yh * p.tile_h;
-  t.b0 = bb * p.tile_b;
-  t.n0 = n_tile * p.block_n;
-  return t;
-}
-
-__device__ __forceinline__ void unpack_half8(const uint4& q, float* f) {
-  const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 x = __half22float2(h[i]);
-    f[2 * i] = x.x;
-    f[2 * i + 1] = x.y;
-  }
-}
-
-// Per-thread addressing of one output position, computed (and the noise value fetched) BEFORE the accumulator is
-// ready so that none of it sits on the MMA -> epilogue critical path.
-struct EpiRow {
-  long long out_off;
-  long long chan_off;  // b * cout + n0: row of the per-image tables (out_scale)
-  long long rgbw_off;  // b * 3 * cout + n0
-  long long rgb_off;   // offset of (n-tile, b, 0, yo, xo) in rgb_part
-  float nz;
-  const __half* r00;
-  const __half* r01;
-  const __half* r10;
-  const __half* r11;
-  float wy0, wy1, wx0, wx1;
-};
-
-__device__ __forceinline__ EpiRow epi_setup(const ConvParams& p, int x, int y, int b, int n0, bool valid, float gain) {
-  EpiRow r;
-  const int xo = x * p.out_x_mul + p.out_x_off;
-  const int yo = y * p.out_y_mul + p.out_y_off;
-  r.out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx + p.out_c_off + n0;
-  r.chan_off = (long long)b * p.cout + n0;
-  r.rgbw_off = (long long)b * 3 * p.cout + n0;
-  r.rgb_off = (long long)(n0 / p.block_n) * p.rgb_image + (long long)b * 3 * p.rgb_plane + (long long)yo * p.rgb_w_px + xo;
-  r.nz = 0.f;
-  if (valid && p.noise != nullptr) r.nz = __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);  // scaled by the caller later
-  r.r00 = r.r01 = r.r10 = r.r11 = nullptr;
-  r.wy0 = r.wy1 = r.wx0 = r.wx1 = 0.f;
-  if (valid && p.res_mode == 1) {
-    r.r00 = p.res + (long long)b * p.res_sb + (long long)yo * p.res_sy + (long long)xo * p.res_sx + n0;
-  } else if (valid && p.res_mode == 2) {
-    // F.interpolate(scale 2, bilinear, align_corners=False): even 2k -> .25*x[k-1] + .75*x[k], odd 2k+1 ->
-    // .75*x[k] + .25*x[k+1], indices clamped to the tensor.
-    const int ky = yo >> 1, kx = xo >> 1;
-    int ya, yb, xa, xb;
-    if (yo & 1) { ya = ky; yb = min(ky + 1, p.res_h - 1); r.wy0 = 0.75f; r.wy1 = 0.25f; }
-    else        { ya = max(ky - 1, 0); yb = ky; r.wy0 = 0.25f; r.wy1 = 0.75f; }
-    if (xo & 1) { xa = kx; xb = min(kx + 1, p.res_w - 1); r.wx0 = 0.75f; r.wx1 = 0.25f; }
-    else        { xa = max(kx - 1, 0); xb = kx; r.wx0 = 0.25f; r.wx1 = 0.75f; }
-    const __half* rb = p.res + (long long)b * p.res_sb + n0;
-    r.r00 = rb + (long long)ya * p.res_sy + (long long)xa * p.res_sx;
-    r.r01 = rb + (long long)ya * p.res_sy + (long long)xb * p.res_sx;
-    r.r10 = rb + (long long)yb * p.res_sy + (long long)xa * p.res_sx;
-    r.r11 = rb + (long long)yb * p.res_sy + (long long)xb * p.res_sx;
-  }
-  return r;
-}
-
-// Drains this thread's row of one 128 x block_n accumulator tile, 16 columns at a time (columns c_begin, c_begin +
-// c_step, ...: two warps share a TMEM lane quarter).  Per chunk the TMEM load is issued first, the operands that do not
-// depend on it (bias / demod from shared memory, residual from global) are fetched while it is in flight.
-//   s_bias  : shared memory, bias[n0 ...] (zeros when the layer has no bias)
-//   s_demod : shared memory, demod[b][n0 ...] for this row's image, or nullptr
-//   g_demod : global fallback for demod (used when the per-tile table does not fit), or nullptr
-//   s_aux   : shared memory, [out_scale | rgb_w[0] | rgb_w[1] | rgb_w[2]] rows of this row's image, aux_stride floats
-//             apart, or nullptr (then out_scale / rgb_w come from global memory: with ~227 KB of dynamic shared memory
-//             there is almost no L1 left, so every such load is an L2 round trip -- measured as the top stall)
-// All shared-memory tables are passed as 32-bit shared addresses and read with ld.shared: selecting between a shared
-// and a global POINTER makes the compiler emit generic loads, which take the long L1TEX path (measured).
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-
-//   s_bias  : shared address of bias[n0 ...] (zeros when the layer has no bias); 0 -> g_bias (global, wide layers)
-//   s_demod : shared address of demod[b][n0 ...] for this row's image, or 0
-//   s_aux   : shared address of the [out_scale | rgb_w[0] | rgb_w[1] | rgb_w[2]] rows, aux_stride floats apart, or 0
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
-                                              uint32_t full_phase, EpiRow r, bool valid, float gain, uint32_t s_bias,
-                                              const float* g_bias, uint32_t s_demod, const float* g_demod,
-                                              uint32_t s_aux, int aux_stride, int c_begin, int c_step) {
-  mbar_wait(full_bar, full_phase);
-  tc_fence_after();
-  if (p.dbg_skip_epi) return;
-  r.nz *= gain;  // the noise load was issued in epi_setup, long before this first use
-  float rgb_acc[3] = {0.f, 0.f, 0.f};
-  for (int c0 = c_begin; c0 < p.block_n; c0 += c_step) {
-    uint32_t raw[16];
-    tmem_ld16(taddr + c0, raw);
-    float4 bs[4], dm[4];
-    if (s_bias != 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bs[j] = lds_f4(s_bias + (c0 + 4 * j) * 4);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bs[j] = __ldg(reinterpret_cast<const float4*>(g_bias + c0) + j);
-    }
-    if (s_demod != 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dm[j] = lds_f4(s_demod + (c0 + 4 * j) * 4);
-    } else if (g_demod != nullptr && valid) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dm[j] = __ldg(reinterpret_cast<const float4*>(g_demod + c0) + j);
-        dm[j].x *= p.act_gain; dm[j].y *= p.act_gain; dm[j].z *= p.act_gain; dm[j].w *= p.act_gain;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dm[j] = make_float4(p.act_gain, p.act_gain, p.act_gain, p.act_gain);
-    }
-    uint4 ra[2], rb[2], rc[2], rd[2];
-    if (valid && p.res_mode != 0) {
-      ra[0] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0));
-      ra[1] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0) + 1);
-      if (p.res_mode == 2) {
-        rb[0] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0));
-        rb[1] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0) + 1);
-        rc[0] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0));
-        rc[1] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0) + 1);
-        rd[0] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0));
-        rd[1] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0) + 1);
-      }
-    }
-    tmem_ld_wait16(raw);
-    if (valid) {
-      // bias / demod / noise arrive pre-multiplied by the activation gain (sqrt 2) when act is set, so the
-      // leaky-ReLU is just max(v, 0.2 v)
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[4 * j] = __uint_as_float(raw[4 * j]) * dm[j].x + (bs[j].x + r.nz);
-        v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) * dm[j].y + (bs[j].y + r.nz);
-        v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) * dm[j].z + (bs[j].z + r.nz);
-        v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) * dm[j].w + (bs[j].w + r.nz);
-      }
-      if (p.act) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
-      }
-      if (p.res_mode == 1) {
-        float f[16];
-        unpack_half8(ra[0], f);
-        unpack_half8(ra[1], f + 8);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (v[j] + f[j]) * p.res_scale;
-      } else if (p.res_mode == 2) {
-        float fa[16], fb[16], fc[16], fd[16];
-        unpack_half8(ra[0], fa); unpack_half8(ra[1], fa + 8);
-        unpack_half8(rb[0], fb); unpack_half8(rb[1], fb + 8);
-        unpack_half8(rc[0], fc); unpack_half8(rc[1], fc + 8);
-        unpack_half8(rd[0], fd); unpack_half8(rd[1], fd + 8);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float up = r.wy0 * (r.wx0 * fa[j] + r.wx1 * fb[j]) + r.wy1 * (r.wx0 * fc[j] + r.wx1 * fd[j]);
-          v[j] = (v[j] + up) * p.res_scale;
-        }
-      }
-      if (p.rgb_w != nullptr) {
-        if (s_aux != 0) {
-#pragma unroll
-          for (int o = 0; o < 3; ++o) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 w4 = lds_f4(s_aux + ((1 + o) * aux_stride + c0 + 4 * j) * 4);
-              rgb_acc[o] = fmaf(v[4 * j], w4.x, rgb_acc[o]);
-              rgb_acc[o] = fmaf(v[4 * j + 1], w4.y, rgb_acc[o]);
-              rgb_acc[o] = fmaf(v[4 * j + 2], w4.z, rgb_acc[o]);
-              rgb_acc[o] = fmaf(v[4 * j + 3], w4.w, rgb_acc[o]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int o = 0; o < 3; ++o) {
-            const float4* wp = reinterpret_cast<const float4*>(p.rgb_w + r.rgbw_off + (long long)o * p.cout + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 w4 = __ldg(wp + j);
-              rgb_acc[o] = fmaf(v[4 * j], w4.x, rgb_acc[o]);
-              rgb_acc[o] = fmaf(v[4 * j + 1], w4.y, rgb_acc[o]);
-              rgb_acc[o] = fmaf(v[4 * j + 2], w4.z, rgb_acc[o]);
-              rgb_acc[o] = fmaf(v[4 * j + 3], w4.w, rgb_acc[o]);
-            }
-          }
-        }
-      }
-      if (p.out_scale != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 s4 = (s_aux != 0) ? lds_f4(s_aux + (c0 + 4 * j) * 4)
-                                         : __ldg(reinterpret_cast<const float4*>(p.out_scale + r.chan_off + c0) + j);
-          v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
-        }
-      }
-      if (p.no_store) {
-      } else if (p.out_fp32) {
-        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r.out_off + c0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      } else {
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        __half* op = reinterpret_cast<__half*>(p.out) + r.out_off + c0;
-        if (p.st256) {  // one full 32-byte sector per thread and instruction (no partial-sector writes in L2)
-          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]),
-                       "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                       : "memory");
-        } else {
-          reinterpret_cast<uint4*>(op)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          reinterpret_cast<uint4*>(op)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
-    }
-  }
-  if (p.rgb_w != nullptr && valid) {
-#pragma unroll
-    for (int o = 0; o < 3; ++o) p.rgb_part[r.rgb_off + o * p.rgb_plane] = rgb_acc[o];
-  }
-}
-
-// ------------------------------------------------------------------------------------------ specialised epilogues
-// The generic epilogue above tests every feature flag per 16-column chunk (measured: ~550 SASS instructions per chunk,
-// which made the epilogue -- not the MMA main loop -- the pace setter of every layer with K <= 1152).  The layers of
-// the network use six feature combinations; each gets an epilogue with the flags as template constants.
-enum : int { F_DEMOD = 1, F_NOISE = 2, F_RES1 = 4, F_RES2 = 8, F_RGB = 16, F_NOSTORE = 32 };
-static constexpr int kNumEpiProfiles = 6;
-__host__ __device__ constexpr int epi_profile_flags(int i) {
-  return i == 0   ? 0
-         : i == 1 ? F_RES1
-         : i == 2 ? F_RES2
-         : i == 3 ? F_DEMOD
-         : i == 4 ? (F_DEMOD | F_NOISE | F_RGB)
-                  : (F_DEMOD | F_NOISE | F_RGB | F_NOSTORE);
-}
-
-struct FastRow {
-  __half* out;  // output row of this position, first channel of the N-tile
-  float* rgb;   // partial ToRGB plane element of this position (channel 0)
-  float nz;
-  const __half* r00;
-  const __half* r01;
-  const __half* r10;
-  const __half* r11;
-  float w00, w01, w10, w11;  // bilinear weights x residual scale
-};
-
-template <int F>
-__device__ __forceinline__ FastRow fast_setup(const ConvParams& p, int x, int y, int b, int n0, bool valid) {
-  FastRow r;
-  const int xo = x * p.out_x_mul + p.out_x_off;
-  const int yo = y * p.out_y_mul + p.out_y_off;
-  r.out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_sb + (long long)yo * p.out_sy +
-          (long long)xo * p.out_sx + p.out_c_off + n0;
-  r.rgb = nullptr;
-  if (F & F_RGB)
-    r.rgb = p.rgb_part + (long long)(n0 / p.block_n) * p.rgb_image + (long long)b * 3 * p.rgb_plane +
-            (long long)yo * p.rgb_w_px + xo;
-  r.nz = 0.f;
-  if ((F & F_NOISE) && valid) r.nz = __ldg(p.noise + b * p.noise_sb + yo * p.noise_sy + xo);
-  r.r00 = r.r01 = r.r10 = r.r11 = nullptr;
-  r.w00 = r.w01 = r.w10 = r.w11 = 0.f;
-  if ((F & F_RES1) && valid) {
-    r.r00 = p.res + (long long)b * p.res_sb + (long long)yo * p.res_sy + (long long)xo * p.res_sx + n0;
-    r.w00 = p.res_scale;
-  }
-  if ((F & F_RES2) && valid) {
-    const int ky = yo >> 1, kx = xo >> 1;
-    int ya, yb, xa, xb;
-    float wy0, wy1, wx0, wx1;
-    if (yo & 1) { ya = ky; yb = min(ky + 1, p.res_h - 1); wy0 = 0.75f; wy1 = 0.25f; }
-    else        { ya = max(ky - 1, 0); yb = ky; wy0 = 0.25f; wy1 = 0.75f; }
-    if (xo & 1) { xa = kx; xb = min(kx + 1, p.res_w - 1); wx0 = 0.75f; wx1 = 0.25f; }
-    else        { xa = max(kx - 1, 0); xb = kx; wx0 = 0.25f; wx1 = 0.75f; }
-    const __half* rb = p.res + (long long)b * p.res_sb + n0;
-    r.r00 = rb + (long long)ya * p.res_sy + (long long)xa * p.res_sx;
-    r.r01 = rb + (long long)ya * p.res_sy + (long long)xb * p.res_sx;
-    r.r10 = rb + (long long)yb * p.res_sy + (long long)xa * p.res_sx;
-    r.r11 = rb + (long long)yb * p.res_sy + (long long)xb * p.res_sx;
-    wy0 *= p.res_scale;
-    wy1 *= p.res_scale;
-    r.w00 = wy0 * wx0; r.w01 = wy0 * wx1; r.w10 = wy1 * wx0; r.w11 = wy1 * wx1;
-  }
-  return r;
-}
-
-// fp16 NHWC output with 32-byte aligned rows, bias (and demod / aux tables) in shared memory, gains pre-folded:
-//   v = acc * (demod*g | g) + (bias*g + noise*gain*g);  v = max(v, slope*v);  v += res * w (w carries the residual scale)
-template <int F>
-__device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
-                                              uint32_t full_phase, const FastRow& r, bool valid, float gain,
-                                              uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride) {
-  mbar_wait(full_bar, full_phase);
-  tc_fence_after();
-  if (p.dbg_skip_epi) return;
-  const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
-  const float ag = p.act_gain, slope = p.slope;
-  float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-    uint32_t raw[16];
-    tmem_ld16(taddr + c0, raw);
-    float4 bs[4], dm[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) bs[j] = lds_f4(s_bias + (c0 + 4 * j) * 4);
-    if (F & F_DEMOD) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dm[j] = lds_f4(s_demod + (c0 + 4 * j) * 4);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dm[j] = make_float4(ag, ag, ag, ag);
-    }
-    uint4 ra[2], rb[2], rc[2], rd[2];
-    if ((F & (F_RES1 | F_RES2)) && valid) {
-      ra[0] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0));
-      ra[1] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0) + 1);
-      if (F & F_RES2) {
-        rb[0] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0));
-        rb[1] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0) + 1);
-        rc[0] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0));
-        rc[1] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0) + 1);
-        rd[0] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0));
-        rd[1] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0) + 1);
-      }
-    }
-    tmem_ld_wait16(raw);
-    if (!valid) continue;
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), dm[j].x, bs[j].x + nz);
-      v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), dm[j].y, bs[j].y + nz);
-      v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), dm[j].z, bs[j].z + nz);
-      v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), dm[j].w, bs[j].w + nz);
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
-    if (F & F_RES1) {
-      float f[16];
-      unpack_half8(ra[0], f);
-      unpack_half8(ra[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
-    }
-    if (F & F_RES2) {
-      float f[16];
-      unpack_half8(ra[0], f); unpack_half8(ra[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
-      unpack_half8(rb[0], f); unpack_half8(rb[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w01, v[j]);
-      unpack_half8(rc[0], f); unpack_half8(rc[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w10, v[j]);
-      unpack_half8(rd[0], f); unpack_half8(rd[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w11, v[j]);
-    }
-    if (F & F_RGB) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 w0 = lds_f4(s_aux + (aux_stride + c0 + 4 * j) * 4);
-        const float4 w1 = lds_f4(s_aux + (2 * aux_stride + c0 + 4 * j) * 4);
-        const float4 w2 = lds_f4(s_aux + (3 * aux_stride + c0 + 4 * j) * 4);
-        rgb0 = fmaf(v[4 * j], w0.x, rgb0); rgb1 = fmaf(v[4 * j], w1.x, rgb1); rgb2 = fmaf(v[4 * j], w2.x, rgb2);
-        rgb0 = fmaf(v[4 * j + 1], w0.y, rgb0); rgb1 = fmaf(v[4 * j + 1], w1.y, rgb1); rgb2 = fmaf(v[4 * j + 1], w2.y, rgb2);
-        rgb0 = fmaf(v[4 * j + 2], w0.z, rgb0); rgb1 = fmaf(v[4 * j + 2], w1.z, rgb1); rgb2 = fmaf(v[4 * j + 2], w2.z, rgb2);
-        rgb0 = fmaf(v[4 * j + 3], w0.w, rgb0); rgb1 = fmaf(v[4 * j + 3], w1.w, rgb1); rgb2 = fmaf(v[4 * j + 3], w2.w, rgb2);
-      }
-      if (!(F & F_NOSTORE)) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 s4 = lds_f4(s_aux + (c0 + 4 * j) * 4);
-          v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
-        }
-      }
-    }
-    if (!(F & F_NOSTORE)) {
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-        pk[j] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(r.out + c0), "r"(pk[0]), "r"(pk[1]),
-                   "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                   : "memory");
-    }
-  }
-  if ((F & F_RGB) && valid) {
-    r.rgb[0] = rgb0;
-    r.rgb[p.rgb_plane] = rgb1;
-    r.rgb[2 * p.rgb_plane] = rgb2;
-  }
-}
-
-// One tile of either kernel through the epilogue the host selected (uniform switch, once per tile).
-#define B200IR_EPI_CASE(I)                                                                                        \
-  case I: {                                                                                                       \
-    constexpr int F = epi_profile_flags(I);                                                                       \
-    const FastRow fr = fast_setup<F>(p, x, y, b, n0, valid);                                                      \
-    epilogue_fast<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride);           \
-  } break;
-
-__device__ __forceinline__ void epilogue_dispatch(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
-                                                  uint32_t full_phase, int x, int y, int b, int n0, bool valid,
-                                                  float gain, uint32_t s_bias, uint32_t s_dm, const float* g_dm,
-                                                  uint32_t s_aux, int aux_stride) {
+static int launch_conv(const ConvParams& p, bool row, int grid, int smem_bytes, int smem_max, cudaStream_t st) {
   switch (p.epi) {
-    B200IR_EPI_CASE(0)
-    B200IR_EPI_CASE(1)
-    B200IR_EPI_CASE(2)
-    B200IR_EPI_CASE(3)
-    B200IR_EPI_CASE(4)
-    B200IR_EPI_CASE(5)
-    default: {
-      const EpiRow r = epi_setup(p, x, y, b, n0, valid, gain);
-      epilogue_tile(p, taddr, full_bar, full_phase, r, valid, gain, s_bias, p.bias + n0, s_dm, g_dm, s_aux, aux_stride,
-                    0, 16);
-    } break;
+    case 0: return launch_conv_variant<0>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
+    case 1: return launch_conv_variant<1>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
+    case 2: return launch_conv_variant<2>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
+    case 3: return launch_conv_variant<3>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
+    case 4: return launch_conv_variant<4>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
+    case 5: return launch_conv_variant<5>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
+    default: return launch_conv_variant<-1>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
   }
 }
-#undef B200IR_EPI_CASE
-
 }  // namespace b200ir
-
-#include "conv_kernels.cuh"
 
 namespace b200ir {
 
@@ -594,19 +95,6 @@ int smem_optin() { return init_device_info() ? 0 : g_smem_optin; }
 }  // namespace b200ir
 
 using namespace b200ir;
-
-template <typename K>
-static int configure_smem(K kernel, int slot) {
-  static bool done[8] = {false, false, false, false, false, false, false, false};
-  if (done[slot]) return 0;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-  if (e != cudaSuccess) {
-    set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    return 1;
-  }
-  done[slot] = true;
-  return 0;
-}
 
 extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   B200IR_REQUIRE(d != nullptr, "conv_igemm: null desc");
@@ -714,7 +202,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   }
   // ---- specialised epilogue selection
   {
-    const bool fp16_fast = !d->out_fp32 && (d->no_store || p.st256) && d->cout <= kMaxBias;
+    const bool fp16_fast = !d->out_fp32 && (d->no_store || p.st256) && d->cout <= kMaxBias && p.block_k >= 32;
     int flags = 0;
     bool ok = fp16_fast;
     if (d->demod != nullptr) { flags |= F_DEMOD; ok = ok && p.smem_demod; }
@@ -774,18 +262,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
         if (row_ok) {
           int grid_r = p.row_items < g_num_sms ? p.row_items : g_num_sms;
           if (d->max_ctas > 0 && grid_r > d->max_ctas) grid_r = d->max_ctas;
-          cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-          if (p.block_k == 64) {
-            if (configure_smem(conv_row_kernel<64>, 3)) return 1;
-            conv_row_kernel<64><<<grid_r, kThreads, smem_row, st>>>(p);
-          } else if (p.block_k == 32) {
-            if (configure_smem(conv_row_kernel<32>, 4)) return 1;
-            conv_row_kernel<32><<<grid_r, kThreads, smem_row, st>>>(p);
-          } else {
-            if (configure_smem(conv_row_kernel<16>, 5)) return 1;
-            conv_row_kernel<16><<<grid_r, kThreads, smem_row, st>>>(p);
-          }
-          return check_launch("conv_row");
+          return launch_conv(p, true, grid_r, smem_row, g_smem_optin, reinterpret_cast<cudaStream_t>(stream));
         }
         // not taken: restore the generic activation map (box = tile)
         cuuint32_t box_g[4] = {(cuuint32_t)p.block_k, (cuuint32_t)d->tile_w, (cuuint32_t)d->tile_h, (cuuint32_t)d->tile_b};
@@ -796,16 +273,5 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
 
   int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p.block_k == 64) {
-    if (configure_smem(conv_igemm_kernel<64>, 0)) return 1;
-    conv_igemm_kernel<64><<<grid, kThreads, smem_bytes, st>>>(p);
-  } else if (p.block_k == 32) {
-    if (configure_smem(conv_igemm_kernel<32>, 1)) return 1;
-    conv_igemm_kernel<32><<<grid, kThreads, smem_bytes, st>>>(p);
-  } else {
-    if (configure_smem(conv_igemm_kernel<16>, 2)) return 1;
-    conv_igemm_kernel<16><<<grid, kThreads, smem_bytes, st>>>(p);
-  }
-  return check_launch("conv_igemm");
+  return launch_conv(p, false, grid, smem_bytes, g_smem_optin, reinterpret_cast<cudaStream_t>(stream));
 }
