@@ -18,7 +18,8 @@ import sys
 import threading
 import time
 
-import torch
+os.environ['NCCL_DEBUG'] = os.environ.get('B200IR_NCCL_DEBUG', 'WARN')   # keep NCCL's banner off stdout (one JSON line)
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -304,7 +305,13 @@ def main():
                 tr = json.load(f)
             line['roofline']['traffic'] = tr.get('dram_bytes_per_launch')
             line['roofline']['traffic_source'] = tr.get('source')
-            line['roofline']['algorithmic_bytes_per_launch'] = tr.get('algorithmic_bytes_per_launch')
+            alg = 0
+            for op in conv_ops:
+                d = op.desc
+                m = d.m_b * d.m_h * d.m_w
+                alg += m * d.cin * 2 + (0 if d.no_store else m * d.cout * (4 if d.out_fp32 else 2)) \
+                    + d.cout * d.num_taps * d.cin * 2
+            line['roofline']['algorithmic_bytes_per_launch'] = alg / len(conv_ops)
         for r in pw_report:
             r['frac_of_hbm_peak'] = r['achieved_gbs'] / hbm_peak
         pw_report.sort(key=lambda r: -r['ms_per_step'])
