@@ -123,6 +123,29 @@ class PwOp:
         self.fn()
 
 
+class _Steps(list):
+    """Launch list of a plan.  The list itself holds the ops in construction order (callables, or ('rgb', i) markers
+    for the optional U-Net toRGB heads); `sched` adds the stream lane of every op and the cross-lane dependencies:
+    ('op', lane, op) | ('rec', lane, key) | ('wait', lane, key).  Lane 0 is the caller's stream, lane 1 an auxiliary
+    stream: the StyleGAN decoder runs there one level behind the U-Net decoder that feeds it, and the
+    1x1 skip branch of every ResBlock runs beside its 3x3 branch."""
+
+    def __init__(self):
+        super().__init__()
+        self.sched = []
+        self.lane = 0
+
+    def append(self, op):
+        super().append(op)
+        self.sched.append(('op', self.lane, op))
+
+    def rec(self, key, lane=None):
+        self.sched.append(('rec', self.lane if lane is None else lane, key))
+
+    def wait(self, key, lane=None):
+        self.sched.append(('wait', self.lane if lane is None else lane, key))
+
+
 class _Plan:
     """All buffers and prepared launches for one batch size."""
 
@@ -133,7 +156,7 @@ class _Plan:
         L = pk.L
         H, W = net.input_height, net.input_width
         nf = net.num_style_feat
-        steps = []          # launch list: zero-arg callables (ConvOp or closure) or ('rgb', i) markers
+        steps = _Steps()    # launch list: zero-arg callables (ConvOp / PwOp) or ('rgb', i) markers, with stream lanes
         self.steps = steps
         e16 = lambda *s: torch.empty(*s, device=dev, dtype=F16)  # noqa: E731
         z16 = lambda *s: torch.zeros(*s, device=dev, dtype=F16)  # noqa: E731
@@ -150,14 +173,20 @@ class _Plan:
         for i in range(L):
             d = pk.down[i]
             cin, cout = d['w1'].shape[0], d['w2'].shape[0]
+            steps.rec(f'enc_in{i}')
             t1 = e16(B, h, w, cin)
             steps.append(ops.conv_same(feat, d['w1'], t1, 3, bias=d['b1'], act=True))
             p = z16(B, h + 2, w + 2, cin)
             steps.append(PwOp('fir_pad22', lambda a=t1, o=p: ops.fir_pad22(a, o), t1, p))
+            steps.lane = 1                     # skip branch (FIR + stride-2 sampling, 1x1 conv) beside the 3x3 branch
+            steps.wait(f'enc_in{i}')
             sk_in = e16(B, h // 2, w // 2, cin)
             steps.append(PwOp('fir_down2', lambda a=feat, o=sk_in: ops.fir_down2(a, o), feat, sk_in))
             sk = e16(B, h // 2, w // 2, cout)
             steps.append(ops.conv_same(sk_in, d['ws'], sk, 1))
+            steps.rec(f'enc_skip{i}')
+            steps.lane = 0
+            steps.wait(f'enc_skip{i}')
             nxt = e16(B, h // 2, w // 2, cout)
             oh, ow = h // 2, w // 2
             steps.append(ops.conv3x3_s2(p, h, w, d['w2'], nxt, bias=d['b2'], act=True, res=sk, res_mode=1,
@@ -173,6 +202,7 @@ class _Plan:
         self.style_code = e32(B, n_lin)
         steps.append(ops.linear_as_conv(g.view(B, -1), pk.lin_w, self.style_code, bias=pk.lin_b,
                                         block_n=64 if n_lin % 64 == 0 else None))
+        steps.rec('style_code')
         if net.different_w:
             self.num_latent = n_lin // nf
             self.latent = self.style_code.view(B, self.num_latent, nf)
@@ -193,12 +223,18 @@ class _Plan:
             cin, cout = d['w1'].shape[0], d['w2'].shape[0]
             a = e16(B, h, w, cin)
             steps.append(PwOp('add', lambda x=feat, y=skips[i], o=a: ops.add(x, y, o), feat, skips[i], a))
+            steps.rec(f'up_a{i}')
             t1 = e16(B, h, w, cin)
             steps.append(ops.conv_same(a, d['w1'], t1, 3, bias=d['b1'], act=True))
             u = e16(B, 2 * h, 2 * w, cin)
             steps.append(PwOp('bilinear_up2', lambda x=t1, o=u: ops.bilinear_up2(x, o), t1, u))
             sl = e16(B, h, w, cout)
+            steps.lane = 2
+            steps.wait(f'up_a{i}')
             steps.append(ops.conv_same(a, d['ws'], sl, 1))
+            steps.rec(f'up_sl{i}')
+            steps.lane = 0
+            steps.wait(f'up_sl{i}')
             h2, w2 = 2 * h, 2 * w
             feat = e16(B, h2, w2, cout)
             steps.append(ops.conv_same(u, d['w2'], feat, 3, bias=d['b2'], act=True, res=sl, res_mode=2,
@@ -207,13 +243,21 @@ class _Plan:
             steps.append(ops.conv_same(feat, d['wh0'], hid, 3, bias=d['bh0'], act=True))
             c_sft = d['wsc'].shape[0]
             sc, sh = e16(B, h2, w2, c_sft), e16(B, h2, w2, c_sft)
+            steps.rec(f'up_hid{i}')
             for half, wk, bk, dst in ((0, 'wsc', 'bsc', sc), (1, 'wsh', 'bsh', sh)):
                 v = ops.View(hid.data_ptr() + 2 * half * cout, cout, w2, h2, B, 2 * cout, w2 * 2 * cout,
                              h2 * w2 * 2 * cout)
                 rk = dict(tile=(128, 1, 1), row_mode=1, block_n=c_sft) if ops.row_mode_ok(B, h2, w2, cout, c_sft) else {}
+                if half == 1:                      # the shift head runs beside the scale head
+                    steps.lane = 2
+                    steps.wait(f'up_hid{i}')
                 steps.append(ops.ConvOp([v], d[wk], cout, c_sft, ops.taps_3x3(), (w2, h2, B), dst,
                                         (c_sft, w2 * c_sft, h2 * w2 * c_sft), bias=d[bk], **rk))
+            steps.rec(f'up_sh{i}')
+            steps.lane = 0
+            steps.wait(f'up_sh{i}')
             self.cond.append((sc, sh))
+            steps.rec(f'cond{i}')
             rgb = e32(B, 3, h2, w2)
             self.out_rgbs.append(rgb)
             self.rgb_steps.append(PwOp('to_rgb', lambda x=feat, dd=d, o=rgb: ops.to_rgb(x, dd['wrgb'], None, dd['brgb'], None, o),
@@ -223,6 +267,8 @@ class _Plan:
         self._hid_keep = None
 
         # ---------------- style modulation vectors and demodulation tables (hoisted: depend on the latent only)
+        steps.lane = 1
+        steps.wait('style_code')
         mod_layers, demod_layers = [], []
 
         def mod(layer, lat_idx):
@@ -285,13 +331,21 @@ class _Plan:
             cout = c1['cout']
             h2, w2 = 2 * h, 2 * w
             raw = z16(B, h2 + 2, w2 + 2, cout)
+            steps.rec(f'sg_xs{lvl}')
             for pi, (py, px) in enumerate(ops.CONVT_PHASES):
+                if pi == 1:                        # the three smaller output phases run beside the 4-tap phase
+                    steps.lane = 3
+                    steps.wait(f'sg_xs{lvl}')
                 steps.append(ops.convt_s2_phase(xs, c1['w_phase'][pi], py, px, raw, demod=d_conv[2 * lvl]))
+            steps.rec(f'sg_ph{lvl}')
+            steps.lane = 1
+            steps.wait(f'sg_ph{lvl}')
             n1 = e32(B, 1, h2, w2)
             n2 = e32(B, 1, h2, w2)
             self.noise[2 * lvl + 1], self.noise[2 * lvl + 2] = n1, n2
             self.noise_shapes += [(h2, w2), (h2, w2)]
             sc, sh = self.cond[lvl]
+            steps.wait(f'cond{lvl}')
             xs2 = e16(B, h2, w2, cout)
             steps.append(PwOp('upfir_act', lambda r=raw, o=xs2, n=n1, c=c1, a=sc, b_=sh, sn=s_conv[2 * lvl + 1]:
                               ops.upfir_act(r, o, n, o.shape[1] * o.shape[2], c['gain'], c['bias'], a, b_, a.shape[3], sn),
@@ -308,17 +362,53 @@ class _Plan:
                               part, skip, nskip))
             skip = nskip
             h, w = h2, w2
+        steps.rec('image')
+        steps.lane = 0
+        steps.wait('image')
         self.image = skip
         self.graphs = {}
+        import os
+        self.lanes = max(1, min(4, int(os.environ.get('B200IR_LANES', '4'))))
+        self.aux_streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        self.events = {e[2]: torch.cuda.Event() for e in steps.sched if e[0] == 'rec'}
         self.noise_state = None
 
     def launch(self, return_rgb):
-        for st in self.steps:
-            if isinstance(st, tuple):
-                if return_rgb:
-                    self.rgb_steps[st[1]]()
+        """Enqueues one forward on the current stream (lane 0) and the plan's auxiliary stream (lane 1); lane 1 forks
+        from the current stream at entry and is joined before return, so callers (and CUDA graph capture) see a
+        single-stream operation."""
+        cur = torch.cuda.current_stream()
+        # lane -> stream; lanes beyond the configured count fold onto lower ones (lane 1 <- 3, lane 0 <- 2)
+        n = self.lanes
+        lanes = [cur] + self.aux_streams
+        if n < 4:
+            lanes[3] = lanes[1]
+        if n < 3:
+            lanes[2] = lanes[0]
+        if n < 2:
+            lanes[1] = lanes[3] = lanes[0]
+        used = [st for st in dict.fromkeys(lanes[1:]) if st is not cur]
+        for st in used:
+            st.wait_stream(cur)
+        for e in self.steps.sched:
+            kind, stream = e[0], lanes[e[1]]
+            if kind == 'op':
+                st = e[2]
+                if isinstance(st, tuple):
+                    if not return_rgb:
+                        continue
+                    st = self.rgb_steps[st[1]]
+                if stream is cur:
+                    st()
+                else:
+                    with torch.cuda.stream(stream):
+                        st()
+            elif kind == 'rec':
+                self.events[e[2]].record(stream)
             else:
-                st()
+                stream.wait_event(self.events[e[2]])
+        for st in used:
+            cur.wait_stream(st)
 
 
 class OcrEngine:
