@@ -262,6 +262,15 @@ class GFPGANv1OCR(nn.Module):
         return image, out_rgbs
 
 
+    def restore_uint8(self, img, bgr=True, randomize_noise=True):
+        """The whole `restoration()` body of api.py:92-117 for a batch already at the network size: uint8 HWC images
+        (B,H,W,3) on the device -> restored uint8 HWC images.  img2tensor + normalize, forward(return_rgb=False) and
+        tensor2img(min_max=(-1,1)) all run on the device."""
+        if not img.is_cuda:
+            raise RuntimeError('restore_uint8 takes a CUDA uint8 tensor (use host_io.HostPipeline for host images)')
+        return self.engine().forward(img, return_rgb=False, randomize_noise=randomize_noise, uint8_io=True, bgr=bgr)[0]
+
+
 def register_into(registry=None, name='GFPGANv1OCR_B200', override=False):
     """Registers the B200 class in a basicsr-style Registry (basicsr/utils/registry.py:4-82).
 

@@ -63,6 +63,40 @@ __global__ void first_conv_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------ uint8 image I/O
+// img2tensor + normalize (basicsr/utils/img_util.py:9-35, api.py:96-101): uint8 HWC (BGR when swap) ->
+// fp32 NCHW RGB, x/255 then (x - mean)/std with mean = std = 0.5.
+__global__ void u8_to_input_kernel(const uint8_t* __restrict__ img, float* __restrict__ x, int B, int HW, int swap) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const int p = (int)(idx % HW);
+  const uint8_t* ip = img + idx * 3;
+  float* xp = x + (long long)b * 3 * HW + p;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __fdiv_rn((float)ip[swap ? 2 - c : c], 255.f);  // IEEE division: same bits as torch / numpy
+    xp[(long long)c * HW] = (v - 0.5f) * 2.f;                        // (v - mean) / std, exact for std = 0.5
+  }
+}
+
+// tensor2img (img_util.py:38-94) with min_max = (-1, 1): clamp -> (x+1)/2 -> *255 -> round half to even -> uint8, CHW RGB ->
+// HWC (BGR when swap).
+__global__ void image_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, int B, int HW, int swap) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const int p = (int)(idx % HW);
+  const float* xp = x + (long long)b * 3 * HW + p;
+  uint8_t* op = img + idx * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = fminf(fmaxf(xp[(long long)c * HW], -1.f), 1.f);
+    v = (v + 1.f) * 0.5f;  // (x - min) / (max - min)
+    op[swap ? 2 - c : c] = (uint8_t)__float2int_rn(__fmul_rn(v, 255.0f));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ FIR family
 // 4x4 FIR outer(k,k), k = kscale*[1,3,3,1], evaluated for FOUR horizontally adjacent outputs per thread (8 channels):
 // 4 rows x 7 columns of 16-byte loads feed 4 outputs (7 loads per output instead of 16); separable per row.
@@ -565,6 +599,18 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
   first_conv_kernel<<<grid_for(n), kPwThreads, cout * 4 * sizeof(float), STREAM>>>(x, w, bias, (__half*)out, B, H * W,
                                                                                   cout);
   return check_launch("first_conv");
+}
+
+extern "C" int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, int W, int swap_rb, void* stream) {
+  B200IR_REQUIRE(img && x && B > 0 && H > 0 && W > 0, "u8_to_input: bad arguments");
+  u8_to_input_kernel<<<grid_for((long long)B * H * W), kPwThreads, 0, STREAM>>>(img, x, B, H * W, swap_rb);
+  return check_launch("u8_to_input");
+}
+
+extern "C" int b200ir_image_to_u8(const float* x, uint8_t* img, int B, int H, int W, int swap_rb, void* stream) {
+  B200IR_REQUIRE(img && x && B > 0 && H > 0 && W > 0, "image_to_u8: bad arguments");
+  image_to_u8_kernel<<<grid_for((long long)B * H * W), kPwThreads, 0, STREAM>>>(x, img, B, H * W, swap_rb);
+  return check_launch("image_to_u8");
 }
 
 extern "C" int b200ir_fir_pad22(const void* in, void* out, int B, int H, int W, int C, int out_h, int out_w,

@@ -443,15 +443,25 @@ class OcrEngine:
 
     @torch.no_grad()
     def forward(self, x, return_rgb=True, randomize_noise=True, save_feat_path=None, load_feat_path=None,
-                noise=None):
+                noise=None, uint8_io=False, bgr=True):
+        """uint8_io: `x` is a uint8 HWC image batch (B,H,W,3) (BGR when `bgr`) as the serving scripts hold it; the
+        img2tensor/normalize on the way in and tensor2img on the way out (api.py:96-105) run on the device and the
+        returned image is uint8 (B,H,W,3)."""
         net = self.net
         B = x.shape[0]
-        if tuple(x.shape[1:]) != (3, net.input_height, net.input_width):
+        if uint8_io:
+            if x.dtype != torch.uint8 or tuple(x.shape[1:]) != (net.input_height, net.input_width, 3):
+                raise ValueError(f'uint8_io expects uint8 (B,{net.input_height},{net.input_width},3), got '
+                                 f'{x.dtype} {tuple(x.shape)}')
+        elif tuple(x.shape[1:]) != (3, net.input_height, net.input_width):
             raise ValueError(f'expected input (B,3,{net.input_height},{net.input_width}), got {tuple(x.shape)}')
         dev = self.packed.dev
         with torch.cuda.device(dev):
             plan = self.plan(B)
-            plan.x_in.copy_(x)
+            if uint8_io:
+                ops.u8_to_input(x.contiguous(), plan.x_in, swap_rb=bgr)
+            else:
+                plan.x_in.copy_(x)
             pk = self.packed
             if noise is None and not randomize_noise and plan.noise_state == 'stored':
                 pass                                  # buffers already hold the registered noise planes
@@ -477,8 +487,12 @@ class OcrEngine:
                         plan.launch(return_rgb)
                     plan.graphs[key] = gr
                 gr.replay()
-            image = plan.image.clone()
             rgbs = [t.clone() for t in plan.out_rgbs] if return_rgb else []
+            if uint8_io:
+                image = torch.empty(B, net.input_height, net.input_width, 3, device=dev, dtype=torch.uint8)
+                ops.image_to_u8(plan.image, image, swap_rb=bgr)
+                return image, rgbs
+            image = plan.image.clone()
         return image.to(x.dtype) if x.dtype != F32 else image, rgbs
 
     def _run_eager(self, plan, return_rgb, save_feat_path, load_feat_path):

@@ -24,12 +24,12 @@ class _Slot:
 
 
 class HostPipeline:
-    def __init__(self, net, depth=2, return_rgb=False, randomize_noise=False):
+    def __init__(self, net, depth=2, return_rgb=False, randomize_noise=False, bgr=True):
         dev = next(net.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('HostPipeline needs the module on a CUDA B200 (no CPU path)')
         self.net, self.dev, self.depth = net, dev, depth
-        self.return_rgb, self.randomize_noise = return_rgb, randomize_noise
+        self.return_rgb, self.randomize_noise, self.bgr = return_rgb, randomize_noise, bgr
         with torch.cuda.device(dev):
             self.h2d = torch.cuda.Stream()
             self.d2h = torch.cuda.Stream()
@@ -38,8 +38,8 @@ class HostPipeline:
         self.n = 0
 
     def submit(self, x_host, y_host, rgbs_host=None):
-        """x_host: (B,3,H,W) float32 host tensor (pinned for true asynchrony); y_host: host tensor for the image.
-        Returns a ticket for wait()."""
+        """x_host: (B,3,H,W) float32 host tensor in [-1,1], or (B,H,W,3) uint8 images (then y_host is uint8 (B,H,W,3)
+        too); pinned for true asynchrony.  Returns a ticket for wait()."""
         if x_host.is_cuda or y_host.is_cuda:
             raise ValueError('HostPipeline.submit takes HOST tensors; call the module directly for device tensors')
         s = self.slots[self.n % self.depth]
@@ -50,12 +50,16 @@ class HostPipeline:
             with torch.cuda.stream(self.h2d):
                 if s.busy:
                     self.h2d.wait_event(s.compute_done)     # previous input of this slot consumed
-                if s.x_dev is None or s.x_dev.shape != x_host.shape:
-                    s.x_dev = torch.empty(x_host.shape, device=self.dev, dtype=torch.float32)
+                if s.x_dev is None or s.x_dev.shape != x_host.shape or s.x_dev.dtype != x_host.dtype:
+                    s.x_dev = torch.empty(x_host.shape, device=self.dev, dtype=x_host.dtype)
                 s.x_dev.copy_(x_host, non_blocking=True)
                 s.h2d_done.record(self.h2d)
             compute.wait_event(s.h2d_done)
-            s.image, s.rgbs = self.net(s.x_dev, return_rgb=self.return_rgb, randomize_noise=self.randomize_noise)
+            if x_host.dtype == torch.uint8:     # uint8 HWC images in, uint8 HWC images out (api.py:96-105 on the device)
+                s.image = self.net.restore_uint8(s.x_dev, bgr=self.bgr, randomize_noise=self.randomize_noise)
+                s.rgbs = []
+            else:
+                s.image, s.rgbs = self.net(s.x_dev, return_rgb=self.return_rgb, randomize_noise=self.randomize_noise)
             s.compute_done.record(compute)
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(s.compute_done)

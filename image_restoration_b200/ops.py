@@ -213,6 +213,18 @@ def first_conv(x, w, bias, out):
           'first_conv')
 
 
+def u8_to_input(img, x, swap_rb=True):
+    """uint8 HWC batch [B,H,W,3] -> fp32 NCHW [-1,1] (img2tensor + normalize of api.py:96-101)."""
+    b, h, w, _ = img.shape
+    check(_lib.lib().b200ir_u8_to_input(_ptr(img), _ptr(x), b, h, w, 1 if swap_rb else 0, _stream()), 'u8_to_input')
+
+
+def image_to_u8(x, img, swap_rb=True):
+    """fp32 NCHW network output -> uint8 HWC (tensor2img with min_max=(-1,1), api.py:105)."""
+    b, _, h, w = x.shape
+    check(_lib.lib().b200ir_image_to_u8(_ptr(x), _ptr(img), b, h, w, 1 if swap_rb else 0, _stream()), 'image_to_u8')
+
+
 def fir_pad22(x, out):
     b, h, w, c = x.shape
     check(_lib.lib().b200ir_fir_pad22(_ptr(x), _ptr(out), b, h, w, c, out.shape[1], out.shape[2], _stream()),

@@ -129,6 +129,14 @@ int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
 int b200ir_first_conv(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int cout,
                       void* stream);
 
+/* Pre / post of the serving scripts (api.py:96-105, inference.py:61-71):
+ * u8_to_input  = img2tensor(img / 255., bgr2rgb=True, float32=True) + normalize(mean .5, std .5)
+ *                (basicsr/utils/img_util.py:9-35): uint8 HWC [B][H][W][3] -> fp32 NCHW [B][3][H][W] in [-1, 1];
+ * image_to_u8  = tensor2img(out, rgb2bgr=True, min_max=(-1, 1)) (img_util.py:38-94): clamp, (x+1)/2, *255, round half
+ *                to even, uint8 HWC.  swap_rb != 0 reverses the channel order (BGR images, as cv2 delivers them). */
+int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, int W, int swap_rb, void* stream);
+int b200ir_image_to_u8(const float* x, uint8_t* img, int B, int H, int W, int swap_rb, void* stream);
+
 /* UpFirDnSmooth before a stride-2 3x3 conv (pad (2,2), ConvLayer downsample=True, k=3):
  * in [B][H][W][C] -> out rows/cols 0..H / 0..W of a [B][out_h][out_w][C] buffer (out_h >= H+1, out_w >= W+1). */
 int b200ir_fir_pad22(const void* in, void* out, int B, int H, int W, int C, int out_h, int out_w, void* stream);

@@ -158,3 +158,39 @@ def test_host_pipeline_matches_direct_call():
     ref = torch.cat([net(xs[0][:2].cuda(), return_rgb=False, randomize_noise=False)[0],
                      net(xs[0][2:].cuda(), return_rgb=False, randomize_noise=False)[0]]).cpu()
     assert torch.equal(y2, ref)
+
+
+def test_uint8_image_io_matches_reference_pre_post():
+    """uint8 BGR HWC in -> uint8 BGR HWC out on the device == tensor2img(net(normalize(img2tensor(img/255))))
+    (basicsr/utils/img_util.py:9-94 as api.py:96-105 calls them): exact against our own fp32 output, within one code of
+    the CPU oracle, through the module method and through the host pipeline."""
+    from image_restoration_b200 import GFPGANv1OCR
+    from image_restoration_b200.host_io import HostPipeline
+    from oracle.gfpgan_ocr_oracle import OcrNetConfig, gfpgan_ocr_forward
+    torch.manual_seed(0)
+    kw = dict(input_width=96, input_height=32, num_style_feat=256, channel_multiplier=0.5, num_mlp=4,
+              input_is_latent=True, different_w=True, narrow=1, sft_half=True)
+    net = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **kw).eval()
+    img = torch.randint(0, 256, (3, 32, 96, 3), dtype=torch.uint8)                 # BGR HWC, as cv2 delivers it
+
+    def pre(im):      # img2tensor(img / 255., bgr2rgb=True, float32=True) + normalize(.5, .5)
+        x = (im.double() / 255.).float().flip(-1).permute(0, 3, 1, 2).contiguous()
+        return (x - 0.5) / 0.5
+
+    def post(y):      # tensor2img(y, rgb2bgr=True, min_max=(-1, 1))
+        y = (y.float().clamp(-1, 1) + 1) / 2
+        return (y.permute(0, 2, 3, 1).flip(-1) * 255.0).round().to(torch.uint8)
+
+    ref, _ = gfpgan_ocr_forward(net.state_dict(), OcrNetConfig(**kw), pre(img), False)
+    net = net.cuda()
+    got = net.restore_uint8(img.cuda(), bgr=True, randomize_noise=False).cpu()
+    own = post(net(pre(img).cuda(), return_rgb=False, randomize_noise=False)[0].cpu())
+    assert got.dtype == torch.uint8 and got.shape == img.shape
+    assert torch.equal(got, own)
+    diff = (got.int() - post(ref).int()).abs()
+    print('uint8 path vs oracle: max code diff', diff.max().item(), 'mean', diff.float().mean().item())
+    assert diff.max().item() <= 6 and diff.float().mean().item() < 0.6      # 2e-2 of 255 = 5.1 codes (+ rounding)
+    pipe = HostPipeline(net, depth=2, bgr=True)
+    y_host = torch.empty_like(img).pin_memory()
+    pipe.wait(pipe.submit(img.pin_memory(), y_host))
+    assert torch.equal(y_host, got)
