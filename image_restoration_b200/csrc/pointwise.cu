@@ -97,6 +97,53 @@ __global__ void image_to_u8_kernel(const float* __restrict__ x, uint8_t* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------ tiled full-frame inference
+// BASELINE config 4: a frame is cut into overlapping T x T tiles (positions ty[], tx[]), the tiles go through the network
+// as one batch, and are blended back with separable linear-ramp weights (weight 1 on the frame border side of a border
+// tile, ramp (d+1)/(ov+1) over the first / last `ov` pixels elsewhere), normalised by the weight sum.
+__device__ __forceinline__ float tile_ramp(int i, int T, int ov, bool at_lo, bool at_hi) {
+  float w = 1.f;
+  if (!at_lo) w = fminf(w, (float)(i + 1) / (float)(ov + 1));
+  if (!at_hi) w = fminf(w, (float)(T - i) / (float)(ov + 1));
+  return w;
+}
+
+__global__ void tiles_gather_kernel(const float* __restrict__ frame, float* __restrict__ tiles, int C, int H, int W, int T,
+                                    const int* __restrict__ ty, const int* __restrict__ tx, int nty, int ntx) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_tile = (long long)C * T * T;
+  if (idx >= per_tile * nty * ntx) return;
+  const int t = (int)(idx / per_tile);
+  long long r = idx % per_tile;
+  const int c = (int)(r / (T * T));
+  r %= (long long)T * T;
+  const int y = (int)(r / T), x = (int)(r % T);
+  const int y0 = ty[t / ntx], x0 = tx[t % ntx];
+  tiles[idx] = frame[((long long)c * H + y0 + y) * W + x0 + x];
+}
+
+__global__ void tiles_blend_kernel(const float* __restrict__ tiles, float* __restrict__ frame, int C, int H, int W, int T,
+                                   int ov, const int* __restrict__ ty, const int* __restrict__ tx, int nty, int ntx) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)H * W) return;
+  const int y = (int)(idx / W), x = (int)(idx % W);
+  float num[4] = {0.f, 0.f, 0.f, 0.f}, den = 0.f;
+  for (int iy = 0; iy < nty; ++iy) {
+    const int y0 = ty[iy];
+    if (y < y0 || y >= y0 + T) continue;
+    const float wy = tile_ramp(y - y0, T, ov, y0 == 0, y0 + T == H);
+    for (int ix = 0; ix < ntx; ++ix) {
+      const int x0 = tx[ix];
+      if (x < x0 || x >= x0 + T) continue;
+      const float w = wy * tile_ramp(x - x0, T, ov, x0 == 0, x0 + T == W);
+      const float* tp = tiles + ((long long)(iy * ntx + ix) * C * T + (y - y0)) * T + (x - x0);
+      for (int c = 0; c < C; ++c) num[c] += w * tp[(long long)c * T * T];
+      den += w;
+    }
+  }
+  for (int c = 0; c < C; ++c) frame[((long long)c * H + y) * W + x] = num[c] / den;
+}
+
 // ------------------------------------------------------------------------------------------ FIR family
 // 4x4 FIR outer(k,k), k = kscale*[1,3,3,1], evaluated for FOUR horizontally adjacent outputs per thread (8 channels):
 // 4 rows x 7 columns of 16-byte loads feed 4 outputs (7 loads per output instead of 16); separable per row.
@@ -599,6 +646,24 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
   first_conv_kernel<<<grid_for(n), kPwThreads, cout * 4 * sizeof(float), STREAM>>>(x, w, bias, (__half*)out, B, H * W,
                                                                                   cout);
   return check_launch("first_conv");
+}
+
+extern "C" int b200ir_tiles_gather(const float* frame, float* tiles, int C, int H, int W, int T, const int32_t* ty,
+                                   const int32_t* tx, int nty, int ntx, void* stream) {
+  B200IR_REQUIRE(frame && tiles && ty && tx && C > 0 && T > 0 && T <= H && T <= W && nty > 0 && ntx > 0,
+                 "tiles_gather: bad arguments");
+  tiles_gather_kernel<<<grid_for((long long)C * T * T * nty * ntx), kPwThreads, 0, STREAM>>>(frame, tiles, C, H, W, T, ty,
+                                                                                           tx, nty, ntx);
+  return check_launch("tiles_gather");
+}
+
+extern "C" int b200ir_tiles_blend(const float* tiles, float* frame, int C, int H, int W, int T, int overlap,
+                                  const int32_t* ty, const int32_t* tx, int nty, int ntx, void* stream) {
+  B200IR_REQUIRE(frame && tiles && ty && tx && C > 0 && C <= 4 && T > 0 && overlap >= 0 && nty > 0 && ntx > 0,
+                 "tiles_blend: bad arguments");
+  tiles_blend_kernel<<<grid_for((long long)H * W), kPwThreads, 0, STREAM>>>(tiles, frame, C, H, W, T, overlap, ty, tx,
+                                                                            nty, ntx);
+  return check_launch("tiles_blend");
 }
 
 extern "C" int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, int W, int swap_rb, void* stream) {

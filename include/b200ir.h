@@ -137,6 +137,16 @@ int b200ir_first_conv(const float* x, const float* w, const float* bias, void* o
 int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, int W, int swap_rb, void* stream);
 int b200ir_image_to_u8(const float* x, uint8_t* img, int B, int H, int W, int swap_rb, void* stream);
 
+/* Tiled full-frame inference (BASELINE config 4; the reference has no tiling code -- api_plate_oto.py:376-401 resizes
+ * the whole image -- so the contract is this header): frame fp32 [C][H][W]; tiles fp32 [nty*ntx][C][T][T] at rows ty[]
+ * and columns tx[] (device int32 arrays, ascending, first 0, last H-T / W-T).  Blend weights are separable linear
+ * ramps min(1, (d+1)/(overlap+1)) with d the distance to a tile edge that is not a frame edge; the result is the
+ * weight-normalised sum. */
+int b200ir_tiles_gather(const float* frame, float* tiles, int C, int H, int W, int T, const int32_t* ty,
+                        const int32_t* tx, int nty, int ntx, void* stream);
+int b200ir_tiles_blend(const float* tiles, float* frame, int C, int H, int W, int T, int overlap, const int32_t* ty,
+                       const int32_t* tx, int nty, int ntx, void* stream);
+
 /* UpFirDnSmooth before a stride-2 3x3 conv (pad (2,2), ConvLayer downsample=True, k=3):
  * in [B][H][W][C] -> out rows/cols 0..H / 0..W of a [B][out_h][out_w][C] buffer (out_h >= H+1, out_w >= W+1). */
 int b200ir_fir_pad22(const void* in, void* out, int B, int H, int W, int C, int out_h, int out_w, void* stream);

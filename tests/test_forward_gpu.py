@@ -194,3 +194,23 @@ def test_uint8_image_io_matches_reference_pre_post():
     y_host = torch.empty_like(img).pin_memory()
     pipe.wait(pipe.submit(img.pin_memory(), y_host))
     assert torch.equal(y_host, got)
+
+
+def test_config3_sharded_micro_batches_match_direct_calls():
+    """BASELINE config 3 on one GPU: each emulated rank of an 8-way split runs its contiguous shard in micro-batches
+    (sharding.run_sharded, no collective); the concatenation over ranks equals direct calls on the same crops bit for
+    bit (crops are independent: batch composition must not change a result)."""
+    from image_restoration_b200 import GFPGANv1OCR
+    from image_restoration_b200.sharding import run_sharded, shard_bounds
+    torch.manual_seed(5)
+    kw = dict(input_width=96, input_height=32, num_style_feat=256, channel_multiplier=0.5, num_mlp=4,
+              input_is_latent=True, different_w=True, narrow=1, sft_half=True)
+    net = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **kw).eval().cuda()
+    n, world = 203, 8                                   # ragged: shards of 26/25 crops, micro-batches of 16 + remainder
+    x = (torch.rand(n, 3, 32, 96) * 2 - 1).cuda()
+    fn = lambda xb: net(xb, return_rgb=False, randomize_noise=False)[0]       # noqa: E731
+    parts = [run_sharded(fn, x, r, world, micro_batch=16) for r in range(world)]
+    assert [p.shape[0] for p in parts] == [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
+    full = torch.cat(parts, 0)
+    direct = torch.cat([fn(x[i:i + 29]) for i in range(0, n, 29)], 0)
+    assert torch.equal(full, direct)
