@@ -34,6 +34,7 @@ class ConvDesc(C.Structure):
         ('row_mode', C.c_int32),
         ('out_scale', C.c_void_p), ('rgb_w', C.c_void_p), ('rgb_part', C.c_void_p),
         ('rgb_w_px', C.c_int32), ('rgb_h', C.c_int32), ('no_store', C.c_int32),
+        ('act_slope', C.c_float), ('res_mul', C.c_float), ('ps_r', C.c_int32),
     ]
 
 
@@ -74,6 +75,11 @@ SIGNATURES = {
     'b200ir_mod_linear_multi': [_P, _I, _I, _P, _I, _I, _F, _I, _P],
     'b200ir_demod_multi': [_P, _I, _I, _I, _P],
     'b200ir_nhwc_to_nchw_f32': [_P, _P, _I, _I, _I, _P],
+    'b200ir_nchw_to_nhwc_pad': [_P, _P, _I, _I, _I, _I, _I, _P, _F, _P],
+    'b200ir_sr_output': [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P],
+    'b200ir_channel_mean': [_P, _P, _I, _I, _I, _P],
+    'b200ir_ca_mlp': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    'b200ir_ca_scale_add': [_P, _P, _P, _P, _F, _I, _I, _I, _P],
     'b200ir_degrade': [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64}

@@ -66,6 +66,8 @@ struct alignas(64) ConvParams {
   long long res_sx, res_sy, res_sb;
   int res_w, res_h;
   float res_scale;
+  float res_mul;  // weight of the residual term: v * res_scale + res * res_mul (legacy (v + res) * s: res_mul = s)
+  int ps_r;       // pixel-shuffle factor of the store (0: off)
   const float* out_scale;
   const float* rgb_w;
   float* rgb_part;
@@ -121,9 +123,16 @@ struct EpiRow {
 
 __device__ __forceinline__ EpiRow epi_setup(const ConvParams& p, int x, int y, int b, int n0, bool valid, float gain) {
   EpiRow r;
-  const int xo = x * p.out_x_mul + p.out_x_off;
-  const int yo = y * p.out_y_mul + p.out_y_off;
-  r.out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx + p.out_c_off + n0;
+  int xo = x * p.out_x_mul + p.out_x_off;
+  int yo = y * p.out_y_mul + p.out_y_off;
+  int nch = n0;  // channel offset of this N-tile in the output
+  if (p.ps_r) {  // nn.PixelShuffle fused into the store: N-tile t -> sub-pixel (t / r, t % r), channels restart at 0
+    const int t = n0 / p.block_n;
+    xo = x * p.ps_r + t % p.ps_r;
+    yo = y * p.ps_r + t / p.ps_r;
+    nch = 0;
+  }
+  r.out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx + p.out_c_off + nch;
   r.chan_off = (long long)b * p.cout + n0;
   r.rgbw_off = (long long)b * 3 * p.cout + n0;
   r.rgb_off = (long long)(n0 / p.block_n) * p.rgb_image + (long long)b * 3 * p.rgb_plane + (long long)yo * p.rgb_w_px + xo;
@@ -231,14 +240,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
       }
       if (p.act) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], p.slope * v[j]);
       }
       if (p.res_mode == 1) {
         float f[16];
         unpack_half8(ra[0], f);
         unpack_half8(ra[1], f + 8);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (v[j] + f[j]) * p.res_scale;
+        for (int j = 0; j < 16; ++j) v[j] = v[j] * p.res_scale + f[j] * p.res_mul;
       } else if (p.res_mode == 2) {
         float fa[16], fb[16], fc[16], fd[16];
         unpack_half8(ra[0], fa); unpack_half8(ra[1], fa + 8);
@@ -248,7 +257,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float up = r.wy0 * (r.wx0 * fa[j] + r.wx1 * fb[j]) + r.wy1 * (r.wx0 * fc[j] + r.wx1 * fd[j]);
-          v[j] = (v[j] + up) * p.res_scale;
+          v[j] = v[j] * p.res_scale + up * p.res_mul;
         }
       }
       if (p.rgb_w != nullptr) {
@@ -346,10 +355,17 @@ struct FastRow {
 template <int F>
 __device__ __forceinline__ FastRow fast_setup(const ConvParams& p, int x, int y, int b, int n0, bool valid) {
   FastRow r;
-  const int xo = x * p.out_x_mul + p.out_x_off;
-  const int yo = y * p.out_y_mul + p.out_y_off;
+  int xo = x * p.out_x_mul + p.out_x_off;
+  int yo = y * p.out_y_mul + p.out_y_off;
+  int nch = n0;
+  if (p.ps_r) {  // see epi_setup
+    const int t = n0 / p.block_n;
+    xo = x * p.ps_r + t % p.ps_r;
+    yo = y * p.ps_r + t / p.ps_r;
+    nch = 0;
+  }
   r.out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_sb + (long long)yo * p.out_sy +
-          (long long)xo * p.out_sx + p.out_c_off + n0;
+          (long long)xo * p.out_sx + p.out_c_off + nch;
   r.rgb = nullptr;
   if (F & F_RGB)
     r.rgb = p.rgb_part + (long long)(n0 / p.block_n) * p.rgb_image + (long long)b * 3 * p.rgb_plane +
@@ -360,7 +376,7 @@ __device__ __forceinline__ FastRow fast_setup(const ConvParams& p, int x, int y,
   r.w00 = r.w01 = r.w10 = r.w11 = 0.f;
   if ((F & F_RES1) && valid) {
     r.r00 = p.res + (long long)b * p.res_sb + (long long)yo * p.res_sy + (long long)xo * p.res_sx + n0;
-    r.w00 = p.res_scale;
+    r.w00 = p.res_mul;
   }
   if ((F & F_RES2) && valid) {
     const int ky = yo >> 1, kx = xo >> 1;
@@ -375,8 +391,8 @@ __device__ __forceinline__ FastRow fast_setup(const ConvParams& p, int x, int y,
     r.r01 = rb + (long long)ya * p.res_sy + (long long)xb * p.res_sx;
     r.r10 = rb + (long long)yb * p.res_sy + (long long)xa * p.res_sx;
     r.r11 = rb + (long long)yb * p.res_sy + (long long)xb * p.res_sx;
-    wy0 *= p.res_scale;
-    wy1 *= p.res_scale;
+    wy0 *= p.res_mul;
+    wy1 *= p.res_mul;
     r.w00 = wy0 * wx0; r.w01 = wy0 * wx1; r.w10 = wy1 * wx0; r.w11 = wy1 * wx1;
   }
   return r;

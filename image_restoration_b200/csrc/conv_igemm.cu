@@ -113,6 +113,10 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   B200IR_REQUIRE(d->res_mode >= 0 && d->res_mode <= 2, "conv_igemm: res_mode");
   B200IR_REQUIRE(d->res_mode == 0 || d->res != nullptr, "conv_igemm: res_mode set but res is NULL");
   B200IR_REQUIRE(d->noise == nullptr || d->noise_gain != nullptr, "conv_igemm: noise without noise_gain");
+  B200IR_REQUIRE(d->act >= 0 && d->act <= 2, "conv_igemm: act=%d", d->act);
+  B200IR_REQUIRE(d->ps_r == 0 || ((d->ps_r == 2 || d->ps_r == 3) && d->block_n * d->ps_r * d->ps_r == d->cout &&
+                                  d->rgb_w == nullptr && d->res_mode == 0 && d->noise == nullptr),
+                 "conv_igemm: ps_r=%d needs block_n = cout / ps_r^2 and a plain epilogue", d->ps_r);
   B200IR_REQUIRE(d->rgb_w == nullptr || (d->rgb_part != nullptr && d->rgb_w_px > 0 && d->rgb_h > 0),
                  "conv_igemm: rgb_w needs rgb_part and the plane extents");
   B200IR_REQUIRE(!d->no_store || d->rgb_w != nullptr, "conv_igemm: no_store without a fused ToRGB leaves no output");
@@ -191,9 +195,11 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   p.cout = d->cout;
   p.bias = d->bias; p.demod = d->demod; p.noise = d->noise; p.noise_gain = d->noise_gain;
   p.noise_sb = d->noise_stride_b; p.noise_sy = d->noise_stride_y;
-  p.act = d->act; p.act_gain = d->act ? 1.4142135623730951f : 1.f; p.res_mode = d->res_mode; p.res = reinterpret_cast<const __half*>(d->res);
+  p.act = d->act; p.act_gain = d->act == 1 ? 1.4142135623730951f : 1.f; p.res_mode = d->res_mode; p.res = reinterpret_cast<const __half*>(d->res);
   p.res_sx = d->res_stride_x; p.res_sy = d->res_stride_y; p.res_sb = d->res_stride_b;
   p.res_w = d->res_w; p.res_h = d->res_h; p.res_scale = d->res_scale;
+  p.res_mul = d->res_mul != 0.f ? d->res_mul : d->res_scale;
+  p.ps_r = d->ps_r;
   {
     static int dbg = -1;
     if (dbg < 0) dbg = (getenv("B200IR_DBG_SKIP_EPI") != nullptr) ? 1 : 0;
@@ -218,7 +224,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
     static int force_generic = -1;
     if (force_generic < 0) force_generic = (getenv("B200IR_GENERIC_EPI") != nullptr) ? 1 : 0;
     if (force_generic) p.epi = -1;
-    p.slope = d->act ? 0.2f : 1.f;
+    p.slope = d->act == 1 ? 0.2f : (d->act == 2 ? d->act_slope : 1.f);
     if (p.epi >= 0 && d->res_mode != 0) p.act_gain *= d->res_scale;
   }
   p.out_scale = d->out_scale; p.rgb_w = d->rgb_w; p.rgb_part = d->rgb_part; p.no_store = d->no_store;

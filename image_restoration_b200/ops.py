@@ -62,7 +62,7 @@ class ConvOp:
                  out_mul_off=(1, 0, 1, 0), bias=None, demod=None, noise=None, noise_gain=None, noise_strides=(0, 0),
                  act=False, res=None, res_mode=0, res_strides=(0, 0, 0), res_wh=(0, 0), res_scale=1.0, block_n=None,
                  tile=None, max_ctas=0, row_mode=0, out_scale=None, rgb_w=None, rgb_part=None, rgb_hw=(0, 0),
-                 no_store=False):
+                 no_store=False, act_slope=None, res_mul=0.0, ps_r=0):
         d = ConvDesc()
         assert 1 <= len(views) <= _lib.MAX_VIEWS and 1 <= len(taps) <= _lib.MAX_TAPS
         for i, v in enumerate(views):
@@ -87,7 +87,11 @@ class ConvOp:
                 _req(t, torch.float32, name)
                 setattr(d, name, t.data_ptr())
         d.noise_stride_b, d.noise_stride_y = noise_strides
-        d.act = 1 if act else 0
+        # act=True: FusedLeakyReLU (slope 0.2, gain sqrt 2); act_slope given: max(v, act_slope * v) without gain
+        d.act = 2 if act_slope is not None else (1 if act else 0)
+        d.act_slope = float(act_slope) if act_slope is not None else 0.0
+        d.res_mul = res_mul
+        d.ps_r = ps_r
         d.res_mode = res_mode
         if res is not None:
             _req(res, torch.float16, 'res')
@@ -327,6 +331,36 @@ class DemodMulti:
 
     def __call__(self):
         check(_lib.lib().b200ir_demod_multi(_ptr(self.table), self.n, self.max_cout, self.b, _stream()), 'demod_multi')
+
+
+# ------------------------------------------------------------------------------------------ SR-network stages
+def nchw_to_nhwc_pad(x, out, sub=None, mul=1.0):
+    b, c, h, w = x.shape
+    check(_lib.lib().b200ir_nchw_to_nhwc_pad(_ptr(x), _ptr(out), b, c, h, w, out.shape[3], _ptr(sub), mul, _stream()),
+          'nchw_to_nhwc_pad')
+
+
+def sr_output(y, out, mul=1.0, add=None, base=None, scale=1):
+    b, c, h, w = out.shape
+    check(_lib.lib().b200ir_sr_output(_ptr(y), _ptr(out), b, c, h, w, y.shape[3], mul, _ptr(add), _ptr(base), scale,
+                                      _stream()), 'sr_output')
+
+
+def channel_mean(x, mean):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_channel_mean(_ptr(x), _ptr(mean), b, h * w, c, _stream()), 'channel_mean')
+
+
+def ca_mlp(mean, w1, b1, w2, b2, att):
+    b, c = mean.shape
+    check(_lib.lib().b200ir_ca_mlp(_ptr(mean), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(att), b, c, w1.shape[0],
+                                   _stream()), 'ca_mlp')
+
+
+def ca_scale_add(x, att, identity, out, res_scale=1.0):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_ca_scale_add(_ptr(x), _ptr(att), _ptr(identity), _ptr(out), res_scale, b, h * w, c,
+                                         _stream()), 'ca_scale_add')
 
 
 def nhwc_to_nchw_f32(x, out):

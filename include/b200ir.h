@@ -100,7 +100,7 @@ typedef struct {
   const float* noise;      /* fp32 plane(s) indexed [b*noise_stride_b + yo*noise_stride_y + xo] or NULL */
   const float* noise_gain; /* device scalar (StyleConv.weight) */
   int64_t noise_stride_b, noise_stride_y;
-  int32_t act;      /* 0 none, 1 leaky-relu(0.2)*sqrt(2) */
+  int32_t act;      /* 0 none, 1 leaky-relu(0.2)*sqrt(2) (FusedLeakyReLU), 2 max(v, act_slope*v) */
   int32_t res_mode; /* 0 none, 1 same resolution, 2 bilinear x2 of a half-resolution tensor */
   const void* res;  /* fp16 NHWC */
   int64_t res_stride_x, res_stride_y, res_stride_b;
@@ -115,6 +115,16 @@ typedef struct {
   float* rgb_part;        /* [cout/block_n][m_b][3][rgb_h][rgb_w_px] fp32, required with rgb_w */
   int32_t rgb_w_px, rgb_h;
   int32_t no_store;       /* 1: do not write `out` (the tensor is only consumed by the fused ToRGB) */
+  /* plain nn.Conv2d networks (options/*.yml archs: MSRResNet / EDSR / RCAN, basicsr/archs/arch_util.py):
+   * act == 2: v = max(v, act_slope * v) without the sqrt(2) gain (nn.ReLU: slope 0, nn.LeakyReLU(0.1): slope 0.1);
+   * res_mul != 0: the residual merge is v * res_scale + res * res_mul (ResidualBlockNoBN: identity + out * res_scale,
+   *   arch_util.py:90-93) instead of (v + res) * res_scale;
+   * ps_r = 2 or 3: nn.PixelShuffle(ps_r) fused into the store (arch_util.py:96-109, srresnet_arch.py:60-64): the
+   *   weight rows are packed in (dy, dx, c) order with block_n = cout / ps_r^2, N-tile t = dy * ps_r + dx writes its
+   *   block_n channels to pixel (y * ps_r + dy, x * ps_r + dx); out strides describe the up-sampled tensor. */
+  float act_slope;
+  float res_mul;
+  int32_t ps_r;
 } b200ir_conv_desc;
 
 int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
@@ -219,6 +229,30 @@ int b200ir_demod_multi(const b200ir_demod_layer* layers_dev, int n_layers, int m
 /* NHWC fp16 [B][P][C] -> fp32 matrix [B][P*C] is a reinterpretation; this converts fp32 NCHW image batches to the
  * caller-facing layout when needed: out_nchw[b][c][p] = in_nhwc[b][p][c] (fp16 -> fp32). */
 int b200ir_nhwc_to_nchw_f32(const void* in, float* out, int B, int P, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Plain-conv SR networks of options/*.yml (MSRResNet srresnet_arch.py:8-68, EDSR edsr_arch.py:8-72, RCAN
+ * rcan_arch.py:8-135): the 3x3 convs, ReLU / LeakyReLU(0.1), residual merges and nn.PixelShuffle run in
+ * b200ir_conv_igemm (act == 2, res_mul, ps_r); these are the memory-bound stages around them.
+ */
+
+/* fp32 NCHW [B][C][H][W] -> NHWC fp16 [B][H][W][Cpad], (x - sub[c]) * mul, zero padding channels (edsr_arch.py:62:
+ * (x - mean) * img_range; sub may be NULL). */
+int b200ir_nchw_to_nhwc_pad(const float* x, void* out, int B, int C, int H, int W, int Cpad, const float* sub, float mul,
+                            void* stream);
+/* conv_last output fp32 NHWC [B][H][W][Cpad] -> fp32 NCHW [B][C][H][W]: y * mul + add[c] (edsr_arch.py:69:
+ * x / img_range + mean) + F.interpolate(base, scale_factor=scale, mode='bilinear', align_corners=False)
+ * (srresnet_arch.py:66-67; base fp32 NCHW [B][C][H/scale][W/scale] or NULL). */
+int b200ir_sr_output(const float* y, float* out, int B, int C, int H, int W, int Cpad, float mul, const float* add,
+                     const float* base, int scale, void* stream);
+/* RCAN channel attention (rcan_arch.py:8-24): nn.AdaptiveAvgPool2d(1) of an NHWC fp16 tensor -> mean fp32 [B][C];
+ * att = sigmoid(W2 relu(W1 mean + b1) + b2) with W1 [Cs][C], W2 [C][Cs]; RCAB tail (rcan_arch.py:43-45)
+ * out = x * att[b][c] * res_scale + identity. */
+int b200ir_channel_mean(const void* x, float* mean, int B, int HW, int C, void* stream);
+int b200ir_ca_mlp(const float* mean, const float* w1, const float* b1, const float* w2, const float* b2, float* att,
+                  int B, int C, int Cs, void* stream);
+int b200ir_ca_scale_add(const void* x, const float* att, const void* identity, void* out, float res_scale, int B, int HW,
+                        int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused degradation (pyblur blur -> cv2.resize down -> Gaussian noise -> clip -> cv2.resize up -> round/clip ->
