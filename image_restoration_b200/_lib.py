@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ('out_scale', C.c_void_p), ('rgb_w', C.c_void_p), ('rgb_part', C.c_void_p),
         ('rgb_w_px', C.c_int32), ('rgb_h', C.c_int32), ('no_store', C.c_int32),
         ('act_slope', C.c_float), ('res_mul', C.c_float), ('ps_r', C.c_int32),
+        ('ps_c', C.c_int32), ('demod_c', C.c_int32), ('use_tap_mask', C.c_int32), ('tap_mask', C.c_uint32 * 8),
     ]
 
 

@@ -68,6 +68,10 @@ struct alignas(64) ConvParams {
   float res_scale;
   float res_mul;  // weight of the residual term: v * res_scale + res * res_mul (legacy (v + res) * s: res_mul = s)
   int ps_r;       // pixel-shuffle factor of the store (0: off)
+  int ps_shift;   // log2(ps_c) when ps_c is a power of two, else -1
+  int ps_c;       // channels per sub-pixel phase: output column n belongs to phase n / ps_c, channel n % ps_c
+  int demod_c;    // demod / out_scale tables are indexed with channel n % demod_c (phases share one table row)
+  uint32_t tap_mask[8];  // per N-tile: taps to execute (bit t); tiles whose weight block for a tap is all zero skip it
   const float* out_scale;
   const float* rgb_w;
   float* rgb_part;
@@ -126,10 +130,9 @@ __device__ __forceinline__ EpiRow epi_setup(const ConvParams& p, int x, int y, i
   int xo = x * p.out_x_mul + p.out_x_off;
   int yo = y * p.out_y_mul + p.out_y_off;
   int nch = n0;  // channel offset of this N-tile in the output
-  if (p.ps_r) {  // nn.PixelShuffle fused into the store: N-tile t -> sub-pixel (t / r, t % r), channels restart at 0
-    const int t = n0 / p.block_n;
-    xo = x * p.ps_r + t % p.ps_r;
-    yo = y * p.ps_r + t / p.ps_r;
+  if (p.ps_r) {  // nn.PixelShuffle / transposed-conv phases fused into the store: base of sub-pixel (0, 0), channel 0;
+    xo = x * p.ps_r;  // the per-chunk phase offset is added by ps_offset()
+    yo = y * p.ps_r;
     nch = 0;
   }
   r.out_off = (long long)b * p.out_sb + (long long)yo * p.out_sy + (long long)xo * p.out_sx + p.out_c_off + nch;
@@ -160,6 +163,17 @@ __device__ __forceinline__ EpiRow epi_setup(const ConvParams& p, int x, int y, i
   return r;
 }
 
+// Output offset (elements) of GEMM column n = n0 + c0 relative to the sub-pixel (0,0) / channel 0 base when the store is
+// a pixel shuffle: phase t = n / ps_c -> sub-pixel (t / r, t % r), channel n % ps_c.  0 when ps_r == 0 (then the base
+// already contains n0 and the caller adds c0).
+__device__ __forceinline__ long long ps_offset(const ConvParams& p, int n0, int c0) {
+  const int n = n0 + c0;
+  const int t = (p.ps_shift >= 0) ? (n >> p.ps_shift) : (n / p.ps_c);  // ps_c is a power of two on the hot paths
+  const int ty = (p.ps_r == 2) ? (t >> 1) : (t / p.ps_r);
+  const int tx = t - ty * p.ps_r;
+  return (long long)ty * p.out_sy + (long long)tx * p.out_sx + (n - t * p.ps_c) - c0;
+}
+
 // Drains this thread's row of one 128 x block_n accumulator tile, 16 columns at a time (columns c_begin, c_begin +
 // c_step, ...: two warps share a TMEM lane quarter).  Per chunk the TMEM load is issued first, the operands that do not
 // depend on it (bias / demod from shared memory, residual from global) are fetched while it is in flight.
@@ -183,7 +197,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
                                               uint32_t full_phase, EpiRow r, bool valid, float gain, uint32_t s_bias,
                                               const float* g_bias, uint32_t s_demod, const float* g_demod,
-                                              uint32_t s_aux, int aux_stride, int c_begin, int c_step) {
+                                              uint32_t s_aux, int aux_stride, int c_begin, int c_step, int n0) {
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
@@ -298,7 +312,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
       }
       if (p.no_store) {
       } else if (p.out_fp32) {
-        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r.out_off + c0);
+        const long long pso = p.ps_r ? ps_offset(p, n0, c0) : 0;
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r.out_off + c0 + pso);
 #pragma unroll
         for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       } else {
@@ -308,7 +323,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
           __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
           pk[j] = *reinterpret_cast<uint32_t*>(&h);
         }
-        __half* op = reinterpret_cast<__half*>(p.out) + r.out_off + c0;
+        const long long pso = p.ps_r ? ps_offset(p, n0, c0) : 0;
+        __half* op = reinterpret_cast<__half*>(p.out) + r.out_off + c0 + pso;
         if (p.st256) {  // one full 32-byte sector per thread and instruction (no partial-sector writes in L2)
           asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]),
                        "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
@@ -359,9 +375,8 @@ __device__ __forceinline__ FastRow fast_setup(const ConvParams& p, int x, int y,
   int yo = y * p.out_y_mul + p.out_y_off;
   int nch = n0;
   if (p.ps_r) {  // see epi_setup
-    const int t = n0 / p.block_n;
-    xo = x * p.ps_r + t % p.ps_r;
-    yo = y * p.ps_r + t / p.ps_r;
+    xo = x * p.ps_r;
+    yo = y * p.ps_r;
     nch = 0;
   }
   r.out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_sb + (long long)yo * p.out_sy +
@@ -403,7 +418,8 @@ __device__ __forceinline__ FastRow fast_setup(const ConvParams& p, int x, int y,
 template <int F>
 __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
                                               uint32_t full_phase, const FastRow& r, bool valid, float gain,
-                                              uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride) {
+                                              uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride,
+                                              int n0) {
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
@@ -497,7 +513,8 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
         __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
         pk[j] = *reinterpret_cast<uint32_t*>(&h);
       }
-      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(r.out + c0), "r"(pk[0]), "r"(pk[1]),
+      const __half* op = r.out + c0 + (p.ps_r ? ps_offset(p, n0, c0) : 0);
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]),
                    "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
                    : "memory");
     }
@@ -520,10 +537,11 @@ __device__ __forceinline__ void epilogue_one(const ConvParams& p, uint32_t taddr
   if constexpr (EPI >= 0) {
     constexpr int F = epi_profile_flags(EPI);
     const FastRow fr = fast_setup<F>(p, x, y, b, n0, valid);
-    epilogue_fast<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride);
+    epilogue_fast<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride, n0);
   } else {
     const EpiRow r = epi_setup(p, x, y, b, n0, valid, gain);
-    epilogue_tile(p, taddr, full_bar, full_phase, r, valid, gain, s_bias, p.bias + n0, s_dm, g_dm, s_aux, aux_stride, 0, 16);
+    epilogue_tile(p, taddr, full_bar, full_phase, r, valid, gain, s_bias, p.bias + n0, s_dm, g_dm, s_aux, aux_stride, 0, 16,
+                  n0);
   }
 }
 
@@ -597,8 +615,9 @@ __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const K
     mbar_init(s.w_bar, 1);
     fence_barrier_init();
   }
-  if (p.cout <= kMaxBias)
-    for (int i = threadIdx.x; i < p.cout; i += kThreads)
+  // bias table: all output channels when they fit; all zeros (any kMaxBias-periodic window is valid) without a bias
+  if (p.cout <= kMaxBias || p.bias == nullptr)
+    for (int i = threadIdx.x; i < min(p.cout, kMaxBias); i += kThreads)
       s.bias[i] = (p.bias != nullptr) ? p.bias[i] * p.act_gain : 0.f;
   if (warp == 1) {
     tmem_alloc(s.tmem_slot, p.tmem_cols);
@@ -632,8 +651,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t tmem_base = kernel_prologue(p, s, p.stages, warp);
-  const int num_kb = p.num_taps * p.k_chunks;
-
   if (warp == 0) {
     // ---------------- TMA producer
     if (lane == 0) {
@@ -644,8 +661,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
+      const uint32_t mask = p.tap_mask[(tile % p.tiles_n) & 7];
       int kb = 0;
       for (int tap = 0; tap < p.num_taps; ++tap) {
+        if (!((mask >> tap) & 1u)) {
+          kb += p.k_chunks;
+          continue;
+        }
         const int view = p.tap_view[tap];
         const int cx = t.x0 + p.tap_dx[tap];
         const int cy = t.y0 + p.tap_dy[tap];
@@ -678,6 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       mbar_wait(&s.tmem_empty[acc], ((it >> p.acc_shift) & 1) ^ 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * p.block_n;
+      const int num_kb = __popc(p.tap_mask[(tile % p.tiles_n) & 7] & ((1u << p.num_taps) - 1u)) * p.k_chunks;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&s.full_bar[stage], phase);
         tc_fence_after();
@@ -708,6 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const int bi = row / (p.tile_w * p.tile_h);
     const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) * p.act_gain : 0.f;
     int it = group;
+    int last_key = -1;
     for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
       const int acc = it & (p.acc_stages - 1);
       const TileCoord t = decode_tile(p, tile);
@@ -718,27 +742,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const int tab_n = p.tile_b * p.block_n;
       if ((p.demod != nullptr && p.smem_demod) || p.smem_aux) {
         float* tab = s.demod + group * kDemodTable;
+        // the tables depend on (first image, N-tile) only: consecutive tiles of a group usually share both, so the
+        // staging (global loads + two group barriers, ~10k cycles when done per tile) is skipped when the key repeats
+        const int key = t.b0 * p.tiles_n + (tile % p.tiles_n);
+        if (key != last_key) {
+        last_key = key;
         epi_group_sync(group);  // previous tile of this group fully drained
-        for (int i = gt; i < tab_n; i += 128) {
-          const int bb = t.b0 + i / p.block_n;
-          const long long ch = (long long)bb * p.cout + t.n0 + (i % p.block_n);
-          const bool in = bb < p.m_b;
-          if (p.smem_demod) tab[i] = in ? __ldg(p.demod + ch) * p.act_gain : 0.f;
-          if (p.smem_aux) {
-            tab[tab_n + i] = (in && p.out_scale != nullptr) ? __ldg(p.out_scale + ch) : 1.f;
+        // thread gt owns columns gt, gt + 128 of every image row of the table (block_n <= 256): channel indices are
+        // computed once, the loads of the tile_b images are independent
+        for (int col = gt; col < p.block_n; col += 128) {
+          const int n = t.n0 + col;
+          const int nd = n % p.demod_c;
+#pragma unroll 4
+          for (int j = 0; j < p.tile_b; ++j) {
+            const int bb = t.b0 + j;
+            const bool in = bb < p.m_b;
+            const int i = j * p.block_n + col;
+            if (p.smem_demod) tab[i] = in ? __ldg(p.demod + (long long)bb * p.demod_c + nd) * p.act_gain : 0.f;
+            if (p.smem_aux) {
+              tab[tab_n + i] = (in && p.out_scale != nullptr) ? __ldg(p.out_scale + (long long)bb * p.cout + n) : 1.f;
 #pragma unroll
-            for (int o = 0; o < 3; ++o)
-              tab[(2 + o) * tab_n + i] =
-                  (in && p.rgb_w != nullptr) ? __ldg(p.rgb_w + ((long long)bb * 3 + o) * p.cout + t.n0 + (i % p.block_n)) : 0.f;
+              for (int o = 0; o < 3; ++o)
+                tab[(2 + o) * tab_n + i] =
+                    (in && p.rgb_w != nullptr) ? __ldg(p.rgb_w + ((long long)bb * 3 + o) * p.cout + n) : 0.f;
+            }
           }
         }
         epi_group_sync(group);
+        }
         if (p.smem_demod) s_dm = smem_u32(tab + bi * p.block_n);
         if (p.smem_aux) s_aux = smem_u32(tab + tab_n + bi * p.block_n);
       }
-      if (p.demod != nullptr && !p.smem_demod) g_dm = p.demod + (long long)b * p.cout + t.n0;
+      if (p.demod != nullptr && !p.smem_demod) g_dm = p.demod + (long long)b * p.demod_c + t.n0 % p.demod_c;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-      const uint32_t s_bias = (p.cout <= kMaxBias) ? smem_u32(s.bias + t.n0) : 0u;  // wide layers: global, act == 0
+      // wide layers (cout > kMaxBias): bias from global memory (act == 0), or the zero table when there is none
+      const uint32_t s_bias = (p.cout <= kMaxBias) ? smem_u32(s.bias + t.n0)
+                                                   : (p.bias == nullptr ? smem_u32(s.bias + t.n0 % kMaxBias) : 0u);
       epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, y, b, t.n0, valid, gain, s_bias, s_dm,
                         g_dm, s_aux, tab_n);
       tc_fence_before();

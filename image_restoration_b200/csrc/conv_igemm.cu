@@ -114,9 +114,17 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   B200IR_REQUIRE(d->res_mode == 0 || d->res != nullptr, "conv_igemm: res_mode set but res is NULL");
   B200IR_REQUIRE(d->noise == nullptr || d->noise_gain != nullptr, "conv_igemm: noise without noise_gain");
   B200IR_REQUIRE(d->act >= 0 && d->act <= 2, "conv_igemm: act=%d", d->act);
-  B200IR_REQUIRE(d->ps_r == 0 || ((d->ps_r == 2 || d->ps_r == 3) && d->block_n * d->ps_r * d->ps_r == d->cout &&
-                                  d->rgb_w == nullptr && d->res_mode == 0 && d->noise == nullptr),
-                 "conv_igemm: ps_r=%d needs block_n = cout / ps_r^2 and a plain epilogue", d->ps_r);
+  {
+    const int ps_c = d->ps_c ? d->ps_c : d->block_n;
+    B200IR_REQUIRE(d->ps_r == 0 || ((d->ps_r == 2 || d->ps_r == 3) && ps_c * d->ps_r * d->ps_r == d->cout &&
+                                    ps_c % 16 == 0 && d->rgb_w == nullptr && d->res_mode == 0 && d->noise == nullptr),
+                   "conv_igemm: ps_r=%d needs ps_c (or block_n) = cout / ps_r^2 and a plain epilogue", d->ps_r);
+    B200IR_REQUIRE(!d->use_tap_mask || d->cout / d->block_n <= 8, "conv_igemm: tap masks cover at most 8 N-tiles");
+    B200IR_REQUIRE(d->demod_c == 0 || d->demod_c == d->cout || d->demod_c % d->block_n == 0 ||
+                       d->tile_b * d->block_n <= kDemodTable,
+                   "conv_igemm: demod_c=%d needs block_n | demod_c or a tile whose demod table fits shared memory",
+                   d->demod_c);
+  }
   B200IR_REQUIRE(d->rgb_w == nullptr || (d->rgb_part != nullptr && d->rgb_w_px > 0 && d->rgb_h > 0),
                  "conv_igemm: rgb_w needs rgb_part and the plane extents");
   B200IR_REQUIRE(!d->no_store || d->rgb_w != nullptr, "conv_igemm: no_store without a fused ToRGB leaves no output");
@@ -164,7 +172,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   p.smem_aux = ((d->out_scale != nullptr || d->rgb_w != nullptr) && 5 * d->tile_b * d->block_n <= kDemodTable) ? 1 : 0;
   p.st256 = (!d->out_fp32 && d->out_c_off % 16 == 0 && d->out_stride_x % 16 == 0 && d->out_stride_y % 16 == 0 &&
              d->out_stride_b % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 31) == 0) ? 1 : 0;
-  B200IR_REQUIRE(d->cout <= kMaxBias || (d->bias != nullptr && !d->act),
+  B200IR_REQUIRE(d->cout <= kMaxBias || d->bias == nullptr || !d->act,
                  "conv_igemm: cout=%d > %d needs a bias vector and no activation", d->cout, kMaxBias);
   // accumulator ring depth: the epilogue latency of a tile is hidden behind the main loops of the next
   // (acc_stages - 1) tiles; small tiles (short main loops) need a deeper ring
@@ -200,6 +208,12 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   p.res_w = d->res_w; p.res_h = d->res_h; p.res_scale = d->res_scale;
   p.res_mul = d->res_mul != 0.f ? d->res_mul : d->res_scale;
   p.ps_r = d->ps_r;
+  p.ps_c = d->ps_c ? d->ps_c : d->block_n;
+  p.ps_shift = -1;
+  for (int sh = 0; sh < 16; ++sh)
+    if ((1 << sh) == p.ps_c) p.ps_shift = sh;
+  p.demod_c = d->demod_c ? d->demod_c : d->cout;
+  for (int t = 0; t < 8; ++t) p.tap_mask[t] = d->use_tap_mask ? d->tap_mask[t] : 0xffffffffu;
   {
     static int dbg = -1;
     if (dbg < 0) dbg = (getenv("B200IR_DBG_SKIP_EPI") != nullptr) ? 1 : 0;
@@ -208,7 +222,8 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   }
   // ---- specialised epilogue selection
   {
-    const bool fp16_fast = !d->out_fp32 && (d->no_store || p.st256) && d->cout <= kMaxBias && p.block_k >= 32;
+    const bool fp16_fast = !d->out_fp32 && (d->no_store || p.st256) && (d->cout <= kMaxBias || d->bias == nullptr) &&
+                           p.block_k >= 32;
     int flags = 0;
     bool ok = fp16_fast;
     if (d->demod != nullptr) { flags |= F_DEMOD; ok = ok && p.smem_demod; }

@@ -173,7 +173,17 @@ def _pack_kernels(kernels):
     return taps, np.asarray(sizes, dtype=np.int32), kmax
 
 
-def degrade_batch(gt_u8, kernels, lr_sizes, noise=None, bgr2rgb=True, return_blur=False):
+def pack_degradation(kernels, lr_sizes, dev):
+    """Device-side parameter block of a batch (blur taps, kernel sizes, low-resolution sizes): build once, reuse."""
+    taps, ksize, kmax = _pack_kernels(kernels)
+    lw = np.asarray([s[0] for s in lr_sizes], dtype=np.int32)
+    lh = np.asarray([s[1] for s in lr_sizes], dtype=np.int32)
+    assert lw.min() >= 1 and lh.min() >= 1
+    return dict(taps=torch.from_numpy(taps).to(dev), ks=torch.from_numpy(ksize).to(dev), lw=torch.from_numpy(lw).to(dev),
+                lh=torch.from_numpy(lh).to(dev), kmax=kmax, lr_wmax=int(lw.max()), lr_hmax=int(lh.max()), n=len(lw))
+
+
+def degrade_batch(gt_u8, kernels, lr_sizes, noise=None, bgr2rgb=True, return_blur=False, packed=None):
     """Runs the fused degradation on a batch.
 
     gt_u8    : uint8 CUDA tensor [B,H,W,3] (BGR as cv2 gives it) — what random_pyblur feeds pyblur.
@@ -186,16 +196,13 @@ def degrade_batch(gt_u8, kernels, lr_sizes, noise=None, bgr2rgb=True, return_blu
     gt_u8 = gt_u8.contiguous()
     B, H, W, _ = gt_u8.shape
     dev = gt_u8.device
-    taps, ksize, kmax = _pack_kernels(kernels)
-    lw = np.asarray([s[0] for s in lr_sizes], dtype=np.int32)
-    lh = np.asarray([s[1] for s in lr_sizes], dtype=np.int32)
-    assert len(lw) == B and lw.min() >= 1 and lh.min() >= 1
-    lr_wmax, lr_hmax = int(lw.max()), int(lh.max())
+    pk = packed if packed is not None else pack_degradation(kernels, lr_sizes, dev)
+    assert pk['n'] == B
+    kmax, lr_wmax, lr_hmax = pk['kmax'], pk['lr_wmax'], pk['lr_hmax']
     if noise is not None:
         assert noise.is_cuda and noise.dtype == torch.float32 and tuple(noise.shape) == (B, lr_hmax, lr_wmax, 3)
         noise = noise.contiguous()
-    t_taps = torch.from_numpy(taps).to(dev)
-    t_ks, t_lw, t_lh = (torch.from_numpy(a).to(dev) for a in (ksize, lw, lh))
+    t_taps, t_ks, t_lw, t_lh = pk['taps'], pk['ks'], pk['lw'], pk['lh']
     out = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
     blur_u8 = torch.empty(B, H, W, 3, device=dev, dtype=torch.uint8) if return_blur else None
     blur_f32 = torch.empty(B, H, W, 3, device=dev, dtype=torch.float32) if return_blur else None

@@ -93,6 +93,7 @@ class _Packed:
                 ws = (w * scale).to(F16)
                 d['w_phase'] = [torch.cat([ws[:, :, kh, kw] for kh, kw in ops.convt_phase_taps(py, px)], 1).contiguous()
                                 for py, px in ops.CONVT_PHASES]
+                d['w_merged'] = ops.convt_merged_weight(w, scale)
             else:
                 d['w'] = _pack_conv(w, scale)
             return d
@@ -331,15 +332,21 @@ class _Plan:
             cout = c1['cout']
             h2, w2 = 2 * h, 2 * w
             raw = z16(B, h2 + 2, w2 + 2, cout)
-            steps.rec(f'sg_xs{lvl}')
-            for pi, (py, px) in enumerate(ops.CONVT_PHASES):
-                if pi == 1:                        # the three smaller output phases run beside the 4-tap phase
-                    steps.lane = 3
-                    steps.wait(f'sg_xs{lvl}')
-                steps.append(ops.convt_s2_phase(xs, c1['w_phase'][pi], py, px, raw, demod=d_conv[2 * lvl]))
-            steps.rec(f'sg_ph{lvl}')
-            steps.lane = 1
-            steps.wait(f'sg_ph{lvl}')
+            # merged form: N = 256 MMAs for the 64/128-channel levels and one launch for the small ones; the 512-channel
+            # levels with enough tiles run faster as four exact-work phase GEMMs (tools/time_convt.py)
+            if eng.convt_merged and (cout <= 128 or B * h * w < 40000):
+                # one implicit GEMM for the whole stride-2 transposed conv (phases = column blocks)
+                steps.append(ops.convt_s2_merged(xs, c1['w_merged'], raw, d_conv[2 * lvl]))
+            else:
+                steps.rec(f'sg_xs{lvl}')
+                for pi, (py, px) in enumerate(ops.CONVT_PHASES):
+                    if pi == 1:                    # the three smaller output phases run beside the 4-tap phase
+                        steps.lane = 3
+                        steps.wait(f'sg_xs{lvl}')
+                    steps.append(ops.convt_s2_phase(xs, c1['w_phase'][pi], py, px, raw, demod=d_conv[2 * lvl]))
+                steps.rec(f'sg_ph{lvl}')
+                steps.lane = 1
+                steps.wait(f'sg_ph{lvl}')
             n1 = e32(B, 1, h2, w2)
             n2 = e32(B, 1, h2, w2)
             self.noise[2 * lvl + 1], self.noise[2 * lvl + 2] = n1, n2
@@ -428,6 +435,8 @@ class OcrEngine:
             self.packed = _Packed(net)
         self.plans = {}
         self.use_graphs = True
+        import os
+        self.convt_merged = os.environ.get('B200IR_CONVT_MERGED', '1') != '0'
 
     def _signature(self):
         ps = list(self.net.parameters()) + list(self.net.buffers())

@@ -29,12 +29,15 @@ def _req(t, dtype, name):
         raise ValueError(f'{name}: expected contiguous CUDA {dtype}, got {t.dtype} on {t.device}')
 
 
-def pick_tile(m_w, m_h, m_b):
-    """Choose (tile_w, tile_h, tile_b), powers of two with product 128, minimising the number of tiles."""
+def pick_tile(m_w, m_h, m_b, min_w=1, max_b=128):
+    """Choose (tile_w, tile_h, tile_b), powers of two with product 128, minimising the number of tiles (optionally
+    with a minimum row-segment length, for DRAM-friendly TMA boxes, and a cap on images per tile)."""
     best = None
     for lw in range(8):
         for lh in range(8 - lw):
             tw, th, tb = 1 << lw, 1 << lh, 1 << (7 - lw - lh)
+            if tw < min(min_w, m_w) or tb > max_b:
+                continue
             tiles = -(-m_w // tw) * -(-m_h // th) * -(-m_b // tb)
             key = (tiles, -tw, -th)
             if best is None or key < best[0]:
@@ -62,7 +65,7 @@ class ConvOp:
                  out_mul_off=(1, 0, 1, 0), bias=None, demod=None, noise=None, noise_gain=None, noise_strides=(0, 0),
                  act=False, res=None, res_mode=0, res_strides=(0, 0, 0), res_wh=(0, 0), res_scale=1.0, block_n=None,
                  tile=None, max_ctas=0, row_mode=0, out_scale=None, rgb_w=None, rgb_part=None, rgb_hw=(0, 0),
-                 no_store=False, act_slope=None, res_mul=0.0, ps_r=0):
+                 no_store=False, act_slope=None, res_mul=0.0, ps_r=0, ps_c=0, demod_c=0, tap_mask=None):
         d = ConvDesc()
         assert 1 <= len(views) <= _lib.MAX_VIEWS and 1 <= len(taps) <= _lib.MAX_TAPS
         for i, v in enumerate(views):
@@ -92,6 +95,12 @@ class ConvOp:
         d.act_slope = float(act_slope) if act_slope is not None else 0.0
         d.res_mul = res_mul
         d.ps_r = ps_r
+        d.ps_c, d.demod_c = ps_c, demod_c
+        if tap_mask is not None:
+            assert len(tap_mask) <= 8
+            d.use_tap_mask = 1
+            for i, m in enumerate(tap_mask):
+                d.tap_mask[i] = m
         d.res_mode = res_mode
         if res is not None:
             _req(res, torch.float16, 'res')
@@ -200,6 +209,48 @@ def convt_s2_phase(x, weight_phase, py, px, raw, **kw):
     m_w = w + 1 if px == 0 else w
     return ConvOp([nhwc_view(x)], weight_phase, cin, cout, taps, (m_w, m_h, b), raw,
                   (cout, rw * cout, rh * rw * cout), out_mul_off=(2, px, 2, py), **kw)
+
+
+def convt_merged_weight(w, scale):
+    """(cout, cin, 3, 3) fp32 -> fp16 [4*cout][4*cin] for convt_s2_merged: row block = output phase (py, px), column
+    block = input tap (ty, tx) (input offset (-ty, -tx)); phase (py, px) uses tap (ty, tx) through kernel element
+    (py + 2 ty, px + 2 tx) when that index is <= 2, zero otherwise."""
+    cout, cin = w.shape[:2]
+    big = w.new_zeros(4, cout, 4, cin)
+    for py in range(2):
+        for px in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    kh, kw = py + 2 * ty, px + 2 * tx
+                    if kh <= 2 and kw <= 2:
+                        big[py * 2 + px, :, ty * 2 + tx, :] = w[:, :, kh, kw] * scale
+    return big.reshape(4 * cout, 4 * cin).contiguous().to(torch.float16)
+
+
+def convt_s2_merged(x, w_big, raw, demod):
+    """conv_transpose2d(stride 2, padding 0, 3x3) (stylegan2_ocr_arch.py:265) as ONE implicit GEMM: the four output
+    phases are column blocks of N = 4*cout (N = 256 MMAs even for cout = 64), the four input taps (i - ty, j - tx) are
+    K blocks, every N-tile skips the taps its phases do not use, and the epilogue stores column block (py, px) to
+    raw[b, 2i + py, 2j + px, :].  M runs over (h+1) x (w+1); the surplus row / column of the odd phases lands in the
+    padding row / column of `raw` that nothing reads."""
+    b, h, w, cin = x.shape
+    _, rh, rw, cout = raw.shape
+    assert rh >= 2 * h + 2 and rw >= 2 * w + 2 and w_big.shape == (4 * cout, 4 * cin)
+    taps = [(0, -tx, -ty) for ty in range(2) for tx in range(2)]
+    bn = min(256, 4 * cout)
+    masks = []
+    for j in range(4 * cout // bn):
+        m = 0
+        for ph in range(j * bn // cout, ((j + 1) * bn - 1) // cout + 1):
+            py, px = ph // 2, ph % 2
+            for ty in range(2):
+                for tx in range(2):
+                    if py + 2 * ty <= 2 and px + 2 * tx <= 2:
+                        m |= 1 << (ty * 2 + tx)
+        masks.append(m)
+    tile = pick_tile(w + 1, h + 1, b, min_w=8, max_b=max(1, 2560 // bn))
+    return ConvOp([nhwc_view(x)], w_big, cin, 4 * cout, taps, (w + 1, h + 1, b), raw, (cout, rw * cout, rh * rw * cout),
+                  demod=demod, block_n=bn, tile=tile, ps_r=2, ps_c=cout, demod_c=cout, tap_mask=masks)
 
 
 def linear_as_conv(x2d, weight, out, **kw):

@@ -125,6 +125,12 @@ typedef struct {
   float act_slope;
   float res_mul;
   int32_t ps_r;
+  /* Sub-pixel phases as GEMM columns (the stride-2 transposed conv of an upsampling StyleConv as ONE conv:
+   * column n belongs to phase n / ps_c (0: ps_c = block_n, the plain pixel shuffle above) and channel n % ps_c;
+   * demod_c != 0: the demod table has demod_c channels per image and is indexed with n % demod_c;
+   * use_tap_mask: N-tile t executes only the taps in tap_mask[t] (its weight block for the others is all zero). */
+  int32_t ps_c, demod_c, use_tap_mask;
+  uint32_t tap_mask[8];
 } b200ir_conv_desc;
 
 int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);

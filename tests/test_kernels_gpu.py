@@ -456,3 +456,23 @@ def test_row_sliding_conv_forced(B, H, W, cin, cout, kind):
     check_close(nchw32(out), ref, what=f'row conv {cin}->{cout} @{H}x{W} B{B} {kind}')
     if kind == 'modrgb':
         check_close(part.sum(0), torch.einsum('bchw,boc->bohw', yy, wm), tol=2e-3, what='row conv fused rgb')
+
+
+@pytest.mark.parametrize('B,h,w,cin,cout', [(2, 4, 12, 512, 512), (3, 32, 96, 512, 128), (2, 64, 192, 128, 64),
+                                            (1, 5, 7, 64, 64), (9, 8, 24, 512, 512)])
+def test_transposed_conv_merged_single_gemm(B, h, w, cin, cout):
+    """conv_transpose2d(stride 2) as ONE implicit GEMM (phases = column blocks, per-N-tile tap masks, phase-scatter
+    store) == F.conv_transpose2d * demod on the (2h+1) x (2w+1) valid region; the padding row / column may hold anything."""
+    ops = _ops()
+    torch.manual_seed(15)
+    x = torch.randn(B, cin, h, w, device=DEV)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    demod = torch.rand(B, cout, device=DEV) + 0.5
+    xh = nhwc16(x)
+    w_big = ops.convt_merged_weight(wt, 1.0)
+    raw = torch.full((B, 2 * h + 2, 2 * w + 2, cout), 3.0, device=DEV, dtype=torch.float16)
+    op = ops.convt_s2_merged(xh, w_big, raw, demod)
+    op()
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(nchw32(xh), wt.half().float().transpose(0, 1), stride=2) * demod[:, :, None, None]
+    check_close(nchw32(raw)[:, :, :2 * h + 1, :2 * w + 1], ref, what=f'merged convT {cin}->{cout} {h}x{w}')
