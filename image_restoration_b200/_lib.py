@@ -76,11 +76,12 @@ SIGNATURES = {
     'b200ir_mod_linear_multi': [_P, _I, _I, _P, _I, _I, _F, _I, _P],
     'b200ir_demod_multi': [_P, _I, _I, _I, _P],
     'b200ir_nhwc_to_nchw_f32': [_P, _P, _I, _I, _I, _P],
-    'b200ir_nchw_to_nhwc_pad': [_P, _P, _I, _I, _I, _I, _I, _P, _F, _P],
+    'b200ir_nchw_to_nhwc_pad': [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P],
+    'b200ir_nearest_up2': [_P, _P, _I, _I, _I, _I, _P],
     'b200ir_sr_output': [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P],
     'b200ir_channel_mean': [_P, _P, _I, _I, _I, _P],
     'b200ir_ca_mlp': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
-    'b200ir_ca_scale_add': [_P, _P, _P, _P, _F, _I, _I, _I, _P],
+    'b200ir_ca_scale_add': [_P, _P, _P, _P, _F, _I, _I, _I, _L, _L, _P],
     'b200ir_degrade': [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64}

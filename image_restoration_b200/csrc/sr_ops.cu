@@ -10,29 +10,56 @@ static constexpr int kSrThreads = 256;
 static inline int sr_grid(long long n) { return (int)((n + kSrThreads - 1) / kSrThreads); }
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
-// x fp32 NCHW [B][C][H][W] -> NHWC fp16 [B][H][W][Cpad]: (x - sub[c]) * mul for c < C, 0 for the padding channels
-__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int C, int HW,
-                                        int Cpad, const float* __restrict__ sub, float mul) {
+// x fp32 NCHW [B][C][H*s][W*s] -> NHWC fp16 [B][H][W][Cpad]: (x - sub[c]) * mul, zero padding channels.  s > 1 fuses
+// arch_util.pixel_unshuffle (:185-201): output channel c*s*s + dy*s + dx reads x[b][c][y*s + dy][x*s + dx].
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int C, int H, int W,
+                                        int Cpad, const float* __restrict__ sub, float mul, int s) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (pixel, 8-channel group)
   const int cg = Cpad >> 3;
+  const int HW = H * W;
   if (idx >= (long long)B * HW * cg) return;
   const int g = (int)(idx % cg);
   const long long pix = idx / cg;
   const int b = (int)(pix / HW);
   const int p = (int)(pix % HW);
+  const int yy = p / W, xx = p % W;
+  const int ss = s * s;
   __half2 h[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float v[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int c = g * 8 + 2 * j + e;
+      const int co = g * 8 + 2 * j + e;
       v[e] = 0.f;
-      if (c < C) v[e] = (__ldg(x + ((long long)b * C + c) * HW + p) - (sub ? __ldg(sub + c) : 0.f)) * mul;
+      if (co < C * ss) {
+        const int c = co / ss, dy = (co % ss) / s, dx = co % s;
+        const long long src = (((long long)b * C + c) * (H * s) + (yy * s + dy)) * (W * s) + xx * s + dx;
+        v[e] = (__ldg(x + src) - (sub ? __ldg(sub + c) : 0.f)) * mul;
+      }
     }
     h[j] = __floats2half2_rn(v[0], v[1]);
   }
   *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<uint4*>(h);
+}
+
+// F.interpolate(scale_factor=2, mode='nearest') on NHWC fp16 (rrdbnet_arch.py:118-119): out[b][y][x] = in[b][y/2][x/2]
+__global__ void nearest_up2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int h, int w, int C) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (input pixel, 8 channels)
+  const int cg = C >> 3;
+  if (idx >= (long long)B * h * w * cg) return;
+  const int g = (int)(idx % cg);
+  long long r = idx / cg;
+  const int xx = (int)(r % w);
+  r /= w;
+  const int yy = (int)(r % h);
+  const int b = (int)(r / h);
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(in) + idx);
+  __half* op = out + (((long long)b * 2 * h + 2 * yy) * (2 * w) + 2 * xx) * C + g * 8;
+  *reinterpret_cast<uint4*>(op) = q;
+  *reinterpret_cast<uint4*>(op + C) = q;
+  *reinterpret_cast<uint4*>(op + (long long)2 * w * C) = q;
+  *reinterpret_cast<uint4*>(op + (long long)2 * w * C + C) = q;
 }
 
 // F.interpolate(scale_factor=r, mode='bilinear', align_corners=False) sample of a [h][w] plane at output (y, x)
@@ -117,28 +144,31 @@ __global__ void ca_mlp_kernel(const float* __restrict__ mean, const float* __res
   }
 }
 
-// RCAB tail (rcan_arch.py:43-45): out = x * att[b][c] * res_scale + identity   (fp16 NHWC)
+// RCAB tail (rcan_arch.py:43-45): out = x * att[b][c] * res_scale + identity (fp16 NHWC; att == NULL: 1, which is the
+// RRDB merge out * 0.2 + x of rrdbnet_arch.py:59-63).  identity / out may be channel slices of wider NHWC buffers
+// (pixel strides id_stride / out_stride in elements); x is dense.
 __global__ void ca_scale_add_kernel(const __half* __restrict__ x, const float* __restrict__ att,
                                     const __half* __restrict__ identity, __half* __restrict__ out, float res_scale, int B,
-                                    int HW, int C) {
+                                    int HW, int C, long long id_stride, long long out_stride) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = C >> 3;
   if (idx >= (long long)B * HW * cg) return;
   const int g = (int)(idx % cg);
-  const int b = (int)(idx / ((long long)HW * cg));
+  const long long pix = idx / cg;
+  const int b = (int)(pix / HW);
   const uint4 qx = __ldg(reinterpret_cast<const uint4*>(x) + idx);
-  const uint4 qi = __ldg(reinterpret_cast<const uint4*>(identity) + idx);
+  const uint4 qi = __ldg(reinterpret_cast<const uint4*>(identity + pix * id_stride + g * 8));
   const __half2* hx = reinterpret_cast<const __half2*>(&qx);
   const __half2* hi = reinterpret_cast<const __half2*>(&qi);
   __half2 ho[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 fx = __half22float2(hx[j]), fi = __half22float2(hi[j]);
-    const float a0 = __ldg(att + (long long)b * C + g * 8 + 2 * j) * res_scale;
-    const float a1 = __ldg(att + (long long)b * C + g * 8 + 2 * j + 1) * res_scale;
+    const float a0 = (att ? __ldg(att + (long long)b * C + g * 8 + 2 * j) : 1.f) * res_scale;
+    const float a1 = (att ? __ldg(att + (long long)b * C + g * 8 + 2 * j + 1) : 1.f) * res_scale;
     ho[j] = __floats2half2_rn(fx.x * a0 + fi.x, fx.y * a1 + fi.y);
   }
-  reinterpret_cast<uint4*>(out)[idx] = *reinterpret_cast<uint4*>(ho);
+  *reinterpret_cast<uint4*>(out + pix * out_stride + g * 8) = *reinterpret_cast<uint4*>(ho);
 }
 
 }  // namespace b200ir
@@ -146,11 +176,19 @@ __global__ void ca_scale_add_kernel(const __half* __restrict__ x, const float* _
 using namespace b200ir;
 
 extern "C" int b200ir_nchw_to_nhwc_pad(const float* x, void* out, int B, int C, int H, int W, int Cpad, const float* sub,
-                                       float mul, void* stream) {
-  B200IR_REQUIRE(x && out && C > 0 && Cpad >= C && Cpad % 8 == 0, "nchw_to_nhwc_pad: bad arguments");
+                                       float mul, int unshuffle, void* stream) {
+  const int s = unshuffle > 1 ? unshuffle : 1;
+  B200IR_REQUIRE(x && out && C > 0 && Cpad >= C * s * s && Cpad % 8 == 0, "nchw_to_nhwc_pad: bad arguments");
   const long long n = (long long)B * H * W * (Cpad / 8);
-  nchw_to_nhwc_pad_kernel<<<sr_grid(n), kSrThreads, 0, STREAM>>>(x, (__half*)out, B, C, H * W, Cpad, sub, mul);
+  nchw_to_nhwc_pad_kernel<<<sr_grid(n), kSrThreads, 0, STREAM>>>(x, (__half*)out, B, C, H, W, Cpad, sub, mul, s);
   return check_launch("nchw_to_nhwc_pad");
+}
+
+extern "C" int b200ir_nearest_up2(const void* in, void* out, int B, int h, int w, int C, void* stream) {
+  B200IR_REQUIRE(in && out && C % 8 == 0, "nearest_up2: bad arguments");
+  const long long n = (long long)B * h * w * (C / 8);
+  nearest_up2_kernel<<<sr_grid(n), kSrThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, h, w, C);
+  return check_launch("nearest_up2");
 }
 
 extern "C" int b200ir_sr_output(const float* y, float* out, int B, int C, int H, int W, int Cpad, float mul,
@@ -176,10 +214,12 @@ extern "C" int b200ir_ca_mlp(const float* mean, const float* w1, const float* b1
 }
 
 extern "C" int b200ir_ca_scale_add(const void* x, const float* att, const void* identity, void* out, float res_scale,
-                                   int B, int HW, int C, void* stream) {
-  B200IR_REQUIRE(x && att && identity && out && C % 8 == 0, "ca_scale_add: bad arguments");
+                                   int B, int HW, int C, int64_t id_stride, int64_t out_stride, void* stream) {
+  B200IR_REQUIRE(x && identity && out && C % 8 == 0 && id_stride % 8 == 0 && out_stride % 8 == 0 && id_stride >= C &&
+                     out_stride >= C,
+                 "ca_scale_add: bad arguments");
   const long long n = (long long)B * HW * (C / 8);
   ca_scale_add_kernel<<<sr_grid(n), kSrThreads, 0, STREAM>>>((const __half*)x, att, (const __half*)identity, (__half*)out,
-                                                            res_scale, B, HW, C);
+                                                            res_scale, B, HW, C, id_stride, out_stride);
   return check_launch("ca_scale_add");
 }

@@ -385,10 +385,15 @@ class DemodMulti:
 
 
 # ------------------------------------------------------------------------------------------ SR-network stages
-def nchw_to_nhwc_pad(x, out, sub=None, mul=1.0):
-    b, c, h, w = x.shape
-    check(_lib.lib().b200ir_nchw_to_nhwc_pad(_ptr(x), _ptr(out), b, c, h, w, out.shape[3], _ptr(sub), mul, _stream()),
-          'nchw_to_nhwc_pad')
+def nchw_to_nhwc_pad(x, out, sub=None, mul=1.0, unshuffle=1):
+    b, c = x.shape[:2]
+    check(_lib.lib().b200ir_nchw_to_nhwc_pad(_ptr(x), _ptr(out), b, c, out.shape[1], out.shape[2], out.shape[3], _ptr(sub),
+                                             mul, unshuffle, _stream()), 'nchw_to_nhwc_pad')
+
+
+def nearest_up2(x, out):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_nearest_up2(_ptr(x), _ptr(out), b, h, w, c, _stream()), 'nearest_up2')
 
 
 def sr_output(y, out, mul=1.0, add=None, base=None, scale=1):
@@ -408,10 +413,12 @@ def ca_mlp(mean, w1, b1, w2, b2, att):
                                    _stream()), 'ca_mlp')
 
 
-def ca_scale_add(x, att, identity, out, res_scale=1.0):
+def ca_scale_add(x, att, identity, out, res_scale=1.0, id_stride=None, out_stride=None):
+    """out = x * att * res_scale + identity; identity / out may be the leading channels of wider NHWC buffers (pass the
+    tensors and their pixel strides)."""
     b, h, w, c = x.shape
     check(_lib.lib().b200ir_ca_scale_add(_ptr(x), _ptr(att), _ptr(identity), _ptr(out), res_scale, b, h * w, c,
-                                         _stream()), 'ca_scale_add')
+                                         id_stride or c, out_stride or c, _stream()), 'ca_scale_add')
 
 
 def nhwc_to_nchw_f32(x, out):

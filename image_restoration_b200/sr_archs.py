@@ -1,6 +1,7 @@
-"""Drop-in MSRResNet / EDSR / RCAN for B200: the networks the reference's `options/*.yml` select from ARCH_REGISTRY.
+"""Drop-in MSRResNet / EDSR / RCAN / RRDBNet for B200: the networks the reference's `options/*.yml` select from ARCH_REGISTRY.
 
-Mirrors `basicsr/archs/srresnet_arch.py:8-68` (MSRResNet), `edsr_arch.py:8-72` (EDSR), `rcan_arch.py:8-135` (RCAN) and
+Mirrors `basicsr/archs/srresnet_arch.py:8-68` (MSRResNet), `edsr_arch.py:8-72` (EDSR), `rcan_arch.py:8-135` (RCAN),
+`rrdbnet_arch.py:9-123` (RRDBNet: dense concatenation = channel-offset outputs into one NHWC buffer, nearest x2, pixel_unshuffle) and
 the blocks of `arch_util.py` they use (`ResidualBlockNoBN :66-93`, `Upsample :96-109`, `default_init_weights :12-43`):
 same constructor keywords, same parameter names / shapes (checkpoints load unchanged), same `forward(x)`.
 The modules only hold parameters; every arithmetic op runs in libb200ir.so:
@@ -168,6 +169,45 @@ class RCAN(_SrBase):
         self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
 
 
+class _ResidualDenseBlock(nn.Module):
+    """Parameters of rrdbnet_arch.ResidualDenseBlock (:9-39)."""
+
+    def __init__(self, num_feat=64, num_grow_ch=32):
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_feat, num_grow_ch, 3, 1, 1)
+        self.conv2 = nn.Conv2d(num_feat + num_grow_ch, num_grow_ch, 3, 1, 1)
+        self.conv3 = nn.Conv2d(num_feat + 2 * num_grow_ch, num_grow_ch, 3, 1, 1)
+        self.conv4 = nn.Conv2d(num_feat + 3 * num_grow_ch, num_grow_ch, 3, 1, 1)
+        self.conv5 = nn.Conv2d(num_feat + 4 * num_grow_ch, num_feat, 3, 1, 1)
+        _default_init_weights([self.conv1, self.conv2, self.conv3, self.conv4, self.conv5], 0.1)
+
+
+class _RRDB(nn.Module):
+    def __init__(self, num_feat, num_grow_ch=32):
+        super().__init__()
+        self.rdb1 = _ResidualDenseBlock(num_feat, num_grow_ch)
+        self.rdb2 = _ResidualDenseBlock(num_feat, num_grow_ch)
+        self.rdb3 = _ResidualDenseBlock(num_feat, num_grow_ch)
+
+
+class RRDBNet(_SrBase):
+    """rrdbnet_arch.RRDBNet (:66-123)."""
+
+    def __init__(self, num_in_ch, num_out_ch, scale=4, num_feat=64, num_block=23, num_grow_ch=32):
+        super().__init__()
+        self.scale, self.num_feat, self.num_grow_ch = scale, num_feat, num_grow_ch
+        self.num_in_ch, self.num_out_ch = num_in_ch, num_out_ch           # of the image (before pixel_unshuffle)
+        self.upscale = scale
+        cin = num_in_ch * (4 if scale == 2 else (16 if scale == 1 else 1))
+        self.conv_first = nn.Conv2d(cin, num_feat, 3, 1, 1)
+        self.body = nn.Sequential(*[_RRDB(num_feat, num_grow_ch=num_grow_ch) for _ in range(num_block)])
+        self.conv_body = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_up1 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_up2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_hr = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
+
+
 # ------------------------------------------------------------------------------------------ engine
 def _pack(conv, cin_pad=None, cout_pad=None, ps_r=0):
     """nn.Conv2d 3x3 -> (fp16 [cout][9*cin] tap-major, fp32 bias); optional zero padding of cin / cout; for a conv
@@ -229,9 +269,12 @@ class _SrPlan:
         x16 = e16(B, H, W, cin_pad)
         sub = eng.mean_dev if hasattr(net, 'img_range') else None
         mul = float(net.img_range) if hasattr(net, 'img_range') else 1.0
-        steps.append(lambda: ops.nchw_to_nhwc_pad(self.x_in, x16, sub, mul))
+        if not isinstance(net, RRDBNet):
+            steps.append(lambda: ops.nchw_to_nhwc_pad(self.x_in, x16, sub, mul))
 
-        if isinstance(net, MSRResNet):
+        if isinstance(net, RRDBNet):
+            self._build_rrdb(eng, B, H, W, conv, e16, e32)
+        elif isinstance(net, MSRResNet):
             # srresnet_arch.py:55-68
             feat = conv(x16, net.conv_first, slope=0.1, cin_pad=cin_pad)
             out = feat
@@ -284,6 +327,74 @@ class _SrPlan:
             steps.append(lambda: ops.sr_output(y, self.out, 1.0 / float(net.img_range), eng.mean_dev, None, 1))
         self.graph = None
 
+    def _build_rrdb(self, eng, B, H, W, conv, e16, e32):
+        """rrdbnet_arch.RRDBNet.forward (:105-123).  Every ResidualDenseBlock works in one NHWC buffer of
+        num_feat + 4 * grow channels: its input occupies the first num_feat channels, conv_k writes its grow channels
+        behind them (torch.cat is a channel offset), conv5 merges x5 * 0.2 + x into the next block's buffer."""
+        net, steps = eng.net, self.steps
+        nf, g = net.num_feat, net.num_grow_ch
+        if nf % 32 or g % 16:
+            raise NotImplementedError('RRDBNet: num_feat % 32 == 0 and num_grow_ch % 16 == 0 are supported')
+        s = 2 if net.scale == 2 else (4 if net.scale == 1 else 1)
+        if H % s or W % s:
+            raise ValueError(f'RRDBNet(scale={net.scale}) needs input extents divisible by {s}')
+        h, w = H // s, W // s
+        cin = net.num_in_ch * s * s
+        cin_pad = -(-cin // 16) * 16
+        x0 = e16(B, h, w, cin_pad)
+        steps.append(lambda: ops.nchw_to_nhwc_pad(self.x_in, x0, None, 1.0, s))
+        ctot = nf + 4 * g
+        dense = [e16(B, h, w, ctot) for _ in range(4)]      # ring: an RRDB keeps its first buffer until its final merge
+
+        def dconv(src, cin_used, mod, dst, c_off, **kw):
+            """conv over the first cin_used channels of dense buffer `src` -> channels [c_off, c_off+cout) of `dst`."""
+            wt, bias = eng.packed(mod, None, None, 0)
+            cout = wt.shape[0]
+            v = ops.View(src.data_ptr(), cin_used, w, h, B, src.shape[3], w * src.shape[3], h * w * src.shape[3])
+            oc = dst.shape[3]
+            steps.append(ops.ConvOp([v], wt, cin_used, cout, ops.taps_3x3(), (w, h, B), dst, (oc, w * oc, h * w * oc),
+                                    bias=bias, out_c_off=c_off, **kw))
+
+        feat = e16(B, h, w, nf)
+        conv(x0, net.conv_first, feat, cin_pad=cin_pad)
+        # feat is kept for the trunk residual; the first dense buffer starts as a copy of it (feat * 0 + feat, strided)
+        steps.append(lambda: ops.ca_scale_add(feat, None, feat, dense[0], 0.0, nf, ctot))
+        k = 0
+        for rrdb in net.body:
+            first = dense[k % len(dense)]
+            cur = first
+            for j, rdb in enumerate((rrdb.rdb1, rrdb.rdb2, rrdb.rdb3)):
+                nxt = dense[(k + 1) % len(dense)]
+                for i, c in enumerate((rdb.conv1, rdb.conv2, rdb.conv3, rdb.conv4)):
+                    dconv(cur, nf + i * g, c, cur, nf + i * g, act_slope=0.2)
+                res_kw = dict(res=cur, res_mode=1, res_strides=(ctot, w * ctot, h * w * ctot), res_wh=(w, h),
+                              res_scale=0.2, res_mul=1.0)
+                if j < 2:
+                    dconv(cur, ctot, rdb.conv5, nxt, 0, **res_kw)                      # x5 * 0.2 + x -> next block's input
+                else:
+                    t = e16(B, h, w, nf)
+                    dconv(cur, ctot, rdb.conv5, t, 0, **res_kw)
+                    steps.append(lambda a=t, idn=first, o=nxt: ops.ca_scale_add(a, None, idn, o, 0.2, ctot, ctot))  # RRDB: out*0.2 + x
+                cur = nxt
+                k += 1
+        body_out = cur                                                                   # first nf channels
+        trunk = e16(B, h, w, nf)
+        wt, bias = eng.packed(net.conv_body, None, None, 0)
+        v = ops.View(body_out.data_ptr(), nf, w, h, B, ctot, w * ctot, h * w * ctot)
+        steps.append(ops.ConvOp([v], wt, nf, nf, ops.taps_3x3(), (w, h, B), trunk, (nf, w * nf, h * w * nf), bias=bias,
+                                res=feat, res_mode=1, res_strides=(nf, w * nf, h * w * nf), res_wh=(w, h), res_scale=1.0,
+                                res_mul=1.0))                                            # feat + conv_body(body(feat))
+        up = trunk
+        for c in (net.conv_up1, net.conv_up2):
+            bb, hh, ww, _ = up.shape
+            big = e16(bb, 2 * hh, 2 * ww, nf)
+            steps.append(lambda a=up, o=big: ops.nearest_up2(a, o))
+            up = conv(big, c, slope=0.2)
+        hr = conv(up, net.conv_hr, slope=0.2)
+        y = conv(hr, net.conv_last, cout_pad=16, out_fp32=True)
+        self.out = e32(B, net.num_out_ch, y.shape[1], y.shape[2])
+        steps.append(lambda: ops.sr_output(y, self.out, 1.0, None, None, 1))
+
     def launch(self):
         for st in self.steps:
             st()
@@ -297,7 +408,7 @@ class SrEngine:
         from . import _lib
         with torch.cuda.device(self.dev):
             _lib.check(_lib.lib().b200ir_device_check(), 'device check')
-        if net.num_in_ch > 16 or net.num_out_ch > 16 or net.num_feat % 16:
+        if (net.num_in_ch > 16 and not isinstance(net, RRDBNet)) or net.num_out_ch > 16 or net.num_feat % 16:
             raise NotImplementedError('num_in_ch / num_out_ch <= 16 and num_feat % 16 == 0 are supported')
         self.net = net
         self._sig = self._signature()
@@ -350,7 +461,7 @@ def register_sr_archs(registry=None, suffix='_B200', override=False):
     or replaces the reference entries when `override` (Registry asserts on duplicates, registry.py:38-41)."""
     registry = registry if registry is not None else ARCH_REGISTRY
     out = {}
-    for cls in (MSRResNet, EDSR, RCAN):
+    for cls in (MSRResNet, EDSR, RCAN, RRDBNet):
         if override:
             registry._obj_map[cls.__name__] = cls
             out[cls.__name__] = cls
@@ -364,6 +475,6 @@ def register_sr_archs(registry=None, suffix='_B200', override=False):
 
 register_sr_archs(ARCH_REGISTRY)
 if not USING_BASICSR_REGISTRY:
-    for _cls in (MSRResNet, EDSR, RCAN):
+    for _cls in (MSRResNet, EDSR, RCAN, RRDBNet):
         if _cls.__name__ not in ARCH_REGISTRY:
             ARCH_REGISTRY.register(_cls)

@@ -242,10 +242,13 @@ int b200ir_nhwc_to_nchw_f32(const void* in, float* out, int B, int P, int C, voi
  * b200ir_conv_igemm (act == 2, res_mul, ps_r); these are the memory-bound stages around them.
  */
 
-/* fp32 NCHW [B][C][H][W] -> NHWC fp16 [B][H][W][Cpad], (x - sub[c]) * mul, zero padding channels (edsr_arch.py:62:
- * (x - mean) * img_range; sub may be NULL). */
+/* fp32 NCHW [B][C][H*s][W*s] -> NHWC fp16 [B][H][W][Cpad], (x - sub[c]) * mul, zero padding channels (edsr_arch.py:62:
+ * (x - mean) * img_range; sub may be NULL).  unshuffle = s > 1 fuses pixel_unshuffle (arch_util.py:185-201, RRDBNet
+ * scale 2 / 1): output channel c*s*s + dy*s + dx <- x[b][c][y*s+dy][x*s+dx]; H, W are the OUTPUT extents. */
 int b200ir_nchw_to_nhwc_pad(const float* x, void* out, int B, int C, int H, int W, int Cpad, const float* sub, float mul,
-                            void* stream);
+                            int unshuffle, void* stream);
+/* F.interpolate(scale_factor=2, mode='nearest') on NHWC fp16 (rrdbnet_arch.py:118-119). */
+int b200ir_nearest_up2(const void* in, void* out, int B, int h, int w, int C, void* stream);
 /* conv_last output fp32 NHWC [B][H][W][Cpad] -> fp32 NCHW [B][C][H][W]: y * mul + add[c] (edsr_arch.py:69:
  * x / img_range + mean) + F.interpolate(base, scale_factor=scale, mode='bilinear', align_corners=False)
  * (srresnet_arch.py:66-67; base fp32 NCHW [B][C][H/scale][W/scale] or NULL). */
@@ -253,12 +256,13 @@ int b200ir_sr_output(const float* y, float* out, int B, int C, int H, int W, int
                      const float* base, int scale, void* stream);
 /* RCAN channel attention (rcan_arch.py:8-24): nn.AdaptiveAvgPool2d(1) of an NHWC fp16 tensor -> mean fp32 [B][C];
  * att = sigmoid(W2 relu(W1 mean + b1) + b2) with W1 [Cs][C], W2 [C][Cs]; RCAB tail (rcan_arch.py:43-45)
- * out = x * att[b][c] * res_scale + identity. */
+ * out = x * att[b][c] * res_scale + identity (att NULL = 1: the RRDB merge out * 0.2 + x, rrdbnet_arch.py:59-63;
+ * identity / out may be channel slices of wider NHWC buffers: pixel strides in elements). */
 int b200ir_channel_mean(const void* x, float* mean, int B, int HW, int C, void* stream);
 int b200ir_ca_mlp(const float* mean, const float* w1, const float* b1, const float* w2, const float* b2, float* att,
                   int B, int C, int Cs, void* stream);
 int b200ir_ca_scale_add(const void* x, const float* att, const void* identity, void* out, float res_scale, int B, int HW,
-                        int C, void* stream);
+                        int C, int64_t id_stride, int64_t out_stride, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused degradation (pyblur blur -> cv2.resize down -> Gaussian noise -> clip -> cv2.resize up -> round/clip ->

@@ -5,6 +5,7 @@ Follows, line by line:
   MSRResNet.forward   Car_Plate-Restoration/basicsr/archs/srresnet_arch.py:55-68
   EDSR.forward        .../edsr_arch.py:59-72
   RCAN.forward        .../rcan_arch.py:122-135 (ChannelAttention :8-24, RCAB :27-45, ResidualGroup :48-66)
+  RRDBNet.forward     .../rrdbnet_arch.py:105-123 (ResidualDenseBlock :9-39, RRDB :42-63), pixel_unshuffle arch_util.py:185-201
   ResidualBlockNoBN   .../arch_util.py:66-93 ; Upsample :96-109
 
 Pinned: against the unmodified reference modules imported in the build container (tests/test_sr_cpu.py, max rel diff
@@ -83,6 +84,37 @@ def rcan_forward(sd, x, res_scale=1, img_range=255., rgb_mean=(0.4488, 0.4371, 0
     res = _conv(sd, 'conv_after_body', out) + x
     x = _conv(sd, 'conv_last', _upsample(sd, res))
     return x / img_range + mean
+
+
+def _rdb(sd, p, x):                                     # rrdbnet_arch.py:31-39
+    lr = lambda t: F.leaky_relu(t, 0.2)                 # noqa: E731
+    x1 = lr(_conv(sd, p + '.conv1', x))
+    x2 = lr(_conv(sd, p + '.conv2', torch.cat((x, x1), 1)))
+    x3 = lr(_conv(sd, p + '.conv3', torch.cat((x, x1, x2), 1)))
+    x4 = lr(_conv(sd, p + '.conv4', torch.cat((x, x1, x2, x3), 1)))
+    x5 = _conv(sd, p + '.conv5', torch.cat((x, x1, x2, x3, x4), 1))
+    return x5 * 0.2 + x
+
+
+def _pixel_unshuffle(x, scale):                         # arch_util.py:185-201
+    b, c, hh, hw = x.shape
+    h, w = hh // scale, hw // scale
+    return x.view(b, c, h, scale, w, scale).permute(0, 1, 3, 5, 2, 4).reshape(b, c * scale * scale, h, w)
+
+
+def rrdbnet_forward(sd, x, scale=4):                    # rrdbnet_arch.py:105-123
+    feat = _pixel_unshuffle(x, 2) if scale == 2 else (_pixel_unshuffle(x, 4) if scale == 1 else x)
+    feat = _conv(sd, 'conv_first', feat)
+    out = feat
+    for i in range(_count(sd, 'body.')):
+        y = out
+        for j in (1, 2, 3):
+            y = _rdb(sd, f'body.{i}.rdb{j}', y)
+        out = y * 0.2 + out                             # RRDB.forward :59-63
+    feat = feat + _conv(sd, 'conv_body', out)
+    feat = F.leaky_relu(_conv(sd, 'conv_up1', F.interpolate(feat, scale_factor=2, mode='nearest')), 0.2)
+    feat = F.leaky_relu(_conv(sd, 'conv_up2', F.interpolate(feat, scale_factor=2, mode='nearest')), 0.2)
+    return _conv(sd, 'conv_last', F.leaky_relu(_conv(sd, 'conv_hr', feat), 0.2))
 
 
 def psnr01(a, b):

@@ -19,6 +19,8 @@ CASES = [  # name, arch, kwargs, (B, H, W), seed
     ('sr_msrresnet_x4_seed0', 'MSRResNet', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=4, upscale=4), (2, 24, 40), 0),
     ('sr_msrresnet_x3_seed1', 'MSRResNet', dict(num_in_ch=3, num_out_ch=3, num_feat=32, num_block=2, upscale=3), (1, 16, 24), 1),
     ('sr_edsr_x2_seed2', 'EDSR', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=4, upscale=2, res_scale=0.1), (2, 24, 32), 2),
+    ('sr_rrdbnet_x4_seed4', 'RRDBNet', dict(num_in_ch=3, num_out_ch=3, scale=4, num_feat=64, num_block=2, num_grow_ch=32), (2, 16, 24), 4),
+    ('sr_rrdbnet_x2_seed5', 'RRDBNet', dict(num_in_ch=3, num_out_ch=3, scale=2, num_feat=32, num_block=1, num_grow_ch=16), (1, 32, 48), 5),
     ('sr_rcan_x4_seed3', 'RCAN', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_group=2, num_block=2, squeeze_factor=16, upscale=4), (2, 16, 24), 3),
 ]
 
@@ -26,7 +28,7 @@ CASES = [  # name, arch, kwargs, (B, H, W), seed
 def main():
     ref_import.load_reference_arch()                      # registers every reference arch
     import importlib
-    mods = {'MSRResNet': 'srresnet_arch', 'EDSR': 'edsr_arch', 'RCAN': 'rcan_arch'}
+    mods = {'MSRResNet': 'srresnet_arch', 'EDSR': 'edsr_arch', 'RCAN': 'rcan_arch', 'RRDBNet': 'rrdbnet_arch'}
     for name, arch, kw, (B, H, W), seed in CASES:
         cls = getattr(importlib.import_module('basicsr.archs.' + mods[arch]), arch)
         torch.manual_seed(seed)

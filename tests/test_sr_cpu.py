@@ -15,7 +15,8 @@ from tests.helpers import GOLDEN_DIR, state_checksum
 
 FWD = {'MSRResNet': lambda sd, x, kw: sr_oracle.msrresnet_forward(sd, x, kw.get('upscale', 4)),
        'EDSR': lambda sd, x, kw: sr_oracle.edsr_forward(sd, x, kw.get('res_scale', 1)),
-       'RCAN': lambda sd, x, kw: sr_oracle.rcan_forward(sd, x, kw.get('res_scale', 1))}
+       'RCAN': lambda sd, x, kw: sr_oracle.rcan_forward(sd, x, kw.get('res_scale', 1)),
+       'RRDBNet': lambda sd, x, kw: sr_oracle.rrdbnet_forward(sd, x, kw.get('scale', 4))}
 
 
 def sr_golden_files():
@@ -47,6 +48,7 @@ def test_seeded_init_and_oracle_match_reference_golden(path):
     ('MSRResNet', 'srresnet_arch', dict(num_feat=32, num_block=2, upscale=2)),
     ('EDSR', 'edsr_arch', dict(num_in_ch=3, num_out_ch=3, num_feat=32, num_block=2, upscale=3, res_scale=0.5)),
     ('RCAN', 'rcan_arch', dict(num_in_ch=3, num_out_ch=3, num_feat=32, num_group=2, num_block=1, squeeze_factor=8, upscale=2)),
+    ('RRDBNet', 'rrdbnet_arch', dict(num_in_ch=3, num_out_ch=3, scale=1, num_feat=32, num_block=1, num_grow_ch=16)),
 ])
 def test_state_dict_contract_and_oracle_against_reference_modules(arch, mod, kw):
     import importlib
@@ -77,7 +79,7 @@ def test_state_dict_contract_and_oracle_against_reference_modules(arch, mod, kw)
 def test_sr_archs_registered_and_refuse_cpu():
     from image_restoration_b200 import sr_archs
     from image_restoration_b200.registry import ARCH_REGISTRY
-    for name in ('MSRResNet_B200', 'EDSR_B200', 'RCAN_B200'):
+    for name in ('MSRResNet_B200', 'EDSR_B200', 'RCAN_B200', 'RRDBNet_B200'):
         assert name in ARCH_REGISTRY
     net = ARCH_REGISTRY.get('MSRResNet_B200')(num_feat=16, num_block=1, upscale=2)
     with pytest.raises(RuntimeError):

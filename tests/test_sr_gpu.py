@@ -47,6 +47,8 @@ def test_sr_forward_matches_reference_golden(path):
     ('MSRResNet', dict(num_feat=64, num_block=16, upscale=4), (4, 3, 64, 96)),       # options/test/SRResNet_SRGAN config
     ('EDSR', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=16, upscale=4, res_scale=1), (2, 3, 48, 48)),
     ('RCAN', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_group=3, num_block=4, upscale=2), (2, 3, 40, 56)),
+    ('RRDBNet', dict(num_in_ch=3, num_out_ch=3, scale=4, num_feat=64, num_block=3, num_grow_ch=32), (2, 3, 24, 40)),
+    ('RRDBNet', dict(num_in_ch=3, num_out_ch=3, scale=1, num_feat=64, num_block=2, num_grow_ch=32), (1, 3, 64, 96)),
 ])
 def test_sr_forward_matches_oracle_perturbed_weights(arch, kw, shape):
     from image_restoration_b200 import sr_archs
@@ -57,7 +59,7 @@ def test_sr_forward_matches_oracle_perturbed_weights(arch, kw, shape):
     for k, v in sd.items():
         if k.endswith('bias'):
             v.add_(torch.randn(v.shape, generator=g) * 0.02)
-        elif arch == 'MSRResNet':
+        elif arch in ('MSRResNet', 'RRDBNet') and ('rdb' in k or arch == 'MSRResNet'):
             v.mul_(4.0)       # the 0.1-scaled default init leaves the conv branch ~1e-4 of the bilinear base: scale it up
     net.load_state_dict(sd)
     x = torch.rand(*shape)
