@@ -75,6 +75,7 @@ SIGNATURES = {
     'b200ir_demod': [_P, _P, _F, _P, _I, _I, _I, _P],
     'b200ir_mod_linear_multi': [_P, _I, _I, _P, _I, _I, _F, _I, _P],
     'b200ir_demod_multi': [_P, _I, _I, _I, _P],
+    'b200ir_style_mlp': [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     'b200ir_nhwc_to_nchw_f32': [_P, _P, _I, _I, _I, _P],
     'b200ir_nchw_to_nhwc_pad': [_P, _P, _I, _I, _I, _I, _I, _P, _F, _I, _P],
     'b200ir_nearest_up2': [_P, _P, _I, _I, _I, _I, _P],

@@ -623,6 +623,46 @@ __global__ void __launch_bounds__(kRdOut) demod_multi_kernel(const b200ir_demod_
   }
 }
 
+// Style MLP of StyleGAN2OCRGenerator (stylegan2_ocr_arch.py:12-23, 424-430; used when input_is_latent=False):
+// NormStyleCode x * rsqrt(mean(x^2) + 1e-8), then num_mlp x [EqualLinear(F, F, lr_mul) + fused leaky-ReLU]:
+//   y = lrelu(x W^T * (lr_mul / sqrt(F)) + b * lr_mul, 0.2) * sqrt(2).   One block per style vector; w [n_layers][F][F].
+__global__ void style_mlp_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ bias,
+                                 float* __restrict__ out, int F, int n_layers, float lr_mul) {
+  extern __shared__ float sv[];  // [2][F]
+  float* cur = sv;
+  float* nxt = sv + F;
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const float v = z[(long long)b * F + i];
+    cur[i] = v;
+    ss += v * v;
+  }
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float nrm = rsqrtf(tot / (float)F + 1e-8f);
+  for (int i = threadIdx.x; i < F; i += blockDim.x) cur[i] *= nrm;
+  __syncthreads();
+  const float wscale = lr_mul * rsqrtf((float)F);
+  for (int l = 0; l < n_layers; ++l) {
+    const float* wl = w + (long long)l * F * F;
+    for (int o = threadIdx.x; o < F; o += blockDim.x) {
+      float acc = 0.f;
+      for (int k = 0; k < F; ++k) acc = fmaf(__ldg(wl + (long long)o * F + k), cur[k], acc);
+      nxt[o] = lrelu_s(acc * wscale + __ldg(bias + l * F + o) * lr_mul);
+    }
+    __syncthreads();
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  for (int i = threadIdx.x; i < F; i += blockDim.x) out[(long long)b * F + i] = cur[i];
+}
+
 __global__ void nhwc_to_nchw_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, int B, int P, int C) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * P * C) return;
@@ -822,6 +862,13 @@ extern "C" int b200ir_demod_multi(const b200ir_demod_layer* layers_dev, int n_la
   dim3 grid((max_cout + kRdOut - 1) / kRdOut, n_layers, (B + kRdBatch - 1) / kRdBatch);
   demod_multi_kernel<<<grid, kRdOut, 0, STREAM>>>(layers_dev, B);
   return check_launch("demod_multi");
+}
+
+extern "C" int b200ir_style_mlp(const float* z, const float* w, const float* bias, float* out, int B, int F, int n_layers,
+                                float lr_mul, void* stream) {
+  B200IR_REQUIRE(z && w && bias && out && B > 0 && F > 0 && n_layers >= 0, "style_mlp: bad arguments");
+  style_mlp_kernel<<<B, 256, 2 * F * sizeof(float), STREAM>>>(z, w, bias, out, F, n_layers, lr_mul);
+  return check_launch("style_mlp");
 }
 
 extern "C" int b200ir_nhwc_to_nchw_f32(const void* in, float* out, int B, int P, int C, void* stream) {

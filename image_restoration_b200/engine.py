@@ -110,6 +110,12 @@ class _Packed:
         self.rgbs = [rgb(f'{D}.to_rgbs.{i}') for i in range(L)]
         self.stored_noise = [f32(f'{D}.noises.noise{j}') for j in range(2 * L + 1)]
         self.mod_wscale = 1.0 / math.sqrt(net.num_style_feat)
+        # style MLP (only executed when input_is_latent=False)
+        self.mlp_w = torch.stack([g(f'{D}.style_mlp.{i}.weight').float() for i in range(1, net.num_mlp + 1)]).contiguous() \
+            if net.num_mlp > 0 else torch.zeros(0, net.num_style_feat, net.num_style_feat, device=dev)
+        self.mlp_b = torch.stack([g(f'{D}.style_mlp.{i}.bias').float() for i in range(1, net.num_mlp + 1)]).contiguous() \
+            if net.num_mlp > 0 else torch.zeros(0, net.num_style_feat, device=dev)
+        self.mlp_lr_mul = float(net.stylegan_decoder.style_mlp[1].lr_mul) if net.num_mlp > 0 else 1.0
 
 
 class PwOp:
@@ -203,6 +209,11 @@ class _Plan:
         self.style_code = e32(B, n_lin)
         steps.append(ops.linear_as_conv(g.view(B, -1), pk.lin_w, self.style_code, bias=pk.lin_b,
                                         block_n=64 if n_lin % 64 == 0 else None))
+        if not net.input_is_latent:
+            # style code -> latent through the style MLP (gfpganv1_ocr_arch.py:77-78, stylegan2_ocr_arch.py:424-430)
+            z = self.style_code
+            self.style_code = e32(B, n_lin)
+            steps.append(lambda a=z, o=self.style_code: ops.style_mlp(a, pk.mlp_w, pk.mlp_b, o, pk.mlp_lr_mul))
         steps.rec('style_code')
         if net.different_w:
             self.num_latent = n_lin // nf
@@ -420,9 +431,10 @@ class _Plan:
 
 class OcrEngine:
     def __init__(self, net):
-        if net.input_is_latent is False:
-            raise NotImplementedError('input_is_latent=False (style MLP path) is not built yet; every shipped '
-                                      'reference config uses input_is_latent=True')
+        if not net.input_is_latent and net.different_w:
+            # the reference fails here too: style_mlp's fused_leaky_relu broadcasts its bias over dim 1 of a
+            # (B, num_latent, F) tensor (stylegan2_ocr_arch.py:175, fused_act.py:94)
+            raise ValueError('input_is_latent=False needs different_w=False (one style vector per image)')
         dev = next(net.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('image_restoration_b200 needs the module on a CUDA B200 (no CPU path)')
@@ -505,8 +517,30 @@ class OcrEngine:
         return image.to(x.dtype) if x.dtype != F32 else image, rgbs
 
     def _run_eager(self, plan, return_rgb, save_feat_path, load_feat_path):
-        if load_feat_path is None and save_feat_path is None:
-            plan.launch(return_rgb)
-            return
-        # conditions are produced by the first half of the step list; split at the first modulation step
-        raise NotImplementedError('save_feat_path / load_feat_path are not wired in the B200 engine yet')
+        """Eager (non-graph) execution; also serves save_feat_path / load_feat_path (gfpganv1_ocr_arch.py:380-384):
+        the SFT conditions are saved as the reference saves them (list of 2L fp32 NCHW tensors, scale then shift per
+        level) and loaded conditions replace the computed ones before the StyleGAN decoder consumes them."""
+        plan.launch(return_rgb)
+        if save_feat_path is not None:
+            conds = []
+            for sc, sh in plan.cond:
+                for t in (sc, sh):
+                    b, h, w, c = t.shape
+                    o = torch.empty(b, c, h, w, device=t.device, dtype=F32)
+                    ops.nhwc_to_nchw_f32(t, o)
+                    conds.append(o)
+            torch.save(conds, save_feat_path)
+        if load_feat_path is not None:
+            conds = torch.load(load_feat_path)
+            if len(conds) != 2 * len(plan.cond):
+                raise ValueError(f'{load_feat_path}: expected {2 * len(plan.cond)} condition tensors, got {len(conds)}')
+            for i, (sc, sh) in enumerate(plan.cond):
+                for t, src in ((sc, conds[2 * i]), (sh, conds[2 * i + 1])):
+                    src = src.to(t.device, F32).contiguous()
+                    if tuple(src.shape) != (t.shape[0], t.shape[3], t.shape[1], t.shape[2]):
+                        raise ValueError(f'{load_feat_path}: condition {i} has shape {tuple(src.shape)}')
+                    ops.nchw_to_nhwc_pad(src, t)
+            # re-run the StyleGAN decoder (lanes 1 and 3 of the schedule) on the loaded conditions
+            for e in plan.steps.sched:
+                if e[0] == 'op' and e[1] in (1, 3):
+                    e[2]()

@@ -421,6 +421,12 @@ def ca_scale_add(x, att, identity, out, res_scale=1.0, id_stride=None, out_strid
                                          id_stride or c, out_stride or c, _stream()), 'ca_scale_add')
 
 
+def style_mlp(z, w, bias, out, lr_mul):
+    b, f = z.shape
+    check(_lib.lib().b200ir_style_mlp(_ptr(z), _ptr(w), _ptr(bias), _ptr(out), b, f, w.shape[0], lr_mul, _stream()),
+          'style_mlp')
+
+
 def nhwc_to_nchw_f32(x, out):
     b, h, w, c = x.shape
     check(_lib.lib().b200ir_nhwc_to_nchw_f32(_ptr(x), _ptr(out), b, h * w, c, _stream()), 'nhwc_to_nchw_f32')

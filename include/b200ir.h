@@ -232,6 +232,12 @@ int b200ir_mod_linear_multi(const float* latent, int L, int F, const b200ir_mod_
                             int max_cin, float wscale, int B, void* stream);
 int b200ir_demod_multi(const b200ir_demod_layer* layers_dev, int n_layers, int max_cout, int B, void* stream);
 
+/* Style MLP (StyleGAN2OCRGenerator.style_mlp, stylegan2_ocr_arch.py:12-23,424-430; the input_is_latent=False path):
+ * out = MLP(NormStyleCode(z)), n_layers x [EqualLinear(F, F, lr_mul) + fused leaky-ReLU]; z, out fp32 [B][F];
+ * w fp32 [n_layers][F][F] and bias fp32 [n_layers][F] as stored in the state_dict (not pre-scaled). */
+int b200ir_style_mlp(const float* z, const float* w, const float* bias, float* out, int B, int F, int n_layers,
+                     float lr_mul, void* stream);
+
 /* NHWC fp16 [B][P][C] -> fp32 matrix [B][P*C] is a reinterpretation; this converts fp32 NCHW image batches to the
  * caller-facing layout when needed: out_nchw[b][c][p] = in_nhwc[b][p][c] (fp16 -> fp32). */
 int b200ir_nhwc_to_nchw_f32(const void* in, float* out, int B, int P, int C, void* stream);

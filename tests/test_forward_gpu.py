@@ -214,3 +214,66 @@ def test_config3_sharded_micro_batches_match_direct_calls():
     full = torch.cat(parts, 0)
     direct = torch.cat([fn(x[i:i + 29]) for i in range(0, n, 29)], 0)
     assert torch.equal(full, direct)
+
+
+def test_style_mlp_path_input_is_latent_false():
+    """input_is_latent=False, different_w=False: the style code goes through NormStyleCode + the style MLP
+    (stylegan2_ocr_arch.py:12-23,424-430) and is shared by all layers.  different_w=True with that flag fails in the
+    reference (bias broadcast of fused_leaky_relu) and is refused here."""
+    from image_restoration_b200 import GFPGANv1OCR
+    from oracle.gfpgan_ocr_oracle import OcrNetConfig, gfpgan_ocr_forward, psnr01, to01
+    torch.manual_seed(7)
+    kw = dict(input_width=96, input_height=32, num_style_feat=256, channel_multiplier=0.5, num_mlp=4,
+              input_is_latent=False, different_w=False, narrow=1, sft_half=True)
+    net = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **kw).eval()
+    sd = net.state_dict()
+    g = torch.Generator().manual_seed(8)
+    for k, v in sd.items():
+        if 'style_mlp' in k and k.endswith('bias'):
+            v.add_(torch.randn(v.shape, generator=g) * 30.0)          # bias * lr_mul(0.01) must matter
+    net.load_state_dict(sd)
+    x = torch.rand(3, 3, 32, 96) * 2 - 1
+    ref, _ = gfpgan_ocr_forward(net.state_dict(), OcrNetConfig(**kw), x, False)
+    got = net.cuda()(x.cuda(), return_rgb=False, randomize_noise=False)[0].cpu()
+    a, b = to01(got), to01(ref)
+    print(f'style-MLP path: max-abs {(a - b).abs().max().item():.3e} psnr {psnr01(a, b):.1f} dB')
+    assert (a - b).abs().max().item() <= 2e-2 and psnr01(a, b) >= 45.0
+    bad = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **dict(kw, different_w=True)).eval().cuda()
+    with pytest.raises(ValueError):
+        bad(x.cuda())
+
+
+def test_save_and_load_feat_path(tmp_path):
+    """save_feat_path / load_feat_path (gfpganv1_ocr_arch.py:380-384): the saved file is the reference's list of 2L fp32
+    NCHW condition tensors; loading it back reproduces the call; loading another image's conditions gives what the
+    oracle's decoder gives for (own style code, foreign conditions)."""
+    from image_restoration_b200 import GFPGANv1OCR
+    from oracle import gfpgan_ocr_oracle as go
+    torch.manual_seed(9)
+    kw = dict(input_width=96, input_height=32, num_style_feat=256, channel_multiplier=0.5, num_mlp=4,
+              input_is_latent=True, different_w=True, narrow=1, sft_half=True)
+    net = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **kw).eval()
+    cfg = go.OcrNetConfig(**kw)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x1, x2 = torch.rand(2, 3, 32, 96) * 2 - 1, torch.rand(2, 3, 32, 96) * 2 - 1
+    net = net.cuda()
+    f1 = str(tmp_path / 'cond1.pth')
+    y1 = net(x1.cuda(), return_rgb=False, randomize_noise=False, save_feat_path=f1)[0]
+    conds = torch.load(f1)
+    assert len(conds) == 2 * cfg.num_levels and conds[0].dtype == torch.float32 and conds[0].dim() == 4
+    taps = {}
+    go.gfpgan_ocr_forward(sd, cfg, x1, False, taps=taps)
+    for i in range(cfg.num_levels):
+        for j, name in enumerate(('scale', 'shift')):
+            ref = taps[f'{name}{i}']
+            err = (conds[2 * i + j].cpu() - ref).abs().max().item()
+            assert err <= 2e-2 * (ref.abs().max().item() + 1e-6), (i, name, err)
+    assert torch.equal(net(x1.cuda(), return_rgb=False, randomize_noise=False, load_feat_path=f1)[0], y1)
+    # foreign conditions: oracle decoder on x2's style code with x1's (saved) conditions
+    taps2 = {}
+    go.gfpgan_ocr_forward(sd, cfg, x2, False, taps=taps2)
+    sdf = {k: v.float() for k, v in sd.items()}
+    ref = go.stylegan_decoder(sdf, cfg, taps2['style_code'], [c.cpu() for c in conds], go.stored_noises(sdf, cfg))
+    got = net(x2.cuda(), return_rgb=False, randomize_noise=False, load_feat_path=f1)[0].cpu()
+    a, b = go.to01(got), go.to01(ref)
+    assert (a - b).abs().max().item() <= 2e-2 and go.psnr01(a, b) >= 45.0
