@@ -235,9 +235,11 @@ def main():
         return ms
 
     # clocks take a few hundred ms to settle after the idle -> busy transition: untimed pre-roll before the W warm-ups
-    for _ in range(40):
-        step_resident()
-    torch.cuda.synchronize()
+    t_pre = time.time()
+    while time.time() - t_pre < 1.5:
+        for _ in range(10):
+            step_resident()
+        torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
     ms_total = timed(step_resident, args.steps, warmup)
