@@ -56,3 +56,51 @@ def test_two_rank_gloo_sharding(n):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from image_restoration_b200.grad_sync import GradAllReducer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    for p in net[3].parameters():          # an unused branch: no gradient (find_unused_parameters semantics)
+        p.grad = None
+    x = torch.full((3, 8), float(rank + 1))
+    net[2](net[1](net[0](x))).sum().backward()
+    red = GradAllReducer(net.parameters(), bucket_mb=0.0001)      # tiny buckets: several all-reduces
+    assert len(red.buckets) > 1
+    red.sync(average=True)
+    q.put((rank, [p.grad.clone() for p in net.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    """Flat-buffer bucketed gradient all-reduce (the DDP exchange of base_model.py:70-73): both ranks end with the mean
+    of their gradients; parameters without a gradient get zeros."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # expected: average of the two single-rank gradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+    exp = None
+    for rank in range(2):
+        net.zero_grad(set_to_none=True)
+        net[2](net[1](net[0](torch.full((3, 8), float(rank + 1))))).sum().backward()
+        g = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in net.parameters()]
+        exp = g if exp is None else [a + b for a, b in zip(exp, g)]
+    exp = [e / 2 for e in exp]
+    for rank in range(2):
+        for got, e in zip(res[rank], exp):
+            assert torch.allclose(got, e, atol=1e-6)
