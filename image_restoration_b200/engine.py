@@ -457,8 +457,14 @@ class OcrEngine:
     def stale(self):
         return self._sig != self._signature()
 
+    MAX_PLANS = 4   # a plan holds every activation of its batch size (~0.15 GB per crop @128x384): keep the most recent
+
     def plan(self, B):
-        if B not in self.plans:
+        if B in self.plans:
+            self.plans[B] = self.plans.pop(B)          # most recently used last
+        else:
+            while len(self.plans) >= self.MAX_PLANS:
+                self.plans.pop(next(iter(self.plans)))  # evict the least recently used plan (buffers, graphs)
             self.plans[B] = _Plan(self, B)
         return self.plans[B]
 

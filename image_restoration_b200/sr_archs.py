@@ -438,7 +438,11 @@ class SrEngine:
         B, _, H, W = x.shape
         with torch.cuda.device(self.dev):
             key = (B, H, W)
-            if key not in self.plans:
+            if key in self.plans:
+                self.plans[key] = self.plans.pop(key)
+            else:
+                while len(self.plans) >= 4:             # keep the four most recently used input shapes
+                    self.plans.pop(next(iter(self.plans)))
                 self.plans[key] = _SrPlan(self, B, H, W)
             plan = self.plans[key]
             plan.x_in.copy_(x)
