@@ -18,9 +18,16 @@
 namespace b200ir {
 
 static constexpr int kBlockM = 128;
-static constexpr int kEpiWarps = 8;                         // two per TMEM lane quarter
-static constexpr int kEpiThreads = kEpiWarps * 32;
-static constexpr int kThreads = 64 + kEpiThreads;       // warp 0 producer, warp 1 MMA, warps 2.. epilogue
+// warp 0 producer, warp 1 MMA issuer, then kEpiGroups groups of 4 epilogue warps (one warp per TMEM lane quarter) that
+// drain tiles round-robin.  The specialised epilogues (<= 105 registers) run three groups: on the low-K layers the
+// epilogue of a tile takes longer than its main loop, and the third group closes most of that gap.  The run-time generic
+// epilogue (168 registers) stays at two so that it fits the register file.
+template <int EPI>
+struct EpiCfg {
+  static constexpr int kGroups = (EPI >= 0) ? 3 : 2;
+  static constexpr int kThreads = 64 + 128 * kGroups;
+};
+static constexpr int kMaxEpiGroups = 3;
 static constexpr int kDemodTable = 2560;  // floats per epilogue group: per-tile tables [demod | out_scale | rgb_w x3]
 static constexpr int kMaxBias = 512;
 static constexpr int kMaxStages = 8;
@@ -578,7 +585,7 @@ struct KernelSmem {
 };
 
 // bytes after the pipeline buffers: barriers + TMEM slot + bias + demod tables
-static constexpr int kTailBytes = 512 + kMaxBias * 4 + 2 * kDemodTable * 4;
+static constexpr int kTailBytes = 512 + kMaxBias * 4 + kMaxEpiGroups * kDemodTable * 4;
 
 // the two epilogue warp groups (4 warps each) drain alternate tiles; each group syncs on its own named barrier
 __device__ __forceinline__ void epi_group_sync(int group) {
@@ -617,7 +624,7 @@ __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const K
   }
   // bias table: all output channels when they fit; all zeros (any kMaxBias-periodic window is valid) without a bias
   if (p.cout <= kMaxBias || p.bias == nullptr)
-    for (int i = threadIdx.x; i < min(p.cout, kMaxBias); i += kThreads)
+    for (int i = threadIdx.x; i < min(p.cout, kMaxBias); i += blockDim.x)
       s.bias[i] = (p.bias != nullptr) ? p.bias[i] * p.act_gain : 0.f;
   if (warp == 1) {
     tmem_alloc(s.tmem_slot, p.tmem_cols);
@@ -640,7 +647,8 @@ __device__ __forceinline__ void kernel_epilogue(const ConvParams& p, uint32_t tm
 
 // ================================================================================================ generic tiles
 template <int kBlockK, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kGroups = EpiCfg<EPI>::kGroups;
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t row_bytes = kBlockK * 2;
   constexpr uint32_t a_bytes = kBlockM * row_bytes;
@@ -732,7 +740,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) * p.act_gain : 0.f;
     int it = group;
     int last_key = -1;
-    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+    // a group may wait at most one phase ahead on an accumulator's mbarrier, so no more groups than accumulator stages
+    // take part (block_n = 256 has two stages: the third group idles there, those layers are main-loop bound anyway)
+    const int ngroups = min(kGroups, p.acc_stages);
+    for (int tile = (group < ngroups) ? blockIdx.x + group * gridDim.x : p.num_tiles; tile < p.num_tiles;
+         tile += ngroups * gridDim.x, it += ngroups) {
       const int acc = it & (p.acc_stages - 1);
       const TileCoord t = decode_tile(p, tile);
       const int x = t.x0 + xx, y = t.y0 + yy, b = t.b0 + bi;
@@ -816,7 +828,8 @@ __device__ __forceinline__ RowItem decode_item(const ConvParams& p, int item) {
 }
 
 template <int kBlockK, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_row_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kGroups = EpiCfg<EPI>::kGroups;
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t row_bytes = kBlockK * 2;
   constexpr int k_steps = kBlockK / 16;
@@ -941,6 +954,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_cons
     const int gt = (threadIdx.x - 64) & 127;
     const int row = q * 32 + lane;
     const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) * p.act_gain : 0.f;
+    const int ngroups = min(kGroups, p.acc_stages);  // see conv_igemm_kernel (the ring has 8 or 16 stages here)
     int it = 0;
     for (int item = blockIdx.x; item < p.row_items; item += gridDim.x) {
       const RowItem w = decode_item(p, item);
@@ -966,7 +980,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_row_kernel(const __grid_cons
         if (p.smem_aux) s_aux = smem_u32(tab + p.block_n);
       }
       for (int j = 0; j < w.rows_out; ++j, ++it) {
-        if ((it & 1) != group) continue;
+        if (it % ngroups != group) continue;
         const int acc = it & (p.acc_stages - 1);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
         epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, w.y0 + j, w.b, 0, valid, gain,
@@ -995,7 +1009,7 @@ static int launch_one(const ConvParams& p, int grid, int smem_bytes, int smem_ma
       }
       configured = true;
     }
-    conv_row_kernel<kBlockK, EPI><<<grid, kThreads, smem_bytes, st>>>(p);
+    conv_row_kernel<kBlockK, EPI><<<grid, EpiCfg<EPI>::kThreads, smem_bytes, st>>>(p);
     return check_launch("conv_row");
   }
   if (!configured) {
@@ -1006,7 +1020,7 @@ static int launch_one(const ConvParams& p, int grid, int smem_bytes, int smem_ma
     }
     configured = true;
   }
-  conv_igemm_kernel<kBlockK, EPI><<<grid, kThreads, smem_bytes, st>>>(p);
+  conv_igemm_kernel<kBlockK, EPI><<<grid, EpiCfg<EPI>::kThreads, smem_bytes, st>>>(p);
   return check_launch("conv_igemm");
 }
 

@@ -155,7 +155,7 @@ def row_mode_ok(b, h, w, cin, cout):
     block_k = 64 if cin % 64 == 0 else (32 if cin % 32 == 0 else 16)
     kc = cin // block_k
     w_bytes = 9 * kc * cout * block_k * 2
-    slots = (232448 - 1024 - (512 + 512 * 4 + 2 * 2560 * 4) - w_bytes) // (136 * block_k * 2)
+    slots = (232448 - 1024 - (512 + 512 * 4 + 3 * 2560 * 4) - w_bytes) // (136 * block_k * 2)
     if slots < 2 * kc:
         return False
     return b * -(-w // 128) * -(-h // 8) >= 2 * NUM_SMS
