@@ -53,6 +53,9 @@ struct FirLaunch {
 // returns -1 when the shape is not eligible (caller uses the direct kernels), else 0 / 1 like every launcher
 int fir_stream_launch(const FirLaunch& a, cudaStream_t st, const char* what);
 
+// TMA-fed streaming resamplers (resample_tma.cu): FIR pad (1,1) + stride 2 (down) / bilinear x2 (up); -1 = not eligible
+int resample_stream_launch(bool down, const __half* in, __half* out, int B, int H, int W, int C, cudaStream_t st);
+
 #define B200IR_REQUIRE(cond, ...)    \
   do {                               \
     if (!(cond)) {                   \

@@ -738,6 +738,10 @@ extern "C" int b200ir_fir_pad22(const void* in, void* out, int B, int H, int W, 
 
 extern "C" int b200ir_fir_down2(const void* in, void* out, int B, int H, int W, int C, void* stream) {
   B200IR_REQUIRE(in && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "fir_down2: bad arguments");
+  {
+    const int r = resample_stream_launch(true, (const __half*)in, (__half*)out, B, H, W, C, STREAM);
+    if (r >= 0) return r;
+  }
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
   fir_down2_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, H, W, C);
   return check_launch("fir_down2");
@@ -745,6 +749,10 @@ extern "C" int b200ir_fir_down2(const void* in, void* out, int B, int H, int W, 
 
 extern "C" int b200ir_bilinear_up2(const void* in, void* out, int B, int h, int w, int C, void* stream) {
   B200IR_REQUIRE(in && out && C % 8 == 0, "bilinear_up2: bad arguments");
+  {
+    const int r = resample_stream_launch(false, (const __half*)in, (__half*)out, B, h, w, C, STREAM);
+    if (r >= 0) return r;
+  }
   const long long n = (long long)B * h * w * (C / 8);
   bilinear_up2_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((const __half*)in, (__half*)out, B, h, w, C);
   return check_launch("bilinear_up2");

@@ -476,3 +476,22 @@ def test_transposed_conv_merged_single_gemm(B, h, w, cin, cout):
     torch.cuda.synchronize()
     ref = F.conv_transpose2d(nchw32(xh), wt.half().float().transpose(0, 1), stride=2) * demod[:, :, None, None]
     check_close(nchw32(raw)[:, :, :2 * h + 1, :2 * w + 1], ref, what=f'merged convT {cin}->{cout} {h}x{w}')
+
+
+@pytest.mark.parametrize('B,H,W,C', [(2, 128, 384, 32), (3, 64, 192, 64), (2, 32, 96, 256), (5, 8, 24, 256),
+                                     (64, 4, 12, 256), (1, 34, 70, 64), (2, 6, 10, 96), (2, 16, 16, 16)])
+def test_resamplers_streaming(B, H, W, C):
+    """fir_down2 (FIR pad (1,1) + stride-2 sampling) and bilinear_up2 through the TMA-fed streaming kernels (C % 32 == 0)
+    and the direct kernels (C = 16), ragged strips and row chunks included."""
+    ops = _ops()
+    torch.manual_seed(16)
+    xh = nhwc16(torch.randn(B, C, H, W, device=DEV))
+    down = torch.full((B, H // 2, W // 2, C), 9.0, device=DEV, dtype=torch.float16)
+    ops.fir_down2(xh, down)
+    ref = upfirdn_ref(nchw32(xh), fir_k(DEV), pad=(1, 1))[:, :, ::2, ::2]
+    check_close(nchw32(down), ref, what=f'fir_down2 C={C} {H}x{W}')
+    up = torch.full((B, 2 * H, 2 * W, C), 9.0, device=DEV, dtype=torch.float16)
+    ops.bilinear_up2(xh, up)
+    torch.cuda.synchronize()
+    check_close(nchw32(up), F.interpolate(nchw32(xh), scale_factor=2, mode='bilinear', align_corners=False),
+                what=f'bilinear_up2 C={C} {H}x{W}')
