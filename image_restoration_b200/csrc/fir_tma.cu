@@ -158,8 +158,25 @@ __global__ void __launch_bounds__(NT + 32, (NT == 256 && !(POST && XP == 2)) ? 2
     const int x0 = t.strip * TW + xl;
     const int y_end = min(t.y0 + p.R, p.OH);
     bool xv[XP];
+    bool any_x = false;
 #pragma unroll
-    for (int j = 0; j < XP; ++j) xv[j] = x0 + j < p.OW;
+    for (int j = 0; j < XP; ++j) {
+      xv[j] = x0 + j < p.OW;
+      any_x = any_x || xv[j];
+    }
+    if (!any_x) {
+      // ragged last strip (OW = 385, 193, 97 ...): threads past the image only keep the stage ring moving, so a strip
+      // that holds a single column costs its (mostly out-of-bounds, i.e. free) TMA traffic and little else
+      for (int k = 0; k < p.KS; ++k, ++g) {
+        mbar_wait(&full_bar[slot], phase);
+        mbar_arrive(&empty_bar[slot]);
+        if (++slot == p.NS) {
+          slot = 0;
+          phase ^= 1u;
+        }
+      }
+      continue;
+    }
     float bs[8], sn[8];
     const bool sft = POST && p.has_sft && (c0 >= p.c_keep);
     if (POST) {
@@ -273,6 +290,7 @@ static int fir_launch_variant(const FirLaunch& a, cudaStream_t st, const char* w
   if (const char* e = getenv("B200IR_FIR_R")) R = atoi(e) > 0 ? atoi(e) : R;
   while (R > 8 && (long long)a.B * p.strips * p.chunks * ((a.OH + R - 1) / R) < 4LL * sms) R /= 2;
   if (R > a.OH) R = a.OH;
+  R = (a.OH + (a.OH + R - 1) / R - 1) / ((a.OH + R - 1) / R);  // equal row chunks (OH = 33 -> 17 + 16, not 32 + 1)
   p.R = R;
   p.rchunks = (a.OH + R - 1) / R;
   p.KS = (R + 3 + SR - 1) / SR;
@@ -337,8 +355,12 @@ static int fir_launch_variant(const FirLaunch& a, cudaStream_t st, const char* w
   return check_launch(what);
 }
 
-// strips * TW / OW: x slots per real output; smaller is better
-static inline double fir_waste(int ow, int tw) { return (double)((ow + tw - 1) / tw) * tw / ow; }
+// cost of covering ow outputs with strips of tw: full strips count fully, a ragged last strip by its real width plus a
+// fixed share (its idle threads skip the arithmetic, its out-of-bounds TMA traffic is free); smaller is better
+static inline double fir_waste(int ow, int tw) {
+  const int full = ow / tw, rem = ow - full * tw;
+  return ((double)full * tw + (rem ? rem + 0.15 * tw : 0.0)) / ow;
+}
 
 template <int CC, bool POST>
 static int fir_dispatch(const FirLaunch& a, cudaStream_t st, const char* what) {

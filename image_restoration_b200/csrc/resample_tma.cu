@@ -235,7 +235,9 @@ static int rs_launch_variant(const __half* in, __half* out, int B, int H, int W,
   if (sms == 0) return 1;
   int R = 32;
   while (R > 8 && (long long)B * p.strips * p.chunks * ((span_h + R - 1) / R) < 4LL * sms) R /= 2;
-  if (R > span_h) R = DOWN ? ((span_h + 1) & ~1) : span_h;
+  if (R > span_h) R = span_h;
+  R = (span_h + (span_h + R - 1) / R - 1) / ((span_h + R - 1) / R);  // equal row chunks
+  if (DOWN) R = (R + 1) & ~1;                                          // the stride-2 window advances two rows per stage
   p.R = R;
   p.rchunks = (span_h + R - 1) / R;
   // DOWN: R/2 aligned outputs per ... every stage yields two output rows, plus one stage for the last straddling row;
