@@ -271,8 +271,12 @@ def main():
                     op()
             ms = timed(run_group, args.steps, 3) / args.steps
             nbytes = sum(op.nbytes for op in group)
+            big = max(group, key=lambda op: op.nbytes)        # the largest launch of the kind, alone
+            ms_big = timed(big, args.steps, 3) / args.steps
             pw_report.append({'kernel': name, 'launches_per_step': len(group), 'algorithmic_mb_per_step': nbytes / 1e6,
-                              'ms_per_step': ms, 'achieved_gbs': nbytes / ms / 1e6})
+                              'ms_per_step': ms, 'achieved_gbs': nbytes / ms / 1e6,
+                              'largest_launch': {'algorithmic_mb': big.nbytes / 1e6, 'ms': ms_big,
+                                                 'achieved_gbs': big.nbytes / ms_big / 1e6}})
 
     # fused degradation kernel (north_star (c)): crops/s of pyblur blur + down-resize + noise + up-resize + quantise,
     # beside the reference's own CPU library calls (oracle/pyblur_oracle.py) on a few crops
@@ -348,6 +352,7 @@ def main():
             line['roofline']['algorithmic_bytes_per_launch'] = alg / len(conv_ops)
         for r in pw_report:
             r['frac_of_hbm_peak'] = r['achieved_gbs'] / hbm_peak
+            r['largest_launch']['frac_of_hbm_peak'] = r['largest_launch']['achieved_gbs'] / hbm_peak
         pw_report.sort(key=lambda r: -r['ms_per_step'])
         line['memory_bound_kernels'] = pw_report
         if degr is not None:
@@ -357,7 +362,9 @@ def main():
             top = pw_report[0]
             line['roofline_hbm'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_gbs'],
                                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': top['achieved_gbs'] / hbm_peak,
-                                    'traffic': None, 'peak_source': f'{src} hbm_gbs'}
+                                    'traffic': None, 'peak_source': f'{src} hbm_gbs',
+                                    'note': 'all launches of the kind back to back (five pyramid levels, the small ones '
+                                            'are latency-bound); largest_launch in memory_bound_kernels is one level'}
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_oracle_rate()
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
