@@ -36,6 +36,7 @@ class ConvDesc(C.Structure):
         ('rgb_w_px', C.c_int32), ('rgb_h', C.c_int32), ('no_store', C.c_int32),
         ('act_slope', C.c_float), ('res_mul', C.c_float), ('ps_r', C.c_int32),
         ('ps_c', C.c_int32), ('demod_c', C.c_int32), ('use_tap_mask', C.c_int32), ('tap_mask', C.c_uint32 * 8),
+        ('corr_top', C.c_void_p), ('corr_bot', C.c_void_p), ('corr_left', C.c_void_p), ('corr_right', C.c_void_p),
     ]
 
 
@@ -58,6 +59,8 @@ SIGNATURES = {
     'b200ir_device_check': [],
     'b200ir_conv_igemm': [C.POINTER(ConvDesc), _P],
     'b200ir_first_conv': [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_replicate_border': [_P, _I, _I, _I, _I, _P],
+    'b200ir_upfold_corners': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_tiles_gather': [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _P],
     'b200ir_tiles_blend': [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
     'b200ir_u8_to_input': [_P, _P, _I, _I, _I, _I, _P],

@@ -77,7 +77,13 @@ struct alignas(64) ConvParams {
   int ps_r;       // pixel-shuffle factor of the store (0: off)
   int ps_shift;   // log2(ps_c) when ps_c is a power of two, else -1
   int ps_c;       // channels per sub-pixel phase: output column n belongs to phase n / ps_c, channel n % ps_c
+  int bias_c;     // entries of the bias vector (cout, or ps_c when the phases share one bias: folded ConvUpLayer)
   int demod_c;    // demod / out_scale tables are indexed with channel n % demod_c (phases share one table row)
+  // up-fold border corrections (see epilogue_upfold): fp32 [m_b][2*m_w][ps_c] (top, bottom) / [m_b][2*m_h][ps_c]
+  const float* corr_top;
+  const float* corr_bot;
+  const float* corr_left;
+  const float* corr_right;
   uint32_t tap_mask[8];  // per N-tile: taps to execute (bit t); tiles whose weight block for a tap is all zero skip it
   const float* out_scale;
   const float* rgb_w;
@@ -353,15 +359,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 // The generic epilogue above tests every feature flag per 16-column chunk (measured: ~550 SASS instructions per chunk,
 // which made the epilogue -- not the MMA main loop -- the pace setter of every layer with K <= 1152).  The layers of
 // the network use six feature combinations; each gets an epilogue with the flags as template constants.
-enum : int { F_DEMOD = 1, F_NOISE = 2, F_RES1 = 4, F_RES2 = 8, F_RGB = 16, F_NOSTORE = 32 };
-static constexpr int kNumEpiProfiles = 6;
+enum : int { F_DEMOD = 1, F_NOISE = 2, F_RES1 = 4, F_RES2 = 8, F_RGB = 16, F_NOSTORE = 32, F_UPFOLD = 64 };
+static constexpr int kNumEpiProfiles = 7;
 __host__ __device__ constexpr int epi_profile_flags(int i) {
   return i == 0   ? 0
          : i == 1 ? F_RES1
          : i == 2 ? F_RES2
          : i == 3 ? F_DEMOD
          : i == 4 ? (F_DEMOD | F_NOISE | F_RGB)
-                  : (F_DEMOD | F_NOISE | F_RGB | F_NOSTORE);
+         : i == 5 ? (F_DEMOD | F_NOISE | F_RGB | F_NOSTORE)
+                  : (F_RES2 | F_UPFOLD);
 }
 
 struct FastRow {
@@ -533,6 +540,120 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
   }
 }
 
+// ------------------------------------------------------------------------------------------ ConvUpLayer, folded
+// ConvUpLayer.forward (gfpganv1_ocr_arch.py:188-202) = conv3x3(F.interpolate(x, 2, 'bilinear')): bilinear x2 is linear and
+// fixed, so for every output phase (py, px) the pair collapses into ONE 3x3 conv over the LOW-resolution input with
+// weights sum_{kh,kw} W[kh,kw] A[py+kh][dy] A[px+kw][dx] (A = the bilinear tap matrix; same MMA work as the conv on the
+// up-sampled grid, but no up-sampled tensor, and the four phases are column blocks: N = 4*cout).  The low-resolution
+// input is replicate-padded, which reproduces the clamped interpolation everywhere; the only difference to the reference
+// is the outermost output ring, where the reference's conv sees ZERO padding of the up-sampled tensor while the folded
+// form sees interpolated values.  That surplus is four 1-D convolutions of the border rows / columns (computed by small
+// GEMMs of the same kernel, corner terms added back) and is subtracted here before bias and activation.  Verified in
+// fp64 against F.conv2d(F.interpolate(...)): max |diff| 1e-14 (tests/test_upfold_cpu.py).
+// Per 16-column chunk: phase t = column / ps_c -> output pixel (2y + t/2, 2x + t%2); the ResUpBlock skip
+// (gfpganv1_ocr_arch.py:224, 1x1 conv commuted to low resolution) is sampled bilinearly for that pixel.
+__device__ __forceinline__ void epilogue_upfold(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
+                                                uint32_t full_phase, int x, int y, int b, int n0, bool valid,
+                                                uint32_t s_bias) {
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+  if (p.dbg_skip_epi) return;
+  const float ag = p.act_gain, slope = p.slope;
+  const int OH = 2 * p.m_h, OW = 2 * p.m_w;
+  __half* out_b = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_sb + p.out_c_off;
+  const __half* res_b = p.res + (long long)b * p.res_sb;
+#pragma unroll 1
+  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+    uint32_t raw[16];
+    tmem_ld16(taddr + c0, raw);
+    const int n = n0 + c0;
+    const int t = n >> p.ps_shift;
+    const int cc = n - (t << p.ps_shift);
+    const int yo = 2 * y + (t >> 1), xo = 2 * x + (t & 1);
+    float4 bs[4];  // the four phases share one bias vector of ps_c entries: s_bias points at entry n0 % ps_c
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bs[j] = lds_f4(s_bias + (cc - (n0 & (p.ps_c - 1)) + 4 * j) * 4);
+    // bilinear sample of the low-resolution skip at (yo, xo) (align_corners=False, clamped)
+    uint4 ra[2], rb[2], rc[2], rd[2];
+    float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+    float cr[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cr[j] = 0.f;
+    if (valid) {
+      const int ky = yo >> 1, kx = xo >> 1;
+      int ya, yb, xa, xb;
+      float wy0, wy1, wx0, wx1;
+      if (yo & 1) { ya = ky; yb = min(ky + 1, p.res_h - 1); wy0 = 0.75f; wy1 = 0.25f; }
+      else        { ya = max(ky - 1, 0); yb = ky; wy0 = 0.25f; wy1 = 0.75f; }
+      if (xo & 1) { xa = kx; xb = min(kx + 1, p.res_w - 1); wx0 = 0.75f; wx1 = 0.25f; }
+      else        { xa = max(kx - 1, 0); xb = kx; wx0 = 0.25f; wx1 = 0.75f; }
+      const __half* r00 = res_b + (long long)ya * p.res_sy + (long long)xa * p.res_sx + cc;
+      const __half* r01 = res_b + (long long)ya * p.res_sy + (long long)xb * p.res_sx + cc;
+      const __half* r10 = res_b + (long long)yb * p.res_sy + (long long)xa * p.res_sx + cc;
+      const __half* r11 = res_b + (long long)yb * p.res_sy + (long long)xb * p.res_sx + cc;
+      ra[0] = __ldg(reinterpret_cast<const uint4*>(r00)); ra[1] = __ldg(reinterpret_cast<const uint4*>(r00) + 1);
+      rb[0] = __ldg(reinterpret_cast<const uint4*>(r01)); rb[1] = __ldg(reinterpret_cast<const uint4*>(r01) + 1);
+      rc[0] = __ldg(reinterpret_cast<const uint4*>(r10)); rc[1] = __ldg(reinterpret_cast<const uint4*>(r10) + 1);
+      rd[0] = __ldg(reinterpret_cast<const uint4*>(r11)); rd[1] = __ldg(reinterpret_cast<const uint4*>(r11) + 1);
+      wy0 *= p.res_mul;
+      wy1 *= p.res_mul;
+      w00 = wy0 * wx0; w01 = wy0 * wx1; w10 = wy1 * wx0; w11 = wy1 * wx1;
+      // surplus of the folded form on the outermost ring
+      if (yo == 0 || yo == OH - 1) {
+        const float* cp = (yo == 0 ? p.corr_top : p.corr_bot) + ((long long)b * OW + xo) * p.ps_c + cc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cp) + j);
+          cr[4 * j] += c4.x; cr[4 * j + 1] += c4.y; cr[4 * j + 2] += c4.z; cr[4 * j + 3] += c4.w;
+        }
+      }
+      if (xo == 0 || xo == OW - 1) {
+        const float* cp = (xo == 0 ? p.corr_left : p.corr_right) + ((long long)b * OH + yo) * p.ps_c + cc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cp) + j);
+          cr[4 * j] += c4.x; cr[4 * j + 1] += c4.y; cr[4 * j + 2] += c4.z; cr[4 * j + 3] += c4.w;
+        }
+      }
+    }
+    tmem_ld_wait16(raw);
+    if (!valid) continue;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[4 * j] = fmaf(__uint_as_float(raw[4 * j]) - cr[4 * j], ag, bs[j].x);
+      v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]) - cr[4 * j + 1], ag, bs[j].y);
+      v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]) - cr[4 * j + 2], ag, bs[j].z);
+      v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]) - cr[4 * j + 3], ag, bs[j].w);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+    float f[16];
+    unpack_half8(ra[0], f); unpack_half8(ra[1], f + 8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], w00, v[j]);
+    unpack_half8(rb[0], f); unpack_half8(rb[1], f + 8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], w01, v[j]);
+    unpack_half8(rc[0], f); unpack_half8(rc[1], f + 8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], w10, v[j]);
+    unpack_half8(rd[0], f); unpack_half8(rd[1], f + 8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], w11, v[j]);
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    const __half* op = out_b + (long long)yo * p.out_sy + (long long)xo * p.out_sx + cc;
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                 "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                 : "memory");
+  }
+}
+
 // One tile through the epilogue this kernel instantiation was compiled for: EPI = index into epi_profile_flags (flags are
 // template constants) or -1 for the run-time generic one.  Every (block_k, EPI) pair is its own kernel, compiled in its
 // own translation unit (conv_epi*.cu): with all variants inlined behind a switch the register allocator spilled
@@ -541,7 +662,9 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_one(const ConvParams& p, uint32_t taddr, uint64_t* full_bar, uint32_t full_phase,
                                              int x, int y, int b, int n0, bool valid, float gain, uint32_t s_bias,
                                              uint32_t s_dm, const float* g_dm, uint32_t s_aux, int aux_stride) {
-  if constexpr (EPI >= 0) {
+  if constexpr (EPI >= 0 && (epi_profile_flags(EPI < 0 ? 0 : EPI) & F_UPFOLD) != 0) {
+    epilogue_upfold(p, taddr, full_bar, full_phase, x, y, b, n0, valid, s_bias);
+  } else if constexpr (EPI >= 0) {
     constexpr int F = epi_profile_flags(EPI);
     const FastRow fr = fast_setup<F>(p, x, y, b, n0, valid);
     epilogue_fast<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride, n0);
@@ -623,8 +746,8 @@ __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const K
     fence_barrier_init();
   }
   // bias table: all output channels when they fit; all zeros (any kMaxBias-periodic window is valid) without a bias
-  if (p.cout <= kMaxBias || p.bias == nullptr)
-    for (int i = threadIdx.x; i < min(p.cout, kMaxBias); i += blockDim.x)
+  if (p.bias_c <= kMaxBias || p.bias == nullptr)
+    for (int i = threadIdx.x; i < min(p.bias_c, kMaxBias); i += blockDim.x)
       s.bias[i] = (p.bias != nullptr) ? p.bias[i] * p.act_gain : 0.f;
   if (warp == 1) {
     tmem_alloc(s.tmem_slot, p.tmem_cols);
@@ -788,8 +911,8 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
       if (p.demod != nullptr && !p.smem_demod) g_dm = p.demod + (long long)b * p.demod_c + t.n0 % p.demod_c;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
       // wide layers (cout > kMaxBias): bias from global memory (act == 0), or the zero table when there is none
-      const uint32_t s_bias = (p.cout <= kMaxBias) ? smem_u32(s.bias + t.n0)
-                                                   : (p.bias == nullptr ? smem_u32(s.bias + t.n0 % kMaxBias) : 0u);
+      const uint32_t s_bias = (p.bias_c <= kMaxBias) ? smem_u32(s.bias + t.n0 % p.bias_c)
+                                                     : (p.bias == nullptr ? smem_u32(s.bias + t.n0 % kMaxBias) : 0u);
       epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, y, b, t.n0, valid, gain, s_bias, s_dm,
                         g_dm, s_aux, tab_n);
       tc_fence_before();

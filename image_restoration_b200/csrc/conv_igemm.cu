@@ -11,6 +11,7 @@ extern template int launch_conv_variant<2>(const ConvParams&, int, bool, int, in
 extern template int launch_conv_variant<3>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
 extern template int launch_conv_variant<4>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
 extern template int launch_conv_variant<5>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
+extern template int launch_conv_variant<6>(const ConvParams&, int, bool, int, int, int, cudaStream_t);
 
 static int launch_conv(const ConvParams& p, bool row, int grid, int smem_bytes, int smem_max, cudaStream_t st) {
   switch (p.epi) {
@@ -20,6 +21,7 @@ static int launch_conv(const ConvParams& p, bool row, int grid, int smem_bytes, 
     case 3: return launch_conv_variant<3>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
     case 4: return launch_conv_variant<4>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
     case 5: return launch_conv_variant<5>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
+    case 6: return launch_conv_variant<6>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
     default: return launch_conv_variant<-1>(p, p.block_k, row, grid, smem_bytes, smem_max, st);
   }
 }
@@ -117,7 +119,8 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   {
     const int ps_c = d->ps_c ? d->ps_c : d->block_n;
     B200IR_REQUIRE(d->ps_r == 0 || ((d->ps_r == 2 || d->ps_r == 3) && ps_c * d->ps_r * d->ps_r == d->cout &&
-                                    ps_c % 16 == 0 && d->rgb_w == nullptr && d->res_mode == 0 && d->noise == nullptr),
+                                    ps_c % 16 == 0 && d->rgb_w == nullptr && d->noise == nullptr &&
+                                    (d->res_mode == 0 || d->corr_top != nullptr)),
                    "conv_igemm: ps_r=%d needs ps_c (or block_n) = cout / ps_r^2 and a plain epilogue", d->ps_r);
     B200IR_REQUIRE(!d->use_tap_mask || d->cout / d->block_n <= 8, "conv_igemm: tap masks cover at most 8 N-tiles");
     B200IR_REQUIRE(d->demod_c == 0 || d->demod_c == d->cout || d->demod_c % d->block_n == 0 ||
@@ -172,7 +175,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   p.smem_aux = ((d->out_scale != nullptr || d->rgb_w != nullptr) && 5 * d->tile_b * d->block_n <= kDemodTable) ? 1 : 0;
   p.st256 = (!d->out_fp32 && d->out_c_off % 16 == 0 && d->out_stride_x % 16 == 0 && d->out_stride_y % 16 == 0 &&
              d->out_stride_b % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 31) == 0) ? 1 : 0;
-  B200IR_REQUIRE(d->cout <= kMaxBias || d->bias == nullptr || !d->act,
+  B200IR_REQUIRE(d->cout <= kMaxBias || d->bias == nullptr || !d->act || (d->corr_top != nullptr && d->ps_c <= kMaxBias),
                  "conv_igemm: cout=%d > %d needs a bias vector and no activation", d->cout, kMaxBias);
   // accumulator ring depth: the epilogue latency of a tile is hidden behind the main loops of the next
   // (acc_stages - 1) tiles; small tiles (short main loops) need a deeper ring
@@ -208,11 +211,13 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   p.res_w = d->res_w; p.res_h = d->res_h; p.res_scale = d->res_scale;
   p.res_mul = d->res_mul != 0.f ? d->res_mul : d->res_scale;
   p.ps_r = d->ps_r;
+  p.corr_top = d->corr_top; p.corr_bot = d->corr_bot; p.corr_left = d->corr_left; p.corr_right = d->corr_right;
   p.ps_c = d->ps_c ? d->ps_c : d->block_n;
   p.ps_shift = -1;
   for (int sh = 0; sh < 16; ++sh)
     if ((1 << sh) == p.ps_c) p.ps_shift = sh;
   p.demod_c = d->demod_c ? d->demod_c : d->cout;
+  p.bias_c = (d->corr_top != nullptr && d->ps_c > 0) ? d->ps_c : d->cout;
   for (int t = 0; t < 8; ++t) p.tap_mask[t] = d->use_tap_mask ? d->tap_mask[t] : 0xffffffffu;
   {
     static int dbg = -1;
@@ -222,7 +227,8 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   }
   // ---- specialised epilogue selection
   {
-    const bool fp16_fast = !d->out_fp32 && (d->no_store || p.st256) && (d->cout <= kMaxBias || d->bias == nullptr) &&
+    const bool fp16_fast = !d->out_fp32 && (d->no_store || p.st256) &&
+                           (d->cout <= kMaxBias || d->bias == nullptr || (d->corr_top != nullptr && d->ps_c <= kMaxBias)) &&
                            p.block_k >= 32;
     int flags = 0;
     bool ok = fp16_fast;
@@ -233,12 +239,19 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
     if (d->rgb_w != nullptr) { flags |= F_RGB; ok = ok && p.smem_aux; }
     else if (d->out_scale != nullptr) ok = false;
     if (d->no_store) flags |= F_NOSTORE;
+    if (d->corr_top != nullptr) {
+      flags |= F_UPFOLD;
+      ok = ok && d->ps_r == 2 && p.ps_shift >= 0 && d->res_mode == 2 && d->corr_bot && d->corr_left && d->corr_right;
+    }
     p.epi = -1;
     for (int i = 0; ok && i < kNumEpiProfiles; ++i)
       if (epi_profile_flags(i) == flags) p.epi = i;
     static int force_generic = -1;
     if (force_generic < 0) force_generic = (getenv("B200IR_GENERIC_EPI") != nullptr) ? 1 : 0;
     if (force_generic) p.epi = -1;
+    B200IR_REQUIRE(d->corr_top == nullptr || p.epi == 6,
+                   "conv_igemm: the folded ConvUpLayer epilogue needs ps_r = 2, a power-of-two ps_c, res_mode = 2, fp16 "
+                   "32-byte aligned output and all four correction buffers");
     p.slope = d->act == 1 ? 0.2f : (d->act == 2 ? d->act_slope : 1.f);
     if (p.epi >= 0 && d->res_mode != 0) p.act_gain *= d->res_scale;
   }

@@ -97,6 +97,48 @@ __global__ void image_to_u8_kernel(const float* __restrict__ x, uint8_t* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------ folded ConvUpLayer helpers
+// Replicate padding of an NHWC fp16 buffer [B][h+2][w+2][C] whose interior has been written: the ring takes the nearest
+// interior pixel (the clamped indices of F.interpolate(..., align_corners=False), gfpganv1_ocr_arch.py:190).
+__global__ void replicate_border_kernel(__half* __restrict__ t, int B, int h, int w, int C) {
+  const int cg = C >> 3;
+  const int ring = 2 * (w + 2) + 2 * h;  // top row, bottom row, left / right columns of the interior rows
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * ring * cg) return;
+  const int g = (int)(idx % cg);
+  long long r = idx / cg;
+  const int q = (int)(r % ring);
+  const int b = (int)(r / ring);
+  int Y, X;
+  if (q < w + 2) { Y = 0; X = q; }
+  else if (q < 2 * (w + 2)) { Y = h + 1; X = q - (w + 2); }
+  else { const int k = q - 2 * (w + 2); Y = 1 + (k >> 1); X = (k & 1) ? w + 1 : 0; }
+  const int ys = min(max(Y, 1), h), xs = min(max(X, 1), w);
+  __half* base = t + (long long)b * (h + 2) * (w + 2) * C + g * 8;
+  *reinterpret_cast<uint4*>(base + ((long long)Y * (w + 2) + X) * C) =
+      *reinterpret_cast<const uint4*>(base + ((long long)ys * (w + 2) + xs) * C);
+}
+
+// Corner add-back of the folded ConvUpLayer correction: the row and the column surplus both contain the term of the
+// corner tap, so top[b][0] -= W[0][0] t[b,0,0], top[b][OW-1] -= W[0][2] t[b,0,w-1], bot[b][0] -= W[2][0] t[b,h-1,0],
+// bot[b][OW-1] -= W[2][2] t[b,h-1,w-1].  wc fp32 [4][cout][cin]; tp = the replicate-padded input [B][h+2][w+2][cin].
+__global__ void upfold_corner_kernel(const __half* __restrict__ tp, const float* __restrict__ wc, float* __restrict__ top,
+                                     float* __restrict__ bot, int h, int w, int cin, int cout) {
+  // block = (image, corner); one warp per output channel (lanes stride over cin: coalesced weight rows)
+  const int b = blockIdx.x, corner = blockIdx.y;
+  const int Y = (corner & 2) ? h : 1, X = (corner & 1) ? w : 1;
+  const __half* tv = tp + (((long long)b * (h + 2) + Y) * (w + 2) + X) * cin;
+  float* dst = ((corner & 2) ? bot : top) + ((long long)b * 2 * w + ((corner & 1) ? 2 * w - 1 : 0)) * cout;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int co = warp; co < cout; co += nwarps) {
+    const float* wr = wc + ((long long)corner * cout + co) * cin;
+    float acc = 0.f;
+    for (int ci = lane; ci < cin; ci += 32) acc = fmaf(__ldg(wr + ci), __half2float(tv[ci]), acc);
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) dst[co] -= acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ tiled full-frame inference
 // BASELINE config 4: a frame is cut into overlapping T x T tiles (positions ty[], tx[]), the tiles go through the network
 // as one batch, and are blended back with separable linear-ramp weights (weight 1 on the frame border side of a border
@@ -686,6 +728,20 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
   first_conv_kernel<<<grid_for(n), kPwThreads, cout * 4 * sizeof(float), STREAM>>>(x, w, bias, (__half*)out, B, H * W,
                                                                                   cout);
   return check_launch("first_conv");
+}
+
+extern "C" int b200ir_replicate_border(void* t, int B, int h, int w, int C, void* stream) {
+  B200IR_REQUIRE(t && C % 8 == 0 && h > 0 && w > 0, "replicate_border: bad arguments");
+  const long long n = (long long)B * (2 * (w + 2) + 2 * h) * (C / 8);
+  replicate_border_kernel<<<grid_for(n), kPwThreads, 0, STREAM>>>((__half*)t, B, h, w, C);
+  return check_launch("replicate_border");
+}
+
+extern "C" int b200ir_upfold_corners(const void* tp, const float* wc, float* top, float* bot, int B, int h, int w, int cin,
+                                     int cout, void* stream) {
+  B200IR_REQUIRE(tp && wc && top && bot && B > 0, "upfold_corners: bad arguments");
+  upfold_corner_kernel<<<dim3(B, 4), 256, 0, STREAM>>>((const __half*)tp, wc, top, bot, h, w, cin, cout);
+  return check_launch("upfold_corners");
 }
 
 extern "C" int b200ir_tiles_gather(const float* frame, float* tiles, int C, int H, int W, int T, const int32_t* ty,

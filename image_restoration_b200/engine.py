@@ -73,6 +73,8 @@ class _Packed:
             self.up.append(dict(
                 w1=eq(f'{p}.conv1.0.weight'), b1=f32(f'{p}.conv1.1.bias'),
                 w2=eq(f'{p}.conv2.weight'), b2=f32(f'{p}.conv2.activation.bias'), ws=eq(f'{p}.skip.weight'),
+                w2_fold=ops.upfold_weights(g(f'{p}.conv2.weight').float(),
+                                           1.0 / math.sqrt(g(f'{p}.conv2.weight').shape[1] * 9)),
                 wh0=torch.cat([eq(f'{cs}.0.weight'), eq(f'{ch}.0.weight')], 0).contiguous(),
                 bh0=torch.cat([f32(f'{cs}.0.bias'), f32(f'{ch}.0.bias')]).contiguous(),
                 wsc=eq(f'{cs}.2.weight'), bsc=f32(f'{cs}.2.bias'), wsh=eq(f'{ch}.2.weight'), bsh=f32(f'{ch}.2.bias'),
@@ -236,21 +238,48 @@ class _Plan:
             a = e16(B, h, w, cin)
             steps.append(PwOp('add', lambda x=feat, y=skips[i], o=a: ops.add(x, y, o), feat, skips[i], a))
             steps.rec(f'up_a{i}')
-            t1 = e16(B, h, w, cin)
-            steps.append(ops.conv_same(a, d['w1'], t1, 3, bias=d['b1'], act=True))
-            u = e16(B, 2 * h, 2 * w, cin)
-            steps.append(PwOp('bilinear_up2', lambda x=t1, o=u: ops.bilinear_up2(x, o), t1, u))
+            # folding pays where the plain conv would run N = cout <= 64 MMAs in the generic kernel (256 -> 64 @64x192:
+            # 442 us with the bilinear kernel -> 254 us); wide layers gain nothing from N = 4*cout and the 64 -> 32 layer
+            # is faster in the row-sliding kernel (weights resident), see tools/time_ops.py
+            fold = (eng.upfold and cin % 64 == 0 and cin >= 128 and cout % 16 == 0 and (cout & (cout - 1)) == 0 and
+                    4 * cout <= 256)
+            if fold:
+                # ConvUpLayer folded (ops.UpFoldConv): conv1 writes into the interior of a replicate-padded buffer, the
+                # up-sampled tensor is never materialised, conv2 runs over the low-resolution input with N = 4*cout
+                tp = e16(B, h + 2, w + 2, cin)
+                steps.append(ops.ConvOp([ops.nhwc_view(a)], d['w1'], cin, cin, ops.taps_3x3(), (w, h, B), tp[:, 1:, 1:, :],
+                                        (cin, (w + 2) * cin, (h + 2) * (w + 2) * cin), bias=d['b1'], act=True))
+            else:
+                t1 = e16(B, h, w, cin)
+                steps.append(ops.conv_same(a, d['w1'], t1, 3, bias=d['b1'], act=True))
+                u = e16(B, 2 * h, 2 * w, cin)
+                steps.append(PwOp('bilinear_up2', lambda x=t1, o=u: ops.bilinear_up2(x, o), t1, u))
             sl = e16(B, h, w, cout)
             steps.lane = 2
             steps.wait(f'up_a{i}')
             steps.append(ops.conv_same(a, d['ws'], sl, 1))
             steps.rec(f'up_sl{i}')
             steps.lane = 0
-            steps.wait(f'up_sl{i}')
             h2, w2 = 2 * h, 2 * w
             feat = e16(B, h2, w2, cout)
-            steps.append(ops.conv_same(u, d['w2'], feat, 3, bias=d['b2'], act=True, res=sl, res_mode=2,
-                                       res_strides=(cout, w * cout, h * w * cout), res_wh=(w, h), res_scale=inv))
+            if fold:
+                uf = ops.UpFoldConv(tp, d['w2_fold'], d['b2'], feat, sl, inv)
+                steps.append(PwOp('replicate_border', uf.pad, tp[:, 0]))
+                steps.rec(f'up_tp{i}')
+                steps.lane = 2                      # the four border GEMMs + corner fix run beside the main conv's start
+                steps.wait(f'up_tp{i}')
+                for bop in uf.border_ops:
+                    steps.append(bop)
+                steps.append(PwOp('upfold_corners', uf.corners))
+                steps.rec(f'up_corr{i}')
+                steps.lane = 0
+                steps.wait(f'up_sl{i}')
+                steps.wait(f'up_corr{i}')
+                steps.append(uf.main)
+            else:
+                steps.wait(f'up_sl{i}')
+                steps.append(ops.conv_same(u, d['w2'], feat, 3, bias=d['b2'], act=True, res=sl, res_mode=2,
+                                           res_strides=(cout, w * cout, h * w * cout), res_wh=(w, h), res_scale=inv))
             hid = e16(B, h2, w2, 2 * cout)
             steps.append(ops.conv_same(feat, d['wh0'], hid, 3, bias=d['bh0'], act=True))
             c_sft = d['wsc'].shape[0]
@@ -449,6 +478,7 @@ class OcrEngine:
         self.use_graphs = True
         import os
         self.convt_merged = os.environ.get('B200IR_CONVT_MERGED', '1') != '0'
+        self.upfold = os.environ.get('B200IR_UPFOLD', '1') != '0'
 
     def _signature(self):
         ps = list(self.net.parameters()) + list(self.net.buffers())

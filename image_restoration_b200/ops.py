@@ -65,7 +65,7 @@ class ConvOp:
                  out_mul_off=(1, 0, 1, 0), bias=None, demod=None, noise=None, noise_gain=None, noise_strides=(0, 0),
                  act=False, res=None, res_mode=0, res_strides=(0, 0, 0), res_wh=(0, 0), res_scale=1.0, block_n=None,
                  tile=None, max_ctas=0, row_mode=0, out_scale=None, rgb_w=None, rgb_part=None, rgb_hw=(0, 0),
-                 no_store=False, act_slope=None, res_mul=0.0, ps_r=0, ps_c=0, demod_c=0, tap_mask=None):
+                 no_store=False, act_slope=None, res_mul=0.0, ps_r=0, ps_c=0, demod_c=0, tap_mask=None, corr=None):
         d = ConvDesc()
         assert 1 <= len(views) <= _lib.MAX_VIEWS and 1 <= len(taps) <= _lib.MAX_TAPS
         for i, v in enumerate(views):
@@ -96,6 +96,11 @@ class ConvOp:
         d.res_mul = res_mul
         d.ps_r = ps_r
         d.ps_c, d.demod_c = ps_c, demod_c
+        if corr is not None:        # (top, bottom, left, right) fp32 correction buffers of the folded ConvUpLayer
+            for name, t in zip(('corr_top', 'corr_bot', 'corr_left', 'corr_right'), corr):
+                _req(t, torch.float32, name)
+                setattr(d, name, t.data_ptr())
+            self._keep_corr = corr
         if tap_mask is not None:
             assert len(tap_mask) <= 8
             d.use_tap_mask = 1
@@ -251,6 +256,73 @@ def convt_s2_merged(x, w_big, raw, demod):
     tile = pick_tile(w + 1, h + 1, b, min_w=8, max_b=max(1, 2560 // bn))
     return ConvOp([nhwc_view(x)], w_big, cin, 4 * cout, taps, (w + 1, h + 1, b), raw, (cout, rw * cout, rh * rw * cout),
                   demod=demod, block_n=bn, tile=tile, ps_r=2, ps_c=cout, demod_c=cout, tap_mask=masks)
+
+
+# ------------------------------------------------------------------------------------------ folded ConvUpLayer
+_BILIN = ((.75, .25, 0.), (.25, .75, 0.), (0., .75, .25), (0., .25, .75))   # A[r + 1][dy + 1]: weight of t[i + dy] in up(2i + r)
+
+
+def upfold_weights(w, scale):
+    """ConvUpLayer (gfpganv1_ocr_arch.py:188-202) folded: conv3x3(bilinear_up2(t)) == for every output phase (py, px) a 3x3
+    conv over the replicate-padded low-resolution t with  Wp = sum_{kh,kw} W[kh,kw] A[py+kh][dy] A[px+kw][dx].
+    w (cout, cin, 3, 3) fp32 ->  dict(main fp16 [4*cout][9*cin] (phase-major rows, taps (dy, dx) row-major),
+    top / bot fp16 [2*cout][3*cin], left / right fp16 [2*cout][3*cin] (1-D surplus convs of the border ring),
+    corners fp32 [4][cout][cin])."""
+    A = torch.tensor(_BILIN, dtype=torch.float32, device=w.device)
+    w = w.float() * scale
+    cout, cin = w.shape[:2]
+    Ay = torch.stack([A[py:py + 3] for py in range(2)])                 # [py][kh][dy]
+    wp = torch.einsum('oikl,pkd,qle->pqodei', w, Ay, Ay)                # [py][px][co][dy][dx][ci]
+    row = lambda kh: torch.einsum('oil,qle->qoei', w[:, :, kh, :], Ay)  # noqa: E731  [px][co][dx][ci]
+    col = lambda kw: torch.einsum('oik,pkd->podi', w[:, :, :, kw], Ay)  # noqa: E731  [py][co][dy][ci]
+    f16 = lambda t, rows: t.reshape(rows, -1).contiguous().to(torch.float16)  # noqa: E731
+    return dict(main=f16(wp, 4 * cout), top=f16(row(0), 2 * cout), bot=f16(row(2), 2 * cout), left=f16(col(0), 2 * cout),
+                right=f16(col(2), 2 * cout),
+                corners=torch.stack([w[:, :, 0, 0], w[:, :, 0, 2], w[:, :, 2, 0], w[:, :, 2, 2]]).contiguous())
+
+
+class UpFoldConv:
+    """Prepared launches of one folded ConvUpLayer + ResUpBlock merge: tp [B, h+2, w+2, cin] is the replicate-padded
+    low-resolution input (interior written by the producer), out [B, 2h, 2w, cout]."""
+
+    def __init__(self, tp, fw, bias, out, res, res_scale):
+        b, hp, wp_, cin = tp.shape
+        h, w = hp - 2, wp_ - 2
+        cout = out.shape[3]
+        dev = tp.device
+        self.tp, self.h, self.w, self.cin, self.cout, self.fw = tp, h, w, cin, cout, fw
+        e32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        self.top, self.bot = e32(b, 2 * w, cout), e32(b, 2 * w, cout)
+        self.left, self.right = e32(b, 2 * h, cout), e32(b, 2 * h, cout)
+        sb, sy = hp * wp_ * cin, wp_ * cin
+        base = tp.data_ptr()
+        taps3 = [(0, d, 0) for d in range(3)]
+
+        def border(ptr, n, stride_n, wgt, dst):
+            v = View(ptr, cin, n + 2, 1, b, stride_n, sb, sb)
+            return ConvOp([v], wgt, cin, 2 * cout, taps3, (n, 1, b), dst, (2 * cout, n * 2 * cout, n * 2 * cout),
+                          out_fp32=True)
+        self.border_ops = [border(base + 2 * (1 * sy), w, cin, fw['top'], self.top),             # row t[0]
+                           border(base + 2 * (h * sy), w, cin, fw['bot'], self.bot),             # row t[h-1]
+                           border(base + 2 * (1 * cin), h, sy, fw['left'], self.left),           # column t[:, 0]
+                           border(base + 2 * (w * cin), h, sy, fw['right'], self.right)]         # column t[:, w-1]
+        taps9 = [(0, dx, dy) for dy in range(3) for dx in range(3)]
+        view = View(base, cin, wp_, hp, b, cin, sy, sb)
+        cr = res.shape[3]
+        self.main = ConvOp([view], fw['main'], cin, 4 * cout, taps9, (w, h, b), out,
+                           (cout, 2 * w * cout, 4 * h * w * cout), bias=bias, act=True, res=res, res_mode=2,
+                           res_strides=(cr, w * cr, h * w * cr), res_wh=(w, h), res_scale=res_scale,
+                           block_n=min(256, 4 * cout), ps_r=2, ps_c=cout,
+                           corr=(self.top, self.bot, self.left, self.right))
+
+    def pad(self):
+        check(_lib.lib().b200ir_replicate_border(_ptr(self.tp), self.tp.shape[0], self.h, self.w, self.cin, _stream()),
+              'replicate_border')
+
+    def corners(self):
+        check(_lib.lib().b200ir_upfold_corners(_ptr(self.tp), _ptr(self.fw['corners']), _ptr(self.top), _ptr(self.bot),
+                                               self.tp.shape[0], self.h, self.w, self.cin, self.cout, _stream()),
+              'upfold_corners')
 
 
 def linear_as_conv(x2d, weight, out, **kw):

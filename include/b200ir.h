@@ -131,6 +131,14 @@ typedef struct {
    * use_tap_mask: N-tile t executes only the taps in tap_mask[t] (its weight block for the others is all zero). */
   int32_t ps_c, demod_c, use_tap_mask;
   uint32_t tap_mask[8];
+  /* ConvUpLayer folded (bilinear x2 + 3x3 conv as one conv over the low-resolution, replicate-padded input; phases =
+   * column blocks, ps_r = 2, res_mode = 2): surplus of the folded form on the outermost output ring, subtracted from
+   * the accumulator before bias / activation.  fp32, [m_b][2*m_w][ps_c] (top / bottom rows) and [m_b][2*m_h][ps_c]
+   * (left / right columns), corner terms already folded into top / bottom.  All four or none. */
+  const float* corr_top;
+  const float* corr_bot;
+  const float* corr_left;
+  const float* corr_right;
 } b200ir_conv_desc;
 
 int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
@@ -152,6 +160,14 @@ int b200ir_first_conv(const float* x, const float* w, const float* bias, void* o
  *                to even, uint8 HWC.  swap_rb != 0 reverses the channel order (BGR images, as cv2 delivers them). */
 int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, int W, int swap_rb, void* stream);
 int b200ir_image_to_u8(const float* x, uint8_t* img, int B, int H, int W, int swap_rb, void* stream);
+
+/* Helpers of the folded ConvUpLayer (b200ir_conv_desc.corr_*): replicate_border fills the one-pixel ring of an NHWC fp16
+ * buffer [B][h+2][w+2][C] from its interior (the clamp of F.interpolate(..., 'bilinear'), gfpganv1_ocr_arch.py:190);
+ * upfold_corners removes the doubly counted corner taps from the top / bottom correction rows (wc fp32 [4][cout][cin] =
+ * W[:, :, 0, 0], W[:, :, 0, 2], W[:, :, 2, 0], W[:, :, 2, 2] of the 3x3 conv; top / bot fp32 [B][2w][cout]). */
+int b200ir_replicate_border(void* t, int B, int h, int w, int C, void* stream);
+int b200ir_upfold_corners(const void* tp, const float* wc, float* top, float* bot, int B, int h, int w, int cin, int cout,
+                          void* stream);
 
 /* Tiled full-frame inference (BASELINE config 4; the reference has no tiling code -- api_plate_oto.py:376-401 resizes
  * the whole image -- so the contract is this header): frame fp32 [C][H][W]; tiles fp32 [nty*ntx][C][T][T] at rows ty[]

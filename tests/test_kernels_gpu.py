@@ -495,3 +495,37 @@ def test_resamplers_streaming(B, H, W, C):
     torch.cuda.synchronize()
     check_close(nchw32(up), F.interpolate(nchw32(xh), scale_factor=2, mode='bilinear', align_corners=False),
                 what=f'bilinear_up2 C={C} {H}x{W}')
+
+
+@pytest.mark.parametrize('B,h,w,cin,cout', [(2, 8, 24, 256, 256), (2, 32, 96, 256, 64), (1, 64, 192, 64, 32),
+                                            (3, 5, 7, 64, 64), (2, 4, 12, 256, 256)])
+def test_conv_up_layer_folded(B, h, w, cin, cout):
+    """ResUpBlock tail with the ConvUpLayer folded (ops.UpFoldConv): one conv over the replicate-padded low-resolution
+    input with the four output phases as column blocks + border-ring corrections ==
+    (lrelu(conv3x3(F.interpolate(t, 2, bilinear)) + b) * sqrt2 + F.interpolate(skip, 2, bilinear)) / sqrt2."""
+    ops = _ops()
+    torch.manual_seed(17)
+    t = torch.randn(B, cin, h, w, device=DEV)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV)
+    scale = 1 / math.sqrt(cin * 9)
+    bias = torch.randn(cout, device=DEV) * 0.2
+    sl = nhwc16(torch.randn(B, cout, h, w, device=DEV))
+    th = nhwc16(t)
+    tp = torch.zeros(B, h + 2, w + 2, cin, device=DEV, dtype=torch.float16)
+    tp[:, 1:-1, 1:-1] = th
+    out = torch.empty(B, 2 * h, 2 * w, cout, device=DEV, dtype=torch.float16)
+    uf = ops.UpFoldConv(tp, ops.upfold_weights(wt, scale), bias, out, sl, 1 / math.sqrt(2))
+    uf.pad()
+    for op in uf.border_ops:
+        op()
+    uf.corners()
+    uf.main()
+    torch.cuda.synchronize()
+    up = lambda z: F.interpolate(z, scale_factor=2, mode='bilinear', align_corners=False)   # noqa: E731
+    y = F.conv2d(up(nchw32(th)), (wt * scale).half().float(), bias, padding=1)
+    ref = (F.leaky_relu(y, 0.2) * math.sqrt(2) + up(nchw32(sl))) / math.sqrt(2)
+    got = nchw32(out)
+    err_in = (got - ref)[:, :, 1:-1, 1:-1].abs().max().item() if h > 1 else 0.0
+    err = (got - ref).abs().max().item()
+    print(f'folded ConvUpLayer {cin}->{cout} {h}x{w}: interior {err_in:.3e} full {err:.3e} scale {ref.abs().max().item():.2f}')
+    assert err <= 1.5e-2 * ref.abs().max().item()
