@@ -41,6 +41,8 @@ struct alignas(64) ConvParams {
   int block_n, block_k, k_chunks, num_taps;
   int m_w, m_h, m_b;
   int stages;
+  int b_resident;  // generic kernel: all weight tiles (num_taps * k_chunks of block_n rows) stay in shared memory, the
+                   // stage ring carries activations only (single N-tile layers whose weights fit next to >= 3 stages)
   uint32_t idesc;
   uint32_t idesc_n[3];  // row mode: instruction descriptors for N = 1, 2, 3 x block_n
   uint32_t tmem_cols;
@@ -777,8 +779,10 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
   constexpr uint32_t a_bytes = kBlockM * row_bytes;
   constexpr int k_steps = kBlockK / 16;
   const uint32_t b_bytes = p.block_n * row_bytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  const KernelSmem s = carve_smem(smem_raw, p.stages * stage_bytes);
+  const uint32_t stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
+  const uint32_t w_bytes = p.b_resident ? p.num_taps * p.k_chunks * b_bytes : 0u;  // resident weights sit in front
+  const KernelSmem s = carve_smem(smem_raw, w_bytes + p.stages * stage_bytes);
+  uint8_t* const ring = s.base + w_bytes;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t tmem_base = kernel_prologue(p, s, p.stages, warp);
@@ -787,7 +791,13 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
     if (lane == 0) {
       for (int v = 0; v < B200IR_MAX_VIEWS; ++v) tma_prefetch_desc(&p.tmap_a[v]);
       tma_prefetch_desc(&p.tmap_b);
+      if (p.b_resident) {  // one N-tile: every CTA needs the same weights for every tile, load them once
+        mbar_arrive_expect_tx(s.w_bar, w_bytes);
+        for (int kb = 0; kb < p.num_taps * p.k_chunks; ++kb)
+          tma_load_2d(s.base + kb * b_bytes, &p.tmap_b, s.w_bar, kb * kBlockK, 0);
+      }
     }
+    __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -805,10 +815,10 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
         for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
           mbar_wait(&s.empty_bar[stage], phase ^ 1u);
           if (elect_one()) {
-            uint8_t* sa = s.base + stage * stage_bytes;
+            uint8_t* sa = ring + stage * stage_bytes;
             mbar_arrive_expect_tx(&s.full_bar[stage], stage_bytes);
             tma_load_4d(sa, &p.tmap_a[view], &s.full_bar[stage], kc * kBlockK, cx, cy, t.b0);
-            tma_load_2d(sa + a_bytes, &p.tmap_b, &s.full_bar[stage], kb * kBlockK, t.n0);
+            if (!p.b_resident) tma_load_2d(sa + a_bytes, &p.tmap_b, &s.full_bar[stage], kb * kBlockK, t.n0);
           }
           __syncwarp();
           if (++stage == p.stages) {
@@ -821,8 +831,13 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
   } else if (warp == 1) {
     // ---------------- MMA issuer
     const uint32_t hi = desc_hi_word(row_bytes);
-    const uint32_t base_lo = smem_u32(s.base) >> 4;
+    const uint32_t base_lo = smem_u32(ring) >> 4;
+    const uint32_t w_lo = smem_u32(s.base) >> 4;
     const uint32_t stage_lo = stage_bytes >> 4;
+    if (p.b_resident) {
+      mbar_wait(s.w_bar, 0);
+      tc_fence_after();
+    }
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -837,7 +852,8 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_lo = base_lo + stage * stage_lo;
-          const uint32_t b_lo = a_lo + (a_bytes >> 4);
+          // resident weights: every tap is executed (no tap mask), so the k-block index is the running kb
+          const uint32_t b_lo = p.b_resident ? w_lo + kb * (b_bytes >> 4) : a_lo + (a_bytes >> 4);
 #pragma unroll
           for (int k = 0; k < k_steps; ++k)
             umma_f16(tmem_d, desc64(a_lo + 2 * k, hi), desc64(b_lo + 2 * k, hi), p.idesc, (k > 0 || kb > 0) ? 1u : 0u);

@@ -196,8 +196,23 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   int stages = (g_smem_optin - 1024 - tail) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   B200IR_REQUIRE(stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
+  int smem_bytes = stages * stage_bytes + tail + 1024;
+  {
+    // weights resident in shared memory: single N-tile layers re-read the same weight tiles for every M-tile
+    // (folded ConvUpLayer 64 -> 4x32: 147 KB of weights per 144 KB of activations, measured L2-bound); keep them
+    // when at least three activation stages still fit
+    const int a_bytes = kBlockM * row_bytes;
+    const int w_bytes = d->num_taps * p.k_chunks * d->block_n * row_bytes;
+    const int st_res = (g_smem_optin - 1024 - tail - w_bytes) / a_bytes;
+    static int no_res = -1;
+    if (no_res < 0) no_res = (getenv("B200IR_NO_RESIDENT") != nullptr) ? 1 : 0;
+    if (!no_res && d->block_n == d->cout && !d->use_tap_mask && st_res >= 3 && d->num_taps * p.k_chunks >= 2) {
+      p.b_resident = 1;
+      stages = st_res > kMaxStages ? kMaxStages : st_res;
+      smem_bytes = w_bytes + stages * a_bytes + tail + 1024;
+    }
+  }
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + tail + 1024;
 
   p.out = d->out; p.out_fp32 = d->out_fp32;
   p.out_sx = d->out_stride_x; p.out_sy = d->out_stride_y; p.out_sb = d->out_stride_b;

@@ -242,7 +242,7 @@ class _Plan:
             # 442 us with the bilinear kernel -> 254 us); wide layers gain nothing from N = 4*cout and the 64 -> 32 layer
             # is faster in the row-sliding kernel (weights resident), see tools/time_ops.py
             fold = (eng.upfold and cin % 64 == 0 and cin >= 128 and cout % 16 == 0 and (cout & (cout - 1)) == 0 and
-                    4 * cout <= 256)
+                    4 * cout <= 256) or (eng.upfold_all and cin % 64 == 0 and (cout & (cout - 1)) == 0 and cout >= 16)
             if fold:
                 # ConvUpLayer folded (ops.UpFoldConv): conv1 writes into the interior of a replicate-padded buffer, the
                 # up-sampled tensor is never materialised, conv2 runs over the low-resolution input with N = 4*cout
@@ -479,6 +479,7 @@ class OcrEngine:
         import os
         self.convt_merged = os.environ.get('B200IR_CONVT_MERGED', '1') != '0'
         self.upfold = os.environ.get('B200IR_UPFOLD', '1') != '0'
+        self.upfold_all = os.environ.get('B200IR_UPFOLD', '1') == '2'     # experiment: fold every ConvUpLayer
 
     def _signature(self):
         ps = list(self.net.parameters()) + list(self.net.buffers())
