@@ -268,17 +268,18 @@ def upfold_weights(w, scale):
     w (cout, cin, 3, 3) fp32 ->  dict(main fp16 [4*cout][9*cin] (phase-major rows, taps (dy, dx) row-major),
     top / bot fp16 [2*cout][3*cin], left / right fp16 [2*cout][3*cin] (1-D surplus convs of the border ring),
     corners fp32 [4][cout][cin])."""
-    A = torch.tensor(_BILIN, dtype=torch.float32, device=w.device)
-    w = w.float() * scale
+    dev = w.device
+    A = torch.tensor(_BILIN, dtype=torch.float32)
+    w = w.detach().float().cpu() * scale      # one-time host-side packing (no device GEMMs on behalf of weight prep)
     cout, cin = w.shape[:2]
     Ay = torch.stack([A[py:py + 3] for py in range(2)])                 # [py][kh][dy]
     wp = torch.einsum('oikl,pkd,qle->pqodei', w, Ay, Ay)                # [py][px][co][dy][dx][ci]
     row = lambda kh: torch.einsum('oil,qle->qoei', w[:, :, kh, :], Ay)  # noqa: E731  [px][co][dx][ci]
     col = lambda kw: torch.einsum('oik,pkd->podi', w[:, :, :, kw], Ay)  # noqa: E731  [py][co][dy][ci]
-    f16 = lambda t, rows: t.reshape(rows, -1).contiguous().to(torch.float16)  # noqa: E731
+    f16 = lambda t, rows: t.reshape(rows, -1).contiguous().to(torch.float16).to(dev)  # noqa: E731
     return dict(main=f16(wp, 4 * cout), top=f16(row(0), 2 * cout), bot=f16(row(2), 2 * cout), left=f16(col(0), 2 * cout),
                 right=f16(col(2), 2 * cout),
-                corners=torch.stack([w[:, :, 0, 0], w[:, :, 0, 2], w[:, :, 2, 0], w[:, :, 2, 2]]).contiguous())
+                corners=torch.stack([w[:, :, 0, 0], w[:, :, 0, 2], w[:, :, 2, 0], w[:, :, 2, 2]]).contiguous().to(dev))
 
 
 class UpFoldConv:
