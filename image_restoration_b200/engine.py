@@ -514,6 +514,14 @@ class OcrEngine:
         elif tuple(x.shape[1:]) != (3, net.input_height, net.input_width):
             raise ValueError(f'expected input (B,3,{net.input_height},{net.input_width}), got {tuple(x.shape)}')
         dev = self.packed.dev
+        if B == 0:                                       # empty batch: nothing to launch (as nn.Module layers return empties)
+            H, W = net.input_height, net.input_width
+            if uint8_io:
+                return torch.empty(0, H, W, 3, device=dev, dtype=torch.uint8), []
+            L = self.packed.L
+            rgbs = [torch.empty(0, 3, 8 * 2 ** i, 8 * 2 ** i * int(W / H), device=dev, dtype=x.dtype) for i in range(L)] \
+                if return_rgb else []
+            return torch.empty(0, 3, H, W, device=dev, dtype=x.dtype), rgbs
         with torch.cuda.device(dev):
             plan = self.plan(B)
             if uint8_io:

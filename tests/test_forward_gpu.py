@@ -277,3 +277,21 @@ def test_save_and_load_feat_path(tmp_path):
     got = net(x2.cuda(), return_rgb=False, randomize_noise=False, load_feat_path=f1)[0].cpu()
     a, b = go.to01(got), go.to01(ref)
     assert (a - b).abs().max().item() <= 2e-2 and go.psnr01(a, b) >= 45.0
+
+
+def test_empty_and_large_batches():
+    """Edge cases of the batch dimension: an empty batch returns empty tensors of the right shapes; batch 256 (BASELINE
+    config 5's per-GPU batch: the largest index ranges, 805 M activation elements per tensor) equals the same crops
+    run in four batches of 64 bit for bit."""
+    from image_restoration_b200 import GFPGANv1OCR
+    torch.manual_seed(11)
+    kw = dict(input_width=384, input_height=128, num_style_feat=256, channel_multiplier=0.5, num_mlp=4,
+              input_is_latent=True, different_w=True, narrow=1, sft_half=True)
+    net = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **kw).eval().cuda()
+    y0, rgbs0 = net(torch.empty(0, 3, 128, 384, device='cuda'), return_rgb=True, randomize_noise=False)
+    assert y0.shape == (0, 3, 128, 384) and [tuple(r.shape) for r in rgbs0] == [(0, 3, 8 * 2 ** i, 24 * 2 ** i) for i in range(5)]
+    x = (torch.rand(256, 3, 128, 384) * 2 - 1).cuda()
+    big = net(x, return_rgb=False, randomize_noise=False)[0]
+    assert torch.isfinite(big).all()
+    parts = torch.cat([net(x[i:i + 64], return_rgb=False, randomize_noise=False)[0] for i in range(0, 256, 64)])
+    assert torch.equal(big, parts)
