@@ -21,19 +21,29 @@ struct ResizeAxis {
   float w0, w1;
 };
 
+// one non-zero blur tap in scipy's accumulation order: source offset (dy, dx) and weight
+struct NzTap {
+  short dy, dx;
+  float w;
+};
+
 // shared-memory layout (every region 16-byte aligned):
-//   taps | row taps (lr_hmax) | col taps (lr_wmax) | LR image (lh*lw*3 f32) | sampled blur (2lh*2lw*3 u8) | [GT u8]
+//   non-zero taps (kmax^2) | row taps (lr_hmax) | col taps (lr_wmax) | up-resize row taps (H) | up-resize col taps (W) |
+//   sampled blur (2lh*2lw*3 u8) | GT u8, later reused for the LR image (lh*lw*3 f32): the GT crop is dead once the
+//   blur samples exist
 struct DegLayout {
-  size_t row, col, lr, samp, gt;
+  size_t row, col, urow, ucol, lr, samp, gt;
 };
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-__host__ __device__ inline DegLayout deg_layout(int kmax, int lr_wmax, int lr_hmax) {
+__host__ __device__ inline DegLayout deg_layout(int kmax, int lr_wmax, int lr_hmax, int H, int W) {
   DegLayout l;
-  l.row = align16((size_t)kmax * kmax * 4);
+  l.row = align16((size_t)kmax * kmax * sizeof(NzTap));
   l.col = l.row + (size_t)lr_hmax * sizeof(ResizeAxis);
-  l.lr = l.col + (size_t)lr_wmax * sizeof(ResizeAxis);
-  l.samp = align16(l.lr + (size_t)lr_hmax * lr_wmax * 3 * 4);
+  l.urow = l.col + (size_t)lr_wmax * sizeof(ResizeAxis);
+  l.ucol = l.urow + (size_t)H * sizeof(ResizeAxis);
+  l.samp = align16(l.ucol + (size_t)W * sizeof(ResizeAxis));
   l.gt = align16(l.samp + (size_t)2 * lr_hmax * 2 * lr_wmax * 3);
+  l.lr = l.gt;  // aliases the staged GT crop
   return l;
 }
 
@@ -85,28 +95,77 @@ __device__ __forceinline__ uint8_t trunc_u8(float s) {
   return (uint8_t)s;  // truncation toward zero, as ndarray.astype(uint8)
 }
 
+// Blur of the three channels of one sample from the compacted tap list (same (i, j)-ascending fp32 accumulation order as
+// scipy.signal.convolve2d; a product and an add per tap, not fused).  kInterior: the whole footprint lies inside the image.
+template <bool kInterior>
+__device__ __forceinline__ void blur3(const uint8_t* __restrict__ img, int H, int W, int y, int x,
+                                      const NzTap* __restrict__ nz, int n_nz, float (&s)[3]) {
+  s[0] = s[1] = s[2] = 0.f;
+  for (int k = 0; k < n_nz; ++k) {
+    const NzTap t = nz[k];
+    const int iy = y + t.dy, ix = x + t.dx;
+    float v0 = 255.f, v1 = 255.f, v2 = 255.f;  // fillvalue outside the image
+    if (kInterior || (iy >= 0 && iy < H && ix >= 0 && ix < W)) {
+      const uint8_t* px = img + (iy * W + ix) * 3;
+      v0 = (float)px[0];
+      v1 = (float)px[1];
+      v2 = (float)px[2];
+    }
+    s[0] = __fadd_rn(s[0], __fmul_rn(t.w, v0));
+    s[1] = __fadd_rn(s[1], __fmul_rn(t.w, v1));
+    s[2] = __fadd_rn(s[2], __fmul_rn(t.w, v2));
+  }
+}
+
 template <bool kStage>
 __global__ void __launch_bounds__(kDegThreads, 1)
 degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_all, const int* __restrict__ ksize,
                int kmax, const int* __restrict__ lr_w, const int* __restrict__ lr_h, const float* __restrict__ noise,
                int lr_wmax, int lr_hmax, float* __restrict__ out, int H, int W, int bgr2rgb) {
   extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_nnz;
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int lw = lr_w[b], lh = lr_h[b];
   const int ksz = ksize[b];
-  const DegLayout lay = deg_layout(kmax, lr_wmax, lr_hmax);
-  float* s_taps = reinterpret_cast<float*>(smem);
+  const DegLayout lay = deg_layout(kmax, lr_wmax, lr_hmax, H, W);
+  NzTap* s_nz = reinterpret_cast<NzTap*>(smem);
   ResizeAxis* s_row = reinterpret_cast<ResizeAxis*>(smem + lay.row);
   ResizeAxis* s_col = reinterpret_cast<ResizeAxis*>(smem + lay.col);
+  ResizeAxis* s_urow = reinterpret_cast<ResizeAxis*>(smem + lay.urow);
+  ResizeAxis* s_ucol = reinterpret_cast<ResizeAxis*>(smem + lay.ucol);
   float* s_lr = reinterpret_cast<float*>(smem + lay.lr);
   uint8_t* s_samp = smem + lay.samp;
   uint8_t* s_gt = smem + lay.gt;
   const uint8_t* g_img = gt + (size_t)b * H * W * 3;
 
-  for (int i = tid; i < kmax * kmax; i += kDegThreads) s_taps[i] = taps_all[(size_t)b * kmax * kmax + i];
+  // non-zero taps, compacted by one warp in (i, j) order: tap (i, j) of the centred ksz x ksz kernel reads the source
+  // pixel at offset (cm - i, cm - j) (true convolution: the kernel is flipped)
+  if (tid < 32) {
+    const int cm = (kmax - 1) >> 1, r = (ksz - 1) >> 1;
+    const float* tp = taps_all + (size_t)b * kmax * kmax;
+    int count = 0;
+    const int span = 2 * r + 1;
+    for (int base = 0; ksz > 0 && base < span * span; base += 32) {
+      const int e = base + tid;
+      const int i = cm - r + e / span, j = cm - r + e % span;
+      const float t = (e < span * span) ? tp[i * kmax + j] : 0.f;
+      const unsigned m = __ballot_sync(0xffffffffu, t != 0.f);
+      if (t != 0.f) {
+        NzTap z;
+        z.dy = (short)(cm - i);
+        z.dx = (short)(cm - j);
+        z.w = t;
+        s_nz[count + __popc(m & ((1u << tid) - 1u))] = z;
+      }
+      count += __popc(m);
+    }
+    if (tid == 0) s_nnz = count;
+  }
   for (int i = tid; i < lh; i += kDegThreads) s_row[i] = cv_linear_tap(i, H, lh);
   for (int i = tid; i < lw; i += kDegThreads) s_col[i] = cv_linear_tap(i, W, lw);
+  for (int i = tid; i < H; i += kDegThreads) s_urow[i] = cv_linear_tap(i, lh, H);
+  for (int i = tid; i < W; i += kDegThreads) s_ucol[i] = cv_linear_tap(i, lw, W);
   if (kStage) {
     const int n16 = (H * W * 3) >> 4;  // H*W*3 is a multiple of 16 whenever W % 16 == 0 (checked on the host)
     const uint4* src = reinterpret_cast<const uint4*>(g_img);
@@ -115,19 +174,30 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
   }
   __syncthreads();
   const uint8_t* img = kStage ? s_gt : g_img;
+  const int n_nz = s_nnz;
+  const int rad = (ksz - 1) >> 1;
 
-  // 1a. blurred uint8 samples on the separable grid {row i0/i1} x {col i0/i1}
+  // 1a. blurred uint8 samples on the separable grid {row i0/i1} x {col i0/i1}: one thread per sample, three channels
   const int nr = 2 * lh, nc = 2 * lw;
-  for (int it = tid; it < nr * nc * 3; it += kDegThreads) {
-    const int c = it % 3;
-    const int q = (it / 3) % nc;
-    const int r = it / (3 * nc);
+  for (int it = tid; it < nr * nc; it += kDegThreads) {
+    const int q = it % nc;
+    const int r = it / nc;
     const int y = (r & 1) ? s_row[r >> 1].i1 : s_row[r >> 1].i0;
     const int x = (q & 1) ? s_col[q >> 1].i1 : s_col[q >> 1].i0;
-    uint8_t v;
-    if (ksz > 0) v = trunc_u8(blur_at(img, H, W, y, x, c, s_taps, kmax, ksz));
-    else v = img[(y * W + x) * 3 + c];
-    s_samp[it] = v;
+    uint8_t* d = s_samp + it * 3;
+    if (ksz > 0) {
+      float s3[3];
+      if (y >= rad && y + rad < H && x >= rad && x + rad < W) blur3<true>(img, H, W, y, x, s_nz, n_nz, s3);
+      else blur3<false>(img, H, W, y, x, s_nz, n_nz, s3);
+      d[0] = trunc_u8(s3[0]);
+      d[1] = trunc_u8(s3[1]);
+      d[2] = trunc_u8(s3[2]);
+    } else {
+      const uint8_t* px = img + (y * W + x) * 3;
+      d[0] = px[0];
+      d[1] = px[1];
+      d[2] = px[2];
+    }
   }
   __syncthreads();
   // 1b. down-resize (horizontal then vertical), add noise, clip
@@ -151,7 +221,7 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
   float* o = out + (size_t)b * 3 * H * W;
   for (int it = tid; it < H * W; it += kDegThreads) {
     const int x = it % W, y = it / W;
-    const ResizeAxis ry = cv_linear_tap(y, lh, H), rx = cv_linear_tap(x, lw, W);
+    const ResizeAxis ry = s_urow[y], rx = s_ucol[x];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float p00 = s_lr[(ry.i0 * lw + rx.i0) * 3 + c], p01 = s_lr[(ry.i0 * lw + rx.i1) * 3 + c];
@@ -208,8 +278,10 @@ extern "C" int b200ir_degrade(const uint8_t* gt, const float* taps, const int32_
     set_error("degrade: no CUDA device");
     return 1;
   }
-  const size_t base = deg_layout(kmax, lr_wmax, lr_hmax).gt;
-  const size_t staged = base + (size_t)H * W * 3;
+  const size_t lr_bytes = (size_t)lr_hmax * lr_wmax * 3 * 4;
+  const size_t gt_off = deg_layout(kmax, lr_wmax, lr_hmax, H, W).gt;
+  const size_t base = gt_off + lr_bytes;  // without staging the tail only holds the LR image
+  const size_t staged = gt_off + ((size_t)H * W * 3 > lr_bytes ? (size_t)H * W * 3 : lr_bytes);
   const bool stage = (staged <= (size_t)smem_optin) && ((H * W * 3) % 16 == 0) &&
                      ((reinterpret_cast<uintptr_t>(gt) & 15) == 0);
   B200IR_REQUIRE(base <= (size_t)smem_optin, "degrade: low-resolution image %dx%d does not fit shared memory", lr_wmax,
