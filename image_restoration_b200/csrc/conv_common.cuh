@@ -26,7 +26,12 @@ template <int EPI>
 struct EpiCfg {
   static constexpr int kGroups = (EPI >= 0) ? 3 : 2;
   static constexpr int kThreads = 64 + 128 * kGroups;
+  // row kernel: a fourth epilogue group was measured and buys nothing (the cout = 64 layers are bound by the shared-
+  // memory pipe -- MMA operand reads plus the epilogue's table reads -- not by epilogue latency)
+  static constexpr int kRowGroups = kGroups;
+  static constexpr int kRowThreads = 64 + 128 * kRowGroups;
 };
+static constexpr int kRowTable = 5 * 64;  // floats per epilogue group in the row kernel (block_n <= 64)
 static constexpr int kMaxEpiGroups = 3;
 static constexpr int kDemodTable = 2560;  // floats per epilogue group: per-tile tables [demod | out_scale | rgb_w x3]
 static constexpr int kMaxBias = 512;
@@ -213,7 +218,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                                               uint32_t full_phase, EpiRow r, bool valid, float gain, uint32_t s_bias,
                                               const float* g_bias, uint32_t s_demod, const float* g_demod,
                                               uint32_t s_aux, int aux_stride, int c_begin, int c_step, int n0) {
-  mbar_wait(full_bar, full_phase);
+  mbar_wait_parked(full_bar, full_phase);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
   r.nz *= gain;  // the noise load was issued in epi_setup, long before this first use
@@ -436,7 +441,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
                                               uint32_t full_phase, const FastRow& r, bool valid, float gain,
                                               uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride,
                                               int n0) {
-  mbar_wait(full_bar, full_phase);
+  mbar_wait_parked(full_bar, full_phase);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
   const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
@@ -557,7 +562,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
 __device__ __forceinline__ void epilogue_upfold(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
                                                 uint32_t full_phase, int x, int y, int b, int n0, bool valid,
                                                 uint32_t s_bias) {
-  mbar_wait(full_bar, full_phase);
+  mbar_wait_parked(full_bar, full_phase);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
   const float ag = p.act_gain, slope = p.slope;
@@ -813,7 +818,7 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
         const int cx = t.x0 + p.tap_dx[tap];
         const int cy = t.y0 + p.tap_dy[tap];
         for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
-          mbar_wait(&s.empty_bar[stage], phase ^ 1u);
+          mbar_wait_parked(&s.empty_bar[stage], phase ^ 1u);
           if (elect_one()) {
             uint8_t* sa = ring + stage * stage_bytes;
             mbar_arrive_expect_tx(&s.full_bar[stage], stage_bytes);
@@ -967,8 +972,8 @@ __device__ __forceinline__ RowItem decode_item(const ConvParams& p, int item) {
 }
 
 template <int kBlockK, int EPI>
-__global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_row_kernel(const __grid_constant__ ConvParams p) {
-  constexpr int kGroups = EpiCfg<EPI>::kGroups;
+__global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kGroups = EpiCfg<EPI>::kRowGroups;
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t row_bytes = kBlockK * 2;
   constexpr int k_steps = kBlockK / 16;
@@ -1004,7 +1009,7 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_row_kernel(cons
       const int cx = w.seg * 128 - 1;
       for (int r = 0; r < w.rows_out + 2; ++r) {
         for (int kc = 0; kc < kc_n; ++kc) {
-          mbar_wait(&s.empty_bar[slot], phase ^ 1u);
+          mbar_wait_parked(&s.empty_bar[slot], phase ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(&s.full_bar[slot], 130 * row_bytes);
             tma_load_4d(s_ring + slot * slot_bytes, &p.tmap_a[0], &s.full_bar[slot], kc * kBlockK, cx, w.y0 - 1 + r,
@@ -1019,7 +1024,11 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_row_kernel(cons
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer
+    // ---------------- MMA issuer.  Warp-uniform control flow, one elected lane issues (the compiler recognises the
+    // elect.sync pattern and emits plain UTCHMMA; a lane == 0 branch makes it wrap every MMA in an election loop).
+    // The issuing thread executes dependent scalar instructions only every ~5 cycles and nothing else bounds the
+    // low-channel layers (measured on 32 -> 32 channels: tensor pipe 20 % busy, no wait on data or accumulators), so
+    // the common row -- three targets, the newest one fresh, no wrap of the accumulator ring -- is straight-line code.
     mbar_wait(s.w_bar, 0);
     tc_fence_after();
     const uint32_t hi = desc_hi_word(row_bytes);
@@ -1029,6 +1038,8 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_row_kernel(cons
     constexpr uint32_t slot_lo = slot_bytes >> 4;
     constexpr uint32_t px_lo = row_bytes >> 4;  // one pixel (one smem row) in descriptor units
     const int ring = p.acc_stages;               // accumulator slots (power of two)
+    const uint32_t id1 = p.idesc_n[0], id2 = p.idesc_n[1], id3 = p.idesc_n[2];
+    const uint32_t bn = p.block_n;
     int slot = 0;                                // ring slot of (current input row, kc 0)
     uint32_t phase = 0;
     int it_base = 0;                             // output rows issued before this item
@@ -1049,15 +1060,40 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_row_kernel(cons
           mbar_wait(&s.tmem_empty[it & (ring - 1)], ((it >> p.acc_shift) & 1) ^ 1u);
         }
         tc_fence_after();
+        const int sa = (it_base + i - 2) & (ring - 1);
+        if (kc_n == 1 && i >= 2 && fresh && sa <= ring - 3) {
+          if (elect_one()) {
+            const uint32_t d = tmem_base + sa * bn;
+            const uint32_t a_lo = ring_lo + row_slot * slot_lo;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int k = 0; k < k_steps; ++k) {
+                const uint64_t a_desc = desc64(a_lo + kw * px_lo + 2 * k, hi);
+                const uint32_t b_lo = w_lo + kw * 3 * wtile_lo + 2 * k;
+                if (kw == 0 && k == 0) {
+                  umma_f16_fixed<true>(d, a_desc, desc64(b_lo, hi), id2);
+                  umma_f16_fixed<false>(d + 2 * bn, a_desc, desc64(b_lo + 2 * wtile_lo, hi), id1);
+                } else {
+                  umma_f16_fixed<true>(d, a_desc, desc64(b_lo, hi), id3);
+                }
+              }
+            }
+            umma_commit(&s.empty_bar[row_slot]);
+            umma_commit(&s.tmem_full[sa]);
+          }
+          __syncwarp();
+          continue;
+        }
         if (elect_one()) {
           const int j_lo = max(i - 2, 0), j_hi = min(i, w.rows_out - 1);
           // one accumulating run over output rows [ja, jb] (split where the accumulator ring wraps)
           auto run = [&](int ja, int jb, uint64_t a_desc, uint32_t tile_lo, uint32_t accumulate) {
             const int n = jb - ja + 1;
-            const int sa = (it_base + ja) & (ring - 1);
-            const int n1 = min(n, ring - sa);
+            const int s0 = (it_base + ja) & (ring - 1);
+            const int n1 = min(n, ring - s0);
             const uint32_t b_lo = tile_lo + (ja - (i - 2)) * wtile_lo;
-            umma_f16(tmem_base + sa * p.block_n, a_desc, desc64(b_lo, hi), p.idesc_n[n1 - 1], accumulate);
+            umma_f16(tmem_base + s0 * bn, a_desc, desc64(b_lo, hi), p.idesc_n[n1 - 1], accumulate);
             if (n1 < n) umma_f16(tmem_base, a_desc, desc64(b_lo + n1 * wtile_lo, hi), p.idesc_n[n - n1 - 1], accumulate);
           };
           int sl = row_slot;
@@ -1101,7 +1137,7 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_row_kernel(cons
       const bool valid = x < p.m_w;
       uint32_t s_dm = 0, s_aux = 0;
       if (p.demod != nullptr || p.smem_aux) {  // one image per item: each group stages that image's table rows once
-        float* tab = s.demod + group * kDemodTable;
+        float* tab = s.demod + group * kRowTable;
         epi_group_sync(group);
         for (int i = gt; i < p.block_n; i += 128) {
           const long long ch = (long long)w.b * p.cout + i;
@@ -1142,13 +1178,17 @@ static int launch_one(const ConvParams& p, int grid, int smem_bytes, int smem_ma
   if (ROW) {
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<kBlockK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      // the two-CTA-per-SM configuration needs the full shared-memory carve-out, not the smallest one that fits one CTA
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_row_kernel<kBlockK, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
       if (e != cudaSuccess) {
         set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return 1;
       }
       configured = true;
     }
-    conv_row_kernel<kBlockK, EPI><<<grid, EpiCfg<EPI>::kThreads, smem_bytes, st>>>(p);
+    conv_row_kernel<kBlockK, EPI><<<grid, EpiCfg<EPI>::kRowThreads, smem_bytes, st>>>(p);
     return check_launch("conv_row");
   }
   if (!configured) {

@@ -236,7 +236,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
   for (int t = 0; t < 8; ++t) p.tap_mask[t] = d->use_tap_mask ? d->tap_mask[t] : 0xffffffffu;
   {
     static int dbg = -1;
-    if (dbg < 0) dbg = (getenv("B200IR_DBG_SKIP_EPI") != nullptr) ? 1 : 0;
+    if (dbg < 0) dbg = (getenv("B200IR_DBG_SKIP_EPI") != nullptr) ? atoi(getenv("B200IR_DBG_SKIP_EPI")) : 0;
     p.dbg_skip_epi = dbg;
 
   }
@@ -288,6 +288,23 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
       const int tail_r = kTailBytes;
       int slots = (g_smem_optin - 1024 - tail_r - w_bytes) / slot_bytes;
       if (slots > kMaxStages) slots = kMaxStages;
+      // Two CTAs per SM for the leanest layers (cout <= 32 with the plain epilogue profiles, 60-72 registers): there
+      // the single MMA-issuing thread is the bound (measured 32 -> 32: main-loop floor 98 us against 61 us of HBM
+      // time, tensor pipe 20 % busy), and a second resident CTA is a second issuing thread.  Each CTA takes half the
+      // shared memory and 256 TMEM columns (ring of 8 accumulators).
+      static int dual_env = -1;
+      if (dual_env < 0) dual_env = (getenv("B200IR_ROW_DUAL") != nullptr) ? atoi(getenv("B200IR_ROW_DUAL")) : 1;
+      bool dual = dual_env && (p.epi == 0 || p.epi == 1) && d->cout <= 32 && p.k_chunks == 1 && d->max_ctas <= 0;
+      if (dual) {
+        const int budget = 233472 / 2 - 1024 - 512;  // per-SM shared memory / 2, minus the per-CTA reservation
+        const int s2 = (budget - 1024 - tail_r - w_bytes) / slot_bytes;
+        if (s2 >= 4) {
+          slots = s2 > kMaxStages ? kMaxStages : s2;
+        } else {
+          dual = false;
+        }
+      }
+      const int row_ctas = dual ? 2 * g_num_sms : g_num_sms;
       if (slots >= 2 * p.k_chunks) {
         // re-encode the activation map with the 130-pixel halo box
         const b200ir_view& a = d->a[0];
@@ -295,13 +312,29 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
         cuuint64_t strides[3] = {(cuuint64_t)a.stride_w * 2, (cuuint64_t)a.stride_h * 2, (cuuint64_t)a.stride_b * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.block_k, 130u, 1u, 1u};
         if (encode_map(&p.tmap_a[0], a.ptr, 4, dims, strides, box, swz, "activation(row)")) return 1;
+        // Rows per work item: an item of R output rows costs R + 2 input rows (halo), and the CTA with the most items
+        // sets the time, so pick the chunk count that minimises ceil(items / CTAs) * (R + 2) (measured at batch 64,
+        // 128x384: 3 chunks of 43 rows -> 4 items per CTA = 180 row times, against 204 for 4 chunks of 32).
         int R = d->m_h;
-        while ((long long)d->m_b * p.tiles_w * ((d->m_h + R - 1) / R) < 4LL * g_num_sms && R > 8) R = (R + 1) / 2;
+        {
+          const int ctas = (d->max_ctas > 0 && d->max_ctas < row_ctas) ? d->max_ctas : row_ctas;
+          long long best = -1;
+          for (int c = 1; c <= d->m_h; ++c) {
+            const int r = (d->m_h + c - 1) / c;
+            if (r < 4 && c > 1) break;
+            const long long items = (long long)d->m_b * p.tiles_w * ((d->m_h + r - 1) / r);
+            const long long cost = ((items + ctas - 1) / ctas) * (r + 2);
+            if (best < 0 || cost < best) {
+              best = cost;
+              R = r;
+            }
+          }
+        }
         p.row_R = R;
         p.row_chunks = (d->m_h + R - 1) / R;
         p.row_items = d->m_b * p.tiles_w * p.row_chunks;
         // too little parallelism at small batch: generic tiles are faster (row_mode == 2 forces the variant: tests)
-        row_ok = p.row_items >= 2 * g_num_sms || d->row_mode == 2;
+        row_ok = (long long)d->m_b * p.tiles_w * d->m_h >= 16LL * g_num_sms || d->row_mode == 2;
         p.row_slots = slots;
         p.row_slot_bytes = slot_bytes;
         p.row_w_bytes = w_bytes;
@@ -309,7 +342,13 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
         for (int n = 1; n <= 3; ++n) p.idesc_n[n - 1] = make_idesc_f16(kBlockM, n * d->block_n, false);
         const int smem_row = w_bytes + slots * slot_bytes + tail_r + 1024;
         if (row_ok) {
-          int grid_r = p.row_items < g_num_sms ? p.row_items : g_num_sms;
+          if (dual) {
+            p.acc_stages = 256 / d->block_n;
+            p.acc_shift = 0;
+            while ((1 << p.acc_shift) < p.acc_stages) ++p.acc_shift;
+            p.tmem_cols = 256;
+          }
+          int grid_r = p.row_items < row_ctas ? p.row_items : row_ctas;
           if (d->max_ctas > 0 && grid_r > d->max_ctas) grid_r = d->max_ctas;
           return launch_conv(p, true, grid_r, smem_row, g_smem_optin, reinterpret_cast<cudaStream_t>(stream));
         }
