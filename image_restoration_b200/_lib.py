@@ -49,6 +49,12 @@ class DemodLayer(C.Structure):
                 ('cin', C.c_int32), ('cout', C.c_int32)]
 
 
+class DegradeCrop(C.Structure):
+    """b200ir_degrade_crop (include/b200ir.h); numpy view: DEGRADE_CROP_DTYPE."""
+    _fields_ = [('blur_mode', C.c_int32), ('ksize', C.c_int32), ('blur_f64', C.c_int32), ('lr_w', C.c_int32), ('lr_h', C.c_int32),
+                ('jpeg_quality', C.c_int32), ('gray', C.c_int32), ('jitter', C.c_float * 3)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> argtypes (return type is int unless listed in _RESTYPES); mirrors include/b200ir.h one to one
@@ -87,6 +93,7 @@ SIGNATURES = {
     'b200ir_ca_mlp': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'b200ir_ca_scale_add': [_P, _P, _P, _P, _F, _I, _I, _I, _L, _L, _P],
     'b200ir_degrade': [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_degrade_full': [_P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64}
 

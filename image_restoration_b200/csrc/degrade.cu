@@ -47,28 +47,25 @@ __host__ __device__ inline DegLayout deg_layout(int kmax, int lr_wmax, int lr_hm
   return l;
 }
 
-// OpenCV's linear-resize tap for destination index d: resize from `src_n` to `dst_n` samples.
+// cv2.resize(INTER_LINEAR) tap for destination index d, resize from `src_n` to `dst_n` samples, AS EXECUTED for float
+// images in the build container (opencv-python 4.13 dispatches to Intel IPP): source coordinate (d + 0.5) * src/dst - 0.5
+// in float64, fraction rounded to fp32, indices clamped; each pass is fma(S1 - S0, f, S0), horizontal pass first.
+// Restated and pinned bit-exactly against cv2.resize in oracle/degrade_full_oracle.py::resize_linear.
+// (OpenCV's own C++ path rounds the coordinate to fp32 before taking the fraction and uses S0*(1-f) + S1*f: it differs
+// from IPP by up to 1.3e-5 on noise images.)
 __device__ __forceinline__ ResizeAxis cv_linear_tap(int d, int src_n, int dst_n) {
-  const double inv_scale = (double)dst_n / (double)src_n;
-  const double scale = 1.0 / inv_scale;
-  float f = (float)((d + 0.5) * scale - 0.5);
-  int s = (int)floorf(f);
-  f -= (float)s;
-  if (s < 0) {
-    f = 0.f;
-    s = 0;
-  }
-  if (s >= src_n - 1) {
-    f = 0.f;
-    s = src_n - 1;
-  }
+  const double scale = (double)src_n / (double)dst_n;
+  const double f = (d + 0.5) * scale - 0.5;
+  const double fl = floor(f);
+  const int s = (int)fl;
   ResizeAxis a;
-  a.i0 = s;
-  a.i1 = min(s + 1, src_n - 1);
-  a.w0 = __fsub_rn(1.f, f);
-  a.w1 = f;
+  a.i0 = min(max(s, 0), src_n - 1);
+  a.i1 = min(max(s + 1, 0), src_n - 1);
+  a.w1 = (float)(f - fl);
+  a.w0 = 0.f;  // unused
   return a;
 }
+__device__ __forceinline__ float cv_lerp(float s0, float s1, float f) { return __fmaf_rn(__fsub_rn(s1, s0), f, s0); }
 
 __device__ __forceinline__ float blur_at(const uint8_t* __restrict__ img, int H, int W, int y, int x, int c,
                                          const float* __restrict__ taps, int kmax, int ksz) {
@@ -210,9 +207,7 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
     const float p01 = __fdiv_rn((float)s_samp[((2 * ly) * nc + 2 * lx + 1) * 3 + c], 255.f);
     const float p10 = __fdiv_rn((float)s_samp[((2 * ly + 1) * nc + 2 * lx) * 3 + c], 255.f);
     const float p11 = __fdiv_rn((float)s_samp[((2 * ly + 1) * nc + 2 * lx + 1) * 3 + c], 255.f);
-    const float h0 = __fadd_rn(__fmul_rn(p00, rx.w0), __fmul_rn(p01, rx.w1));
-    const float h1 = __fadd_rn(__fmul_rn(p10, rx.w0), __fmul_rn(p11, rx.w1));
-    float v = __fadd_rn(__fmul_rn(h0, ry.w0), __fmul_rn(h1, ry.w1));
+    float v = cv_lerp(cv_lerp(p00, p01, rx.w1), cv_lerp(p10, p11, rx.w1), ry.w1);
     if (noise != nullptr) v = __fadd_rn(v, noise[(((size_t)b * lr_hmax + ly) * lr_wmax + lx) * 3 + c]);
     s_lr[it] = fminf(fmaxf(v, 0.f), 1.f);
   }
@@ -226,9 +221,7 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
     for (int c = 0; c < 3; ++c) {
       const float p00 = s_lr[(ry.i0 * lw + rx.i0) * 3 + c], p01 = s_lr[(ry.i0 * lw + rx.i1) * 3 + c];
       const float p10 = s_lr[(ry.i1 * lw + rx.i0) * 3 + c], p11 = s_lr[(ry.i1 * lw + rx.i1) * 3 + c];
-      const float h0 = __fadd_rn(__fmul_rn(p00, rx.w0), __fmul_rn(p01, rx.w1));
-      const float h1 = __fadd_rn(__fmul_rn(p10, rx.w0), __fmul_rn(p11, rx.w1));
-      float v = __fadd_rn(__fmul_rn(h0, ry.w0), __fmul_rn(h1, ry.w1));
+      float v = cv_lerp(cv_lerp(p00, p01, rx.w1), cv_lerp(p10, p11, rx.w1), ry.w1);
       v = fminf(fmaxf(v, 0.f), 1.f);
       v = fminf(fmaxf(rintf(__fmul_rn(v, 255.f)), 0.f), 255.f);
       v = __fdiv_rn(v, 255.f);

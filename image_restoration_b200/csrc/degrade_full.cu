@@ -1,0 +1,566 @@
+// Full per-crop degradation chain of FFHQDegradationDataset.__getitem__ (ffhq_degradation_dataset.py:242-311), one CTA
+// per crop, everything between the GT crop and the normalised LQ tensor in ONE launch:
+//   blur        random_mixed_kernels (degradations.py:419-523): 'iso' / 'aniso' / 'motion' / 'average' -> cv2.filter2D on
+//               the float image (correlation, BORDER_REFLECT_101, no quantisation); 'pyblur' -> scipy convolve2d on the
+//               uint8 image, fill 255, truncated to uint8 (pyblur/*.py)
+//   down        cv2.resize(INTER_LINEAR) to (lr_w, lr_h)                      (:255-256)
+//   noise       clip(img + noise, 0, 1)                                       (degradations.py:660-669)
+//   JPEG        add_jpg_compression (degradations.py:876-892): cv2.imencode / imdecode = libjpeg-turbo baseline 4:2:0,
+//               islow DCT, quality-scaled Annex K tables, fancy up-sampling; entropy coding is lossless and skipped.
+//               Integer arithmetic, restated in oracle/jpeg_oracle.py (bit-exact against cv2 in the build container).
+//   up          cv2.resize(INTER_LINEAR) back to (W, H)                       (:272)
+//   jitter      clip(img + shift[c], 0, 1)                                    (:90-95, :280-281)
+//   gray        cv2.cvtColor(BGR2GRAY) tiled to 3 channels                    (:283-285)
+//   tail        clamp(round(x*255), 0, 255)/255, (x-0.5)/0.5, BGR->RGB, NCHW  (:288, :307-311)
+// The blur is evaluated only at the 2x2 source pixels each low-resolution pixel interpolates (4 lanes per LR pixel, combined
+// with shuffles); the GT crop is staged in shared memory once.
+#include "host_common.h"
+
+namespace b200ir {
+
+static constexpr int kDfThreads = 512;
+
+struct DfAxis {
+  int i0, i1;
+  float w0, w1;
+};
+// one non-zero blur tap: weight, source offset, and where it sits in the reference's summation tree
+struct DfTap {
+  double w;
+  short dy, dx;
+  int grp;  // (group id << 2) | 2 * last-of-group | first-of-group
+};
+__device__ __forceinline__ float df_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float df_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double df_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double df_add(double a, double b) { return __dadd_rn(a, b); }
+
+// cv2.resize(INTER_LINEAR) tap for destination index d, resize from `src_n` to `dst_n` samples, AS EXECUTED for float
+// images in the build container (opencv-python 4.13 dispatches to Intel IPP): source coordinate (d + 0.5) * src/dst - 0.5
+// in float64, fraction rounded to fp32, indices clamped; each pass is fma(S1 - S0, f, S0), horizontal pass first.
+// Restated and pinned bit-exactly against cv2.resize in oracle/degrade_full_oracle.py::resize_linear.
+// (OpenCV's own C++ path rounds the coordinate to fp32 before taking the fraction and uses S0*(1-f) + S1*f: it differs
+// from IPP by up to 1.3e-5 on noise images.)
+__device__ __forceinline__ DfAxis df_linear_tap(int d, int src_n, int dst_n) {
+  const double scale = (double)src_n / (double)dst_n;
+  const double f = (d + 0.5) * scale - 0.5;
+  const double fl = floor(f);
+  const int s = (int)fl;
+  DfAxis a;
+  a.i0 = min(max(s, 0), src_n - 1);
+  a.i1 = min(max(s + 1, 0), src_n - 1);
+  a.w1 = (float)(f - fl);
+  a.w0 = 0.f;  // unused
+  return a;
+}
+__device__ __forceinline__ float df_lerp(float s0, float s1, float f) { return __fmaf_rn(__fsub_rn(s1, s0), f, s0); }
+
+// ------------------------------------------------------------------------------------------ libjpeg "islow" DCT
+#define DF_DESCALE(x, n) (((x) + (1 << ((n)-1))) >> (n))
+static constexpr int kF0298 = 2446, kF0390 = 3196, kF0541 = 4433, kF0765 = 6270, kF0899 = 7373, kF1175 = 9633,
+                     kF1501 = 12299, kF1847 = 15137, kF1961 = 16069, kF2053 = 16819, kF2562 = 20995, kF3072 = 25172;
+
+// jfdctint.c jpeg_fdct_islow, one pass over 8 samples (pass 1: rows, results scaled up by 2^PASS1_BITS; pass 2: columns)
+template <bool kFirst>
+__device__ __forceinline__ void fdct8(int (&d)[8]) {
+  const int t0 = d[0] + d[7], t7 = d[0] - d[7], t1 = d[1] + d[6], t6 = d[1] - d[6];
+  const int t2 = d[2] + d[5], t5 = d[2] - d[5], t3 = d[3] + d[4], t4 = d[3] - d[4];
+  const int t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+  constexpr int sh = kFirst ? 11 : 15;  // CONST_BITS -/+ PASS1_BITS
+  if (kFirst) {
+    d[0] = (t10 + t11) << 2;
+    d[4] = (t10 - t11) << 2;
+  } else {
+    d[0] = DF_DESCALE(t10 + t11, 2);
+    d[4] = DF_DESCALE(t10 - t11, 2);
+  }
+  int z1 = (t12 + t13) * kF0541;
+  d[2] = DF_DESCALE(z1 + t13 * kF0765, sh);
+  d[6] = DF_DESCALE(z1 + t12 * (-kF1847), sh);
+  z1 = t4 + t7;
+  int z2 = t5 + t6, z3 = t4 + t6, z4 = t5 + t7;
+  const int z5 = (z3 + z4) * kF1175;
+  const int a4 = t4 * kF0298, a5 = t5 * kF2053, a6 = t6 * kF3072, a7 = t7 * kF1501;
+  z1 *= -kF0899;
+  z2 *= -kF2562;
+  z3 = z3 * (-kF1961) + z5;
+  z4 = z4 * (-kF0390) + z5;
+  d[7] = DF_DESCALE(a4 + z1 + z3, sh);
+  d[5] = DF_DESCALE(a5 + z2 + z4, sh);
+  d[3] = DF_DESCALE(a6 + z2 + z3, sh);
+  d[1] = DF_DESCALE(a7 + z1 + z4, sh);
+}
+
+// jidctint.c jpeg_idct_islow, one pass (pass 1: columns; pass 2: rows with the final descale)
+template <bool kFirst>
+__device__ __forceinline__ void idct8(int (&c)[8]) {
+  int z2 = c[2], z3 = c[6];
+  int z1 = (z2 + z3) * kF0541;
+  const int e2 = z1 + z3 * (-kF1847);
+  const int e3 = z1 + z2 * kF0765;
+  const int e0 = (c[0] + c[4]) << 13, e1 = (c[0] - c[4]) << 13;
+  const int t10 = e0 + e3, t13 = e0 - e3, t11 = e1 + e2, t12 = e1 - e2;
+  int o0 = c[7], o1 = c[5], o2 = c[3], o3 = c[1];
+  z1 = o0 + o3;
+  z2 = o1 + o2;
+  z3 = o0 + o2;
+  int z4 = o1 + o3;
+  const int z5 = (z3 + z4) * kF1175;
+  o0 *= kF0298;
+  o1 *= kF2053;
+  o2 *= kF3072;
+  o3 *= kF1501;
+  z1 *= -kF0899;
+  z2 *= -kF2562;
+  z3 = z3 * (-kF1961) + z5;
+  z4 = z4 * (-kF0390) + z5;
+  o0 += z1 + z3;
+  o1 += z2 + z4;
+  o2 += z2 + z3;
+  o3 += z1 + z4;
+  constexpr int sh = kFirst ? 11 : 18;  // CONST_BITS - PASS1_BITS | CONST_BITS + PASS1_BITS + 3
+  c[0] = DF_DESCALE(t10 + o3, sh);
+  c[7] = DF_DESCALE(t10 - o3, sh);
+  c[1] = DF_DESCALE(t11 + o2, sh);
+  c[6] = DF_DESCALE(t11 - o2, sh);
+  c[2] = DF_DESCALE(t12 + o1, sh);
+  c[5] = DF_DESCALE(t12 - o1, sh);
+  c[3] = DF_DESCALE(t13 + o0, sh);
+  c[4] = DF_DESCALE(t13 - o0, sh);
+}
+
+__constant__ uint8_t kStdLuma[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+                                     14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                                     18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                                     49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+__constant__ uint8_t kStdChroma[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                                       24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                                       99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                       99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+
+// jccolor.c rgb_ycc_convert (FIX(x) = (int)(x * 65536 + 0.5))
+__device__ __forceinline__ void rgb2ycc(int r, int g, int b, int& y, int& cb, int& cr) {
+  y = (19595 * r + 38470 * g + 7471 * b + 32768) >> 16;
+  cb = (-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16;
+  cr = (32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16;
+}
+__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+
+// shared-memory layout
+struct DfLayout {
+  size_t row, col, urow, ucol, lut, qt, lr, yp, cbp, crp, gt, total;
+};
+__host__ __device__ inline size_t df_align(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline DfLayout df_layout(int kmax, int lr_wmax, int lr_hmax, int H, int W, bool stage) {
+  DfLayout l;
+  const int wp = (lr_wmax + 15) / 16 * 16, hp = (lr_hmax + 15) / 16 * 16;
+  l.row = df_align((size_t)kmax * kmax * sizeof(DfTap));
+  l.col = l.row + (size_t)lr_hmax * sizeof(DfAxis);
+  l.urow = l.col + (size_t)lr_wmax * sizeof(DfAxis);
+  l.ucol = l.urow + (size_t)H * sizeof(DfAxis);
+  l.lut = df_align(l.ucol + (size_t)W * sizeof(DfAxis));
+  l.qt = l.lut + 256 * sizeof(float);
+  l.lr = l.qt + 128 * sizeof(int);
+  l.yp = df_align(l.lr + (size_t)lr_hmax * lr_wmax * 3 * sizeof(float));
+  l.cbp = l.yp + (size_t)hp * wp * sizeof(int);
+  l.crp = l.cbp + (size_t)(hp / 2) * (wp / 2) * sizeof(int);
+  l.gt = df_align(l.crp + (size_t)(hp / 2) * (wp / 2) * sizeof(int));
+  l.total = l.gt + (stage ? (size_t)H * W * 3 : 0);
+  return l;
+}
+
+// Blur of the three channels at (y, x), in the arithmetic type T the reference's library call used.
+// kMode 1: scipy.signal.convolve2d on the uint8 values, fill 255 outside (pyblur).  scipy 1.18 (this container; pinned
+//   1.9.3) walks the kernel rows in ascending order and, inside a row, adds blocks of four columns as
+//   ((p0 + p1) + p2) + p3 to the running sum, then the remaining columns one by one -- products and sums rounded
+//   separately, in float64 when the kernel is float64 (box / disk / line under NumPy 2) and float32 when it is float32
+//   (psf).  The tap list carries that tree (first / last of group), so the result is bit-identical; zero taps add
+//   exact zeros and are dropped.
+// kMode 2: cv2.filter2D on value/255, BORDER_REFLECT_101: every tap is its own group (plain running sum, fp32).
+template <typename T, int kMode, bool kInterior>
+__device__ __forceinline__ void df_blur3(const uint8_t* __restrict__ img, const float* __restrict__ lut, int H, int W, int y,
+                                         int x, const DfTap* __restrict__ nz, int n_nz, T (&s)[3]) {
+  s[0] = s[1] = s[2] = (T)0;
+  T g0 = (T)0, g1 = (T)0, g2 = (T)0;
+  for (int k = 0; k < n_nz; ++k) {
+    const DfTap t = nz[k];
+    const T w = (T)t.w;
+    int iy = y + t.dy, ix = x + t.dx;
+    T v0, v1, v2;
+    if (kMode == 1) {
+      v0 = v1 = v2 = (T)255;
+      if (kInterior || (iy >= 0 && iy < H && ix >= 0 && ix < W)) {
+        const uint8_t* px = img + (iy * W + ix) * 3;
+        v0 = (T)px[0];
+        v1 = (T)px[1];
+        v2 = (T)px[2];
+      }
+    } else {
+      if (!kInterior) {
+        iy = iy < 0 ? -iy : (iy >= H ? 2 * H - 2 - iy : iy);
+        ix = ix < 0 ? -ix : (ix >= W ? 2 * W - 2 - ix : ix);
+      }
+      const uint8_t* px = img + (iy * W + ix) * 3;
+      v0 = (T)lut[px[0]];
+      v1 = (T)lut[px[1]];
+      v2 = (T)lut[px[2]];
+    }
+    const T p0 = df_mul(w, v0), p1 = df_mul(w, v1), p2 = df_mul(w, v2);
+    if (t.grp & 1) {
+      g0 = p0;
+      g1 = p1;
+      g2 = p2;
+    } else {
+      g0 = df_add(g0, p0);
+      g1 = df_add(g1, p1);
+      g2 = df_add(g2, p2);
+    }
+    if (t.grp & 2) {
+      s[0] = df_add(s[0], g0);
+      s[1] = df_add(s[1], g1);
+      s[2] = df_add(s[2], g2);
+    }
+  }
+}
+
+template <typename T, int kMode>
+__device__ __forceinline__ void df_blur3_at(const uint8_t* __restrict__ img, const float* __restrict__ lut, int H, int W,
+                                            int y, int x, int rad, const DfTap* __restrict__ nz, int n_nz, float (&v)[3]) {
+  T s[3];
+  if (y >= rad && y + rad < H && x >= rad && x + rad < W) df_blur3<T, kMode, true>(img, lut, H, W, y, x, nz, n_nz, s);
+  else df_blur3<T, kMode, false>(img, lut, H, W, y, x, nz, n_nz, s);
+  if (kMode == 1) {  // .astype(uint8) (truncation; the sum is inside [0, 255] up to rounding), then / 255
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = lut[(int)fmin(fmax((double)s[c], 0.0), 255.0)];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (float)s[c];
+  }
+}
+
+template <bool kStage>
+__global__ void __launch_bounds__(kDfThreads, 1)
+degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ taps_all, int kmax,
+                    const b200ir_degrade_crop* __restrict__ crops, const float* __restrict__ noise, int lr_wmax,
+                    int lr_hmax, float* __restrict__ out, float* __restrict__ lr_out, int H, int W, int bgr2rgb) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_nnz;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const b200ir_degrade_crop cp = crops[b];
+  const int lw = cp.lr_w, lh = cp.lr_h, ksz = cp.ksize, mode = cp.blur_mode;
+  const DfLayout lay = df_layout(kmax, lr_wmax, lr_hmax, H, W, kStage);
+  DfTap* s_nz = reinterpret_cast<DfTap*>(smem);
+  DfAxis* s_row = reinterpret_cast<DfAxis*>(smem + lay.row);
+  DfAxis* s_col = reinterpret_cast<DfAxis*>(smem + lay.col);
+  DfAxis* s_urow = reinterpret_cast<DfAxis*>(smem + lay.urow);
+  DfAxis* s_ucol = reinterpret_cast<DfAxis*>(smem + lay.ucol);
+  float* s_lut = reinterpret_cast<float*>(smem + lay.lut);
+  int* s_qt = reinterpret_cast<int*>(smem + lay.qt);
+  float* s_lr = reinterpret_cast<float*>(smem + lay.lr);
+  int* s_y = reinterpret_cast<int*>(smem + lay.yp);
+  int* s_cb = reinterpret_cast<int*>(smem + lay.cbp);
+  int* s_cr = reinterpret_cast<int*>(smem + lay.crp);
+  uint8_t* s_gt = smem + lay.gt;
+  const uint8_t* g_img = gt + (size_t)b * H * W * 3;
+
+  // ---- set-up: compacted taps (one warp, kernel order), resize taps, u8/255 table, quantisation tables, GT staging
+  if (tid < 32) {
+    const int cm = (kmax - 1) >> 1, r = (ksz - 1) >> 1;
+    const double* tp = taps_all + (size_t)b * kmax * kmax;
+    int count = 0;
+    const int span = 2 * r + 1;
+    const int blocked = span & ~3;  // columns summed in blocks of four by convolve2d
+    for (int base = 0; mode != 0 && ksz > 0 && base < span * span; base += 32) {
+      const int e = base + tid;
+      const int ir = e / span, jr = e % span;
+      const int i = cm - r + ir, j = cm - r + jr;
+      const double t = (e < span * span) ? tp[i * kmax + j] : 0.0;
+      const unsigned m = __ballot_sync(0xffffffffu, t != 0.0);
+      if (t != 0.0) {
+        DfTap z;
+        // convolution (pyblur) reads the flipped offset, correlation (filter2D) the direct one
+        z.dy = (short)(mode == 1 ? cm - i : i - cm);
+        z.dx = (short)(mode == 1 ? cm - j : j - cm);
+        z.w = t;
+        const int gid = (mode == 1 && jr < blocked) ? ir * 64 + (jr >> 2) : ir * 64 + 32 + jr;
+        z.grp = gid << 2;
+        s_nz[count + __popc(m & ((1u << tid) - 1u))] = z;
+      }
+      count += __popc(m);
+    }
+    __syncwarp();
+    for (int base = 0; base < count; base += 32) {  // first / last of its group among the non-zero taps
+      const int k = base + tid;
+      int bits = 0, gid = 0;
+      if (k < count) {
+        gid = s_nz[k].grp >> 2;
+        const int prev = k > 0 ? (s_nz[k - 1].grp >> 2) : -1;
+        const int next = k + 1 < count ? (s_nz[k + 1].grp >> 2) : -1;
+        bits = (prev != gid ? 1 : 0) | (next != gid ? 2 : 0);
+      }
+      __syncwarp();
+      if (k < count) s_nz[k].grp = (gid << 2) | bits;
+      __syncwarp();
+    }
+    if (tid == 0) s_nnz = count;
+  }
+  for (int i = tid; i < lh; i += kDfThreads) s_row[i] = df_linear_tap(i, H, lh);
+  for (int i = tid; i < lw; i += kDfThreads) s_col[i] = df_linear_tap(i, W, lw);
+  for (int i = tid; i < H; i += kDfThreads) s_urow[i] = df_linear_tap(i, lh, H);
+  for (int i = tid; i < W; i += kDfThreads) s_ucol[i] = df_linear_tap(i, lw, W);
+  if (tid < 256) s_lut[tid] = __fdiv_rn((float)tid, 255.f);
+  if (tid < 128 && cp.jpeg_quality > 0) {  // jcparam.c jpeg_quality_scaling + jpeg_add_quant_table (baseline)
+    int q = min(max(cp.jpeg_quality, 1), 100);
+    const int scale = q < 50 ? 5000 / q : 200 - 2 * q;
+    const int base = tid < 64 ? kStdLuma[tid] : kStdChroma[tid - 64];
+    s_qt[tid] = min(max((base * scale + 50) / 100, 1), 255);
+  }
+  if (kStage) {
+    const int n16 = (H * W * 3) >> 4;
+    const uint4* src = reinterpret_cast<const uint4*>(g_img);
+    uint4* dst = reinterpret_cast<uint4*>(s_gt);
+    for (int i = tid; i < n16; i += kDfThreads) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const uint8_t* img = kStage ? s_gt : g_img;
+  const int n_nz = s_nnz;
+  const int rad = (ksz - 1) >> 1;
+  const bool do_blur = mode != 0 && ksz > 0 && n_nz > 0;
+
+  // ---- 1. blur at the 2x2 source pixels of every LR pixel (4 lanes per LR pixel), down-resize, noise, clip
+  {
+    const int total = lh * lw * 4;
+    const int rounds = (total + kDfThreads - 1) / kDfThreads;
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int it = rd * kDfThreads + tid;
+      const bool live = it < total;
+      const int e = live ? it : 0;
+      const int q = e & 3, px = e >> 2;
+      const int lx = px % lw, ly = px / lw;
+      const DfAxis ry = s_row[ly], rx = s_col[lx];
+      const int y = (q & 2) ? ry.i1 : ry.i0;
+      const int x = (q & 1) ? rx.i1 : rx.i0;
+      float v[3];
+      if (do_blur) {
+        if (mode == 1) {
+          if (cp.blur_f64) df_blur3_at<double, 1>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
+          else df_blur3_at<float, 1>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
+        } else {
+          df_blur3_at<float, 2>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
+        }
+      } else {
+        const uint8_t* p = img + (y * W + x) * 3;
+        v[0] = s_lut[p[0]];
+        v[1] = s_lut[p[1]];
+        v[2] = s_lut[p[2]];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float p01 = __shfl_down_sync(0xffffffffu, v[c], 1);
+        const float p10 = __shfl_down_sync(0xffffffffu, v[c], 2);
+        const float p11 = __shfl_down_sync(0xffffffffu, v[c], 3);
+        if (live && q == 0) {
+          float r = df_lerp(df_lerp(v[c], p01, rx.w1), df_lerp(p10, p11, rx.w1), ry.w1);
+          if (noise != nullptr) r = __fadd_rn(r, noise[(((size_t)b * lr_hmax + ly) * lr_wmax + lx) * 3 + c]);
+          s_lr[px * 3 + c] = fminf(fmaxf(r, 0.f), 1.f);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. JPEG round trip on the LR image (channel order of the image is B, G, R)
+  if (cp.jpeg_quality > 0) {
+    const int wp = (lw + 15) / 16 * 16, hp = (lh + 15) / 16 * 16;
+    const int cwp = wp / 2, chp = hp / 2;
+    const int cw = (lw + 1) / 2, ch = (lh + 1) / 2;
+    // 2a. 8-bit conversion (cv::saturate_cast: round half to even), colour conversion, edge replication, chroma 2x2
+    for (int it = tid; it < hp * wp; it += kDfThreads) {
+      const int x = it % wp, y = it / wp;
+      const float* p = s_lr + (min(y, lh - 1) * lw + min(x, lw - 1)) * 3;
+      const int bb = (int)rintf(__fmul_rn(p[0], 255.f)), gg = (int)rintf(__fmul_rn(p[1], 255.f)),
+                rr = (int)rintf(__fmul_rn(p[2], 255.f));
+      int yy, cb, cr;
+      rgb2ycc(rr, gg, bb, yy, cb, cr);
+      s_y[it] = yy - 128;
+    }
+    for (int it = tid; it < chp * cwp; it += kDfThreads) {
+      const int cx = it % cwp, cy = it / cwp;
+      const int cyc = min(cy, ch - 1);  // rows below the image repeat the last DOWN-SAMPLED row (jcprepct.c)
+      int sb = 0, sr = 0;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float* p = s_lr + (min(2 * cyc + dy, lh - 1) * lw + min(2 * cx + dx, lw - 1)) * 3;
+          const int bb = (int)rintf(__fmul_rn(p[0], 255.f)), gg = (int)rintf(__fmul_rn(p[1], 255.f)),
+                    rr = (int)rintf(__fmul_rn(p[2], 255.f));
+          int yy, cb, cr;
+          rgb2ycc(rr, gg, bb, yy, cb, cr);
+          sb += cb;
+          sr += cr;
+        }
+      const int bias = (cx & 1) ? 2 : 1;  // jcsample.c h2v2_downsample: alternating 1, 2
+      s_cb[it] = ((sb + bias) >> 2) - 128;
+      s_cr[it] = ((sr + bias) >> 2) - 128;
+    }
+    __syncthreads();
+    // 2b. per 8x8 block (8 lanes each): forward DCT, quantise, de-quantise, inverse DCT -- in place
+    const int nby = (hp / 8) * (wp / 8), nbc = (chp / 8) * (cwp / 8);
+    const int nblocks = nby + 2 * nbc;
+    const int lane8 = tid & 7;
+    for (int blk = tid >> 3; blk < (nblocks + 63) / 64 * 64; blk += kDfThreads / 8) {
+      const bool live = blk < nblocks;
+      int* plane = s_y;
+      int pw = wp, bi = live ? blk : 0;
+      const int* qt = s_qt;
+      if (bi >= nby) {
+        bi -= nby;
+        plane = s_cb;
+        pw = cwp;
+        qt = s_qt + 64;
+        if (bi >= nbc) {
+          bi -= nbc;
+          plane = s_cr;
+        }
+      }
+      const int bpr = pw / 8;
+      int* base = plane + (bi / bpr) * 8 * pw + (bi % bpr) * 8;
+      int d[8];
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] = base[lane8 * pw + k];  // row lane8
+        fdct8<true>(d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) base[lane8 * pw + k] = d[k];
+      }
+      __syncwarp();
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] = base[k * pw + lane8];  // column lane8
+        fdct8<false>(d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // jcdctmgr.c quantize (divisor = table << 3), then de-quantise
+          const int qv = qt[k * 8 + lane8];
+          const int dv = qv << 3;
+          const int a = abs(d[k]);
+          int r = (a + (dv >> 1)) / dv;
+          r = d[k] < 0 ? -r : r;
+          d[k] = r * qv;
+        }
+        idct8<true>(d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) base[k * pw + lane8] = d[k];
+      }
+      __syncwarp();
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] = base[lane8 * pw + k];
+        idct8<false>(d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) base[lane8 * pw + k] = clamp255(d[k] + 128);
+      }
+    }
+    __syncthreads();
+    // 2c. fancy chroma up-sampling (jdsample.c h2v2_fancy_upsample) + jdcolor.c ycc_rgb_convert -> LR image / 255
+    for (int it = tid; it < lh * lw; it += kDfThreads) {
+      const int x = it % lw, y = it / lw;
+      const int cx = x >> 1, cy = y >> 1;
+      const int cyf = (y & 1) ? min(cy + 1, ch - 1) : max(cy - 1, 0);  // farther row
+      const int cxf = (x & 1) ? min(cx + 1, cw - 1) : max(cx - 1, 0);  // farther column
+      const int rnd = (x & 1) ? 7 : 8;
+      int cval[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int* pl = k ? s_cr : s_cb;
+        const int s_this = 3 * pl[cy * cwp + cx] + pl[cyf * cwp + cx];
+        const int s_far = 3 * pl[cy * cwp + cxf] + pl[cyf * cwp + cxf];
+        cval[k] = (3 * s_this + s_far + rnd) >> 4;
+      }
+      const int yy = s_y[y * wp + x];
+      const int xb = cval[0] - 128, xr = cval[1] - 128;
+      const int rr = clamp255(yy + ((91881 * xr + 32768) >> 16));
+      const int gg = clamp255(yy + ((-22554 * xb + 32768 - 46802 * xr) >> 16));
+      const int bb = clamp255(yy + ((116130 * xb + 32768) >> 16));
+      s_lr[it * 3 + 0] = s_lut[bb];
+      s_lr[it * 3 + 1] = s_lut[gg];
+      s_lr[it * 3 + 2] = s_lut[rr];
+    }
+    __syncthreads();
+  }
+  if (lr_out != nullptr) {  // parity aid: the LR image after noise / JPEG, [B][lr_hmax][lr_wmax][3]
+    for (int it = tid; it < lh * lw * 3; it += kDfThreads) {
+      const int c = it % 3, lx = (it / 3) % lw, ly = it / (3 * lw);
+      lr_out[(((size_t)b * lr_hmax + ly) * lr_wmax + lx) * 3 + c] = s_lr[it];
+    }
+  }
+
+  // ---- 3. up-resize, colour jitter, gray, 8-bit grid, normalise, NCHW (optionally BGR -> RGB)
+  float* o = out + (size_t)b * 3 * H * W;
+  const float j0 = cp.jitter[0], j1 = cp.jitter[1], j2 = cp.jitter[2];
+  const bool jit = j0 != 0.f || j1 != 0.f || j2 != 0.f;
+  for (int it = tid; it < H * W; it += kDfThreads) {
+    const int x = it % W, y = it / W;
+    const DfAxis ry = s_urow[y], rx = s_ucol[x];
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float p00 = s_lr[(ry.i0 * lw + rx.i0) * 3 + c], p01 = s_lr[(ry.i0 * lw + rx.i1) * 3 + c];
+      const float p10 = s_lr[(ry.i1 * lw + rx.i0) * 3 + c], p11 = s_lr[(ry.i1 * lw + rx.i1) * 3 + c];
+      v[c] = df_lerp(df_lerp(p00, p01, rx.w1), df_lerp(p10, p11, rx.w1), ry.w1);
+    }
+    if (jit) {
+      v[0] = fminf(fmaxf(__fadd_rn(v[0], j0), 0.f), 1.f);
+      v[1] = fminf(fmaxf(__fadd_rn(v[1], j1), 0.f), 1.f);
+      v[2] = fminf(fmaxf(__fadd_rn(v[2], j2), 0.f), 1.f);
+    }
+    if (cp.gray) {  // OpenCV's float BGR2GRAY as executed in the build container: fma(r, .299, fma(b, .114, g * .587))
+      const float g = __fmaf_rn(v[2], 0.299f, __fmaf_rn(v[0], 0.114f, __fmul_rn(v[1], 0.587f)));
+      v[0] = v[1] = v[2] = g;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float t = fminf(fmaxf(v[c], 0.f), 1.f);
+      t = fminf(fmaxf(rintf(__fmul_rn(t, 255.f)), 0.f), 255.f);
+      t = __fdiv_rn(t, 255.f);
+      t = __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);
+      const int co = bgr2rgb ? 2 - c : c;
+      o[(size_t)co * H * W + it] = t;
+    }
+  }
+}
+
+}  // namespace b200ir
+
+using namespace b200ir;
+
+extern "C" int b200ir_degrade_full(const uint8_t* gt, const double* taps, int kmax, const b200ir_degrade_crop* crops,
+                                   const float* noise, int lr_wmax, int lr_hmax, float* out, float* lr_out, int B, int H,
+                                   int W, int bgr2rgb, void* stream) {
+  B200IR_REQUIRE(gt && taps && crops && out, "degrade_full: null pointer");
+  B200IR_REQUIRE(B > 0 && H > 1 && W > 1 && kmax > 0 && (kmax & 1) && lr_wmax > 0 && lr_hmax > 0,
+                 "degrade_full: bad sizes (kmax must be odd)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0, smem_optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+    set_error("degrade_full: no CUDA device");
+    return 1;
+  }
+  const size_t base = df_layout(kmax, lr_wmax, lr_hmax, H, W, false).total;
+  const size_t staged = df_layout(kmax, lr_wmax, lr_hmax, H, W, true).total;
+  B200IR_REQUIRE(base <= (size_t)smem_optin, "degrade_full: low-resolution image %dx%d does not fit shared memory",
+                 lr_wmax, lr_hmax);
+  const bool stage = staged <= (size_t)smem_optin && (H * W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(gt) & 15) == 0;
+  if (stage) {
+    cudaFuncSetAttribute(degrade_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
+    degrade_full_kernel<true><<<B, kDfThreads, staged, st>>>(gt, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
+                                                            H, W, bgr2rgb);
+  } else {
+    cudaFuncSetAttribute(degrade_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+    degrade_full_kernel<false><<<B, kDfThreads, base, st>>>(gt, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
+                                                           H, W, bgr2rgb);
+  }
+  return check_launch("degrade_full");
+}

@@ -159,11 +159,11 @@ def random_blur_kernel(rng=np.random):
 
 
 # ------------------------------------------------------------------------------------------ device launch
-def _pack_kernels(kernels):
-    """List of KxK arrays (or None = no blur) -> (taps [B,kmax,kmax] fp32 centred, ksize [B] int32)."""
+def _pack_kernels(kernels, dtype=np.float32):
+    """List of KxK arrays (or None = no blur) -> (taps [B,kmax,kmax] centred, ksize [B] int32)."""
     sizes = [0 if k is None else k.shape[0] for k in kernels]
     kmax = max(max(sizes), 1)
-    taps = np.zeros((len(kernels), kmax, kmax), dtype=np.float32)
+    taps = np.zeros((len(kernels), kmax, kmax), dtype=dtype)
     for b, k in enumerate(kernels):
         if k is None:
             continue
@@ -264,3 +264,174 @@ def random_degradation_params(B, H, W, downsample_range=(4, 12), noise_range=(0,
     for b, n in enumerate(noises):
         nz[b, :n.shape[0], :n.shape[1]] = n
     return kernels, sizes, nz
+
+
+# ====================================================================================== full LQ synthesis (b200ir_degrade_full)
+# Host mirror of the kernel builders and of the order of random draws of random_mixed_kernels (degradations.py:419-523)
+# and FFHQDegradationDataset.__getitem__ (ffhq_degradation_dataset.py:242-285).  `random` and `np.random` are the two
+# generators the reference draws from; pass seeded stand-ins (random.Random / np.random.RandomState) to reproduce a
+# reference run draw for draw.
+FILTER2D_KINDS = ('iso', 'aniso', 'motion', 'average')
+UNSUPPORTED_KINDS = ('median', 'bilateral', 'generalized_iso', 'generalized_aniso', 'plateau_iso', 'plateau_aniso',
+                     'pyblur_motion', 'random_cover', 'bicubic')
+
+
+def mesh_axis(kernel_size):
+    """Coordinates of mesh_grid (degradations.py:35-50): -k//2 + 1 ... k//2."""
+    return np.arange(-kernel_size // 2 + 1., kernel_size // 2 + 1.)
+
+
+def bivariate_Gaussian(kernel_size, sig_x, sig_y, theta, isotropic=True):
+    """degradations.py:87-112 (with sigma_matrix2 :19-32 and pdf2 :53-66): exp(-x^T S^-1 x / 2) on the centred grid,
+    S = R diag(sx^2, sy^2) R^T, normalised to sum 1.  Returns float64 [k, k] indexed [y, x]."""
+    if isotropic:
+        cov = np.array([[sig_x ** 2, 0.], [0., sig_x ** 2]])
+    else:
+        rot = np.array([[np.cos(theta), -np.sin(theta)], [np.sin(theta), np.cos(theta)]])
+        cov = rot @ np.diag([sig_x ** 2, sig_y ** 2]) @ rot.T
+    inv = np.linalg.inv(cov)
+    ax = mesh_axis(kernel_size)
+    xx, yy = np.meshgrid(ax, ax)
+    pts = np.stack([xx, yy], axis=-1)                                  # [y, x, (x, y)]
+    k = np.exp(-0.5 * np.sum((pts @ inv) * pts, axis=2))
+    return k / np.sum(k)
+
+
+def motion_kernel(kernel_size, horizontal):
+    """motion_blur (degradations.py:330-341): a centred horizontal or vertical line of 1/k."""
+    k = np.zeros((kernel_size, kernel_size))
+    c = int((kernel_size - 1) / 2)
+    if horizontal:
+        k[c, :] = 1
+    else:
+        k[:, c] = 1
+    return k / kernel_size
+
+
+def average_kernel(kernel_size):
+    """average_blur (degradations.py:344-350): float32 ones / k^2."""
+    return np.ones((kernel_size, kernel_size), np.float32) / (kernel_size * kernel_size)
+
+
+def _pad_to(k, size):
+    pad = (size - k.shape[0]) // 2
+    return np.pad(k, ((pad, pad), (pad, pad))) if pad > 0 else k
+
+
+def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=(0.6, 5), sigma_y_range=(0.6, 5),
+                        rotation_range=(-math.pi, math.pi), pad_kernel=False, pad_kernel_size=21, py_random=None,
+                        np_random=np.random):
+    """The kernel random_mixed_kernels would apply (degradations.py:419-523), drawn with the same calls in the same
+    order.  Returns (blur_mode, kernel, description): blur_mode 2 = cv2.filter2D kinds, 1 = 'pyblur'."""
+    import random as _random
+    py_random = py_random or _random
+    kind = py_random.choices(kernel_list, kernel_prob)[0]
+    if kind in ('iso', 'aniso'):
+        assert kernel_size % 2 == 1 and sigma_x_range[0] < sigma_x_range[1]
+        sx = np_random.uniform(sigma_x_range[0], sigma_x_range[1])
+        sy, rot = sx, 0
+        if kind == 'aniso':
+            sy = np_random.uniform(sigma_y_range[0], sigma_y_range[1])
+            rot = np_random.uniform(rotation_range[0], rotation_range[1])
+        k = bivariate_Gaussian(kernel_size, sx, sy, rot, isotropic=(kind == 'iso'))
+        k = k / np.sum(k)                       # random_bivariate_Gaussian normalises once more (:222)
+        desc = (kind, sx, sy, rot)
+    elif kind == 'motion':
+        horizontal = py_random.random() > 0.5
+        k, desc = motion_kernel(kernel_size, horizontal), (kind, horizontal)
+    elif kind == 'average':
+        k, desc = average_kernel(kernel_size), (kind,)
+    elif kind == 'pyblur':
+        k, d = random_blur_kernel(np_random)
+        return 1, k, ('pyblur',) + tuple(d)
+    else:
+        raise NotImplementedError(f"blur kind '{kind}' has no B200 implementation (supported: "
+                                  f"{FILTER2D_KINDS + ('pyblur',)})")
+    if pad_kernel:
+        k = _pad_to(k, pad_kernel_size)
+    return 2, k, desc
+
+
+def sample_params(B, H, W, opt, py_random=None, np_random=np.random):
+    """Per-crop random draws of __getitem__ for the stages b200ir_degrade_full runs, in the reference's order: blur
+    kind + kernel, scale, noise sigma (+ the gray-noise coin) + noise field, JPEG quality, colour-jitter coin / shifts,
+    gray coin.  opt carries the dataset options of the training YAML (kernel_list, kernel_prob, blur_kernel_size,
+    blur_sigma, downsample_range, noise_range, jpeg_range, color_jitter_prob, color_jitter_shift, gray_prob).
+    Returns a dict of host arrays ready for degrade_full_batch."""
+    ks = opt['blur_kernel_size']
+    modes, kernels, sizes, noises, quality, jitter, gray, desc = [], [], [], [], [], [], [], []
+    for _ in range(B):
+        m, k, d = random_mixed_kernel(opt['kernel_list'], opt['kernel_prob'], ks, opt['blur_sigma'], opt['blur_sigma'],
+                                      (-math.pi, math.pi), pad_kernel=True, pad_kernel_size=ks, py_random=py_random,
+                                      np_random=np_random)
+        modes.append(m)
+        kernels.append(np.asarray(k))       # dtype kept: it selects the arithmetic type of the reference's blur
+        desc.append(d)
+        scale = np_random.uniform(opt['downsample_range'][0], opt['downsample_range'][1])
+        lw, lh = int(W // scale), int(H // scale)
+        sizes.append((lw, lh))
+        if opt.get('noise_range') is not None:
+            sigma = np_random.uniform(opt['noise_range'][0], opt['noise_range'][1])
+            np_random.uniform()                 # gray-noise coin of random_generate_gaussian_noise (degradations.py:652)
+            noises.append(np.float32(np_random.randn(lh, lw, 3)) * sigma / 255.)
+        else:
+            noises.append(None)
+        if opt.get('jpeg_range') is not None:
+            quality.append(int(np_random.uniform(opt['jpeg_range'][0], opt['jpeg_range'][1])))
+        else:
+            quality.append(0)
+        j = np.zeros(3, dtype=np.float32)
+        if opt.get('color_jitter_prob') is not None and np_random.uniform() < opt['color_jitter_prob']:
+            shift = opt.get('color_jitter_shift', 20) / 255.
+            j = np_random.uniform(-shift, shift, 3).astype(np.float32)
+        jitter.append(j)
+        gray.append(1 if (opt.get('gray_prob') and np_random.uniform() < opt['gray_prob']) else 0)
+    lr_wmax, lr_hmax = max(s[0] for s in sizes), max(s[1] for s in sizes)
+    nz = None
+    if any(n is not None for n in noises):
+        nz = np.zeros((B, lr_hmax, lr_wmax, 3), dtype=np.float32)
+        for b, n in enumerate(noises):
+            if n is not None:
+                nz[b, :n.shape[0], :n.shape[1]] = n
+    return dict(modes=modes, kernels=kernels, sizes=sizes, noise=nz, quality=quality, jitter=jitter, gray=gray,
+                desc=desc)
+
+
+def degrade_full_batch(gt_u8, modes, kernels, sizes, noise=None, quality=None, jitter=None, gray=None, bgr2rgb=True,
+                       return_lr=False, **_unused):
+    """One launch of b200ir_degrade_full over a batch (see include/b200ir.h).  gt_u8: uint8 CUDA tensor [B,H,W,3] in
+    the reference's channel order (BGR); the other arguments as returned by sample_params.  Returns the LQ batch fp32
+    [B,3,H,W] in [-1,1] (and the low-resolution image after noise / JPEG if return_lr)."""
+    if not (gt_u8.is_cuda and gt_u8.dtype == torch.uint8 and gt_u8.dim() == 4 and gt_u8.shape[3] == 3):
+        raise ValueError('gt_u8 must be a uint8 CUDA tensor [B,H,W,3]; image_restoration_b200 has no CPU path')
+    gt_u8 = gt_u8.contiguous()
+    B, H, W, _ = gt_u8.shape
+    dev = gt_u8.device
+    taps, ksize, kmax = _pack_kernels([k if m != 0 else None for k, m in zip(kernels, modes)], np.float64)
+    crops = (_lib.DegradeCrop * B)()
+    for b in range(B):
+        c = crops[b]
+        c.blur_mode, c.ksize = int(modes[b]), int(ksize[b])
+        c.blur_f64 = 1 if (c.blur_mode == 1 and np.asarray(kernels[b]).dtype == np.float64) else 0
+        c.lr_w, c.lr_h = int(sizes[b][0]), int(sizes[b][1])
+        if c.lr_w < 2 or c.lr_h < 2:
+            raise ValueError('low-resolution size must be at least 2x2')
+        c.jpeg_quality = int(quality[b]) if quality is not None else 0
+        c.gray = int(gray[b]) if gray is not None else 0
+        for i in range(3):
+            c.jitter[i] = float(jitter[b][i]) if jitter is not None else 0.0
+    lr_wmax, lr_hmax = max(s[0] for s in sizes), max(s[1] for s in sizes)
+    t_crops = torch.frombuffer(bytearray(bytes(crops)), dtype=torch.uint8).to(dev)
+    t_taps = torch.from_numpy(taps).to(dev)
+    if noise is not None:
+        noise = torch.as_tensor(noise, dtype=torch.float32).to(dev).contiguous()
+        assert tuple(noise.shape) == (B, lr_hmax, lr_wmax, 3)
+    out = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
+    lr = torch.zeros(B, lr_hmax, lr_wmax, 3, device=dev, dtype=torch.float32) if return_lr else None
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)  # noqa: E731
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().b200ir_degrade_full(p(gt_u8), p(t_taps), kmax, p(t_crops), p(noise), lr_wmax, lr_hmax,
+                                                  p(out), p(lr), B, H, W, 1 if bgr2rgb else 0, st),
+                   'b200ir_degrade_full')
+    return (out, lr) if return_lr else out

@@ -304,6 +304,41 @@ int b200ir_degrade(const uint8_t* gt, const float* taps, const int32_t* ksize, i
                    const int32_t* lr_h, const float* noise, int lr_wmax, int lr_hmax, float* out, uint8_t* blur_u8_out,
                    float* blur_f32_out, int B, int H, int W, int bgr2rgb, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The whole LQ synthesis of FFHQDegradationDataset.__getitem__ (ffhq_degradation_dataset.py:242-311) in one launch,
+ * one CTA per crop:  blur (random_mixed_kernels, degradations.py:419-523) -> cv2.resize down (:255-256) ->
+ * random_add_gaussian_noise (degradations.py:660-669) -> random_add_jpg_compression (degradations.py:876-910:
+ * cv2.imencode / imdecode, i.e. libjpeg-turbo baseline 4:2:0 with the islow DCT; the lossless entropy coding is
+ * skipped, the rest is the same integer arithmetic) -> cv2.resize up (:272) -> color_jitter (:90-95) ->
+ * cv2.cvtColor(BGR2GRAY) (:283-285) -> round / clip / normalize (:307-311).
+ * Random draws stay on the host (image_restoration_b200.degradation.sample_params mirrors the reference's order of
+ * random / np.random calls); this entry point is deterministic in its arguments.
+ * Not covered (host fallback does not exist either -- callers must not select them): 'median' and 'bilateral' blur
+ * kinds, color_jitter_pt, random_mask.
+ */
+typedef struct b200ir_degrade_crop {
+  int32_t blur_mode;    /* 0 none; 1 'pyblur': scipy convolve2d on the uint8 image, fill 255, truncated to uint8;
+                           2 cv2.filter2D on image/255 ('iso', 'aniso', 'motion', 'average'): correlation,
+                           BORDER_REFLECT_101, fp32 sum in kernel order (OpenCV itself switches to a DFT for kernels
+                           >= 11x11, so its result differs in the last bits) */
+  int32_t ksize;        /* odd extent of the kernel inside its kmax x kmax block */
+  int32_t blur_f64;     /* blur_mode 1 only: 1 = the reference's convolve2d ran in float64 (box / disk / line kernels are
+                           float64 under NumPy 2), 0 = in float32 (psf kernels).  The kernel reproduces scipy's summation
+                           tree in that type, so the truncated uint8 result is bit-identical */
+  int32_t lr_w, lr_h;   /* int(w // scale), int(h // scale) */
+  int32_t jpeg_quality; /* int(quality); 0 = no JPEG stage */
+  int32_t gray;         /* 1: BGR2GRAY tiled to 3 channels */
+  float jitter[3];      /* color_jitter shift per channel in the image's channel order; all 0 = off */
+} b200ir_degrade_crop;
+
+/* gt uint8 [B][H][W][3] (channel order B,G,R as the reference holds images); taps fp64 [B][kmax][kmax] centred, zero
+ * padded (blur_mode 2 rounds them to fp32 as cv2.filter2D does); crops: device array [B]; noise fp32 [B][lr_hmax][lr_wmax][3] already scaled by sigma/255, or NULL;
+ * out fp32 NCHW [B][3][H][W] normalised to [-1, 1] (channels reversed when bgr2rgb); lr_out (optional, parity aid):
+ * the low-resolution image after noise / JPEG, fp32 [B][lr_hmax][lr_wmax][3]. */
+int b200ir_degrade_full(const uint8_t* gt, const double* taps, int kmax, const b200ir_degrade_crop* crops,
+                        const float* noise, int lr_wmax, int lr_hmax, float* out, float* lr_out, int B, int H, int W,
+                        int bgr2rgb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

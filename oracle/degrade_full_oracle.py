@@ -1,0 +1,155 @@
+"""TEST INFRASTRUCTURE ONLY (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline) -- never imported by the product.
+
+CPU restatement of the LQ synthesis of FFHQDegradationDataset.__getitem__
+(Car_Plate-Restoration/basicsr/data/ffhq_degradation_dataset.py:242-311) for the stages b200ir_degrade_full runs, as a
+deterministic function of explicit parameters (the random draws are made by the caller):
+
+    blur    'iso' / 'aniso' / 'motion' / 'average': cv2.filter2D(img, -1, kernel) (degradations.py:460-515)
+            'pyblur': scipy convolve2d on the uint8 image, truncated to uint8 (oracle/pyblur_oracle.py; explicit
+                      arithmetic: convolve2d_same_fill)
+    down    cv2.resize(img, (lr_w, lr_h), INTER_LINEAR)                         (:255-256)
+    noise   clip(img + noise, 0, 1)                                             (degradations.py:660-669)
+    JPEG    add_jpg_compression                                                 (degradations.py:876-892)
+    up      cv2.resize(img, (W, H), INTER_LINEAR)                               (:272)
+    jitter  clip(img + shift, 0, 1)                                             (:90-95)
+    gray    cv2.cvtColor(BGR2GRAY), tiled                                       (:283-285)
+    tail    clamp(round(x * 255), 0, 255) / 255; (x - 0.5) / 0.5; BGR -> RGB; CHW   (:288, :307-311)
+
+The heavy lifting is the same third-party calls the reference makes (OpenCV 4.13 here, pinned 4.6.0.66 in
+requirements.txt:24).  Two stages also exist as explicit arithmetic because the CUDA kernel has to match them bit for
+bit: the JPEG round trip (oracle/jpeg_oracle.py, bit-exact against cv2) and the filter2D sum (`filter2d_direct`: fp32
+products and adds in kernel order, BORDER_REFLECT_101 -- OpenCV itself uses a DFT for kernels >= 11x11, so its result
+differs from ANY direct sum in the last bits; tests bound that difference).
+
+Pinning: tests/test_degrade_full_cpu.py runs the reference's own functions (imported from /root/reference, seeded)
+beside `image_restoration_b200.degradation.sample_params` + this module and requires identical results;
+tests/golden/degrade_full.npz holds reference outputs for the GPU box (tests/golden/make_golden_degrade_full.py).
+"""
+import cv2
+import numpy as np
+
+from . import jpeg_oracle, pyblur_oracle
+
+
+def filter2d_direct(img, kernel):
+    """cv2.filter2D(img, -1, kernel) for float32 HxWx3: correlation, anchor at the centre, BORDER_REFLECT_101.  fp32
+    product and add per tap, taps in row-major order, zero taps skipped (adding an exact zero changes nothing)."""
+    k = np.asarray(kernel, dtype=np.float32)
+    r = k.shape[0] // 2
+    pad = np.pad(img, ((r, r), (r, r), (0, 0)), mode='reflect')
+    h, w = img.shape[:2]
+    acc = np.zeros_like(img, dtype=np.float32)
+    for i in range(k.shape[0]):
+        for j in range(k.shape[1]):
+            if k[i, j] != 0:
+                acc = acc + k[i, j] * pad[i:i + h, j:j + w]
+    return acc
+
+
+def convolve2d_same_fill(img_u8, kernel, fill=255.0):
+    """scipy.signal.convolve2d(float32(img), kernel, mode='same', fillvalue=fill) per channel, as explicit arithmetic in
+    the type scipy computes in (result_type of float32 and the kernel's dtype).  scipy 1.18 (this container) walks kernel
+    rows in ascending order; within a row it adds blocks of four columns as ((p0 + p1) + p2) + p3 to the running sum and
+    the remaining columns one at a time; products and sums are rounded separately.  Found by probing and pinned
+    bit-exactly against scipy in tests/test_degrade_full_cpu.py."""
+    k = np.asarray(kernel)
+    dt = np.result_type(np.float32, k.dtype)
+    n = k.shape[0]
+    c = (n - 1) // 2
+    H, W = img_u8.shape[:2]
+    pad = np.pad(img_u8.astype(dt), ((c, c), (c, c), (0, 0)), constant_values=fill)
+    k = k.astype(dt)
+    acc = np.zeros(img_u8.shape, dt)
+
+    def prod(i, j):
+        return k[i, j] * pad[2 * c - i:2 * c - i + H, 2 * c - j:2 * c - j + W]
+    for i in range(n):
+        j = 0
+        while j + 4 <= n:
+            if np.any(k[i, j:j + 4] != 0):
+                acc = acc + (((prod(i, j) + prod(i, j + 1)) + prod(i, j + 2)) + prod(i, j + 3))
+            j += 4
+        while j < n:
+            if k[i, j] != 0:
+                acc = acc + prod(i, j)
+            j += 1
+    return acc
+
+
+def _fma32(a, b, c):
+    """fp32 fused multiply-add: the float64 product of two fp32 values is exact, so one float64 add + one rounding to
+    fp32 reproduces it (up to double-rounding cases of probability ~2^-29)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def resize_linear(img, dsize):
+    """cv2.resize(img, dsize, interpolation=INTER_LINEAR) for float32 HxWxC as this container's OpenCV 4.13 executes it
+    (Intel IPP): source coordinate (d + 0.5) * src / dst - 0.5 in float64, fraction rounded to fp32, indices clamped,
+    each pass fma(S1 - S0, f, S0), horizontal pass then vertical.  Found by probing; pinned bit-exactly against
+    cv2.resize in tests/test_degrade_full_cpu.py.  This is what the CUDA kernels evaluate."""
+    W, H = dsize
+    h, w = img.shape[:2]
+
+    def coords(dst_n, src_n):
+        f = (np.arange(dst_n) + 0.5) * (np.float64(src_n) / dst_n) - 0.5
+        s = np.floor(f)
+        return (np.clip(s, 0, src_n - 1).astype(int), np.clip(s + 1, 0, src_n - 1).astype(int), (f - s).astype(np.float32))
+
+    def lerp(a, b, f):
+        return _fma32(b - a, np.broadcast_to(f, a.shape), a)
+    x0, x1, fx = coords(W, w)
+    y0, y1, fy = coords(H, h)
+    t = lerp(img[:, x0], img[:, x1], fx[None, :, None])
+    return lerp(t[y0], t[y1], fy[:, None, None])
+
+
+def gray_bgr(img):
+    """cv2.cvtColor(img, COLOR_BGR2GRAY) on float32 as this container's OpenCV evaluates it:
+    fma(r, 0.299, fma(b, 0.114, g * 0.587)) (found by comparing all orderings against cv2; bit-exact)."""
+    b, g, r = (img[..., i].astype(np.float64) for i in range(3))
+    c = [float(np.float32(v)) for v in (0.114, 0.587, 0.299)]
+    t = (g * c[1]).astype(np.float32).astype(np.float64)
+    t = (b * c[0] + t).astype(np.float32).astype(np.float64)
+    return (r * c[2] + t).astype(np.float32)
+
+
+def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, exact_blur=True, lib_jpeg=False):
+    """uint8 BGR [H,W,3] -> float32 BGR [H,W,3] LQ image before the 8-bit rounding, plus the LR image after noise/JPEG."""
+    H, W = gt_u8.shape[:2]
+    img = gt_u8.astype(np.float32) / np.float32(255.)
+    if mode == 2:
+        k = np.asarray(kernel, dtype=np.float32)
+        img = filter2d_direct(img, k) if exact_blur else cv2.filter2D(img, -1, np.asarray(kernel))
+    elif mode == 1:     # the kernel's dtype decides the arithmetic type, as in the reference (float64 box / disk / line)
+        blur = convolve2d_same_fill(gt_u8, kernel) if exact_blur else pyblur_oracle.blur_f32(gt_u8, np.asarray(kernel))
+        img = blur.astype('uint8').astype(np.float32) / np.float32(255.)
+    lr = cv2.resize(img, tuple(lr_size), interpolation=cv2.INTER_LINEAR)
+    if noise is not None:
+        lr = np.clip(lr + noise, 0, 1)
+    if quality:
+        if lib_jpeg:
+            enc = cv2.imencode('.jpg', np.clip(lr, 0, 1) * 255.0, [int(cv2.IMWRITE_JPEG_QUALITY), int(quality)])[1]
+            lr = np.float32(cv2.imdecode(enc, 1)) / 255.0
+        else:
+            lr = jpeg_oracle.add_jpg_compression(lr, quality)
+    up = cv2.resize(lr, (W, H), interpolation=cv2.INTER_LINEAR)
+    if jitter is not None and np.any(np.asarray(jitter) != 0):
+        up = np.clip(up + np.asarray(jitter, dtype=np.float32), 0, 1)
+    if gray:
+        up = np.tile(gray_bgr(up)[:, :, None], [1, 1, 3])
+    return up, lr
+
+
+def lq_tensor(up, bgr2rgb=True):
+    """Tail of __getitem__: 8-bit grid, normalise with mean = std = 0.5, HWC -> CHW (numpy float32)."""
+    x = np.clip(np.rint(np.clip(up, 0, 1) * np.float32(255.)), 0, 255) / np.float32(255.)
+    x = (x - np.float32(0.5)) / np.float32(0.5)
+    if bgr2rgb:
+        x = x[..., ::-1]
+    return np.ascontiguousarray(x.transpose(2, 0, 1)).astype(np.float32)
+
+
+def degrade_full(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, bgr2rgb=True, exact_blur=True,
+                 lib_jpeg=False):
+    up, lr = lq_image(gt_u8, mode, kernel, lr_size, noise, quality, jitter, gray, exact_blur, lib_jpeg)
+    return lq_tensor(up, bgr2rgb), lr

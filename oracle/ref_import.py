@@ -122,3 +122,19 @@ def load_reference_pyblur():
         _pyblur_cache['lines0'] = copy.deepcopy(lmb.lineDict.lines)
     _pyblur_cache['lmb'].lineDict.lines = copy.deepcopy(_pyblur_cache['lines0'])
     return _pyblur_cache['mod']
+
+
+def load_reference_degradations():
+    """Returns (basicsr.data.degradations, FFHQDegradationDataset) of the reference.  One more stand-in module:
+    torchvision.transforms.functional_tensor (removed from torchvision 0.26; degradations.py:11 only takes
+    rgb_to_grayscale from it, which still exists in torchvision.transforms.functional)."""
+    load_reference_arch()
+    load_reference_pyblur()
+    if 'torchvision.transforms.functional_tensor' not in sys.modules:
+        import torchvision.transforms.functional as TF
+        m = types.ModuleType('torchvision.transforms.functional_tensor')
+        m.rgb_to_grayscale = TF.rgb_to_grayscale
+        sys.modules['torchvision.transforms.functional_tensor'] = m
+    deg = importlib.import_module('basicsr.data.degradations')
+    ds = importlib.import_module('basicsr.data.ffhq_degradation_dataset')
+    return deg, ds.FFHQDegradationDataset

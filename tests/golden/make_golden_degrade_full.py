@@ -1,0 +1,101 @@
+"""Generates tests/golden/degrade_full.npz by running the REFERENCE's own degradation functions
+(basicsr/data/degradations.py, ffhq_degradation_dataset.py, imported from /root/reference) on seeded synthetic crops.
+Run in the build container: python tests/golden/make_golden_degrade_full.py"""
+import math
+import os
+import random
+import sys
+
+import cv2
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_import  # noqa: E402
+from image_restoration_b200 import degradation as D  # noqa: E402
+
+OPT = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'pyblur'],
+           kernel_prob=[0.2, 0.2, 0.15, 0.15, 0.3], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
+           noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.1)
+
+
+def smooth_crop(rng, h, w):
+    """A plate-like synthetic crop: smooth background + sharp strokes, uint8 BGR."""
+    base = cv2.resize(rng.random((h // 16 + 2, w // 16 + 2, 3)).astype(np.float32), (w, h), interpolation=cv2.INTER_CUBIC)
+    img = np.clip(base, 0, 1)
+    for _ in range(12):
+        x0, y0 = int(rng.integers(0, w - 8)), int(rng.integers(0, h - 8))
+        img[y0:y0 + int(rng.integers(4, 40)), x0:x0 + int(rng.integers(2, 12))] = rng.random(3)
+    return (img * 255).astype(np.uint8)
+
+
+def reference_lq(deg, DS, gt_u8, opt):
+    """__getitem__ lines 242-311 for one crop, calling the reference's functions (random state: the global
+    `random` / `np.random`, seeded by the caller)."""
+    img_gt = gt_u8.astype(np.float32) / 255.
+    h, w, _ = img_gt.shape
+    img_lq = deg.random_mixed_kernels(img=img_gt, kernel_list=opt['kernel_list'], kernel_prob=opt['kernel_prob'],
+                                      kernel_size=opt['blur_kernel_size'], sigma_x_range=opt['blur_sigma'],
+                                      sigma_y_range=opt['blur_sigma'], rotation_range=[-math.pi, math.pi],
+                                      noise_range=None, pad_kernel=True, pad_kernel_size=opt['blur_kernel_size'])
+    scale = np.random.uniform(opt['downsample_range'][0], opt['downsample_range'][1])
+    img_lq = cv2.resize(img_lq, (int(w // scale), int(h // scale)), interpolation=cv2.INTER_LINEAR)
+    if opt['noise_range'] is not None:
+        img_lq = deg.random_add_gaussian_noise(img_lq, opt['noise_range'])
+    if opt['jpeg_range'] is not None:
+        img_lq = deg.random_add_jpg_compression(img_lq, opt['jpeg_range'])
+    img_lq = cv2.resize(img_lq, (w, h), interpolation=cv2.INTER_LINEAR)
+    if opt['color_jitter_prob'] is not None and (np.random.uniform() < opt['color_jitter_prob']):
+        img_lq = DS.color_jitter(img_lq, opt['color_jitter_shift'] / 255.)
+    if opt['gray_prob'] and np.random.uniform() < opt['gray_prob']:
+        img_lq = cv2.cvtColor(img_lq, cv2.COLOR_BGR2GRAY)
+        img_lq = np.tile(img_lq[:, :, None], [1, 1, 3])
+    t = torch.from_numpy(np.ascontiguousarray(img_lq[..., ::-1].transpose(2, 0, 1))).float()   # img2tensor(bgr2rgb)
+    t = torch.clamp((t * 255.0).round(), 0, 255) / 255.
+    return ((t - 0.5) / 0.5).numpy()
+
+
+def main():
+    deg, DS = ref_import.load_reference_degradations()
+    rng = np.random.default_rng(7)
+    H, W, N = 128, 384, 16
+    gts, outs, seeds = [], [], []
+    for i in range(N):
+        gt = smooth_crop(rng, H, W)
+        seed = 1000 + i
+        ref_import.load_reference_pyblur()          # fresh LineDictionary (the reference mutates it)
+        random.seed(seed)
+        np.random.seed(seed)
+        outs.append(reference_lq(deg, DS, gt, OPT))
+        gts.append(gt)
+        seeds.append(seed)
+    # parameters the host mirror draws from the same seeds (stored so the GPU box needs no reference)
+    recs = []
+    for gt, seed in zip(gts, seeds):
+        pr, nr = random.Random(seed), np.random.RandomState(seed)
+        recs.append(D.sample_params(1, H, W, OPT, py_random=pr, np_random=nr))
+    kmax = 29
+    taps = np.zeros((N, kmax, kmax), np.float64)
+    for i, r in enumerate(recs):
+        k = r['kernels'][0]
+        o = (kmax - k.shape[0]) // 2
+        taps[i, o:o + k.shape[0], o:o + k.shape[0]] = k
+    lw = np.array([r['sizes'][0][0] for r in recs]); lh = np.array([r['sizes'][0][1] for r in recs])
+    noise = np.zeros((N, lh.max(), lw.max(), 3), np.float32)
+    for i, r in enumerate(recs):
+        noise[i, :lh[i], :lw[i]] = r['noise'][0]
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'degrade_full.npz'), gt=np.stack(gts),
+                        out_u8=np.rint((np.stack(outs) * 0.5 + 0.5) * 255).astype(np.uint8), seeds=np.array(seeds),
+                        modes=np.array([r['modes'][0] for r in recs]), taps=taps,
+                        ksize=np.array([r['kernels'][0].shape[0] for r in recs]),
+                        f64=np.array([int(r['kernels'][0].dtype == np.float64) for r in recs]), lr_w=lw, lr_h=lh, noise=noise,
+                        quality=np.array([r['quality'][0] for r in recs]),
+                        jitter=np.stack([r['jitter'][0] for r in recs]), gray=np.array([r['gray'][0] for r in recs]),
+                        kinds=np.array([r['desc'][0][0] for r in recs]))
+    print('kinds', [r['desc'][0][0] for r in recs])
+    print('gray', [r['gray'][0] for r in recs], 'quality', [r['quality'][0] for r in recs])
+
+
+if __name__ == '__main__':
+    main()
