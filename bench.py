@@ -306,6 +306,28 @@ def main():
                                   'sample': f'{n_cpu} crops through scipy.signal.convolve2d + cv2.resize (the '
                                             'reference\'s own library calls, oracle/pyblur_oracle.py)'}}
 
+        # the whole LQ synthesis of __getitem__ (blur kinds of the training YAML, JPEG, jitter, gray) in one launch
+        from oracle import degrade_full_oracle as dfo
+        opt = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'pyblur'],
+                   kernel_prob=[0.2, 0.2, 0.15, 0.15, 0.3], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
+                   noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.1)
+        import random as _random
+        prm = dg.sample_params(DB, H, W, opt, py_random=_random.Random(0), np_random=np.random.RandomState(0))
+        pk = dg.pack_degrade_full(dev=dev, **prm)
+        ms_full = timed(lambda: dg.degrade_full_batch(gt_d, packed=pk), 10, 3) / 10
+        t0 = time.time()
+        for b in range(n_cpu):
+            lw, lh = prm['sizes'][b]
+            dfo.degrade_full(gt[b], prm['modes'][b], prm['kernels'][b], (lw, lh), prm['noise'][b, :lh, :lw],
+                             prm['quality'][b], prm['jitter'][b], prm['gray'][b], exact_blur=False, lib_jpeg=True)
+        cpu_full_ms = (time.time() - t0) / n_cpu * 1e3
+        degr['full_chain'] = {'kernel': 'degrade_full_kernel', 'crops_per_s': DB / (ms_full / 1e3), 'ms_per_batch': ms_full,
+                              'batch': DB, 'achieved_gbs': alg / ms_full / 1e6,
+                              'stages': 'blur (iso/aniso/motion/average/pyblur) + resize + noise + JPEG + resize + jitter + gray',
+                              'cpu_reference': {'ms_per_crop': cpu_full_ms, 'crops_per_s': 1e3 / cpu_full_ms, 'cores': 1,
+                                                'kind': 'port', 'sample': f'{n_cpu} crops through cv2.filter2D / scipy '
+                                                'convolve2d + cv2.resize + cv2.imencode/imdecode (the reference\'s calls)'}}
+
     if rank == 0:
         tf_peak, hbm_peak, src = peaks()
         crops = B * world * args.steps

@@ -271,9 +271,9 @@ def random_degradation_params(B, H, W, downsample_range=(4, 12), noise_range=(0,
 # and FFHQDegradationDataset.__getitem__ (ffhq_degradation_dataset.py:242-285).  `random` and `np.random` are the two
 # generators the reference draws from; pass seeded stand-ins (random.Random / np.random.RandomState) to reproduce a
 # reference run draw for draw.
-FILTER2D_KINDS = ('iso', 'aniso', 'motion', 'average')
-UNSUPPORTED_KINDS = ('median', 'bilateral', 'generalized_iso', 'generalized_aniso', 'plateau_iso', 'plateau_aniso',
-                     'pyblur_motion', 'random_cover', 'bicubic')
+FILTER2D_KINDS = ('iso', 'aniso', 'generalized_iso', 'generalized_aniso', 'plateau_iso', 'plateau_aniso', 'motion',
+                  'average')
+UNSUPPORTED_KINDS = ('median', 'bilateral', 'pyblur_motion', 'random_cover', 'bicubic')
 
 
 def mesh_axis(kernel_size):
@@ -294,6 +294,32 @@ def bivariate_Gaussian(kernel_size, sig_x, sig_y, theta, isotropic=True):
     xx, yy = np.meshgrid(ax, ax)
     pts = np.stack([xx, yy], axis=-1)                                  # [y, x, (x, y)]
     k = np.exp(-0.5 * np.sum((pts @ inv) * pts, axis=2))
+    return k / np.sum(k)
+
+
+def _quad_form(kernel_size, sig_x, sig_y, theta, isotropic):
+    """x^T S^-1 x on the centred grid (shared by the three kernel families, degradations.py:87-176)."""
+    if isotropic:
+        cov = np.array([[sig_x ** 2, 0.], [0., sig_x ** 2]])
+    else:
+        rot = np.array([[np.cos(theta), -np.sin(theta)], [np.sin(theta), np.cos(theta)]])
+        cov = rot @ np.diag([sig_x ** 2, sig_y ** 2]) @ rot.T
+    inv = np.linalg.inv(cov)
+    ax = mesh_axis(kernel_size)
+    xx, yy = np.meshgrid(ax, ax)
+    pts = np.stack([xx, yy], axis=-1)
+    return np.sum((pts @ inv) * pts, axis=2)
+
+
+def bivariate_generalized_Gaussian(kernel_size, sig_x, sig_y, theta, beta, isotropic=True):
+    """degradations.py:115-147: exp(-0.5 * (x^T S^-1 x)^beta), normalised."""
+    k = np.exp(-0.5 * np.power(_quad_form(kernel_size, sig_x, sig_y, theta, isotropic), beta))
+    return k / np.sum(k)
+
+
+def bivariate_plateau(kernel_size, sig_x, sig_y, theta, beta, isotropic=True):
+    """degradations.py:150-176: 1 / ((x^T S^-1 x)^beta + 1), normalised."""
+    k = np.reciprocal(np.power(_quad_form(kernel_size, sig_x, sig_y, theta, isotropic), beta) + 1)
     return k / np.sum(k)
 
 
@@ -320,7 +346,7 @@ def _pad_to(k, size):
 
 def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=(0.6, 5), sigma_y_range=(0.6, 5),
                         rotation_range=(-math.pi, math.pi), pad_kernel=False, pad_kernel_size=21, py_random=None,
-                        np_random=np.random):
+                        np_random=np.random, betag_range=(0.5, 8), betap_range=(0.5, 8)):
     """The kernel random_mixed_kernels would apply (degradations.py:419-523), drawn with the same calls in the same
     order.  Returns (blur_mode, kernel, description): blur_mode 2 = cv2.filter2D kinds, 1 = 'pyblur'."""
     import random as _random
@@ -336,6 +362,21 @@ def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=
         k = bivariate_Gaussian(kernel_size, sx, sy, rot, isotropic=(kind == 'iso'))
         k = k / np.sum(k)                       # random_bivariate_Gaussian normalises once more (:222)
         desc = (kind, sx, sy, rot)
+    elif kind in ('generalized_iso', 'generalized_aniso', 'plateau_iso', 'plateau_aniso'):
+        # random_bivariate_generalized_Gaussian / random_bivariate_plateau (degradations.py:226-327): sigma_x, [sigma_y,
+        # rotation], the beta coin, beta
+        iso = kind.endswith('_iso')
+        sx = np_random.uniform(sigma_x_range[0], sigma_x_range[1])
+        sy, rot = sx, 0
+        if not iso:
+            sy = np_random.uniform(sigma_y_range[0], sigma_y_range[1])
+            rot = np_random.uniform(rotation_range[0], rotation_range[1])
+        br = betag_range if kind.startswith('generalized') else betap_range
+        beta = np_random.uniform(br[0], 1) if np_random.uniform() < 0.5 else np_random.uniform(1, br[1])
+        build = bivariate_generalized_Gaussian if kind.startswith('generalized') else bivariate_plateau
+        k = build(kernel_size, sx, sy, rot, beta, isotropic=iso)
+        k = k / np.sum(k)
+        desc = (kind, sx, sy, rot, beta)
     elif kind == 'motion':
         horizontal = py_random.random() > 0.5
         k, desc = motion_kernel(kernel_size, horizontal), (kind, horizontal)
@@ -397,16 +438,10 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random):
                 desc=desc)
 
 
-def degrade_full_batch(gt_u8, modes, kernels, sizes, noise=None, quality=None, jitter=None, gray=None, bgr2rgb=True,
-                       return_lr=False, **_unused):
-    """One launch of b200ir_degrade_full over a batch (see include/b200ir.h).  gt_u8: uint8 CUDA tensor [B,H,W,3] in
-    the reference's channel order (BGR); the other arguments as returned by sample_params.  Returns the LQ batch fp32
-    [B,3,H,W] in [-1,1] (and the low-resolution image after noise / JPEG if return_lr)."""
-    if not (gt_u8.is_cuda and gt_u8.dtype == torch.uint8 and gt_u8.dim() == 4 and gt_u8.shape[3] == 3):
-        raise ValueError('gt_u8 must be a uint8 CUDA tensor [B,H,W,3]; image_restoration_b200 has no CPU path')
-    gt_u8 = gt_u8.contiguous()
-    B, H, W, _ = gt_u8.shape
-    dev = gt_u8.device
+def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=None, gray=None, dev='cuda', **_unused):
+    """Device-side parameter block of a batch for b200ir_degrade_full (taps, per-crop records, noise): build once per
+    batch of draws, reuse across launches.  Arguments as returned by sample_params."""
+    B = len(modes)
     taps, ksize, kmax = _pack_kernels([k if m != 0 else None for k, m in zip(kernels, modes)], np.float64)
     crops = (_lib.DegradeCrop * B)()
     for b in range(B):
@@ -421,17 +456,32 @@ def degrade_full_batch(gt_u8, modes, kernels, sizes, noise=None, quality=None, j
         for i in range(3):
             c.jitter[i] = float(jitter[b][i]) if jitter is not None else 0.0
     lr_wmax, lr_hmax = max(s[0] for s in sizes), max(s[1] for s in sizes)
-    t_crops = torch.frombuffer(bytearray(bytes(crops)), dtype=torch.uint8).to(dev)
-    t_taps = torch.from_numpy(taps).to(dev)
     if noise is not None:
         noise = torch.as_tensor(noise, dtype=torch.float32).to(dev).contiguous()
         assert tuple(noise.shape) == (B, lr_hmax, lr_wmax, 3)
+    return dict(crops=torch.frombuffer(bytearray(bytes(crops)), dtype=torch.uint8).to(dev),
+                taps=torch.from_numpy(taps).to(dev), kmax=kmax, noise=noise, lr_wmax=lr_wmax, lr_hmax=lr_hmax, n=B)
+
+
+def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, quality=None, jitter=None, gray=None,
+                       bgr2rgb=True, return_lr=False, packed=None, **_unused):
+    """One launch of b200ir_degrade_full over a batch (see include/b200ir.h).  gt_u8: uint8 CUDA tensor [B,H,W,3] in
+    the reference's channel order (BGR); the other arguments as returned by sample_params (or packed= the result of
+    pack_degrade_full).  Returns the LQ batch fp32 [B,3,H,W] in [-1,1] (and the low-resolution image after noise /
+    JPEG if return_lr)."""
+    if not (gt_u8.is_cuda and gt_u8.dtype == torch.uint8 and gt_u8.dim() == 4 and gt_u8.shape[3] == 3):
+        raise ValueError('gt_u8 must be a uint8 CUDA tensor [B,H,W,3]; image_restoration_b200 has no CPU path')
+    gt_u8 = gt_u8.contiguous()
+    B, H, W, _ = gt_u8.shape
+    dev = gt_u8.device
+    pk = packed if packed is not None else pack_degrade_full(modes, kernels, sizes, noise, quality, jitter, gray, dev)
+    assert pk['n'] == B
     out = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
-    lr = torch.zeros(B, lr_hmax, lr_wmax, 3, device=dev, dtype=torch.float32) if return_lr else None
+    lr = torch.zeros(B, pk['lr_hmax'], pk['lr_wmax'], 3, device=dev, dtype=torch.float32) if return_lr else None
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)  # noqa: E731
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.lib().b200ir_degrade_full(p(gt_u8), p(t_taps), kmax, p(t_crops), p(noise), lr_wmax, lr_hmax,
-                                                  p(out), p(lr), B, H, W, 1 if bgr2rgb else 0, st),
-                   'b200ir_degrade_full')
+        _lib.check(_lib.lib().b200ir_degrade_full(p(gt_u8), p(pk['taps']), pk['kmax'], p(pk['crops']), p(pk['noise']),
+                                                  pk['lr_wmax'], pk['lr_hmax'], p(out), p(lr), B, H, W,
+                                                  1 if bgr2rgb else 0, st), 'b200ir_degrade_full')
     return (out, lr) if return_lr else out

@@ -109,6 +109,27 @@ def test_kernel_builders_match_reference():
 
 
 @pytest.mark.skipif(not ref_import.available(), reason='/root/reference not present')
+def test_generalized_and_plateau_kinds_match_reference_draws():
+    """Same seeds -> random_mixed_kernel builds the kernel the reference's random_mixed_kernels applies (checked through
+    the blurred image: cv2.filter2D with our kernel == the reference's output)."""
+    deg, _ = ref_import.load_reference_degradations()
+    rng = np.random.default_rng(4)
+    img = rng.random((32, 48, 3)).astype(np.float32)
+    for kind in ('generalized_iso', 'generalized_aniso', 'plateau_iso', 'plateau_aniso', 'iso', 'aniso'):
+        for seed in (1, 2, 3):
+            random.seed(seed)
+            np.random.seed(seed)
+            ref = deg.random_mixed_kernels(img=img, kernel_list=[kind], kernel_prob=[1.0], kernel_size=21,
+                                           sigma_x_range=[0.1, 10], sigma_y_range=[0.1, 10],
+                                           rotation_range=[-math.pi, math.pi], noise_range=None, pad_kernel=True,
+                                           pad_kernel_size=21)
+            mode, k, desc = D.random_mixed_kernel([kind], [1.0], 21, [0.1, 10], [0.1, 10], (-math.pi, math.pi),
+                                                  pad_kernel=True, pad_kernel_size=21, py_random=random.Random(seed),
+                                                  np_random=np.random.RandomState(seed))
+            assert mode == 2 and np.array_equal(cv2.filter2D(img, -1, k), ref), (kind, seed, desc)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='/root/reference not present')
 def test_host_mirror_and_oracle_equal_reference_chain():
     """Same seeds -> the reference's __getitem__ chain and (sample_params + oracle) give the same LQ tensor."""
     import importlib.util
