@@ -4,12 +4,14 @@
 //
 // Reference semantics (see include/b200ir.h for file:line):
 //   blur   : scipy.signal.convolve2d(img_f32[:,:,c], K, mode='same', boundary='fill', fillvalue=255).astype(uint8)
-//            out[y,x] = sum_{i,j} K[i,j] * img[y + ci - i, x + cj - j], fp32 accumulation in (i,j) ascending order,
-//            then truncation to uint8, then /255 in fp32 (degradations.py:363-366)
-//   resize : OpenCV INTER_LINEAR on float32: src = (dst+0.5)*scale-0.5 (double), floor, clamp, horizontal pass then
-//            vertical pass in fp32
+//            out[y,x] = sum_{i,j} K[i,j] * img[y + ci - i, x + cj - j], accumulated in scipy's summation tree and in the
+//            type scipy computes in (blur_taps.cuh: float64 for float64 kernels, float32 for float32 ones), then
+//            truncation to uint8 -- bit-identical -- then /255 in fp32 (degradations.py:363-366)
+//   resize : cv2.resize(INTER_LINEAR) on float32 as the build container's OpenCV runs it (Intel IPP): float64 source
+//            coordinate, fp32 fraction, fma(S1 - S0, f, S0), horizontal pass then vertical pass
 //   noise  : clip(img + noise, 0, 1) (degradations.py:660-669; noise already scaled by sigma/255)
 //   tail   : clamp(round(x*255), 0, 255)/255 then (x-0.5)/0.5 (ffhq_degradation_dataset.py:307-311), BGR->RGB
+#include "blur_taps.cuh"
 #include "host_common.h"
 
 namespace b200ir {
@@ -19,12 +21,6 @@ static constexpr int kDegThreads = 512;
 struct ResizeAxis {
   int i0, i1;
   float w0, w1;
-};
-
-// one non-zero blur tap in scipy's accumulation order: source offset (dy, dx) and weight
-struct NzTap {
-  short dy, dx;
-  float w;
 };
 
 // shared-memory layout (every region 16-byte aligned):
@@ -37,7 +33,7 @@ struct DegLayout {
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline DegLayout deg_layout(int kmax, int lr_wmax, int lr_hmax, int H, int W) {
   DegLayout l;
-  l.row = align16((size_t)kmax * kmax * sizeof(NzTap));
+  l.row = align16((size_t)kmax * kmax * sizeof(DfTap));
   l.col = l.row + (size_t)lr_hmax * sizeof(ResizeAxis);
   l.urow = l.col + (size_t)lr_wmax * sizeof(ResizeAxis);
   l.ucol = l.urow + (size_t)H * sizeof(ResizeAxis);
@@ -67,57 +63,30 @@ __device__ __forceinline__ ResizeAxis cv_linear_tap(int d, int src_n, int dst_n)
 }
 __device__ __forceinline__ float cv_lerp(float s0, float s1, float f) { return __fmaf_rn(__fsub_rn(s1, s0), f, s0); }
 
-__device__ __forceinline__ float blur_at(const uint8_t* __restrict__ img, int H, int W, int y, int x, int c,
-                                         const float* __restrict__ taps, int kmax, int ksz) {
-  // taps: kmax x kmax, the ksz x ksz kernel centred; zero taps contribute nothing and are skipped
-  const int cm = (kmax - 1) >> 1;
-  const int r = (ksz - 1) >> 1;
-  float s = 0.f;
-  for (int i = cm - r; i <= cm + r; ++i) {
-    const int iy = y + cm - i;
-    const bool yin = (iy >= 0) && (iy < H);
-    for (int j = cm - r; j <= cm + r; ++j) {
-      const float t = taps[i * kmax + j];
-      if (t == 0.f) continue;
-      const int ix = x + cm - j;
-      const float v = (yin && ix >= 0 && ix < W) ? (float)img[(iy * W + ix) * 3 + c] : 255.f;
-      s = __fadd_rn(s, __fmul_rn(t, v));
-    }
-  }
-  return s;
-}
-
-__device__ __forceinline__ uint8_t trunc_u8(float s) {
-  s = fminf(fmaxf(s, 0.f), 255.f);
+__device__ __forceinline__ uint8_t trunc_u8(double s) {
+  s = fmin(fmax(s, 0.0), 255.0);
   return (uint8_t)s;  // truncation toward zero, as ndarray.astype(uint8)
 }
 
-// Blur of the three channels of one sample from the compacted tap list (same (i, j)-ascending fp32 accumulation order as
-// scipy.signal.convolve2d; a product and an add per tap, not fused).  kInterior: the whole footprint lies inside the image.
-template <bool kInterior>
-__device__ __forceinline__ void blur3(const uint8_t* __restrict__ img, int H, int W, int y, int x,
-                                      const NzTap* __restrict__ nz, int n_nz, float (&s)[3]) {
-  s[0] = s[1] = s[2] = 0.f;
-  for (int k = 0; k < n_nz; ++k) {
-    const NzTap t = nz[k];
-    const int iy = y + t.dy, ix = x + t.dx;
-    float v0 = 255.f, v1 = 255.f, v2 = 255.f;  // fillvalue outside the image
-    if (kInterior || (iy >= 0 && iy < H && ix >= 0 && ix < W)) {
-      const uint8_t* px = img + (iy * W + ix) * 3;
-      v0 = (float)px[0];
-      v1 = (float)px[1];
-      v2 = (float)px[2];
-    }
-    s[0] = __fadd_rn(s[0], __fmul_rn(t.w, v0));
-    s[1] = __fadd_rn(s[1], __fmul_rn(t.w, v1));
-    s[2] = __fadd_rn(s[2], __fmul_rn(t.w, v2));
+// pyblur blur of the three channels at (y, x) in the reference's arithmetic type; raw sums returned as double (exact
+// for both types)
+__device__ __forceinline__ void blur3(const uint8_t* __restrict__ img, int H, int W, int y, int x, int rad, int f64,
+                                      const DfTap* __restrict__ nz, int n_nz, double (&s)[3]) {
+  if (f64) {
+    df_pyblur_raw<double>(img, H, W, y, x, rad, nz, n_nz, s);
+  } else {
+    float t[3];
+    df_pyblur_raw<float>(img, H, W, y, x, rad, nz, n_nz, t);
+    s[0] = t[0];
+    s[1] = t[1];
+    s[2] = t[2];
   }
 }
 
 template <bool kStage>
 __global__ void __launch_bounds__(kDegThreads, 1)
-degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_all, const int* __restrict__ ksize,
-               int kmax, const int* __restrict__ lr_w, const int* __restrict__ lr_h, const float* __restrict__ noise,
+degrade_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ taps_all, const int* __restrict__ ksize,
+               const int* __restrict__ taps_f64, int kmax, const int* __restrict__ lr_w, const int* __restrict__ lr_h, const float* __restrict__ noise,
                int lr_wmax, int lr_hmax, float* __restrict__ out, int H, int W, int bgr2rgb) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_nnz;
@@ -126,7 +95,7 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
   const int lw = lr_w[b], lh = lr_h[b];
   const int ksz = ksize[b];
   const DegLayout lay = deg_layout(kmax, lr_wmax, lr_hmax, H, W);
-  NzTap* s_nz = reinterpret_cast<NzTap*>(smem);
+  DfTap* s_nz = reinterpret_cast<DfTap*>(smem);
   ResizeAxis* s_row = reinterpret_cast<ResizeAxis*>(smem + lay.row);
   ResizeAxis* s_col = reinterpret_cast<ResizeAxis*>(smem + lay.col);
   ResizeAxis* s_urow = reinterpret_cast<ResizeAxis*>(smem + lay.urow);
@@ -136,27 +105,9 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
   uint8_t* s_gt = smem + lay.gt;
   const uint8_t* g_img = gt + (size_t)b * H * W * 3;
 
-  // non-zero taps, compacted by one warp in (i, j) order: tap (i, j) of the centred ksz x ksz kernel reads the source
-  // pixel at offset (cm - i, cm - j) (true convolution: the kernel is flipped)
+  // non-zero taps with their summation groups, compacted by one warp (blur_taps.cuh)
   if (tid < 32) {
-    const int cm = (kmax - 1) >> 1, r = (ksz - 1) >> 1;
-    const float* tp = taps_all + (size_t)b * kmax * kmax;
-    int count = 0;
-    const int span = 2 * r + 1;
-    for (int base = 0; ksz > 0 && base < span * span; base += 32) {
-      const int e = base + tid;
-      const int i = cm - r + e / span, j = cm - r + e % span;
-      const float t = (e < span * span) ? tp[i * kmax + j] : 0.f;
-      const unsigned m = __ballot_sync(0xffffffffu, t != 0.f);
-      if (t != 0.f) {
-        NzTap z;
-        z.dy = (short)(cm - i);
-        z.dx = (short)(cm - j);
-        z.w = t;
-        s_nz[count + __popc(m & ((1u << tid) - 1u))] = z;
-      }
-      count += __popc(m);
-    }
+    const int count = df_compact_taps(taps_all + (size_t)b * kmax * kmax, kmax, ksz, ksz > 0 ? 1 : 0, s_nz, tid);
     if (tid == 0) s_nnz = count;
   }
   for (int i = tid; i < lh; i += kDegThreads) s_row[i] = cv_linear_tap(i, H, lh);
@@ -173,6 +124,7 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
   const uint8_t* img = kStage ? s_gt : g_img;
   const int n_nz = s_nnz;
   const int rad = (ksz - 1) >> 1;
+  const int f64 = taps_f64 != nullptr ? taps_f64[b] : 0;
 
   // 1a. blurred uint8 samples on the separable grid {row i0/i1} x {col i0/i1}: one thread per sample, three channels
   const int nr = 2 * lh, nc = 2 * lw;
@@ -183,9 +135,8 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
     const int x = (q & 1) ? s_col[q >> 1].i1 : s_col[q >> 1].i0;
     uint8_t* d = s_samp + it * 3;
     if (ksz > 0) {
-      float s3[3];
-      if (y >= rad && y + rad < H && x >= rad && x + rad < W) blur3<true>(img, H, W, y, x, s_nz, n_nz, s3);
-      else blur3<false>(img, H, W, y, x, s_nz, n_nz, s3);
+      double s3[3];
+      blur3(img, H, W, y, x, rad, f64, s_nz, n_nz, s3);
       d[0] = trunc_u8(s3[0]);
       d[1] = trunc_u8(s3[1]);
       d[2] = trunc_u8(s3[2]);
@@ -233,31 +184,44 @@ degrade_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_al
 }
 
 // Full-resolution blur dump for parity tests (uint8 after truncation and/or fp32 before it).
-__global__ void blur_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ taps_all,
-                                 const int* __restrict__ ksize, int kmax, uint8_t* __restrict__ blur_u8,
-                                 float* __restrict__ blur_f32, int B, int H, int W) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)B * H * W * 3;
-  if (idx >= total) return;
-  const int c = (int)(idx % 3);
-  size_t r = idx / 3;
-  const int x = (int)(r % W);
-  r /= W;
-  const int y = (int)(r % H);
-  const int b = (int)(r / H);
-  const uint8_t* img = gt + (size_t)b * H * W * 3;
+// parity aid: the full blurred image as pyblur returns it.  grid (ceil(H*W / 256), B); every block compacts the taps of
+// its crop again (cheap next to H*W*taps).
+__global__ void blur_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ taps_all,
+                                 const int* __restrict__ ksize, const int* __restrict__ taps_f64, int kmax,
+                                 uint8_t* __restrict__ blur_u8, float* __restrict__ blur_f32, int H, int W) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ int s_nnz;
+  DfTap* s_nz = reinterpret_cast<DfTap*>(smem);
+  const int b = blockIdx.y;
   const int ksz = ksize[b];
-  float s = (ksz > 0) ? blur_at(img, H, W, y, x, c, taps_all + (size_t)b * kmax * kmax, kmax, ksz)
-                      : (float)img[(y * W + x) * 3 + c];
-  if (blur_f32) blur_f32[idx] = s;
-  if (blur_u8) blur_u8[idx] = trunc_u8(s);
+  if (threadIdx.x < 32) {
+    const int count = df_compact_taps(taps_all + (size_t)b * kmax * kmax, kmax, ksz, ksz > 0 ? 1 : 0, s_nz, threadIdx.x);
+    if (threadIdx.x == 0) s_nnz = count;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const int x = p % W, y = p / W;
+  const uint8_t* img = gt + (size_t)b * H * W * 3;
+  double s3[3];
+  if (ksz > 0) {
+    blur3(img, H, W, y, x, (ksz - 1) >> 1, taps_f64 != nullptr ? taps_f64[b] : 0, s_nz, s_nnz, s3);
+  } else {
+    for (int c = 0; c < 3; ++c) s3[c] = (double)img[(size_t)p * 3 + c];
+  }
+  const size_t o = ((size_t)b * H * W + p) * 3;
+  for (int c = 0; c < 3; ++c) {
+    if (blur_f32) blur_f32[o + c] = (float)s3[c];
+    if (blur_u8) blur_u8[o + c] = trunc_u8(s3[c]);
+  }
 }
 
 }  // namespace b200ir
 
 using namespace b200ir;
 
-extern "C" int b200ir_degrade(const uint8_t* gt, const float* taps, const int32_t* ksize, int kmax, const int32_t* lr_w,
+extern "C" int b200ir_degrade(const uint8_t* gt, const double* taps, const int32_t* ksize, const int32_t* taps_f64,
+                              int kmax, const int32_t* lr_w,
                               const int32_t* lr_h, const float* noise, int lr_wmax, int lr_hmax, float* out,
                               uint8_t* blur_u8_out, float* blur_f32_out, int B, int H, int W, int bgr2rgb,
                               void* stream) {
@@ -281,18 +245,19 @@ extern "C" int b200ir_degrade(const uint8_t* gt, const float* taps, const int32_
                  lr_hmax);
   if (stage) {
     cudaFuncSetAttribute(degrade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
-    degrade_kernel<true><<<B, kDegThreads, staged, st>>>(gt, taps, ksize, kmax, lr_w, lr_h, noise, lr_wmax, lr_hmax,
+    degrade_kernel<true><<<B, kDegThreads, staged, st>>>(gt, taps, ksize, taps_f64, kmax, lr_w, lr_h, noise, lr_wmax, lr_hmax,
                                                         out, H, W, bgr2rgb);
   } else {
     cudaFuncSetAttribute(degrade_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-    degrade_kernel<false><<<B, kDegThreads, base, st>>>(gt, taps, ksize, kmax, lr_w, lr_h, noise, lr_wmax, lr_hmax,
+    degrade_kernel<false><<<B, kDegThreads, base, st>>>(gt, taps, ksize, taps_f64, kmax, lr_w, lr_h, noise, lr_wmax, lr_hmax,
                                                         out, H, W, bgr2rgb);
   }
   if (check_launch("degrade")) return 1;
   if (blur_u8_out || blur_f32_out) {
-    const size_t n = (size_t)B * H * W * 3;
-    blur_full_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gt, taps, ksize, kmax, blur_u8_out, blur_f32_out, B,
-                                                                  H, W);
+    const size_t tap_bytes = (size_t)kmax * kmax * sizeof(DfTap);
+    cudaFuncSetAttribute(blur_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tap_bytes);
+    blur_full_kernel<<<dim3((unsigned)((H * W + 255) / 256), (unsigned)B), 256, tap_bytes, st>>>(
+        gt, taps, ksize, taps_f64, kmax, blur_u8_out, blur_f32_out, H, W);
     if (check_launch("degrade(blur dump)")) return 1;
   }
   return 0;

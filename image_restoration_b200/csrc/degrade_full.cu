@@ -14,6 +14,7 @@
 //   tail        clamp(round(x*255), 0, 255)/255, (x-0.5)/0.5, BGR->RGB, NCHW  (:288, :307-311)
 // The blur is evaluated only at the 2x2 source pixels each low-resolution pixel interpolates (4 lanes per LR pixel, combined
 // with shuffles); the GT crop is staged in shared memory once.
+#include "blur_taps.cuh"
 #include "host_common.h"
 
 namespace b200ir {
@@ -24,17 +25,6 @@ struct DfAxis {
   int i0, i1;
   float w0, w1;
 };
-// one non-zero blur tap: weight, source offset, and where it sits in the reference's summation tree
-struct DfTap {
-  double w;
-  short dy, dx;
-  int grp;  // (group id << 2) | 2 * last-of-group | first-of-group
-};
-__device__ __forceinline__ float df_mul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float df_add(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double df_mul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double df_add(double a, double b) { return __dadd_rn(a, b); }
-
 // cv2.resize(INTER_LINEAR) tap for destination index d, resize from `src_n` to `dst_n` samples, AS EXECUTED for float
 // images in the build container (opencv-python 4.13 dispatches to Intel IPP): source coordinate (d + 0.5) * src/dst - 0.5
 // in float64, fraction rounded to fp32, indices clamped; each pass is fma(S1 - S0, f, S0), horizontal pass first.
@@ -169,75 +159,6 @@ __host__ __device__ inline DfLayout df_layout(int kmax, int lr_wmax, int lr_hmax
   return l;
 }
 
-// Blur of the three channels at (y, x), in the arithmetic type T the reference's library call used.
-// kMode 1: scipy.signal.convolve2d on the uint8 values, fill 255 outside (pyblur).  scipy 1.18 (this container; pinned
-//   1.9.3) walks the kernel rows in ascending order and, inside a row, adds blocks of four columns as
-//   ((p0 + p1) + p2) + p3 to the running sum, then the remaining columns one by one -- products and sums rounded
-//   separately, in float64 when the kernel is float64 (box / disk / line under NumPy 2) and float32 when it is float32
-//   (psf).  The tap list carries that tree (first / last of group), so the result is bit-identical; zero taps add
-//   exact zeros and are dropped.
-// kMode 2: cv2.filter2D on value/255, BORDER_REFLECT_101: every tap is its own group (plain running sum, fp32).
-template <typename T, int kMode, bool kInterior>
-__device__ __forceinline__ void df_blur3(const uint8_t* __restrict__ img, const float* __restrict__ lut, int H, int W, int y,
-                                         int x, const DfTap* __restrict__ nz, int n_nz, T (&s)[3]) {
-  s[0] = s[1] = s[2] = (T)0;
-  T g0 = (T)0, g1 = (T)0, g2 = (T)0;
-  for (int k = 0; k < n_nz; ++k) {
-    const DfTap t = nz[k];
-    const T w = (T)t.w;
-    int iy = y + t.dy, ix = x + t.dx;
-    T v0, v1, v2;
-    if (kMode == 1) {
-      v0 = v1 = v2 = (T)255;
-      if (kInterior || (iy >= 0 && iy < H && ix >= 0 && ix < W)) {
-        const uint8_t* px = img + (iy * W + ix) * 3;
-        v0 = (T)px[0];
-        v1 = (T)px[1];
-        v2 = (T)px[2];
-      }
-    } else {
-      if (!kInterior) {
-        iy = iy < 0 ? -iy : (iy >= H ? 2 * H - 2 - iy : iy);
-        ix = ix < 0 ? -ix : (ix >= W ? 2 * W - 2 - ix : ix);
-      }
-      const uint8_t* px = img + (iy * W + ix) * 3;
-      v0 = (T)lut[px[0]];
-      v1 = (T)lut[px[1]];
-      v2 = (T)lut[px[2]];
-    }
-    const T p0 = df_mul(w, v0), p1 = df_mul(w, v1), p2 = df_mul(w, v2);
-    if (t.grp & 1) {
-      g0 = p0;
-      g1 = p1;
-      g2 = p2;
-    } else {
-      g0 = df_add(g0, p0);
-      g1 = df_add(g1, p1);
-      g2 = df_add(g2, p2);
-    }
-    if (t.grp & 2) {
-      s[0] = df_add(s[0], g0);
-      s[1] = df_add(s[1], g1);
-      s[2] = df_add(s[2], g2);
-    }
-  }
-}
-
-template <typename T, int kMode>
-__device__ __forceinline__ void df_blur3_at(const uint8_t* __restrict__ img, const float* __restrict__ lut, int H, int W,
-                                            int y, int x, int rad, const DfTap* __restrict__ nz, int n_nz, float (&v)[3]) {
-  T s[3];
-  if (y >= rad && y + rad < H && x >= rad && x + rad < W) df_blur3<T, kMode, true>(img, lut, H, W, y, x, nz, n_nz, s);
-  else df_blur3<T, kMode, false>(img, lut, H, W, y, x, nz, n_nz, s);
-  if (kMode == 1) {  // .astype(uint8) (truncation; the sum is inside [0, 255] up to rounding), then / 255
-#pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = lut[(int)fmin(fmax((double)s[c], 0.0), 255.0)];
-  } else {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = (float)s[c];
-  }
-}
-
 template <bool kStage>
 __global__ void __launch_bounds__(kDfThreads, 1)
 degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ taps_all, int kmax,
@@ -266,43 +187,7 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
 
   // ---- set-up: compacted taps (one warp, kernel order), resize taps, u8/255 table, quantisation tables, GT staging
   if (tid < 32) {
-    const int cm = (kmax - 1) >> 1, r = (ksz - 1) >> 1;
-    const double* tp = taps_all + (size_t)b * kmax * kmax;
-    int count = 0;
-    const int span = 2 * r + 1;
-    const int blocked = span & ~3;  // columns summed in blocks of four by convolve2d
-    for (int base = 0; mode != 0 && ksz > 0 && base < span * span; base += 32) {
-      const int e = base + tid;
-      const int ir = e / span, jr = e % span;
-      const int i = cm - r + ir, j = cm - r + jr;
-      const double t = (e < span * span) ? tp[i * kmax + j] : 0.0;
-      const unsigned m = __ballot_sync(0xffffffffu, t != 0.0);
-      if (t != 0.0) {
-        DfTap z;
-        // convolution (pyblur) reads the flipped offset, correlation (filter2D) the direct one
-        z.dy = (short)(mode == 1 ? cm - i : i - cm);
-        z.dx = (short)(mode == 1 ? cm - j : j - cm);
-        z.w = t;
-        const int gid = (mode == 1 && jr < blocked) ? ir * 64 + (jr >> 2) : ir * 64 + 32 + jr;
-        z.grp = gid << 2;
-        s_nz[count + __popc(m & ((1u << tid) - 1u))] = z;
-      }
-      count += __popc(m);
-    }
-    __syncwarp();
-    for (int base = 0; base < count; base += 32) {  // first / last of its group among the non-zero taps
-      const int k = base + tid;
-      int bits = 0, gid = 0;
-      if (k < count) {
-        gid = s_nz[k].grp >> 2;
-        const int prev = k > 0 ? (s_nz[k - 1].grp >> 2) : -1;
-        const int next = k + 1 < count ? (s_nz[k + 1].grp >> 2) : -1;
-        bits = (prev != gid ? 1 : 0) | (next != gid ? 2 : 0);
-      }
-      __syncwarp();
-      if (k < count) s_nz[k].grp = (gid << 2) | bits;
-      __syncwarp();
-    }
+    const int count = df_compact_taps(taps_all + (size_t)b * kmax * kmax, kmax, ksz, mode, s_nz, tid);
     if (tid == 0) s_nnz = count;
   }
   for (int i = tid; i < lh; i += kDfThreads) s_row[i] = df_linear_tap(i, H, lh);

@@ -175,11 +175,15 @@ def _pack_kernels(kernels, dtype=np.float32):
 
 def pack_degradation(kernels, lr_sizes, dev):
     """Device-side parameter block of a batch (blur taps, kernel sizes, low-resolution sizes): build once, reuse."""
-    taps, ksize, kmax = _pack_kernels(kernels)
+    taps, ksize, kmax = _pack_kernels(kernels, np.float64)
+    # the dtype of each kernel selects the arithmetic type of the reference's convolve2d (float64 box / disk / line
+    # kernels under NumPy 2, float32 psf kernels)
+    f64 = np.asarray([1 if (k is not None and np.asarray(k).dtype == np.float64) else 0 for k in kernels], dtype=np.int32)
     lw = np.asarray([s[0] for s in lr_sizes], dtype=np.int32)
     lh = np.asarray([s[1] for s in lr_sizes], dtype=np.int32)
     assert lw.min() >= 1 and lh.min() >= 1
-    return dict(taps=torch.from_numpy(taps).to(dev), ks=torch.from_numpy(ksize).to(dev), lw=torch.from_numpy(lw).to(dev),
+    return dict(taps=torch.from_numpy(taps).to(dev), ks=torch.from_numpy(ksize).to(dev), f64=torch.from_numpy(f64).to(dev),
+                lw=torch.from_numpy(lw).to(dev),
                 lh=torch.from_numpy(lh).to(dev), kmax=kmax, lr_wmax=int(lw.max()), lr_hmax=int(lh.max()), n=len(lw))
 
 
@@ -209,7 +213,7 @@ def degrade_batch(gt_u8, kernels, lr_sizes, noise=None, bgr2rgb=True, return_blu
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)  # noqa: E731
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.lib().b200ir_degrade(p(gt_u8), p(t_taps), p(t_ks), kmax, p(t_lw), p(t_lh), p(noise), lr_wmax,
+        _lib.check(_lib.lib().b200ir_degrade(p(gt_u8), p(t_taps), p(t_ks), p(pk['f64']), kmax, p(t_lw), p(t_lh), p(noise), lr_wmax,
                                              lr_hmax, p(out), p(blur_u8), p(blur_f32), B, H, W, 1 if bgr2rgb else 0,
                                              st), 'b200ir_degrade')
     if return_blur:

@@ -294,13 +294,17 @@ int b200ir_ca_scale_add(const void* x, const float* att, const void* identity, v
  * (ffhq_degradation_dataset.py:244-272,307-311; degradations.py:660-669).
  *
  * gt:     uint8 [B][H][W][3] (the uint8 image random_pyblur builds: np.array(img*255, dtype=uint8))
- * taps:   fp32 [B][kmax][kmax] blur kernels, zero padded, centred; ksize[b] odd (0 = no blur)
+ * taps:   fp64 [B][kmax][kmax] blur kernels, zero padded, centred; ksize[b] odd (0 = no blur)
+ * taps_f64: int32 [B] (NULL = all 0): 1 = the reference's convolve2d ran in float64 for this crop (box / disk / line
+ *         kernels are float64 under NumPy 2), 0 = in float32 (psf kernels; every kernel under the pinned NumPy 1.23).
+ *         The blur reproduces scipy's summation tree in that type: the truncated uint8 image is bit-identical.
  * lr_w/lr_h: int32 [B] low-resolution size per crop; noise: fp32 [B][lr_hmax][lr_wmax][3] (already sigma/255-scaled)
  * out:    fp32 NCHW [B][3][H][W], (x-0.5)/0.5-normalised, channel order reversed if bgr2rgb.
  * blur_u8_out / blur_f32_out (optional, parity checks): the full blurred image [B][H][W][3] as pyblur returns it
  *         (uint8, truncated) and the fp32 convolution result before the truncation.
  */
-int b200ir_degrade(const uint8_t* gt, const float* taps, const int32_t* ksize, int kmax, const int32_t* lr_w,
+int b200ir_degrade(const uint8_t* gt, const double* taps, const int32_t* ksize, const int32_t* taps_f64, int kmax,
+                   const int32_t* lr_w,
                    const int32_t* lr_h, const float* noise, int lr_wmax, int lr_hmax, float* out, uint8_t* blur_u8_out,
                    float* blur_f32_out, int B, int H, int W, int bgr2rgb, void* stream);
 

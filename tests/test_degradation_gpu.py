@@ -1,8 +1,8 @@
 """GPU parity of the fused degradation kernel (through the C ABI) against the CPU oracle (scipy convolve2d + cv2.resize,
 i.e. the reference's own library calls) on seeded synthetic crops.
-Tolerances: fp32 blur within 1e-5 * 255 (north_star: "within 1e-5"); blurred byte identical except where the fp32
-value is within that distance of an integer (truncation tie); final LQ tensor identical on the 8-bit grid except
-where a tie / rounding boundary flips one code (2/255 in [-1,1] units)."""
+Bar (north_star: "within 1e-5"): the kernel reproduces scipy's summation tree in scipy's arithmetic type and the IPP
+resize arithmetic of cv2 (restated and pinned in tests/test_degrade_full_cpu.py), so everything is required to be
+IDENTICAL: the convolution sum, the truncated blurred byte (ties included) and the final LQ tensor."""
 import numpy as np
 import pytest
 import torch
@@ -44,25 +44,11 @@ def test_degrade_matches_oracle(H, W):
     for b in range(B):
         lw, lh = sizes[b]
         if kernels[b] is not None:
-            ref_f = po.blur_f32(gt[b], kernels[b])
-            err = np.abs(blur_f32[b] - ref_f).max()
-            assert err <= 1e-5 * 255, (b, err)
-            ref_u8 = ref_f.astype('uint8')
-            diff = blur_u8[b] != ref_u8
-            tie = np.abs(ref_f - np.round(ref_f)) <= 1e-5 * 255
-            assert not np.any(diff & ~tie), (b, int((diff & ~tie).sum()))
-            assert np.all(np.abs(blur_u8[b].astype(int) - ref_u8.astype(int)) <= 1)
-        # feed the oracle the byte image the device produced so that ties do not propagate into the later stages
-        ref = degrade_from_blurred(blur_u8[b] if kernels[b] is not None else gt[b], sizes[b], noise[b, :lh, :lw], H, W)
-        d = np.abs(out[b] - ref)
-        flips = (d > 1e-6).mean()
-        print(f'crop {b}: lr={sizes[b]} blur max err {0 if kernels[b] is None else err:.2e} '
-              f'out max diff {d.max():.4f} flipped codes {flips:.2e}')
-        assert d.max() <= 2 / 255 + 1e-6 and flips <= 2e-3
-
-
-def degrade_from_blurred(blur_u8, lr_size, noise, H, W):
-    return po.degrade(blur_u8, None, lr_size, noise, bgr2rgb=True)
+            ref_f = po.blur_f32(gt[b], kernels[b])              # scipy.signal.convolve2d, float64 or float32
+            assert np.array_equal(blur_f32[b], ref_f.astype(np.float32)), (b, np.abs(blur_f32[b] - ref_f).max())
+            assert np.array_equal(blur_u8[b], ref_f.astype('uint8')), (b, int((blur_u8[b] != ref_f.astype('uint8')).sum()))
+        ref = po.degrade(gt[b], kernels[b], sizes[b], noise[b, :lh, :lw], bgr2rgb=True)
+        assert np.array_equal(out[b], ref), (b, np.abs(out[b] - ref).max() * 127.5)
 
 
 def test_pyblur_style_operators():
@@ -73,10 +59,8 @@ def test_pyblur_style_operators():
                         (dg.LinearMotionBlur, (13, 45, 'full'), po.line_kernel(13, 45, 'full')),
                         (dg.PsfBlur, (10,), po.psf_kernel(10))):
         got = fn(img, *args)
-        ref_f = po.blur_f32(img, k)
-        tie = np.abs(ref_f - np.round(ref_f)) <= 1e-5 * 255
         assert got.shape == img.shape and got.dtype == np.uint8
-        assert not np.any((got != ref_f.astype('uint8')) & ~tie)
+        assert np.array_equal(got, po.blur_u8(img, k))
     out = dg.RandomizedBlur(torch.from_numpy(img)[None].cuda(), np.random.RandomState(0))
     assert out.shape == (1, 64, 192, 3) and out.dtype == torch.uint8
 
