@@ -340,7 +340,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          __half2 h = f2h2_sat(v[2 * j], v[2 * j + 1]);
           pk[j] = *reinterpret_cast<uint32_t*>(&h);
         }
         const long long pso = p.ps_r ? ps_offset(p, n0, c0) : 0;
@@ -531,7 +531,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
       uint32_t pk[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        __half2 h = f2h2_sat(v[2 * j], v[2 * j + 1]);
         pk[j] = *reinterpret_cast<uint32_t*>(&h);
       }
       const __half* op = r.out + c0 + (p.ps_r ? ps_offset(p, n0, c0) : 0);
@@ -651,7 +651,7 @@ __device__ __forceinline__ void epilogue_upfold(const ConvParams& p, uint32_t ta
     uint32_t pk[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      __half2 h = f2h2_sat(v[2 * j], v[2 * j + 1]);
       pk[j] = *reinterpret_cast<uint32_t*>(&h);
     }
     const __half* op = out_b + (long long)yo * p.out_sy + (long long)xo * p.out_sx + cc;

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(NT + 32, (NT == 256 && !(POST && XP == 2)) ? 2
               uint4 o;
               __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+              for (int e = 0; e < 4; ++e) oh[e] = f2h2_sat(v[2 * e], v[2 * e + 1]);
               *reinterpret_cast<uint4*>(out_row + (long long)r * p.out_sy + (long long)j * p.C) = o;
             }
           }

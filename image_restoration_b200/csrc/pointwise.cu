@@ -2,6 +2,7 @@
 // Reference semantics: see include/b200ir.h; numerics follow upfirdn2d.py:162-192 (zero padding, FIR
 // outer([1,3,3,1])/64), F.interpolate bilinear align_corners=False, fused_bias_act_kernel.cu:27-48.
 #include "host_common.h"
+#include "ptx.cuh"
 
 namespace b200ir {
 
@@ -28,7 +29,7 @@ __device__ __forceinline__ void st8(__half* p, const H8& r) {
   uint4 q;
   __half2* h = reinterpret_cast<__half2*>(&q);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(r.v[2 * i], r.v[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) h[i] = f2h2_sat(r.v[2 * i], r.v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = q;
 }
 __device__ __forceinline__ float lrelu_s(float x) { return (x > 0.f ? x : 0.2f * x) * kSqrt2; }

@@ -8,6 +8,15 @@
 
 namespace b200ir {
 
+// fp32 pair -> packed fp16 with saturation (F2FP.SATFINITE, same cost as the plain conversion): activations beyond
+// +-65504 clamp instead of turning into inf and then NaN downstream (trained StyleGAN2 checkpoints have such outliers;
+// the reference runs fp32 and never sees them).  Identical to __floats2half2_rn for every in-range value.
+__device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -62,7 +62,7 @@ __device__ __forceinline__ void rs_store8(__half* p, const float* v) {
   uint4 o;
   __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+  for (int e = 0; e < 4; ++e) oh[e] = f2h2_sat(v[2 * e], v[2 * e + 1]);
   *reinterpret_cast<uint4*>(p) = o;
 }
 

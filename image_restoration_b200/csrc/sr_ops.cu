@@ -3,6 +3,7 @@
 // image, and RCAN's channel attention (global average pool -> 1x1 -> ReLU -> 1x1 -> sigmoid -> scale, rcan_arch.py:8-24).
 // The 3x3 convolutions, their activations, residual merges and nn.PixelShuffle run in b200ir_conv_igemm.
 #include "host_common.h"
+#include "ptx.cuh"
 
 namespace b200ir {
 
@@ -38,7 +39,7 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __half* __r
         v[e] = (__ldg(x + src) - (sub ? __ldg(sub + c) : 0.f)) * mul;
       }
     }
-    h[j] = __floats2half2_rn(v[0], v[1]);
+    h[j] = f2h2_sat(v[0], v[1]);
   }
   *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<uint4*>(h);
 }
@@ -166,7 +167,7 @@ __global__ void ca_scale_add_kernel(const __half* __restrict__ x, const float* _
     const float2 fx = __half22float2(hx[j]), fi = __half22float2(hi[j]);
     const float a0 = (att ? __ldg(att + (long long)b * C + g * 8 + 2 * j) : 1.f) * res_scale;
     const float a1 = (att ? __ldg(att + (long long)b * C + g * 8 + 2 * j + 1) : 1.f) * res_scale;
-    ho[j] = __floats2half2_rn(fx.x * a0 + fi.x, fx.y * a1 + fi.y);
+    ho[j] = f2h2_sat(fx.x * a0 + fi.x, fx.y * a1 + fi.y);
   }
   *reinterpret_cast<uint4*>(out + pix * out_stride + g * 8) = *reinterpret_cast<uint4*>(ho);
 }

@@ -529,3 +529,24 @@ def test_conv_up_layer_folded(B, h, w, cin, cout):
     err = (got - ref).abs().max().item()
     print(f'folded ConvUpLayer {cin}->{cout} {h}x{w}: interior {err_in:.3e} full {err:.3e} scale {ref.abs().max().item():.2f}')
     assert err <= 1.5e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize('cin,cout,H,W', [(256, 256, 16, 48), (32, 32, 128, 384)])
+def test_fp16_stores_saturate_instead_of_overflowing(cin, cout, H, W):
+    """Activations are stored as fp16; the reference computes in fp32.  Values beyond +-65504 must clamp to the largest
+    finite fp16 (F2FP.SATFINITE) rather than become inf, which would turn into NaN in the next layer."""
+    ops = _ops()
+    torch.manual_seed(3)
+    x = torch.randn(1, cin, H, W, device=DEV) * 200
+    w = torch.randn(cout, cin, 3, 3, device=DEV) * 2
+    xh, wh = nhwc16(x), pack3x3(w)
+    out = torch.empty(1, H, W, cout, device=DEV, dtype=torch.float16)
+    ops.conv_same(xh, wh, out, 3, bias=torch.zeros(cout, device=DEV), act=True)()
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(F.conv2d(nchw32(xh), wh.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), padding=1), 0.2) * math.sqrt(2)
+    assert ref.abs().max().item() > 65504                     # the case is real: fp32 result exceeds the fp16 range
+    got = nchw32(out)
+    assert torch.isfinite(got).all()
+    assert torch.equal(got, ref.clamp(-65504, 65504).half().float()) or \
+        (got - ref.clamp(-65504, 65504)).abs().max().item() <= 1e-2 * 65504
+    assert (got.abs() == 65504).any()
