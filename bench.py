@@ -293,7 +293,7 @@ def main():
         packed = dg.pack_degradation(kernels, sizes, dev)
         ms = timed(lambda: dg.degrade_batch(gt_d, kernels, sizes, nz_d, packed=packed), 10, 3) / 10
         t0 = time.time()
-        n_cpu = 6
+        n_cpu = 8
         for b in range(n_cpu):
             lw, lh = sizes[b]
             po.degrade(gt[b], kernels[b], sizes[b], nz[b, :lh, :lw])
@@ -308,8 +308,8 @@ def main():
 
         # the whole LQ synthesis of __getitem__ (blur kinds of the training YAML, JPEG, jitter, gray) in one launch
         from oracle import degrade_full_oracle as dfo
-        opt = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'pyblur'],
-                   kernel_prob=[0.2, 0.2, 0.15, 0.15, 0.3], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
+        opt = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'],
+                   kernel_prob=[0.08, 0.08, 0.08, 0.08, 0.08, 0.08, 0.28], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
                    noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.1)
         import random as _random
         prm = dg.sample_params(DB, H, W, opt, py_random=_random.Random(0), np_random=np.random.RandomState(0))
@@ -319,7 +319,8 @@ def main():
         for b in range(n_cpu):
             lw, lh = prm['sizes'][b]
             dfo.degrade_full(gt[b], prm['modes'][b], prm['kernels'][b], (lw, lh), prm['noise'][b, :lh, :lw],
-                             prm['quality'][b], prm['jitter'][b], prm['gray'][b], exact_blur=False, lib_jpeg=True)
+                             prm['quality'][b], prm['jitter'][b], prm['gray'][b], exact_blur=False, lib_jpeg=True,
+                             bilateral_sigma=prm['bilateral_sigma'][b])
         cpu_full_ms = (time.time() - t0) / n_cpu * 1e3
         # BASELINE config 4: tiled full-frame inference, 3x1080x1920 -> 45 overlapping 256x256 tiles in one batch
         from image_restoration_b200.tiling import TiledRestorer
@@ -337,7 +338,9 @@ def main():
         del net256, tiler
         degr['full_chain'] = {'kernel': 'degrade_full_kernel', 'crops_per_s': DB / (ms_full / 1e3), 'ms_per_batch': ms_full,
                               'batch': DB, 'achieved_gbs': alg / ms_full / 1e6,
-                              'stages': 'blur (iso/aniso/motion/average/pyblur) + resize + noise + JPEG + resize + jitter + gray',
+                              'stages': 'blur (iso/aniso/motion/average/median/bilateral/pyblur, kernel_list and kernel_prob of '
+                                        'training_config/train_gfpgan_v4_square_license_mix_pyblur.yml) + resize + noise + '
+                                        'JPEG + resize + jitter + gray',
                               'cpu_reference': {'ms_per_crop': cpu_full_ms, 'crops_per_s': 1e3 / cpu_full_ms, 'cores': 1,
                                                 'kind': 'port', 'sample': f'{n_cpu} crops through cv2.filter2D / scipy '
                                                 'convolve2d + cv2.resize + cv2.imencode/imdecode (the reference\'s calls)'}}

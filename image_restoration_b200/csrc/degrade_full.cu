@@ -138,7 +138,7 @@ __device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
 
 // shared-memory layout
 struct DfLayout {
-  size_t row, col, urow, ucol, lut, qt, lr, yp, cbp, crp, gt, total;
+  size_t row, col, urow, ucol, lut, cw, qt, lr, yp, cbp, crp, gt, total;
 };
 __host__ __device__ inline size_t df_align(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline DfLayout df_layout(int kmax, int lr_wmax, int lr_hmax, int H, int W, bool stage) {
@@ -149,7 +149,8 @@ __host__ __device__ inline DfLayout df_layout(int kmax, int lr_wmax, int lr_hmax
   l.urow = l.col + (size_t)lr_wmax * sizeof(DfAxis);
   l.ucol = l.urow + (size_t)H * sizeof(DfAxis);
   l.lut = df_align(l.ucol + (size_t)W * sizeof(DfAxis));
-  l.qt = l.lut + 256 * sizeof(float);
+  l.cw = l.lut + 256 * sizeof(float);   // bilateral colour weights, 3 * 256 entries
+  l.qt = l.cw + 768 * sizeof(float);
   l.lr = l.qt + 128 * sizeof(int);
   l.yp = df_align(l.lr + (size_t)lr_hmax * lr_wmax * 3 * sizeof(float));
   l.cbp = l.yp + (size_t)hp * wp * sizeof(int);
@@ -157,6 +158,73 @@ __host__ __device__ inline DfLayout df_layout(int kmax, int lr_wmax, int lr_hmax
   l.gt = df_align(l.crp + (size_t)(hp / 2) * (wp / 2) * sizeof(int));
   l.total = l.gt + (stage ? (size_t)H * W * 3 : 0);
   return l;
+}
+
+// cv2.medianBlur(uint8 image, k) at (y, x), BORDER_REPLICATE: exact median of the k*k window per channel, found by a
+// radix-4 search on the value (four passes over the window, three thresholds per pass).
+template <bool kInterior>
+__device__ __forceinline__ void df_median3(const uint8_t* __restrict__ img, int H, int W, int y, int x, int rad,
+                                           int (&med)[3]) {
+  const int need = ((2 * rad + 1) * (2 * rad + 1)) / 2 + 1;  // 1-based rank of the median
+  int lo[3] = {0, 0, 0};
+#pragma unroll 1
+  for (int shift = 6; shift >= 0; shift -= 2) {
+    int t1[3], c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0}, c3[3] = {0, 0, 0};
+    const int step = 1 << shift;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) t1[c] = lo[c] + step;
+    for (int dy = -rad; dy <= rad; ++dy) {
+      const int iy = kInterior ? y + dy : min(max(y + dy, 0), H - 1);
+      const uint8_t* row = img + iy * W * 3;
+      for (int dx = -rad; dx <= rad; ++dx) {
+        const int ix = kInterior ? x + dx : min(max(x + dx, 0), W - 1);
+        const uint8_t* px = row + ix * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int v = px[c];
+          c1[c] += v < t1[c];
+          c2[c] += v < t1[c] + step;
+          c3[c] += v < t1[c] + 2 * step;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) lo[c] += (c1[c] >= need) ? 0 : (c2[c] >= need) ? step : (c3[c] >= need) ? 2 * step : 3 * step;
+  }
+  med[0] = lo[0];
+  med[1] = lo[1];
+  med[2] = lo[2];
+}
+
+// cv2.bilateralFilter(uint8 image, d, sigma, sigma) at (y, x), BORDER_REFLECT_101 (bilateral_filter.simd.hpp, 8-bit three
+// channel path): taps inside the radius in row-major order, weight = space[k] * colour[|db| + |dg| + |dr|] (fp32),
+// sum = fma(value, weight, sum), result cvRound(sum / wsum).  nz holds the space weights (built on the host exactly as
+// OpenCV does), cw the colour table.
+template <bool kInterior>
+__device__ __forceinline__ void df_bilateral3(const uint8_t* __restrict__ img, int H, int W, int y, int x,
+                                              const DfTap* __restrict__ nz, int n_nz, const float* __restrict__ cw,
+                                              int (&out)[3]) {
+  const uint8_t* cp = img + (y * W + x) * 3;
+  const int c0 = cp[0], c1 = cp[1], c2 = cp[2];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, ws = 0.f;
+  for (int k = 0; k < n_nz; ++k) {
+    const DfTap t = nz[k];
+    int iy = y + t.dy, ix = x + t.dx;
+    if (!kInterior) {
+      iy = iy < 0 ? -iy : (iy >= H ? 2 * H - 2 - iy : iy);
+      ix = ix < 0 ? -ix : (ix >= W ? 2 * W - 2 - ix : ix);
+    }
+    const uint8_t* px = img + (iy * W + ix) * 3;
+    const int b = px[0], g = px[1], r = px[2];
+    const float w = __fmul_rn((float)t.w, cw[abs(b - c0) + abs(g - c1) + abs(r - c2)]);
+    s0 = __fmaf_rn((float)b, w, s0);
+    s1 = __fmaf_rn((float)g, w, s1);
+    s2 = __fmaf_rn((float)r, w, s2);
+    ws = __fadd_rn(ws, w);
+  }
+  out[0] = min(max((int)rintf(__fdiv_rn(s0, ws)), 0), 255);
+  out[1] = min(max((int)rintf(__fdiv_rn(s1, ws)), 0), 255);
+  out[2] = min(max((int)rintf(__fdiv_rn(s2, ws)), 0), 255);
 }
 
 template <bool kStage>
@@ -177,6 +245,7 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
   DfAxis* s_urow = reinterpret_cast<DfAxis*>(smem + lay.urow);
   DfAxis* s_ucol = reinterpret_cast<DfAxis*>(smem + lay.ucol);
   float* s_lut = reinterpret_cast<float*>(smem + lay.lut);
+  float* s_cw = reinterpret_cast<float*>(smem + lay.cw);
   int* s_qt = reinterpret_cast<int*>(smem + lay.qt);
   float* s_lr = reinterpret_cast<float*>(smem + lay.lr);
   int* s_y = reinterpret_cast<int*>(smem + lay.yp);
@@ -187,8 +256,13 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
 
   // ---- set-up: compacted taps (one warp, kernel order), resize taps, u8/255 table, quantisation tables, GT staging
   if (tid < 32) {
-    const int count = df_compact_taps(taps_all + (size_t)b * kmax * kmax, kmax, ksz, mode, s_nz, tid);
+    const int count = df_compact_taps(taps_all + (size_t)b * kmax * kmax, kmax, ksz, mode == 4 ? 2 : (mode == 3 ? 0 : mode),
+                                      s_nz, tid);
     if (tid == 0) s_nnz = count;
+  }
+  if (mode == 4) {  // colour weights: (float)exp(i * i * -0.5 / sigma^2), evaluated in double as OpenCV does
+    const double gc = -0.5 / ((double)cp.bilateral_sigma * (double)cp.bilateral_sigma);
+    for (int i = tid; i < 768; i += kDfThreads) s_cw[i] = (float)exp((double)(i * i) * gc);
   }
   for (int i = tid; i < lh; i += kDfThreads) s_row[i] = df_linear_tap(i, H, lh);
   for (int i = tid; i < lw; i += kDfThreads) s_col[i] = df_linear_tap(i, W, lw);
@@ -211,7 +285,7 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
   const uint8_t* img = kStage ? s_gt : g_img;
   const int n_nz = s_nnz;
   const int rad = (ksz - 1) >> 1;
-  const bool do_blur = mode != 0 && ksz > 0 && n_nz > 0;
+  const bool do_blur = mode != 0 && ksz > 0 && (n_nz > 0 || mode == 3);
 
   // ---- 1. blur at the 2x2 source pixels of every LR pixel (4 lanes per LR pixel), down-resize, noise, clip
   {
@@ -231,8 +305,21 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
         if (mode == 1) {
           if (cp.blur_f64) df_blur3_at<double, 1>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
           else df_blur3_at<float, 1>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
-        } else {
+        } else if (mode == 2) {
           df_blur3_at<float, 2>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
+        } else {
+          const bool inside = y >= rad && y + rad < H && x >= rad && x + rad < W;
+          int u[3];
+          if (mode == 3) {
+            if (inside) df_median3<true>(img, H, W, y, x, rad, u);
+            else df_median3<false>(img, H, W, y, x, rad, u);
+          } else {
+            if (inside) df_bilateral3<true>(img, H, W, y, x, s_nz, n_nz, s_cw, u);
+            else df_bilateral3<false>(img, H, W, y, x, s_nz, n_nz, s_cw, u);
+          }
+          v[0] = s_lut[u[0]];
+          v[1] = s_lut[u[1]];
+          v[2] = s_lut[u[2]];
         }
       } else {
         const uint8_t* p = img + (y * W + x) * 3;

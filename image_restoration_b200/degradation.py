@@ -277,7 +277,7 @@ def random_degradation_params(B, H, W, downsample_range=(4, 12), noise_range=(0,
 # reference run draw for draw.
 FILTER2D_KINDS = ('iso', 'aniso', 'generalized_iso', 'generalized_aniso', 'plateau_iso', 'plateau_aniso', 'motion',
                   'average')
-UNSUPPORTED_KINDS = ('median', 'bilateral', 'pyblur_motion', 'random_cover', 'bicubic')
+UNSUPPORTED_KINDS = ('pyblur_motion', 'random_cover', 'bicubic')
 
 
 def mesh_axis(kernel_size):
@@ -343,6 +343,18 @@ def average_kernel(kernel_size):
     return np.ones((kernel_size, kernel_size), np.float32) / (kernel_size * kernel_size)
 
 
+def bilateral_space_kernel(d, sigma_space):
+    """Space weights of cv2.bilateralFilter (bilateral_filter.dispatch.cpp): radius = d // 2, for every (i, j) with
+    sqrt(i^2 + j^2) <= radius the weight (float)exp(r^2 * -0.5 / sigma^2); zero outside the circle.  float32 [2r+1, 2r+1]."""
+    radius = max(d // 2, 1)
+    gs = -0.5 / (float(sigma_space) * float(sigma_space))
+    ax = np.arange(-radius, radius + 1, dtype=np.float64)
+    r = np.sqrt(ax[:, None] ** 2 + ax[None, :] ** 2)
+    k = np.exp(r * r * gs).astype(np.float32)
+    k[r > radius] = 0
+    return k
+
+
 def _pad_to(k, size):
     pad = (size - k.shape[0]) // 2
     return np.pad(k, ((pad, pad), (pad, pad))) if pad > 0 else k
@@ -352,7 +364,8 @@ def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=
                         rotation_range=(-math.pi, math.pi), pad_kernel=False, pad_kernel_size=21, py_random=None,
                         np_random=np.random, betag_range=(0.5, 8), betap_range=(0.5, 8)):
     """The kernel random_mixed_kernels would apply (degradations.py:419-523), drawn with the same calls in the same
-    order.  Returns (blur_mode, kernel, description): blur_mode 2 = cv2.filter2D kinds, 1 = 'pyblur'."""
+    order.  Returns (blur_mode, kernel, description): blur_mode 2 = cv2.filter2D kinds, 1 = 'pyblur', 3 = 'median'
+    (kernel: zeros, only its size is used), 4 = 'bilateral' (kernel: the space weights; description carries sigma)."""
     import random as _random
     py_random = py_random or _random
     kind = py_random.choices(kernel_list, kernel_prob)[0]
@@ -389,6 +402,11 @@ def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=
     elif kind == 'pyblur':
         k, d = random_blur_kernel(np_random)
         return 1, k, ('pyblur',) + tuple(d)
+    elif kind == 'median':          # median_blur (degradations.py:353-355): cv2.medianBlur(uint8 image, kernel_size)
+        return 3, np.zeros((kernel_size, kernel_size), np.float32), ('median', kernel_size)
+    elif kind == 'bilateral':       # bilateral_blur (degradations.py:358-361): sigma = random.randint(150, 250)
+        sigma = py_random.randint(150, 250)
+        return 4, bilateral_space_kernel(kernel_size, sigma), ('bilateral', kernel_size, sigma)
     else:
         raise NotImplementedError(f"blur kind '{kind}' has no B200 implementation (supported: "
                                   f"{FILTER2D_KINDS + ('pyblur',)})")
@@ -404,12 +422,13 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random):
     blur_sigma, downsample_range, noise_range, jpeg_range, color_jitter_prob, color_jitter_shift, gray_prob).
     Returns a dict of host arrays ready for degrade_full_batch."""
     ks = opt['blur_kernel_size']
-    modes, kernels, sizes, noises, quality, jitter, gray, desc = [], [], [], [], [], [], [], []
+    modes, kernels, sizes, noises, quality, jitter, gray, desc, bsigma = [], [], [], [], [], [], [], [], []
     for _ in range(B):
         m, k, d = random_mixed_kernel(opt['kernel_list'], opt['kernel_prob'], ks, opt['blur_sigma'], opt['blur_sigma'],
                                       (-math.pi, math.pi), pad_kernel=True, pad_kernel_size=ks, py_random=py_random,
                                       np_random=np_random)
         modes.append(m)
+        bsigma.append(float(d[2]) if m == 4 else 0.0)
         kernels.append(np.asarray(k))       # dtype kept: it selects the arithmetic type of the reference's blur
         desc.append(d)
         scale = np_random.uniform(opt['downsample_range'][0], opt['downsample_range'][1])
@@ -439,10 +458,11 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random):
             if n is not None:
                 nz[b, :n.shape[0], :n.shape[1]] = n
     return dict(modes=modes, kernels=kernels, sizes=sizes, noise=nz, quality=quality, jitter=jitter, gray=gray,
-                desc=desc)
+                bilateral_sigma=bsigma, desc=desc)
 
 
-def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=None, gray=None, dev='cuda', **_unused):
+def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=None, gray=None, bilateral_sigma=None,
+                      dev='cuda', **_unused):
     """Device-side parameter block of a batch for b200ir_degrade_full (taps, per-crop records, noise): build once per
     batch of draws, reuse across launches.  Arguments as returned by sample_params."""
     B = len(modes)
@@ -457,6 +477,9 @@ def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=No
             raise ValueError('low-resolution size must be at least 2x2')
         c.jpeg_quality = int(quality[b]) if quality is not None else 0
         c.gray = int(gray[b]) if gray is not None else 0
+        c.bilateral_sigma = float(bilateral_sigma[b]) if bilateral_sigma is not None else 0.0
+        if c.blur_mode == 4 and not c.bilateral_sigma > 0:
+            raise ValueError('bilateral blur needs bilateral_sigma > 0')
         for i in range(3):
             c.jitter[i] = float(jitter[b][i]) if jitter is not None else 0.0
     lr_wmax, lr_hmax = max(s[0] for s in sizes), max(s[1] for s in sizes)
@@ -468,7 +491,7 @@ def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=No
 
 
 def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, quality=None, jitter=None, gray=None,
-                       bgr2rgb=True, return_lr=False, packed=None, **_unused):
+                       bilateral_sigma=None, bgr2rgb=True, return_lr=False, packed=None, **_unused):
     """One launch of b200ir_degrade_full over a batch (see include/b200ir.h).  gt_u8: uint8 CUDA tensor [B,H,W,3] in
     the reference's channel order (BGR); the other arguments as returned by sample_params (or packed= the result of
     pack_degrade_full).  Returns the LQ batch fp32 [B,3,H,W] in [-1,1] (and the low-resolution image after noise /
@@ -478,7 +501,8 @@ def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, 
     gt_u8 = gt_u8.contiguous()
     B, H, W, _ = gt_u8.shape
     dev = gt_u8.device
-    pk = packed if packed is not None else pack_degrade_full(modes, kernels, sizes, noise, quality, jitter, gray, dev)
+    pk = packed if packed is not None else pack_degrade_full(modes, kernels, sizes, noise, quality, jitter, gray,
+                                                             bilateral_sigma, dev)
     assert pk['n'] == B
     out = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
     lr = torch.zeros(B, pk['lr_hmax'], pk['lr_wmax'], 3, device=dev, dtype=torch.float32) if return_lr else None

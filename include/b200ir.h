@@ -317,14 +317,17 @@ int b200ir_degrade(const uint8_t* gt, const double* taps, const int32_t* ksize, 
  * cv2.cvtColor(BGR2GRAY) (:283-285) -> round / clip / normalize (:307-311).
  * Random draws stay on the host (image_restoration_b200.degradation.sample_params mirrors the reference's order of
  * random / np.random calls); this entry point is deterministic in its arguments.
- * Not covered (host fallback does not exist either -- callers must not select them): 'median' and 'bilateral' blur
- * kinds, color_jitter_pt, random_mask.
+ * Not covered (host fallback does not exist either -- callers must not select them): color_jitter_pt, random_mask,
+ * the 'pyblur_motion' / 'random_cover' / 'bicubic' kinds.
  */
 typedef struct b200ir_degrade_crop {
   int32_t blur_mode;    /* 0 none; 1 'pyblur': scipy convolve2d on the uint8 image, fill 255, truncated to uint8;
                            2 cv2.filter2D on image/255 ('iso', 'aniso', 'motion', 'average'): correlation,
                            BORDER_REFLECT_101, fp32 sum in kernel order (OpenCV itself switches to a DFT for kernels
-                           >= 11x11, so its result differs in the last bits) */
+                           >= 11x11, so its result differs in the last bits);
+                           3 'median': cv2.medianBlur(uint8 image, ksize), BORDER_REPLICATE (degradations.py:353-355);
+                           4 'bilateral': cv2.bilateralFilter(uint8 image, ksize, sigma, sigma) (degradations.py:358-361);
+                             taps = the space weights exp(-r^2 / (2 sigma^2)) inside the radius, zero outside */
   int32_t ksize;        /* odd extent of the kernel inside its kmax x kmax block */
   int32_t blur_f64;     /* blur_mode 1 only: 1 = the reference's convolve2d ran in float64 (box / disk / line kernels are
                            float64 under NumPy 2), 0 = in float32 (psf kernels).  The kernel reproduces scipy's summation
@@ -333,6 +336,7 @@ typedef struct b200ir_degrade_crop {
   int32_t jpeg_quality; /* int(quality); 0 = no JPEG stage */
   int32_t gray;         /* 1: BGR2GRAY tiled to 3 channels */
   float jitter[3];      /* color_jitter shift per channel in the image's channel order; all 0 = off */
+  float bilateral_sigma; /* blur_mode 4: sigmaColor = sigmaSpace */
 } b200ir_degrade_crop;
 
 /* gt uint8 [B][H][W][3] (channel order B,G,R as the reference holds images); taps fp64 [B][kmax][kmax] centred, zero

@@ -4,7 +4,8 @@ CPU restatement of the LQ synthesis of FFHQDegradationDataset.__getitem__
 (Car_Plate-Restoration/basicsr/data/ffhq_degradation_dataset.py:242-311) for the stages b200ir_degrade_full runs, as a
 deterministic function of explicit parameters (the random draws are made by the caller):
 
-    blur    'iso' / 'aniso' / 'motion' / 'average': cv2.filter2D(img, -1, kernel) (degradations.py:460-515)
+    blur    'iso' / 'aniso' / 'generalized_*' / 'plateau_*' / 'motion' / 'average': cv2.filter2D(img, -1, kernel)
+            (degradations.py:460-515); 'median': cv2.medianBlur; 'bilateral': cv2.bilateralFilter (:353-361)
             'pyblur': scipy convolve2d on the uint8 image, truncated to uint8 (oracle/pyblur_oracle.py; explicit
                       arithmetic: convolve2d_same_fill)
     down    cv2.resize(img, (lr_w, lr_h), INTER_LINEAR)                         (:255-256)
@@ -103,6 +104,42 @@ def resize_linear(img, dsize):
     return lerp(t[y0], t[y1], fy[:, None, None])
 
 
+def median_u8(img_u8, k):
+    """cv2.medianBlur(uint8 HxWx3, k): exact median of the k x k window per channel, BORDER_REPLICATE."""
+    r = k // 2
+    pad = np.pad(img_u8, ((r, r), (r, r), (0, 0)), mode='edge')
+    win = np.lib.stride_tricks.sliding_window_view(pad, (k, k), axis=(0, 1))
+    h, w = img_u8.shape[:2]
+    return np.sort(win.reshape(h, w, 3, -1), axis=-1)[..., (k * k) // 2].astype(np.uint8)
+
+
+def bilateral_u8(img_u8, d, sigma):
+    """cv2.bilateralFilter(uint8 HxWx3, d, sigma, sigma) (bilateral_filter.dispatch.cpp / .simd.hpp, 8-bit 3-channel):
+    BORDER_REFLECT_101; taps with sqrt(i^2 + j^2) <= d // 2 in row-major order; colour table (float)exp(n^2 * gc) over
+    n = |db| + |dg| + |dr|, space weights (float)exp(r^2 * gs), both evaluated in double; weight = space * colour in fp32,
+    sum = fma(value, weight, sum), result cvRound(sum / wsum).  Pinned against cv2 in tests/test_degrade_full_cpu.py."""
+    radius = max(d // 2, 1)
+    gc = gs = -0.5 / (float(sigma) * float(sigma))
+    n = np.arange(256 * 3, dtype=np.float64)
+    cw = np.exp(n * n * gc).astype(np.float32)
+    pad = np.pad(img_u8.astype(np.int32), ((radius, radius), (radius, radius), (0, 0)), mode='reflect')
+    h, w = img_u8.shape[:2]
+    acc = np.zeros((h, w, 3), np.float32)
+    wsum = np.zeros((h, w), np.float32)
+    c = img_u8.astype(np.int32)
+    for i in range(-radius, radius + 1):
+        for j in range(-radius, radius + 1):
+            rr = np.sqrt(float(i * i + j * j))
+            if rr > radius:
+                continue
+            sw = np.float32(np.exp(rr * rr * gs))
+            v = pad[radius + i:radius + i + h, radius + j:radius + j + w]
+            wt = (sw * cw[np.abs(v - c).sum(axis=2)]).astype(np.float32)
+            wsum = wsum + wt
+            acc = _fma32(v.astype(np.float32), np.broadcast_to(wt[..., None], v.shape), acc)
+    return np.clip(np.rint(acc / wsum[..., None]), 0, 255).astype(np.uint8)
+
+
 def gray_bgr(img):
     """cv2.cvtColor(img, COLOR_BGR2GRAY) on float32 as this container's OpenCV evaluates it:
     fma(r, 0.299, fma(b, 0.114, g * 0.587)) (found by comparing all orderings against cv2; bit-exact)."""
@@ -113,7 +150,8 @@ def gray_bgr(img):
     return (r * c[2] + t).astype(np.float32)
 
 
-def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, exact_blur=True, lib_jpeg=False):
+def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, exact_blur=True, lib_jpeg=False,
+             bilateral_sigma=0.0):
     """uint8 BGR [H,W,3] -> float32 BGR [H,W,3] LQ image before the 8-bit rounding, plus the LR image after noise/JPEG."""
     H, W = gt_u8.shape[:2]
     img = gt_u8.astype(np.float32) / np.float32(255.)
@@ -123,6 +161,15 @@ def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, g
     elif mode == 1:     # the kernel's dtype decides the arithmetic type, as in the reference (float64 box / disk / line)
         blur = convolve2d_same_fill(gt_u8, kernel) if exact_blur else pyblur_oracle.blur_f32(gt_u8, np.asarray(kernel))
         img = blur.astype('uint8').astype(np.float32) / np.float32(255.)
+    elif mode == 3:     # median_blur (degradations.py:353-355)
+        k = np.asarray(kernel).shape[0]
+        blur = median_u8(gt_u8, k) if exact_blur else cv2.medianBlur(gt_u8, k)
+        img = blur.astype(np.float32) / np.float32(255.)
+    elif mode == 4:     # bilateral_blur (degradations.py:358-361)
+        k = np.asarray(kernel).shape[0]
+        blur = (bilateral_u8(gt_u8, k, bilateral_sigma) if exact_blur
+                else cv2.bilateralFilter(gt_u8, k, bilateral_sigma, bilateral_sigma))
+        img = blur.astype(np.float32) / np.float32(255.)
     lr = cv2.resize(img, tuple(lr_size), interpolation=cv2.INTER_LINEAR)
     if noise is not None:
         lr = np.clip(lr + noise, 0, 1)
@@ -150,6 +197,6 @@ def lq_tensor(up, bgr2rgb=True):
 
 
 def degrade_full(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, bgr2rgb=True, exact_blur=True,
-                 lib_jpeg=False):
-    up, lr = lq_image(gt_u8, mode, kernel, lr_size, noise, quality, jitter, gray, exact_blur, lib_jpeg)
+                 lib_jpeg=False, bilateral_sigma=0.0):
+    up, lr = lq_image(gt_u8, mode, kernel, lr_size, noise, quality, jitter, gray, exact_blur, lib_jpeg, bilateral_sigma)
     return lq_tensor(up, bgr2rgb), lr

@@ -15,9 +15,11 @@ sys.path.insert(0, ROOT)
 from oracle import ref_import  # noqa: E402
 from image_restoration_b200 import degradation as D  # noqa: E402
 
-OPT = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'pyblur'],
-           kernel_prob=[0.2, 0.2, 0.15, 0.15, 0.3], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
-           noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.1)
+# kernel_list of training_config/train_gfpgan_v4_square_license_mix_pyblur.yml:26-28 (probabilities evened out so that 20
+# crops reach every kind)
+OPT = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'],
+           kernel_prob=[0.12, 0.12, 0.12, 0.12, 0.16, 0.16, 0.2], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
+           noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.25)
 
 
 def smooth_crop(rng, h, w):
@@ -59,7 +61,7 @@ def reference_lq(deg, DS, gt_u8, opt):
 def main():
     deg, DS = ref_import.load_reference_degradations()
     rng = np.random.default_rng(7)
-    H, W, N = 128, 384, 16
+    H, W, N = 128, 384, 20
     gts, outs, seeds = [], [], []
     for i in range(N):
         gt = smooth_crop(rng, H, W)
@@ -92,6 +94,7 @@ def main():
                         f64=np.array([int(r['kernels'][0].dtype == np.float64) for r in recs]), lr_w=lw, lr_h=lh, noise=noise,
                         quality=np.array([r['quality'][0] for r in recs]),
                         jitter=np.stack([r['jitter'][0] for r in recs]), gray=np.array([r['gray'][0] for r in recs]),
+                        bsigma=np.array([r['bilateral_sigma'][0] for r in recs], dtype=np.float32),
                         kinds=np.array([r['desc'][0][0] for r in recs]))
     print('kinds', [r['desc'][0][0] for r in recs])
     print('gray', [r['gray'][0] for r in recs], 'quality', [r['quality'][0] for r in recs])

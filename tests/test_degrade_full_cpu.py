@@ -32,13 +32,14 @@ def golden_case(g, i):
     if not int(g['f64'][i]):
         kernel = kernel.astype(np.float32)         # psf kernels: the reference's convolve2d runs in float32
     return dict(gt=g['gt'][i], mode=int(g['modes'][i]), kernel=kernel, lr_size=(lw, lh),
-                noise=g['noise'][i, :lh, :lw], quality=int(g['quality'][i]), jitter=g['jitter'][i], gray=int(g['gray'][i]))
+                noise=g['noise'][i, :lh, :lw], quality=int(g['quality'][i]), jitter=g['jitter'][i], gray=int(g['gray'][i]),
+                bsigma=float(g['bsigma'][i]))
 
 
 def test_golden_covers_every_stage():
     g = np.load(GOLD)
     kinds = set(str(k) for k in g['kinds'])
-    assert {'iso', 'aniso', 'motion', 'average', 'pyblur'} <= kinds, kinds
+    assert {'iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'} <= kinds, kinds
     assert g['gray'].any() and (g['jitter'] != 0).any() and (g['quality'] > 0).all()
 
 
@@ -47,13 +48,13 @@ def test_oracle_reproduces_golden_reference_outputs():
     for i in range(len(g['seeds'])):
         c = golden_case(g, i)
         lib, _ = dfo.degrade_full(c['gt'], c['mode'], c['kernel'], c['lr_size'], c['noise'], c['quality'], c['jitter'],
-                                  c['gray'], exact_blur=False)
+                                  c['gray'], exact_blur=False, bilateral_sigma=c['bsigma'])
         assert np.array_equal(to_u8(lib), g['out_u8'][i].astype(np.int32)), (i, str(g['kinds'][i]))
         # explicit-sum blur: the same image up to the last-bit difference of OpenCV's DFT path, i.e. rare single codes
         exact, _ = dfo.degrade_full(c['gt'], c['mode'], c['kernel'], c['lr_size'], c['noise'], c['quality'], c['jitter'],
-                                    c['gray'], exact_blur=True)
+                                    c['gray'], exact_blur=True, bilateral_sigma=c['bsigma'])
         diff = np.abs(to_u8(exact) - g['out_u8'][i].astype(np.int32))
-        if c['mode'] == 1:      # pyblur: the explicit summation tree is scipy's -> identical
+        if c['mode'] in (1, 3):  # pyblur: the explicit summation tree is scipy's; median: integer -> identical
             assert diff.max() == 0, (i, diff.max())
         else:
             assert (diff > 0).mean() < 0.02 and diff.max() <= 6, (i, str(g['kinds'][i]), (diff > 0).mean(), diff.max())
@@ -78,6 +79,26 @@ def test_explicit_convolve2d_is_bit_exact_against_scipy():
         assert got.dtype == ref.dtype and np.array_equal(got, ref), (k.shape, k.dtype)
 
 
+def test_explicit_median_and_bilateral_against_cv2():
+    """Pins oracle median_u8 (exact) and bilateral_u8 (the arithmetic the CUDA kernel runs) against cv2: the median is an
+    integer operation and must be identical; the bilateral filter accumulates in fp32 inside OpenCV's SIMD code, whose
+    scalar tail differs from its vector body, so a handful of bytes per image may round the other way."""
+    rng = np.random.default_rng(8)
+    noise = rng.integers(0, 256, (48, 80, 3)).astype(np.uint8)
+    smooth = (np.clip(cv2.resize(rng.random((5, 8, 3)).astype(np.float32), (80, 48), interpolation=cv2.INTER_CUBIC), 0, 1)
+              * 255).astype(np.uint8)
+    for img in (noise, smooth):
+        for k in (3, 7, 21):
+            assert np.array_equal(dfo.median_u8(img, k), cv2.medianBlur(img, k)), k
+        for sigma in (150, 187, 250):
+            ref = cv2.bilateralFilter(img, 21, sigma, sigma)
+            got = dfo.bilateral_u8(img, 21, sigma)
+            d = np.abs(got.astype(int) - ref.astype(int))
+            assert d.max() <= 1 and (d > 0).sum() <= 3, (sigma, d.max(), int((d > 0).sum()))
+    k = D.bilateral_space_kernel(21, 200)
+    assert k.shape == (21, 21) and k[0, 0] == 0 and k[10, 10] == 1 and k[0, 10] > 0 and np.count_nonzero(k) == 317
+
+
 def test_filter2d_direct_close_to_cv2():
     rng = np.random.default_rng(3)
     img = rng.random((40, 70, 3)).astype(np.float32)
@@ -95,7 +116,7 @@ def test_kernel_builders_known_answers():
     assert np.count_nonzero(D.motion_kernel(7, True)[3]) == 7 and np.count_nonzero(D.motion_kernel(7, False)[:, 3]) == 7
     assert D.average_kernel(5).dtype == np.float32 and np.allclose(D.average_kernel(5), 0.04)
     with pytest.raises(NotImplementedError):
-        D.random_mixed_kernel(['median'], [1.0], 21)
+        D.random_mixed_kernel(['bicubic'], [1.0], 21)
 
 
 @pytest.mark.skipif(not ref_import.available(), reason='/root/reference not present')
@@ -140,7 +161,7 @@ def test_host_mirror_and_oracle_equal_reference_chain():
     rng = np.random.default_rng(21)
     H, W = 64, 192
     kinds = set()
-    for i in range(12):
+    for i in range(16):
         gt = mk.smooth_crop(rng, H, W)
         seed = 500 + i
         ref_import.load_reference_pyblur()
@@ -151,9 +172,10 @@ def test_host_mirror_and_oracle_equal_reference_chain():
         kinds.add(p['desc'][0][0])
         lw, lh = p['sizes'][0]
         got, _ = dfo.degrade_full(gt, p['modes'][0], p['kernels'][0], (lw, lh), p['noise'][0, :lh, :lw], p['quality'][0],
-                                  p['jitter'][0], p['gray'][0], exact_blur=False, lib_jpeg=False)
+                                  p['jitter'][0], p['gray'][0], exact_blur=False, lib_jpeg=False,
+                                  bilateral_sigma=p['bilateral_sigma'][0])
         assert np.array_equal(got, ref), (i, p['desc'][0])
-    assert len(kinds) >= 3
+    assert len(kinds) >= 5 and {'median', 'bilateral'} <= kinds, kinds
 
 
 def test_explicit_resize_is_bit_exact_against_cv2():

@@ -24,10 +24,10 @@ def to_u8(x):
     return np.rint((np.asarray(x) * 0.5 + 0.5) * 255).astype(np.int32)
 
 
-def run_gpu(gt, modes, kernels, sizes, noise, quality, jitter, gray, bgr2rgb=True):
+def run_gpu(gt, modes, kernels, sizes, noise, quality, jitter, gray, bgr2rgb=True, bsigma=None):
     from image_restoration_b200 import degradation as D
     out, lr = D.degrade_full_batch(torch.from_numpy(gt).cuda(), modes, kernels, sizes, noise=noise, quality=quality,
-                                   jitter=jitter, gray=gray, bgr2rgb=bgr2rgb, return_lr=True)
+                                   jitter=jitter, gray=gray, bilateral_sigma=bsigma, bgr2rgb=bgr2rgb, return_lr=True)
     torch.cuda.synchronize()
     return out.cpu().numpy(), lr.cpu().numpy()
 
@@ -48,13 +48,14 @@ def golden_batch():
 def test_golden_reference_outputs():
     g, kernels, sizes = golden_batch()
     out, lr = run_gpu(g['gt'], [int(m) for m in g['modes']], kernels, sizes, g['noise'], [int(q) for q in g['quality']],
-                      g['jitter'], [int(x) for x in g['gray']])
+                      g['jitter'], [int(x) for x in g['gray']], bsigma=[float(x) for x in g['bsigma']])
     exact = 0
     for i in range(len(kernels)):
         diff = np.abs(to_u8(out[i]) - g['out_u8'][i].astype(np.int32))
-        if int(g['modes'][i]) == 1:       # pyblur crops: every stage restated bit-exactly -> the reference's output
+        if int(g['modes'][i]) in (1, 3):  # pyblur / median crops: every stage restated bit-exactly -> the reference's output
             assert diff.max() == 0, (i, str(g['kinds'][i]), (diff > 0).mean(), diff.max())
-        else:                             # filter2D crops: OpenCV's DFT blur vs the direct sum (see the CPU test)
+        else:                             # filter2D crops: OpenCV's DFT blur vs the direct sum; bilateral: fp32 sums inside
+                                          # OpenCV's SIMD code (see the CPU tests)
             assert (diff > 0).mean() < 0.02 and diff.max() <= 6, (i, str(g['kinds'][i]), (diff > 0).mean(), diff.max())
         exact += int(diff.max() == 0)
     assert exact >= len(kernels) // 2, exact
@@ -63,11 +64,12 @@ def test_golden_reference_outputs():
 def test_golden_against_oracle_stage_by_stage():
     g, kernels, sizes = golden_batch()
     out, lr = run_gpu(g['gt'], [int(m) for m in g['modes']], kernels, sizes, g['noise'], [int(q) for q in g['quality']],
-                      g['jitter'], [int(x) for x in g['gray']])
+                      g['jitter'], [int(x) for x in g['gray']], bsigma=[float(x) for x in g['bsigma']])
     for i in range(len(kernels)):
         lw, lh = sizes[i]
         ref, ref_lr = dfo.degrade_full(g['gt'][i], int(g['modes'][i]), kernels[i], sizes[i], g['noise'][i, :lh, :lw],
-                                       int(g['quality'][i]), g['jitter'][i], int(g['gray'][i]), exact_blur=True)
+                                       int(g['quality'][i]), g['jitter'][i], int(g['gray'][i]), exact_blur=True,
+                                       bilateral_sigma=float(g['bsigma'][i]))
         # the oracle's explicit-sum blur is the arithmetic the kernel runs: LR image (8-bit after JPEG) identical
         assert np.array_equal(lr[i, :lh, :lw], ref_lr), (i, str(g['kinds'][i]), np.abs(lr[i, :lh, :lw] - ref_lr).max() * 255)
         assert np.array_equal(out[i], ref), (i, str(g['kinds'][i]), np.abs(to_u8(out[i]) - to_u8(ref)).max())
@@ -81,8 +83,11 @@ def test_seeded_cases_every_stage(H, W):
                D.LineKernel(21, 99, 'left'), D.LineKernel(15, 30, 'right'), np.asarray(D.psfDictionary[3], dtype=np.float32),
                np.asarray(D.psfDictionary[77], dtype=np.float32), None,
                D.bivariate_Gaussian(21, 2.0, 2.0, 0, True), D.bivariate_Gaussian(21, 4.0, 0.8, 0.7, False),
-               D.motion_kernel(21, True), D.motion_kernel(9, False), D.average_kernel(21), D.average_kernel(5)]
-    modes = [1] * 9 + [0] + [2] * 6
+               D.motion_kernel(21, True), D.motion_kernel(9, False), D.average_kernel(21), D.average_kernel(5),
+               np.zeros((21, 21), np.float32), np.zeros((7, 7), np.float32), D.bilateral_space_kernel(21, 150),
+               D.bilateral_space_kernel(21, 250), D.bilateral_space_kernel(9, 201)]
+    modes = [1] * 9 + [0] + [2] * 6 + [3, 3, 4, 4, 4]
+    bsigma = [0.0] * 18 + [150.0, 250.0, 201.0]
     B = len(kernels)
     gt = rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
     gt[1, :, : W // 2] = 255                      # flat white: box-blur sums land on integers (truncation ties)
@@ -100,11 +105,11 @@ def test_seeded_cases_every_stage(H, W):
     noise = np.zeros((B, lhm, lwm, 3), np.float32)
     for b, (lw, lh) in enumerate(sizes):
         noise[b, :lh, :lw] = np.float32(rng.randn(lh, lw, 3)) * rng.uniform(0, 20) / 255.
-    out, lr = run_gpu(gt, modes, kernels, sizes, noise, quality, jitter, gray)
+    out, lr = run_gpu(gt, modes, kernels, sizes, noise, quality, jitter, gray, bsigma=bsigma)
     for b in range(B):
         lw, lh = sizes[b]
         ref, ref_lr = dfo.degrade_full(gt[b], modes[b], kernels[b], sizes[b], noise[b, :lh, :lw], quality[b], jitter[b],
-                                       gray[b], exact_blur=True)
+                                       gray[b], exact_blur=True, bilateral_sigma=bsigma[b])
         assert np.array_equal(lr[b, :lh, :lw], ref_lr), (b, np.abs(lr[b, :lh, :lw] - ref_lr).max() * 255)
         assert np.array_equal(out[b], ref), (b, np.abs(to_u8(out[b]) - to_u8(ref)).max())
 
