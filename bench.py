@@ -310,7 +310,8 @@ def main():
         from oracle import degrade_full_oracle as dfo
         opt = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'],
                    kernel_prob=[0.08, 0.08, 0.08, 0.08, 0.08, 0.08, 0.28], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
-                   noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.1)
+                   noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, color_jitter_pt_prob=0.3,
+           gray_prob=0.01)
         import random as _random
         prm = dg.sample_params(DB, H, W, opt, py_random=_random.Random(0), np_random=np.random.RandomState(0))
         pk = dg.pack_degrade_full(dev=dev, **prm)
@@ -320,7 +321,7 @@ def main():
             lw, lh = prm['sizes'][b]
             dfo.degrade_full(gt[b], prm['modes'][b], prm['kernels'][b], (lw, lh), prm['noise'][b, :lh, :lw],
                              prm['quality'][b], prm['jitter'][b], prm['gray'][b], exact_blur=False, lib_jpeg=True,
-                             bilateral_sigma=prm['bilateral_sigma'][b])
+                             bilateral_sigma=prm['bilateral_sigma'][b], cj=prm['color_jitter_pt'][b])
         cpu_full_ms = (time.time() - t0) / n_cpu * 1e3
         # BASELINE config 4: tiled full-frame inference, 3x1080x1920 -> 45 overlapping 256x256 tiles in one batch
         from image_restoration_b200.tiling import TiledRestorer
@@ -340,7 +341,7 @@ def main():
                               'batch': DB, 'achieved_gbs': alg / ms_full / 1e6,
                               'stages': 'blur (iso/aniso/motion/average/median/bilateral/pyblur, kernel_list and kernel_prob of '
                                         'training_config/train_gfpgan_v4_square_license_mix_pyblur.yml) + resize + noise + '
-                                        'JPEG + resize + jitter + gray',
+                                        'JPEG + resize + colour jitter + gray + color_jitter_pt (same probabilities as that YAML)',
                               'cpu_reference': {'ms_per_crop': cpu_full_ms, 'crops_per_s': 1e3 / cpu_full_ms, 'cores': 1,
                                                 'kind': 'port', 'sample': f'{n_cpu} crops through cv2.filter2D / scipy '
                                                 'convolve2d + cv2.resize + cv2.imencode/imdecode (the reference\'s calls)'}}

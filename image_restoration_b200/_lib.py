@@ -52,7 +52,8 @@ class DemodLayer(C.Structure):
 class DegradeCrop(C.Structure):
     """b200ir_degrade_crop (include/b200ir.h); numpy view: DEGRADE_CROP_DTYPE."""
     _fields_ = [('blur_mode', C.c_int32), ('ksize', C.c_int32), ('blur_f64', C.c_int32), ('lr_w', C.c_int32), ('lr_h', C.c_int32),
-                ('jpeg_quality', C.c_int32), ('gray', C.c_int32), ('jitter', C.c_float * 3), ('bilateral_sigma', C.c_float)]
+                ('jpeg_quality', C.c_int32), ('gray', C.c_int32), ('jitter', C.c_float * 3), ('bilateral_sigma', C.c_float), ('cj_count', C.c_int32),
+                ('cj_order', C.c_int32 * 4), ('cj_factor', C.c_float * 4), ('cj_one_minus', C.c_float * 4)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float

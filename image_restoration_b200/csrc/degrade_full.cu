@@ -11,6 +11,7 @@
 //   up          cv2.resize(INTER_LINEAR) back to (W, H)                       (:272)
 //   jitter      clip(img + shift[c], 0, 1)                                    (:90-95, :280-281)
 //   gray        cv2.cvtColor(BGR2GRAY) tiled to 3 channels                    (:283-285)
+//   jitter (pt) color_jitter_pt: torchvision adjust_brightness / contrast / saturation / hue in a drawn order (:187-207, :290-296)
 //   tail        clamp(round(x*255), 0, 255)/255, (x-0.5)/0.5, BGR->RGB, NCHW  (:288, :307-311)
 // The blur is evaluated only at the 2x2 source pixels each low-resolution pixel interpolates (4 lanes per LR pixel, combined
 // with shuffles); the GT crop is staged in shared memory once.
@@ -158,6 +159,65 @@ __host__ __device__ inline DfLayout df_layout(int kmax, int lr_wmax, int lr_hmax
   l.gt = df_align(l.crp + (size_t)(hp / 2) * (wp / 2) * sizeof(int));
   l.total = l.gt + (stage ? (size_t)H * W * 3 : 0);
   return l;
+}
+
+// ---- torchvision.transforms.functional colour adjustments on one float RGB pixel (functional_tensor: _blend,
+// rgb_to_grayscale, _rgb2hsv, _hsv2rgb), every product / sum / quotient rounded separately in fp32 as the tensor ops are.
+__device__ __forceinline__ float df_gray_tv(float r, float g, float b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(0.2989f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+}
+__device__ __forceinline__ float df_blend(float a, float bb, float ratio, float one_minus) {
+  return fminf(fmaxf(__fadd_rn(__fmul_rn(ratio, a), __fmul_rn(one_minus, bb)), 0.f), 1.f);
+}
+__device__ __forceinline__ void df_hue(float hue, float& r, float& g, float& b) {
+  // _rgb2hsv
+  const float maxc = fmaxf(fmaxf(r, g), b), minc = fminf(fminf(r, g), b);
+  const bool eqc = maxc == minc;
+  const float cr = __fsub_rn(maxc, minc);
+  const float sat = __fdiv_rn(cr, eqc ? 1.f : maxc);
+  const float div = eqc ? 1.f : cr;
+  const float rc = __fdiv_rn(__fsub_rn(maxc, r), div), gc = __fdiv_rn(__fsub_rn(maxc, g), div),
+              bc = __fdiv_rn(__fsub_rn(maxc, b), div);
+  const float hr = (maxc == r) ? __fsub_rn(bc, gc) : 0.f;
+  const float hg = ((maxc == g) && (maxc != r)) ? __fsub_rn(__fadd_rn(2.f, rc), bc) : 0.f;
+  const float hb = ((maxc != g) && (maxc != r)) ? __fsub_rn(__fadd_rn(4.f, gc), rc) : 0.f;
+  float h = __fadd_rn(__fadd_rn(hr, hg), hb);
+  h = fmodf(__fadd_rn(__fdiv_rn(h, 6.f), 1.f), 1.f);
+  // h = (h + hue_factor) % 1.0 (torch.remainder: the sign follows the divisor)
+  h = fmodf(__fadd_rn(h, hue), 1.f);
+  if (h != 0.f && h < 0.f) h = __fadd_rn(h, 1.f);
+  // _hsv2rgb
+  const float v = maxc;
+  const float h6 = __fmul_rn(h, 6.f);
+  const float fi = floorf(h6);
+  const float f = __fsub_rn(h6, fi);
+  const int i = ((int)fi) % 6;
+  const float p = fminf(fmaxf(__fmul_rn(v, __fsub_rn(1.f, sat)), 0.f), 1.f);
+  const float q = fminf(fmaxf(__fmul_rn(v, __fsub_rn(1.f, __fmul_rn(sat, f))), 0.f), 1.f);
+  const float t = fminf(fmaxf(__fmul_rn(v, __fsub_rn(1.f, __fmul_rn(sat, __fsub_rn(1.f, f)))), 0.f), 1.f);
+  r = i == 0 ? v : i == 1 ? q : i == 2 ? p : i == 3 ? p : i == 4 ? t : v;
+  g = i == 0 ? t : i == 1 ? v : i == 2 ? v : i == 3 ? q : i == 4 ? p : p;
+  b = i == 0 ? p : i == 1 ? p : i == 2 ? t : i == 3 ? v : i == 4 ? v : q;
+}
+// op: 0 brightness, 1 contrast (mean = mean gray of the image), 2 saturation, 3 hue (factor = hue shift)
+__device__ __forceinline__ void df_color_op(int op, float factor, float one_minus, float mean, float& r, float& g,
+                                            float& b) {
+  if (op == 0) {
+    r = df_blend(r, 0.f, factor, one_minus);
+    g = df_blend(g, 0.f, factor, one_minus);
+    b = df_blend(b, 0.f, factor, one_minus);
+  } else if (op == 1) {
+    r = df_blend(r, mean, factor, one_minus);
+    g = df_blend(g, mean, factor, one_minus);
+    b = df_blend(b, mean, factor, one_minus);
+  } else if (op == 2) {
+    const float gr = df_gray_tv(r, g, b);
+    r = df_blend(r, gr, factor, one_minus);
+    g = df_blend(g, gr, factor, one_minus);
+    b = df_blend(b, gr, factor, one_minus);
+  } else {
+    df_hue(factor, r, g, b);
+  }
 }
 
 // cv2.medianBlur(uint8 image, k) at (y, x), BORDER_REPLICATE: exact median of the k*k window per channel, found by a
@@ -468,14 +528,13 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
     }
   }
 
-  // ---- 3. up-resize, colour jitter, gray, 8-bit grid, normalise, NCHW (optionally BGR -> RGB)
+  // ---- 3. up-resize, colour jitter, gray, colour jitter (torchvision ops), 8-bit grid, normalise, NCHW
   float* o = out + (size_t)b * 3 * H * W;
   const float j0 = cp.jitter[0], j1 = cp.jitter[1], j2 = cp.jitter[2];
   const bool jit = j0 != 0.f || j1 != 0.f || j2 != 0.f;
-  for (int it = tid; it < H * W; it += kDfThreads) {
+  auto pixel = [&](int it, float (&v)[3]) {  // image after :272-285, channel order B, G, R
     const int x = it % W, y = it / W;
     const DfAxis ry = s_urow[y], rx = s_ucol[x];
-    float v[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float p00 = s_lr[(ry.i0 * lw + rx.i0) * 3 + c], p01 = s_lr[(ry.i0 * lw + rx.i1) * 3 + c];
@@ -490,6 +549,50 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
     if (cp.gray) {  // OpenCV's float BGR2GRAY as executed in the build container: fma(r, .299, fma(b, .114, g * .587))
       const float g = __fmaf_rn(v[2], 0.299f, __fmaf_rn(v[0], 0.114f, __fmul_rn(v[1], 0.587f)));
       v[0] = v[1] = v[2] = g;
+    }
+  };
+  // color_jitter_pt (ffhq_degradation_dataset.py:187-207): the four torchvision adjustments in the drawn order; the
+  // contrast step blends with the mean gray level of the whole image at that point, so the pixels before it are
+  // evaluated once more in a first pass that only accumulates that mean.
+  const int n_ops = cp.cj_count;
+  float cj_mean = 0.f;
+  if (n_ops > 0) {
+    int k_con = -1;
+    for (int k = 0; k < n_ops; ++k)
+      if (cp.cj_order[k] == 1) k_con = k;
+    if (k_con >= 0) {
+      double part = 0.0;
+      for (int it = tid; it < H * W; it += kDfThreads) {
+        float v[3];
+        pixel(it, v);
+        float r = v[2], g = v[1], bl = v[0];
+        for (int k = 0; k < k_con; ++k) df_color_op(cp.cj_order[k], cp.cj_factor[k], cp.cj_one_minus[k], 0.f, r, g, bl);
+        part += (double)df_gray_tv(r, g, bl);
+      }
+      __shared__ double s_red[kDfThreads / 32];
+      __shared__ float s_mean;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      if ((tid & 31) == 0) s_red[tid >> 5] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kDfThreads / 32; ++i) t += s_red[i];
+        s_mean = (float)(t / (double)(H * W));
+      }
+      __syncthreads();
+      cj_mean = s_mean;
+    }
+  }
+  for (int it = tid; it < H * W; it += kDfThreads) {
+    float v[3];
+    pixel(it, v);
+    if (n_ops > 0) {
+      float r = v[2], g = v[1], bl = v[0];
+      for (int k = 0; k < n_ops; ++k) df_color_op(cp.cj_order[k], cp.cj_factor[k], cp.cj_one_minus[k], cj_mean, r, g, bl);
+      v[2] = r;
+      v[1] = g;
+      v[0] = bl;
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

@@ -415,14 +415,15 @@ def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=
     return 2, k, desc
 
 
-def sample_params(B, H, W, opt, py_random=None, np_random=np.random):
+def sample_params(B, H, W, opt, py_random=None, np_random=np.random, torch_generator=None):
     """Per-crop random draws of __getitem__ for the stages b200ir_degrade_full runs, in the reference's order: blur
     kind + kernel, scale, noise sigma (+ the gray-noise coin) + noise field, JPEG quality, colour-jitter coin / shifts,
-    gray coin.  opt carries the dataset options of the training YAML (kernel_list, kernel_prob, blur_kernel_size,
+    gray coin, color_jitter_pt coin + torch.randperm(4) + one torch uniform per adjustment (torch_generator=None draws
+    from torch's global generator, as the reference does).  opt carries the dataset options of the training YAML (kernel_list, kernel_prob, blur_kernel_size,
     blur_sigma, downsample_range, noise_range, jpeg_range, color_jitter_prob, color_jitter_shift, gray_prob).
     Returns a dict of host arrays ready for degrade_full_batch."""
     ks = opt['blur_kernel_size']
-    modes, kernels, sizes, noises, quality, jitter, gray, desc, bsigma = [], [], [], [], [], [], [], [], []
+    modes, kernels, sizes, noises, quality, jitter, gray, desc, bsigma, cj = [], [], [], [], [], [], [], [], [], []
     for _ in range(B):
         m, k, d = random_mixed_kernel(opt['kernel_list'], opt['kernel_prob'], ks, opt['blur_sigma'], opt['blur_sigma'],
                                       (-math.pi, math.pi), pad_kernel=True, pad_kernel_size=ks, py_random=py_random,
@@ -450,6 +451,15 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random):
             j = np_random.uniform(-shift, shift, 3).astype(np.float32)
         jitter.append(j)
         gray.append(1 if (opt.get('gray_prob') and np_random.uniform() < opt['gray_prob']) else 0)
+        steps = []
+        if opt.get('color_jitter_pt_prob') is not None and np_random.uniform() < opt['color_jitter_pt_prob']:
+            ranges = (opt.get('brightness', (0.5, 1.5)), opt.get('contrast', (0.5, 1.5)), opt.get('saturation', (0, 1.5)),
+                      opt.get('hue', (-0.1, 0.1)))
+            for fn_id in torch.randperm(4, generator=torch_generator).tolist():
+                if ranges[fn_id] is not None:
+                    f = torch.tensor(1.0).uniform_(ranges[fn_id][0], ranges[fn_id][1], generator=torch_generator).item()
+                    steps.append((fn_id, f))
+        cj.append(steps)
     lr_wmax, lr_hmax = max(s[0] for s in sizes), max(s[1] for s in sizes)
     nz = None
     if any(n is not None for n in noises):
@@ -458,11 +468,11 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random):
             if n is not None:
                 nz[b, :n.shape[0], :n.shape[1]] = n
     return dict(modes=modes, kernels=kernels, sizes=sizes, noise=nz, quality=quality, jitter=jitter, gray=gray,
-                bilateral_sigma=bsigma, desc=desc)
+                bilateral_sigma=bsigma, color_jitter_pt=cj, desc=desc)
 
 
 def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=None, gray=None, bilateral_sigma=None,
-                      dev='cuda', **_unused):
+                      color_jitter_pt=None, dev='cuda', **_unused):
     """Device-side parameter block of a batch for b200ir_degrade_full (taps, per-crop records, noise): build once per
     batch of draws, reuse across launches.  Arguments as returned by sample_params."""
     B = len(modes)
@@ -482,6 +492,10 @@ def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=No
             raise ValueError('bilateral blur needs bilateral_sigma > 0')
         for i in range(3):
             c.jitter[i] = float(jitter[b][i]) if jitter is not None else 0.0
+        steps = color_jitter_pt[b] if color_jitter_pt is not None else []
+        c.cj_count = len(steps)
+        for i, (op, f) in enumerate(steps):     # torchvision's _blend: ratio and (1.0 - ratio) become float32 scalars
+            c.cj_order[i], c.cj_factor[i], c.cj_one_minus[i] = int(op), float(f), float(1.0 - float(f))
     lr_wmax, lr_hmax = max(s[0] for s in sizes), max(s[1] for s in sizes)
     if noise is not None:
         noise = torch.as_tensor(noise, dtype=torch.float32).to(dev).contiguous()
@@ -491,7 +505,7 @@ def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=No
 
 
 def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, quality=None, jitter=None, gray=None,
-                       bilateral_sigma=None, bgr2rgb=True, return_lr=False, packed=None, **_unused):
+                       bilateral_sigma=None, color_jitter_pt=None, bgr2rgb=True, return_lr=False, packed=None, **_unused):
     """One launch of b200ir_degrade_full over a batch (see include/b200ir.h).  gt_u8: uint8 CUDA tensor [B,H,W,3] in
     the reference's channel order (BGR); the other arguments as returned by sample_params (or packed= the result of
     pack_degrade_full).  Returns the LQ batch fp32 [B,3,H,W] in [-1,1] (and the low-resolution image after noise /
@@ -502,7 +516,7 @@ def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, 
     B, H, W, _ = gt_u8.shape
     dev = gt_u8.device
     pk = packed if packed is not None else pack_degrade_full(modes, kernels, sizes, noise, quality, jitter, gray,
-                                                             bilateral_sigma, dev)
+                                                             bilateral_sigma, color_jitter_pt, dev)
     assert pk['n'] == B
     out = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
     lr = torch.zeros(B, pk['lr_hmax'], pk['lr_wmax'], 3, device=dev, dtype=torch.float32) if return_lr else None

@@ -314,10 +314,11 @@ int b200ir_degrade(const uint8_t* gt, const double* taps, const int32_t* ksize, 
  * random_add_gaussian_noise (degradations.py:660-669) -> random_add_jpg_compression (degradations.py:876-910:
  * cv2.imencode / imdecode, i.e. libjpeg-turbo baseline 4:2:0 with the islow DCT; the lossless entropy coding is
  * skipped, the rest is the same integer arithmetic) -> cv2.resize up (:272) -> color_jitter (:90-95) ->
- * cv2.cvtColor(BGR2GRAY) (:283-285) -> round / clip / normalize (:307-311).
+ * cv2.cvtColor(BGR2GRAY) (:283-285) -> color_jitter_pt (torchvision adjust_*; :187-207, :290-296) -> round / clip /
+ * normalize (:307-311).
  * Random draws stay on the host (image_restoration_b200.degradation.sample_params mirrors the reference's order of
  * random / np.random calls); this entry point is deterministic in its arguments.
- * Not covered (host fallback does not exist either -- callers must not select them): color_jitter_pt, random_mask,
+ * Not covered (host fallback does not exist either -- callers must not select them): random_mask,
  * the 'pyblur_motion' / 'random_cover' / 'bicubic' kinds.
  */
 typedef struct b200ir_degrade_crop {
@@ -337,6 +338,10 @@ typedef struct b200ir_degrade_crop {
   int32_t gray;         /* 1: BGR2GRAY tiled to 3 channels */
   float jitter[3];      /* color_jitter shift per channel in the image's channel order; all 0 = off */
   float bilateral_sigma; /* blur_mode 4: sigmaColor = sigmaSpace */
+  int32_t cj_count;      /* color_jitter_pt (ffhq_degradation_dataset.py:187-207, :290-296): number of adjustments, 0 = off */
+  int32_t cj_order[4];   /* the drawn order: 0 brightness, 1 contrast, 2 saturation, 3 hue */
+  float cj_factor[4];    /* the factor of each step as float32 (hue: the shift) */
+  float cj_one_minus[4]; /* (float)(1.0 - factor), the second blend weight as torchvision's _blend evaluates it */
 } b200ir_degrade_crop;
 
 /* gt uint8 [B][H][W][3] (channel order B,G,R as the reference holds images); taps fp64 [B][kmax][kmax] centred, zero

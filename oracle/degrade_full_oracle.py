@@ -14,6 +14,7 @@ deterministic function of explicit parameters (the random draws are made by the 
     up      cv2.resize(img, (W, H), INTER_LINEAR)                               (:272)
     jitter  clip(img + shift, 0, 1)                                             (:90-95)
     gray    cv2.cvtColor(BGR2GRAY), tiled                                       (:283-285)
+    jitter2 color_jitter_pt: torchvision adjust_* in the drawn order            (:187-207, :290-296)
     tail    clamp(round(x * 255), 0, 255) / 255; (x - 0.5) / 0.5; BGR -> RGB; CHW   (:288, :307-311)
 
 The heavy lifting is the same third-party calls the reference makes (OpenCV 4.13 here, pinned 4.6.0.66 in
@@ -150,8 +151,21 @@ def gray_bgr(img):
     return (r * c[2] + t).astype(np.float32)
 
 
+def color_jitter_pt(img_bgr, steps):
+    """FFHQDegradationDataset.color_jitter_pt (ffhq_degradation_dataset.py:187-207) with the drawn (op, factor) list
+    made explicit: torchvision's adjust_brightness / contrast / saturation / hue (the reference's own library calls;
+    torchvision 0.14.0 pinned in requirements.txt:45, 0.26 here) on the RGB CHW tensor img2tensor builds (:288)."""
+    import torch
+    import torchvision.transforms.functional as TF
+    t = torch.from_numpy(np.ascontiguousarray(img_bgr[..., ::-1].transpose(2, 0, 1))).float()
+    fns = (TF.adjust_brightness, TF.adjust_contrast, TF.adjust_saturation, TF.adjust_hue)
+    for op, f in steps:
+        t = fns[op](t, f)
+    return np.ascontiguousarray(t.numpy().transpose(1, 2, 0)[..., ::-1])
+
+
 def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, exact_blur=True, lib_jpeg=False,
-             bilateral_sigma=0.0):
+             bilateral_sigma=0.0, cj=None):
     """uint8 BGR [H,W,3] -> float32 BGR [H,W,3] LQ image before the 8-bit rounding, plus the LR image after noise/JPEG."""
     H, W = gt_u8.shape[:2]
     img = gt_u8.astype(np.float32) / np.float32(255.)
@@ -184,6 +198,8 @@ def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, g
         up = np.clip(up + np.asarray(jitter, dtype=np.float32), 0, 1)
     if gray:
         up = np.tile(gray_bgr(up)[:, :, None], [1, 1, 3])
+    if cj:
+        up = color_jitter_pt(up, cj)
     return up, lr
 
 
@@ -197,6 +213,6 @@ def lq_tensor(up, bgr2rgb=True):
 
 
 def degrade_full(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, bgr2rgb=True, exact_blur=True,
-                 lib_jpeg=False, bilateral_sigma=0.0):
-    up, lr = lq_image(gt_u8, mode, kernel, lr_size, noise, quality, jitter, gray, exact_blur, lib_jpeg, bilateral_sigma)
+                 lib_jpeg=False, bilateral_sigma=0.0, cj=None):
+    up, lr = lq_image(gt_u8, mode, kernel, lr_size, noise, quality, jitter, gray, exact_blur, lib_jpeg, bilateral_sigma, cj)
     return lq_tensor(up, bgr2rgb), lr

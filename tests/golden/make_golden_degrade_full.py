@@ -19,7 +19,8 @@ from image_restoration_b200 import degradation as D  # noqa: E402
 # crops reach every kind)
 OPT = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'],
            kernel_prob=[0.12, 0.12, 0.12, 0.12, 0.16, 0.16, 0.2], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
-           noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.25)
+           noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.25,
+           color_jitter_pt_prob=0.4)
 
 
 def smooth_crop(rng, h, w):
@@ -54,6 +55,10 @@ def reference_lq(deg, DS, gt_u8, opt):
         img_lq = cv2.cvtColor(img_lq, cv2.COLOR_BGR2GRAY)
         img_lq = np.tile(img_lq[:, :, None], [1, 1, 3])
     t = torch.from_numpy(np.ascontiguousarray(img_lq[..., ::-1].transpose(2, 0, 1))).float()   # img2tensor(bgr2rgb)
+    if opt.get('color_jitter_pt_prob') is not None and (np.random.uniform() < opt['color_jitter_pt_prob']):
+        t = DS.color_jitter_pt(t, opt.get('brightness', (0.5, 1.5)), opt.get('contrast', (0.5, 1.5)),
+                               opt.get('saturation', (0, 1.5)), opt.get('hue', (-0.1, 0.1)))
+    t = t.clamp(0, 1)                                             # tensor2img(out_type=float32) / img2tensor round trip (:299-303)
     t = torch.clamp((t * 255.0).round(), 0, 255) / 255.
     return ((t - 0.5) / 0.5).numpy()
 
@@ -69,6 +74,7 @@ def main():
         ref_import.load_reference_pyblur()          # fresh LineDictionary (the reference mutates it)
         random.seed(seed)
         np.random.seed(seed)
+        torch.manual_seed(seed)
         outs.append(reference_lq(deg, DS, gt, OPT))
         gts.append(gt)
         seeds.append(seed)
@@ -76,7 +82,8 @@ def main():
     recs = []
     for gt, seed in zip(gts, seeds):
         pr, nr = random.Random(seed), np.random.RandomState(seed)
-        recs.append(D.sample_params(1, H, W, OPT, py_random=pr, np_random=nr))
+        recs.append(D.sample_params(1, H, W, OPT, py_random=pr, np_random=nr,
+                                    torch_generator=torch.Generator().manual_seed(seed)))
     kmax = 29
     taps = np.zeros((N, kmax, kmax), np.float64)
     for i, r in enumerate(recs):
@@ -95,9 +102,15 @@ def main():
                         quality=np.array([r['quality'][0] for r in recs]),
                         jitter=np.stack([r['jitter'][0] for r in recs]), gray=np.array([r['gray'][0] for r in recs]),
                         bsigma=np.array([r['bilateral_sigma'][0] for r in recs], dtype=np.float32),
+                        cj_n=np.array([len(r['color_jitter_pt'][0]) for r in recs]),
+                        cj_op=np.array([[s[0] for s in r['color_jitter_pt'][0]] + [0] * (4 - len(r['color_jitter_pt'][0]))
+                                        for r in recs]),
+                        cj_f=np.array([[s[1] for s in r['color_jitter_pt'][0]] + [0.] * (4 - len(r['color_jitter_pt'][0]))
+                                       for r in recs], dtype=np.float64),
                         kinds=np.array([r['desc'][0][0] for r in recs]))
     print('kinds', [r['desc'][0][0] for r in recs])
     print('gray', [r['gray'][0] for r in recs], 'quality', [r['quality'][0] for r in recs])
+    print('cj', [r['color_jitter_pt'][0] for r in recs])
 
 
 if __name__ == '__main__':

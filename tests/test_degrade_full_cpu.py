@@ -12,6 +12,7 @@ import random
 import cv2
 import numpy as np
 import pytest
+import torch
 
 from image_restoration_b200 import degradation as D
 from oracle import degrade_full_oracle as dfo
@@ -33,14 +34,15 @@ def golden_case(g, i):
         kernel = kernel.astype(np.float32)         # psf kernels: the reference's convolve2d runs in float32
     return dict(gt=g['gt'][i], mode=int(g['modes'][i]), kernel=kernel, lr_size=(lw, lh),
                 noise=g['noise'][i, :lh, :lw], quality=int(g['quality'][i]), jitter=g['jitter'][i], gray=int(g['gray'][i]),
-                bsigma=float(g['bsigma'][i]))
+                bsigma=float(g['bsigma'][i]),
+                cj=[(int(g['cj_op'][i][k]), float(g['cj_f'][i][k])) for k in range(int(g['cj_n'][i]))])
 
 
 def test_golden_covers_every_stage():
     g = np.load(GOLD)
     kinds = set(str(k) for k in g['kinds'])
     assert {'iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'} <= kinds, kinds
-    assert g['gray'].any() and (g['jitter'] != 0).any() and (g['quality'] > 0).all()
+    assert g['gray'].any() and (g['jitter'] != 0).any() and (g['quality'] > 0).all() and (g['cj_n'] == 4).sum() >= 4
 
 
 def test_oracle_reproduces_golden_reference_outputs():
@@ -48,11 +50,11 @@ def test_oracle_reproduces_golden_reference_outputs():
     for i in range(len(g['seeds'])):
         c = golden_case(g, i)
         lib, _ = dfo.degrade_full(c['gt'], c['mode'], c['kernel'], c['lr_size'], c['noise'], c['quality'], c['jitter'],
-                                  c['gray'], exact_blur=False, bilateral_sigma=c['bsigma'])
+                                  c['gray'], exact_blur=False, bilateral_sigma=c['bsigma'], cj=c['cj'])
         assert np.array_equal(to_u8(lib), g['out_u8'][i].astype(np.int32)), (i, str(g['kinds'][i]))
         # explicit-sum blur: the same image up to the last-bit difference of OpenCV's DFT path, i.e. rare single codes
         exact, _ = dfo.degrade_full(c['gt'], c['mode'], c['kernel'], c['lr_size'], c['noise'], c['quality'], c['jitter'],
-                                    c['gray'], exact_blur=True, bilateral_sigma=c['bsigma'])
+                                    c['gray'], exact_blur=True, bilateral_sigma=c['bsigma'], cj=c['cj'])
         diff = np.abs(to_u8(exact) - g['out_u8'][i].astype(np.int32))
         if c['mode'] in (1, 3):  # pyblur: the explicit summation tree is scipy's; median: integer -> identical
             assert diff.max() == 0, (i, diff.max())
@@ -167,13 +169,15 @@ def test_host_mirror_and_oracle_equal_reference_chain():
         ref_import.load_reference_pyblur()
         random.seed(seed)
         np.random.seed(seed)
+        torch.manual_seed(seed)
         ref = mk.reference_lq(deg, DS, gt, mk.OPT)
-        p = D.sample_params(1, H, W, mk.OPT, py_random=random.Random(seed), np_random=np.random.RandomState(seed))
+        p = D.sample_params(1, H, W, mk.OPT, py_random=random.Random(seed), np_random=np.random.RandomState(seed),
+                            torch_generator=torch.Generator().manual_seed(seed))
         kinds.add(p['desc'][0][0])
         lw, lh = p['sizes'][0]
         got, _ = dfo.degrade_full(gt, p['modes'][0], p['kernels'][0], (lw, lh), p['noise'][0, :lh, :lw], p['quality'][0],
                                   p['jitter'][0], p['gray'][0], exact_blur=False, lib_jpeg=False,
-                                  bilateral_sigma=p['bilateral_sigma'][0])
+                                  bilateral_sigma=p['bilateral_sigma'][0], cj=p['color_jitter_pt'][0])
         assert np.array_equal(got, ref), (i, p['desc'][0])
     assert len(kinds) >= 5 and {'median', 'bilateral'} <= kinds, kinds
 

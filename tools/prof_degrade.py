@@ -18,7 +18,8 @@ nz_d = torch.from_numpy(nz).cuda()
 packed = dg.pack_degradation(kernels, sizes, 'cuda')
 opt = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'],
            kernel_prob=[0.08, 0.08, 0.08, 0.08, 0.08, 0.08, 0.28], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
-           noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, gray_prob=0.1)
+           noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20, color_jitter_pt_prob=0.3,
+           gray_prob=0.01)
 prm = dg.sample_params(DB, H, W, opt, py_random=random.Random(0), np_random=np.random.RandomState(0))
 pk = dg.pack_degrade_full(dev='cuda', **prm)
 for _ in range(3):
