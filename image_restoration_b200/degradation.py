@@ -422,6 +422,8 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random, torch_gener
     from torch's global generator, as the reference does).  opt carries the dataset options of the training YAML (kernel_list, kernel_prob, blur_kernel_size,
     blur_sigma, downsample_range, noise_range, jpeg_range, color_jitter_prob, color_jitter_shift, gray_prob).
     Returns a dict of host arrays ready for degrade_full_batch."""
+    if opt.get('random_mask'):
+        raise NotImplementedError('random_mask (ffhq_degradation_dataset.py:153-186) has no B200 implementation')
     ks = opt['blur_kernel_size']
     modes, kernels, sizes, noises, quality, jitter, gray, desc, bsigma, cj = [], [], [], [], [], [], [], [], [], []
     for _ in range(B):

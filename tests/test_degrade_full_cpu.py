@@ -119,6 +119,8 @@ def test_kernel_builders_known_answers():
     assert D.average_kernel(5).dtype == np.float32 and np.allclose(D.average_kernel(5), 0.04)
     with pytest.raises(NotImplementedError):
         D.random_mixed_kernel(['bicubic'], [1.0], 21)
+    with pytest.raises(NotImplementedError):
+        D.sample_params(1, 32, 64, dict(blur_kernel_size=21, random_mask=True))
 
 
 @pytest.mark.skipif(not ref_import.available(), reason='/root/reference not present')
