@@ -94,7 +94,7 @@ SIGNATURES = {
     'b200ir_ca_mlp': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'b200ir_ca_scale_add': [_P, _P, _P, _P, _F, _I, _I, _I, _L, _L, _P],
     'b200ir_degrade': [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
-    'b200ir_degrade_full': [_P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_degrade_full': [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64}
 

@@ -71,7 +71,8 @@ __device__ __forceinline__ int df_compact_taps(const double* __restrict__ tp, in
 // kMode 2: cv2.filter2D on value/255, BORDER_REFLECT_101: every tap is its own group (plain running sum, fp32).
 template <typename T, int kMode, bool kInterior>
 __device__ __forceinline__ void df_blur3(const uint8_t* __restrict__ img, const float* __restrict__ lut, int H, int W, int y,
-                                         int x, const DfTap* __restrict__ nz, int n_nz, T (&s)[3]) {
+                                         int x, const DfTap* __restrict__ nz, int n_nz, T (&s)[3],
+                                         const float* __restrict__ imgf = nullptr) {
   s[0] = s[1] = s[2] = (T)0;
   T g0 = (T)0, g1 = (T)0, g2 = (T)0;
   for (int k = 0; k < n_nz; ++k) {
@@ -92,10 +93,17 @@ __device__ __forceinline__ void df_blur3(const uint8_t* __restrict__ img, const 
         iy = iy < 0 ? -iy : (iy >= H ? 2 * H - 2 - iy : iy);
         ix = ix < 0 ? -ix : (ix >= W ? 2 * W - 2 - ix : ix);
       }
-      const uint8_t* px = img + (iy * W + ix) * 3;
-      v0 = (T)lut[px[0]];
-      v1 = (T)lut[px[1]];
-      v2 = (T)lut[px[2]];
+      if (imgf != nullptr) {  // float GT image (not on the 8-bit grid): filter2D works on the float values
+        const float* pf = imgf + (iy * W + ix) * 3;
+        v0 = (T)pf[0];
+        v1 = (T)pf[1];
+        v2 = (T)pf[2];
+      } else {
+        const uint8_t* px = img + (iy * W + ix) * 3;
+        v0 = (T)lut[px[0]];
+        v1 = (T)lut[px[1]];
+        v2 = (T)lut[px[2]];
+      }
     }
     const T p0 = df_mul(w, v0), p1 = df_mul(w, v1), p2 = df_mul(w, v2);
     if (t.grp & 1) {
@@ -117,10 +125,11 @@ __device__ __forceinline__ void df_blur3(const uint8_t* __restrict__ img, const 
 
 template <typename T, int kMode>
 __device__ __forceinline__ void df_blur3_at(const uint8_t* __restrict__ img, const float* __restrict__ lut, int H, int W,
-                                            int y, int x, int rad, const DfTap* __restrict__ nz, int n_nz, float (&v)[3]) {
+                                            int y, int x, int rad, const DfTap* __restrict__ nz, int n_nz, float (&v)[3],
+                                            const float* __restrict__ imgf = nullptr) {
   T s[3];
-  if (y >= rad && y + rad < H && x >= rad && x + rad < W) df_blur3<T, kMode, true>(img, lut, H, W, y, x, nz, n_nz, s);
-  else df_blur3<T, kMode, false>(img, lut, H, W, y, x, nz, n_nz, s);
+  if (y >= rad && y + rad < H && x >= rad && x + rad < W) df_blur3<T, kMode, true>(img, lut, H, W, y, x, nz, n_nz, s, imgf);
+  else df_blur3<T, kMode, false>(img, lut, H, W, y, x, nz, n_nz, s, imgf);
   if (kMode == 1) {  // .astype(uint8) (truncation; the sum is inside [0, 255] up to rounding), then / 255
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = lut[(int)fmin(fmax((double)s[c], 0.0), 255.0)];

@@ -289,7 +289,8 @@ __device__ __forceinline__ void df_bilateral3(const uint8_t* __restrict__ img, i
 
 template <bool kStage>
 __global__ void __launch_bounds__(kDfThreads, 1)
-degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ taps_all, int kmax,
+degrade_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ gt_f32, const double* __restrict__ taps_all,
+                    int kmax,
                     const b200ir_degrade_crop* __restrict__ crops, const float* __restrict__ noise, int lr_wmax,
                     int lr_hmax, float* __restrict__ out, float* __restrict__ lr_out, int H, int W, int bgr2rgb) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -313,6 +314,8 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
   int* s_cr = reinterpret_cast<int*>(smem + lay.crp);
   uint8_t* s_gt = smem + lay.gt;
   const uint8_t* g_img = gt + (size_t)b * H * W * 3;
+  const float* g_imgf = gt_f32 != nullptr ? gt_f32 + (size_t)b * H * W * 3 : nullptr;  // float GT: used where the
+                                                                                       // reference keeps float values
 
   // ---- set-up: compacted taps (one warp, kernel order), resize taps, u8/255 table, quantisation tables, GT staging
   if (tid < 32) {
@@ -366,7 +369,7 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
           if (cp.blur_f64) df_blur3_at<double, 1>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
           else df_blur3_at<float, 1>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
         } else if (mode == 2) {
-          df_blur3_at<float, 2>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v);
+          df_blur3_at<float, 2>(img, s_lut, H, W, y, x, rad, s_nz, n_nz, v, g_imgf);
         } else {
           const bool inside = y >= rad && y + rad < H && x >= rad && x + rad < W;
           int u[3];
@@ -381,6 +384,11 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
           v[1] = s_lut[u[1]];
           v[2] = s_lut[u[2]];
         }
+      } else if (g_imgf != nullptr) {
+        const float* p = g_imgf + (y * W + x) * 3;
+        v[0] = p[0];
+        v[1] = p[1];
+        v[2] = p[2];
       } else {
         const uint8_t* p = img + (y * W + x) * 3;
         v[0] = s_lut[p[0]];
@@ -606,11 +614,19 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const double* __restrict__ t
   }
 }
 
+// np.array(img * 255.0, dtype=np.uint8) of random_pyblur / median_blur / bilateral_blur (degradations.py:353-366):
+// fp32 product, truncation toward zero.
+__global__ void gt_to_u8_kernel(const float* __restrict__ f, uint8_t* __restrict__ u, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) u[i] = (uint8_t)(int)fminf(fmaxf(__fmul_rn(f[i], 255.f), 0.f), 255.f);
+}
+
 }  // namespace b200ir
 
 using namespace b200ir;
 
-extern "C" int b200ir_degrade_full(const uint8_t* gt, const double* taps, int kmax, const b200ir_degrade_crop* crops,
+extern "C" int b200ir_degrade_full(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
+                                   const b200ir_degrade_crop* crops,
                                    const float* noise, int lr_wmax, int lr_hmax, float* out, float* lr_out, int B, int H,
                                    int W, int bgr2rgb, void* stream) {
   B200IR_REQUIRE(gt && taps && crops && out, "degrade_full: null pointer");
@@ -623,6 +639,11 @@ extern "C" int b200ir_degrade_full(const uint8_t* gt, const double* taps, int km
     set_error("degrade_full: no CUDA device");
     return 1;
   }
+  if (gt_f32 != nullptr) {
+    const size_t n = (size_t)B * H * W * 3;
+    gt_to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gt_f32, gt, n);
+    if (check_launch("degrade_full(gt -> uint8)")) return 1;
+  }
   const size_t base = df_layout(kmax, lr_wmax, lr_hmax, H, W, false).total;
   const size_t staged = df_layout(kmax, lr_wmax, lr_hmax, H, W, true).total;
   B200IR_REQUIRE(base <= (size_t)smem_optin, "degrade_full: low-resolution image %dx%d does not fit shared memory",
@@ -630,11 +651,11 @@ extern "C" int b200ir_degrade_full(const uint8_t* gt, const double* taps, int km
   const bool stage = staged <= (size_t)smem_optin && (H * W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(gt) & 15) == 0;
   if (stage) {
     cudaFuncSetAttribute(degrade_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
-    degrade_full_kernel<true><<<B, kDfThreads, staged, st>>>(gt, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
+    degrade_full_kernel<true><<<B, kDfThreads, staged, st>>>(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
                                                             H, W, bgr2rgb);
   } else {
     cudaFuncSetAttribute(degrade_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-    degrade_full_kernel<false><<<B, kDfThreads, base, st>>>(gt, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
+    degrade_full_kernel<false><<<B, kDfThreads, base, st>>>(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
                                                            H, W, bgr2rgb);
   }
   return check_launch("degrade_full");

@@ -509,14 +509,18 @@ def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=No
 def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, quality=None, jitter=None, gray=None,
                        bilateral_sigma=None, color_jitter_pt=None, bgr2rgb=True, return_lr=False, packed=None, **_unused):
     """One launch of b200ir_degrade_full over a batch (see include/b200ir.h).  gt_u8: uint8 CUDA tensor [B,H,W,3] in
-    the reference's channel order (BGR); the other arguments as returned by sample_params (or packed= the result of
+    the reference's channel order (BGR), or a float32 CUDA tensor [B,H,W,3] in [0,1] (the reference's img_gt after
+    cv2.resize, not on the 8-bit grid: filter2D kinds then work on the float values as the reference does); the other arguments as returned by sample_params (or packed= the result of
     pack_degrade_full).  Returns the LQ batch fp32 [B,3,H,W] in [-1,1] (and the low-resolution image after noise /
     JPEG if return_lr)."""
-    if not (gt_u8.is_cuda and gt_u8.dtype == torch.uint8 and gt_u8.dim() == 4 and gt_u8.shape[3] == 3):
-        raise ValueError('gt_u8 must be a uint8 CUDA tensor [B,H,W,3]; image_restoration_b200 has no CPU path')
+    if not (gt_u8.is_cuda and gt_u8.dtype in (torch.uint8, torch.float32) and gt_u8.dim() == 4 and gt_u8.shape[3] == 3):
+        raise ValueError('gt_u8 must be a uint8 or float32 CUDA tensor [B,H,W,3]; image_restoration_b200 has no CPU path')
     gt_u8 = gt_u8.contiguous()
     B, H, W, _ = gt_u8.shape
     dev = gt_u8.device
+    gt_f32 = None
+    if gt_u8.dtype == torch.float32:
+        gt_f32, gt_u8 = gt_u8, torch.empty(B, H, W, 3, device=dev, dtype=torch.uint8)   # scratch the launch fills
     pk = packed if packed is not None else pack_degrade_full(modes, kernels, sizes, noise, quality, jitter, gray,
                                                              bilateral_sigma, color_jitter_pt, dev)
     assert pk['n'] == B
@@ -525,7 +529,7 @@ def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, 
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)  # noqa: E731
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.lib().b200ir_degrade_full(p(gt_u8), p(pk['taps']), pk['kmax'], p(pk['crops']), p(pk['noise']),
+        _lib.check(_lib.lib().b200ir_degrade_full(p(gt_u8), p(gt_f32), p(pk['taps']), pk['kmax'], p(pk['crops']), p(pk['noise']),
                                                   pk['lr_wmax'], pk['lr_hmax'], p(out), p(lr), B, H, W,
                                                   1 if bgr2rgb else 0, st), 'b200ir_degrade_full')
     return (out, lr) if return_lr else out

@@ -344,11 +344,15 @@ typedef struct b200ir_degrade_crop {
   float cj_one_minus[4]; /* (float)(1.0 - factor), the second blend weight as torchvision's _blend evaluates it */
 } b200ir_degrade_crop;
 
-/* gt uint8 [B][H][W][3] (channel order B,G,R as the reference holds images); taps fp64 [B][kmax][kmax] centred, zero
+/* gt uint8 [B][H][W][3] (channel order B,G,R as the reference holds images).  gt_f32 (optional): the float image
+ * img_gt in [0, 1] when it is NOT on the 8-bit grid (the dataset resizes every GT image with cv2.resize,
+ * ffhq_degradation_dataset.py:230): the filter2D kinds and the no-blur case then read the float values, and gt is a
+ * caller-owned scratch buffer that this call first fills with np.array(img * 255.0, dtype=uint8) for the pyblur /
+ * median / bilateral kinds (degradations.py:353-366); taps fp64 [B][kmax][kmax] centred, zero
  * padded (blur_mode 2 rounds them to fp32 as cv2.filter2D does); crops: device array [B]; noise fp32 [B][lr_hmax][lr_wmax][3] already scaled by sigma/255, or NULL;
  * out fp32 NCHW [B][3][H][W] normalised to [-1, 1] (channels reversed when bgr2rgb); lr_out (optional, parity aid):
  * the low-resolution image after noise / JPEG, fp32 [B][lr_hmax][lr_wmax][3]. */
-int b200ir_degrade_full(const uint8_t* gt, const double* taps, int kmax, const b200ir_degrade_crop* crops,
+int b200ir_degrade_full(uint8_t* gt, const float* gt_f32, const double* taps, int kmax, const b200ir_degrade_crop* crops,
                         const float* noise, int lr_wmax, int lr_hmax, float* out, float* lr_out, int B, int H, int W,
                         int bgr2rgb, void* stream);
 

@@ -166,9 +166,14 @@ def color_jitter_pt(img_bgr, steps):
 
 def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, exact_blur=True, lib_jpeg=False,
              bilateral_sigma=0.0, cj=None):
-    """uint8 BGR [H,W,3] -> float32 BGR [H,W,3] LQ image before the 8-bit rounding, plus the LR image after noise/JPEG."""
+    """uint8 BGR [H,W,3] (or the float32 image in [0,1] the dataset holds after its cv2.resize) -> float32 BGR [H,W,3] LQ
+    image before the 8-bit rounding, plus the LR image after noise/JPEG."""
     H, W = gt_u8.shape[:2]
-    img = gt_u8.astype(np.float32) / np.float32(255.)
+    if gt_u8.dtype == np.uint8:
+        img = gt_u8.astype(np.float32) / np.float32(255.)
+    else:       # random_pyblur / median_blur / bilateral_blur quantise with np.array(img * 255.0, dtype=np.uint8)
+        img = gt_u8
+        gt_u8 = np.array(img * 255.0, dtype=np.uint8)
     if mode == 2:
         k = np.asarray(kernel, dtype=np.float32)
         img = filter2d_direct(img, k) if exact_blur else cv2.filter2D(img, -1, np.asarray(kernel))

@@ -33,10 +33,11 @@ def smooth_crop(rng, h, w):
     return (img * 255).astype(np.uint8)
 
 
-def reference_lq(deg, DS, gt_u8, opt):
+def reference_lq(deg, DS, gt, opt):
     """__getitem__ lines 242-311 for one crop, calling the reference's functions (random state: the global
-    `random` / `np.random`, seeded by the caller)."""
-    img_gt = gt_u8.astype(np.float32) / 255.
+    `random` / `np.random` / torch generator, seeded by the caller).  gt: uint8 image (imfrombytes float32 = u8 / 255) or the
+    float32 image in [0, 1] the dataset holds after its cv2.resize (:230)."""
+    img_gt = gt.astype(np.float32) / 255. if gt.dtype == np.uint8 else gt
     h, w, _ = img_gt.shape
     img_lq = deg.random_mixed_kernels(img=img_gt, kernel_list=opt['kernel_list'], kernel_prob=opt['kernel_prob'],
                                       kernel_size=opt['blur_kernel_size'], sigma_x_range=opt['blur_sigma'],
@@ -65,12 +66,19 @@ def reference_lq(deg, DS, gt_u8, opt):
 
 def main():
     deg, DS = ref_import.load_reference_degradations()
-    rng = np.random.default_rng(7)
-    H, W, N = 128, 384, 20
+    make(deg, DS, 'degrade_full.npz', 128, 384, 20, 1000, np.random.default_rng(7), float_gt=False)
+    # GT images that are not on the 8-bit grid: the dataset resizes every image to the network size (:230)
+    make(deg, DS, 'degrade_full_floatgt.npz', 64, 192, 12, 3000, np.random.default_rng(9), float_gt=True)
+
+
+def make(deg, DS, fname, H, W, N, seed0, rng, float_gt):
     gts, outs, seeds = [], [], []
     for i in range(N):
         gt = smooth_crop(rng, H, W)
-        seed = 1000 + i
+        if float_gt:
+            big = smooth_crop(rng, H * 2 + 7, W * 2 + 5).astype(np.float32) / 255.
+            gt = cv2.resize(big, (W, H), interpolation=cv2.INTER_LINEAR)
+        seed = seed0 + i
         ref_import.load_reference_pyblur()          # fresh LineDictionary (the reference mutates it)
         random.seed(seed)
         np.random.seed(seed)
@@ -94,7 +102,7 @@ def main():
     noise = np.zeros((N, lh.max(), lw.max(), 3), np.float32)
     for i, r in enumerate(recs):
         noise[i, :lh[i], :lw[i]] = r['noise'][0]
-    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'degrade_full.npz'), gt=np.stack(gts),
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', fname), gt=np.stack(gts),
                         out_u8=np.rint((np.stack(outs) * 0.5 + 0.5) * 255).astype(np.uint8), seeds=np.array(seeds),
                         modes=np.array([r['modes'][0] for r in recs]), taps=taps,
                         ksize=np.array([r['kernels'][0].shape[0] for r in recs]),

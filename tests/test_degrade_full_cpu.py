@@ -45,8 +45,9 @@ def test_golden_covers_every_stage():
     assert g['gray'].any() and (g['jitter'] != 0).any() and (g['quality'] > 0).all() and (g['cj_n'] == 4).sum() >= 4
 
 
-def test_oracle_reproduces_golden_reference_outputs():
-    g = np.load(GOLD)
+@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz'])
+def test_oracle_reproduces_golden_reference_outputs(fname):
+    g = np.load(os.path.join(os.path.dirname(GOLD), fname))
     for i in range(len(g['seeds'])):
         c = golden_case(g, i)
         lib, _ = dfo.degrade_full(c['gt'], c['mode'], c['kernel'], c['lr_size'], c['noise'], c['quality'], c['jitter'],

@@ -33,8 +33,8 @@ def run_gpu(gt, modes, kernels, sizes, noise, quality, jitter, gray, bgr2rgb=Tru
     return out.cpu().numpy(), lr.cpu().numpy()
 
 
-def golden_batch():
-    g = np.load(GOLD)
+def golden_batch(fname='degrade_full.npz'):
+    g = np.load(os.path.join(os.path.dirname(GOLD), fname))
     n, kmax = len(g['seeds']), g['taps'].shape[1]
     kernels = []
     for i in range(n):
@@ -47,8 +47,10 @@ def golden_batch():
     return g, kernels, sizes, cj
 
 
-def test_golden_reference_outputs():
-    g, kernels, sizes, cj = golden_batch()
+@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz'])
+def test_golden_reference_outputs(fname):
+    """degrade_full_floatgt.npz: GT images off the 8-bit grid (the dataset's cv2.resize), passed as float32."""
+    g, kernels, sizes, cj = golden_batch(fname)
     out, lr = run_gpu(g['gt'], [int(m) for m in g['modes']], kernels, sizes, g['noise'], [int(q) for q in g['quality']],
                       g['jitter'], [int(x) for x in g['gray']], bsigma=[float(x) for x in g['bsigma']], cj=cj)
     exact = 0
@@ -65,8 +67,9 @@ def test_golden_reference_outputs():
     assert exact >= len(kernels) // 2, exact
 
 
-def test_golden_against_oracle_stage_by_stage():
-    g, kernels, sizes, cj = golden_batch()
+@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz'])
+def test_golden_against_oracle_stage_by_stage(fname):
+    g, kernels, sizes, cj = golden_batch(fname)
     out, lr = run_gpu(g['gt'], [int(m) for m in g['modes']], kernels, sizes, g['noise'], [int(q) for q in g['quality']],
                       g['jitter'], [int(x) for x in g['gray']], bsigma=[float(x) for x in g['bsigma']], cj=cj)
     for i in range(len(kernels)):

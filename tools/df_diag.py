@@ -2,7 +2,7 @@ import sys, numpy as np, torch
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import test_degrade_full_gpu as T
 from oracle import degrade_full_oracle as dfo
-g, kernels, sizes, cj = T.golden_batch()
+g, kernels, sizes, cj = T.golden_batch(sys.argv[1] if len(sys.argv) > 1 else 'degrade_full.npz')
 out, lr = T.run_gpu(g['gt'], [int(m) for m in g['modes']], kernels, sizes, g['noise'], [int(q) for q in g['quality']], g['jitter'], [int(x) for x in g['gray']], bsigma=[float(x) for x in g['bsigma']], cj=cj)
 for i in range(len(kernels)):
     lw, lh = sizes[i]
