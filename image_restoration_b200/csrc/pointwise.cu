@@ -84,6 +84,19 @@ __global__ void u8_to_input_kernel(const uint8_t* __restrict__ img, float* __res
   }
 }
 
+// img2tensor(bgr2rgb) + normalize(mean .5, std .5) of a float image in [0, 1] (the GT side of
+// FFHQDegradationDataset.__getitem__, ffhq_degradation_dataset.py:288, :310): fp32 HWC -> fp32 NCHW, (x - 0.5) / 0.5.
+__global__ void f32_to_input_kernel(const float* __restrict__ img, float* __restrict__ x, int B, int HW, int swap) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int b = (int)(idx / HW);
+  const int p = (int)(idx % HW);
+  const float* ip = img + idx * 3;
+  float* xp = x + (long long)b * 3 * HW + p;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) xp[(long long)c * HW] = __fdiv_rn(__fsub_rn(ip[swap ? 2 - c : c], 0.5f), 0.5f);
+}
+
 // tensor2img (img_util.py:38-94) with min_max = (-1, 1): clamp -> (x+1)/2 -> *255 -> round half to even -> uint8, CHW RGB ->
 // HWC (BGR when swap).
 __global__ void image_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, int B, int HW, int swap) {
@@ -832,6 +845,12 @@ extern "C" int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, in
   B200IR_REQUIRE(img && x && B > 0 && H > 0 && W > 0, "u8_to_input: bad arguments");
   u8_to_input_kernel<<<grid_for((long long)B * H * W), kPwThreads, 0, STREAM>>>(img, x, B, H * W, swap_rb);
   return check_launch("u8_to_input");
+}
+
+extern "C" int b200ir_f32_to_input(const float* img, float* x, int B, int H, int W, int swap_rb, void* stream) {
+  B200IR_REQUIRE(img && x && B > 0 && H > 0 && W > 0, "f32_to_input: bad arguments");
+  f32_to_input_kernel<<<grid_for((long long)B * H * W), kPwThreads, 0, STREAM>>>(img, x, B, H * W, swap_rb);
+  return check_launch("f32_to_input");
 }
 
 extern "C" int b200ir_image_to_u8(const float* x, uint8_t* img, int B, int H, int W, int swap_rb, void* stream) {

@@ -533,3 +533,19 @@ def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, 
                                                   pk['lr_wmax'], pk['lr_hmax'], p(out), p(lr), B, H, W,
                                                   1 if bgr2rgb else 0, st), 'b200ir_degrade_full')
     return (out, lr) if return_lr else out
+
+
+def synthesize_pairs(gt, opt, py_random=None, np_random=np.random, torch_generator=None):
+    """The training pair FFHQDegradationDataset.__getitem__ returns (ffhq_degradation_dataset.py:221-331), for a batch of
+    GT crops already at the network size and resident on the device: gt uint8 [B,H,W,3] (BGR) or float32 in [0,1].
+    Returns {'lq': fp32 [B,3,H,W], 'gt': fp32 [B,3,H,W]} (RGB, normalised with mean = std = 0.5) and the drawn parameters.
+    Two launches: b200ir_degrade_full for lq, img2tensor + normalize for gt."""
+    B, H, W, _ = gt.shape
+    prm = sample_params(B, H, W, opt, py_random=py_random, np_random=np_random, torch_generator=torch_generator)
+    lq = degrade_full_batch(gt, **prm)
+    gt_t = torch.empty(B, 3, H, W, device=gt.device, dtype=torch.float32)
+    fn = _lib.lib().b200ir_u8_to_input if gt.dtype == torch.uint8 else _lib.lib().b200ir_f32_to_input
+    with torch.cuda.device(gt.device):
+        _lib.check(fn(C.c_void_p(gt.contiguous().data_ptr()), C.c_void_p(gt_t.data_ptr()), B, H, W, 1,
+                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'gt img2tensor + normalize')
+    return {'lq': lq, 'gt': gt_t}, prm

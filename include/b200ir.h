@@ -159,6 +159,9 @@ int b200ir_first_conv(const float* x, const float* w, const float* bias, void* o
  * image_to_u8  = tensor2img(out, rgb2bgr=True, min_max=(-1, 1)) (img_util.py:38-94): clamp, (x+1)/2, *255, round half
  *                to even, uint8 HWC.  swap_rb != 0 reverses the channel order (BGR images, as cv2 delivers them). */
 int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, int W, int swap_rb, void* stream);
+/* the same for a float image in [0, 1] (the GT side of FFHQDegradationDataset.__getitem__,
+ * ffhq_degradation_dataset.py:288, :310): fp32 HWC [B][H][W][3] -> fp32 NCHW, (x - 0.5) / 0.5 */
+int b200ir_f32_to_input(const float* img, float* x, int B, int H, int W, int swap_rb, void* stream);
 int b200ir_image_to_u8(const float* x, uint8_t* img, int B, int H, int W, int swap_rb, void* stream);
 
 /* Helpers of the folded ConvUpLayer (b200ir_conv_desc.corr_*): replicate_border fills the one-pixel ring of an NHWC fp16

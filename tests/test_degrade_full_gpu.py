@@ -153,3 +153,36 @@ def test_bad_arguments_raise():
         D.degrade_full_batch(gt, [0], [None], [(8, 4)])                       # CPU tensor: no CPU path
     with pytest.raises(ValueError):
         D.degrade_full_batch(gt.cuda(), [0], [None], [(1, 1)])                # LR image below 2x2
+
+
+def test_synthesize_pairs_feeds_the_network():
+    """The data path of BASELINE config 5: GT crops on the device -> (lq, gt) pair -> forward of the restoration net."""
+    import random
+    from image_restoration_b200 import GFPGANv1OCR, degradation as D
+    opt = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'],
+               kernel_prob=[0.08, 0.08, 0.08, 0.08, 0.08, 0.08, 0.28], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
+               noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20,
+               color_jitter_pt_prob=0.3, gray_prob=0.01)
+    rng = np.random.RandomState(1)
+    for dtype in (np.uint8, np.float32):
+        gt = rng.randint(0, 256, (8, 128, 384, 3)).astype(np.uint8)
+        gt_in = gt if dtype == np.uint8 else (gt.astype(np.float32) / 255.)
+        pair, prm = D.synthesize_pairs(torch.from_numpy(gt_in).cuda(), opt, py_random=random.Random(3),
+                                       np_random=np.random.RandomState(3), torch_generator=torch.Generator().manual_seed(3))
+        ref_gt = (gt[..., ::-1].transpose(0, 3, 1, 2).astype(np.float32) / np.float32(255.) - np.float32(0.5)) / np.float32(0.5)
+        assert np.array_equal(pair['gt'].cpu().numpy(), ref_gt)
+        lq = pair['lq']
+        assert lq.shape == (8, 3, 128, 384) and torch.isfinite(lq).all() and lq.min() >= -1 and lq.max() <= 1
+        for b in range(8):                      # same draws, oracle on the host
+            lw, lh = prm['sizes'][b]
+            ref, _ = dfo.degrade_full(gt_in[b], prm['modes'][b], prm['kernels'][b], (lw, lh), prm['noise'][b, :lh, :lw],
+                                      prm['quality'][b], prm['jitter'][b], prm['gray'][b], exact_blur=True,
+                                      bilateral_sigma=prm['bilateral_sigma'][b], cj=prm['color_jitter_pt'][b])
+            d = np.abs(to_u8(lq[b].cpu().numpy()) - to_u8(ref))
+            assert d.max() <= 1 and (d > 0).mean() < 1e-3, (b, prm['desc'][b], d.max())
+    kw = dict(input_width=384, input_height=128, num_style_feat=256, channel_multiplier=0.5, num_mlp=4,
+              input_is_latent=True, different_w=True, narrow=1, sft_half=True)
+    torch.manual_seed(0)
+    net = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **kw).eval().cuda()
+    out, _ = net(lq, return_rgb=False, randomize_noise=False)
+    assert out.shape == (8, 3, 128, 384) and torch.isfinite(out).all()
