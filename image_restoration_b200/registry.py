@@ -7,37 +7,38 @@ import sys
 
 
 class Registry:
+    """name -> class table.  `_obj_map` is kept as the storage attribute because callers of the reference's registry
+    (and register_into(override=True) here) reach into it directly."""
+
     def __init__(self, name):
-        self._name = name
-        self._obj_map = {}
+        self._name, self._obj_map = name, {}
 
     def _do_register(self, name, obj):
-        assert name not in self._obj_map, (f"An object named '{name}' was already registered "
-                                           f"in '{self._name}' registry!")
+        if name in self._obj_map:       # the reference asserts on duplicates (registry.py:38-41); same exception type
+            raise AssertionError(f"'{name}' is already present in the '{self._name}' registry")
         self._obj_map[name] = obj
 
     def register(self, obj=None):
-        if obj is None:
-            def deco(func_or_class):
-                self._do_register(func_or_class.__name__, func_or_class)
-                return func_or_class
-            return deco
-        self._do_register(obj.__name__, obj)
+        """@REGISTRY.register() on a class / function, or REGISTRY.register(obj)."""
+        def add(target):
+            self._do_register(target.__name__, target)
+            return target
+        return add if obj is None else (add(obj) and None)
 
     def get(self, name):
-        ret = self._obj_map.get(name)
-        if ret is None:
-            raise KeyError(f"No object named '{name}' found in '{self._name}' registry!")
-        return ret
+        try:
+            return self._obj_map[name]
+        except KeyError:
+            raise KeyError(f"'{name}' is not in the '{self._name}' registry (known: {sorted(self._obj_map)})") from None
+
+    def keys(self):
+        return self._obj_map.keys()
 
     def __contains__(self, name):
         return name in self._obj_map
 
     def __iter__(self):
-        return iter(self._obj_map.items())
-
-    def keys(self):
-        return self._obj_map.keys()
+        yield from self._obj_map.items()
 
 
 _ref = sys.modules.get('basicsr.utils.registry')
