@@ -337,6 +337,16 @@ def main():
                  'config': '3x1080x1920 frame, 256x256 tiles, overlap 32 (5x9 tiles, one batch), gather + forward + '
                            'ramp blend, frame resident in HBM'}
         del net256, tiler
+        # network_d of the training YAMLs (forward only: first piece of the training-step row)
+        from image_restoration_b200.disc import StyleGAN2Discriminator
+        torch.manual_seed(0)
+        netd = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1).eval().to(dev)
+        xd = torch.rand(B, 3, H, W, device=dev) * 2 - 1
+        ms_d = timed(lambda: netd(xd), 10, 3) / 10
+        disc = {'crops_per_s': B / (ms_d / 1e3), 'ms_per_batch': ms_d, 'batch': B,
+                'config': f'StyleGAN2Discriminator(input_width={W}, input_height={H}, channel_multiplier=1) forward, eager '
+                          'launches'}
+        del netd
         degr['full_chain'] = {'kernel': 'degrade_full_kernel', 'crops_per_s': DB / (ms_full / 1e3), 'ms_per_batch': ms_full,
                               'batch': DB, 'achieved_gbs': alg / ms_full / 1e6,
                               'stages': 'blur (iso/aniso/motion/average/median/bilateral/pyblur, kernel_list and kernel_prob of '
@@ -399,6 +409,7 @@ def main():
             degr['frac_of_hbm_peak'] = degr['achieved_gbs'] / hbm_peak
             line['degradation'] = degr
             line['tiled_full_frame'] = tiled
+            line['discriminator_forward'] = disc
         if pw_report:
             top = pw_report[0]
             line['roofline_hbm'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_gbs'],

@@ -67,6 +67,45 @@ __global__ void first_conv_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------ minibatch stddev
+// StyleGAN2Discriminator.forward (stylegan2_arch.py:791-801): group = min(B, stddev_group); the batch is viewed as
+// (group, M = B / group, C, h, w); s[m] = mean over (c, h, w) of sqrt(var over the group (biased) + 1e-8); sample b gets
+// s[b % M] as one extra channel.  x NHWC fp16 [B][P][C]; one block per m reduces P * C positions.
+__global__ void mbstd_reduce_kernel(const __half* __restrict__ x, float* __restrict__ s, int M, int group, int PC) {
+  const int m = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < PC; i += blockDim.x) {
+    float v[8], mean = 0.f;
+    for (int g = 0; g < group; ++g) {
+      v[g] = __half2float(x[((long long)g * M + m) * PC + i]);
+      mean += v[g];
+    }
+    mean /= (float)group;
+    float var = 0.f;
+    for (int g = 0; g < group; ++g) var += (v[g] - mean) * (v[g] - mean);
+    acc += sqrtf(var / (float)group + 1e-8f);
+  }
+  __shared__ float red[32];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    s[m] = t / (float)PC;
+  }
+}
+// out [B][P][c_pad] = concat(x, s[b % M], zeros): the input of final_conv with its channel count padded to the MMA K step
+__global__ void mbstd_concat_kernel(const __half* __restrict__ x, const float* __restrict__ s, __half* __restrict__ out,
+                                    int B, int P, int C, int c_pad, int M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * P * c_pad) return;
+  const int c = (int)(idx % c_pad);
+  const long long bp = idx / c_pad;
+  const int b = (int)(bp / P);
+  out[idx] = c < C ? x[bp * C + c] : (c == C ? __float2half_rn(s[b % M]) : __float2half_rn(0.f));
+}
+
 // ------------------------------------------------------------------------------------------ uint8 image I/O
 // img2tensor + normalize (basicsr/utils/img_util.py:9-35, api.py:96-101): uint8 HWC (BGR when swap) ->
 // fp32 NCHW RGB, x/255 then (x - mean)/std with mean = std = 0.5.
@@ -845,6 +884,19 @@ extern "C" int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, in
   B200IR_REQUIRE(img && x && B > 0 && H > 0 && W > 0, "u8_to_input: bad arguments");
   u8_to_input_kernel<<<grid_for((long long)B * H * W), kPwThreads, 0, STREAM>>>(img, x, B, H * W, swap_rb);
   return check_launch("u8_to_input");
+}
+
+extern "C" int b200ir_minibatch_stddev(const void* x, float* s, void* out, int B, int P, int C, int c_pad, int group,
+                                       void* stream) {
+  B200IR_REQUIRE(x && s && out && B > 0 && P > 0 && C > 0 && c_pad > C, "minibatch_stddev: bad arguments");
+  B200IR_REQUIRE(group >= 1 && group <= 8 && B % group == 0, "minibatch_stddev: batch %d is not divisible by group %d", B,
+                 group);
+  const int M = B / group;
+  mbstd_reduce_kernel<<<M, 256, 0, STREAM>>>((const __half*)x, s, M, group, P * C);
+  if (check_launch("minibatch_stddev(reduce)")) return 1;
+  mbstd_concat_kernel<<<grid_for((long long)B * P * c_pad), kPwThreads, 0, STREAM>>>((const __half*)x, s, (__half*)out, B, P,
+                                                                                    C, c_pad, M);
+  return check_launch("minibatch_stddev(concat)");
 }
 
 extern "C" int b200ir_f32_to_input(const float* img, float* x, int B, int H, int W, int swap_rb, void* stream) {

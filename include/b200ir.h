@@ -153,6 +153,11 @@ int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
 int b200ir_first_conv(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int cout,
                       void* stream);
 
+/* Minibatch standard deviation of StyleGAN2Discriminator.forward (basicsr/archs/stylegan2_arch.py:791-801), stddev_feat = 1:
+ * x NHWC fp16 [B][P][C]; group = min(B, stddev_group) must divide B; s fp32 [B / group] (work buffer);
+ * out NHWC fp16 [B][P][c_pad] = concat(x, stddev channel, zero padding up to c_pad): the input of final_conv. */
+int b200ir_minibatch_stddev(const void* x, float* s, void* out, int B, int P, int C, int c_pad, int group, void* stream);
+
 /* Pre / post of the serving scripts (api.py:96-105, inference.py:61-71):
  * u8_to_input  = img2tensor(img / 255., bgr2rgb=True, float32=True) + normalize(mean .5, std .5)
  *                (basicsr/utils/img_util.py:9-35): uint8 HWC [B][H][W][3] -> fp32 NCHW [B][3][H][W] in [-1, 1];
