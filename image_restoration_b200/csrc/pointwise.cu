@@ -67,6 +67,55 @@ __global__ void first_conv_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------ optimiser step
+// torch.optim.Adam (no amsgrad, the optimizer_g / optimizer_d of gfpgan_model.py:217-248, betas (0, 0.99)) over one flat
+// fp32 buffer: four elements per thread, 16-byte accesses; grad_scale folds the all-reduce average (1 / world) in.
+//   g = grad * grad_scale + wd * p;  m = b1 * m + (1 - b1) * g;  v = b2 * v + (1 - b2) * g * g
+//   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, float b1, float b2, float eps, float wd,
+                                 float step_size, float inv_bc2_sqrt, float grad_scale, float* __restrict__ ema,
+                                 float ema_decay) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  float pp[4], gg[4], mm[4], vv[4], ee[4];
+  const bool full = i4 + 4 <= n;
+  if (full) {
+    *reinterpret_cast<float4*>(pp) = *reinterpret_cast<const float4*>(p + i4);
+    *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(g + i4);
+    *reinterpret_cast<float4*>(mm) = *reinterpret_cast<const float4*>(m + i4);
+    *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(v + i4);
+    if (ema) *reinterpret_cast<float4*>(ee) = *reinterpret_cast<const float4*>(ema + i4);
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (i4 + k < n) {
+        pp[k] = p[i4 + k]; gg[k] = g[i4 + k]; mm[k] = m[i4 + k]; vv[k] = v[i4 + k];
+        if (ema) ee[k] = ema[i4 + k];
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float gr = gg[k] * grad_scale + wd * pp[k];
+    mm[k] = b1 * mm[k] + (1.f - b1) * gr;
+    vv[k] = b2 * vv[k] + (1.f - b2) * gr * gr;
+    const float denom = __fsqrt_rn(vv[k]) * inv_bc2_sqrt + eps;          // IEEE sqrt / divide (the file builds with fast-math)
+    pp[k] = pp[k] - step_size * __fdiv_rn(mm[k], denom);
+    if (ema) ee[k] = ema_decay * ee[k] + (1.f - ema_decay) * pp[k];      // model_ema (base_model.py:50-57)
+  }
+  if (full) {
+    *reinterpret_cast<float4*>(p + i4) = *reinterpret_cast<float4*>(pp);
+    *reinterpret_cast<float4*>(m + i4) = *reinterpret_cast<float4*>(mm);
+    *reinterpret_cast<float4*>(v + i4) = *reinterpret_cast<float4*>(vv);
+    if (ema) *reinterpret_cast<float4*>(ema + i4) = *reinterpret_cast<float4*>(ee);
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (i4 + k < n) {
+        p[i4 + k] = pp[k]; m[i4 + k] = mm[k]; v[i4 + k] = vv[k];
+        if (ema) ema[i4 + k] = ee[k];
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ minibatch stddev
 // StyleGAN2Discriminator.forward (stylegan2_arch.py:791-801): group = min(B, stddev_group); the batch is viewed as
 // (group, M = B / group, C, h, w); s[m] = mean over (c, h, w) of sqrt(var over the group (biased) + 1e-8); sample b gets
@@ -884,6 +933,21 @@ extern "C" int b200ir_u8_to_input(const uint8_t* img, float* x, int B, int H, in
   B200IR_REQUIRE(img && x && B > 0 && H > 0 && W > 0, "u8_to_input: bad arguments");
   u8_to_input_kernel<<<grid_for((long long)B * H * W), kPwThreads, 0, STREAM>>>(img, x, B, H * W, swap_rb);
   return check_launch("u8_to_input");
+}
+
+extern "C" int b200ir_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                float* ema, float ema_decay, void* stream) {
+  B200IR_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+  B200IR_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+                   reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq) |
+                   reinterpret_cast<uintptr_t>(ema)) & 15) == 0, "adam_step: buffers must be 16-byte aligned");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1), inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  adam_step_kernel<<<grid_for((n + 3) / 4), kPwThreads, 0, STREAM>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+                                                                    weight_decay, step_size, inv_bc2_sqrt, grad_scale, ema,
+                                                                    ema_decay);
+  return check_launch("adam_step");
 }
 
 extern "C" int b200ir_minibatch_stddev(const void* x, float* s, void* out, int B, int P, int C, int c_pad, int group,

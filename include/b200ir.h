@@ -153,6 +153,16 @@ int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
 int b200ir_first_conv(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int cout,
                       void* stream);
 
+/* One torch.optim.Adam step (no amsgrad; optimizer_g / optimizer_d of basicsr/models/gfpgan_model.py:217-248) over a flat
+ * fp32 parameter buffer, fused with the gradient scaling of the data-parallel average (grad_scale = 1 / world) and,
+ * when ema != NULL, with the EMA update of BaseModel.model_ema (basicsr/models/base_model.py:50-57):
+ *   g = grad * grad_scale + weight_decay * p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2
+ *   p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps);  ema = decay * ema + (1 - decay) * p
+ * All buffers n fp32 elements, 16-byte aligned; step counts from 1. */
+int b200ir_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale, float* ema, float ema_decay,
+                     void* stream);
+
 /* Minibatch standard deviation of StyleGAN2Discriminator.forward (basicsr/archs/stylegan2_arch.py:791-801), stddev_feat = 1:
  * x NHWC fp16 [B][P][C]; group = min(B, stddev_group) must divide B; s fp32 [B / group] (work buffer);
  * out NHWC fp16 [B][P][c_pad] = concat(x, stddev channel, zero padding up to c_pad): the input of final_conv. */
