@@ -1,0 +1,211 @@
+// Weight gradient of a 3x3 stride-1 'same' convolution (the EqualConv2d / ConvUpLayer convs of the U-Net and of the SFT
+// heads; first backward kernel of the training-step row) as a tcgen05 GEMM whose contraction runs over
+// PIXELS:
+//     dW[co][kh][kw][ci] = sum_{b,y,x} dy[b][y][x][co] * x[b][y + kh - 1][x + kw - 1][ci]
+// Both operands arrive exactly as the forward kernel's activation tiles do -- TMA boxes of (64 channels, 32 x 4 pixels)
+// with the 128-byte swizzle, i.e. one 128-byte row per pixel -- but are handed to the tensor core as MN-MAJOR matrices
+// (rows = K = pixels, the 64 contiguous channels = M resp. N): no transposed copy of the activations exists anywhere.
+// Zero padding of the conv = TMA out-of-bounds fill of the shifted x box; pixels outside the image contribute zeros on
+// the dy side as well, so ragged tiles need no masks.
+//   CTA = (128 output channels) x (64 input channels) x (one kernel row kh: 3 accumulators of 128 x 64 fp32 in TMEM)
+//         x (one contiguous range of pixel tiles: split-K); warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 =
+//         epilogue (TMEM -> fp32 atomic adds into dW, which the entry point zeroes first).
+// First version: correct and tensor-core fed, not yet tuned (dy is re-read per kernel row and per 64-channel block of
+// the input; L2 -> shared traffic bounds it before the tensor pipe does).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace b200ir {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgTileW = 32, kWgTileH = 4;                 // 128 pixels = K of one stage
+constexpr uint32_t kWgBox = 128 * 128;                     // bytes of one (64 ch x 128 px) box
+constexpr uint32_t kWgStage = 5 * kWgBox;                  // dy: 2 boxes (128 co) | x: 3 boxes (kw = 0, 1, 2)
+constexpr int kWgStages = 2;
+constexpr uint32_t kWgTmemCols = 256;                      // 3 x 64 accumulator columns, rounded to a power of two
+
+struct WgradParams {
+  CUtensorMap tmap_x, tmap_dy;
+  float* dw;
+  int cin, cout;
+  int tiles_x, tiles_y, num_tiles, splits, ci_blocks;
+};
+
+// Shared-memory matrix descriptor of an MN-major operand with the 128-byte swizzle (canonical layout, in 16-byte units:
+// ((8, n), (8, k)) : ((1, LBO), (8, SBO)) -- 64 MN-elements contiguous per K row, 8 K rows per 1024-byte atom, SBO
+// between K atoms, LBO between 64-element MN chunks).
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t wg_smem[];
+  __shared__ __align__(8) uint64_t full_bar[kWgStages], empty_bar[kWgStages], acc_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int u = blockIdx.x;
+  const int split = u % p.splits;
+  u /= p.splits;
+  const int kh = u % 3;
+  u /= 3;
+  const int ci_blk = u % p.ci_blocks;
+  const int co_blk = u / p.ci_blocks;
+  const int t0 = (int)((long long)split * p.num_tiles / p.splits);
+  const int t1 = (int)((long long)(split + 1) * p.num_tiles / p.splits);
+  if (t0 >= t1) return;  // CTA-uniform
+
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_smem) + 1023) & ~(uintptr_t)1023);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmap_x);
+    tma_prefetch_desc(&p.tmap_dy);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, kWgTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      const int per_img = p.tiles_x * p.tiles_y;
+      for (int t = t0; t < t1; ++t) {
+        const int b = t / per_img, r = t - b * per_img;
+        const int y0 = (r / p.tiles_x) * kWgTileH, x0 = (r % p.tiles_x) * kWgTileW;
+        mbar_wait_parked(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = ring + stage * kWgStage;
+        mbar_arrive_expect_tx(&full_bar[stage], kWgStage);
+        tma_load_4d(sa, &p.tmap_dy, &full_bar[stage], co_blk * 128, x0, y0, b);
+        tma_load_4d(sa + kWgBox, &p.tmap_dy, &full_bar[stage], co_blk * 128 + 64, x0, y0, b);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          tma_load_4d(sa + (2 + kw) * kWgBox, &p.tmap_x, &full_bar[stage], ci_blk * 64, x0 + kw - 1, y0 + kh - 1, b);
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      // instruction descriptor: fp16 x fp16 -> fp32, M = 128, N = 64, A and B MN-major (bits 15 / 16)
+      const uint32_t idesc = make_idesc_f16(128, 64, false) | (1u << 15) | (1u << 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + stage * kWgStage);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // 16 pixels (two 1024-byte atoms) per MMA
+            const uint64_t da = make_mnmajor_desc(sa + ks * 2048, kWgBox, 1024);
+            const uint64_t db = make_mnmajor_desc(sa + (2 + kw) * kWgBox + ks * 2048, kWgBox, 1024);
+            umma_f16(tmem_base + kw * 64, da, db, idesc, (t > t0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    // ---------------- epilogue: warp w reads TMEM lanes 32 * (w % 4) ... + 31 = output channels of this block
+    mbar_wait_parked(&acc_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int co = co_blk * 128 + q * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int kw = 0; kw < 3; ++kw) {
+      float* dst = p.dw + ((long long)co * 9 + kh * 3 + kw) * p.cin + ci_blk * 64;
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(trow + kw * 64 + c16 * 16, v);
+        tmem_ld_wait16(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(dst + c16 * 16 + j, __uint_as_float(v[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kWgTmemCols);
+  }
+}
+
+}  // namespace b200ir
+
+using namespace b200ir;
+
+extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int cin, int cout,
+                                 void* stream) {
+  B200IR_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0, "conv_wgrad: bad arguments");
+  B200IR_REQUIRE(cin % 64 == 0 && cout % 128 == 0, "conv_wgrad: cin=%d must be a multiple of 64 and cout=%d of 128", cin,
+                 cout);
+  B200IR_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0,
+                 "conv_wgrad: operands must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int sms = num_sms();
+  if (sms <= 0) return 1;
+  WgradParams p = {};
+  {
+    cuuint32_t box[4] = {64u, (cuuint32_t)kWgTileW, (cuuint32_t)kWgTileH, 1u};
+    cuuint64_t dx[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t sx[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
+    if (encode_map(&p.tmap_x, x, 4, dx, sx, box, CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad(x)")) return 1;
+    cuuint64_t dd[4] = {(cuuint64_t)cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t sd[3] = {(cuuint64_t)cout * 2, (cuuint64_t)W * cout * 2, (cuuint64_t)H * W * cout * 2};
+    if (encode_map(&p.tmap_dy, dy, 4, dd, sd, box, CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad(dy)")) return 1;
+  }
+  p.dw = dw;
+  p.cin = cin;
+  p.cout = cout;
+  p.tiles_x = (W + kWgTileW - 1) / kWgTileW;
+  p.tiles_y = (H + kWgTileH - 1) / kWgTileH;
+  p.num_tiles = B * p.tiles_x * p.tiles_y;
+  p.ci_blocks = cin / 64;
+  const int units = (cout / 128) * p.ci_blocks * 3;
+  int splits = (2 * sms + units - 1) / units;
+  if (splits > p.num_tiles) splits = p.num_tiles;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  if (cudaMemsetAsync(dw, 0, (size_t)cout * 9 * cin * sizeof(float), st) != cudaSuccess) {
+    set_error("conv_wgrad: cudaMemsetAsync failed");
+    return 1;
+  }
+  const int smem = kWgStages * kWgStage + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("conv_wgrad: cudaFuncSetAttribute failed");
+      return 1;
+    }
+    configured = true;
+  }
+  conv_wgrad_kernel<<<units * splits, kWgThreads, smem, st>>>(p);
+  return check_launch("conv_wgrad");
+}

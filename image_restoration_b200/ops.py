@@ -503,3 +503,15 @@ def style_mlp(z, w, bias, out, lr_mul):
 def nhwc_to_nchw_f32(x, out):
     b, h, w, c = x.shape
     check(_lib.lib().b200ir_nhwc_to_nchw_f32(_ptr(x), _ptr(out), b, h * w, c, _stream()), 'nhwc_to_nchw_f32')
+
+
+def conv_wgrad(x, dy, dw=None):
+    """Weight gradient of the 3x3 stride-1 'same' conv: x NHWC fp16 [B,H,W,Cin], dy NHWC fp16 [B,H,W,Cout] ->
+    dw fp32 [Cout, 9, Cin] (tap-major like the packed forward weights).  Backward of F.conv2d(x, W, padding=1) w.r.t. W."""
+    b, h, w, cin = x.shape
+    cout = dy.shape[3]
+    assert tuple(dy.shape[:3]) == (b, h, w) and x.dtype == torch.float16 and dy.dtype == torch.float16
+    if dw is None:
+        dw = torch.empty(cout, 9, cin, device=x.device, dtype=torch.float32)
+    check(_lib.lib().b200ir_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), b, h, w, cin, cout, _stream()), 'conv_wgrad')
+    return dw

@@ -153,6 +153,13 @@ int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
 int b200ir_first_conv(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int cout,
                       void* stream);
 
+/* Weight gradient of a 3x3 stride-1 'same' convolution (F.conv2d(x, W, padding=1), the EqualConv2d / ConvUpLayer convs:
+ * stylegan2_ocr_arch.py:639-648, gfpganv1_ocr_arch.py:192): dW[co][kh][kw][ci] = sum_{b,y,x} dy[b][y][x][co] *
+ * x[b][y+kh-1][x+kw-1][ci].  x NHWC fp16 [B][H][W][cin], dy NHWC fp16 [B][H][W][cout], dw fp32 [cout][9][cin] (the
+ * layout of the packed forward weights; the equalised-lr scale is the caller's), overwritten.  cin % 64 == 0,
+ * cout % 128 == 0.  tcgen05 GEMM over pixels with MN-major operands, split over pixel ranges, fp32 atomic reduction. */
+int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int cin, int cout, void* stream);
+
 /* One torch.optim.Adam step (no amsgrad; optimizer_g / optimizer_d of basicsr/models/gfpgan_model.py:217-248) over a flat
  * fp32 parameter buffer, fused with the gradient scaling of the data-parallel average (grad_scale = 1 / world) and,
  * when ema != NULL, with the EMA update of BaseModel.model_ema (basicsr/models/base_model.py:50-57):
