@@ -7,11 +7,15 @@
 // (rows = K = pixels, the 64 contiguous channels = M resp. N): no transposed copy of the activations exists anywhere.
 // Zero padding of the conv = TMA out-of-bounds fill of the shifted x box; pixels outside the image contribute zeros on
 // the dy side as well, so ragged tiles need no masks.
-//   CTA = (128 output channels) x (64 input channels) x (one kernel row kh: 3 accumulators of 128 x 64 fp32 in TMEM)
-//         x (one contiguous range of pixel tiles: split-K); warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 =
-//         epilogue (TMEM -> fp32 atomic adds into dW, which the entry point zeroes first).
-// First version: correct and tensor-core fed, not yet tuned (dy is re-read per kernel row and per 64-channel block of
-// the input; L2 -> shared traffic bounds it before the tensor pipe does).
+//   CTA = (128 output channels) x (128 or 64 input channels) x (one kernel row kh: 3 accumulators of 128 x N fp32 in
+//         TMEM) x (one contiguous range of pixel tiles: split-K); warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5
+//         = epilogue (TMEM -> fp32 atomic adds into dW, which the entry point zeroes first).
+// The x tile carries a one-pixel halo left and right (box 34 x 4 pixels) and is loaded ONCE per stage: the three kw taps
+// read it through descriptors whose start address is shifted by kw pixel rows of 128 bytes (the K dimension of an
+// MN-major operand is linear in shared memory: 128 bytes per pixel, 8-pixel atoms 1024 bytes apart; the swizzle XOR uses
+// absolute address bits, so unaligned starts work with the base-offset field at 0, as in the forward row kernel).
+// MMAs are issued per image row of the tile (32 pixels = two K = 16 steps) because dy (pitch 32) and x (pitch 34) only
+// share the pixel order inside a row.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -19,10 +23,15 @@ namespace b200ir {
 
 constexpr int kWgThreads = 192;
 constexpr int kWgTileW = 32, kWgTileH = 4;                 // 128 pixels = K of one stage
-constexpr uint32_t kWgBox = 128 * 128;                     // bytes of one (64 ch x 128 px) box
-constexpr uint32_t kWgStage = 5 * kWgBox;                  // dy: 2 boxes (128 co) | x: 3 boxes (kw = 0, 1, 2)
-constexpr int kWgStages = 2;
-constexpr uint32_t kWgTmemCols = 256;                      // 3 x 64 accumulator columns, rounded to a power of two
+constexpr uint32_t kWgBoxDy = 128 * 128;                   // bytes of one dy box (64 ch x 32 x 4 px)
+constexpr uint32_t kWgBoxX = (kWgTileW + 2) * kWgTileH * 128;  // x box with halo (64 ch x 34 x 4 px) = 17 KB
+constexpr uint32_t kWgTmemCols = 512;                      // 3 accumulators of up to 128 columns, power of two
+
+template <int kNC>  // 64-channel chunks of the input-channel block: N = 64 * kNC
+struct WgCfg {
+  static constexpr uint32_t kStage = 2 * kWgBoxDy + kNC * kWgBoxX;  // dy: 2 boxes (128 co) | x: kNC boxes
+  static constexpr int kStages = kNC == 2 ? 3 : 4;
+};
 
 struct WgradParams {
   CUtensorMap tmap_x, tmap_dy;
@@ -44,9 +53,12 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
   return d;
 }
 
+template <int kNC>
 __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  constexpr uint32_t kWgStage = WgCfg<kNC>::kStage;
+  constexpr int kWgStages = WgCfg<kNC>::kStages;
   extern __shared__ __align__(1024) uint8_t wg_smem[];
-  __shared__ __align__(8) uint64_t full_bar[kWgStages], empty_bar[kWgStages], acc_bar;
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], acc_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -93,10 +105,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
         uint8_t* sa = ring + stage * kWgStage;
         mbar_arrive_expect_tx(&full_bar[stage], kWgStage);
         tma_load_4d(sa, &p.tmap_dy, &full_bar[stage], co_blk * 128, x0, y0, b);
-        tma_load_4d(sa + kWgBox, &p.tmap_dy, &full_bar[stage], co_blk * 128 + 64, x0, y0, b);
+        tma_load_4d(sa + kWgBoxDy, &p.tmap_dy, &full_bar[stage], co_blk * 128 + 64, x0, y0, b);
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          tma_load_4d(sa + (2 + kw) * kWgBox, &p.tmap_x, &full_bar[stage], ci_blk * 64, x0 + kw - 1, y0 + kh - 1, b);
+        for (int c = 0; c < kNC; ++c)
+          tma_load_4d(sa + 2 * kWgBoxDy + c * kWgBoxX, &p.tmap_x, &full_bar[stage], (ci_blk * kNC + c) * 64, x0 - 1,
+                      y0 + kh - 1, b);
         if (++stage == kWgStages) {
           stage = 0;
           phase ^= 1u;
@@ -105,21 +118,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer
-      // instruction descriptor: fp16 x fp16 -> fp32, M = 128, N = 64, A and B MN-major (bits 15 / 16)
-      const uint32_t idesc = make_idesc_f16(128, 64, false) | (1u << 15) | (1u << 16);
+      // instruction descriptor: fp16 x fp16 -> fp32, M = 128, N = 64 * kNC, A and B MN-major (bits 15 / 16)
+      const uint32_t idesc = make_idesc_f16(128, 64 * kNC, false) | (1u << 15) | (1u << 16);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + stage * kWgStage);
+        const uint32_t sx = sa + 2 * kWgBoxDy;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {  // 16 pixels (two 1024-byte atoms) per MMA
-            const uint64_t da = make_mnmajor_desc(sa + ks * 2048, kWgBox, 1024);
-            const uint64_t db = make_mnmajor_desc(sa + (2 + kw) * kWgBox + ks * 2048, kWgBox, 1024);
-            umma_f16(tmem_base + kw * 64, da, db, idesc, (t > t0 || ks > 0) ? 1u : 0u);
+          for (int h = 0; h < kWgTileH; ++h) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {  // 16 pixels of image row h per MMA; x shifted by kw pixels inside its halo
+              const uint64_t da = make_mnmajor_desc(sa + (h * kWgTileW + ks * 16) * 128, kWgBoxDy, 1024);
+              const uint64_t db = make_mnmajor_desc(sx + (h * (kWgTileW + 2) + kw + ks * 16) * 128, kWgBoxX, 1024);
+              umma_f16(tmem_base + kw * (64 * kNC), da, db, idesc, (t > t0 || h > 0 || ks > 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -138,11 +155,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     const int co = co_blk * 128 + q * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     for (int kw = 0; kw < 3; ++kw) {
-      float* dst = p.dw + ((long long)co * 9 + kh * 3 + kw) * p.cin + ci_blk * 64;
+      float* dst = p.dw + ((long long)co * 9 + kh * 3 + kw) * p.cin + ci_blk * (64 * kNC);
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {
+      for (int c16 = 0; c16 < 4 * kNC; ++c16) {
         uint32_t v[16];
-        tmem_ld16(trow + kw * 64 + c16 * 16, v);
+        tmem_ld16(trow + kw * (64 * kNC) + c16 * 16, v);
         tmem_ld_wait16(v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) atomicAdd(dst + c16 * 16 + j, __uint_as_float(v[j]));
@@ -174,9 +191,10 @@ extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B
   WgradParams p = {};
   {
     cuuint32_t box[4] = {64u, (cuuint32_t)kWgTileW, (cuuint32_t)kWgTileH, 1u};
+    cuuint32_t box_x[4] = {64u, (cuuint32_t)kWgTileW + 2u, (cuuint32_t)kWgTileH, 1u};
     cuuint64_t dx[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t sx[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
-    if (encode_map(&p.tmap_x, x, 4, dx, sx, box, CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad(x)")) return 1;
+    if (encode_map(&p.tmap_x, x, 4, dx, sx, box_x, CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad(x)")) return 1;
     cuuint64_t dd[4] = {(cuuint64_t)cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t sd[3] = {(cuuint64_t)cout * 2, (cuuint64_t)W * cout * 2, (cuuint64_t)H * W * cout * 2};
     if (encode_map(&p.tmap_dy, dy, 4, dd, sd, box, CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad(dy)")) return 1;
@@ -187,7 +205,8 @@ extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B
   p.tiles_x = (W + kWgTileW - 1) / kWgTileW;
   p.tiles_y = (H + kWgTileH - 1) / kWgTileH;
   p.num_tiles = B * p.tiles_x * p.tiles_y;
-  p.ci_blocks = cin / 64;
+  const int nc = (cin % 128 == 0) ? 2 : 1;   // input-channel block of 128 (N = 128 MMAs) whenever cin allows it
+  p.ci_blocks = cin / (64 * nc);
   const int units = (cout / 128) * p.ci_blocks * 3;
   int splits = (2 * sms + units - 1) / units;
   if (splits > p.num_tiles) splits = p.num_tiles;
@@ -197,15 +216,18 @@ extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B
     set_error("conv_wgrad: cudaMemsetAsync failed");
     return 1;
   }
-  const int smem = kWgStages * kWgStage + 1024;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+  auto launch = [&](auto kernel, int smem) -> int {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       set_error("conv_wgrad: cudaFuncSetAttribute failed");
       return 1;
     }
-    configured = true;
+    kernel<<<units * splits, kWgThreads, smem, st>>>(p);
+    return 0;
+  };
+  if (nc == 2) {
+    if (launch(conv_wgrad_kernel<2>, WgCfg<2>::kStages * WgCfg<2>::kStage + 1024)) return 1;
+  } else {
+    if (launch(conv_wgrad_kernel<1>, WgCfg<1>::kStages * WgCfg<1>::kStage + 1024)) return 1;
   }
-  conv_wgrad_kernel<<<units * splits, kWgThreads, smem, st>>>(p);
   return check_launch("conv_wgrad");
 }
