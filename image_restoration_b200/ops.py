@@ -515,3 +515,31 @@ def conv_wgrad(x, dy, dw=None):
         dw = torch.empty(cout, 9, cin, device=x.device, dtype=torch.float32)
     check(_lib.lib().b200ir_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), b, h, w, cin, cout, _stream()), 'conv_wgrad')
     return dw
+
+
+def conv_dgrad_weight(weight, cin):
+    """Packed forward weights [Cout, 9*Cin] (tap-major, fp16) -> the packed weights of the input-gradient conv
+    [Cin, 9*Cout]: dx = conv_same(dz, Wt) with Wt[ci][kh][kw][co] = W[co][2-kh][2-kw][ci] (the 3x3 stride-1 'same' conv
+    is its own adjoint up to this flip / transpose, so dgrad runs on b200ir_conv_igemm)."""
+    cout = weight.shape[0]
+    assert weight.shape == (cout, 9 * cin)
+    return weight.view(cout, 3, 3, cin).flip(1, 2).permute(3, 1, 2, 0).reshape(cin, 9 * cout).contiguous()
+
+
+def conv_dgrad(dz, weight_t, dx, **kw):
+    """Input gradient of F.conv2d(x, W, padding=1): dz NHWC fp16 [B,H,W,Cout], weight_t from conv_dgrad_weight ->
+    dx NHWC fp16 [B,H,W,Cin].  Returns the prepared ConvOp (call it to launch)."""
+    return conv_same(dz, weight_t, dx, 3, **kw)
+
+
+def lrelu_bias_bwd(dy, y, dz=None, dbias=None, slope=0.2, scale=2 ** 0.5, want_bias=True):
+    """Backward of FusedLeakyReLU + bias gradient (b200ir_lrelu_bias_bwd): dy, y NHWC fp16 [..., C] -> (dz, dbias)."""
+    assert dy.shape == y.shape and dy.dtype == torch.float16 and y.dtype == torch.float16
+    c = dy.shape[-1]
+    if dz is None:
+        dz = torch.empty_like(dy)
+    if dbias is None and want_bias:
+        dbias = torch.empty(c, device=dy.device, dtype=torch.float32)
+    check(_lib.lib().b200ir_lrelu_bias_bwd(_ptr(dy), _ptr(y), _ptr(dz), _ptr(dbias) if dbias is not None else None,
+                                           dy.numel() // c, c, slope, scale, _stream()), 'lrelu_bias_bwd')
+    return dz, dbias

@@ -160,6 +160,14 @@ int b200ir_first_conv(const float* x, const float* w, const float* bias, void* o
  * cout % 128 == 0.  tcgen05 GEMM over pixels with MN-major operands, split over pixel ranges, fp32 atomic reduction. */
 int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int cin, int cout, void* stream);
 
+/* Backward of FusedLeakyReLU fused with the bias gradient (basicsr/ops/fused_act/fused_act.py:30-63; device code
+ * fused_bias_act_kernel.cu:20-50 with act = 3, grad = 1, and the grad_input.sum over batch and pixels of
+ * FusedLeakyReLUFunctionBackward.forward):  dz = dy * scale * (y > 0 ? 1 : slope),  dbias[c] = sum_p dz[p][c].
+ * dy, y (the saved forward output, the reference's `out`), dz: NHWC fp16 [n_pix][C]; dbias fp32 [C], overwritten, may be
+ * NULL (ScaledLeakyReLU, stylegan2_ocr_arch.py:604-606).  C = 8 * a divisor of 256.  dz may alias dy. */
+int b200ir_lrelu_bias_bwd(const void* dy, const void* y, void* dz, float* dbias, int64_t n_pix, int C, float slope,
+                          float scale, void* stream);
+
 /* One torch.optim.Adam step (no amsgrad; optimizer_g / optimizer_d of basicsr/models/gfpgan_model.py:217-248) over a flat
  * fp32 parameter buffer, fused with the gradient scaling of the data-parallel average (grad_scale = 1 / world) and,
  * when ema != NULL, with the EMA update of BaseModel.model_ema (basicsr/models/base_model.py:50-57):
