@@ -67,6 +67,62 @@ __global__ void first_conv_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// Same arithmetic, output staged through shared memory for cout = 16 / 32 / 64: each thread parks the 2 * cout bytes of
+// its pixel as 16-byte chunks (chunk index XOR-swizzled so that the eight threads of a quarter warp hit eight different
+// bank groups), then the CTA writes its 256 pixels as one contiguous run of 16-byte chunks: full 128-byte lines per
+// warp store instead of 32 partial lines.  Four rounds of 256 pixels per CTA with all input loads issued up front.
+constexpr int kFcPix = 4;  // pixels per thread (rounds of 256 pixels per CTA)
+__global__ void __launch_bounds__(kPwThreads) first_conv_staged_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                       const float* __restrict__ bias, __half* __restrict__ out,
+                                                                       long long n_pix, int HW, int cout) {
+  extern __shared__ __align__(16) uint8_t fc_smem[];
+  uint4* stage = reinterpret_cast<uint4*>(fc_smem);                       // [256 pixels][cout / 8] chunks
+  float* sw = reinterpret_cast<float*>(fc_smem + kPwThreads * cout * 2);  // [cout*3] weights, [cout] bias
+  for (int i = threadIdx.x; i < cout * 3; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * 3 + i] = bias[i];
+  __syncthreads();
+  const int cpp = cout >> 3;                                              // chunks per pixel: 2, 4 or 8
+  const int t = threadIdx.x;
+  const int swz = (t / (8 / cpp)) & (cpp - 1);
+  const long long base0 = (long long)blockIdx.x * (kPwThreads * kFcPix);
+  float r[kFcPix], g[kFcPix], bl[kFcPix];
+#pragma unroll
+  for (int k = 0; k < kFcPix; ++k) {                                      // all 3 * kFcPix loads in flight before any use
+    const long long idx = base0 + k * kPwThreads + t;
+    r[k] = g[k] = bl[k] = 0.f;
+    if (idx < n_pix) {
+      const float* xp = x + (idx / HW) * 3 * HW + (idx % HW);
+      r[k] = __ldg(xp), g[k] = __ldg(xp + HW), bl[k] = __ldg(xp + 2 * HW);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kFcPix; ++k) {
+    const long long base = base0 + k * kPwThreads;
+    if (base >= n_pix) break;
+    if (k) __syncthreads();                                               // previous round's copy-out done
+    for (int j = 0; j < cpp; ++j) {
+      uint4 q;
+      __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float* wc = sw + (j * 8 + 2 * c) * 3;
+        const float* bc = sw + cout * 3 + j * 8 + 2 * c;
+        h[c] = f2h2_sat(lrelu_s(wc[0] * r[k] + wc[1] * g[k] + wc[2] * bl[k] + bc[0]),
+                        lrelu_s(wc[3] * r[k] + wc[4] * g[k] + wc[5] * bl[k] + bc[1]));
+      }
+      stage[t * cpp + (j ^ swz)] = q;
+    }
+    __syncthreads();
+    const long long rem = n_pix - base;
+    const int chunks = (int)(rem < kPwThreads ? rem : kPwThreads) * cpp;
+    uint4* dst = reinterpret_cast<uint4*>(out) + base * cpp;
+    for (int q = t; q < chunks; q += kPwThreads) {
+      const int px = q / cpp, j = q & (cpp - 1);
+      __stcs(dst + q, stage[px * cpp + (j ^ ((px / (8 / cpp)) & (cpp - 1)))]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ optimiser step
 // torch.optim.Adam (no amsgrad, the optimizer_g / optimizer_d of gfpgan_model.py:217-248, betas (0, 0.99)) over one flat
 // fp32 buffer: four elements per thread, 16-byte accesses; grad_scale folds the all-reduce average (1 / world) in.
@@ -892,6 +948,11 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
   B200IR_REQUIRE(x && w && bias && out, "first_conv: null pointer");
   B200IR_REQUIRE(cout % 8 == 0 && cout <= 512, "first_conv: cout=%d", cout);
   const long long n = (long long)B * H * W;
+  if (cout == 16 || cout == 32 || cout == 64) {
+    const size_t smem = (size_t)kPwThreads * cout * 2 + cout * 4 * sizeof(float);  // <= 33 KB
+    first_conv_staged_kernel<<<grid_for((n + kFcPix - 1) / kFcPix), kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
+    return check_launch("first_conv");
+  }
   first_conv_kernel<<<grid_for(n), kPwThreads, cout * 4 * sizeof(float), STREAM>>>(x, w, bias, (__half*)out, B, H * W,
                                                                                   cout);
   return check_launch("first_conv");
