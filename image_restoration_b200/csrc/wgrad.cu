@@ -38,6 +38,9 @@ struct WgradParams {
   float* dw;
   int cin, cout;
   int tiles_x, tiles_y, num_tiles, splits, ci_blocks;
+  uint32_t tap_mask;   // bit kh * 3 + kw: taps to compute (the others stay zero)
+  int num_kh;          // kernel rows with at least one tap in the mask
+  int kh_list[3];
 };
 
 // Shared-memory matrix descriptor of an MN-major operand with the 128-byte swizzle (canonical layout, in 16-byte units:
@@ -65,8 +68,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   int u = blockIdx.x;
   const int split = u % p.splits;
   u /= p.splits;
-  const int kh = u % 3;
-  u /= 3;
+  const int kh = p.kh_list[u % p.num_kh];
+  u /= p.num_kh;
+  const uint32_t kw_mask = (p.tap_mask >> (kh * 3)) & 7u;
   const int ci_blk = u % p.ci_blocks;
   const int co_blk = u / p.ci_blocks;
   const int t0 = (int)((long long)split * p.num_tiles / p.splits);
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
         const uint32_t sx = sa + 2 * kWgBoxDy;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
+          if (!((kw_mask >> kw) & 1u)) continue;
 #pragma unroll
           for (int h = 0; h < kWgTileH; ++h) {
 #pragma unroll
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     const int co = co_blk * 128 + q * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     for (int kw = 0; kw < 3; ++kw) {
+      if (!((kw_mask >> kw) & 1u)) continue;
       float* dst = p.dw + ((long long)co * 9 + kh * 3 + kw) * p.cin + ci_blk * (64 * kNC);
 #pragma unroll
       for (int c16 = 0; c16 < 4 * kNC; ++c16) {
@@ -178,13 +184,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
 
 using namespace b200ir;
 
-extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int cin, int cout,
-                                 void* stream) {
-  B200IR_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0, "conv_wgrad: bad arguments");
+extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, float* dw, int B, int H, int W, int cout,
+                                      uint32_t tap_mask, void* stream) {
+  B200IR_REQUIRE(xv && xv->ptr && dy && dw && B > 0 && H > 0 && W > 0 && xv->b == B, "conv_wgrad: bad arguments");
+  const int cin = xv->c;
+  tap_mask &= 0x1FFu;
+  B200IR_REQUIRE(tap_mask != 0, "conv_wgrad: empty tap mask");
   B200IR_REQUIRE(cin % 64 == 0 && cout % 128 == 0, "conv_wgrad: cin=%d must be a multiple of 64 and cout=%d of 128", cin,
                  cout);
-  B200IR_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0,
-                 "conv_wgrad: operands must be 16-byte aligned");
+  B200IR_REQUIRE(((reinterpret_cast<uintptr_t>(xv->ptr) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0 &&
+                     xv->stride_w % 8 == 0 && xv->stride_h % 8 == 0 && xv->stride_b % 8 == 0,
+                 "conv_wgrad: operands must be 16-byte aligned, view strides multiples of 8 elements");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = num_sms();
   if (sms <= 0) return 1;
@@ -192,9 +202,9 @@ extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B
   {
     cuuint32_t box[4] = {64u, (cuuint32_t)kWgTileW, (cuuint32_t)kWgTileH, 1u};
     cuuint32_t box_x[4] = {64u, (cuuint32_t)kWgTileW + 2u, (cuuint32_t)kWgTileH, 1u};
-    cuuint64_t dx[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t sx[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
-    if (encode_map(&p.tmap_x, x, 4, dx, sx, box_x, CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad(x)")) return 1;
+    cuuint64_t dx[4] = {(cuuint64_t)cin, (cuuint64_t)xv->w, (cuuint64_t)xv->h, (cuuint64_t)B};
+    cuuint64_t sx[3] = {(cuuint64_t)xv->stride_w * 2, (cuuint64_t)xv->stride_h * 2, (cuuint64_t)xv->stride_b * 2};
+    if (encode_map(&p.tmap_x, xv->ptr, 4, dx, sx, box_x, CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad(x)")) return 1;
     cuuint64_t dd[4] = {(cuuint64_t)cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t sd[3] = {(cuuint64_t)cout * 2, (cuuint64_t)W * cout * 2, (cuuint64_t)H * W * cout * 2};
     if (encode_map(&p.tmap_dy, dy, 4, dd, sd, box, CU_TENSOR_MAP_SWIZZLE_128B, "conv_wgrad(dy)")) return 1;
@@ -202,12 +212,15 @@ extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B
   p.dw = dw;
   p.cin = cin;
   p.cout = cout;
+  p.tap_mask = tap_mask;
+  for (int kh = 0; kh < 3; ++kh)
+    if ((tap_mask >> (kh * 3)) & 7u) p.kh_list[p.num_kh++] = kh;
   p.tiles_x = (W + kWgTileW - 1) / kWgTileW;
   p.tiles_y = (H + kWgTileH - 1) / kWgTileH;
   p.num_tiles = B * p.tiles_x * p.tiles_y;
   const int nc = (cin % 128 == 0) ? 2 : 1;   // input-channel block of 128 (N = 128 MMAs) whenever cin allows it
   p.ci_blocks = cin / (64 * nc);
-  const int units = (cout / 128) * p.ci_blocks * 3;
+  const int units = (cout / 128) * p.ci_blocks * p.num_kh;
   int splits = (2 * sms + units - 1) / units;
   if (splits > p.num_tiles) splits = p.num_tiles;
   if (splits < 1) splits = 1;
@@ -230,4 +243,14 @@ extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B
     if (launch(conv_wgrad_kernel<1>, WgCfg<1>::kStages * WgCfg<1>::kStage + 1024)) return 1;
   }
   return check_launch("conv_wgrad");
+}
+
+extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int cin, int cout,
+                                 void* stream) {
+  B200IR_REQUIRE(x && B > 0 && H > 0 && W > 0 && cin > 0, "conv_wgrad: bad arguments");
+  b200ir_view v = {};
+  v.ptr = x;
+  v.c = cin, v.w = W, v.h = H, v.b = B;
+  v.stride_w = cin, v.stride_h = (int64_t)W * cin, v.stride_b = (int64_t)H * W * cin;
+  return b200ir_conv_wgrad_view(&v, dy, dw, B, H, W, cout, 0x1FFu, stream);
 }

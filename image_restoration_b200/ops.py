@@ -543,3 +543,42 @@ def lrelu_bias_bwd(dy, y, dz=None, dbias=None, slope=0.2, scale=2 ** 0.5, want_b
     check(_lib.lib().b200ir_lrelu_bias_bwd(_ptr(dy), _ptr(y), _ptr(dz), _ptr(dbias) if dbias is not None else None,
                                            dy.numel() // c, c, slope, scale, _stream()), 'lrelu_bias_bwd')
     return dz, dbias
+
+
+def conv_wgrad_view(view, dy, dw=None, tap_mask=0x1FF):
+    """b200ir_conv_wgrad_view: weight gradient over a strided view of x and a subset of the nine taps (see
+    include/b200ir.h).  dy NHWC fp16 [B,H,W,Cout] -> dw fp32 [Cout, 9, Cin] (taps outside the mask are zero)."""
+    b, h, w, cout = dy.shape
+    assert dy.dtype == torch.float16 and dy.is_contiguous()
+    if dw is None:
+        dw = torch.empty(cout, 9, view.c, device=dy.device, dtype=torch.float32)
+    check(_lib.lib().b200ir_conv_wgrad_view(C.byref(view), _ptr(dy), _ptr(dw), b, h, w, cout, tap_mask, _stream()),
+          'conv_wgrad_view')
+    return dw
+
+
+def conv1x1_wgrad(x, dy):
+    """Weight gradient of a 1x1 conv (EqualConv2d k = 1): x NHWC fp16 [B,H,W,Cin], dy [B,H,W,Cout] -> fp32 [Cout, Cin]."""
+    assert x.dtype == torch.float16 and x.is_contiguous() and tuple(x.shape[:3]) == tuple(dy.shape[:3])
+    return conv_wgrad_view(nhwc_view(x), dy, tap_mask=1 << 4)[:, 4, :]
+
+
+def conv3x3_s2_wgrad(p, h, w, dy):
+    """Weight gradient of conv3x3_s2 (the stride-2 conv of ResBlock.conv2 over the FIR-smoothed buffer p [B,H+2,W+2,C]):
+    dy [B,H/2,W/2,Cout] -> fp32 [Cout, 9, C].  One masked launch per pixel phase of p; kernel element (2 sy + ry, 2 sx + rx)
+    is tap (sy + 1, sx + 1) of the launch over phase (ry, rx)."""
+    b, hp, wp, c = p.shape
+    assert hp == h + 2 and wp == w + 2 and h % 2 == 0 and w % 2 == 0 and p.dtype == torch.float16 and p.is_contiguous()
+    cout = dy.shape[3]
+    assert tuple(dy.shape[:3]) == (b, h // 2, w // 2)
+    dw = torch.empty(cout, 3, 3, c, device=p.device, dtype=torch.float32)
+    for ry in range(2):
+        for rx in range(2):
+            view = View(p.data_ptr() + 2 * (ry * wp + rx) * c, c, wp // 2, hp // 2, b, 2 * c, 2 * wp * c, hp * wp * c)
+            sys_, sxs = ((0, 1) if ry == 0 else (0,)), ((0, 1) if rx == 0 else (0,))
+            mask = sum(1 << ((sy + 1) * 3 + sx + 1) for sy in sys_ for sx in sxs)
+            part = conv_wgrad_view(view, dy, tap_mask=mask).view(cout, 3, 3, c)
+            for sy in sys_:
+                for sx in sxs:
+                    dw[:, 2 * sy + ry, 2 * sx + rx] = part[:, sy + 1, sx + 1]
+    return dw.view(cout, 9, c)

@@ -160,6 +160,17 @@ int b200ir_first_conv(const float* x, const float* w, const float* bias, void* o
  * cout % 128 == 0.  tcgen05 GEMM over pixels with MN-major operands, split over pixel ranges, fp32 atomic reduction. */
 int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int cin, int cout, void* stream);
 
+/* The same kernel over a strided view of x and a subset of the nine taps:
+ *   dW[co][kh][kw][ci] = sum_{b,y,x} dy[b][y][x][co] * xv[b][y+kh-1][x+kw-1][ci]   for the taps with bit kh*3+kw of tap_mask
+ * set (zero outside the view's extent, which may differ from H x W; taps outside the mask are left zero).  This covers
+ *   - 1x1 convs (EqualConv2d k = 1: ResBlock / ResUpBlock skips, condition heads):  tap_mask = 1 << 4;
+ *   - the stride-2 3x3 convs of ResBlock.conv2 (stylegan2_ocr_arch.py:685-697, F.conv2d(stride=2) over the FIR-smoothed
+ *     buffer p): one call per pixel phase (ry, rx) of p, the view's strides stepping two pixels / two rows from
+ *     p + (ry * row + rx) * cin; kernel element (2*sy + ry, 2*sx + rx) of the conv comes back at tap (sy + 1, sx + 1).
+ * xv->c = cin (multiple of 64), xv->b = B, cout % 128 == 0. */
+int b200ir_conv_wgrad_view(const b200ir_view* x, const void* dy, float* dw, int B, int H, int W, int cout,
+                           uint32_t tap_mask, void* stream);
+
 /* Backward of FusedLeakyReLU fused with the bias gradient (basicsr/ops/fused_act/fused_act.py:30-63; device code
  * fused_bias_act_kernel.cu:20-50 with act = 3, grad = 1, and the grad_input.sum over batch and pixels of
  * FusedLeakyReLUFunctionBackward.forward):  dz = dy * scale * (y > 0 ? 1 : slope),  dbias[c] = sum_p dz[p][c].

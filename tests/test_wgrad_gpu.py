@@ -31,3 +31,34 @@ def test_wgrad_rejects_unsupported_channels():
     dy = torch.zeros(1, 8, 8, 128, device='cuda', dtype=torch.float16)
     with pytest.raises(RuntimeError):
         ops.conv_wgrad(x, dy)
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout', [(2, 8, 32, 64, 128), (3, 16, 48, 256, 256), (1, 5, 37, 128, 128)])
+def test_wgrad_1x1(B, H, W, cin, cout):
+    from image_restoration_b200 import ops
+    torch.manual_seed(B + W)
+    x = torch.randn(B, cin, H, W, device='cuda').half()
+    dy = torch.randn(B, cout, H, W, device='cuda').half()
+    ref = torch.nn.grad.conv2d_weight(x.float(), (cout, cin, 1, 1), dy.float())[:, :, 0, 0]
+    got = ops.conv1x1_wgrad(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous())
+    torch.cuda.synchronize()
+    err, scale = (got - ref).abs().max().item(), ref.abs().max().item()
+    print(f'wgrad 1x1 B{B} {H}x{W} {cin}->{cout}: max err {err:.3e} of {scale:.3e}')
+    assert err <= 1e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout', [(2, 8, 32, 64, 128), (2, 32, 96, 64, 256), (3, 16, 48, 256, 256), (1, 6, 70, 128, 128)])
+def test_wgrad_3x3_stride2(B, H, W, cin, cout):
+    """ResBlock.conv2: F.conv2d(p, W, stride=2) over the (H+1)x(W+1) FIR output held in a [B,H+2,W+2,C] buffer."""
+    from image_restoration_b200 import ops
+    torch.manual_seed(B + W + 1)
+    p = torch.randn(B, H + 2, W + 2, cin, device='cuda').half()          # padding row / column holds garbage on purpose
+    dy = torch.randn(B, cout, H // 2, W // 2, device='cuda').half()
+    valid = p[:, :H + 1, :W + 1].permute(0, 3, 1, 2).float()
+    ref = torch.nn.grad.conv2d_weight(valid, (cout, cin, 3, 3), dy.float(), stride=2)
+    ref = ref.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    got = ops.conv3x3_s2_wgrad(p, H, W, dy.permute(0, 2, 3, 1).contiguous())
+    torch.cuda.synchronize()
+    err, scale = (got - ref).abs().max().item(), ref.abs().max().item()
+    print(f'wgrad 3x3 s2 B{B} {H}x{W} {cin}->{cout}: max err {err:.3e} of {scale:.3e}')
+    assert err <= 1e-3 * scale, (err, scale)
