@@ -16,6 +16,8 @@
 // absolute address bits, so unaligned starts work with the base-offset field at 0, as in the forward row kernel).
 // MMAs are issued per image row of the tile (32 pixels = two K = 16 steps) because dy (pitch 32) and x (pitch 34) only
 // share the pixel order inside a row.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -221,7 +223,12 @@ extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, flo
   const int nc = (cin % 128 == 0) ? 2 : 1;   // input-channel block of 128 (N = 128 MMAs) whenever cin allows it
   p.ci_blocks = cin / (64 * nc);
   const int units = (cout / 128) * p.ci_blocks * p.num_kh;
-  int splits = (2 * sms + units - 1) / units;
+  // One wave of CTAs (one per SM: the ring takes the whole shared memory) and at least ~16 pixel tiles per CTA, so that
+  // the fixed cost of a CTA -- 128 x N x 3 fp32 atomics into dW -- stays below its MMA time (measured sweep:
+  // tools/sweep_wgrad.py; two waves were 20-45 % slower on every layer of the B = 64 step).
+  int splits = sms / units;
+  if (splits > p.num_tiles / 16) splits = p.num_tiles / 16;
+  if (const char* e = getenv("B200IR_WGRAD_SPLITS")) splits = atoi(e);  // tuning switch (tools/time_wgrad.py sweeps it)
   if (splits > p.num_tiles) splits = p.num_tiles;
   if (splits < 1) splits = 1;
   p.splits = splits;
