@@ -74,6 +74,8 @@ SIGNATURES = {
     'b200ir_conv_wgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_conv_wgrad_view': [C.POINTER(View), _P, _P, _I, _I, _I, _I, C.c_uint32, _P],
     'b200ir_lrelu_bias_bwd': [_P, _P, _P, _P, _L, _I, _F, _F, _P],
+    'b200ir_fir_pad11': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'b200ir_fir_down2_adjoint': [_P, _P, _P, _I, _I, _I, _I, _P],
     'b200ir_adam_step': [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _F, _P],
     'b200ir_minibatch_stddev': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_f32_to_input': [_P, _P, _I, _I, _I, _I, _P],

@@ -51,6 +51,69 @@ __global__ void __launch_bounds__(kBwThreads) lrelu_bias_bwd_kernel(const uint4*
   }
 }
 
+// Adjoint of fir_down2 (upfirdn2d(x, k, pad = (1, 1)) sampled at the even positions: the FIR + stride-2 front of the 1x1
+// skip conv of ResBlock, stylegan2_ocr_arch.py:685-697 with kernel_size = 1): zero-stuffing x2 followed by the same 4-tap
+// FIR, i.e. upfirdn2d(d, k, up = 2, pad = (2, 1)) without UpFirDnUpsample's gain of 4.  Per axis
+//   out[2i] = (3 d[i] + d[i-1]) / 8,   out[2i+1] = (3 d[i] + d[i+1]) / 8,   d = 0 outside.
+// One thread per (input pixel, 8 channels): 3 x 3 neighbourhood in, 2 x 2 outputs (+ optional addend) out.
+__global__ void __launch_bounds__(kBwThreads) fir_down2_adjoint_kernel(const uint4* __restrict__ d, const uint4* __restrict__ add,
+                                                                       uint4* __restrict__ out, int B, int h, int w, int groups) {
+  const long long n = (long long)B * h * w * groups;
+  for (long long idx = (long long)blockIdx.x * kBwThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kBwThreads) {
+    const int g = (int)(idx % groups);
+    long long r = idx / groups;
+    const int j = (int)(r % w);
+    r /= w;
+    const int i = (int)(r % h);
+    const int b = (int)(r / h);
+    float v[3][3][8];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int y = i + dy - 1, x = j + dx - 1;
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (y >= 0 && y < h && x >= 0 && x < w) q = __ldg(d + (((long long)b * h + y) * w + x) * groups + g);
+        const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(hq[k]);
+          v[dy][dx][2 * k] = f.x;
+          v[dy][dx][2 * k + 1] = f.y;
+        }
+      }
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const long long o = (((long long)b * 2 * h + 2 * i + py) * (2 * w) + 2 * j + px) * groups + g;
+        float acc[8];
+        if (add) {
+          const uint4 q = __ldcs(add + o);
+          const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(hq[k]);
+            acc[2 * k] = f.x;
+            acc[2 * k + 1] = f.y;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        }
+        const int ny = py ? 2 : 0, nx = px ? 2 : 0;  // the neighbour that gets weight 1/8 on this phase
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          acc[k] += (9.f * v[1][1][k] + 3.f * (v[ny][1][k] + v[1][nx][k]) + v[ny][nx][k]) * (1.f / 64.f);
+        uint4 q;
+        __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hq[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+        __stcs(out + o, q);
+      }
+  }
+}
+
 }  // namespace b200ir
 
 using namespace b200ir;
@@ -74,4 +137,30 @@ extern "C" int b200ir_lrelu_bias_bwd(const void* dy, const void* y, void* dz, fl
   lrelu_bias_bwd_kernel<<<(int)grid, kBwThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (uint4*)dz, dbias, n_pix, groups,
                                                           slope, scale);
   return check_launch("lrelu_bias_bwd");
+}
+
+extern "C" int b200ir_fir_pad11(const void* in, void* out, int B, int H, int W, int C, int in_h, int in_w, void* stream) {
+  B200IR_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && in_h >= H + 1 && in_w >= W + 1, "fir_pad11: bad arguments");
+  FirLaunch a = {};
+  a.in = (const __half*)in; a.B = B; a.Hv = H + 1; a.Wv = W + 1;
+  a.in_sw = C; a.in_sh = (long long)in_w * C; a.in_sb = (long long)in_h * in_w * C;
+  a.C = C; a.OH = H; a.OW = W; a.pad = 1; a.kscale = 0.125f;
+  a.out = (__half*)out; a.out_sy = (long long)W * C; a.out_sb = (long long)H * W * C;
+  a.post = false;
+  const int r = fir_stream_launch(a, reinterpret_cast<cudaStream_t>(stream), "fir_pad11");
+  if (r >= 0) return r;
+  set_error("fir_pad11: C=%d must be a multiple of 32 and the input 16-byte aligned (TMA streaming kernel only)", C);
+  return 1;
+}
+
+extern "C" int b200ir_fir_down2_adjoint(const void* d, const void* add, void* out, int B, int h, int w, int C, void* stream) {
+  B200IR_REQUIRE(d && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0, "fir_down2_adjoint: bad arguments");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const long long n = (long long)B * h * w * (C / 8);
+  long long grid = (n + kBwThreads - 1) / kBwThreads;
+  if (grid > 16LL * sms) grid = 16LL * sms;
+  fir_down2_adjoint_kernel<<<(int)grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const uint4*)d, (const uint4*)add, (uint4*)out, B, h, w, C / 8);
+  return check_launch("fir_down2_adjoint");
 }

@@ -161,16 +161,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     const int q = warp & 3;
     const int co = co_blk * 128 + q * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int ci0 = ci_blk * (64 * kNC);
     for (int kw = 0; kw < 3; ++kw) {
       if (!((kw_mask >> kw) & 1u)) continue;
-      float* dst = p.dw + ((long long)co * 9 + kh * 3 + kw) * p.cin + ci_blk * (64 * kNC);
+      float* dst = p.dw + ((long long)co * 9 + kh * 3 + kw) * p.cin + ci0;
 #pragma unroll
       for (int c16 = 0; c16 < 4 * kNC; ++c16) {
+        if (ci0 + c16 * 16 >= p.cin) break;  // warp-uniform: channels past cin were zero-filled by TMA
         uint32_t v[16];
         tmem_ld16(trow + kw * (64 * kNC) + c16 * 16, v);
         tmem_ld_wait16(v);
+        if (co < p.cout) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(dst + c16 * 16 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + c16 * 16 + j, __uint_as_float(v[j]));
+        }
       }
     }
   }
@@ -192,8 +196,8 @@ extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, flo
   const int cin = xv->c;
   tap_mask &= 0x1FFu;
   B200IR_REQUIRE(tap_mask != 0, "conv_wgrad: empty tap mask");
-  B200IR_REQUIRE(cin % 64 == 0 && cout % 128 == 0, "conv_wgrad: cin=%d must be a multiple of 64 and cout=%d of 128", cin,
-                 cout);
+  B200IR_REQUIRE(cin > 0 && cin % 16 == 0 && cout > 0 && cout % 8 == 0,
+                 "conv_wgrad: cin=%d must be a multiple of 16 and cout=%d of 8", cin, cout);
   B200IR_REQUIRE(((reinterpret_cast<uintptr_t>(xv->ptr) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0 &&
                      xv->stride_w % 8 == 0 && xv->stride_h % 8 == 0 && xv->stride_b % 8 == 0,
                  "conv_wgrad: operands must be 16-byte aligned, view strides multiples of 8 elements");
@@ -220,9 +224,12 @@ extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, flo
   p.tiles_x = (W + kWgTileW - 1) / kWgTileW;
   p.tiles_y = (H + kWgTileH - 1) / kWgTileH;
   p.num_tiles = B * p.tiles_x * p.tiles_y;
-  const int nc = (cin % 128 == 0) ? 2 : 1;   // input-channel block of 128 (N = 128 MMAs) whenever cin allows it
-  p.ci_blocks = cin / (64 * nc);
-  const int units = (cout / 128) * p.ci_blocks * p.num_kh;
+  // Channel blocks are 128 (cout) x 64 or 128 (cin); the TMA boxes of a ragged last block are zero-filled past the
+  // tensor's channel extent and the epilogue skips those rows / columns, so small layers (32, 64 channels) run on the
+  // same kernel with part of the MMA idle.
+  const int nc = (cin > 64) ? 2 : 1;
+  p.ci_blocks = (cin + 64 * nc - 1) / (64 * nc);
+  const int units = ((cout + 127) / 128) * p.ci_blocks * p.num_kh;
   // One wave of CTAs (one per SM: the ring takes the whole shared memory) and at least ~16 pixel tiles per CTA, so that
   // the fixed cost of a CTA -- 128 x N x 3 fp32 atomics into dW -- stays below its MMA time (measured sweep:
   // tools/sweep_wgrad.py; two waves were 20-45 % slower on every layer of the B = 64 step).

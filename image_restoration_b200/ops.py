@@ -582,3 +582,16 @@ def conv3x3_s2_wgrad(p, h, w, dy):
                 for sx in sxs:
                     dw[:, 2 * sy + ry, 2 * sx + rx] = part[:, sy + 1, sx + 1]
     return dw.view(cout, 9, c)
+
+
+def fir_pad11(raw, out):
+    """Adjoint of fir_pad22: raw [B,RH,RW,C] (valid (H+1)x(W+1) at the origin) -> out [B,H,W,C]."""
+    b, h, w, c = out.shape
+    check(_lib.lib().b200ir_fir_pad11(_ptr(raw), _ptr(out), b, h, w, c, raw.shape[1], raw.shape[2], _stream()), 'fir_pad11')
+
+
+def fir_down2_adjoint(d, out, add=None):
+    """Adjoint of fir_down2: d [B,h,w,C] -> out [B,2h,2w,C] (+ add)."""
+    b, h, w, c = d.shape
+    assert tuple(out.shape) == (b, 2 * h, 2 * w, c) and (add is None or add.shape == out.shape)
+    check(_lib.lib().b200ir_fir_down2_adjoint(_ptr(d), _ptr(add), _ptr(out), b, h, w, c, _stream()), 'fir_down2_adjoint')

@@ -156,8 +156,8 @@ int b200ir_first_conv(const float* x, const float* w, const float* bias, void* o
 /* Weight gradient of a 3x3 stride-1 'same' convolution (F.conv2d(x, W, padding=1), the EqualConv2d / ConvUpLayer convs:
  * stylegan2_ocr_arch.py:639-648, gfpganv1_ocr_arch.py:192): dW[co][kh][kw][ci] = sum_{b,y,x} dy[b][y][x][co] *
  * x[b][y+kh-1][x+kw-1][ci].  x NHWC fp16 [B][H][W][cin], dy NHWC fp16 [B][H][W][cout], dw fp32 [cout][9][cin] (the
- * layout of the packed forward weights; the equalised-lr scale is the caller's), overwritten.  cin % 64 == 0,
- * cout % 128 == 0.  tcgen05 GEMM over pixels with MN-major operands, split over pixel ranges, fp32 atomic reduction. */
+ * layout of the packed forward weights; the equalised-lr scale is the caller's), overwritten.  cin % 16 == 0,
+ * cout % 8 == 0 (channel blocks are 128 x 64/128; ragged blocks are zero-filled by TMA).  tcgen05 GEMM over pixels with MN-major operands, split over pixel ranges, fp32 atomic reduction. */
 int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int cin, int cout, void* stream);
 
 /* The same kernel over a strided view of x and a subset of the nine taps:
@@ -167,7 +167,7 @@ int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, in
  *   - the stride-2 3x3 convs of ResBlock.conv2 (stylegan2_ocr_arch.py:685-697, F.conv2d(stride=2) over the FIR-smoothed
  *     buffer p): one call per pixel phase (ry, rx) of p, the view's strides stepping two pixels / two rows from
  *     p + (ry * row + rx) * cin; kernel element (2*sy + ry, 2*sx + rx) of the conv comes back at tap (sy + 1, sx + 1).
- * xv->c = cin (multiple of 64), xv->b = B, cout % 128 == 0. */
+ * xv->c = cin (multiple of 16), xv->b = B, cout % 8 == 0. */
 int b200ir_conv_wgrad_view(const b200ir_view* x, const void* dy, float* dw, int B, int H, int W, int cout,
                            uint32_t tap_mask, void* stream);
 
@@ -178,6 +178,17 @@ int b200ir_conv_wgrad_view(const b200ir_view* x, const void* dy, float* dw, int 
  * NULL (ScaledLeakyReLU, stylegan2_ocr_arch.py:604-606).  C = 8 * a divisor of 256.  dz may alias dy. */
 int b200ir_lrelu_bias_bwd(const void* dy, const void* y, void* dz, float* dbias, int64_t n_pix, int C, float slope,
                           float scale, void* stream);
+
+/* Adjoint of b200ir_fir_pad22 (upfirdn2d(x, k, pad = (2, 2)), upfirdn2d.py:153-192: the blur in front of the stride-2 3x3
+ * conv of ResBlock.conv2) = upfirdn2d(d, k, pad = (1, 1)): in [B][in_h][in_w][C] fp16 with the valid (H+1) x (W+1) region
+ * at the origin (the raw output of the transposed conv that is the stride-2 conv's input gradient) -> out [B][H][W][C].
+ * TMA streaming kernel; C % 32 == 0. */
+int b200ir_fir_pad11(const void* in, void* out, int B, int H, int W, int C, int in_h, int in_w, void* stream);
+
+/* Adjoint of b200ir_fir_down2 (FIR pad (1, 1) + even-position sampling in front of the 1x1 skip conv of ResBlock):
+ * d [B][h][w][C] fp16 -> out [B][2h][2w][C] = add + upfirdn2d(d, k, up = 2, pad = (2, 1)) (k normalised to sum 1, no
+ * up-sampling gain); add may be NULL or alias out. */
+int b200ir_fir_down2_adjoint(const void* d, const void* add, void* out, int B, int h, int w, int C, void* stream);
 
 /* One torch.optim.Adam step (no amsgrad; optimizer_g / optimizer_d of basicsr/models/gfpgan_model.py:217-248) over a flat
  * fp32 parameter buffer, fused with the gradient scaling of the data-parallel average (grad_scale = 1 / world) and,

@@ -86,3 +86,81 @@ def test_conv_layer_autograd(B, H, W, cin, cout):
         rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
         print(f'conv layer {cin}->{cout} {name}: rel rms {rel:.3e}')
         assert rel <= 2e-3, (name, rel)                  # fp16 storage of y, dz and dx: 2^-11 per element
+
+
+def _fir(x, pad, stride=1):
+    """upfirdn2d(x, outer([1,3,3,1]) / 64, pad=(pad, pad)) (+ sampling), the reference's upfirdn2d_native (upfirdn2d.py:162-192)."""
+    k = torch.tensor([1., 3., 3., 1.], device=x.device, dtype=x.dtype)
+    k2 = (torch.outer(k, k) / 64).view(1, 1, 4, 4).repeat(x.shape[1], 1, 1, 1)
+    return F.conv2d(F.pad(x, (pad,) * 4), k2, groups=x.shape[1], stride=stride)
+
+
+@pytest.mark.parametrize('B,H,W,C', [(2, 8, 24, 64), (1, 32, 96, 256), (3, 6, 10, 32)])
+def test_fir_adjoints(B, H, W, C):
+    from image_restoration_b200 import ops
+    torch.manual_seed(H + C)
+    # adjoint of fir_pad22: gradient of sum(fir(x, 2) * d) w.r.t. x
+    d = torch.randn(B, C, H + 1, W + 1, device='cuda').half()
+    x = torch.zeros(B, C, H, W, device='cuda', requires_grad=True)
+    (_fir(x, 2) * d.float()).sum().backward()
+    raw = torch.randn(B, H + 2, W + 2, C, device='cuda').half()          # garbage in the padding row / column
+    raw[:, :H + 1, :W + 1] = d.permute(0, 2, 3, 1)
+    out = torch.empty(B, H, W, C, device='cuda', dtype=torch.float16)
+    ops.fir_pad11(raw, out)
+    torch.cuda.synchronize()
+    err = (out.float().permute(0, 3, 1, 2) - x.grad).abs().max().item()
+    assert err <= 2e-3 * x.grad.abs().max().item(), err
+    # adjoint of fir_down2 (+ addend)
+    d2 = torch.randn(B, C, H // 2, W // 2, device='cuda').half()
+    x2 = torch.zeros(B, C, H, W, device='cuda', requires_grad=True)
+    (_fir(x2, 1, stride=2) * d2.float()).sum().backward()
+    addend = torch.randn(B, H, W, C, device='cuda').half()
+    out2 = addend.clone()
+    ops.fir_down2_adjoint(d2.permute(0, 2, 3, 1).contiguous(), out2, add=out2)
+    ref2 = x2.grad.permute(0, 2, 3, 1) + addend.float()
+    torch.cuda.synchronize()
+    err2 = (out2.float() - ref2).abs().max().item()
+    assert err2 <= 2e-3 * ref2.abs().max().item(), err2
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout', [(2, 16, 48, 64, 128), (2, 32, 96, 256, 256), (1, 32, 96, 32, 64), (2, 8, 24, 64, 256)])
+def test_res_block_autograd(B, H, W, cin, cout):
+    """ResBlock (stylegan2_ocr_arch.py:708-734) forward + backward against the fp32 restatement through torch.autograd."""
+    from image_restoration_b200.backward import ResBlockFunction, res_block
+    torch.manual_seed(cin + cout)
+    par = dict(w1=torch.randn(cin, cin, 3, 3), b1=0.1 * torch.randn(cin), w2=torch.randn(cout, cin, 3, 3),
+               b2=0.1 * torch.randn(cout), ws=torch.randn(cout, cin, 1, 1))
+    par = {k: v.cuda().requires_grad_() for k, v in par.items()}
+    x = torch.randn(B, cin, H, W, device='cuda').half()
+    dout = torch.randn(B, cout, H // 2, W // 2, device='cuda').half()
+
+    xg = x.permute(0, 2, 3, 1).contiguous().requires_grad_()
+    ResBlockFunction.debug_saved = saved = {}
+    out = res_block(xg, par['w1'], par['b1'], par['w2'], par['b2'], par['ws'])
+    ResBlockFunction.debug_saved = None
+    out.backward(dout.permute(0, 2, 3, 1).contiguous())
+    got = {'out': out.detach().float().permute(0, 3, 1, 2), 'dx': xg.grad.float().permute(0, 3, 1, 2)}
+    got.update({'d' + k: v.grad.clone() for k, v in par.items()})
+
+    ref_par = {k: v.detach().clone().requires_grad_() for k, v in par.items()}
+    s1, s2, ss = 1 / math.sqrt(cin * 9), 1 / math.sqrt(cin * 9), 1 / math.sqrt(cin)
+    x_ref = x.float().requires_grad_()
+    # The fp16 forward moves pre-activations by ~3e-4, so ~2e-4 of them cross zero relative to an fp32 forward; each
+    # crossing changes that element's gradient by a factor 5, which would dominate an RMS comparison (~1e-2).  The
+    # reference therefore takes the leaky-ReLU branch from the sign of the kernels' own activations.
+    def lrelu(z, act):
+        return z * torch.where(act.float().permute(0, 3, 1, 2) > 0, SQRT2, 0.2 * SQRT2)
+    t1 = lrelu(F.conv2d(x_ref, ref_par['w1'] * s1, padding=1) + ref_par['b1'].view(1, -1, 1, 1), saved['t1'])
+    y2 = lrelu(F.conv2d(_fir(t1, 2), ref_par['w2'] * s2, stride=2) + ref_par['b2'].view(1, -1, 1, 1), saved['y2'])
+    sk = F.conv2d(_fir(x_ref, 1), ref_par['ws'] * ss, stride=2)
+    out_ref = (y2 + sk) / SQRT2
+    out_ref.backward(dout.float())
+    ref = {'out': out_ref.detach(), 'dx': x_ref.grad}
+    ref.update({'d' + k: v.grad for k, v in ref_par.items()})
+    torch.cuda.synchronize()
+    for name in ref:
+        g, r = got[name], ref[name]
+        assert g.shape == r.shape, (name, g.shape, r.shape)
+        rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
+        print(f'res block {cin}->{cout} {H}x{W} {name}: rel rms {rel:.3e}')
+        assert rel <= 1.5e-3, (name, rel)    # fp16 weights and fp16 storage of t1, p, y2, dz2, raw, dt1, dx

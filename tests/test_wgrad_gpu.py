@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('B,H,W,cin,cout', [(2, 8, 32, 64, 128), (3, 16, 48, 128, 256), (1, 7, 45, 64, 128),
-                                              (4, 32, 96, 256, 256), (2, 4, 12, 512, 512)])
+                                              (4, 32, 96, 256, 256), (2, 4, 12, 512, 512), (2, 16, 48, 64, 64), (1, 32, 96, 32, 32),
+                                              (2, 8, 24, 32, 64), (1, 8, 24, 192, 24), (1, 8, 16, 48, 200)])
 def test_wgrad_matches_torch(B, H, W, cin, cout):
     from image_restoration_b200 import ops
     torch.manual_seed(B * 100 + H)
@@ -27,7 +28,7 @@ def test_wgrad_matches_torch(B, H, W, cin, cout):
 
 def test_wgrad_rejects_unsupported_channels():
     from image_restoration_b200 import ops
-    x = torch.zeros(1, 8, 8, 32, device='cuda', dtype=torch.float16)
+    x = torch.zeros(1, 8, 8, 24, device='cuda', dtype=torch.float16)          # cin must be a multiple of 16
     dy = torch.zeros(1, 8, 8, 128, device='cuda', dtype=torch.float16)
     with pytest.raises(RuntimeError):
         ops.conv_wgrad(x, dy)
@@ -47,7 +48,8 @@ def test_wgrad_1x1(B, H, W, cin, cout):
     assert err <= 1e-3 * scale, (err, scale)
 
 
-@pytest.mark.parametrize('B,H,W,cin,cout', [(2, 8, 32, 64, 128), (2, 32, 96, 64, 256), (3, 16, 48, 256, 256), (1, 6, 70, 128, 128)])
+@pytest.mark.parametrize('B,H,W,cin,cout', [(2, 8, 32, 64, 128), (2, 32, 96, 64, 256), (3, 16, 48, 256, 256), (1, 6, 70, 128, 128),
+                                              (2, 16, 48, 32, 64)])
 def test_wgrad_3x3_stride2(B, H, W, cin, cout):
     """ResBlock.conv2: F.conv2d(p, W, stride=2) over the (H+1)x(W+1) FIR output held in a [B,H+2,W+2,C] buffer."""
     from image_restoration_b200 import ops
