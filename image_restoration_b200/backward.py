@@ -152,3 +152,77 @@ class ResBlockFunction(torch.autograd.Function):
 
 def res_block(x, w1, b1, w2, b2, ws):
     return ResBlockFunction.apply(x, w1, b1, w2, b2, ws)
+
+
+class ResUpBlockFunction(torch.autograd.Function):
+    """ResUpBlock of the U-Net decoder (gfpganv1_ocr_arch.py:205-225) on NHWC fp16 activations, forward and backward:
+
+        t1  = FusedLeakyReLU(conv3x3(x, W1) + b1)                                conv1
+        y2  = FusedLeakyReLU(conv3x3(bilinear_up2(t1), W2) + b2)                 conv2 (ConvUpLayer)
+        out = (y2 + bilinear_up2(conv1x1(x, Ws))) / sqrt 2                       skip (the 1x1 conv commutes with bilinear x2)
+
+    y2 / sqrt 2 is produced directly (leaky ReLU without the sqrt 2 gain) and kept for the backward pass; the 1 / sqrt 2
+    of the skip is folded into Ws."""
+
+    debug_saved = None
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, ws):
+        if not x.is_cuda:
+            raise RuntimeError('image_restoration_b200.backward.ResUpBlockFunction needs CUDA tensors (no CPU path)')
+        b, h, w, cin = x.shape
+        cout = w2.shape[0]
+        dev = x.device
+        w1p, s1 = pack_equal_conv(w1)
+        w2p, s2 = pack_equal_conv(w2)
+        wsp, ss = pack_equal_conv(ws * ops.INV_SQRT2)
+        e16 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float16)   # noqa: E731
+        t1 = e16(b, h, w, cin)
+        ops.conv_same(x, w1p, t1, 3, bias=b1.detach().float().contiguous(), act=True)()
+        u = e16(b, 2 * h, 2 * w, cin)
+        ops.bilinear_up2(t1, u)
+        y2 = e16(b, 2 * h, 2 * w, cout)
+        ops.conv_same(u, w2p, y2, 3, bias=b2.detach().float().contiguous(), act_slope=0.2)()
+        sl = e16(b, h, w, cout)
+        ops.conv_same(x, wsp, sl, 1)()
+        su = e16(b, 2 * h, 2 * w, cout)
+        ops.bilinear_up2(sl, su)
+        out = e16(b, 2 * h, 2 * w, cout)
+        ops.add(y2, su, out)
+        ctx.save_for_backward(x, t1, u, y2, w1p, w2p, wsp)
+        ctx.scales = (s1, s2, ss * ops.INV_SQRT2)
+        if ResUpBlockFunction.debug_saved is not None:
+            ResUpBlockFunction.debug_saved.update(t1=t1, y2=y2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, t1, u, y2, w1p, w2p, wsp = ctx.saved_tensors
+        s1, s2, ss = ctx.scales
+        b, h, w, cin = x.shape
+        cout = y2.shape[3]
+        need = ctx.needs_input_grad
+        dout = dout.contiguous()
+        dz2, db2 = ops.lrelu_bias_bwd(dout, y2, scale=1.0, want_bias=need[4])
+        dw2 = ops.conv_wgrad(u, dz2).view(cout, 3, 3, cin).permute(0, 3, 1, 2) * s2 if need[3] else None
+        du = torch.empty_like(u)
+        ops.conv_dgrad(dz2, ops.conv_dgrad_weight(w2p, cin), du)()
+        dt1 = torch.empty_like(t1)
+        ops.bilinear_up2_adjoint(du, dt1)
+        dz1, db1 = ops.lrelu_bias_bwd(dt1, t1, dz=dt1, want_bias=need[2])
+        dw1 = ops.conv_wgrad(x, dz1).view(cin, 3, 3, cin).permute(0, 3, 1, 2) * s1 if need[1] else None
+        dsl = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float16)
+        ops.bilinear_up2_adjoint(dout, dsl)
+        dws = (ops.conv1x1_wgrad(x, dsl) * ss).reshape(cout, cin, 1, 1) if need[5] else None
+        dx = None
+        if need[0]:
+            dx1 = torch.empty_like(x)
+            ops.conv_dgrad(dz1, ops.conv_dgrad_weight(w1p, cin), dx1)()
+            dx = torch.empty_like(x)
+            ops.conv_same(dsl, wsp.t().contiguous(), dx, 1, res=dx1, res_mode=1, res_strides=(cin, w * cin, h * w * cin),
+                          res_wh=(w, h), res_scale=1.0)()
+        return dx, dw1, db1, dw2, db2, dws
+
+
+def res_up_block(x, w1, b1, w2, b2, ws):
+    return ResUpBlockFunction.apply(x, w1, b1, w2, b2, ws)

@@ -114,6 +114,49 @@ __global__ void __launch_bounds__(kBwThreads) fir_down2_adjoint_kernel(const uin
   }
 }
 
+// Adjoint of b200ir_bilinear_up2 (F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) of ConvUpLayer,
+// gfpganv1_ocr_arch.py:190): per axis hi[2i] = .75 lo[i] + .25 lo[max(i-1, 0)], hi[2i+1] = .75 lo[i] + .25 lo[min(i+1, n-1)],
+// so  dlo[i] = sum_t (.25, .75, .75, .25)[t] * dhi[clamp(2i - 1 + t, 0, 2n - 1)]  (the clamp returns the border rows'
+// replicated taps to the row that was replicated).  One thread per (low-resolution pixel, 8 channels): 4 x 4 gather.
+__global__ void __launch_bounds__(kBwThreads) bilinear_up2_adjoint_kernel(const uint4* __restrict__ d, uint4* __restrict__ out,
+                                                                          int B, int h, int w, int groups, float scale) {
+  const long long n = (long long)B * h * w * groups;
+  for (long long idx = (long long)blockIdx.x * kBwThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kBwThreads) {
+    const int g = (int)(idx % groups);
+    long long r = idx / groups;
+    const int j = (int)(r % w);
+    r /= w;
+    const int i = (int)(r % h);
+    const int b = (int)(r / h);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty) {
+      const int y = min(max(2 * i - 1 + ty, 0), 2 * h - 1);
+      const float wy = (ty == 0 || ty == 3) ? 0.25f : 0.75f;
+#pragma unroll
+      for (int tx = 0; tx < 4; ++tx) {
+        const int x = min(max(2 * j - 1 + tx, 0), 2 * w - 1);
+        const float wt = wy * ((tx == 0 || tx == 3) ? 0.25f : 0.75f);
+        const uint4 q = __ldg(d + (((long long)b * 2 * h + y) * (2 * w) + x) * groups + g);
+        const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(hq[k]);
+          acc[2 * k] += wt * f.x;
+          acc[2 * k + 1] += wt * f.y;
+        }
+      }
+    }
+    uint4 q;
+    __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hq[k] = __floats2half2_rn(acc[2 * k] * scale, acc[2 * k + 1] * scale);
+    out[idx] = q;
+  }
+}
+
 }  // namespace b200ir
 
 using namespace b200ir;
@@ -163,4 +206,16 @@ extern "C" int b200ir_fir_down2_adjoint(const void* d, const void* add, void* ou
   fir_down2_adjoint_kernel<<<(int)grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const uint4*)d, (const uint4*)add, (uint4*)out, B, h, w, C / 8);
   return check_launch("fir_down2_adjoint");
+}
+
+extern "C" int b200ir_bilinear_up2_adjoint(const void* d, void* out, int B, int h, int w, int C, float scale, void* stream) {
+  B200IR_REQUIRE(d && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0, "bilinear_up2_adjoint: bad arguments");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const long long n = (long long)B * h * w * (C / 8);
+  long long grid = (n + kBwThreads - 1) / kBwThreads;
+  if (grid > 16LL * sms) grid = 16LL * sms;
+  bilinear_up2_adjoint_kernel<<<(int)grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const uint4*)d, (uint4*)out, B, h, w, C / 8, scale);
+  return check_launch("bilinear_up2_adjoint");
 }

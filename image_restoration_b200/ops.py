@@ -595,3 +595,10 @@ def fir_down2_adjoint(d, out, add=None):
     b, h, w, c = d.shape
     assert tuple(out.shape) == (b, 2 * h, 2 * w, c) and (add is None or add.shape == out.shape)
     check(_lib.lib().b200ir_fir_down2_adjoint(_ptr(d), _ptr(add), _ptr(out), b, h, w, c, _stream()), 'fir_down2_adjoint')
+
+
+def bilinear_up2_adjoint(d, out, scale=1.0):
+    """Adjoint of bilinear_up2: d [B,2h,2w,C] -> out [B,h,w,C] (times scale)."""
+    b, h, w, c = out.shape
+    assert tuple(d.shape) == (b, 2 * h, 2 * w, c)
+    check(_lib.lib().b200ir_bilinear_up2_adjoint(_ptr(d), _ptr(out), b, h, w, c, scale, _stream()), 'bilinear_up2_adjoint')

@@ -190,6 +190,11 @@ int b200ir_fir_pad11(const void* in, void* out, int B, int H, int W, int C, int 
  * up-sampling gain); add may be NULL or alias out. */
 int b200ir_fir_down2_adjoint(const void* d, const void* add, void* out, int B, int h, int w, int C, void* stream);
 
+/* Adjoint of b200ir_bilinear_up2 (F.interpolate x2 bilinear, align_corners=False, of ConvUpLayer, gfpganv1_ocr_arch.py:190):
+ * d [B][2h][2w][C] fp16 -> out [B][h][w][C] = scale * sum of the 4 x 4 taps (.25, .75, .75, .25)^2 at rows / columns
+ * clamp(2i - 1 + t, 0, 2n - 1). */
+int b200ir_bilinear_up2_adjoint(const void* d, void* out, int B, int h, int w, int C, float scale, void* stream);
+
 /* One torch.optim.Adam step (no amsgrad; optimizer_g / optimizer_d of basicsr/models/gfpgan_model.py:217-248) over a flat
  * fp32 parameter buffer, fused with the gradient scaling of the data-parallel average (grad_scale = 1 / world) and,
  * when ema != NULL, with the EMA update of BaseModel.model_ema (basicsr/models/base_model.py:50-57):

@@ -164,3 +164,62 @@ def test_res_block_autograd(B, H, W, cin, cout):
         rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
         print(f'res block {cin}->{cout} {H}x{W} {name}: rel rms {rel:.3e}')
         assert rel <= 1.5e-3, (name, rel)    # fp16 weights and fp16 storage of t1, p, y2, dz2, raw, dt1, dx
+
+
+@pytest.mark.parametrize('B,h,w,C', [(2, 4, 12, 64), (1, 16, 48, 256), (3, 5, 7, 32)])
+def test_bilinear_up2_adjoint(B, h, w, C):
+    from image_restoration_b200 import ops
+    torch.manual_seed(h + C)
+    d = torch.randn(B, C, 2 * h, 2 * w, device='cuda').half()
+    x = torch.zeros(B, C, h, w, device='cuda', requires_grad=True)
+    (F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) * d.float()).sum().backward()
+    out = torch.empty(B, h, w, C, device='cuda', dtype=torch.float16)
+    ops.bilinear_up2_adjoint(d.permute(0, 2, 3, 1).contiguous(), out, scale=0.5)
+    torch.cuda.synchronize()
+    err = (out.float().permute(0, 3, 1, 2) - 0.5 * x.grad).abs().max().item()
+    assert err <= 2e-3 * x.grad.abs().max().item(), err
+
+
+@pytest.mark.parametrize('B,h,w,cin,cout', [(2, 8, 24, 256, 256), (2, 16, 48, 256, 64), (1, 32, 96, 64, 32), (2, 4, 12, 128, 128)])
+def test_res_up_block_autograd(B, h, w, cin, cout):
+    """ResUpBlock (gfpganv1_ocr_arch.py:205-225) forward + backward against the fp32 restatement through torch.autograd
+    (leaky-ReLU branches taken from the kernels' own activations, see test_res_block_autograd)."""
+    from image_restoration_b200.backward import ResUpBlockFunction, res_up_block
+    torch.manual_seed(cin + cout + 1)
+    par = dict(w1=torch.randn(cin, cin, 3, 3), b1=0.1 * torch.randn(cin), w2=torch.randn(cout, cin, 3, 3),
+               b2=0.1 * torch.randn(cout), ws=torch.randn(cout, cin, 1, 1))
+    par = {k: v.cuda().requires_grad_() for k, v in par.items()}
+    x = torch.randn(B, cin, h, w, device='cuda').half()
+    dout = torch.randn(B, cout, 2 * h, 2 * w, device='cuda').half()
+
+    xg = x.permute(0, 2, 3, 1).contiguous().requires_grad_()
+    ResUpBlockFunction.debug_saved = saved = {}
+    out = res_up_block(xg, par['w1'], par['b1'], par['w2'], par['b2'], par['ws'])
+    ResUpBlockFunction.debug_saved = None
+    out.backward(dout.permute(0, 2, 3, 1).contiguous())
+    got = {'out': out.detach().float().permute(0, 3, 1, 2), 'dx': xg.grad.float().permute(0, 3, 1, 2)}
+    got.update({'d' + k: v.grad.clone() for k, v in par.items()})
+
+    ref_par = {k: v.detach().clone().requires_grad_() for k, v in par.items()}
+    s3, s1x1 = 1 / math.sqrt(cin * 9), 1 / math.sqrt(cin)
+    x_ref = x.float().requires_grad_()
+
+    def lrelu(z, act):
+        return z * torch.where(act.float().permute(0, 3, 1, 2) > 0, SQRT2, 0.2 * SQRT2)
+
+    def up(t):
+        return F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=False)
+    t1 = lrelu(F.conv2d(x_ref, ref_par['w1'] * s3, padding=1) + ref_par['b1'].view(1, -1, 1, 1), saved['t1'])
+    y2 = lrelu(F.conv2d(up(t1), ref_par['w2'] * s3, padding=1) + ref_par['b2'].view(1, -1, 1, 1), saved['y2'])
+    sk = F.conv2d(up(x_ref), ref_par['ws'] * s1x1)
+    out_ref = (y2 + sk) / SQRT2
+    out_ref.backward(dout.float())
+    ref = {'out': out_ref.detach(), 'dx': x_ref.grad}
+    ref.update({'d' + k: v.grad for k, v in ref_par.items()})
+    torch.cuda.synchronize()
+    for name in ref:
+        g, r = got[name], ref[name]
+        assert g.shape == r.shape, (name, g.shape, r.shape)
+        rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
+        print(f'res up block {cin}->{cout} {h}x{w} {name}: rel rms {rel:.3e}')
+        assert rel <= 1.5e-3, (name, rel)
