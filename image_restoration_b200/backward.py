@@ -29,18 +29,20 @@ def pack_equal_conv3x3(weight):
 
 
 class ConvLayer3x3Function(torch.autograd.Function):
-    """y = FusedLeakyReLU(EqualConv2d(x)) on NHWC fp16 activations; gradients for x, weight and bias."""
+    """y = FusedLeakyReLU(EqualConv2d(x)) (activate=True; also EqualConv2d(bias=True) + ScaledLeakyReLU of the SFT heads,
+    gfpganv1_ocr_arch.py:322-339) or y = EqualConv2d(x) + bias (activate=False) on NHWC fp16 activations; gradients for x,
+    weight and bias."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, activate=True):
         if not x.is_cuda:
             raise RuntimeError('image_restoration_b200.backward.ConvLayer3x3Function needs CUDA tensors (no CPU path)')
         b, h, w, cin = x.shape
         cout = weight.shape[0]
         wp, scale = pack_equal_conv3x3(weight)
         y = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float16)
-        ops.conv_same(x, wp, y, 3, bias=bias.detach().float().contiguous(), act=True)()
-        ctx.save_for_backward(x, y, wp)
+        ops.conv_same(x, wp, y, 3, bias=bias.detach().float().contiguous(), act=activate)()
+        ctx.save_for_backward(x, y if activate else None, wp)
         ctx.scale = scale
         return y
 
@@ -48,8 +50,12 @@ class ConvLayer3x3Function(torch.autograd.Function):
     def backward(ctx, dy):
         x, y, wp = ctx.saved_tensors
         b, h, w, cin = x.shape
-        cout = y.shape[3]
-        dz, dbias = ops.lrelu_bias_bwd(dy.contiguous(), y, want_bias=ctx.needs_input_grad[2])
+        cout = wp.shape[0]
+        dy = dy.contiguous()
+        if y is not None:
+            dz, dbias = ops.lrelu_bias_bwd(dy, y, want_bias=ctx.needs_input_grad[2])
+        else:
+            dz, dbias = dy, (ops.lrelu_bias_bwd(dy, None, scale=1.0)[1] if ctx.needs_input_grad[2] else None)
         dx = dweight = None
         if ctx.needs_input_grad[1]:
             dw = ops.conv_wgrad(x, dz)                                           # [cout, 9, cin] fp32
@@ -57,11 +63,52 @@ class ConvLayer3x3Function(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             ops.conv_dgrad(dz, ops.conv_dgrad_weight(wp, cin), dx)()
-        return dx, dweight, dbias
+        return dx, dweight, dbias, None
 
 
-def conv_layer3x3(x, weight, bias):
-    return ConvLayer3x3Function.apply(x, weight, bias)
+def conv_layer3x3(x, weight, bias, activate=True):
+    return ConvLayer3x3Function.apply(x, weight, bias, activate)
+
+
+class EqualLinearFunction(torch.autograd.Function):
+    """EqualLinear without activation (stylegan2_ocr_arch.py:165-175; final_linear of GFPGANv1OCR, 12288 -> 3072):
+    y = x @ (W * scale)^T + bias * lr_mul on fp16 rows x [B, in].  Forward and input gradient are 1x1 convs over B
+    'pixels'; the weight gradient dW = dy^T x is the wgrad kernel with the batch laid out along the pixel axis."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lr_mul=1.0):
+        if not x.is_cuda:
+            raise RuntimeError('image_restoration_b200.backward.EqualLinearFunction needs CUDA tensors (no CPU path)')
+        b, cin = x.shape
+        cout = weight.shape[0]
+        scale = lr_mul / math.sqrt(cin)
+        wp = (weight.detach() * scale).to(torch.float16).contiguous()
+        y = torch.empty(b, cout, device=x.device, dtype=torch.float16)
+        ops.conv_same(x.view(1, 1, b, cin), wp, y.view(1, 1, b, cout), 1, bias=(bias.detach().float() * lr_mul).contiguous())()
+        ctx.save_for_backward(x, wp)
+        ctx.consts = (scale, lr_mul)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wp = ctx.saved_tensors
+        scale, lr_mul = ctx.consts
+        b, cin = x.shape
+        cout = wp.shape[0]
+        dy = dy.contiguous()
+        dx = dweight = dbias = None
+        if ctx.needs_input_grad[2]:
+            dbias = ops.lrelu_bias_bwd(dy, None, scale=1.0)[1] * lr_mul
+        if ctx.needs_input_grad[1]:
+            dweight = ops.conv1x1_wgrad(x.view(1, 1, b, cin), dy.view(1, 1, b, cout)) * scale
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.conv_same(dy.view(1, 1, b, cout), wp.t().contiguous(), dx.view(1, 1, b, cin), 1)()
+        return dx, dweight, dbias, None
+
+
+def equal_linear(x, weight, bias, lr_mul=1.0):
+    return EqualLinearFunction.apply(x, weight, bias, lr_mul)
 
 
 def pack_equal_conv(weight):

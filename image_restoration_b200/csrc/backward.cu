@@ -13,7 +13,8 @@ constexpr int kBwThreads = 256;
 
 __global__ void __launch_bounds__(kBwThreads) lrelu_bias_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y,
                                                                     uint4* __restrict__ dz, float* __restrict__ dbias,
-                                                                    long long n_pix, int groups, float slope, float scale) {
+                                                                    long long n_pix, int groups, int row_groups, float slope,
+                                                                    float scale) {
   __shared__ float part[kBwThreads][9];  // padded rows: the column sums below walk rows with stride `groups`
   const int g = threadIdx.x % groups;                   // channel group (8 channels) of this thread
   const int lane = threadIdx.x / groups;                // pixel lane inside the CTA
@@ -23,8 +24,9 @@ __global__ void __launch_bounds__(kBwThreads) lrelu_bias_bwd_kernel(const uint4*
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   const float pos = scale, neg = scale * slope;
   for (long long p = (long long)blockIdx.x * lanes + lane; p < n_pix; p += (long long)gridDim.x * lanes) {
-    const long long i = p * groups + g;
-    const uint4 a = __ldcs(dy + i), b = __ldcs(y + i);
+    const long long i = p * row_groups + blockIdx.y * groups + g;   // blockIdx.y: chunk of `groups` channel groups
+    const uint4 a = __ldcs(dy + i);
+    const uint4 b = y ? __ldcs(y + i) : make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);  // no y: all 1.0
     uint4 o;
     const __half2* ah = reinterpret_cast<const __half2*>(&a);
     const __half2* bh = reinterpret_cast<const __half2*>(&b);
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(kBwThreads) lrelu_bias_bwd_kernel(const uint4*
       acc[2 * j] += v0;
       acc[2 * j + 1] += v1;
     }
-    __stcs(dz + i, o);
+    if (dz) __stcs(dz + i, o);
   }
   if (dbias == nullptr) return;
 #pragma unroll
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(kBwThreads) lrelu_bias_bwd_kernel(const uint4*
     const int cg = c >> 3, cj = c & 7;
     float s = 0.f;
     for (int l = 0; l < lanes; ++l) s += part[l * groups + cg][cj];
-    atomicAdd(dbias + c, s);
+    atomicAdd(dbias + blockIdx.y * groups * 8 + c, s);
   }
 }
 
@@ -163,9 +165,8 @@ using namespace b200ir;
 
 extern "C" int b200ir_lrelu_bias_bwd(const void* dy, const void* y, void* dz, float* dbias, int64_t n_pix, int C, float slope,
                                      float scale, void* stream) {
-  B200IR_REQUIRE(n_pix >= 0 && C > 0 && C % 8 == 0 && kBwThreads % (C / 8) == 0,
-                 "lrelu_bias_bwd: C=%d must be 8 * a divisor of %d", C, kBwThreads);
-  B200IR_REQUIRE(n_pix == 0 || (dy && y && dz), "lrelu_bias_bwd: null pointer");
+  B200IR_REQUIRE(n_pix >= 0 && C > 0 && C % 8 == 0, "lrelu_bias_bwd: C=%d must be a multiple of 8", C);
+  B200IR_REQUIRE(n_pix == 0 || (dy && (dz || dbias)), "lrelu_bias_bwd: null pointer");
   const int sms = num_sms();
   if (sms == 0) return 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -174,11 +175,16 @@ extern "C" int b200ir_lrelu_bias_bwd(const void* dy, const void* y, void* dz, fl
     return 1;
   }
   if (n_pix == 0) return 0;
-  const int groups = C / 8, lanes = kBwThreads / groups;
+  // channel groups (8 channels each) are cut into chunks whose size divides the CTA (every thread keeps one group)
+  const int row_groups = C / 8;
+  int groups = kBwThreads;
+  while (row_groups % groups) groups >>= 1;
+  const int chunks = row_groups / groups, lanes = kBwThreads / groups;
   long long grid = (n_pix + lanes - 1) / lanes;
-  if (grid > 8LL * sms) grid = 8LL * sms;  // 8 resident CTAs of 256 threads per SM, one wave
-  lrelu_bias_bwd_kernel<<<(int)grid, kBwThreads, 0, st>>>((const uint4*)dy, (const uint4*)y, (uint4*)dz, dbias, n_pix, groups,
-                                                          slope, scale);
+  const long long cap = (8LL * sms + chunks - 1) / chunks;  // 8 resident CTAs of 256 threads per SM, one wave
+  if (grid > cap) grid = cap;
+  lrelu_bias_bwd_kernel<<<dim3((unsigned)grid, (unsigned)chunks), kBwThreads, 0, st>>>(
+      (const uint4*)dy, (const uint4*)y, (uint4*)dz, dbias, n_pix, groups, row_groups, slope, scale);
   return check_launch("lrelu_bias_bwd");
 }
 

@@ -533,10 +533,11 @@ def conv_dgrad(dz, weight_t, dx, **kw):
 
 
 def lrelu_bias_bwd(dy, y, dz=None, dbias=None, slope=0.2, scale=2 ** 0.5, want_bias=True):
-    """Backward of FusedLeakyReLU + bias gradient (b200ir_lrelu_bias_bwd): dy, y NHWC fp16 [..., C] -> (dz, dbias)."""
-    assert dy.shape == y.shape and dy.dtype == torch.float16 and y.dtype == torch.float16
+    """Backward of FusedLeakyReLU + bias gradient (b200ir_lrelu_bias_bwd): dy, y NHWC fp16 [..., C] -> (dz, dbias).
+    y=None: no activation, only the bias gradient sum_p dy (pass scale=1.0); returns (None, dbias)."""
+    assert dy.dtype == torch.float16 and (y is None or (dy.shape == y.shape and y.dtype == torch.float16))
     c = dy.shape[-1]
-    if dz is None:
+    if dz is None and y is not None:
         dz = torch.empty_like(dy)
     if dbias is None and want_bias:
         dbias = torch.empty(c, device=dy.device, dtype=torch.float32)

@@ -175,7 +175,9 @@ int b200ir_conv_wgrad_view(const b200ir_view* x, const void* dy, float* dw, int 
  * fused_bias_act_kernel.cu:20-50 with act = 3, grad = 1, and the grad_input.sum over batch and pixels of
  * FusedLeakyReLUFunctionBackward.forward):  dz = dy * scale * (y > 0 ? 1 : slope),  dbias[c] = sum_p dz[p][c].
  * dy, y (the saved forward output, the reference's `out`), dz: NHWC fp16 [n_pix][C]; dbias fp32 [C], overwritten, may be
- * NULL (ScaledLeakyReLU, stylegan2_ocr_arch.py:604-606).  C = 8 * a divisor of 256.  dz may alias dy. */
+ * NULL (ScaledLeakyReLU, stylegan2_ocr_arch.py:604-606).  C % 8 == 0.  dz may alias dy.  y == NULL means
+ * "no activation" (every element takes the scale branch) and dz == NULL skips the store: with scale = 1 that is the plain
+ * bias gradient of a conv without activation (dbias[c] = sum_p dy[p][c]). */
 int b200ir_lrelu_bias_bwd(const void* dy, const void* y, void* dz, float* dbias, int64_t n_pix, int C, float slope,
                           float scale, void* stream);
 

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 SQRT2 = math.sqrt(2.0)
 
 
-@pytest.mark.parametrize('n_pix,C', [(1000, 32), (4 * 32 * 96, 256), (7, 512), (12345, 64), (0, 128)])
+@pytest.mark.parametrize('n_pix,C', [(1000, 32), (4 * 32 * 96, 256), (7, 512), (12345, 64), (0, 128), (64, 3072), (300, 24)])
 def test_lrelu_bias_bwd(n_pix, C):
     from image_restoration_b200 import ops
     torch.manual_seed(C + n_pix)
@@ -38,7 +38,7 @@ def test_lrelu_bwd_without_bias_and_bad_channels():
     assert db is None
     assert torch.equal(dz, (dy.float() * torch.where(y.float() > 0, SQRT2, 0.2 * SQRT2)).half())
     with pytest.raises(RuntimeError):
-        ops.lrelu_bias_bwd(torch.zeros(4, 24, device='cuda').half(), torch.zeros(4, 24, device='cuda').half())
+        ops.lrelu_bias_bwd(torch.zeros(4, 12, device='cuda').half(), torch.zeros(4, 12, device='cuda').half())
 
 
 @pytest.mark.parametrize('B,H,W,cin,cout', [(2, 8, 32, 64, 128), (3, 16, 48, 128, 256), (1, 7, 45, 64, 32),
@@ -223,3 +223,51 @@ def test_res_up_block_autograd(B, h, w, cin, cout):
         rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
         print(f'res up block {cin}->{cout} {h}x{w} {name}: rel rms {rel:.3e}')
         assert rel <= 1.5e-3, (name, rel)
+
+
+def test_conv_without_activation_autograd():
+    """Second conv of an SFT head (EqualConv2d 3x3 with bias, no activation; gfpganv1_ocr_arch.py:322-339)."""
+    from image_restoration_b200.backward import conv_layer3x3
+    torch.manual_seed(5)
+    B, H, W, cin, cout = 2, 16, 48, 128, 64
+    weight = torch.randn(cout, cin, 3, 3, device='cuda', requires_grad=True)
+    bias = torch.ones(cout, device='cuda', requires_grad=True)
+    x = torch.randn(B, cin, H, W, device='cuda').half()
+    dy = torch.randn(B, cout, H, W, device='cuda').half()
+    xg = x.permute(0, 2, 3, 1).contiguous().requires_grad_()
+    y = conv_layer3x3(xg, weight, bias, False)
+    y.backward(dy.permute(0, 2, 3, 1).contiguous())
+    scale = 1.0 / math.sqrt(cin * 9)
+    w_ref, b_ref, x_ref = weight.detach().clone().requires_grad_(), bias.detach().clone().requires_grad_(), x.float().requires_grad_()
+    y_ref = F.conv2d(x_ref, w_ref * scale, b_ref, padding=1)
+    y_ref.backward(dy.float())
+    torch.cuda.synchronize()
+    for name, g, r in (('y', y.detach().float().permute(0, 3, 1, 2), y_ref.detach()), ('dx', xg.grad.float().permute(0, 3, 1, 2), x_ref.grad),
+                       ('dweight', weight.grad, w_ref.grad), ('dbias', bias.grad, b_ref.grad)):
+        rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
+        print(f'conv (no activation) {name}: rel rms {rel:.3e}')
+        assert rel <= 1e-3, (name, rel)
+
+
+@pytest.mark.parametrize('B,cin,cout', [(64, 12288, 3072), (8, 256, 512), (3, 64, 128)])
+def test_equal_linear_autograd(B, cin, cout):
+    """final_linear of GFPGANv1OCR (EqualLinear, stylegan2_ocr_arch.py:165-175) forward + backward."""
+    from image_restoration_b200.backward import equal_linear
+    torch.manual_seed(B)
+    weight = torch.randn(cout, cin, device='cuda', requires_grad=True)
+    bias = (0.1 * torch.randn(cout, device='cuda')).requires_grad_()
+    x = torch.randn(B, cin, device='cuda').half()
+    dy = torch.randn(B, cout, device='cuda').half()
+    xg = x.clone().requires_grad_()
+    y = equal_linear(xg, weight, bias)
+    y.backward(dy)
+    scale = 1.0 / math.sqrt(cin)
+    w_ref, b_ref, x_ref = weight.detach().clone().requires_grad_(), bias.detach().clone().requires_grad_(), x.float().requires_grad_()
+    y_ref = F.linear(x_ref, w_ref * scale, b_ref)
+    y_ref.backward(dy.float())
+    torch.cuda.synchronize()
+    for name, g, r in (('y', y.detach().float(), y_ref.detach()), ('dx', xg.grad.float(), x_ref.grad), ('dweight', weight.grad, w_ref.grad),
+                       ('dbias', bias.grad, b_ref.grad)):
+        rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
+        print(f'equal linear {cin}->{cout} B{B} {name}: rel rms {rel:.3e}')
+        assert rel <= 1e-3, (name, rel)
