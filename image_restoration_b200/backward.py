@@ -273,3 +273,76 @@ class ResUpBlockFunction(torch.autograd.Function):
 
 def res_up_block(x, w1, b1, w2, b2, ws):
     return ResUpBlockFunction.apply(x, w1, b1, w2, b2, ws)
+
+
+class FirstConvFunction(torch.autograd.Function):
+    """conv_body_first = ConvLayer(3, C, 1, bias=True, activate=True) over the fp32 NCHW input image (no input gradient:
+    the image is data)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        b, _, h, w = x.shape
+        cout = weight.shape[0]
+        scale = 1.0 / math.sqrt(3.0)
+        y = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float16)
+        ops.first_conv(x, (weight.detach().view(cout, 3) * scale).contiguous(), bias.detach().float().contiguous(), y)
+        ctx.save_for_backward(x, y)
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dz, dbias = ops.lrelu_bias_bwd(dy.contiguous(), y)
+        dw = ops.first_conv_wgrad(x, dz) * ctx.scale
+        return None, dw.view(-1, 3, 1, 1), dbias
+
+
+class AddFunction(torch.autograd.Function):
+    """feat + unet_skips[i] (gfpganv1_ocr_arch.py:368) on the b200ir_add kernel; the gradient goes to both inputs."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = torch.empty_like(a)
+        ops.add(a, b, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return d, d
+
+
+def unet_forward(sd, x, different_w=True, num_style_feat=256):
+    """The trainable part of GFPGANv1OCR.forward (gfpganv1_ocr_arch.py:352-378; everything the optimiser touches when
+    fix_decoder=True): U-Net encoder -> style code, U-Net decoder -> SFT conditions, on the B200 kernels with autograd
+    through the Function wrappers above.  `sd`: tensors under the reference's state_dict names (fp32 CUDA parameters);
+    x fp32 NCHW [B,3,H,W].  Returns (style_code fp16 [B, num_latent, num_style_feat] or [B, n], conditions: list of NHWC fp16
+    tensors scale0, shift0, scale1, ...)."""
+    feat = FirstConvFunction.apply(x.contiguous(), sd['conv_body_first.0.weight'], sd['conv_body_first.1.bias'])
+    levels = 0
+    while f'conv_body_down.{levels}.conv1.0.weight' in sd:
+        levels += 1
+    skips = []
+    for i in range(levels):
+        pre = f'conv_body_down.{i}'
+        feat = res_block(feat, sd[f'{pre}.conv1.0.weight'], sd[f'{pre}.conv1.1.bias'], sd[f'{pre}.conv2.1.weight'],
+                         sd[f'{pre}.conv2.2.bias'], sd[f'{pre}.skip.1.weight'])
+        skips.insert(0, feat)
+    feat = conv_layer3x3(feat, sd['final_conv.0.weight'], sd['final_conv.1.bias'])
+    b, h, w, c = feat.shape
+    # final_linear reads the NCHW flattening (gfpganv1_ocr_arch.py:361): permute its columns to the NHWC order instead
+    wl = sd['final_linear.weight']
+    wl = wl.view(wl.shape[0], c, h, w).permute(0, 2, 3, 1).reshape(wl.shape[0], -1)
+    style_code = equal_linear(feat.reshape(b, -1), wl, sd['final_linear.bias'])
+    if different_w:
+        style_code = style_code.view(b, -1, num_style_feat)
+    conditions = []
+    for i in range(levels):
+        pre = f'conv_body_up.{i}'
+        feat = AddFunction.apply(feat, skips[i])
+        feat = res_up_block(feat, sd[f'{pre}.conv1.0.weight'], sd[f'{pre}.conv1.1.bias'], sd[f'{pre}.conv2.weight'],
+                            sd[f'{pre}.conv2.activation.bias'], sd[f'{pre}.skip.weight'])
+        for head in ('condition_scale', 'condition_shift'):
+            hid = conv_layer3x3(feat, sd[f'{head}.{i}.0.weight'], sd[f'{head}.{i}.0.bias'])
+            conditions.append(conv_layer3x3(hid, sd[f'{head}.{i}.2.weight'], sd[f'{head}.{i}.2.bias'], False))
+    return style_code, conditions

@@ -159,6 +159,42 @@ __global__ void __launch_bounds__(kBwThreads) bilinear_up2_adjoint_kernel(const 
   }
 }
 
+// Weight gradient of conv_body_first (ConvLayer(3, C, 1): EqualConv2d 1x1 over the fp32 NCHW input image,
+// stylegan2_ocr_arch.py:658-705): dw[c][k] = sum_p dz[p][c] * x[b(p)][k][hw(p)], k = 0..2.  Same thread layout as
+// lrelu_bias_bwd_kernel (one group of 8 channels per thread, strided pixels), 24 partial sums per thread.
+__global__ void __launch_bounds__(kBwThreads) first_conv_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ dz,
+                                                                      float* __restrict__ dw, long long n_pix, int HW,
+                                                                      int groups) {
+  __shared__ float part[kBwThreads][25];
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = kBwThreads / groups;
+  float acc[8][3];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0.f;
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < n_pix; p += (long long)gridDim.x * lanes) {
+    const uint4 a = __ldcs(dz + p * groups + g);
+    const float* xp = x + (p / HW) * 3 * HW + (p % HW);
+    const float x0 = __ldg(xp), x1 = __ldg(xp + HW), x2 = __ldg(xp + 2 * HW);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 d = __half22float2(ah[j]);
+      acc[2 * j][0] += d.x * x0, acc[2 * j][1] += d.x * x1, acc[2 * j][2] += d.x * x2;
+      acc[2 * j + 1][0] += d.y * x0, acc[2 * j + 1][1] += d.y * x1, acc[2 * j + 1][2] += d.y * x2;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) part[threadIdx.x][j * 3 + k] = acc[j][k];
+  __syncthreads();
+  for (int e = threadIdx.x; e < groups * 24; e += kBwThreads) {  // e = channel * 3 + k inside this CTA's channel range
+    const int cg = e / 24, r = e % 24;
+    float sum = 0.f;
+    for (int l = 0; l < lanes; ++l) sum += part[l * groups + cg][r];
+    atomicAdd(dw + e, sum);
+  }
+}
+
 }  // namespace b200ir
 
 using namespace b200ir;
@@ -224,4 +260,22 @@ extern "C" int b200ir_bilinear_up2_adjoint(const void* d, void* out, int B, int 
   bilinear_up2_adjoint_kernel<<<(int)grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const uint4*)d, (uint4*)out, B, h, w, C / 8, scale);
   return check_launch("bilinear_up2_adjoint");
+}
+
+extern "C" int b200ir_first_conv_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, int cout, void* stream) {
+  B200IR_REQUIRE(x && dz && dw && B > 0 && H > 0 && W > 0 && cout > 0 && cout % 8 == 0 && kBwThreads % (cout / 8) == 0,
+                 "first_conv_wgrad: cout=%d must be 8 * a divisor of %d", cout, kBwThreads);
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(dw, 0, sizeof(float) * cout * 3, st) != cudaSuccess) {
+    set_error("first_conv_wgrad: cudaMemsetAsync failed");
+    return 1;
+  }
+  const long long n_pix = (long long)B * H * W;
+  const int groups = cout / 8, lanes = kBwThreads / groups;
+  long long grid = (n_pix + lanes - 1) / lanes;
+  if (grid > 4LL * sms) grid = 4LL * sms;
+  first_conv_wgrad_kernel<<<(int)grid, kBwThreads, 0, st>>>(x, (const uint4*)dz, dw, n_pix, H * W, groups);
+  return check_launch("first_conv_wgrad");
 }

@@ -603,3 +603,13 @@ def bilinear_up2_adjoint(d, out, scale=1.0):
     b, h, w, c = out.shape
     assert tuple(d.shape) == (b, 2 * h, 2 * w, c)
     check(_lib.lib().b200ir_bilinear_up2_adjoint(_ptr(d), _ptr(out), b, h, w, c, scale, _stream()), 'bilinear_up2_adjoint')
+
+
+def first_conv_wgrad(x, dz):
+    """Weight gradient of first_conv: x fp32 NCHW [B,3,H,W], dz NHWC fp16 [B,H,W,Cout] -> fp32 [Cout, 3]."""
+    b, _, h, w = x.shape
+    cout = dz.shape[3]
+    _req(x, torch.float32, 'x')
+    dw = torch.empty(cout, 3, device=x.device, dtype=torch.float32)
+    check(_lib.lib().b200ir_first_conv_wgrad(_ptr(x), _ptr(dz), _ptr(dw), b, h, w, cout, _stream()), 'first_conv_wgrad')
+    return dw

@@ -197,6 +197,11 @@ int b200ir_fir_down2_adjoint(const void* d, const void* add, void* out, int B, i
  * clamp(2i - 1 + t, 0, 2n - 1). */
 int b200ir_bilinear_up2_adjoint(const void* d, void* out, int B, int h, int w, int C, float scale, void* stream);
 
+/* Weight gradient of b200ir_first_conv (conv_body_first, the 1x1 EqualConv2d over the 3-channel input image): x fp32 NCHW
+ * [B][3][H][W], dz NHWC fp16 [B][H][W][cout] (after b200ir_lrelu_bias_bwd) -> dw fp32 [cout][3], overwritten (gradient
+ * w.r.t. the scaled weights the forward entry point takes).  cout = 8 * a divisor of 256. */
+int b200ir_first_conv_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, int cout, void* stream);
+
 /* One torch.optim.Adam step (no amsgrad; optimizer_g / optimizer_d of basicsr/models/gfpgan_model.py:217-248) over a flat
  * fp32 parameter buffer, fused with the gradient scaling of the data-parallel average (grad_scale = 1 / world) and,
  * when ema != NULL, with the EMA update of BaseModel.model_ema (basicsr/models/base_model.py:50-57):

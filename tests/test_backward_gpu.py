@@ -271,3 +271,59 @@ def test_equal_linear_autograd(B, cin, cout):
         rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
         print(f'equal linear {cin}->{cout} B{B} {name}: rel rms {rel:.3e}')
         assert rel <= 1e-3, (name, rel)
+
+
+def test_unet_forward_backward_against_oracle():
+    """Trainable part of GFPGANv1OCR (U-Net encoder -> style code, decoder -> SFT conditions; everything optimizer_g updates
+    with fix_decoder=True) through backward.unet_forward, against torch.autograd over the fp32 oracle on the same seeded
+    stock-init parameters.  The fp16 forward flips the leaky-ReLU branch of ~2e-4 of the pre-activations relative to an
+    fp32 forward (each flip changes that element's gradient five-fold), so the end-to-end gradient bound is a few per cent
+    relative RMS plus a cosine; the per-block tests above pin every kernel to 5e-4 with the branches held equal."""
+    from image_restoration_b200 import GFPGANv1OCR
+    from image_restoration_b200.backward import unet_forward
+    from oracle.gfpgan_ocr_oracle import OcrNetConfig, gfpgan_ocr_forward
+    from tests.helpers import KW
+    torch.manual_seed(0)
+    W, H, B = 384, 128, 2
+    net = GFPGANv1OCR(input_width=W, input_height=H, decoder_load_path=None, fix_decoder=True, **KW)
+    sd = {k: v.detach().clone().cuda() for k, v in net.state_dict().items()}
+    trainable = [k for k in sd if k.split('.')[0] in ('conv_body_first', 'conv_body_down', 'final_conv', 'final_linear', 'conv_body_up',
+                                                       'condition_scale', 'condition_shift')]
+    sd_a = {k: (v.clone().requires_grad_() if k in trainable else v) for k, v in sd.items()}
+    sd_b = {k: (v.clone().requires_grad_() if k in trainable else v) for k, v in sd.items()}
+    x = (torch.rand(B, 3, H, W, device='cuda') * 2 - 1)
+
+    style, conds = unet_forward(sd_a, x, different_w=True, num_style_feat=KW['num_style_feat'])
+    cfg = OcrNetConfig(input_width=W, input_height=H, **KW)
+    taps = {}
+    gfpgan_ocr_forward.__wrapped__(sd_b, cfg, x, return_rgb=False, taps=taps)    # the oracle without its torch.no_grad()
+    L = cfg.num_levels
+    ref_conds = [taps[f'{n}{i}'] for i in range(L) for n in ('scale', 'shift')]
+    g = torch.Generator(device='cuda').manual_seed(1)
+    loss_a = loss_b = 0.0
+    cot = torch.randn(style.shape, device='cuda', generator=g).half()
+    loss_a = loss_a + (style.float() * cot.float()).sum()
+    loss_b = loss_b + (taps['style_code'] * cot.float()).sum()
+    fwd = [('style_code', style.detach().float(), taps['style_code'].detach())]
+    for i, (c, r) in enumerate(zip(conds, ref_conds)):
+        cot = torch.randn(c.shape, device='cuda', generator=g).half()
+        loss_a = loss_a + (c.float() * cot.float()).sum()
+        loss_b = loss_b + (r * cot.float().permute(0, 3, 1, 2)).sum()
+        fwd.append((f'cond{i}', c.detach().float().permute(0, 3, 1, 2), r.detach()))
+    loss_a.backward()
+    loss_b.backward()
+    torch.cuda.synchronize()
+    for name, a, r in fwd:
+        rel = ((a - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
+        print(f'unet forward {name}: rel rms {rel:.3e}')
+        assert rel <= 5e-3, (name, rel)
+    worst = 0.0
+    for k in trainable:
+        ga, gb = sd_a[k].grad, sd_b[k].grad
+        assert ga is not None and gb is not None and ga.shape == gb.shape, k
+        rel = ((ga - gb).double().pow(2).mean().sqrt() / gb.double().pow(2).mean().sqrt().clamp_min(1e-30)).item()
+        cos = F.cosine_similarity(ga.double().flatten(), gb.double().flatten(), dim=0).item()
+        worst = max(worst, rel)
+        print(f'unet grad {k}: rel rms {rel:.3e} cos {cos:.6f}')
+        assert rel <= 4e-2 and cos >= 0.999, (k, rel, cos)
+    print(f'unet backward: {len(trainable)} parameter tensors, worst rel rms {worst:.3e}')
