@@ -82,18 +82,24 @@ __global__ void __launch_bounds__(kPwThreads) first_conv_staged_kernel(const flo
   for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * 3 + i] = bias[i];
   __syncthreads();
   const int cpp = cout >> 3;                                              // chunks per pixel: 2, 4 or 8
+  const int cs = 31 - __clz(cpp), gs = 3 - cs;                            // shifts: q / cpp, px / (8 / cpp)
   const int t = threadIdx.x;
-  const int swz = (t / (8 / cpp)) & (cpp - 1);
+  const int swz = (t >> gs) & (cpp - 1);
   const long long base0 = (long long)blockIdx.x * (kPwThreads * kFcPix);
   float r[kFcPix], g[kFcPix], bl[kFcPix];
 #pragma unroll
+  // image index / pixel of this thread's first pixel by one 32-bit division (n_pix < 2^31 is checked by the launcher); the
+  // other rounds step from it
+  unsigned img = (unsigned)(base0 + t) / (unsigned)HW, pix = (unsigned)(base0 + t) - img * (unsigned)HW;
+#pragma unroll
   for (int k = 0; k < kFcPix; ++k) {                                      // all 3 * kFcPix loads in flight before any use
-    const long long idx = base0 + k * kPwThreads + t;
     r[k] = g[k] = bl[k] = 0.f;
-    if (idx < n_pix) {
-      const float* xp = x + (idx / HW) * 3 * HW + (idx % HW);
+    if (base0 + k * kPwThreads + t < n_pix) {
+      const float* xp = x + ((size_t)img * 3) * HW + pix;
       r[k] = __ldg(xp), g[k] = __ldg(xp + HW), bl[k] = __ldg(xp + 2 * HW);
     }
+    pix += kPwThreads;
+    while (pix >= (unsigned)HW) pix -= HW, ++img;
   }
 #pragma unroll
   for (int k = 0; k < kFcPix; ++k) {
@@ -105,20 +111,21 @@ __global__ void __launch_bounds__(kPwThreads) first_conv_staged_kernel(const flo
       __half2* h = reinterpret_cast<__half2*>(&q);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        // same expression as first_conv_kernel: the two kernels (and earlier builds) round identically
         const float* wc = sw + (j * 8 + 2 * c) * 3;
         const float* bc = sw + cout * 3 + j * 8 + 2 * c;
         h[c] = f2h2_sat(lrelu_s(wc[0] * r[k] + wc[1] * g[k] + wc[2] * bl[k] + bc[0]),
                         lrelu_s(wc[3] * r[k] + wc[4] * g[k] + wc[5] * bl[k] + bc[1]));
       }
-      stage[t * cpp + (j ^ swz)] = q;
+      stage[(t << cs) + (j ^ swz)] = q;
     }
     __syncthreads();
     const long long rem = n_pix - base;
     const int chunks = (int)(rem < kPwThreads ? rem : kPwThreads) * cpp;
     uint4* dst = reinterpret_cast<uint4*>(out) + base * cpp;
     for (int q = t; q < chunks; q += kPwThreads) {
-      const int px = q / cpp, j = q & (cpp - 1);
-      __stcs(dst + q, stage[px * cpp + (j ^ ((px / (8 / cpp)) & (cpp - 1)))]);
+      const int px = q >> cs, j = q & (cpp - 1);
+      __stcs(dst + q, stage[(px << cs) + (j ^ ((px >> gs) & (cpp - 1)))]);
     }
   }
 }
@@ -948,7 +955,7 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
   B200IR_REQUIRE(x && w && bias && out, "first_conv: null pointer");
   B200IR_REQUIRE(cout % 8 == 0 && cout <= 512, "first_conv: cout=%d", cout);
   const long long n = (long long)B * H * W;
-  if (cout == 16 || cout == 32 || cout == 64) {
+  if ((cout == 16 || cout == 32 || cout == 64) && n < (1LL << 31)) {
     const size_t smem = (size_t)kPwThreads * cout * 2 + cout * 4 * sizeof(float);  // <= 33 KB
     first_conv_staged_kernel<<<grid_for((n + kFcPix - 1) / kFcPix), kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
     return check_launch("first_conv");
