@@ -62,12 +62,12 @@ __global__ void __launch_bounds__(kBwThreads) fir_down2_adjoint_kernel(const uin
                                                                        uint4* __restrict__ out, int B, int h, int w, int groups) {
   const long long n = (long long)B * h * w * groups;
   for (long long idx = (long long)blockIdx.x * kBwThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kBwThreads) {
-    const int g = (int)(idx % groups);
-    long long r = idx / groups;
-    const int j = (int)(r % w);
-    r /= w;
-    const int i = (int)(r % h);
-    const int b = (int)(r / h);
+    unsigned r = (unsigned)idx / (unsigned)groups;   // 32-bit index arithmetic: the launcher keeps n below 2^31
+    const int g = (int)((unsigned)idx - r * (unsigned)groups);
+    const unsigned r2 = r / (unsigned)w;
+    const int j = (int)(r - r2 * (unsigned)w);
+    const int b = (int)(r2 / (unsigned)h);
+    const int i = (int)(r2 - (unsigned)b * (unsigned)h);
     float v[3][3][8];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
@@ -124,12 +124,12 @@ __global__ void __launch_bounds__(kBwThreads) bilinear_up2_adjoint_kernel(const 
                                                                           int B, int h, int w, int groups, float scale) {
   const long long n = (long long)B * h * w * groups;
   for (long long idx = (long long)blockIdx.x * kBwThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kBwThreads) {
-    const int g = (int)(idx % groups);
-    long long r = idx / groups;
-    const int j = (int)(r % w);
-    r /= w;
-    const int i = (int)(r % h);
-    const int b = (int)(r / h);
+    unsigned r = (unsigned)idx / (unsigned)groups;   // 32-bit index arithmetic: the launcher keeps n below 2^31
+    const int g = (int)((unsigned)idx - r * (unsigned)groups);
+    const unsigned r2 = r / (unsigned)w;
+    const int j = (int)(r - r2 * (unsigned)w);
+    const int b = (int)(r2 / (unsigned)h);
+    const int i = (int)(r2 - (unsigned)b * (unsigned)h);
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -239,7 +239,8 @@ extern "C" int b200ir_fir_pad11(const void* in, void* out, int B, int H, int W, 
 }
 
 extern "C" int b200ir_fir_down2_adjoint(const void* d, const void* add, void* out, int B, int h, int w, int C, void* stream) {
-  B200IR_REQUIRE(d && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0, "fir_down2_adjoint: bad arguments");
+  B200IR_REQUIRE(d && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0 && (long long)B * h * w * (C / 8) < (1LL << 31),
+                 "fir_down2_adjoint: bad arguments");
   const int sms = num_sms();
   if (sms == 0) return 1;
   const long long n = (long long)B * h * w * (C / 8);
@@ -251,7 +252,8 @@ extern "C" int b200ir_fir_down2_adjoint(const void* d, const void* add, void* ou
 }
 
 extern "C" int b200ir_bilinear_up2_adjoint(const void* d, void* out, int B, int h, int w, int C, float scale, void* stream) {
-  B200IR_REQUIRE(d && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0, "bilinear_up2_adjoint: bad arguments");
+  B200IR_REQUIRE(d && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0 && (long long)B * h * w * (C / 8) < (1LL << 31),
+                 "bilinear_up2_adjoint: bad arguments");
   const int sms = num_sms();
   if (sms == 0) return 1;
   const long long n = (long long)B * h * w * (C / 8);

@@ -657,10 +657,13 @@ __global__ void rgb_combine4_kernel(const float* __restrict__ part, int n_parts,
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long HW = (long long)h * w;
   if (idx >= (long long)B * h * wq) return;
-  const int xq = (int)(idx % wq);
-  const long long r = idx / wq;
-  const int y = (int)(r % h);
-  const int b = (int)(r / h);
+  // 32-bit index arithmetic (the launcher keeps B * h * w / 4 below 2^31): 64-bit divisions by run-time values cost
+  // more instructions than the rest of the thread
+  const unsigned i32 = (unsigned)idx;
+  const unsigned r = i32 / (unsigned)wq;
+  const int xq = (int)(i32 - r * (unsigned)wq);
+  const int b = (int)(r / (unsigned)h);
+  const int y = (int)(r - (unsigned)b * (unsigned)h);
   const int x0 = xq * 4;
   const long long p = (long long)y * w + x0;
   float o[3][4];
@@ -1147,7 +1150,8 @@ extern "C" int b200ir_rgb_combine(const float* part, int n_parts, const float* b
                                   int B, int h, int w, void* stream) {
   B200IR_REQUIRE(part && bias && rgb && n_parts >= 1 && (skip == nullptr || (h % 2 == 0 && w % 2 == 0)),
                  "rgb_combine: bad arguments");
-  if (w % 4 == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(rgb)) & 15) == 0)
+  if (w % 4 == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(rgb)) & 15) == 0 &&
+      (long long)B * h * (w / 4) < (1LL << 31))
     rgb_combine4_kernel<<<grid_for((long long)B * h * (w / 4)), kPwThreads, 0, STREAM>>>(part, n_parts, bias, skip, rgb, B,
                                                                                         h, w);
   else
