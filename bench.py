@@ -347,6 +347,29 @@ def main():
                 'config': f'StyleGAN2Discriminator(input_width={W}, input_height={H}, channel_multiplier=1) forward, eager '
                           'launches'}
         del netd
+        # trainable part of net_g (U-Net encoder -> style code, decoder -> SFT conditions) forward + backward: the part of
+        # the training-step row that exists; the frozen decoder's input gradients and the losses do not yet
+        from image_restoration_b200.backward import unet_forward
+        names = ('conv_body_first', 'conv_body_down', 'final_conv', 'final_linear', 'conv_body_up', 'condition_scale',
+                 'condition_shift')
+        sd_t = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items() if k.split('.')[0] in names}
+        xt = torch.rand(B, 3, H, W, device=dev) * 2 - 1
+        cots = []
+
+        def unet_step():
+            for v in sd_t.values():
+                v.grad = None
+            sc, cd = unet_forward(sd_t, xt, different_w=True, num_style_feat=NET_KW['num_style_feat'])
+            if not cots:
+                cots.extend(torch.randn_like(t) for t in [sc] + cd)
+            torch.autograd.backward([sc] + cd, cots)
+        ms_t = timed(unet_step, 4, 2) / 4
+        unet_train = {'crops_per_s': B / (ms_t / 1e3), 'ms_per_batch': ms_t, 'batch': B,
+                      'parameters': sum(v.numel() for v in sd_t.values()),
+                      'config': 'U-Net encoder + decoder + SFT heads + final_linear of GFPGANv1OCR (everything optimizer_g updates '
+                                'with fix_decoder=True), forward + backward through backward.unet_forward, eager launches '
+                                '(host-bound at this batch; 3.4 k crops/s at B=256)'}
+        del sd_t, xt, cots
         degr['full_chain'] = {'kernel': 'degrade_full_kernel', 'crops_per_s': DB / (ms_full / 1e3), 'ms_per_batch': ms_full,
                               'batch': DB, 'achieved_gbs': alg / ms_full / 1e6,
                               'stages': 'blur (iso/aniso/motion/average/median/bilateral/pyblur, kernel_list and kernel_prob of '
@@ -410,6 +433,7 @@ def main():
             line['degradation'] = degr
             line['tiled_full_frame'] = tiled
             line['discriminator_forward'] = disc
+            line['unet_forward_backward'] = unet_train
         if pw_report:
             top = pw_report[0]
             line['roofline_hbm'] = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top['achieved_gbs'],
