@@ -72,6 +72,7 @@ __global__ void first_conv_kernel(const float* __restrict__ x, const float* __re
 // bank groups), then the CTA writes its 256 pixels as one contiguous run of 16-byte chunks: full 128-byte lines per
 // warp store instead of 32 partial lines.  Four rounds of 256 pixels per CTA with all input loads issued up front.
 constexpr int kFcPix = 4;  // pixels per thread (rounds of 256 pixels per CTA)
+template <int kCpp>  // 16-byte chunks per pixel = cout / 8: 2, 4 or 8
 __global__ void __launch_bounds__(kPwThreads) first_conv_staged_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                        const float* __restrict__ bias, __half* __restrict__ out,
                                                                        long long n_pix, int HW, int cout) {
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(kPwThreads) first_conv_staged_kernel(const flo
   for (int i = threadIdx.x; i < cout * 3; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * 3 + i] = bias[i];
   __syncthreads();
-  const int cpp = cout >> 3;                                              // chunks per pixel: 2, 4 or 8
-  const int cs = 31 - __clz(cpp), gs = 3 - cs;                            // shifts: q / cpp, px / (8 / cpp)
+  constexpr int cpp = kCpp;
+  constexpr int cs = kCpp == 2 ? 1 : (kCpp == 4 ? 2 : 3), gs = 3 - cs;    // shifts: q / cpp, px / (8 / cpp)
   const int t = threadIdx.x;
   const int swz = (t >> gs) & (cpp - 1);
   const long long base0 = (long long)blockIdx.x * (kPwThreads * kFcPix);
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(kPwThreads) first_conv_staged_kernel(const flo
     const long long base = base0 + k * kPwThreads;
     if (base >= n_pix) break;
     if (k) __syncthreads();                                               // previous round's copy-out done
+#pragma unroll
     for (int j = 0; j < cpp; ++j) {
       uint4 q;
       __half2* h = reinterpret_cast<__half2*>(&q);
@@ -960,7 +962,13 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
   const long long n = (long long)B * H * W;
   if ((cout == 16 || cout == 32 || cout == 64) && n < (1LL << 31)) {
     const size_t smem = (size_t)kPwThreads * cout * 2 + cout * 4 * sizeof(float);  // <= 33 KB
-    first_conv_staged_kernel<<<grid_for((n + kFcPix - 1) / kFcPix), kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
+    const int grid = grid_for((n + kFcPix - 1) / kFcPix);
+    if (cout == 16)
+      first_conv_staged_kernel<2><<<grid, kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
+    else if (cout == 32)
+      first_conv_staged_kernel<4><<<grid, kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
+    else
+      first_conv_staged_kernel<8><<<grid, kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
     return check_launch("first_conv");
   }
   first_conv_kernel<<<grid_for(n), kPwThreads, cout * 4 * sizeof(float), STREAM>>>(x, w, bias, (__half*)out, B, H * W,
