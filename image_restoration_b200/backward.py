@@ -312,12 +312,47 @@ class AddFunction(torch.autograd.Function):
         return d, d
 
 
-def unet_forward(sd, x, different_w=True, num_style_feat=256):
+class ToRGBHeadFunction(torch.autograd.Function):
+    """toRGB[i] of the U-Net (EqualConv2d(C, 3, 1) with bias, gfpganv1_ocr_arch.py:308-311, 377-378), the heads of the image
+    pyramid loss: the three output channels are padded to 16 so that the 1x1 conv, its input gradient and its weight
+    gradient run on the GEMM kernels.  Returns NHWC fp16 [B,h,w,16]; channels 3.. are zero and carry no gradient."""
+
+    PAD = 16
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        b, h, w, cin = x.shape
+        pad = ToRGBHeadFunction.PAD
+        scale = 1.0 / math.sqrt(cin)
+        wp = torch.zeros(pad, cin, device=x.device, dtype=torch.float16)
+        wp[:3] = (weight.detach().view(3, cin) * scale).to(torch.float16)
+        bp = torch.zeros(pad, device=x.device, dtype=torch.float32)
+        bp[:3] = bias.detach().float()
+        y = torch.empty(b, h, w, pad, device=x.device, dtype=torch.float16)
+        ops.conv_same(x, wp, y, 1, bias=bp)()
+        ctx.save_for_backward(x, wp)
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wp = ctx.saved_tensors
+        cin = x.shape[3]
+        dy = dy.contiguous()
+        dbias = ops.lrelu_bias_bwd(dy, None, scale=1.0)[1][:3]
+        dweight = (ops.conv1x1_wgrad(x, dy)[:3] * ctx.scale).reshape(3, cin, 1, 1)
+        dx = torch.empty_like(x)
+        ops.conv_same(dy, wp.t().contiguous(), dx, 1)()
+        return dx, dweight, dbias
+
+
+def unet_forward(sd, x, different_w=True, num_style_feat=256, return_rgb=False):
     """The trainable part of GFPGANv1OCR.forward (gfpganv1_ocr_arch.py:352-378; everything the optimiser touches when
     fix_decoder=True): U-Net encoder -> style code, U-Net decoder -> SFT conditions, on the B200 kernels with autograd
     through the Function wrappers above.  `sd`: tensors under the reference's state_dict names (fp32 CUDA parameters);
     x fp32 NCHW [B,3,H,W].  Returns (style_code fp16 [B, num_latent, num_style_feat] or [B, n], conditions: list of NHWC fp16
-    tensors scale0, shift0, scale1, ...)."""
+    tensors scale0, shift0, scale1, ...); with return_rgb also out_rgbs, the toRGB heads of the image pyramid loss
+    (gfpgan_model.py:531-536), NHWC fp16 [B,h,w,16] with the image in channels 0..2."""
     feat = FirstConvFunction.apply(x.contiguous(), sd['conv_body_first.0.weight'], sd['conv_body_first.1.bias'])
     levels = 0
     while f'conv_body_down.{levels}.conv1.0.weight' in sd:
@@ -336,7 +371,7 @@ def unet_forward(sd, x, different_w=True, num_style_feat=256):
     style_code = equal_linear(feat.reshape(b, -1), wl, sd['final_linear.bias'])
     if different_w:
         style_code = style_code.view(b, -1, num_style_feat)
-    conditions = []
+    conditions, out_rgbs = [], []
     for i in range(levels):
         pre = f'conv_body_up.{i}'
         feat = AddFunction.apply(feat, skips[i])
@@ -345,4 +380,8 @@ def unet_forward(sd, x, different_w=True, num_style_feat=256):
         for head in ('condition_scale', 'condition_shift'):
             hid = conv_layer3x3(feat, sd[f'{head}.{i}.0.weight'], sd[f'{head}.{i}.0.bias'])
             conditions.append(conv_layer3x3(hid, sd[f'{head}.{i}.2.weight'], sd[f'{head}.{i}.2.bias'], False))
+        if return_rgb:
+            out_rgbs.append(ToRGBHeadFunction.apply(feat, sd[f'toRGB.{i}.weight'], sd[f'toRGB.{i}.bias']))
+    if return_rgb:
+        return style_code, conditions, out_rgbs
     return style_code, conditions
