@@ -78,6 +78,7 @@ SIGNATURES = {
     'b200ir_fir_down2_adjoint': [_P, _P, _P, _I, _I, _I, _I, _P],
     'b200ir_bilinear_up2_adjoint': [_P, _P, _I, _I, _I, _I, _F, _P],
     'b200ir_first_conv_wgrad': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_minibatch_stddev_bwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_adam_step': [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _F, _P],
     'b200ir_minibatch_stddev': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_f32_to_input': [_P, _P, _I, _I, _I, _I, _P],

@@ -76,7 +76,7 @@ class EqualLinearFunction(torch.autograd.Function):
     'pixels'; the weight gradient dW = dy^T x is the wgrad kernel with the batch laid out along the pixel axis."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, lr_mul=1.0):
+    def forward(ctx, x, weight, bias, lr_mul=1.0, activate=False):
         if not x.is_cuda:
             raise RuntimeError('image_restoration_b200.backward.EqualLinearFunction needs CUDA tensors (no CPU path)')
         b, cin = x.shape
@@ -84,31 +84,36 @@ class EqualLinearFunction(torch.autograd.Function):
         scale = lr_mul / math.sqrt(cin)
         wp = (weight.detach() * scale).to(torch.float16).contiguous()
         y = torch.empty(b, cout, device=x.device, dtype=torch.float16)
-        ops.conv_same(x.view(1, 1, b, cin), wp, y.view(1, 1, b, cout), 1, bias=(bias.detach().float() * lr_mul).contiguous())()
-        ctx.save_for_backward(x, wp)
+        # activate: EqualLinear(activation='fused_lrelu') = fused_leaky_relu(out, bias * lr_mul) (stylegan2_arch.py:165-175)
+        ops.conv_same(x.view(1, 1, b, cin), wp, y.view(1, 1, b, cout), 1, bias=(bias.detach().float() * lr_mul).contiguous(),
+                      act=activate)()
+        ctx.save_for_backward(x, wp, y if activate else None)
         ctx.consts = (scale, lr_mul)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, wp = ctx.saved_tensors
+        x, wp, y = ctx.saved_tensors
         scale, lr_mul = ctx.consts
         b, cin = x.shape
         cout = wp.shape[0]
         dy = dy.contiguous()
         dx = dweight = dbias = None
-        if ctx.needs_input_grad[2]:
+        if y is not None:
+            dy, dbias = ops.lrelu_bias_bwd(dy, y)
+            dbias = dbias * lr_mul
+        elif ctx.needs_input_grad[2]:
             dbias = ops.lrelu_bias_bwd(dy, None, scale=1.0)[1] * lr_mul
         if ctx.needs_input_grad[1]:
             dweight = ops.conv1x1_wgrad(x.view(1, 1, b, cin), dy.view(1, 1, b, cout)) * scale
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             ops.conv_same(dy.view(1, 1, b, cout), wp.t().contiguous(), dx.view(1, 1, b, cin), 1)()
-        return dx, dweight, dbias, None
+        return dx, dweight, dbias, None, None
 
 
-def equal_linear(x, weight, bias, lr_mul=1.0):
-    return EqualLinearFunction.apply(x, weight, bias, lr_mul)
+def equal_linear(x, weight, bias, lr_mul=1.0, activate=False):
+    return EqualLinearFunction.apply(x, weight, bias, lr_mul, activate)
 
 
 def pack_equal_conv(weight):
@@ -385,3 +390,62 @@ def unet_forward(sd, x, different_w=True, num_style_feat=256, return_rgb=False):
     if return_rgb:
         return style_code, conditions, out_rgbs
     return style_code, conditions
+
+
+
+class MinibatchStddevFunction(torch.autograd.Function):
+    """Minibatch standard deviation of the discriminator (stylegan2_arch.py:791-801): x NHWC fp16 [B,h,w,C] -> [B,h,w,c_pad]
+    = x, the group statistic in channel C, zeros up to c_pad (a multiple of 16, the next conv's input block)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        b, h, w, c = x.shape
+        c_pad = (c + 1 + 15) // 16 * 16
+        out = torch.zeros(b, h, w, c_pad, device=x.device, dtype=torch.float16)
+        s_buf = torch.empty(b // group, device=x.device, dtype=torch.float32)
+        from . import _lib
+        _lib.check(_lib.lib().b200ir_minibatch_stddev(ops._ptr(x), ops._ptr(s_buf), ops._ptr(out), b, h * w, c, c_pad, group,
+                                                      ops._stream()), 'minibatch_stddev')
+        ctx.save_for_backward(x)
+        ctx.group = group
+        return out
+
+    @staticmethod
+    def backward(ctx, dcat):
+        (x,) = ctx.saved_tensors
+        b, h, w, c = x.shape
+        g = ctx.group
+        dcat = dcat.contiguous()
+        ds = dcat[..., c].float().view(g, b // g, h * w).sum(dim=(0, 2)).contiguous()      # B * h * w numbers: host-side glue
+        dx = torch.empty_like(x)
+        from . import _lib
+        _lib.check(_lib.lib().b200ir_minibatch_stddev_bwd(ops._ptr(x), ops._ptr(dcat), ops._ptr(ds), ops._ptr(dx), b, h * w, c,
+                                                          dcat.shape[3], g, ops._stream()), 'minibatch_stddev_bwd')
+        return dx, None
+
+
+def disc_forward(sd, x, stddev_group=4):
+    """StyleGAN2Discriminator.forward (stylegan2_arch.py:788-805; network_d of the training YAMLs) with autograd through
+    the Function wrappers: `sd` = fp32 CUDA parameters under the reference's state_dict names, x fp32 NCHW [B,3,H,W] ->
+    scores fp16 [B, 1]."""
+    feat = FirstConvFunction.apply(x.contiguous(), sd['conv_body.0.0.weight'], sd['conv_body.0.1.bias'])
+    i = 1
+    while f'conv_body.{i}.conv1.0.weight' in sd:
+        pre = f'conv_body.{i}'
+        feat = res_block(feat, sd[f'{pre}.conv1.0.weight'], sd[f'{pre}.conv1.1.bias'], sd[f'{pre}.conv2.1.weight'],
+                         sd[f'{pre}.conv2.2.bias'], sd[f'{pre}.skip.1.weight'])
+        i += 1
+    b, h, w, c = feat.shape
+    group = min(b, stddev_group)
+    cat = MinibatchStddevFunction.apply(feat, group)
+    c_pad = cat.shape[3]
+    wf = sd['final_conv.0.weight']                                       # [c4, C + 1, 3, 3]: zero input channels up to c_pad
+    wf = torch.nn.functional.pad(wf, (0, 0, 0, 0, 0, c_pad - wf.shape[1])) * math.sqrt(c_pad / (c + 1.0))   # keeps 1/sqrt((C+1)*9)
+    g = conv_layer3x3(cat, wf, sd['final_conv.1.bias'])
+    c4 = g.shape[3]
+    w1 = sd['final_linear.0.weight']                                     # reads the NCHW flattening: permute its columns
+    w1 = w1.view(w1.shape[0], c4, h * w).permute(0, 2, 1).reshape(w1.shape[0], -1)
+    hid = equal_linear(g.reshape(b, -1), w1, sd['final_linear.0.bias'], 1.0, True)
+    w2 = torch.nn.functional.pad(sd['final_linear.1.weight'], (0, 0, 0, 15))   # one output row, padded to the 16-channel block
+    b2 = torch.nn.functional.pad(sd['final_linear.1.bias'], (0, 15))
+    return equal_linear(hid, w2, b2)[:, :1]

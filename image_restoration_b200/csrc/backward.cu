@@ -195,6 +195,66 @@ __global__ void __launch_bounds__(kBwThreads) first_conv_wgrad_kernel(const floa
   }
 }
 
+// Backward of the minibatch standard-deviation layer of the discriminator (stylegan2_arch.py:791-801; forward:
+// b200ir_minibatch_stddev).  Sample b = g * M + m belongs to statistic m (M = B / group); s[m] = mean_{p,c} sigma[m][p][c],
+// sigma = sqrt(var_g(x) + 1e-8), is broadcast into channel C of every member of the group.  With ds[m] the summed gradient
+// of that channel:  dx[b][p][c] = dcat[b][p][c] + ds[m] * (x[b][p][c] - mu[m][p][c]) / (C * P * group * sigma[m][p][c]).
+// One thread per (m, p, 8 channels), the group (<= 8 samples) in registers.
+__global__ void __launch_bounds__(kBwThreads) mbstd_bwd_kernel(const uint4* __restrict__ x, const __half* __restrict__ dcat,
+                                                               const float* __restrict__ ds, uint4* __restrict__ dx, int M, int P,
+                                                               int groups, int c_pad, int group) {
+  const long long n = (long long)M * P * groups;
+  const float inv_n = 1.f / ((float)groups * 8.f * (float)P * (float)group);
+  for (long long idx = (long long)blockIdx.x * kBwThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kBwThreads) {
+    const unsigned r = (unsigned)idx / (unsigned)groups;
+    const int g8 = (int)((unsigned)idx - r * (unsigned)groups);
+    const int m = (int)(r / (unsigned)P), p = (int)(r - (unsigned)m * (unsigned)P);
+    float v[8][8], mu[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mu[k] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g < group) {
+        const uint4 q = __ldg(x + ((long long)(g * M + m) * P + p) * groups + g8);
+        const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(hq[k]);
+          v[g][2 * k] = f.x, v[g][2 * k + 1] = f.y;
+          mu[2 * k] += f.x, mu[2 * k + 1] += f.y;
+        }
+      }
+    }
+    float coef[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mu[k] /= (float)group;
+      float var = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (g < group) var += (v[g][k] - mu[k]) * (v[g][k] - mu[k]);
+      coef[k] = ds[m] * inv_n * rsqrtf(var / (float)group + 1e-8f);
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g < group) {
+        const long long row = (long long)(g * M + m) * P + p;
+        const uint4 dq = *reinterpret_cast<const uint4*>(dcat + row * c_pad + g8 * 8);
+        const __half2* dh = reinterpret_cast<const __half2*>(&dq);
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 d = __half22float2(dh[k]);
+          oh[k] = __floats2half2_rn(d.x + coef[2 * k] * (v[g][2 * k] - mu[2 * k]),
+                                    d.y + coef[2 * k + 1] * (v[g][2 * k + 1] - mu[2 * k + 1]));
+        }
+        dx[row * groups + g8] = o;
+      }
+    }
+  }
+}
+
 }  // namespace b200ir
 
 using namespace b200ir;
@@ -280,4 +340,22 @@ extern "C" int b200ir_first_conv_wgrad(const float* x, const void* dz, float* dw
   if (grid > 4LL * sms) grid = 4LL * sms;
   first_conv_wgrad_kernel<<<(int)grid, kBwThreads, 0, st>>>(x, (const uint4*)dz, dw, n_pix, H * W, groups);
   return check_launch("first_conv_wgrad");
+}
+
+extern "C" int b200ir_minibatch_stddev_bwd(const void* x, const void* dcat, const float* ds, void* dx, int B, int P, int C,
+                                           int c_pad, int group, void* stream) {
+  B200IR_REQUIRE(x && dcat && ds && dx && B > 0 && P > 0 && C > 0 && C % 8 == 0 && c_pad > C && c_pad % 8 == 0,
+                 "minibatch_stddev_bwd: bad arguments");
+  B200IR_REQUIRE(group >= 1 && group <= 8 && B % group == 0, "minibatch_stddev_bwd: batch %d is not divisible by group %d", B,
+                 group);
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const int M = B / group;
+  const long long n = (long long)M * P * (C / 8);
+  B200IR_REQUIRE(n < (1LL << 31), "minibatch_stddev_bwd: too many elements");
+  long long grid = (n + kBwThreads - 1) / kBwThreads;
+  if (grid > 8LL * sms) grid = 8LL * sms;
+  mbstd_bwd_kernel<<<(int)grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const uint4*)x, (const __half*)dcat, ds, (uint4*)dx, M, P, C / 8, c_pad, group);
+  return check_launch("minibatch_stddev_bwd");
 }

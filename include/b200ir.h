@@ -202,6 +202,12 @@ int b200ir_bilinear_up2_adjoint(const void* d, void* out, int B, int h, int w, i
  * w.r.t. the scaled weights the forward entry point takes).  cout = 8 * a divisor of 256. */
 int b200ir_first_conv_wgrad(const float* x, const void* dz, float* dw, int B, int H, int W, int cout, void* stream);
 
+/* Backward of b200ir_minibatch_stddev (stylegan2_arch.py:791-801): x NHWC fp16 [B][P][C] (the layer's input), dcat NHWC
+ * fp16 [B][P][c_pad] (gradient of its output: C feature channels + the statistic channel + padding), ds fp32 [B / group]
+ * (ds[m] = sum over the group's samples and pixels of dcat[.., C]) -> dx NHWC fp16 [B][P][C].  C % 8 == 0, group <= 8. */
+int b200ir_minibatch_stddev_bwd(const void* x, const void* dcat, const float* ds, void* dx, int B, int P, int C, int c_pad,
+                                int group, void* stream);
+
 /* One torch.optim.Adam step (no amsgrad; optimizer_g / optimizer_d of basicsr/models/gfpgan_model.py:217-248) over a flat
  * fp32 parameter buffer, fused with the gradient scaling of the data-parallel average (grad_scale = 1 / world) and,
  * when ema != NULL, with the EMA update of BaseModel.model_ema (basicsr/models/base_model.py:50-57):

@@ -96,3 +96,91 @@ def test_pyramid_loss_training_steps_reduce_the_loss():
     assert all(math.isfinite(v) for v in losses)
     assert losses[-1] < 0.7 * losses[0], losses
     assert all(torch.isfinite(e).all() for e in ema)
+
+
+def test_discriminator_forward_backward_against_oracle():
+    """network_d (StyleGAN2Discriminator) forward + backward through backward.disc_forward with the logistic loss of the D step
+    (gfpgan_model.py: l_d = softplus(-real) + softplus(fake)), against torch.autograd over the fp32 oracle."""
+    from image_restoration_b200.backward import disc_forward
+    from image_restoration_b200.disc import StyleGAN2Discriminator
+    from oracle.disc_oracle import discriminator_forward
+    torch.manual_seed(0)
+    W, H, B = 384, 128, 4
+    netd = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1)
+    sd_a = {k: v.detach().clone().cuda().requires_grad_() for k, v in netd.state_dict().items()}
+    sd_b = {k: v.detach().clone().requires_grad_() for k, v in sd_a.items()}
+    x = torch.rand(B, 3, H, W, device='cuda') * 2 - 1
+    sign = torch.tensor([1.0, 1.0, -1.0, -1.0], device='cuda').view(B, 1)          # two "real", two "fake" samples
+    # fp16 activation gradients need a loss scale: d(score) ~ 0.1 shrinks by 1/sqrt(fan_in) per linear layer and would reach
+    # the fp16 subnormals (< 6e-5) at final_conv; the weight gradients come back in fp32 and are unscaled exactly
+    S = 4096.0
+    score = disc_forward(sd_a, x)
+    (F.softplus(-sign * score.float()).mean() * S).backward()
+    for v in sd_a.values():
+        v.grad /= S
+    ref = discriminator_forward(sd_b, x)
+    F.softplus(-sign * ref).mean().backward()
+    torch.cuda.synchronize()
+    err = (score.float() - ref).abs().max().item()
+    print(f'disc scores {score.flatten().tolist()} vs oracle {ref.flatten().tolist()} (max err {err:.2e})')
+    assert err <= 2e-3 + 2e-2 * ref.abs().max().item()
+    stats = {}
+    for k in sd_a:
+        ga, gb = sd_a[k].grad, sd_b[k].grad
+        assert ga is not None and gb is not None, k
+        cos = F.cosine_similarity(ga.double().flatten(), gb.double().flatten(), dim=0).item()
+        rel = ((ga - gb).double().pow(2).mean().sqrt() / gb.double().pow(2).mean().sqrt().clamp_min(1e-30)).item()
+        print(f'disc grad {k}: rel rms {rel:.3e} cos {cos:.6f}')
+        stats[k] = (cos, rel)
+    # Twelve leaky ReLUs sit in series between the score and the first layer.  After eleven fp16 convs the pre-activations of
+    # final_conv differ from the fp32 oracle's by a few 1e-3 of their scale, so ~3e-3 of them take the other branch (each
+    # changes that element's gradient five-fold): ~8 % relative RMS from final_conv upwards, measured.  Every component is
+    # pinned strictly with the branches held equal (test_backward_gpu.py, test_minibatch_stddev_backward,
+    # test_equal_linear_activation_backward below); the two linears behind the last activation show the kernels' own accuracy.
+    assert stats['final_linear.1.weight'][1] <= 2e-2 and stats['final_linear.0.weight'][1] <= 2e-2, stats
+    for k, (cos, rel) in stats.items():
+        assert cos >= 0.99 and rel <= 0.15, (k, cos, rel)
+
+
+@pytest.mark.parametrize('B,h,w,C,group', [(4, 4, 12, 512, 4), (8, 4, 12, 64, 4), (2, 3, 5, 32, 2)])
+def test_minibatch_stddev_backward(B, h, w, C, group):
+    from image_restoration_b200.backward import MinibatchStddevFunction
+    from oracle.disc_oracle import minibatch_stddev
+    torch.manual_seed(B + C)
+    x = torch.randn(B, C, h, w, device='cuda').half()
+    xg = x.permute(0, 2, 3, 1).contiguous().requires_grad_()
+    cat = MinibatchStddevFunction.apply(xg, group)
+    cot = torch.randn(B, h, w, C + 1, device='cuda').half()
+    (cat[..., :C + 1].float() * cot.float()).sum().backward()
+    x_ref = x.float().requires_grad_()
+    ref = minibatch_stddev(x_ref, group)
+    (ref * cot.float().permute(0, 3, 1, 2)).sum().backward()
+    torch.cuda.synchronize()
+    assert (cat[..., :C + 1].float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 2e-3
+    assert (cat[..., C + 1:] == 0).all()
+    err = (xg.grad.float().permute(0, 3, 1, 2) - x_ref.grad).abs().max().item()
+    assert err <= 2e-3 * x_ref.grad.abs().max().item(), err
+
+
+def test_equal_linear_activation_backward():
+    """EqualLinear(activation='fused_lrelu') (final_linear.0 of the discriminator) with the branch taken from the kernel's output."""
+    from image_restoration_b200.backward import equal_linear
+    torch.manual_seed(3)
+    B, cin, cout = 4, 24576, 512
+    weight = torch.randn(cout, cin, device='cuda', requires_grad=True)
+    bias = (0.1 * torch.randn(cout, device='cuda')).requires_grad_()
+    x = torch.randn(B, cin, device='cuda').half()
+    dy = torch.randn(B, cout, device='cuda').half()
+    xg = x.clone().requires_grad_()
+    y = equal_linear(xg, weight, bias, 1.0, True)
+    y.backward(dy)
+    w_ref, b_ref, x_ref = weight.detach().clone().requires_grad_(), bias.detach().clone().requires_grad_(), x.float().requires_grad_()
+    z = F.linear(x_ref, w_ref / math.sqrt(cin), b_ref)
+    y_ref = z * torch.where(y.detach().float() > 0, math.sqrt(2.0), 0.2 * math.sqrt(2.0))
+    y_ref.backward(dy.float())
+    torch.cuda.synchronize()
+    for name, g, r in (('y', y.detach().float(), y_ref.detach()), ('dx', xg.grad.float(), x_ref.grad), ('dweight', weight.grad, w_ref.grad),
+                       ('dbias', bias.grad, b_ref.grad)):
+        rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
+        print(f'equal linear + fused_lrelu {name}: rel rms {rel:.3e}')
+        assert rel <= 1e-3, (name, rel)
