@@ -184,3 +184,32 @@ def test_equal_linear_activation_backward():
         rel = ((g - r).double().pow(2).mean().sqrt() / r.double().pow(2).mean().sqrt()).item()
         print(f'equal linear + fused_lrelu {name}: rel rms {rel:.3e}')
         assert rel <= 1e-3, (name, rel)
+
+
+def test_discriminator_steps_reduce_the_logistic_loss():
+    """The net_d update of optimize_parameters (gfpgan_model.py: real_d_pred / fake_d_pred through net_d, l_d = gan loss of both,
+    optimizer_d.step) on the B200 kernels, without the R1 penalty (needs a double backward): sharp vs blurred synthetic plates.
+    A static loss scale keeps the fp16 activation gradients in range; FlatAdam's grad_scale removes it in the fused step."""
+    from image_restoration_b200.backward import disc_forward
+    from image_restoration_b200.disc import StyleGAN2Discriminator
+    from image_restoration_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    W, H, B = 384, 128, 4
+    netd = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1)
+    sd = {k: v.detach().clone().cuda().requires_grad_() for k, v in netd.state_dict().items()}
+    opt = FlatAdam(list(sd.values()), lr=2e-3, betas=(0.0, 0.99))
+    real = (torch.rand(B, 3, H, W, device='cuda') * 2 - 1)
+    fake = F.avg_pool2d(real, 9, stride=1, padding=4)                     # the "restored" images: blurred copies
+    S = 256.0
+    losses = []
+    for it in range(10):
+        opt.zero_grad()
+        l_real = F.softplus(-disc_forward(sd, real).float()).mean()
+        l_fake = F.softplus(disc_forward(sd, fake).float()).mean()
+        ((l_real + l_fake) * S).backward()
+        opt.step(grad_scale=1.0 / S)
+        losses.append((l_real + l_fake).item())
+    torch.cuda.synchronize()
+    print('l_d per step:', ' '.join(f'{v:.4f}' for v in losses))
+    assert all(math.isfinite(v) for v in losses)
+    assert abs(losses[0] - 2 * math.log(2)) < 0.1 and losses[-1] < 0.5 * losses[0], losses
