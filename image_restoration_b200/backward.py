@@ -1,16 +1,26 @@
-"""Backward pass pieces of the optional training step (BASELINE config 5) for the U-Net encoder's
-`ConvLayer(cin, cout, 3, bias=True, activate=True)` (stylegan2_ocr_arch.py:658-705: EqualConv2d 3x3 stride 1 pad 1
-followed by FusedLeakyReLU), as a torch.autograd.Function in the way the reference wraps its own native ops
-(FusedLeakyReLUFunction, basicsr/ops/fused_act/fused_act.py:66-79: the Python wrapper owns save-for-backward, the
-native side does the arithmetic).
+"""Backward pass of the optional training step (BASELINE config 5): torch.autograd.Function wrappers in
+the way the reference wraps its own native ops (FusedLeakyReLUFunction, basicsr/ops/fused_act/fused_act.py:66-79: the
+Python wrapper owns save-for-backward, the native side does the arithmetic), and the two networks assembled from them.
 
+    ConvLayer3x3Function   EqualConv2d 3x3 + FusedLeakyReLU / + bias only        stylegan2_ocr_arch.py:658-705, SFT heads
+    ResBlockFunction       conv1, FIR + stride-2 conv2, FIR + 1x1 skip            stylegan2_ocr_arch.py:708-734
+    ResUpBlockFunction     conv1, bilinear x2 + conv2, 1x1 skip + bilinear x2     gfpganv1_ocr_arch.py:205-225
+    EqualLinearFunction    EqualLinear (+ fused_lrelu)                            stylegan2_ocr_arch.py:165-175
+    FirstConvFunction      conv_body_first (1x1 over the fp32 NCHW image)
+    ToRGBHeadFunction      toRGB[i] heads of the image pyramid loss               gfpganv1_ocr_arch.py:308-311, 377-378
+    MinibatchStddevFunction                                                       stylegan2_arch.py:791-801
+    unet_forward           trainable part of GFPGANv1OCR.forward                  gfpganv1_ocr_arch.py:352-378
+    disc_forward           StyleGAN2Discriminator.forward (network_d)             stylegan2_arch.py:788-805
+
+For one ConvLayer:
     forward   y  = lrelu(conv2d(x, W / sqrt(9 cin), padding=1) + b, 0.2) * sqrt 2    b200ir_conv_igemm (fused epilogue)
     backward  dz = dy * sqrt 2 * (y > 0 ? 1 : 0.2),  db = sum dz                      b200ir_lrelu_bias_bwd
               dW = x (*) dz / sqrt(9 cin)                                              b200ir_conv_wgrad (tcgen05, MN-major)
               dx = conv2d(dz, flip(W)^T, padding=1)                                    b200ir_conv_igemm (adjoint weights)
 
-Activations are NHWC fp16 on the device; parameters and their gradients are fp32 in the reference's layouts
-([cout, cin, 3, 3] and [cout]).  No CPU path: every call lands in libb200ir.so.
+Activations and their gradients are NHWC fp16 on the device (use a loss scale when the loss gradient is small: see
+tests/test_train_step_gpu.py); parameters and their gradients are fp32 in the reference's layouts.  torch packs weights,
+allocates buffers and runs the autograd graph; no CPU path: every arithmetic call lands in libb200ir.so.
 """
 import math
 
