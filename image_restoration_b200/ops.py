@@ -5,6 +5,7 @@ Naming follows the reference operators these replace (EqualConv2d / ModulatedCon
 upfirdn2d / fused_leaky_relu — see include/b200ir.h for file:line).
 """
 import ctypes as C
+import functools
 import math
 
 import torch
@@ -16,7 +17,14 @@ SQRT2 = math.sqrt(2.0)
 INV_SQRT2 = 1.0 / SQRT2
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _stream():
+    """torch's current CUDA stream of the current device as a cudaStream_t (the raw-handle accessor when this torch has it:
+    torch.cuda.current_stream() builds a Python Stream object per call, ~16 us, and every launch asks)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -29,6 +37,7 @@ def _req(t, dtype, name):
         raise ValueError(f'{name}: expected contiguous CUDA {dtype}, got {t.dtype} on {t.device}')
 
 
+@functools.lru_cache(maxsize=4096)
 def pick_tile(m_w, m_h, m_b, min_w=1, max_b=128):
     """Choose (tile_w, tile_h, tile_b), powers of two with product 128, minimising the number of tiles (optionally
     with a minimum row-segment length, for DRAM-friendly TMA boxes, and a cap on images per tile)."""
