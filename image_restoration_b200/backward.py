@@ -29,6 +29,11 @@ import torch
 from . import ops
 
 
+def _need_cuda(t, who):
+    if not t.is_cuda:
+        raise RuntimeError(f'image_restoration_b200.backward.{who} needs CUDA tensors (no CPU path)')
+
+
 def pack_equal_conv3x3(weight):
     """EqualConv2d weight fp32 [cout, cin, 3, 3] -> (packed fp16 [cout, 9*cin] with the equalised-lr scale folded in,
     scale).  stylegan2_ocr_arch.py:629-648."""
@@ -296,6 +301,7 @@ class FirstConvFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
+        _need_cuda(x, 'FirstConvFunction')
         b, _, h, w = x.shape
         cout = weight.shape[0]
         scale = 1.0 / math.sqrt(3.0)
@@ -318,6 +324,7 @@ class AddFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b):
+        _need_cuda(a, 'AddFunction')
         out = torch.empty_like(a)
         ops.add(a, b, out)
         return out
@@ -336,6 +343,7 @@ class ToRGBHeadFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
+        _need_cuda(x, 'ToRGBHeadFunction')
         b, h, w, cin = x.shape
         pad = ToRGBHeadFunction.PAD
         scale = 1.0 / math.sqrt(cin)
@@ -409,6 +417,7 @@ class MinibatchStddevFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, group):
+        _need_cuda(x, 'MinibatchStddevFunction')
         b, h, w, c = x.shape
         c_pad = (c + 1 + 15) // 16 * 16
         out = torch.zeros(b, h, w, c_pad, device=x.device, dtype=torch.float16)

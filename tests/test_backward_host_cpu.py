@@ -79,3 +79,28 @@ def test_pack_equal_conv_scale():
     wp1, s1 = pack_equal_conv(torch.randn(8, 16, 1, 1))
     assert math.isclose(s1, 0.25) and wp1.shape == (8, 16)
     assert torch.allclose(_unpack(wp.float(), 16), (w * s).half().float())
+
+
+def test_training_functions_have_no_cpu_path():
+    """The autograd wrappers refuse CPU tensors instead of falling back to torch (there is no CPU path in the product)."""
+    import pytest
+    from image_restoration_b200 import backward
+    x = torch.zeros(1, 8, 8, 16, dtype=torch.float16)
+    w = torch.zeros(16, 16, 3, 3, requires_grad=True)
+    b = torch.zeros(16, requires_grad=True)
+    with pytest.raises(RuntimeError):
+        backward.conv_layer3x3(x, w, b)
+    with pytest.raises(RuntimeError):
+        backward.res_block(x, w, b, w, b, torch.zeros(16, 16, 1, 1))
+    with pytest.raises(RuntimeError):
+        backward.res_up_block(x, w, b, w, b, torch.zeros(16, 16, 1, 1))
+    with pytest.raises(RuntimeError):
+        backward.equal_linear(torch.zeros(2, 16, dtype=torch.float16), torch.zeros(16, 16), torch.zeros(16))
+    with pytest.raises(RuntimeError):
+        backward.FirstConvFunction.apply(torch.zeros(1, 3, 8, 8), torch.zeros(16, 3, 1, 1), b)
+    with pytest.raises(RuntimeError):
+        backward.ToRGBHeadFunction.apply(x, torch.zeros(3, 16, 1, 1), torch.zeros(3))
+    with pytest.raises(RuntimeError):
+        backward.MinibatchStddevFunction.apply(x, 1)
+    with pytest.raises(RuntimeError):
+        backward.AddFunction.apply(x, x)
