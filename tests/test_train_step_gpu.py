@@ -2,7 +2,8 @@
 pyramid loss (lines 502-511, 531-536: L1 between the U-Net's toRGB heads and the bilinear GT pyramid), which involves only the
 trainable part of net_g, followed by the optimizer_g step (Adam betas (0, 0.99), lr 2e-3) and the EMA update.
 Forward, backward and the optimiser run in libb200ir.so (backward.unet_forward, optim.FlatAdam); torch does the 3-channel
-L1 itself and the GT pyramid (data preparation)."""
+L1 itself and the GT pyramid (data preparation).  Second half: network_d (StyleGAN2Discriminator) forward + backward through
+backward.disc_forward against the oracle's autograd, strict tests of its two new pieces, and net_d update steps."""
 import math
 
 import pytest
