@@ -3,12 +3,17 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 64] [--impl b200|reference]
 
-A "step" is one forward pass over one batch of `--batch` synthetic 3x128x384 plate crops per GPU (BASELINE
-configs[1]; stock random-init weights, seed 0; randomize_noise=False).  `value` = crops/s with the batch resident in
-HBM; `e2e` = the same through the public module call with pinned HOST input and HOST output (H2D + D2H inside the
-timed region).  Multi-GPU: one process per GPU (torchrun), each rank runs its own shard of crops, no data-path
-collective ("weak" scaling); time = max over ranks of the CUDA-event time.
+N = 1 (BASELINE configs[1]): a "step" is one forward pass over one batch of `--batch` synthetic 3x128x384 plate crops
+(stock random-init weights, seed 0; randomize_noise=False).  N > 1 (BASELINE configs[2]): a "step" is one pass over
+`--total` (4096) crops sharded data-parallel across the N GPUs -- contiguous per-rank shards (sharding.shard_bounds),
+each rank runs its shard in micro-batches of `--batch` through its own engine, no data-path collective; total work is
+fixed as N grows ("strong" scaling).
+`value` = crops/s with the crops resident in HBM; `e2e` = the same through the host-buffer front end
+(host_io.HostPipeline: pinned HOST input, HOST output, H2D + D2H inside the timed region).  Time = max over ranks of
+the CUDA-event time; an untimed pre-roll of >= 0.5 s runs after the barrier, immediately before the first event, so
+every N is timed at the sustained (power-capped) clock.
 `--impl reference` times the CPU fp32 oracle port of the reference forward (oracle/) on the host cores.
+The JSON line is the LAST line printed (NCCL_DEBUG output, if enabled by the caller, comes before it).
 """
 import argparse
 import json
@@ -18,7 +23,6 @@ import sys
 import threading
 import time
 
-os.environ['NCCL_DEBUG'] = os.environ.get('B200IR_NCCL_DEBUG', 'WARN')   # keep NCCL's banner off stdout (one JSON line)
 import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -164,14 +168,17 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--total', type=int, default=4096, help='N > 1: crops per step over all GPUs (BASELINE configs[2])')
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary records (degradation, tiling, training ...)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
 
     import torch.distributed as dist
     from image_restoration_b200 import GFPGANv1OCR, _lib
+    from image_restoration_b200.sharding import micro_batches, run_shard, shard_bounds
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -181,44 +188,67 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     warmup = max(args.warmup, 3)
     B = args.batch
+    # crops this rank processes per step: one micro-batch at N = 1, its shard of --total at N > 1
+    if world > 1:
+        lo, hi = shard_bounds(args.total, rank, world)
+        n_local = hi - lo
+    else:
+        n_local = B
 
     torch.manual_seed(0)
     net = GFPGANv1OCR(**NET_KW).eval().to(dev)
     eng = net.engine()
     gen = torch.Generator().manual_seed(1000 + rank)
-    x_host = (torch.rand(B, 3, H, W, generator=gen) * 2 - 1).pin_memory()
-    y_host = torch.empty(B, 3, H, W).pin_memory()
+    x_host = torch.empty(n_local, 3, H, W).pin_memory()
+    for s, e in micro_batches(0, n_local, 256):
+        x_host[s:e] = torch.rand(e - s, 3, H, W, generator=gen) * 2 - 1
+    y_host = torch.empty(n_local, 3, H, W).pin_memory()
     x_dev = x_host.to(dev)
+    y_dev = torch.empty_like(x_dev)
     plan = eng.plan(B)
     lib = _lib.lib()
 
-    # one eager pass: warms the kernels and counts this library's launches per step
-    plan.x_in.copy_(x_dev)
+    # one eager pass: warms the kernels and counts this library's launches per micro-batch
+    plan.x_in.copy_(x_dev[:B])
     for j, buf in enumerate(plan.noise):
         buf.copy_(eng.packed.stored_noise[j].expand_as(buf))
     n0 = lib.b200ir_launch_count()
     plan.launch(False)
     torch.cuda.synchronize()
-    launches_per_step = lib.b200ir_launch_count() - n0
+    launches_per_mb = lib.b200ir_launch_count() - n0
+    mbs_per_step = len(micro_batches(0, n_local, B))
+
+    def fwd(xb):
+        return net(xb, return_rgb=False, randomize_noise=False)[0]
 
     def step_resident():
-        return net(x_dev, return_rgb=False, randomize_noise=False)[0]
+        if world == 1:
+            return fwd(x_dev)
+        return run_shard(fwd, x_dev, B, out=y_dev)        # this rank's shard, micro-batches of B, results kept in HBM
 
     from image_restoration_b200.host_io import HostPipeline
     pipe = HostPipeline(net, depth=2, return_rgb=False, randomize_noise=False)
 
     def step_e2e():
-        # host (pinned) in, host (pinned) out; the copies of neighbouring steps overlap this step's kernels
-        pipe.submit(x_host, y_host)
+        # host (pinned) in, host (pinned) out; the copies of neighbouring micro-batches overlap the kernels
+        for s, e in micro_batches(0, n_local, B):
+            pipe.submit(x_host[s:e], y_host[s:e])
 
-    def timed(fn, k, w):
+    def timed(fn, k, w, preroll=0.5):
         for _ in range(w):
             fn()
         pipe.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        # untimed pre-roll AFTER the barrier, immediately before the first event: the idle of the barrier lets the board
+        # leave its power cap and the first ~100 ms would run at boost clocks (round-1 SCALE numbers were inflated by it)
+        t_pre = time.time()
+        while preroll > 0 and time.time() - t_pre < preroll:
+            for _ in range(4):
+                fn()
+            pipe.drain()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(k):
@@ -238,7 +268,7 @@ def main():
     t_pre = time.time()
     while time.time() - t_pre < 1.5:
         for _ in range(10):
-            step_resident()
+            fwd(x_dev[:B])
         torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
@@ -246,6 +276,39 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     ms_e2e = timed(step_e2e, args.steps, warmup)
+    pipe.drain()
+
+    # parity of the benchmarked configuration itself: 4 crops of the batch against the CPU oracle (the checker, not the
+    # thing measured); the e2e leg's host output must equal the resident leg's
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.gfpgan_ocr_oracle import OcrNetConfig, gfpgan_ocr_forward, psnr01, to01
+        idx = [0, B // 3, (2 * B) // 3, B - 1]
+        got = fwd(x_dev[:B])[idx].float().cpu()
+        cfg = OcrNetConfig(**{k: v for k, v in NET_KW.items() if k not in ('decoder_load_path', 'fix_decoder')})
+        sd_cpu = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        torch.set_num_threads(os.cpu_count())
+        ref, _ = gfpgan_ocr_forward(sd_cpu, cfg, x_host[idx], False)
+        a, b_ = to01(got), to01(ref)
+        parity = {'crops_checked': idx, 'batch': B, 'max_abs_01': (a - b_).abs().max().item(), 'psnr_db': psnr01(a, b_),
+                  'bar': 'max-abs <= 2e-2 on [0,1], PSNR >= 45 dB vs the fp32 CPU oracle',
+                  'e2e_equals_resident': bool(torch.equal(y_host[:B][idx], got))}
+        parity['ok'] = bool(parity['max_abs_01'] <= 2e-2 and parity['psnr_db'] >= 45.0 and parity['e2e_equals_resident'])
+
+    # what the callers call (gfpgan_model.py:803 / api.py:104 defaults): fresh noise per call, the U-Net's toRGB heads
+    # returned, uint8 images in and out
+    variants = None
+    if world == 1 and not args.no_extras:
+        variants = {}
+        for name, fn in (('randomize_noise_true', lambda: net(x_dev[:B], return_rgb=False, randomize_noise=True)),
+                         ('return_rgb_true', lambda: net(x_dev[:B], return_rgb=True, randomize_noise=False)),
+                         ('defaults_rgb_and_noise', lambda: net(x_dev[:B]))):
+            ms = timed(fn, args.steps, 3, preroll=0.2) / args.steps
+            variants[name] = {'crops_per_s': B / (ms / 1e3), 'ms_per_step': ms}
+        img_u8 = torch.randint(0, 256, (B, H, W, 3), device=dev, dtype=torch.uint8)
+        ms = timed(lambda: net.restore_uint8(img_u8, randomize_noise=False), args.steps, 3, preroll=0.2) / args.steps
+        variants['restore_uint8'] = {'crops_per_s': B / (ms / 1e3), 'ms_per_step': ms,
+                                     'config': 'uint8 HWC BGR in -> uint8 HWC BGR out (api.py:96-105 on the device)'}
 
     # dominant kernel: conv_igemm_kernel.  Time only its launches of one step (same buffers as the real step),
     # back to back on the current stream, with CUDA events.
@@ -255,7 +318,7 @@ def main():
     def conv_only():
         for op in conv_ops:
             op()
-    ms_conv = timed(conv_only, args.steps, warmup)
+    ms_conv = timed(conv_only, args.steps, warmup, preroll=0.3)
 
     # memory-bound kernels: every launch of each kind, back to back, against its algorithmic bytes
     from image_restoration_b200.engine import PwOp
@@ -269,10 +332,10 @@ def main():
             def run_group(g=group):
                 for op in g:
                     op()
-            ms = timed(run_group, args.steps, 3) / args.steps
+            ms = timed(run_group, args.steps, 3, preroll=0.05) / args.steps
             nbytes = sum(op.nbytes for op in group)
             big = max(group, key=lambda op: op.nbytes)        # the largest launch of the kind, alone
-            ms_big = timed(big, args.steps, 3) / args.steps
+            ms_big = timed(big, args.steps, 3, preroll=0.05) / args.steps
             pw_report.append({'kernel': name, 'launches_per_step': len(group), 'algorithmic_mb_per_step': nbytes / 1e6,
                               'ms_per_step': ms, 'achieved_gbs': nbytes / ms / 1e6,
                               'largest_launch': {'algorithmic_mb': big.nbytes / 1e6, 'ms': ms_big,
@@ -281,7 +344,7 @@ def main():
     # fused degradation kernel (north_star (c)): crops/s of pyblur blur + down-resize + noise + up-resize + quantise,
     # beside the reference's own CPU library calls (oracle/pyblur_oracle.py) on a few crops
     degr = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.no_extras:
         import numpy as np
         from image_restoration_b200 import degradation as dg
         from oracle import pyblur_oracle as po
@@ -291,7 +354,7 @@ def main():
         kernels, sizes, nz = dg.random_degradation_params(DB, H, W, rng=rng)
         gt_d, nz_d = torch.from_numpy(gt).to(dev), torch.from_numpy(nz).to(dev)
         packed = dg.pack_degradation(kernels, sizes, dev)
-        ms = timed(lambda: dg.degrade_batch(gt_d, kernels, sizes, nz_d, packed=packed), 10, 3) / 10
+        ms = timed(lambda: dg.degrade_batch(gt_d, kernels, sizes, nz_d, packed=packed), 10, 3, preroll=0.1) / 10
         t0 = time.time()
         n_cpu = 8
         for b in range(n_cpu):
@@ -315,7 +378,7 @@ def main():
         import random as _random
         prm = dg.sample_params(DB, H, W, opt, py_random=_random.Random(0), np_random=np.random.RandomState(0))
         pk = dg.pack_degrade_full(dev=dev, **prm)
-        ms_full = timed(lambda: dg.degrade_full_batch(gt_d, packed=pk), 10, 3) / 10
+        ms_full = timed(lambda: dg.degrade_full_batch(gt_d, packed=pk), 10, 3, preroll=0.1) / 10
         t0 = time.time()
         for b in range(n_cpu):
             lw, lh = prm['sizes'][b]
@@ -331,7 +394,7 @@ def main():
         tiler = TiledRestorer(net256, overlap=32, micro_batch=64)
         frame = torch.rand(3, 1080, 1920, device=dev) * 2 - 1
         with torch.no_grad():
-            ms_frame = timed(lambda: tiler(frame, randomize_noise=False), 10, 3) / 10
+            ms_frame = timed(lambda: tiler(frame, randomize_noise=False), 10, 3, preroll=0.1) / 10
         tiled = {'frames_per_s': 1e3 / ms_frame, 'ms_per_frame': ms_frame, 'tiles_per_frame': 45,
                  'tiles_per_s': 45e3 / ms_frame, 'algorithmic_tflops': 45 * 34.63e9 / ms_frame / 1e9,
                  'config': '3x1080x1920 frame, 256x256 tiles, overlap 32 (5x9 tiles, one batch), gather + forward + '
@@ -342,7 +405,7 @@ def main():
         torch.manual_seed(0)
         netd = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1).eval().to(dev)
         xd = torch.rand(B, 3, H, W, device=dev) * 2 - 1
-        ms_d = timed(lambda: netd(xd), 10, 3) / 10
+        ms_d = timed(lambda: netd(xd), 10, 3, preroll=0.1) / 10
         disc = {'crops_per_s': B / (ms_d / 1e3), 'ms_per_batch': ms_d, 'batch': B,
                 'config': f'StyleGAN2Discriminator(input_width={W}, input_height={H}, channel_multiplier=1) forward, eager '
                           'launches'}
@@ -363,7 +426,7 @@ def main():
             if not cots:
                 cots.extend(torch.randn_like(t) for t in [sc] + cd)
             torch.autograd.backward([sc] + cd, cots)
-        ms_t = timed(unet_step, 4, 2) / 4
+        ms_t = timed(unet_step, 4, 2, preroll=0.1) / 4
         unet_train = {'crops_per_s': B / (ms_t / 1e3), 'ms_per_batch': ms_t, 'batch': B,
                       'parameters': sum(v.numel() for v in sd_t.values()),
                       'config': 'U-Net encoder + decoder + SFT heads + final_linear of GFPGANv1OCR (everything optimizer_g updates '
@@ -381,35 +444,52 @@ def main():
 
     if rank == 0:
         tf_peak, hbm_peak, src = peaks()
-        crops = B * world * args.steps
+        crops_per_step = B if world == 1 else args.total          # whole job
+        crops = crops_per_step * args.steps
         value = crops / (ms_total / 1e3)
         e2e_value = crops / (ms_e2e / 1e3)
         conv_ms_step = ms_conv / args.steps
         conv_tflops = GEMM_GFLOP_PER_CROP * 1e9 * B / (conv_ms_step / 1e3) / 1e12
+        if world == 1:
+            workload = (f'BASELINE configs[1]: GFPGANv1OCR forward (return_rgb=False, randomize_noise=False), batch {B} '
+                        f'synthetic plate crops 3x{H}x{W} on 1 GPU, stock random-init weights seed 0')
+        else:
+            workload = (f'BASELINE configs[2]: {args.total} synthetic plate crops 3x{H}x{W} per step sharded data-parallel '
+                        f'across {world} GPUs ({n_local} per GPU, contiguous shards, micro-batches of {B} through '
+                        f'sharding.run_shard; e2e: host-resident crops through host_io.HostPipeline), GFPGANv1OCR forward '
+                        f'(return_rgb=False, randomize_noise=False), no collective on the path')
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
-            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'fp16', 'data': 'synthetic',
-            'config': {'workload': f'GFPGANv1OCR forward (return_rgb=False, randomize_noise=False), batch {B} '
-                                   f'synthetic plate crops 3x{H}x{W} per GPU, stock random-init weights seed 0',
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong',
+            'vs_baseline': None, 'dtype': 'fp16', 'data': 'synthetic',
+            'config': {'workload': workload,
                        'operands': 'fp16 x fp16 -> fp32 accumulate (tcgen05 kind::f16); bf16 operands fail the '
                                    '2e-2/45 dB parity bar (SURVEY App. D)',
-                       'batch_per_gpu': B, 'parallelism': f'dp{world} (independent shards, no collective)',
-                       'l2': 'working set per step >> 126 MB L2 (activations ~GBs at batch 64); no explicit flush',
-                       'executor': 'CUDA graph replay of the launch plan'},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 4,
-                    'd2h_bytes_per_step': y_host.numel() * 4, 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': int(launches_per_step * args.steps),
-            'launches_per_step': int(launches_per_step),
+                       'micro_batch': B, 'crops_per_step': crops_per_step, 'crops_per_gpu_per_step': n_local,
+                       'parallelism': f'dp{world} (independent shards, no collective)',
+                       'l2': 'working set per forward >> 126 MB L2 (activations ~GBs at batch 64); no explicit flush',
+                       'executor': 'CUDA graph replay of the launch plan',
+                       'timing': 'CUDA events, max over ranks; >= 0.5 s untimed pre-roll after the barrier, immediately '
+                                 'before the first event'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': crops_per_step * 3 * H * W * 4,
+                    'd2h_bytes_per_step': crops_per_step * 3 * H * W * 4, 'ms_per_step': ms_e2e / args.steps,
+                    'bytes': 'whole job (all ranks), fp32 NCHW in and out'},
+            'gpu_launches': int(launches_per_mb * mbs_per_step * args.steps * world),
+            'launches_per_step': int(launches_per_mb * mbs_per_step * world),
+            'launches_per_micro_batch': int(launches_per_mb),
             'roofline': {'bound': 'tensor', 'kernel': 'conv_igemm_kernel', 'achieved': conv_tflops, 'peak': tf_peak,
                          'unit': 'TFLOP/s', 'frac': conv_tflops / tf_peak, 'traffic': None,
-                         'peak_source': f'{src} bf16_tflops_sustained', 'launches_per_step': len(conv_ops),
+                         'peak_source': f'{src} bf16_tflops_sustained', 'launches_per_micro_batch': len(conv_ops),
                          'avg_launch_ms': conv_ms_step / len(conv_ops),
                          'algorithmic_gflop_per_launch': GEMM_GFLOP_PER_CROP * B / len(conv_ops),
-                         'conv_share_of_step': conv_ms_step / (ms_total / args.steps),
+                         'conv_share_of_step': conv_ms_step * mbs_per_step / (ms_total / args.steps),
                          'whole_net_frac': value / world * GFLOP_PER_CROP * 1e9 / 1e12 / tf_peak},
             'clocks': sampler.summary(),
         }
+        if parity is not None:
+            line['parity'] = parity
+        if variants is not None:
+            line['caller_variants'] = variants
         traffic_file = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
         if os.path.exists(traffic_file):
             with open(traffic_file) as f:
@@ -446,9 +526,14 @@ def main():
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
         else:
             line['cpu_baseline'] = None
-        print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)          # the last line of stdout
+        if parity is not None and not parity['ok']:
+            sys.exit('bench.py: the benchmarked batch fails the parity bar against the CPU oracle: ' + json.dumps(parity))
 
 
 if __name__ == '__main__':

@@ -65,6 +65,10 @@ SIGNATURES = {
     'b200ir_launch_count': [],
     'b200ir_device_check': [],
     'b200ir_conv_igemm': [C.POINTER(ConvDesc), _P],
+    'b200ir_conv_plan_create': [C.POINTER(ConvDesc), C.POINTER(_P)],
+    'b200ir_conv_plan_launch': [_P, _P],
+    'b200ir_conv_plan_destroy': [_P],
+    'b200ir_pack_weights': [_P, _P, _I, _I, _I, _I, _F, _I, _I, _P],
     'b200ir_first_conv': [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     'b200ir_replicate_border': [_P, _I, _I, _I, _I, _P],
     'b200ir_upfold_corners': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -104,10 +108,22 @@ SIGNATURES = {
     'b200ir_channel_mean': [_P, _P, _I, _I, _I, _P],
     'b200ir_ca_mlp': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     'b200ir_ca_scale_add': [_P, _P, _P, _P, _F, _I, _I, _I, _L, _L, _P],
+    'b200ir_sft_mod': [_P, _P, _P, _I, _P, _P, _I, _L, _I, _P],
+    'b200ir_sft_mod_bwd': [_P, _P, _L, _P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _L, _I, _P],
+    'b200ir_style_act_bwd': [_P, _P, _P, _L, _P, _P, _P, _F, _P, _P, _I, _L, _I, _P],
+    'b200ir_to_rgb_bwd': [_P, _P, _P, _P, _P, _I, _P, _I, _L, _I, _P],
+    'b200ir_rgb_up_adjoint': [_P, _P, _I, _I, _I, _P],
+    'b200ir_demod_bwd': [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P],
+    'b200ir_mod_linear_bwd': [_P, _P, _F, _P, _I, _I, _I, _I, _I, _P],
+    'b200ir_first_conv_dgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'b200ir_head_to_nchw': [_P, _P, _I, _L, _I, _P],
+    'b200ir_nchw_to_head': [_P, _P, _I, _L, _I, _P],
+    'b200ir_l1_loss': [_P, _P, _L, _F, _F, _P, _P, _P],
+    'b200ir_softplus_loss': [_P, _I, _I, _F, _F, _F, _P, _P, _P],
     'b200ir_degrade': [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     'b200ir_degrade_full': [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
 }
-_RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64}
+_RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64, 'b200ir_conv_plan_destroy': None}
 
 _lib = None
 
@@ -126,6 +142,18 @@ def lib():
             fn.restype = _RESTYPES.get(name, C.c_int)
         _lib = handle
     return _lib
+
+
+def require_cuda(t, who):
+    """Every compute entry point of the package takes CUDA tensors; there is no CPU path."""
+    if not t.is_cuda:
+        raise RuntimeError(f'image_restoration_b200.{who} needs CUDA tensors (no CPU path)')
+
+
+def device_ctx(dev):
+    """`with` context selecting the CUDA device of a tensor for the launches inside."""
+    import torch
+    return torch.cuda.device(dev)
 
 
 class B200irError(RuntimeError):

@@ -26,12 +26,11 @@ import math
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 def _need_cuda(t, who):
-    if not t.is_cuda:
-        raise RuntimeError(f'image_restoration_b200.backward.{who} needs CUDA tensors (no CPU path)')
+    _lib.require_cuda(t, f'backward.{who}')
 
 
 def pack_equal_conv3x3(weight):
@@ -50,8 +49,7 @@ class ConvLayer3x3Function(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, activate=True):
-        if not x.is_cuda:
-            raise RuntimeError('image_restoration_b200.backward.ConvLayer3x3Function needs CUDA tensors (no CPU path)')
+        _need_cuda(x, 'ConvLayer3x3Function')
         b, h, w, cin = x.shape
         cout = weight.shape[0]
         wp, scale = pack_equal_conv3x3(weight)
@@ -92,8 +90,7 @@ class EqualLinearFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, lr_mul=1.0, activate=False):
-        if not x.is_cuda:
-            raise RuntimeError('image_restoration_b200.backward.EqualLinearFunction needs CUDA tensors (no CPU path)')
+        _need_cuda(x, 'EqualLinearFunction')
         b, cin = x.shape
         cout = weight.shape[0]
         scale = lr_mul / math.sqrt(cin)
@@ -153,8 +150,7 @@ class ResBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, ws):
-        if not x.is_cuda:
-            raise RuntimeError('image_restoration_b200.backward.ResBlockFunction needs CUDA tensors (no CPU path)')
+        _need_cuda(x, 'ResBlockFunction')
         b, h, w, cin = x.shape
         cout = w2.shape[0]
         oh, ow = h // 2, w // 2
@@ -235,8 +231,7 @@ class ResUpBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, ws):
-        if not x.is_cuda:
-            raise RuntimeError('image_restoration_b200.backward.ResUpBlockFunction needs CUDA tensors (no CPU path)')
+        _need_cuda(x, 'ResUpBlockFunction')
         b, h, w, cin = x.shape
         cout = w2.shape[0]
         dev = x.device
@@ -296,8 +291,9 @@ def res_up_block(x, w1, b1, w2, b2, ws):
 
 
 class FirstConvFunction(torch.autograd.Function):
-    """conv_body_first = ConvLayer(3, C, 1, bias=True, activate=True) over the fp32 NCHW input image (no input gradient:
-    the image is data)."""
+    """conv_body_first = ConvLayer(3, C, 1, bias=True, activate=True) over the fp32 NCHW input image.  The image is data for
+    net_g (no input gradient); the discriminator's conv_body.0 returns d/d(image) when the image requires grad — that is how
+    l_g_gan reaches net_g (gfpgan_model.py:549-552)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -306,17 +302,24 @@ class FirstConvFunction(torch.autograd.Function):
         cout = weight.shape[0]
         scale = 1.0 / math.sqrt(3.0)
         y = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float16)
-        ops.first_conv(x, (weight.detach().view(cout, 3) * scale).contiguous(), bias.detach().float().contiguous(), y)
-        ctx.save_for_backward(x, y)
+        ws = (weight.detach().view(cout, 3) * scale).contiguous()
+        xc = x.detach().contiguous()
+        ops.first_conv(xc, ws, bias.detach().float().contiguous(), y)
+        ctx.save_for_backward(xc, y, ws)
         ctx.scale = scale
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y = ctx.saved_tensors
-        dz, dbias = ops.lrelu_bias_bwd(dy.contiguous(), y)
-        dw = ops.first_conv_wgrad(x, dz) * ctx.scale
-        return None, dw.view(-1, 3, 1, 1), dbias
+        x, y, ws = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dz, dbias = ops.lrelu_bias_bwd(dy.contiguous(), y, want_bias=need[2])
+        dw = (ops.first_conv_wgrad(x, dz) * ctx.scale).view(-1, 3, 1, 1) if need[1] else None
+        dx = None
+        if need[0]:
+            dx = torch.empty_like(x)
+            ops.first_conv_dgrad(dz, ws, dx)
+        return dx, dw, dbias
 
 
 class AddFunction(torch.autograd.Function):
@@ -422,7 +425,6 @@ class MinibatchStddevFunction(torch.autograd.Function):
         c_pad = (c + 1 + 15) // 16 * 16
         out = torch.zeros(b, h, w, c_pad, device=x.device, dtype=torch.float16)
         s_buf = torch.empty(b // group, device=x.device, dtype=torch.float32)
-        from . import _lib
         _lib.check(_lib.lib().b200ir_minibatch_stddev(ops._ptr(x), ops._ptr(s_buf), ops._ptr(out), b, h * w, c, c_pad, group,
                                                       ops._stream()), 'minibatch_stddev')
         ctx.save_for_backward(x)
@@ -437,7 +439,6 @@ class MinibatchStddevFunction(torch.autograd.Function):
         dcat = dcat.contiguous()
         ds = dcat[..., c].float().view(g, b // g, h * w).sum(dim=(0, 2)).contiguous()      # B * h * w numbers: host-side glue
         dx = torch.empty_like(x)
-        from . import _lib
         _lib.check(_lib.lib().b200ir_minibatch_stddev_bwd(ops._ptr(x), ops._ptr(dcat), ops._ptr(ds), ops._ptr(dx), b, h * w, c,
                                                           dcat.shape[3], g, ops._stream()), 'minibatch_stddev_bwd')
         return dx, None

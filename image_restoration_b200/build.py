@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libb200ir.so')
 SOURCES = ['api.cu', 'conv_igemm.cu', 'conv_epi_generic.cu', 'conv_epi0.cu', 'conv_epi1.cu', 'conv_epi2.cu', 'conv_epi3.cu',
            'conv_epi4.cu', 'conv_epi5.cu', 'conv_epi6.cu', 'pointwise.cu', 'fir_tma.cu', 'resample_tma.cu', 'sr_ops.cu', 'degrade.cu', 'degrade_full.cu', 'wgrad.cu',
-           'backward.cu']
+           'backward.cu', 'train_ops.cu']
 HEADERS = ['ptx.cuh', 'host_common.h', 'conv_common.cuh', 'blur_taps.cuh', os.path.join('..', '..', 'include', 'b200ir.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math', '-Xcompiler', '-fPIC', '-Xptxas', '-v']

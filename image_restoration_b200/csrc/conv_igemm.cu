@@ -98,7 +98,15 @@ int smem_optin() { return init_device_info() ? 0 : g_smem_optin; }
 
 using namespace b200ir;
 
-extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
+// Everything a launch needs besides the stream: kernel parameters (tensor maps included), kernel variant, grid and
+// dynamic shared memory.  Built once per descriptor by build_conv_launch; b200ir_conv_plan keeps it.
+struct ConvLaunch {
+  ConvParams p;
+  bool row;
+  int grid, smem_bytes;
+};
+
+static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
   B200IR_REQUIRE(d != nullptr, "conv_igemm: null desc");
   if (init_device_info()) return 1;
   B200IR_REQUIRE(d->tile_w > 0 && d->tile_h > 0 && d->tile_b > 0 && d->tile_w * d->tile_h * d->tile_b == kBlockM,
@@ -132,7 +140,7 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
                  "conv_igemm: rgb_w needs rgb_part and the plane extents");
   B200IR_REQUIRE(!d->no_store || d->rgb_w != nullptr, "conv_igemm: no_store without a fused ToRGB leaves no output");
 
-  ConvParams p;
+  ConvParams& p = L.p;
   memset(&p, 0, sizeof(p));
   p.block_k = (d->cin % 64 == 0) ? 64 : ((d->cin % 32 == 0) ? 32 : 16);
   p.k_chunks = d->cin / p.block_k;
@@ -350,7 +358,10 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
           }
           int grid_r = p.row_items < row_ctas ? p.row_items : row_ctas;
           if (d->max_ctas > 0 && grid_r > d->max_ctas) grid_r = d->max_ctas;
-          return launch_conv(p, true, grid_r, smem_row, g_smem_optin, reinterpret_cast<cudaStream_t>(stream));
+          L.row = true;
+          L.grid = grid_r;
+          L.smem_bytes = smem_row;
+          return 0;
         }
         // not taken: restore the generic activation map (box = tile)
         cuuint32_t box_g[4] = {(cuuint32_t)p.block_k, (cuuint32_t)d->tile_w, (cuuint32_t)d->tile_h, (cuuint32_t)d->tile_b};
@@ -361,5 +372,42 @@ extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
 
   int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-  return launch_conv(p, false, grid, smem_bytes, g_smem_optin, reinterpret_cast<cudaStream_t>(stream));
+  L.row = false;
+  L.grid = grid;
+  L.smem_bytes = smem_bytes;
+  return 0;
 }
+
+extern "C" int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream) {
+  ConvLaunch L;
+  if (build_conv_launch(d, L)) return 1;
+  return launch_conv(L.p, L.row, L.grid, L.smem_bytes, g_smem_optin, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- launch plans: descriptor validation, tensor-map encoding and tile / ring sizing done once, launched many times
+struct b200ir_conv_plan {
+  ConvLaunch L;
+  int device;
+};
+
+extern "C" int b200ir_conv_plan_create(const b200ir_conv_desc* d, b200ir_conv_plan** plan) {
+  B200IR_REQUIRE(plan != nullptr, "conv_plan_create: null plan pointer");
+  *plan = nullptr;
+  b200ir_conv_plan* pl = static_cast<b200ir_conv_plan*>(aligned_alloc(64, (sizeof(b200ir_conv_plan) + 63) / 64 * 64));
+  B200IR_REQUIRE(pl != nullptr, "conv_plan_create: out of host memory");
+  if (build_conv_launch(d, pl->L)) {
+    free(pl);
+    return 1;
+  }
+  cudaGetDevice(&pl->device);
+  *plan = pl;
+  return 0;
+}
+
+extern "C" int b200ir_conv_plan_launch(const b200ir_conv_plan* plan, void* stream) {
+  B200IR_REQUIRE(plan != nullptr, "conv_plan_launch: null plan");
+  const ConvLaunch& L = plan->L;
+  return launch_conv(L.p, L.row, L.grid, L.smem_bytes, g_smem_optin, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" void b200ir_conv_plan_destroy(b200ir_conv_plan* plan) { free(plan); }

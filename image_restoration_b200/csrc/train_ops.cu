@@ -1,0 +1,586 @@
+// Memory-bound kernels of the training step (BASELINE config 5) that the forward path does not have:
+// the adjoints of the StyleGAN2 decoder's pointwise stages (SFT, modulation, noise + FusedLeakyReLU, ToRGB and its skip
+// up-sampling) together with the per-sample channel reductions that give the style gradients, the input gradient of the
+// first 1x1 conv (the discriminator must pass d(score)/d(image) back to the generator), the L1 / softplus losses with
+// their gradients, and the weight packing entry point.  Reference semantics: include/b200ir.h next to each entry point
+// (stylegan2_ocr_arch.py:239-279, 323-333, 357-374; gfpganv1_ocr_arch.py:108-129; losses/losses.py:81-106, 404-419).
+//
+// Layout as everywhere on the path: activations and their gradients NHWC fp16, 8 channels (16 bytes) per thread access;
+// tables (styles, demodulation, their gradients) fp32 [B][C].  The reductions follow lrelu_bias_bwd_kernel (backward.cu):
+// every thread owns one group of 8 channels and a strided set of pixels of ONE image, partial sums stay in registers until
+// one shared-memory reduction and one fp32 atomic per (CTA, channel).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace b200ir {
+
+constexpr int kTrThreads = 256;
+constexpr float kTrSqrt2 = 1.4142135623730951f;
+
+__device__ __forceinline__ void tr_unpack(const uint4& q, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 x = __half22float2(h[i]);
+    f[2 * i] = x.x;
+    f[2 * i + 1] = x.y;
+  }
+}
+__device__ __forceinline__ uint4 tr_pack(const float* f) {
+  uint4 q;
+  __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = f2h2_sat(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+// Thread layout of the per-image reductions: grid (pixel chunks, channel chunks, B); inside a CTA `groups` channel groups
+// x `lanes` pixel lanes.
+struct TrLayout {
+  int groups, chunks, lanes;
+  unsigned grid_x;
+};
+static TrLayout tr_layout(int C, long long P, int sms, int B) {
+  TrLayout l;
+  const int row_groups = C / 8;
+  l.groups = kTrThreads;
+  while (row_groups % l.groups) l.groups >>= 1;
+  l.chunks = row_groups / l.groups;
+  l.lanes = kTrThreads / l.groups;
+  long long gx = (P + l.lanes - 1) / l.lanes;
+  // about one wave of 8 resident CTAs per SM over the whole launch, at least one CTA per image and channel chunk
+  long long cap = (8LL * sms + (long long)l.chunks * B - 1) / ((long long)l.chunks * B);
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  l.grid_x = (unsigned)gx;
+  return l;
+}
+
+// sums acc[8] over the pixel lanes of the CTA and adds the result to dst[c] (c = channel inside this CTA's chunk)
+__device__ __forceinline__ void tr_reduce_add(const float* acc, float* dst, int groups, int lanes, float (*part)[9]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < groups * 8; c += kTrThreads) {
+    const int cg = c >> 3, cj = c & 7;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += part[l * groups + cg][cj];
+    atomicAdd(dst + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ SFT + modulation, forward
+__global__ void __launch_bounds__(kTrThreads) sft_mod_kernel(const uint4* __restrict__ a, const uint4* __restrict__ scale,
+                                                             const uint4* __restrict__ shift, int sft_groups,
+                                                             const float* __restrict__ s_next, uint4* __restrict__ out,
+                                                             long long n, long long P, int row_groups) {
+  for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
+    const long long pix = idx / row_groups;
+    const int g = (int)(idx - pix * row_groups);
+    const long long b = pix / P;
+    float v[8];
+    tr_unpack(__ldcs(a + idx), v);
+    const int gs = g - (row_groups - sft_groups);
+    if (scale != nullptr && gs >= 0) {
+      float sc[8], sh[8];
+      tr_unpack(__ldcs(scale + pix * sft_groups + gs), sc);
+      tr_unpack(__ldcs(shift + pix * sft_groups + gs), sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    }
+    if (s_next != nullptr) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(s_next + (b * row_groups + g) * 8));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(s_next + (b * row_groups + g) * 8) + 1);
+      v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+      v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    }
+    out[idx] = tr_pack(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ SFT + modulation, backward
+// g = gradient w.r.t. the modulated conv input (the dgrad GEMM's output).  o = SFT output (recomputed from a, scale, shift):
+//   ds[b][c] += sum_p g * o;   do = g * s_next;   da = do (* scale on the SFT channels);   dscale = do * a;   dshift = do
+__global__ void __launch_bounds__(kTrThreads) sft_mod_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ a,
+                                                                 long long a_sb_groups, const uint4* __restrict__ scale,
+                                                                 const uint4* __restrict__ shift, int sft_groups,
+                                                                 const float* __restrict__ s_next, uint4* __restrict__ da,
+                                                                 int accumulate, uint4* __restrict__ dscale,
+                                                                 uint4* __restrict__ dshift, float* __restrict__ ds, long long P,
+                                                                 int groups, int row_groups) {
+  __shared__ float part[kTrThreads][9];
+  const int gi = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = kTrThreads / groups;
+  const int grp = blockIdx.y * groups + gi;  // channel group inside the row
+  const long long b = blockIdx.z;
+  const int gs = grp - (row_groups - sft_groups);
+  const bool sft = scale != nullptr && gs >= 0;
+  float sn[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sn[j] = (s_next != nullptr) ? __ldg(s_next + (b * row_groups + grp) * 8 + j) : 1.f;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < P; p += (long long)gridDim.x * lanes) {
+    const long long pix = b * P + p;
+    const long long i = pix * row_groups + grp;
+    float gv[8], av[8];
+    tr_unpack(__ldcs(g + i), gv);
+    tr_unpack(__ldg(a + b * a_sb_groups + p * row_groups + grp), av);
+    float dov[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dov[j] = gv[j] * sn[j];
+    if (sft) {
+      float sc[8], sh[8], t[8];
+      tr_unpack(__ldcs(scale + pix * sft_groups + gs), sc);
+      tr_unpack(__ldcs(shift + pix * sft_groups + gs), sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv[j], fmaf(av[j], sc[j], sh[j]), acc[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = dov[j] * av[j];
+      dscale[pix * sft_groups + gs] = tr_pack(t);
+      dshift[pix * sft_groups + gs] = tr_pack(dov);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dov[j] *= sc[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv[j], av[j], acc[j]);
+    }
+    if (da != nullptr) {
+      if (accumulate) {
+        float old[8];
+        tr_unpack(da[i], old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dov[j] += old[j];
+      }
+      da[i] = tr_pack(dov);
+    }
+  }
+  if (ds != nullptr) tr_reduce_add(acc, ds + (b * row_groups + (long long)blockIdx.y * groups) * 8, groups, lanes, part);
+}
+
+// ------------------------------------------------------------------------------------------ StyleConv tail, backward
+// a = lrelu(y + gain * noise + bias) * sqrt 2 (saved output);  dz = da * sqrt 2 * (a > 0 ? 1 : 0.2);
+// y reconstructed from a;  dd[b][c] += sum_p dz * y;  out = dz * oscale[b][c] * mul
+__global__ void __launch_bounds__(kTrThreads) style_act_bwd_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a,
+                                                                   const float* __restrict__ noise, long long noise_sb,
+                                                                   const float* __restrict__ noise_gain,
+                                                                   const float* __restrict__ bias,
+                                                                   const float* __restrict__ oscale, float mul,
+                                                                   uint4* __restrict__ out, float* __restrict__ dd, long long P,
+                                                                   int groups, int row_groups) {
+  __shared__ float part[kTrThreads][9];
+  const int gi = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = kTrThreads / groups;
+  const int grp = blockIdx.y * groups + gi;
+  const long long b = blockIdx.z;
+  float bs[8], os[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bs[j] = (bias != nullptr) ? __ldg(bias + grp * 8 + j) : 0.f;
+    os[j] = ((oscale != nullptr) ? __ldg(oscale + (b * row_groups + grp) * 8 + j) : 1.f) * mul;
+  }
+  const float gain = (noise != nullptr) ? __ldg(noise_gain) : 0.f;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < P; p += (long long)gridDim.x * lanes) {
+    const long long i = (b * P + p) * row_groups + grp;
+    float dv[8], av[8], o[8];
+    tr_unpack(__ldcs(da + i), dv);
+    tr_unpack(__ldcs(a + i), av);
+    const float nz = (noise != nullptr) ? gain * __ldg(noise + b * noise_sb + p) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool pos = av[j] > 0.f;
+      const float dz = dv[j] * (pos ? kTrSqrt2 : 0.2f * kTrSqrt2);
+      const float y = av[j] * (pos ? (1.f / kTrSqrt2) : (1.f / (0.2f * kTrSqrt2))) - nz - bs[j];
+      acc[j] = fmaf(dz, y, acc[j]);
+      o[j] = dz * os[j];
+    }
+    out[i] = tr_pack(o);
+  }
+  if (dd != nullptr) tr_reduce_add(acc, dd + (b * row_groups + (long long)blockIdx.y * groups) * 8, groups, lanes, part);
+}
+
+// ------------------------------------------------------------------------------------------ ToRGB, backward
+// t[c] = sum_o drgb[b][o][p] * w[o][c];  da (+)= s[b][c] * t;  ds[b][c] += sum_p a * t
+__global__ void __launch_bounds__(kTrThreads) to_rgb_bwd_kernel(const float* __restrict__ drgb, const uint4* __restrict__ a,
+                                                                const float* __restrict__ w, const float* __restrict__ s,
+                                                                uint4* __restrict__ da, int accumulate, float* __restrict__ ds,
+                                                                long long P, int groups, int row_groups) {
+  __shared__ float part[kTrThreads][9];
+  const int gi = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = kTrThreads / groups;
+  const int grp = blockIdx.y * groups + gi;
+  const long long b = blockIdx.z;
+  const int C = row_groups * 8;
+  float w0[8], w1[8], w2[8], sv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    w0[j] = __ldg(w + grp * 8 + j);
+    w1[j] = __ldg(w + C + grp * 8 + j);
+    w2[j] = __ldg(w + 2 * C + grp * 8 + j);
+    sv[j] = (s != nullptr) ? __ldg(s + (b * row_groups + grp) * 8 + j) : 1.f;
+  }
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const float* dr = drgb + b * 3 * P;
+  for (long long p = (long long)blockIdx.x * lanes + lane; p < P; p += (long long)gridDim.x * lanes) {
+    const long long i = (b * P + p) * row_groups + grp;
+    const float d0 = __ldg(dr + p), d1 = __ldg(dr + P + p), d2 = __ldg(dr + 2 * P + p);
+    float av[8], o[8];
+    tr_unpack(__ldcs(a + i), av);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = fmaf(d0, w0[j], fmaf(d1, w1[j], d2 * w2[j]));
+      acc[j] = fmaf(av[j], t, acc[j]);
+      o[j] = t * sv[j];
+    }
+    if (da != nullptr) {
+      if (accumulate) {
+        float old[8];
+        tr_unpack(da[i], old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += old[j];
+      }
+      da[i] = tr_pack(o);
+    }
+  }
+  if (ds != nullptr) tr_reduce_add(acc, ds + (b * row_groups + (long long)blockIdx.y * groups) * 8, groups, lanes, part);
+}
+
+// adjoint of upfirdn2d(skip, FIR * 4, up = 2, pad = (2, 1)) on fp32 planes: per axis
+//   out[k] = .25 d[2k-1] + .75 d[2k] + .75 d[2k+1] + .25 d[2k+2]   (d = 0 outside)
+__global__ void __launch_bounds__(kTrThreads) rgb_up_adjoint_kernel(const float* __restrict__ d, float* __restrict__ out,
+                                                                    long long n, int h, int w) {
+  const long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x;
+  if (idx >= n) return;
+  const int x = (int)(idx % w);
+  const int y = (int)((idx / w) % h);
+  const long long pl = idx / ((long long)w * h);
+  const float* dp = d + pl * 4 * h * w;
+  const int H2 = 2 * h, W2 = 2 * w;
+  float s = 0.f;
+#pragma unroll
+  for (int ty = 0; ty < 4; ++ty) {
+    const int yy = 2 * y - 1 + ty;
+    if (yy < 0 || yy >= H2) continue;
+    const float wy = (ty == 0 || ty == 3) ? 0.25f : 0.75f;
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) {
+      const int xx = 2 * x - 1 + tx;
+      if (xx < 0 || xx >= W2) continue;
+      s += wy * ((tx == 0 || tx == 3) ? 0.25f : 0.75f) * __ldg(dp + (long long)yy * W2 + xx);
+    }
+  }
+  out[idx] = s;
+}
+
+// ------------------------------------------------------------------------------------------ style gradients (tables)
+// ds[b][ci] -= scale2 * s[b][ci] * sum_co dd[b][co] * d[b][co]^2 * wsq[co][ci]   (one CTA per image)
+__global__ void __launch_bounds__(kTrThreads) demod_bwd_kernel(float* __restrict__ ds, const float* __restrict__ s,
+                                                               const float* __restrict__ dd, const float* __restrict__ d,
+                                                               const float* __restrict__ wsq, float scale2, int cin, int cout) {
+  extern __shared__ float t[];  // [cout]
+  const long long b = blockIdx.x;
+  for (int co = threadIdx.x; co < cout; co += kTrThreads) {
+    const float dv = d[b * cout + co];
+    t[co] = dd[b * cout + co] * dv * dv;
+  }
+  __syncthreads();
+  for (int ci = threadIdx.x; ci < cin; ci += kTrThreads) {
+    float acc = 0.f;
+    for (int co = 0; co < cout; ++co) acc = fmaf(t[co], __ldg(wsq + (long long)co * cin + ci), acc);
+    ds[b * cin + ci] -= scale2 * s[b * cin + ci] * acc;
+  }
+}
+
+// dlat[b][lat_idx][f] += wscale * sum_ci ds[b][ci] * w[ci][f]   (one CTA per image)
+__global__ void __launch_bounds__(kTrThreads) mod_linear_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ w,
+                                                                    float wscale, float* __restrict__ dlat, int L, int F,
+                                                                    int lat_idx, int cin) {
+  extern __shared__ float t[];  // [cin]
+  const long long b = blockIdx.x;
+  for (int ci = threadIdx.x; ci < cin; ci += kTrThreads) t[ci] = ds[b * cin + ci];
+  __syncthreads();
+  for (int f = threadIdx.x; f < F; f += kTrThreads) {
+    float acc = 0.f;
+    for (int ci = 0; ci < cin; ++ci) acc = fmaf(t[ci], __ldg(w + (long long)ci * F + f), acc);
+    dlat[(b * L + lat_idx) * F + f] += wscale * acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ first conv, input gradient
+// dx[b][k][p] (+)= sum_c dz[b][p][c] * w[c][k], k = 0..2: one thread per pixel (coalesced fp32 NCHW stores)
+__global__ void __launch_bounds__(kTrThreads) first_conv_dgrad_kernel(const uint4* __restrict__ dz, const float* __restrict__ w,
+                                                                      float* __restrict__ dx, int accumulate, long long n_pix,
+                                                                      int HW, int cout) {
+  extern __shared__ float sw[];  // [cout * 3]
+  for (int i = threadIdx.x; i < cout * 3; i += kTrThreads) sw[i] = w[i];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x;
+  if (idx >= n_pix) return;
+  const int groups = cout / 8;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int g = 0; g < groups; ++g) {
+    float v[8];
+    tr_unpack(__ldcs(dz + idx * groups + g), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wc = sw + (g * 8 + j) * 3;
+      a0 = fmaf(v[j], wc[0], a0);
+      a1 = fmaf(v[j], wc[1], a1);
+      a2 = fmaf(v[j], wc[2], a2);
+    }
+  }
+  const long long b = idx / HW, p = idx - b * HW;
+  float* o = dx + b * 3 * HW + p;
+  if (accumulate) {
+    a0 += o[0];
+    a1 += o[HW];
+    a2 += o[2 * (long long)HW];
+  }
+  o[0] = a0;
+  o[HW] = a1;
+  o[2 * (long long)HW] = a2;
+}
+
+// ------------------------------------------------------------------------------------------ toRGB heads <-> fp32 NCHW
+// head [B][P][cpad] fp16 (channels 0..2 = the image) -> rgb fp32 [B][3][P], and the adjoint (zero fill of channels 3..)
+__global__ void __launch_bounds__(kTrThreads) head_to_nchw_kernel(const __half* __restrict__ head, float* __restrict__ rgb,
+                                                                  long long n_pix, long long P, int cpad) {
+  const long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x;
+  if (idx >= n_pix) return;
+  const long long b = idx / P, p = idx - b * P;
+  const uint2 q = *reinterpret_cast<const uint2*>(head + idx * cpad);
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+  const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+  float* o = rgb + b * 3 * P + p;
+  o[0] = f0.x;
+  o[P] = f0.y;
+  o[2 * P] = f1.x;
+}
+__global__ void __launch_bounds__(kTrThreads) nchw_to_head_kernel(const float* __restrict__ drgb, __half* __restrict__ dhead,
+                                                                  long long n_pix, long long P, int cpad) {
+  const long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x;
+  if (idx >= n_pix) return;
+  const long long b = idx / P, p = idx - b * P;
+  const float* d = drgb + b * 3 * P + p;
+  uint4 q = make_uint4(0u, 0u, 0u, 0u);
+  __half2* h = reinterpret_cast<__half2*>(&q);
+  h[0] = f2h2_sat(d[0], d[P]);
+  h[1] = f2h2_sat(d[2 * P], 0.f);
+  uint4* o = reinterpret_cast<uint4*>(dhead + idx * cpad);
+  o[0] = q;
+  for (int k = 1; k < cpad / 8; ++k) o[k] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ------------------------------------------------------------------------------------------ losses
+// L1Loss(reduction='mean') * weight: loss[0] += weight / n * sum |x - t|;  grad = gscale * sign(x - t) (0 at ties, as torch)
+__global__ void __launch_bounds__(kTrThreads) l1_loss_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                             long long n, float lscale, float gscale, float* __restrict__ loss,
+                                                             float* __restrict__ grad) {
+  __shared__ float red[kTrThreads / 32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTrThreads) {
+    const float d = __ldcs(x + i) - __ldcs(t + i);
+    acc += fabsf(d);
+    if (grad != nullptr) grad[i] = d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kTrThreads / 32; ++i) s += red[i];
+    atomicAdd(loss, s * lscale);
+  }
+}
+
+// GANLoss('wgan_softplus'): loss[0] += weight / n * sum softplus(sign * pred);  dpred = gscale * sign * sigmoid(sign * pred)
+__global__ void __launch_bounds__(kTrThreads) softplus_loss_kernel(const __half* __restrict__ pred, int n, int stride, float sign,
+                                                                   float lscale, float gscale, float* __restrict__ loss,
+                                                                   __half* __restrict__ dpred) {
+  __shared__ float red[kTrThreads / 32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += kTrThreads) {
+    const float v = sign * __half2float(pred[(long long)i * stride]);
+    acc += fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));  // softplus without overflow
+    if (dpred != nullptr) dpred[(long long)i * stride] = __float2half_rn(gscale * sign / (1.f + expf(-v)));
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kTrThreads / 32; ++i) s += red[i];
+    atomicAdd(loss, s * lscale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+__global__ void __launch_bounds__(kTrThreads) pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout,
+                                                                  int cin, int kh, int kw, float scale, int mode, int cin_pad) {
+  const int taps = kh * kw;
+  const long long n = (mode == 0) ? (long long)cout * taps * cin_pad : (long long)cin * taps * cout;
+  for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
+    float v = 0.f;
+    if (mode == 0) {
+      const int ci = (int)(idx % cin_pad);
+      const int t = (int)((idx / cin_pad) % taps);
+      const int co = (int)(idx / ((long long)cin_pad * taps));
+      if (ci < cin) v = w[((long long)co * cin + ci) * taps + t];
+    } else {
+      const int co = (int)(idx % cout);
+      const int t = (int)((idx / cout) % taps);
+      const int ci = (int)(idx / ((long long)cout * taps));
+      v = w[((long long)co * cin + ci) * taps + (taps - 1 - t)];  // flipped tap: (kh-1-i)*kw + (kw-1-j) = taps-1 - (i*kw+j)
+    }
+    out[idx] = __float2half_rn(v * scale);
+  }
+}
+
+}  // namespace b200ir
+
+using namespace b200ir;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+static inline unsigned tr_grid(long long n, int sms, int per_sm) {
+  long long g = (n + kTrThreads - 1) / kTrThreads;
+  const long long cap = (long long)sms * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+extern "C" int b200ir_sft_mod(const void* a, const void* scale, const void* shift, int c_sft, const float* s_next, void* out,
+                              int B, int64_t P, int C, void* stream) {
+  B200IR_REQUIRE(a && out && B > 0 && P > 0 && C > 0 && C % 8 == 0, "sft_mod: bad arguments");
+  B200IR_REQUIRE((scale == nullptr) == (shift == nullptr), "sft_mod: scale / shift must come together");
+  B200IR_REQUIRE(scale == nullptr || (c_sft > 0 && c_sft % 8 == 0 && c_sft <= C), "sft_mod: c_sft=%d", c_sft);
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const long long n = (long long)B * P * (C / 8);
+  sft_mod_kernel<<<tr_grid(n, sms, 16), kTrThreads, 0, STREAM>>>((const uint4*)a, (const uint4*)scale, (const uint4*)shift,
+                                                                 scale ? c_sft / 8 : 0, s_next, (uint4*)out, n, P, C / 8);
+  return check_launch("sft_mod");
+}
+
+extern "C" int b200ir_sft_mod_bwd(const void* g, const void* a, int64_t a_stride_b, const void* scale, const void* shift,
+                                  int c_sft, const float* s_next, void* da, int accumulate, void* dscale, void* dshift,
+                                  float* ds, int B, int64_t P, int C, void* stream) {
+  B200IR_REQUIRE(g && a && B > 0 && P > 0 && C > 0 && C % 8 == 0 && a_stride_b % 8 == 0, "sft_mod_bwd: bad arguments");
+  B200IR_REQUIRE((scale == nullptr) == (shift == nullptr), "sft_mod_bwd: scale / shift must come together");
+  B200IR_REQUIRE(scale == nullptr || (c_sft > 0 && c_sft % 8 == 0 && c_sft <= C && dscale && dshift),
+                 "sft_mod_bwd: c_sft=%d needs dscale / dshift", c_sft);
+  B200IR_REQUIRE(da || ds || dscale, "sft_mod_bwd: nothing to compute");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const TrLayout l = tr_layout(C, P, sms, B);
+  sft_mod_bwd_kernel<<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(
+      (const uint4*)g, (const uint4*)a, a_stride_b / 8, (const uint4*)scale, (const uint4*)shift, scale ? c_sft / 8 : 0, s_next,
+      (uint4*)da, accumulate, (uint4*)dscale, (uint4*)dshift, ds, P, l.groups, C / 8);
+  return check_launch("sft_mod_bwd");
+}
+
+extern "C" int b200ir_style_act_bwd(const void* da, const void* a, const float* noise, int64_t noise_stride_b,
+                                    const float* noise_gain, const float* bias, const float* oscale, float mul, void* out,
+                                    float* dd, int B, int64_t P, int C, void* stream) {
+  B200IR_REQUIRE(da && a && out && B > 0 && P > 0 && C > 0 && C % 8 == 0, "style_act_bwd: bad arguments");
+  B200IR_REQUIRE(noise == nullptr || noise_gain != nullptr, "style_act_bwd: noise without gain");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const TrLayout l = tr_layout(C, P, sms, B);
+  style_act_bwd_kernel<<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(
+      (const uint4*)da, (const uint4*)a, noise, noise_stride_b, noise_gain, bias, oscale, mul, (uint4*)out, dd, P, l.groups,
+      C / 8);
+  return check_launch("style_act_bwd");
+}
+
+extern "C" int b200ir_to_rgb_bwd(const float* drgb, const void* a, const float* w, const float* s, void* da, int accumulate,
+                                 float* ds, int B, int64_t P, int C, void* stream) {
+  B200IR_REQUIRE(drgb && a && w && (da || ds) && B > 0 && P > 0 && C > 0 && C % 8 == 0, "to_rgb_bwd: bad arguments");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const TrLayout l = tr_layout(C, P, sms, B);
+  to_rgb_bwd_kernel<<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(drgb, (const uint4*)a, w, s, (uint4*)da, accumulate,
+                                                                           ds, P, l.groups, C / 8);
+  return check_launch("to_rgb_bwd");
+}
+
+extern "C" int b200ir_rgb_up_adjoint(const float* d, float* out, int planes, int h, int w, void* stream) {
+  B200IR_REQUIRE(d && out && planes > 0 && h > 0 && w > 0, "rgb_up_adjoint: bad arguments");
+  const long long n = (long long)planes * h * w;
+  rgb_up_adjoint_kernel<<<(unsigned)((n + kTrThreads - 1) / kTrThreads), kTrThreads, 0, STREAM>>>(d, out, n, h, w);
+  return check_launch("rgb_up_adjoint");
+}
+
+extern "C" int b200ir_demod_bwd(float* ds, const float* s, const float* dd, const float* d, const float* wsq, float scale2, int B,
+                                int cin, int cout, void* stream) {
+  B200IR_REQUIRE(ds && s && dd && d && wsq && B > 0 && cin > 0 && cout > 0 && cout <= 8192, "demod_bwd: bad arguments");
+  demod_bwd_kernel<<<B, kTrThreads, cout * sizeof(float), STREAM>>>(ds, s, dd, d, wsq, scale2, cin, cout);
+  return check_launch("demod_bwd");
+}
+
+extern "C" int b200ir_mod_linear_bwd(const float* ds, const float* w, float wscale, float* dlat, int L, int F, int lat_idx, int B,
+                                     int cin, void* stream) {
+  B200IR_REQUIRE(ds && w && dlat && B > 0 && cin > 0 && cin <= 8192 && F > 0 && lat_idx >= 0 && lat_idx < L,
+                 "mod_linear_bwd: bad arguments");
+  mod_linear_bwd_kernel<<<B, kTrThreads, cin * sizeof(float), STREAM>>>(ds, w, wscale, dlat, L, F, lat_idx, cin);
+  return check_launch("mod_linear_bwd");
+}
+
+extern "C" int b200ir_first_conv_dgrad(const void* dz, const float* w, float* dx, int accumulate, int B, int H, int W, int cout,
+                                       void* stream) {
+  B200IR_REQUIRE(dz && w && dx && B > 0 && H > 0 && W > 0 && cout > 0 && cout % 8 == 0 && cout <= 1024,
+                 "first_conv_dgrad: bad arguments");
+  const long long n = (long long)B * H * W;
+  first_conv_dgrad_kernel<<<(unsigned)((n + kTrThreads - 1) / kTrThreads), kTrThreads, cout * 3 * sizeof(float), STREAM>>>(
+      (const uint4*)dz, w, dx, accumulate, n, H * W, cout);
+  return check_launch("first_conv_dgrad");
+}
+
+extern "C" int b200ir_head_to_nchw(const void* head, float* rgb, int B, int64_t P, int cpad, void* stream) {
+  B200IR_REQUIRE(head && rgb && B > 0 && P > 0 && cpad >= 8 && cpad % 8 == 0, "head_to_nchw: bad arguments");
+  const long long n = (long long)B * P;
+  head_to_nchw_kernel<<<(unsigned)((n + kTrThreads - 1) / kTrThreads), kTrThreads, 0, STREAM>>>((const __half*)head, rgb, n, P,
+                                                                                               cpad);
+  return check_launch("head_to_nchw");
+}
+
+extern "C" int b200ir_nchw_to_head(const float* drgb, void* dhead, int B, int64_t P, int cpad, void* stream) {
+  B200IR_REQUIRE(drgb && dhead && B > 0 && P > 0 && cpad >= 8 && cpad % 8 == 0, "nchw_to_head: bad arguments");
+  const long long n = (long long)B * P;
+  nchw_to_head_kernel<<<(unsigned)((n + kTrThreads - 1) / kTrThreads), kTrThreads, 0, STREAM>>>(drgb, (__half*)dhead, n, P,
+                                                                                               cpad);
+  return check_launch("nchw_to_head");
+}
+
+extern "C" int b200ir_l1_loss(const float* x, const float* t, int64_t n, float weight, float grad_scale, float* loss, float* grad,
+                              void* stream) {
+  B200IR_REQUIRE(x && t && loss && n > 0, "l1_loss: bad arguments");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  l1_loss_kernel<<<tr_grid(n, sms, 8), kTrThreads, 0, STREAM>>>(x, t, n, weight / (float)n, grad_scale * weight / (float)n, loss,
+                                                                grad);
+  return check_launch("l1_loss");
+}
+
+extern "C" int b200ir_softplus_loss(const void* pred, int n, int stride, float sign, float weight, float grad_scale, float* loss,
+                                    void* dpred, void* stream) {
+  B200IR_REQUIRE(pred && loss && n > 0 && stride > 0 && (sign == 1.f || sign == -1.f), "softplus_loss: bad arguments");
+  softplus_loss_kernel<<<1, kTrThreads, 0, STREAM>>>((const __half*)pred, n, stride, sign, weight / (float)n,
+                                                     grad_scale * weight / (float)n, loss, (__half*)dpred);
+  return check_launch("softplus_loss");
+}
+
+extern "C" int b200ir_pack_weights(const float* w, void* out, int cout, int cin, int kh, int kw, float scale, int mode,
+                                   int cin_pad, void* stream) {
+  B200IR_REQUIRE(w && out && cout > 0 && cin > 0 && kh > 0 && kw > 0 && (mode == 0 || mode == 1), "pack_weights: bad arguments");
+  if (cin_pad == 0) cin_pad = cin;
+  B200IR_REQUIRE(cin_pad >= cin && (mode == 0 || cin_pad == cin), "pack_weights: cin_pad=%d", cin_pad);
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const long long n = (mode == 0) ? (long long)cout * kh * kw * cin_pad : (long long)cin * kh * kw * cout;
+  pack_weights_kernel<<<tr_grid(n, sms, 16), kTrThreads, 0, STREAM>>>(w, (__half*)out, cout, cin, kh, kw, scale, mode, cin_pad);
+  return check_launch("pack_weights");
+}

@@ -235,7 +235,17 @@ extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, flo
   // tools/sweep_wgrad.py; two waves were 20-45 % slower on every layer of the B = 64 step).
   int splits = sms / units;
   if (splits > p.num_tiles / 16) splits = p.num_tiles / 16;
-  if (const char* e = getenv("B200IR_WGRAD_SPLITS")) splits = atoi(e);  // tuning switch (tools/time_wgrad.py sweeps it)
+  {
+    // tuning switch (tools/sweep_wgrad.py), read once: a positive integer forces the split count; 1 = deterministic
+    // (one CTA per dW block, no cross-CTA atomics: the fp32 summation order is then fixed run to run)
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("B200IR_WGRAD_SPLITS");
+      const int v = e ? atoi(e) : 0;
+      forced = v > 0 ? v : 0;
+    }
+    if (forced > 0) splits = forced;
+  }
   if (splits > p.num_tiles) splits = p.num_tiles;
   if (splits < 1) splits = 1;
   p.splits = splits;

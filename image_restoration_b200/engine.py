@@ -80,44 +80,60 @@ class _Packed:
                 wsc=eq(f'{cs}.2.weight'), bsc=f32(f'{cs}.2.bias'), wsh=eq(f'{ch}.2.weight'), bsh=f32(f'{ch}.2.bias'),
                 wrgb=(wrgb[:, :, 0, 0] / math.sqrt(wrgb.shape[1])).contiguous(), brgb=f32(f'toRGB.{i}.bias')))
         # StyleGAN decoder
-        D = 'stylegan_decoder'
-        cst = g(f'{D}.constant_input.weight').float()[0]                       # (C, 4, 4r)
-        self.const = cst.permute(1, 2, 0).contiguous().to(F16)                 # [4][4r][C]
+        pack_decoder(self, net, g, f32)
 
-        def style_conv(p, upsample):
-            w = g(f'{p}.modulated_conv.weight').float()[0]                     # (cout, cin, 3, 3)
-            cout, cin = w.shape[:2]
-            scale = 1.0 / math.sqrt(cin * 9)
-            d = dict(cin=cin, cout=cout, scale2=scale * scale, wsq=w.pow(2).sum([2, 3]).contiguous(),
-                     mod_w=f32(f'{p}.modulated_conv.modulation.weight'), mod_b=f32(f'{p}.modulated_conv.modulation.bias'),
-                     gain=f32(f'{p}.weight'), bias=f32(f'{p}.activate.bias'))
-            if upsample:
-                ws = (w * scale).to(F16)
-                d['w_phase'] = [torch.cat([ws[:, :, kh, kw] for kh, kw in ops.convt_phase_taps(py, px)], 1).contiguous()
-                                for py, px in ops.CONVT_PHASES]
-                d['w_merged'] = ops.convt_merged_weight(w, scale)
-            else:
-                d['w'] = _pack_conv(w, scale)
-            return d
 
-        def rgb(p):
-            w = g(f'{p}.modulated_conv.weight').float()[0, :, :, 0, 0]         # (3, cin)
-            return dict(w=(w / math.sqrt(w.shape[1])).contiguous(), bias=f32(f'{p}.bias').reshape(3).contiguous(),
-                        mod_w=f32(f'{p}.modulated_conv.modulation.weight'),
-                        mod_b=f32(f'{p}.modulated_conv.modulation.bias'))
+def pack_decoder(self, net, g, f32, train=False):
+    """Packs the StyleGAN2 decoder's weights (stylegan2_ocr_arch.py:408-497) onto `self`: const, sc1, rgb1, sconv[], rgbs[],
+    stored_noise[], mod_wscale and the style MLP.  g(key) -> tensor on the device, f32(key) -> contiguous fp32 copy.
+    Shared by the inference engine (_Packed) and the training path (train.DecoderState: with fix_decoder=True these never
+    change, so they are packed once, not per optimiser step).  train=True adds the adjoint weight packs of the input-gradient
+    convs (`w_dgrad`: [cin][9*cout])."""
+    dev = self.dev
+    L = net.log_size - 2
+    self.L = L
+    D = 'stylegan_decoder'
+    cst = g(f'{D}.constant_input.weight').float()[0]                       # (C, 4, 4r)
+    self.const = cst.permute(1, 2, 0).contiguous().to(F16)                 # [4][4r][C]
 
-        self.sc1 = style_conv(f'{D}.style_conv1', False)
-        self.rgb1 = rgb(f'{D}.to_rgb1')
-        self.sconv = [style_conv(f'{D}.style_convs.{j}', j % 2 == 0) for j in range(2 * L)]
-        self.rgbs = [rgb(f'{D}.to_rgbs.{i}') for i in range(L)]
-        self.stored_noise = [f32(f'{D}.noises.noise{j}') for j in range(2 * L + 1)]
-        self.mod_wscale = 1.0 / math.sqrt(net.num_style_feat)
-        # style MLP (only executed when input_is_latent=False)
-        self.mlp_w = torch.stack([g(f'{D}.style_mlp.{i}.weight').float() for i in range(1, net.num_mlp + 1)]).contiguous() \
-            if net.num_mlp > 0 else torch.zeros(0, net.num_style_feat, net.num_style_feat, device=dev)
-        self.mlp_b = torch.stack([g(f'{D}.style_mlp.{i}.bias').float() for i in range(1, net.num_mlp + 1)]).contiguous() \
-            if net.num_mlp > 0 else torch.zeros(0, net.num_style_feat, device=dev)
-        self.mlp_lr_mul = float(net.stylegan_decoder.style_mlp[1].lr_mul) if net.num_mlp > 0 else 1.0
+    def style_conv(p, upsample):
+        w = g(f'{p}.modulated_conv.weight').float()[0]                     # (cout, cin, 3, 3)
+        cout, cin = w.shape[:2]
+        scale = 1.0 / math.sqrt(cin * 9)
+        d = dict(cin=cin, cout=cout, scale2=scale * scale, wsq=w.pow(2).sum([2, 3]).contiguous(),
+                 mod_w=f32(f'{p}.modulated_conv.modulation.weight'), mod_b=f32(f'{p}.modulated_conv.modulation.bias'),
+                 gain=f32(f'{p}.weight'), bias=f32(f'{p}.activate.bias'))
+        if upsample:
+            ws = (w * scale).to(F16)
+            d['w_phase'] = [torch.cat([ws[:, :, kh, kw] for kh, kw in ops.convt_phase_taps(py, px)], 1).contiguous()
+                            for py, px in ops.CONVT_PHASES]
+            d['w_merged'] = ops.convt_merged_weight(w, scale)
+            if train:   # adjoint of conv_transpose2d(stride 2) = the stride-2 conv with in / out channels exchanged (no flip)
+                d['w_dgrad'] = _pack_conv(w.permute(1, 0, 2, 3), scale)
+        else:
+            d['w'] = _pack_conv(w, scale)
+            if train:   # adjoint of the stride-1 'same' conv = the same conv with flipped taps and exchanged channels
+                d['w_dgrad'] = ops.conv_dgrad_weight(d['w'], cin)
+        return d
+
+    def rgb(p):
+        w = g(f'{p}.modulated_conv.weight').float()[0, :, :, 0, 0]         # (3, cin)
+        return dict(w=(w / math.sqrt(w.shape[1])).contiguous(), bias=f32(f'{p}.bias').reshape(3).contiguous(),
+                    mod_w=f32(f'{p}.modulated_conv.modulation.weight'),
+                    mod_b=f32(f'{p}.modulated_conv.modulation.bias'))
+
+    self.sc1 = style_conv(f'{D}.style_conv1', False)
+    self.rgb1 = rgb(f'{D}.to_rgb1')
+    self.sconv = [style_conv(f'{D}.style_convs.{j}', j % 2 == 0) for j in range(2 * L)]
+    self.rgbs = [rgb(f'{D}.to_rgbs.{i}') for i in range(L)]
+    self.stored_noise = [f32(f'{D}.noises.noise{j}') for j in range(2 * L + 1)]
+    self.mod_wscale = 1.0 / math.sqrt(net.num_style_feat)
+    # style MLP (only executed when input_is_latent=False)
+    self.mlp_w = torch.stack([g(f'{D}.style_mlp.{i}.weight').float() for i in range(1, net.num_mlp + 1)]).contiguous() \
+        if net.num_mlp > 0 else torch.zeros(0, net.num_style_feat, net.num_style_feat, device=dev)
+    self.mlp_b = torch.stack([g(f'{D}.style_mlp.{i}.bias').float() for i in range(1, net.num_mlp + 1)]).contiguous() \
+        if net.num_mlp > 0 else torch.zeros(0, net.num_style_feat, device=dev)
+    self.mlp_lr_mul = float(net.stylegan_decoder.style_mlp[1].lr_mul) if net.num_mlp > 0 else 1.0
 
 
 class PwOp:

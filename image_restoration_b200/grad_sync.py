@@ -32,6 +32,29 @@ class GradAllReducer:
         self.stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
 
     @torch.no_grad()
+    def reduce_flat(self):
+        """Packs the current .grad of every parameter into the flat buffer, all-reduces it (SUM, bucketed, on the side stream)
+        and returns the flat buffer WITHOUT averaging or unpacking: optim.FlatAdam.step(flat_grad=..., grad_scale=1 / world)
+        consumes it directly, which saves the unpack / re-pack passes of sync()."""
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                works = [dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                         for s, e in self.buckets]
+                for w in works:
+                    w.wait()
+            torch.cuda.current_stream().wait_stream(self.stream)
+        else:
+            for s, e in self.buckets:
+                dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group)
+        return self.flat
+
+    @torch.no_grad()
     def sync(self, average=True):
         """All-reduces the current .grad of every parameter across the group (sum, then / world when `average`) and
         writes the result back into .grad (allocating zeros for parameters that had none, like DDP with

@@ -100,8 +100,10 @@ def restore_host(net, x_host, y_host=None, chunks=1):
     if pipe is None:
         pipe = HostPipeline(net)
         net._host_pipe = pipe
-    if y_host is None:
-        y_host = torch.empty(x_host.shape, dtype=torch.float32).pin_memory()
+    if y_host is None:       # uint8 HWC images come back as uint8 HWC images (api.py:105), float batches as float32
+        y_host = torch.empty(x_host.shape, dtype=torch.uint8 if x_host.dtype == torch.uint8 else torch.float32).pin_memory()
+    elif (x_host.dtype == torch.uint8) != (y_host.dtype == torch.uint8):
+        raise ValueError('restore_host: uint8 input needs a uint8 output buffer (and float input a float one)')
     b = x_host.shape[0]
     step = -(-b // chunks)
     tickets = [pipe.submit(x_host[i:i + step], y_host[i:i + step]) for i in range(0, b, step)]

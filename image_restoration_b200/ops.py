@@ -33,7 +33,8 @@ def _ptr(t):
 
 
 def _req(t, dtype, name):
-    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+    _lib.require_cuda(t, f'ops ({name})')
+    if not (t.dtype == dtype and t.is_contiguous()):
         raise ValueError(f'{name}: expected contiguous CUDA {dtype}, got {t.dtype} on {t.device}')
 
 
@@ -135,7 +136,7 @@ class ConvOp:
         self.desc = d
         # keep every tensor alive as long as the op exists
         self._keep = (weight, out, bias, demod, noise, noise_gain, res, out_scale, rgb_w, rgb_part)
-        self._fn = _lib.lib().b200ir_conv_igemm
+        self._plan = None
 
     def attach_rgb(self, rgb_w, hw, no_store=False):
         """Fuse ToRGB into this conv's epilogue: rgb_w fp32 [B][3][cout]; returns the partial-plane buffer
@@ -148,10 +149,43 @@ class ConvOp:
         d.rgb_h, d.rgb_w_px = hw
         d.no_store = 1 if no_store else 0
         self._keep = self._keep + (rgb_w, part)
+        self._plan = None
         return part
 
     def __call__(self):
-        check(self._fn(C.byref(self.desc), _stream()), 'b200ir_conv_igemm')
+        """Launch through a b200ir_conv_plan: validation, tensor-map encoding and tile sizing happen once per distinct
+        descriptor (pointers included), not once per launch."""
+        if self._plan is None:
+            self._plan = _conv_plan(self.desc)
+        check(_lib.lib().b200ir_conv_plan_launch(self._plan, _stream()), 'b200ir_conv_plan_launch')
+
+
+class _PlanCache:
+    """Descriptor bytes -> b200ir_conv_plan handle (LRU).  The training-step Functions build a fresh ConvOp per call, but
+    the caching allocator hands the same buffers back step after step, so the same descriptors recur."""
+
+    def __init__(self, capacity=8192):
+        self.capacity = capacity
+        self.plans = {}
+
+    def get(self, desc):
+        key = bytes(desc)
+        plan = self.plans.pop(key, None)
+        if plan is None:
+            handle = C.c_void_p()
+            check(_lib.lib().b200ir_conv_plan_create(C.byref(desc), C.byref(handle)), 'b200ir_conv_plan_create')
+            plan = handle
+            while len(self.plans) >= self.capacity:
+                _lib.lib().b200ir_conv_plan_destroy(self.plans.pop(next(iter(self.plans))))
+        self.plans[key] = plan              # most recently used last
+        return plan
+
+
+_PLANS = _PlanCache()
+
+
+def _conv_plan(desc):
+    return _PLANS.get(desc)
 
 
 def taps_3x3():
@@ -622,3 +656,103 @@ def first_conv_wgrad(x, dz):
     dw = torch.empty(cout, 3, device=x.device, dtype=torch.float32)
     check(_lib.lib().b200ir_first_conv_wgrad(_ptr(x), _ptr(dz), _ptr(dw), b, h, w, cout, _stream()), 'first_conv_wgrad')
     return dw
+
+
+# ------------------------------------------------------------------------------------------ training step (train_ops.cu)
+def _zeros32(dev, *shape):
+    return torch.zeros(*shape, device=dev, dtype=torch.float32)
+
+
+def sft_mod(a, scale, shift, s_next, out):
+    """SFT + next modulation, training forward (b200ir_sft_mod): a, out NHWC fp16 [B,h,w,C]; scale / shift [B,h,w,c_sft] or None."""
+    b, h, w, c = a.shape
+    check(_lib.lib().b200ir_sft_mod(_ptr(a), _ptr(scale), _ptr(shift), scale.shape[3] if scale is not None else 0,
+                                    _ptr(s_next), _ptr(out), b, h * w, c, _stream()), 'sft_mod')
+
+
+def sft_mod_bwd(g, a, scale, shift, s_next, da, accumulate, dscale, dshift, ds, a_broadcast=False):
+    """b200ir_sft_mod_bwd: g NHWC fp16 [B,h,w,C]; a [B,h,w,C] (or [h,w,C] shared by all images when a_broadcast)."""
+    b, h, w, c = g.shape
+    check(_lib.lib().b200ir_sft_mod_bwd(_ptr(g), _ptr(a), 0 if a_broadcast else h * w * c, _ptr(scale), _ptr(shift),
+                                        scale.shape[3] if scale is not None else 0, _ptr(s_next), _ptr(da),
+                                        1 if accumulate else 0, _ptr(dscale), _ptr(dshift), _ptr(ds), b, h * w, c, _stream()),
+          'sft_mod_bwd')
+
+
+def style_act_bwd(da, a, noise, noise_gain, bias, oscale, mul, out, dd):
+    b, h, w, c = a.shape
+    check(_lib.lib().b200ir_style_act_bwd(_ptr(da), _ptr(a), _ptr(noise), h * w, _ptr(noise_gain), _ptr(bias), _ptr(oscale),
+                                          float(mul), _ptr(out), _ptr(dd), b, h * w, c, _stream()), 'style_act_bwd')
+
+
+def to_rgb_bwd(drgb, a, w, s, da, accumulate, ds):
+    b, h, wd, c = a.shape
+    _req(drgb, torch.float32, 'drgb')
+    check(_lib.lib().b200ir_to_rgb_bwd(_ptr(drgb), _ptr(a), _ptr(w), _ptr(s), _ptr(da), 1 if accumulate else 0, _ptr(ds), b,
+                                       h * wd, c, _stream()), 'to_rgb_bwd')
+
+
+def rgb_up_adjoint(d, out):
+    b, c, h, w = out.shape
+    _req(d, torch.float32, 'd')
+    check(_lib.lib().b200ir_rgb_up_adjoint(_ptr(d), _ptr(out), b * c, h, w, _stream()), 'rgb_up_adjoint')
+
+
+def demod_bwd(ds, s, dd, d, wsq, scale2):
+    b, cin = ds.shape
+    check(_lib.lib().b200ir_demod_bwd(_ptr(ds), _ptr(s), _ptr(dd), _ptr(d), _ptr(wsq), float(scale2), b, cin, wsq.shape[0],
+                                      _stream()), 'demod_bwd')
+
+
+def mod_linear_bwd(ds, w, wscale, dlat, lat_idx):
+    b, L, f = dlat.shape
+    check(_lib.lib().b200ir_mod_linear_bwd(_ptr(ds), _ptr(w), float(wscale), _ptr(dlat), L, f, lat_idx, b, ds.shape[1],
+                                           _stream()), 'mod_linear_bwd')
+
+
+def first_conv_dgrad(dz, w, dx, accumulate=False):
+    b, h, wd, cout = dz.shape
+    check(_lib.lib().b200ir_first_conv_dgrad(_ptr(dz), _ptr(w), _ptr(dx), 1 if accumulate else 0, b, h, wd, cout, _stream()),
+          'first_conv_dgrad')
+
+
+def head_to_nchw(head, rgb):
+    b, h, w, cpad = head.shape
+    check(_lib.lib().b200ir_head_to_nchw(_ptr(head), _ptr(rgb), b, h * w, cpad, _stream()), 'head_to_nchw')
+
+
+def nchw_to_head(drgb, dhead):
+    b, h, w, cpad = dhead.shape
+    _req(drgb, torch.float32, 'drgb')
+    check(_lib.lib().b200ir_nchw_to_head(_ptr(drgb), _ptr(dhead), b, h * w, cpad, _stream()), 'nchw_to_head')
+
+
+def l1_loss(x, t, weight, grad_scale, loss, grad):
+    """loss[0] += weight * mean|x - t|; grad = grad_scale * weight / n * sign(x - t)  (fp32, contiguous, same shape)."""
+    _req(x, torch.float32, 'x')
+    _req(t, torch.float32, 't')
+    assert x.shape == t.shape
+    check(_lib.lib().b200ir_l1_loss(_ptr(x), _ptr(t), x.numel(), float(weight), float(grad_scale), _ptr(loss), _ptr(grad),
+                                    _stream()), 'l1_loss')
+
+
+def softplus_loss(pred, sign, weight, grad_scale, loss, dpred):
+    """GANLoss('wgan_softplus') on fp16 scores [B, 1] (contiguous): sign = -1 for target_is_real."""
+    n = pred.shape[0]
+    stride = pred.stride(0)
+    assert dpred is None or dpred.stride(0) == stride, 'pred and dpred must share the element stride'
+    check(_lib.lib().b200ir_softplus_loss(_ptr(pred), n, stride, float(sign), float(weight), float(grad_scale), _ptr(loss),
+                                          _ptr(dpred), _stream()), 'softplus_loss')
+
+
+def pack_weights(w, scale, mode=0, cin_pad=0):
+    """b200ir_pack_weights: fp32 [cout, cin, kh, kw] -> fp16 [cout, taps*cin_pad] (mode 0) / [cin, taps*cout] (mode 1)."""
+    cout, cin, kh, kw = w.shape
+    _req(w, torch.float32, 'w')
+    if mode == 0:
+        out = torch.empty(cout, kh * kw * (cin_pad or cin), device=w.device, dtype=torch.float16)
+    else:
+        out = torch.empty(cin, kh * kw * cout, device=w.device, dtype=torch.float16)
+    check(_lib.lib().b200ir_pack_weights(_ptr(w), _ptr(out), cout, cin, kh, kw, float(scale), mode, cin_pad, _stream()),
+          'pack_weights')
+    return out

@@ -12,7 +12,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 
 class FlatAdam:
@@ -21,8 +21,7 @@ class FlatAdam:
         if not self.params:
             raise ValueError('no trainable parameters')
         dev = self.params[0].device
-        if dev.type != 'cuda':
-            raise RuntimeError('image_restoration_b200.optim.FlatAdam needs CUDA parameters (no CPU path)')
+        _lib.require_cuda(self.params[0], 'optim.FlatAdam')
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.empty(self.numel, device=dev, dtype=torch.float32)
@@ -31,6 +30,7 @@ class FlatAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.ema = None
         ema_params = list(ema_params) if ema_params is not None else None
+        self.ema_params = ema_params
         if ema_params is not None:
             assert [tuple(e.shape) for e in ema_params] == [tuple(p.shape) for p in self.params]
             self.ema = torch.empty_like(self.flat)
@@ -60,18 +60,23 @@ class FlatAdam:
                 else:
                     v.copy_(p.grad)
             flat_grad = self.grad
-        assert flat_grad.numel() == self.numel and flat_grad.dtype == torch.float32 and flat_grad.is_cuda
+        assert flat_grad.numel() == self.numel and flat_grad.dtype == torch.float32 and flat_grad.device == self.flat.device
         if ema_decay is not None and self.ema is None:
             raise ValueError('ema_decay given but no ema_params were registered')
         self.step_count += 1
         ema_ptr = C.c_void_p(self.ema.data_ptr()) if ema_decay is not None else C.c_void_p(0)
-        with torch.cuda.device(self.flat.device):
-            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        with _lib.device_ctx(self.flat.device):
+            st = ops._stream()
             _lib.check(_lib.lib().b200ir_adam_step(
                 C.c_void_p(self.flat.data_ptr()), C.c_void_p(flat_grad.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
                 C.c_void_p(self.exp_avg_sq.data_ptr()), self.numel, float(self.lr), float(self.betas[0]),
                 float(self.betas[1]), float(self.eps), float(self.weight_decay), self.step_count, float(grad_scale),
                 ema_ptr, float(ema_decay if ema_decay is not None else 0.0), st), 'b200ir_adam_step')
+        # the kernel wrote through raw pointers: tell autograd and the forward engines (OcrEngine.stale() compares the
+        # parameters' version counters) that the values changed, so saved-tensor checks and packed weights stay honest
+        torch.autograd.graph.increment_version(self.params)
+        if ema_decay is not None:
+            torch.autograd.graph.increment_version(self.ema_params)
 
     def zero_grad(self):
         for p in self.params:

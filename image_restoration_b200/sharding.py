@@ -21,6 +21,18 @@ def micro_batches(lo, hi, micro_batch):
     return [(s, min(s + micro_batch, hi)) for s in range(lo, hi, micro_batch)]
 
 
+def run_shard(fn, shard, micro_batch=64, out=None):
+    """Applies `fn` to one rank's shard in micro-batches.  With `out` (a preallocated tensor of the shard's output shape)
+    the results are written in place and `out` is returned; otherwise they are concatenated."""
+    spans = micro_batches(0, shard.shape[0], micro_batch)
+    if out is not None:
+        for s, e in spans:
+            out[s:e].copy_(fn(shard[s:e]))
+        return out
+    outs = [fn(shard[s:e]) for s, e in spans]
+    return torch.cat(outs, 0) if outs else None
+
+
 def run_sharded(fn, batch, rank, world, micro_batch=64):
     """Applies `fn` (micro-batch tensor -> tensor) to this rank's shard of `batch` and returns the shard's outputs
     concatenated (an empty tensor with the right trailing shape when the shard is empty)."""

@@ -17,6 +17,8 @@ def tile_positions(size, tile, overlap):
     """Start offsets of the tiles along one axis: stride tile - overlap, last one flush with the border."""
     if size < tile:
         raise ValueError(f'frame extent {size} is smaller than the tile {tile}')
+    if not 0 <= overlap < tile:
+        raise ValueError(f'overlap {overlap} must satisfy 0 <= overlap < tile ({tile})')
     stride = tile - overlap
     pos = list(range(0, size - tile, stride)) + [size - tile]
     return pos
@@ -40,6 +42,8 @@ class TiledRestorer:
     def __init__(self, net, overlap=32, micro_batch=64):
         if net.input_width != net.input_height:
             raise ValueError('tiling uses square tiles: build the network with input_width == input_height')
+        if not 0 <= overlap < net.input_width:
+            raise ValueError(f'overlap {overlap} must satisfy 0 <= overlap < tile ({net.input_width})')
         self.net, self.tile, self.overlap, self.micro_batch = net, net.input_width, overlap, micro_batch
         self._grid = {}
 

@@ -1,0 +1,459 @@
+"""The training step on the B200 kernels (BASELINE config 5): GFPGANModel.optimize_parameters
+(basicsr/models/gfpgan_model.py:494-691) for the plate configs (`fix_decoder: true`): one net_g update on
+l_g_pix + image-pyramid + l_g_gan, the EMA, one net_d update on the logistic loss — data-parallel with one NCCL all-reduce of
+the flat gradient buffer per network (base_model.py:62-76).
+
+    train_forward(net, lq)          differentiable GFPGANv1OCR.forward(lq, return_rgb=True): U-Net through backward.unet_forward,
+                                    the frozen StyleGAN2 decoder through FrozenDecoderFunction (input gradients only)
+    FrozenDecoderFunction           StyleGAN2OCRGeneratorSFT.forward (gfpganv1_ocr_arch.py:50-136) w.r.t. style code and SFT conditions
+    l1_loss / gan_softplus_loss     L1Loss(mean) / GANLoss('wgan_softplus') (losses/losses.py:81-106, 404-470), value + gradient in one pass
+    disc_forward_image              network_d on an fp32 NCHW image, with the input gradient the generator needs
+    GFPGANTrainer                   feed_data / optimize_parameters / model_ema, mirrors GFPGANModel for these options
+
+Gradients of activations are NHWC fp16: every loss is multiplied by a static loss scale (default 4096 x batch, so that
+d(loss)/d(pixel) of a mean-reduced loss lands near 1e-3..1e+2) that FlatAdam's grad_scale removes inside the fused step.
+torch runs the autograd graph, allocates buffers and owns the NCCL transport; all arithmetic is in libb200ir.so.
+"""
+import math
+import weakref
+
+import torch
+
+from . import _lib, ops
+from .backward import unet_forward
+from .engine import pack_decoder
+
+F16, F32 = torch.float16, torch.float32
+
+
+# ------------------------------------------------------------------------------------------ frozen decoder
+class DecoderState:
+    """Frozen StyleGAN2 decoder packed for the training path: forward operands + the adjoint weight packs of the input-gradient
+    convs.  Built once per (module, decoder parameter versions)."""
+
+    def __init__(self, net):
+        if any(p.requires_grad for p in net.stylegan_decoder.parameters()):
+            raise NotImplementedError('the training path implements fix_decoder=True (every plate config of SURVEY.md §8): the '
+                                      'StyleGAN2 decoder gets input gradients only')
+        if not net.input_is_latent:
+            raise NotImplementedError('training path: input_is_latent=False (style MLP) is not differentiated')
+        dev = next(net.parameters()).device
+        self.dev = dev
+        sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith('stylegan_decoder.')}
+        pack_decoder(self, net, lambda k: sd[k].to(dev), lambda k: sd[k].to(dev).float().contiguous(), train=True)
+        self.different_w, self.sft_half, self.nf = net.different_w, net.sft_half, net.num_style_feat
+        self.H, self.W = net.input_height, net.input_width
+        self.ratio = int(self.W / self.H)
+        self.sig = _decoder_signature(net)
+
+
+_DECODERS = weakref.WeakKeyDictionary()
+
+
+def _decoder_signature(net):
+    ps = list(net.stylegan_decoder.parameters()) + list(net.stylegan_decoder.buffers())
+    return (tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+
+
+def decoder_state(net):
+    st = _DECODERS.get(net)
+    if st is None or st.sig != _decoder_signature(net):
+        with torch.no_grad():
+            st = DecoderState(net)
+        _DECODERS[net] = st
+    return st
+
+
+def _convt_merged(cout, B, h, w):
+    """Same choice as the inference plan (engine._Plan): merged form for the 64/128-channel levels and the small ones."""
+    return cout <= 128 or B * h * w < 40000
+
+
+class FrozenDecoderFunction(torch.autograd.Function):
+    """image = stylegan_decoder([style_code], conditions) (gfpganv1_ocr_arch.py:387-391, 50-136) with gradients for the style
+    code and the SFT conditions; the decoder's own parameters are frozen.
+
+    forward : existing forward kernels, but every StyleConv keeps its un-modulated output `a` (post-activation, pre-SFT) —
+              the inference plan fuses SFT and the next modulation into the producer and keeps neither;
+    backward: per StyleConv  to_rgb_bwd -> sft_mod_bwd (direct style gradient + SFT adjoint) -> style_act_bwd (lrelu, demod
+              reduction) -> dgrad on b200ir_conv_igemm with adjoint weights (stride 1) / fir_pad22 + the stride-2 conv over phase
+              views (adjoint of conv_transpose2d + FIR), then demod_bwd + mod_linear_bwd into d(latent)."""
+
+    @staticmethod
+    def forward(ctx, st, noises, style_code, *conds):
+        _lib.require_cuda(style_code, 'train.FrozenDecoderFunction')
+        dev = style_code.device
+        B = style_code.shape[0]
+        L = st.L
+        e16 = lambda *s: torch.empty(*s, device=dev, dtype=F16)   # noqa: E731
+        z16 = lambda *s: torch.zeros(*s, device=dev, dtype=F16)   # noqa: E731
+        e32 = lambda *s: torch.empty(*s, device=dev, dtype=F32)   # noqa: E731
+        latent = style_code.detach().float().reshape(B, -1, st.nf).contiguous()       # [B, num_latent | 1, F]
+        lat = (lambda i: i) if st.different_w else (lambda i: 0)
+        mod_layers, demod_layers = [], []
+
+        def mod(layer, li):
+            s = e32(B, layer['mod_w'].shape[0])
+            mod_layers.append((layer['mod_w'], layer['mod_b'], lat(li), s))
+            return s
+
+        def dem(layer, s):
+            d = e32(B, layer['cout'])
+            demod_layers.append((s, layer['wsq'], layer['scale2'], d))
+            return d
+
+        s_sc1 = mod(st.sc1, 0)
+        d_sc1 = dem(st.sc1, s_sc1)
+        s_rgb1 = mod(st.rgb1, 1)
+        s_conv, d_conv, s_rgb = [], [], []
+        for lvl in range(L):
+            i = 1 + 2 * lvl
+            s1, s2 = mod(st.sconv[2 * lvl], i), mod(st.sconv[2 * lvl + 1], i + 1)
+            s_conv += [s1, s2]
+            d_conv += [dem(st.sconv[2 * lvl], s1), dem(st.sconv[2 * lvl + 1], s2)]
+            s_rgb.append(mod(st.rgbs[lvl], i + 2))
+        ops.ModLinearMulti(latent, mod_layers, st.mod_wscale)()
+        ops.DemodMulti(demod_layers)()
+
+        nz = [n.expand(B, 1, n.shape[2], n.shape[3]).contiguous() if n.shape[0] != B else n.contiguous() for n in noises]
+        h, w = 4, 4 * st.ratio
+        xs = e16(B, h, w, st.sc1['cin'])
+        ops.modulate_const(st.const, s_sc1, xs)
+        a0 = e16(B, h, w, st.sc1['cout'])
+        ops.conv_same(xs, st.sc1['w'], a0, 3, bias=st.sc1['bias'], demod=d_sc1, noise=nz[0], noise_gain=st.sc1['gain'],
+                      noise_strides=(h * w, w), act=True)()
+        skip = e32(B, 3, h, w)
+        xs = e16(B, h, w, st.sc1['cout']) if L else None
+        ops.to_rgb(a0, st.rgb1['w'], s_rgb1, st.rgb1['bias'], None, skip, s_next=s_conv[0] if L else None, xs_out=xs)
+        acts = []
+        for lvl in range(L):
+            c1, c2 = st.sconv[2 * lvl], st.sconv[2 * lvl + 1]
+            cout = c1['cout']
+            h2, w2 = 2 * h, 2 * w
+            raw = z16(B, h2 + 2, w2 + 2, cout)
+            if _convt_merged(cout, B, h, w):
+                ops.convt_s2_merged(xs, c1['w_merged'], raw, d_conv[2 * lvl])()
+            else:
+                for pi, (py, px) in enumerate(ops.CONVT_PHASES):
+                    ops.convt_s2_phase(xs, c1['w_phase'][pi], py, px, raw, demod=d_conv[2 * lvl])()
+            a1 = e16(B, h2, w2, cout)
+            ops.upfir_act(raw, a1, nz[2 * lvl + 1], h2 * w2, c1['gain'], c1['bias'], None, None, 0, None)
+            del raw
+            sc, sh = conds[2 * lvl].detach(), conds[2 * lvl + 1].detach()
+            xs2 = e16(B, h2, w2, cout)
+            ops.sft_mod(a1, sc, sh, s_conv[2 * lvl + 1], xs2)
+            a2 = e16(B, h2, w2, c2['cout'])
+            ops.conv_same(xs2, c2['w'], a2, 3, bias=c2['bias'], demod=d_conv[2 * lvl + 1], noise=nz[2 * lvl + 2],
+                          noise_gain=c2['gain'], noise_strides=(h2 * w2, w2), act=True)()
+            del xs2
+            last = lvl == L - 1
+            nskip = e32(B, 3, h2, w2)
+            xs = None if last else e16(B, h2, w2, c2['cout'])
+            ops.to_rgb(a2, st.rgbs[lvl]['w'], s_rgb[lvl], st.rgbs[lvl]['bias'], skip, nskip,
+                       s_next=None if last else s_conv[2 * lvl + 2], xs_out=xs)
+            skip = nskip
+            acts.append((a1, a2, sc, sh))
+            h, w = h2, w2
+        ctx.st, ctx.nz, ctx.acts, ctx.a0 = st, nz, acts, a0
+        ctx.tables = (s_sc1, d_sc1, s_rgb1, s_conv, d_conv, s_rgb)
+        ctx.lat_shape = latent.shape
+        ctx.code_shape, ctx.code_dtype = style_code.shape, style_code.dtype
+        return skip
+
+    @staticmethod
+    def backward(ctx, d_image):
+        st, nz, acts, a0 = ctx.st, ctx.nz, ctx.acts, ctx.a0
+        s_sc1, d_sc1, s_rgb1, s_conv, d_conv, s_rgb = ctx.tables
+        dev = d_image.device
+        B = d_image.shape[0]
+        L = st.L
+        e16 = lambda *s: torch.empty(*s, device=dev, dtype=F16)   # noqa: E731
+        z32 = lambda *s: torch.zeros(*s, device=dev, dtype=F32)   # noqa: E731
+        lat = (lambda i: i) if st.different_w else (lambda i: 0)
+        dlat = z32(*ctx.lat_shape)
+        wscale = st.mod_wscale
+        dskip = d_image.contiguous().float()
+        d_conds = [None] * (2 * L)
+        g_next = None           # gradient w.r.t. the modulated input of the conv that consumed this level's a2 (next level's conv1)
+        nxt = None              # (layer, s, d, dd, lat index) of that conv: its style gradient needs this level's a2
+
+        def style_grad(layer, s, d, dd, ds, li):
+            ops.demod_bwd(ds, s, dd, d, layer['wsq'], layer['scale2'])
+            ops.mod_linear_bwd(ds, layer['mod_w'], wscale, dlat, lat(li))
+
+        for lvl in range(L - 1, -1, -1):
+            a1, a2, sc, sh = acts[lvl]
+            c1, c2 = st.sconv[2 * lvl], st.sconv[2 * lvl + 1]
+            i = 1 + 2 * lvl
+            _, h2, w2, C = a2.shape
+            # ---- ToRGB (modulated 1x1, no demod) + skip up-sampling
+            da2 = e16(B, h2, w2, C)
+            ds = z32(B, C)
+            ops.to_rgb_bwd(dskip, a2, st.rgbs[lvl]['w'], s_rgb[lvl], da2, False, ds)
+            ops.mod_linear_bwd(ds, st.rgbs[lvl]['mod_w'], wscale, dlat, lat(i + 2))
+            dprev = torch.empty(B, 3, h2 // 2, w2 // 2, device=dev, dtype=F32)
+            ops.rgb_up_adjoint(dskip, dprev)
+            dskip = dprev
+            # ---- the next level's conv1 read a2 * s
+            if g_next is not None:
+                layer, s, d, dd, li = nxt
+                ds = z32(B, C)
+                ops.sft_mod_bwd(g_next, a2, None, None, s, da2, True, None, None, ds)
+                style_grad(layer, s, d, dd, ds, li)
+            # ---- conv2: a2 = act(conv(xs2) * d + noise + bias)
+            dd2 = z32(B, C)
+            ops.style_act_bwd(da2, a2, nz[2 * lvl + 2], c2['gain'], c2['bias'], d_conv[2 * lvl + 1], 1.0, da2, dd2)
+            g2 = e16(B, h2, w2, c2['cin'])
+            ops.conv_same(da2, c2['w_dgrad'], g2, 3)()
+            del da2
+            # ---- SFT + modulation between conv1 and conv2
+            C1 = a1.shape[3]
+            da1 = e16(B, h2, w2, C1)
+            dsc, dsh = torch.empty_like(sc), torch.empty_like(sh)
+            ds = z32(B, C1)
+            ops.sft_mod_bwd(g2, a1, sc, sh, s_conv[2 * lvl + 1], da1, False, dsc, dsh, ds)
+            del g2
+            style_grad(c2, s_conv[2 * lvl + 1], d_conv[2 * lvl + 1], dd2, ds, i + 1)
+            d_conds[2 * lvl], d_conds[2 * lvl + 1] = dsc, dsh
+            # ---- conv1 (up-sampling): a1 = act(FIR4(convT(xs) * d) + noise + bias)
+            dd1 = z32(B, C1)
+            ops.style_act_bwd(da1, a1, nz[2 * lvl + 1], c1['gain'], c1['bias'], d_conv[2 * lvl], 4.0, da1, dd1)
+            draw = torch.zeros(B, h2 + 2, w2 + 2, C1, device=dev, dtype=F16)
+            ops.fir_pad22(da1, draw)
+            del da1
+            g_next = e16(B, h2 // 2, w2 // 2, c1['cin'])
+            ops.conv3x3_s2(draw, h2, w2, c1['w_dgrad'], g_next)()
+            del draw
+            nxt = (c1, s_conv[2 * lvl], d_conv[2 * lvl], dd1, i)
+        # ---- style_conv1 + to_rgb1 on the constant input
+        _, h, w, C = a0.shape
+        da0 = e16(B, h, w, C)
+        ds = z32(B, C)
+        ops.to_rgb_bwd(dskip, a0, st.rgb1['w'], s_rgb1, da0, False, ds)
+        ops.mod_linear_bwd(ds, st.rgb1['mod_w'], wscale, dlat, lat(1))
+        if g_next is not None:
+            layer, s, d, dd, li = nxt
+            ds = z32(B, C)
+            ops.sft_mod_bwd(g_next, a0, None, None, s, da0, True, None, None, ds)
+            style_grad(layer, s, d, dd, ds, li)
+        dd0 = z32(B, C)
+        ops.style_act_bwd(da0, a0, nz[0], st.sc1['gain'], st.sc1['bias'], d_sc1, 1.0, da0, dd0)
+        g0 = e16(B, h, w, st.sc1['cin'])
+        ops.conv_same(da0, st.sc1['w_dgrad'], g0, 3)()
+        ds = z32(B, st.sc1['cin'])
+        ops.sft_mod_bwd(g0, st.const, None, None, None, None, False, None, None, ds, a_broadcast=True)
+        style_grad(st.sc1, s_sc1, d_sc1, dd0, ds, 0)
+        d_code = dlat.reshape(ctx.code_shape).to(ctx.code_dtype)
+        return (None, None, d_code) + tuple(d_conds)
+
+
+# ------------------------------------------------------------------------------------------ heads / losses
+class HeadToNchwFunction(torch.autograd.Function):
+    """toRGB head [B,h,w,16] fp16 (backward.ToRGBHeadFunction) -> fp32 NCHW [B,3,h,w], what the reference returns in out_rgbs."""
+
+    @staticmethod
+    def forward(ctx, head):
+        _lib.require_cuda(head, 'train.HeadToNchwFunction')
+        b, h, w, cpad = head.shape
+        rgb = torch.empty(b, 3, h, w, device=head.device, dtype=F32)
+        ops.head_to_nchw(head.contiguous(), rgb)
+        ctx.shape = head.shape
+        return rgb
+
+    @staticmethod
+    def backward(ctx, drgb):
+        dhead = torch.empty(ctx.shape, device=drgb.device, dtype=F16)
+        ops.nchw_to_head(drgb.contiguous().float(), dhead)
+        return dhead
+
+
+class L1LossFunction(torch.autograd.Function):
+    """weight * mean|x - t| (L1Loss, losses.py:81-106); value and gradient come out of one pass over x and t.  The
+    gradient is stored scaled by `grad_scale` (the loss scale); backward multiplies by the incoming scalar / grad_scale."""
+
+    @staticmethod
+    def forward(ctx, x, t, weight, grad_scale):
+        _lib.require_cuda(x, 'train.L1LossFunction')
+        x, t = x.contiguous(), t.contiguous()
+        loss = torch.zeros(1, device=x.device, dtype=F32)
+        grad = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        ops.l1_loss(x, t, weight, grad_scale, loss, grad)
+        ctx.grad, ctx.grad_scale = grad, grad_scale
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dl):
+        g = ctx.grad
+        ctx.grad = None
+        return _scaled(g, dl, ctx.grad_scale), None, None, None
+
+
+class SoftplusLossFunction(torch.autograd.Function):
+    """weight * mean softplus(sign * pred) (GANLoss 'wgan_softplus', losses.py:404-419): sign = -1 for target_is_real."""
+
+    @staticmethod
+    def forward(ctx, pred, sign, weight, grad_scale):
+        _lib.require_cuda(pred, 'train.SoftplusLossFunction')
+        assert pred.dtype == F16 and pred.dim() == 2 and pred.shape[1] == 1
+        pred = pred.contiguous()        # the scores are column 0 of a 16-wide GEMM output: pred and dpred share one stride
+        loss = torch.zeros(1, device=pred.device, dtype=F32)
+        dpred = torch.empty(pred.shape, device=pred.device, dtype=F16) if ctx.needs_input_grad[0] else None
+        ops.softplus_loss(pred, sign, weight, grad_scale, loss, dpred)
+        ctx.grad, ctx.grad_scale = dpred, grad_scale
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dl):
+        g = ctx.grad
+        ctx.grad = None
+        return _scaled(g, dl, ctx.grad_scale), None, None, None
+
+
+def _scaled(g, dl, grad_scale):
+    """The stored gradient already carries grad_scale (the loss scale); the incoming scalar dl of
+    total.backward(gradient=loss_scale) equals it, so the factor is 1 — applied on the device, no host sync."""
+    if g is None:
+        return None
+    return g.mul_((dl / grad_scale).to(g.dtype))
+
+
+def l1_loss(x, t, weight=1.0, grad_scale=1.0):
+    return L1LossFunction.apply(x, t, weight, grad_scale)
+
+
+def gan_softplus_loss(pred, target_is_real, weight=1.0, grad_scale=1.0):
+    return SoftplusLossFunction.apply(pred, -1.0 if target_is_real else 1.0, weight, grad_scale)
+
+
+# ------------------------------------------------------------------------------------------ networks
+def train_forward(net, x, return_rgb=True, randomize_noise=True, noise=None):
+    """Differentiable GFPGANv1OCR.forward (gfpganv1_ocr_arch.py:341-393) for training with fix_decoder=True: returns
+    (image fp32 NCHW [B,3,H,W], out_rgbs: list of fp32 NCHW toRGB heads) with autograd history on the trainable parameters.
+    noise: optional list of 2L+1 tensors [B|1,1,h,w]; else fresh N(0,1) planes when randomize_noise (the reference's training
+    default, gfpgan_model.py:508) or the registered noise buffers."""
+    _lib.require_cuda(x, 'train.train_forward')
+    st = decoder_state(net)
+    sd = dict(net.named_parameters())
+    res = unet_forward(sd, x, different_w=net.different_w, num_style_feat=net.num_style_feat, return_rgb=return_rgb)
+    style_code, conds = res[0], res[1]
+    if noise is None:
+        if randomize_noise:
+            B = x.shape[0]
+            noise = [torch.randn(B, 1, n.shape[2], n.shape[3], device=x.device, dtype=F32) for n in st.stored_noise]
+        else:
+            noise = st.stored_noise
+    image = FrozenDecoderFunction.apply(st, noise, style_code, *conds)
+    out_rgbs = [HeadToNchwFunction.apply(r) for r in res[2]] if return_rgb else []
+    return image, out_rgbs
+
+
+def disc_forward_image(sd, x, stddev_group=4):
+    """network_d on an fp32 NCHW image (backward.disc_forward).  When x requires grad the first conv also returns
+    d(score)/d(image): that is what l_g_gan sends back into net_g (gfpgan_model.py:549-552)."""
+    from .backward import disc_forward
+    return disc_forward(sd, x, stddev_group)
+
+
+def construct_img_pyramid(gt, levels):
+    """GFPGANModel.construct_img_pyramid (gfpgan_model.py:326-332): bilinear x0.5 chain of the ground truth, small to large.
+    Data preparation of the targets (no gradient flows into it)."""
+    import torch.nn.functional as F
+    out = [gt]
+    for _ in range(levels - 1):
+        out.insert(0, F.interpolate(out[0], scale_factor=0.5, mode='bilinear', align_corners=False))
+    return out
+
+
+class GFPGANTrainer:
+    """optimize_parameters of GFPGANModel (gfpgan_model.py:494-691) for the plate options: pixel L1 (weight 0.1), image
+    pyramid L1 (weight 1), GAN 'wgan_softplus' (weight 0.1), net_d logistic loss; Adam lr 2e-3 betas (0, 0.99) for both
+    networks; EMA decay 0.5 ** (32 / 10000).  Perceptual / identity / facial-component terms and the R1 penalty are
+    not part of this step (VGG19 weights are not available offline; R1 needs a double backward).
+
+    net_g: image_restoration_b200.GFPGANv1OCR (fix_decoder=True) on the device; net_d: image_restoration_b200.disc.StyleGAN2Discriminator;
+    net_g_ema: optional second GFPGANv1OCR that receives the EMA of the trainable parameters."""
+
+    def __init__(self, net_g, net_d, net_g_ema=None, lr_g=2e-3, lr_d=2e-3, betas=(0.0, 0.99), pix_weight=0.1, pyramid_weight=1.0,
+                 gan_weight=0.1, ema_decay=0.5 ** (32 / (10 * 1000)), loss_scale=None, group=None, net_d_iters=1,
+                 net_d_init_iters=0):
+        from .grad_sync import GradAllReducer
+        from .optim import FlatAdam
+        import torch.distributed as dist
+        self.net_g, self.net_d, self.net_g_ema = net_g, net_d, net_g_ema
+        self.pix_weight, self.pyramid_weight, self.gan_weight = pix_weight, pyramid_weight, gan_weight
+        self.ema_decay, self.loss_scale = ema_decay, loss_scale
+        self.net_d_iters, self.net_d_init_iters = net_d_iters, net_d_init_iters
+        self.g_params = [p for p in net_g.parameters() if p.requires_grad]
+        self.d_params = list(net_d.parameters())
+        ema_params = None
+        if net_g_ema is not None:
+            by_name = dict(net_g_ema.named_parameters())
+            ema_params = [by_name[n] for n, p in net_g.named_parameters() if p.requires_grad]
+        self.opt_g = FlatAdam(self.g_params, lr=lr_g, betas=betas, ema_params=ema_params)
+        self.opt_d = FlatAdam(self.d_params, lr=lr_d, betas=betas)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.sync_g = GradAllReducer(self.g_params, group=group) if self.world > 1 else None
+        self.sync_d = GradAllReducer(self.d_params, group=group) if self.world > 1 else None
+        self.d_sd = dict(net_d.named_parameters())
+        self.log = {}
+
+    def feed_data(self, lq, gt):
+        """lq, gt: fp32 NCHW [B,3,H,W] in [-1, 1] on the device (FFHQDegradationDataset pairs; degradation.synthesize_pairs)."""
+        self.lq, self.gt = lq.contiguous(), gt.contiguous()
+
+    def _scale(self, B):
+        return float(self.loss_scale) if self.loss_scale else 4096.0 * B
+
+    def _backward(self, total, S):
+        total.backward(gradient=torch.full_like(total, S))
+
+    def _step(self, opt, sync, S, ema_decay=None):
+        """All-reduce (sum) of the flat gradient buffer, then the fused Adam (+ EMA) step; the loss scale and the 1 / world
+        average are folded into the step's grad_scale."""
+        if sync is not None:
+            opt.step(flat_grad=sync.reduce_flat(), grad_scale=1.0 / (S * self.world), ema_decay=ema_decay)
+        else:
+            opt.step(grad_scale=1.0 / S, ema_decay=ema_decay)
+
+    def optimize_parameters(self, current_iter=1):
+        lq, gt = self.lq, self.gt
+        B = lq.shape[0]
+        S = self._scale(B)
+        log = {}
+        # ---------------- optimize net_g (gfpgan_model.py:497-667)
+        for p in self.d_params:
+            p.requires_grad_(False)
+        self.opt_g.zero_grad()
+        output, out_rgbs = train_forward(self.net_g, lq, return_rgb=self.pyramid_weight > 0)
+        self.output = output.detach()
+        if current_iter % self.net_d_iters == 0 and current_iter > self.net_d_init_iters:
+            total = l1_loss(output, gt, self.pix_weight, S)                                        # :519-523
+            log['l_g_pix'] = total.detach()
+            if self.pyramid_weight > 0:                                                             # :531-536
+                pyramid_gt = construct_img_pyramid(gt, len(out_rgbs))
+                for i, (rgb, tgt) in enumerate(zip(out_rgbs, pyramid_gt)):
+                    l_p = l1_loss(rgb, tgt, self.pyramid_weight, S)
+                    log[f'l_p_{2 ** (i + 3)}'] = l_p.detach()
+                    total = total + l_p
+            fake_g_pred = disc_forward_image(self.d_sd, output)                                    # :549-552
+            l_g_gan = gan_softplus_loss(fake_g_pred, True, self.gan_weight, S)
+            log['l_g_gan'] = l_g_gan.detach()
+            total = total + l_g_gan
+            self._backward(total, S)
+            self._step(self.opt_g, self.sync_g, S, ema_decay=self.ema_decay if self.net_g_ema is not None else None)
+        # ---------------- optimize net_d (:672-691, without the R1 penalty)
+        for p in self.d_params:
+            p.requires_grad_(True)
+        self.opt_d.zero_grad()
+        fake_d_pred = disc_forward_image(self.d_sd, self.output)
+        real_d_pred = disc_forward_image(self.d_sd, gt)
+        l_d_real = gan_softplus_loss(real_d_pred, True, 1.0, S)
+        l_d_fake = gan_softplus_loss(fake_d_pred, False, 1.0, S)
+        l_d = l_d_real + l_d_fake
+        log['l_d'] = l_d.detach()
+        log['real_score'] = real_d_pred.detach().float().mean()
+        log['fake_score'] = fake_d_pred.detach().float().mean()
+        self._backward(l_d, S)
+        self._step(self.opt_d, self.sync_d, S)
+        self.log = log
+        return log

@@ -143,6 +143,27 @@ typedef struct {
 
 int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
 
+/* Launch plans (one-time *_plan_create / destroy for the TMA descriptors): everything
+ * b200ir_conv_igemm derives from the descriptor on every call -- validation, up to five cuTensorMapEncodeTiled calls,
+ * tile / ring sizing, epilogue-profile selection -- is done once and kept in an opaque host object; plan_launch only
+ * enqueues the kernel.  A plan is bound to the pointers, shapes and device of its descriptor (the tensor maps hold the
+ * base addresses): re-create it when a buffer moves.  Launches of one plan may be issued from any stream, including under
+ * CUDA-graph capture.  destroy(NULL) is a no-op. */
+typedef struct b200ir_conv_plan b200ir_conv_plan;
+int b200ir_conv_plan_create(const b200ir_conv_desc* d, b200ir_conv_plan** plan);
+int b200ir_conv_plan_launch(const b200ir_conv_plan* plan, void* stream);
+void b200ir_conv_plan_destroy(b200ir_conv_plan* plan);
+
+/* Weight packing (SURVEY.md 8(b) `pack_weights`): state_dict layout fp32 [cout][cin][kh][kw] (EqualConv2d.weight,
+ * stylegan2_ocr_arch.py:629-637; nn.Conv2d.weight) -> the fp16 GEMM operand of b200ir_conv_igemm, times `scale` (the
+ * equalised-lr factor 1 / sqrt(cin * kh * kw), stylegan2_ocr_arch.py:631, :640):
+ *   mode 0 (forward):        out[co][(i*kw + j)*cin + ci]                       = w[co][ci][i][j] * scale   ([cout][taps*cin])
+ *   mode 1 (input gradient): out[ci][((kh-1-i)*kw + (kw-1-j))*cout + co]        = w[co][ci][i][j] * scale   ([cin][taps*cout]:
+ *            the stride-1 'same' conv is its own adjoint up to this flip / transpose, so dgrad runs on conv_igemm)
+ * cin_pad >= cin (mode 0) pads the input-channel block with zeros up to cin_pad (0 = cin). */
+int b200ir_pack_weights(const float* w, void* out, int cout, int cin, int kh, int kw, float scale, int mode, int cin_pad,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Memory-bound stages (128-bit NHWC access).  FIR = outer([1,3,3,1])/64 (make_resample_kernel,
  * stylegan2_ocr_arch.py:26-40) evaluated as upfirdn2d does (upfirdn2d.py:162-192; zero padding).
@@ -217,6 +238,73 @@ int b200ir_minibatch_stddev_bwd(const void* x, const void* dcat, const float* ds
 int b200ir_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, float* ema, float ema_decay,
                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step (GFPGANModel.optimize_parameters, basicsr/models/gfpgan_model.py:494-691): adjoints of the frozen StyleGAN2
+ * decoder's pointwise stages and the losses.  With fix_decoder=True the decoder has no weight gradients; l_g needs
+ * d(image)/d(style_code) and d(image)/d(conditions).  Per ModulatedConv2d (stylegan2_ocr_arch.py:239-279), with
+ * x' = x * s[b,ci], y = conv(x', W/sqrt(cin k^2)) * d[b,co], d = rsqrt(scale2 * sum_ci s^2 wsq[co,ci] + 1e-8):
+ *   dx' = dgrad(dy * d)  (b200ir_conv_igemm with adjoint weights),  dx = dx' * s,
+ *   ds[b,ci] = sum_p x * dx'  -  scale2 * s[b,ci] * sum_co dd[b,co] * d[b,co]^2 * wsq[co,ci],   dd[b,co] = sum_p dy * y.
+ * Gradients of activations are NHWC fp16 and carry the caller's loss scale; tables are fp32. */
+
+/* SFT (gfpganv1_ocr_arch.py:118-125) + modulation of the next conv (stylegan2_ocr_arch.py:247-251), training forward
+ * (the inference path fuses both into b200ir_upfir_act; training keeps the pre-SFT tensor `a` for the backward pass):
+ *   out[b,p,c] = (c < C - c_sft ? a : a * scale[b,p,c-(C-c_sft)] + shift[...]) * (s_next ? s_next[b*C+c] : 1)
+ * a, out NHWC fp16 [B][P][C]; scale / shift NHWC fp16 [B][P][c_sft] or both NULL. */
+int b200ir_sft_mod(const void* a, const void* scale, const void* shift, int c_sft, const float* s_next, void* out, int B,
+                   int64_t P, int C, void* stream);
+/* Backward of b200ir_sft_mod and the direct style gradient of the conv that consumed `out`: g NHWC fp16 [B][P][C] =
+ * gradient w.r.t. out (the dgrad GEMM's result); with o the SFT output recomputed from a, scale, shift:
+ *   ds[b][c] += sum_p g * o   (fp32 [B][C], the caller zeroes it; NULL = skip);   do = g * s_next;
+ *   da = do on the plain channels, do * scale on the SFT channels (accumulate != 0: added to the existing da; NULL = skip);
+ *   dscale = do * a,  dshift = do   (NHWC fp16 [B][P][c_sft]).
+ * a_stride_b: batch stride of `a` in elements (0: one [P][C] tensor for all images -- ConstantInput). */
+int b200ir_sft_mod_bwd(const void* g, const void* a, int64_t a_stride_b, const void* scale, const void* shift, int c_sft,
+                       const float* s_next, void* da, int accumulate, void* dscale, void* dshift, float* ds, int B, int64_t P,
+                       int C, void* stream);
+/* Backward of the StyleConv tail (noise injection + FusedLeakyReLU, stylegan2_ocr_arch.py:323-333) with the demodulation
+ * reduction: a = saved output = lrelu(y + gain * noise + bias) * sqrt 2;  dz = da * sqrt 2 * (a > 0 ? 1 : 0.2);  y is
+ * reconstructed from a;  dd[b][c] += sum_p dz * y (fp32 [B][C], caller zeroes; NULL = skip);
+ * out = dz * (oscale ? oscale[b*C+c] : 1) * mul   (the demodulation d, and the gain 4 of the up-sampling FIR). out may alias da. */
+int b200ir_style_act_bwd(const void* da, const void* a, const float* noise, int64_t noise_stride_b, const float* noise_gain,
+                         const float* bias, const float* oscale, float mul, void* out, float* dd, int B, int64_t P, int C,
+                         void* stream);
+/* Backward of ToRGB's modulated 1x1 conv (stylegan2_ocr_arch.py:357-374; no demodulation): drgb fp32 NCHW [B][3][P],
+ * a NHWC fp16 [B][P][C] (its input), w fp32 [3][C] pre-scaled by 1/sqrt(C), s fp32 [B][C] or NULL:
+ *   t = sum_o drgb[b][o][p] * w[o][c];   da (+)= s * t;   ds[b][c] += sum_p a * t. */
+int b200ir_to_rgb_bwd(const float* drgb, const void* a, const float* w, const float* s, void* da, int accumulate, float* ds,
+                      int B, int64_t P, int C, void* stream);
+/* Adjoint of UpFirDnUpsample on the RGB skip (upfirdn2d(skip, FIR*4, up=2, pad=(2,1)), stylegan2_ocr_arch.py:43-69):
+ * d fp32 [planes][2h][2w] -> out fp32 [planes][h][w]. */
+int b200ir_rgb_up_adjoint(const float* d, float* out, int planes, int h, int w, void* stream);
+/* ds[b][ci] -= scale2 * s[b][ci] * sum_co dd[b][co] * d[b][co]^2 * wsq[co][ci]  (the style gradient through the
+ * demodulation table, stylegan2_ocr_arch.py:253-257); in place on ds. */
+int b200ir_demod_bwd(float* ds, const float* s, const float* dd, const float* d, const float* wsq, float scale2, int B, int cin,
+                     int cout, void* stream);
+/* Modulation EqualLinear w.r.t. the latent (stylegan2_ocr_arch.py:229-234): dlat[b][lat_idx][f] += wscale * sum_ci ds[b][ci] *
+ * w[ci][f];  dlat fp32 [B][L][F]. */
+int b200ir_mod_linear_bwd(const float* ds, const float* w, float wscale, float* dlat, int L, int F, int lat_idx, int B, int cin,
+                          void* stream);
+/* Input gradient of b200ir_first_conv (the discriminator's conv_body.0 passes d(score)/d(image) back to net_g,
+ * gfpgan_model.py:549-552): dz NHWC fp16 [B][H][W][cout] (after b200ir_lrelu_bias_bwd), w fp32 [cout][3] (scaled) ->
+ * dx fp32 NCHW [B][3][H][W] (accumulate != 0: added). */
+int b200ir_first_conv_dgrad(const void* dz, const float* w, float* dx, int accumulate, int B, int H, int W, int cout,
+                            void* stream);
+/* The U-Net's toRGB heads (gfpganv1_ocr_arch.py:377-378) are computed with the three channels padded to cpad for the GEMM
+ * kernels: head NHWC fp16 [B][P][cpad] -> rgb fp32 NCHW [B][3][P] (what the reference returns in out_rgbs), and the adjoint. */
+int b200ir_head_to_nchw(const void* head, float* rgb, int B, int64_t P, int cpad, void* stream);
+int b200ir_nchw_to_head(const float* drgb, void* dhead, int B, int64_t P, int cpad, void* stream);
+/* L1Loss(loss_weight, reduction='mean') (basicsr/losses/losses.py:81-106; l_g_pix gfpgan_model.py:521, pyramid :532-536)
+ * forward + gradient in one pass: loss[0] += weight / n * sum |x - t|;  grad[i] = grad_scale * weight / n * sign(x - t).
+ * fp32 arrays; loss is a device scalar the caller zeroes; grad may be NULL. */
+int b200ir_l1_loss(const float* x, const float* t, int64_t n, float weight, float grad_scale, float* loss, float* grad,
+                   void* stream);
+/* GANLoss('wgan_softplus') (losses.py:404-419, 438-470): loss[0] += weight / n * sum softplus(sign * pred) with sign = -1
+ * for target_is_real;  dpred = grad_scale * weight / n * sign * sigmoid(sign * pred).  pred / dpred fp16, element i at
+ * [i * stride]; dpred may be NULL. */
+int b200ir_softplus_loss(const void* pred, int n, int stride, float sign, float weight, float grad_scale, float* loss,
+                         void* dpred, void* stream);
 
 /* Minibatch standard deviation of StyleGAN2Discriminator.forward (basicsr/archs/stylegan2_arch.py:791-801), stddev_feat = 1:
  * x NHWC fp16 [B][P][C]; group = min(B, stddev_group) must divide B; s fp32 [B / group] (work buffer);
