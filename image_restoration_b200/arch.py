@@ -257,6 +257,14 @@ class GFPGANv1OCR(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('image_restoration_b200.GFPGANv1OCR runs on a CUDA B200 only; there is no CPU path '
                                '(move the module and the input to cuda)')
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training call (GFPGANModel.optimize_parameters, gfpgan_model.py:508): the differentiable path -- U-Net through
+            # the autograd Functions of backward.py, frozen decoder through train.FrozenDecoderFunction.  The inference
+            # engine below runs under no_grad and would hand back tensors without history.
+            if save_feat_path is not None or load_feat_path is not None:
+                raise NotImplementedError('save_feat_path / load_feat_path are inference options (call .eval() first)')
+            from .train import train_forward
+            return train_forward(self, x, return_rgb=return_rgb, randomize_noise=randomize_noise)
         image, out_rgbs = self.engine().forward(x, return_rgb=return_rgb, randomize_noise=randomize_noise,
                                                 save_feat_path=save_feat_path, load_feat_path=load_feat_path)
         return image, out_rgbs
