@@ -128,6 +128,94 @@ def cpu_oracle_rate(seconds_budget=20.0, threads=None):
     return 1.0 / best, threads, f'B=1 crop 3x{H}x{W}, fp32 torch-CPU oracle port, 1 warm-up + best of {max(n, 1)}'
 
 
+def conv_gflop(sd, h, w, first_key):
+    """Algorithmic GFLOP (2 x MACs) per crop of a ConvLayer / ResBlock stack described by its state_dict: every 4-D weight is
+    a conv over the resolution its block runs at; `*.conv2.*` / `*.skip.*` of a ResBlock produce the halved resolution."""
+    total = 0.0
+    res = {}
+    for k, v in sd.items():
+        if v.dim() != 4:
+            continue
+        blk = k.split('.')[1] if k.startswith('conv_body.') else None
+        co, ci, kh, kw = v.shape
+        if blk is not None and blk != '0':
+            lvl = int(blk)
+            hh, ww = h >> (lvl - 1), w >> (lvl - 1)
+            if '.conv2.' in k or '.skip.' in k:
+                hh, ww = hh // 2, ww // 2
+        elif k.startswith('final_conv'):
+            n = len({x.split('.')[1] for x in sd if x.startswith('conv_body.')}) - 1
+            hh, ww = h >> n, w >> n
+        else:
+            hh, ww = h, w
+        total += 2.0 * co * ci * kh * kw * hh * ww
+    for k, v in sd.items():
+        if v.dim() == 2:
+            total += 2.0 * v.shape[0] * v.shape[1]
+    return total / 1e9
+
+
+def training_step_record(dev, world, B, steps, timed):
+    """BASELINE configs[4]: on-device pair synthesis (fused degradation kernel) + GFPGANModel.optimize_parameters (net_g
+    update on l_g_pix + image pyramid + l_g_gan, EMA, net_d update) at `B` crops per GPU, NCCL all-reduce of the flat
+    gradient buffers when world > 1.  Returns the record for the JSON line (rank-local timings; the caller's `timed` does the
+    barrier / max over ranks)."""
+    import random as _random
+
+    import numpy as np
+    from image_restoration_b200 import GFPGANv1OCR, degradation as dg, ops, train
+    from image_restoration_b200.disc import StyleGAN2Discriminator
+    torch.manual_seed(0)
+    net = GFPGANv1OCR(**NET_KW).to(dev).train()
+    ema = GFPGANv1OCR(**NET_KW).to(dev).eval()
+    ema.load_state_dict(net.state_dict())
+    netd = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1).to(dev)
+    tr = train.GFPGANTrainer(net, netd, net_g_ema=ema)
+    # GT crops and degradation parameters are drawn up front (the reference's DataLoader workers do this on the host, beside
+    # the step); the synthesis itself (blur / resize / noise / JPEG / jitter -> lq, img2tensor -> gt) runs inside the step
+    rng = np.random.RandomState(int(os.environ.get('RANK', '0')))
+    gt_u8 = torch.from_numpy(rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8)).to(dev)
+    opt = dict(blur_kernel_size=21, kernel_list=['iso', 'aniso', 'motion', 'average', 'median', 'bilateral', 'pyblur'],
+               kernel_prob=[0.08, 0.08, 0.08, 0.08, 0.08, 0.08, 0.28], blur_sigma=[0.1, 10], downsample_range=[4.0, 12.0],
+               noise_range=[0, 20], jpeg_range=[30, 100], color_jitter_prob=0.3, color_jitter_shift=20,
+               color_jitter_pt_prob=0.3, gray_prob=0.01)
+    prm = dg.sample_params(B, H, W, opt, py_random=_random.Random(0), np_random=rng)
+    pk = dg.pack_degrade_full(dev=dev, **prm)
+    gt_t = torch.empty(B, 3, H, W, device=dev)
+    it = [0]
+    logs = []
+
+    def step():
+        lq = dg.degrade_full_batch(gt_u8, packed=pk)
+        ops.u8_to_input(gt_u8, gt_t, swap_rb=True)
+        tr.feed_data(lq, gt_t)
+        it[0] += 1
+        logs.append(tr.optimize_parameters(it[0]))
+    lib = __import__('image_restoration_b200')._lib.lib()
+    step()                                                # first call: packs the frozen decoder, sizes the allocator
+    torch.cuda.synchronize()
+    n0 = lib.b200ir_launch_count()
+    ms = timed(step, steps, 1, preroll=0.0) / steps
+    launches = (lib.b200ir_launch_count() - n0) // (steps + 1)
+    tr.profile = True
+    step()
+    phases = tr.phase_ms()
+    tr.profile = False
+    mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    f_d = conv_gflop({k: v for k, v in netd.state_dict().items()}, H, W, 'conv_body.0')
+    f_dec = 34.9           # SURVEY App. A: modulated convs of the StyleGAN2 decoder (24.7 plain + 10.2 up-sampling)
+    f_unet = GEMM_GFLOP_PER_CROP - f_dec
+    # net_g forward + U-Net dgrad and wgrad + decoder dgrad; net_d: forward + dgrad in the G step, (forward + dgrad + wgrad)
+    # on fake and on real in the D step
+    f_train = GFLOP_PER_CROP + 2 * f_unet + f_dec + 8 * f_d
+    last = {k: float(v) for k, v in logs[-1].items()}
+    first = {k: float(v) for k, v in logs[0].items()}
+    del tr, net, ema, netd
+    torch.cuda.empty_cache()
+    return {'ms': ms, 'batch_per_gpu': B, 'launches_per_step': int(launches), 'phase_ms': phases, 'max_memory_gib': mem_gb,
+            'gflop_per_crop': f_train, 'disc_forward_gflop_per_crop': f_d, 'losses_first_step': first, 'losses_last_step': last}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -171,6 +259,8 @@ def main():
     ap.add_argument('--total', type=int, default=4096, help='N > 1: crops per step over all GPUs (BASELINE configs[2])')
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--train-batch', type=int, default=256, help='crops per GPU of the training-step record (0 = skip)')
+    ap.add_argument('--train-steps', type=int, default=3)
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary records (degradation, tiling, training ...)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -319,6 +409,13 @@ def main():
         for op in conv_ops:
             op()
     ms_conv = timed(conv_only, args.steps, warmup, preroll=0.3)
+    n_conv_ops = len(conv_ops)
+    conv_alg_bytes = 0          # algorithmic bytes of the conv launches: input once + output once + weights, fp16
+    for op in conv_ops:
+        d = op.desc
+        m = d.m_b * d.m_h * d.m_w
+        conv_alg_bytes += m * d.cin * 2 + (0 if d.no_store else m * d.cout * (4 if d.out_fp32 else 2)) \
+            + d.cout * d.num_taps * d.cin * 2
 
     # memory-bound kernels: every launch of each kind, back to back, against its algorithmic bytes
     from image_restoration_b200.engine import PwOp
@@ -442,6 +539,15 @@ def main():
                                                 'kind': 'port', 'sample': f'{n_cpu} crops through cv2.filter2D / scipy '
                                                 'convolve2d + cv2.resize + cv2.imencode/imdecode (the reference\'s calls)'}}
 
+    # BASELINE configs[4]: the training step, batch 256 per GPU (all ranks take part: NCCL all-reduce of the gradients)
+    training = None
+    if not args.no_extras and args.train_batch > 0:
+        del plan, conv_ops, pw_groups, conv_only
+        pipe.slots.clear()
+        eng.plans.clear()
+        torch.cuda.empty_cache()
+        training = training_step_record(dev, world, args.train_batch, args.train_steps, timed)
+
     if rank == 0:
         tf_peak, hbm_peak, src = peaks()
         crops_per_step = B if world == 1 else args.total          # whole job
@@ -479,15 +585,30 @@ def main():
             'launches_per_micro_batch': int(launches_per_mb),
             'roofline': {'bound': 'tensor', 'kernel': 'conv_igemm_kernel', 'achieved': conv_tflops, 'peak': tf_peak,
                          'unit': 'TFLOP/s', 'frac': conv_tflops / tf_peak, 'traffic': None,
-                         'peak_source': f'{src} bf16_tflops_sustained', 'launches_per_micro_batch': len(conv_ops),
-                         'avg_launch_ms': conv_ms_step / len(conv_ops),
-                         'algorithmic_gflop_per_launch': GEMM_GFLOP_PER_CROP * B / len(conv_ops),
+                         'peak_source': f'{src} bf16_tflops_sustained', 'launches_per_micro_batch': n_conv_ops,
+                         'avg_launch_ms': conv_ms_step / n_conv_ops,
+                         'algorithmic_gflop_per_launch': GEMM_GFLOP_PER_CROP * B / n_conv_ops,
                          'conv_share_of_step': conv_ms_step * mbs_per_step / (ms_total / args.steps),
                          'whole_net_frac': value / world * GFLOP_PER_CROP * 1e9 / 1e12 / tf_peak},
             'clocks': sampler.summary(),
         }
         if parity is not None:
             line['parity'] = parity
+        if training is not None:
+            tb = training['batch_per_gpu'] * world
+            cps = tb / (training['ms'] / 1e3)
+            training.update({
+                'crops_per_s': cps, 'ms_per_step': training.pop('ms'), 'global_batch': tb, 'n_gpus': world,
+                'algorithmic_tflops': cps * training['gflop_per_crop'] / 1e3,
+                'frac_of_tensor_peak': cps / world * training['gflop_per_crop'] / 1e3 / tf_peak,
+                'config': 'BASELINE configs[4]: per step and GPU: fused degradation kernel (training-YAML kernel mix incl. JPEG) '
+                          '-> lq, img2tensor -> gt; net_g forward (return_rgb) + l_g_pix 0.1 + image pyramid 1.0 + l_g_gan 0.1 '
+                          '(wgan_softplus) -> backward (U-Net wgrad/dgrad, frozen StyleGAN2 decoder dgrad, net_d dgrad) -> '
+                          'NCCL all-reduce -> fused Adam + EMA; net_d forward on fake and real -> logistic loss -> backward -> '
+                          'all-reduce -> fused Adam.  Not in the step: perceptual loss (VGG19 weights unavailable offline), R1 '
+                          'penalty (double backward), facial-component / identity terms (off for plates)',
+                'timing': 'CUDA events, max over ranks; phase_ms from one extra profiled step on rank 0'})
+            line['training_step'] = training
         if variants is not None:
             line['caller_variants'] = variants
         traffic_file = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
@@ -496,13 +617,7 @@ def main():
                 tr = json.load(f)
             line['roofline']['traffic'] = tr.get('dram_bytes_per_launch')
             line['roofline']['traffic_source'] = tr.get('source')
-            alg = 0
-            for op in conv_ops:
-                d = op.desc
-                m = d.m_b * d.m_h * d.m_w
-                alg += m * d.cin * 2 + (0 if d.no_store else m * d.cout * (4 if d.out_fp32 else 2)) \
-                    + d.cout * d.num_taps * d.cin * 2
-            line['roofline']['algorithmic_bytes_per_launch'] = alg / len(conv_ops)
+            line['roofline']['algorithmic_bytes_per_launch'] = conv_alg_bytes / n_conv_ops
         for r in pw_report:
             r['frac_of_hbm_peak'] = r['achieved_gbs'] / hbm_peak
             r['largest_launch']['frac_of_hbm_peak'] = r['largest_launch']['achieved_gbs'] / hbm_peak

@@ -21,12 +21,10 @@ class GradAllReducer:
             raise ValueError('no trainable parameters')
         dev = self.params[0].device
         self.group = group
-        self.numel = sum(p.numel() for p in self.params)
+        from .optim import flat_layout
+        offsets, self.numel = flat_layout(self.params)        # the layout of optim.FlatAdam: reduce_flat() feeds its step
         self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
-        self.views, off = [], 0
-        for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+        self.views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, offsets)]
         per = max(1, int(bucket_mb * (1 << 20) // 4))
         self.buckets = [(s, min(s + per, self.numel)) for s in range(0, self.numel, per)]
         self.stream = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None

@@ -15,6 +15,20 @@ import torch
 from . import _lib, ops
 
 
+FLAT_ALIGN = 64     # elements: every parameter starts on a 256-byte boundary of the flat buffer
+
+
+def flat_layout(params, align=FLAT_ALIGN):
+    """Offsets of the parameters inside a flat buffer and its total length.  Each view starts on a 256-byte boundary: the
+    kernels read bias / table rows as 16-byte vectors and TMA wants 16-byte aligned bases, and parameters re-pointed at the
+    flat buffer are handed to them as they are.  The padding elements stay zero (zero gradient: Adam leaves them at zero)."""
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += -(-p.numel() // align) * align
+    return offs, off
+
+
 class FlatAdam:
     def __init__(self, params, lr=2e-3, betas=(0.0, 0.99), eps=1e-8, weight_decay=0.0, ema_params=None):
         self.params = [p for p in params if p.requires_grad]
@@ -23,8 +37,8 @@ class FlatAdam:
         dev = self.params[0].device
         _lib.require_cuda(self.params[0], 'optim.FlatAdam')
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(self.numel, device=dev, dtype=torch.float32)
+        self.offsets, self.numel = flat_layout(self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
@@ -33,11 +47,10 @@ class FlatAdam:
         self.ema_params = ema_params
         if ema_params is not None:
             assert [tuple(e.shape) for e in ema_params] == [tuple(p.shape) for p in self.params]
-            self.ema = torch.empty_like(self.flat)
-        off = 0
+            self.ema = torch.zeros_like(self.flat)
         self.grad_views = []
         with torch.no_grad():
-            for i, p in enumerate(self.params):
+            for i, (p, off) in enumerate(zip(self.params, self.offsets)):
                 n = p.numel()
                 self.flat[off:off + n].copy_(p.detach().reshape(-1).float())
                 p.data = self.flat[off:off + n].view_as(p)
@@ -45,7 +58,6 @@ class FlatAdam:
                 if self.ema is not None:
                     self.ema[off:off + n].copy_(ema_params[i].detach().reshape(-1).float())
                     ema_params[i].data = self.ema[off:off + n].view_as(p)
-                off += n
         self.step_count = 0
 
     @torch.no_grad()

@@ -396,6 +396,20 @@ class GFPGANTrainer:
         self.sync_d = GradAllReducer(self.d_params, group=group) if self.world > 1 else None
         self.d_sd = dict(net_d.named_parameters())
         self.log = {}
+        self.profile = False        # True: CUDA events at the phase boundaries of optimize_parameters (self.phase_ms())
+        self._marks = []
+
+    def _mark(self, name):
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
+
+    def phase_ms(self):
+        """Milliseconds between the phase marks of the last optimize_parameters call (profile=True; synchronises)."""
+        torch.cuda.synchronize()
+        m = self._marks
+        return {m[i + 1][0]: m[i][1].elapsed_time(m[i + 1][1]) for i in range(len(m) - 1)}
 
     def feed_data(self, lq, gt):
         """lq, gt: fp32 NCHW [B,3,H,W] in [-1, 1] on the device (FFHQDegradationDataset pairs; degradation.synthesize_pairs)."""
@@ -420,12 +434,15 @@ class GFPGANTrainer:
         B = lq.shape[0]
         S = self._scale(B)
         log = {}
+        self._marks = []
+        self._mark('start')
         # ---------------- optimize net_g (gfpgan_model.py:497-667)
         for p in self.d_params:
             p.requires_grad_(False)
         self.opt_g.zero_grad()
         output, out_rgbs = train_forward(self.net_g, lq, return_rgb=self.pyramid_weight > 0)
         self.output = output.detach()
+        self._mark('g_forward')
         if current_iter % self.net_d_iters == 0 and current_iter > self.net_d_init_iters:
             total = l1_loss(output, gt, self.pix_weight, S)                                        # :519-523
             log['l_g_pix'] = total.detach()
@@ -439,8 +456,11 @@ class GFPGANTrainer:
             l_g_gan = gan_softplus_loss(fake_g_pred, True, self.gan_weight, S)
             log['l_g_gan'] = l_g_gan.detach()
             total = total + l_g_gan
+            self._mark('g_losses_and_d_forward')
             self._backward(total, S)
+            self._mark('g_backward')
             self._step(self.opt_g, self.sync_g, S, ema_decay=self.ema_decay if self.net_g_ema is not None else None)
+        self._mark('g_allreduce_adam_ema')
         # ---------------- optimize net_d (:672-691, without the R1 penalty)
         for p in self.d_params:
             p.requires_grad_(True)
@@ -453,7 +473,10 @@ class GFPGANTrainer:
         log['l_d'] = l_d.detach()
         log['real_score'] = real_d_pred.detach().float().mean()
         log['fake_score'] = fake_d_pred.detach().float().mean()
+        self._mark('d_forward')
         self._backward(l_d, S)
+        self._mark('d_backward')
         self._step(self.opt_d, self.sync_d, S)
+        self._mark('d_allreduce_adam')
         self.log = log
         return log

@@ -46,10 +46,9 @@ def test_flat_gradient_buffer_with_world_average():
     ref_opt = torch.optim.Adam(ref_net.parameters(), lr=2e-3, betas=(0.0, 0.99))
     opt = FlatAdam(net.parameters())
     flat = torch.randn(opt.numel, device='cuda')            # "sum over 8 ranks", averaged inside the step
-    off = 0
-    for p in ref_net.parameters():
+    for p, off in zip(ref_net.parameters(), opt.offsets):   # every parameter starts on a 256-byte boundary (optim.flat_layout)
+        assert off % 64 == 0
         p.grad = (flat[off:off + p.numel()] / 8).view_as(p).clone()
-        off += p.numel()
     ref_opt.step()
     opt.step(flat_grad=flat, grad_scale=1.0 / 8)
     for p, q in zip(ref_net.parameters(), net.parameters()):

@@ -221,3 +221,51 @@ def test_trainer_steps_match_a_torch_reference_loop():
     dec = 0.5 ** (32 / (10 * 1000))
     k0 = g_names[0]
     assert not torch.equal(dict(ema.named_parameters())[k0], dict(net.named_parameters())[k0])
+
+
+def _ddp_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from image_restoration_b200 import train
+    net, netd = _nets(seed=2)                                  # identical replicas
+    lq, gt = _data(2, seed=10 + rank)                          # each rank its own shard of the global batch
+    with cabi_sim.installed():
+        tr = train.GFPGANTrainer(net, netd)
+        orig = train.train_forward
+        train.train_forward = lambda n, x, **kw: orig(n, x, randomize_noise=False, **{k: v for k, v in kw.items() if k != 'randomize_noise'})
+        tr.feed_data(lq, gt)
+        log = tr.optimize_parameters(1)
+        # the exchanged gradient is the SUM over ranks in GradAllReducer.flat (the 1 / world average is inside the Adam step)
+        g_sum = tr.sync_g.flat.clone()
+    q.put((rank, tr.opt_g.flat.double().sum().item(), tr.opt_g.flat.double().abs().sum().item(),
+           tr.opt_d.flat.double().sum().item(), g_sum.double().abs().sum().item(), {k: float(v) for k, v in log.items()}))
+    dist.destroy_process_group()
+
+
+def test_trainer_two_rank_gloo_replicas_stay_identical():
+    """BASELINE configs[4] is data-parallel: one process per GPU, per-rank shards, one all-reduce of the flat gradient buffer
+    per network (base_model.py:62-76).  World-2 gloo run of the trainer on the simulator: after the step both replicas hold
+    bit-identical generator and discriminator weights although they saw different crops."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, g0, ga0, d0, gs0, log0), (_, g1, ga1, d1, gs1, log1) = res
+    assert g0 == g1 and ga0 == ga1 and d0 == d1, res
+    assert gs0 == gs1 and gs0 > 0
+    assert log0['l_g_pix'] != log1['l_g_pix']                  # different shards
+    assert all(math.isfinite(v) for v in list(log0.values()) + list(log1.values()))
