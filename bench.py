@@ -644,11 +644,21 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if rank == 0:
         sys.stdout.flush()
+        sys.stderr.flush()
+        if rank != 0:
+            os._exit(0)      # skip the exit handlers: with NCCL_DEBUG=INFO they print after rank 0's JSON line otherwise
+        time.sleep(1.0)      # the other ranks are gone by now
+    if rank == 0:
+        bad = parity is not None and not parity['ok']
+        if bad:
+            sys.stderr.write('bench.py: the benchmarked batch fails the parity bar against the CPU oracle: ' + json.dumps(parity) + '\n')
+        sys.stderr.flush()
         print(json.dumps(line), flush=True)          # the last line of stdout
-        if parity is not None and not parity['ok']:
-            sys.exit('bench.py: the benchmarked batch fails the parity bar against the CPU oracle: ' + json.dumps(parity))
+        if world > 1:
+            os._exit(1 if bad else 0)
+        if bad:
+            sys.exit(1)
 
 
 if __name__ == '__main__':
