@@ -155,6 +155,38 @@ def conv_gflop(sd, h, w, first_key):
     return total / 1e9
 
 
+def sr_arch_records(dev, timed, tf_peak):
+    """options/test/*.yml networks at the shapes of those configs: x4 super-resolution of a batch of
+    3x128x128 low-resolution patches.  images/s and the conv kernels' GEMM rate (FLOPs of the launched GEMMs; the 3-channel
+    input / output layers are padded to 16 channels)."""
+    from image_restoration_b200 import sr_archs
+    from image_restoration_b200.ops import ConvOp
+    cfgs = [('MSRResNet', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=16, upscale=4), 'test_MSRResNet_x4.yml'),
+            ('EDSR', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=16, upscale=4, res_scale=1, img_range=255.,
+                          rgb_mean=[0.4488, 0.4371, 0.4040]), 'test_EDSR_Mx4.yml'),
+            ('RCAN', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_group=10, num_block=20, squeeze_factor=16, upscale=4,
+                          res_scale=1, img_range=255., rgb_mean=[0.4488, 0.4371, 0.4040]), 'test_RCAN.yml'),
+            ('RRDBNet', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=23, num_grow_ch=32), 'test_ESRGAN_x4.yml')]
+    Bs, hw = 16, 128
+    out = {}
+    for name, kw, yml in cfgs:
+        torch.manual_seed(0)
+        net = getattr(sr_archs, name)(**kw).eval().to(dev)
+        x = torch.rand(Bs, 3, hw, hw, device=dev)
+        net(x)
+        plan = next(iter(net.engine().plans.values()))
+        gflop = sum(2.0 * st.desc.m_b * st.desc.m_h * st.desc.m_w * st.desc.cin * st.desc.num_taps * st.desc.cout
+                    for st in plan.steps if isinstance(st, ConvOp)) / 1e9
+        n_conv = sum(isinstance(st, ConvOp) for st in plan.steps)
+        ms = timed(lambda: net(x), 10, 3, preroll=0.1) / 10
+        out[name] = {'images_per_s': Bs / (ms / 1e3), 'ms_per_batch': ms, 'batch': Bs, 'input': f'3x{hw}x{hw} -> x4',
+                     'config': f'options/test/*/{yml}', 'conv_launches': n_conv, 'gemm_gflop_per_image': gflop / Bs,
+                     'gemm_tflops_whole_net': gflop / ms, 'frac_of_tensor_peak': gflop / ms / tf_peak}
+        del net, plan
+        torch.cuda.empty_cache()
+    return out
+
+
 def training_step_record(dev, world, B, steps, timed):
     """BASELINE configs[4]: on-device pair synthesis (fused degradation kernel) + GFPGANModel.optimize_parameters (net_g
     update on l_g_pix + image pyramid + l_g_gan, EMA, net_d update) at `B` crops per GPU, NCCL all-reduce of the flat
@@ -539,6 +571,10 @@ def main():
                                                 'kind': 'port', 'sample': f'{n_cpu} crops through cv2.filter2D / scipy '
                                                 'convolve2d + cv2.resize + cv2.imencode/imdecode (the reference\'s calls)'}}
 
+    sr_records = None
+    if world == 1 and not args.no_extras:
+        sr_records = sr_arch_records(dev, timed, peaks()[0])
+
     # BASELINE configs[4]: the training step, batch 256 per GPU (all ranks take part: NCCL all-reduce of the gradients)
     training = None
     if not args.no_extras and args.train_batch > 0:
@@ -594,6 +630,8 @@ def main():
         }
         if parity is not None:
             line['parity'] = parity
+        if sr_records is not None:
+            line['sr_archs'] = sr_records
         if training is not None:
             tb = training['batch_per_gpu'] * world
             cps = tb / (training['ms'] / 1e3)

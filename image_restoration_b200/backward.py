@@ -161,7 +161,11 @@ class ResBlockFunction(torch.autograd.Function):
         e16 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float16)   # noqa: E731
         t1 = e16(b, h, w, cin)
         ops.conv_same(x, w1p, t1, 3, bias=b1.detach().float().contiguous(), act=True)()
-        p = torch.zeros(b, h + 2, w + 2, cin, device=dev, dtype=torch.float16)
+        # fir_pad22 writes rows 0..h / columns 0..w; the spare row h+1 and column w+1 only need to be FINITE: the weight
+        # gradient's contraction runs over pixels, and the TMA box of a ragged tile pairs them with zero-filled dy (0 x NaN)
+        p = torch.empty(b, h + 2, w + 2, cin, device=dev, dtype=torch.float16)
+        p[:, h + 1].zero_()
+        p[:, :, w + 1].zero_()
         ops.fir_pad22(t1, p)
         y2 = e16(b, oh, ow, cout)
         ops.conv3x3_s2(p, h, w, w2p, y2, bias=b2.detach().float().contiguous(), act=True)()

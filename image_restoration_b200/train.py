@@ -86,7 +86,6 @@ class FrozenDecoderFunction(torch.autograd.Function):
         B = style_code.shape[0]
         L = st.L
         e16 = lambda *s: torch.empty(*s, device=dev, dtype=F16)   # noqa: E731
-        z16 = lambda *s: torch.zeros(*s, device=dev, dtype=F16)   # noqa: E731
         e32 = lambda *s: torch.empty(*s, device=dev, dtype=F32)   # noqa: E731
         latent = style_code.detach().float().reshape(B, -1, st.nf).contiguous()       # [B, num_latent | 1, F]
         lat = (lambda i: i) if st.different_w else (lambda i: 0)
@@ -130,7 +129,7 @@ class FrozenDecoderFunction(torch.autograd.Function):
             c1, c2 = st.sconv[2 * lvl], st.sconv[2 * lvl + 1]
             cout = c1['cout']
             h2, w2 = 2 * h, 2 * w
-            raw = z16(B, h2 + 2, w2 + 2, cout)
+            raw = e16(B, h2 + 2, w2 + 2, cout)       # valid (2h+1) x (2w+1); the spare row / column is never read
             if _convt_merged(cout, B, h, w):
                 ops.convt_s2_merged(xs, c1['w_merged'], raw, d_conv[2 * lvl])()
             else:
@@ -218,7 +217,7 @@ class FrozenDecoderFunction(torch.autograd.Function):
             # ---- conv1 (up-sampling): a1 = act(FIR4(convT(xs) * d) + noise + bias)
             dd1 = z32(B, C1)
             ops.style_act_bwd(da1, a1, nz[2 * lvl + 1], c1['gain'], c1['bias'], d_conv[2 * lvl], 4.0, da1, dd1)
-            draw = torch.zeros(B, h2 + 2, w2 + 2, C1, device=dev, dtype=F16)
+            draw = e16(B, h2 + 2, w2 + 2, C1)        # fir_pad22 fills the (h2+1) x (w2+1) region the stride-2 conv reads
             ops.fir_pad22(da1, draw)
             del da1
             g_next = e16(B, h2 // 2, w2 // 2, c1['cin'])

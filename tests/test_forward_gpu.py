@@ -64,13 +64,52 @@ def test_forward_128x384_stock_init(seed):
 
 @pytest.mark.parametrize('seed', [0, 1, 2])
 def test_forward_128x384_perturbed(seed):
-    """Stress case: random biases and non-zero noise gains (every epilogue term active).  This pushes >90% of the
-    output outside [-1,1] and raises its scale to ~40, so the [0,1] max-abs bound is relaxed to 3e-2 here; PSNR and the
-    raw-space relative RMS bounds are unchanged."""
+    """Stress case, not the contract configuration: random biases and non-zero noise gains (every epilogue term active) push
+    >90% of the output outside [-1,1] and raise its scale to ~40 (stock init: 3-14).  The [0,1] bound of the contract is an
+    ABSOLUTE bound on the raw output (2e-2 on [0,1] = 4e-2 raw), i.e. 1e-3 of this output's scale — the level of fp16
+    activation storage itself (2^-11 per rounding, ~25 layers in series; per-stage growth: test_error_budget_per_stage and
+    DESIGN.md §5).  The bar here is therefore stated in the output's own scale: max-abs on [0,1] <= 2e-2 x scale / 27
+    (= 3e-2 at scale 40), PSNR >= 45 dB and raw relative RMS <= 5e-3 unchanged."""
     net, cfg = build(384, 128, seed)
     torch.manual_seed(seed)
     x = torch.rand(2, 3, 128, 384) * 2 - 1
-    compare(net, cfg, x, True, f'128x384 perturbed seed {seed}', max_abs_tol=3e-2)
+    ref, _ = gfpgan_ocr_forward({k: v.clone() for k, v in net.state_dict().items()}, cfg, x, False)
+    scale = ref.abs().max().item()
+    compare(net, cfg, x, True, f'128x384 perturbed seed {seed} (scale {scale:.1f})', max_abs_tol=MAX_ABS * max(1.0, scale / 27.0))
+
+
+@pytest.mark.parametrize('seed,perturb', [(0, False), (0, True), (1, True)])
+def test_error_budget_per_stage(seed, perturb):
+    """Where the fp16 path's error comes from: relative RMS error against the fp32 oracle at every stage boundary the engine
+    exposes — style code (encoder + final_linear), SFT conditions per level (U-Net decoder + heads), the U-Net's toRGB heads,
+    the final image.  Each stage must stay within 3e-3 relative RMS (fp16 storage: 2^-11 per rounding, random-walk growth over
+    the layers in series); the numbers are quoted in DESIGN.md §5."""
+    net, cfg = build(384, 128, seed, perturb=perturb)
+    torch.manual_seed(seed)
+    x = torch.rand(2, 3, 128, 384) * 2 - 1
+    taps = {}
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    ref, ref_rgbs = gfpgan_ocr_forward(sd, cfg, x, True, taps=taps)
+    net = net.cuda()
+    eng = net.engine()
+    eng.use_graphs = False
+    got, rgbs = net(x.cuda(), return_rgb=True, randomize_noise=False)
+    plan = eng.plan(2)
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return ((a.float().cpu() - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-30)).item()
+    rows = [('style_code', rel(plan.style_code.view(taps['style_code'].shape), taps['style_code']))]
+    for i, (sc, sh) in enumerate(plan.cond):
+        rows.append((f'scale{i}', rel(sc.permute(0, 3, 1, 2), taps[f'scale{i}'])))
+        rows.append((f'shift{i}', rel(sh.permute(0, 3, 1, 2), taps[f'shift{i}'])))
+    for i, (r, rr) in enumerate(zip(rgbs, ref_rgbs)):
+        rows.append((f'toRGB{i}', rel(r, rr)))
+    rows.append(('image', rel(got, ref)))
+    print(f'error budget (seed {seed}, perturbed={perturb}, image scale {ref.abs().max().item():.1f}): ' +
+          '  '.join(f'{k} {v:.2e}' for k, v in rows))
+    for k, v in rows:
+        assert v <= 3e-3, (k, v)
 
 
 def test_forward_stock_init_single_crop():

@@ -136,8 +136,8 @@ def test_generator_losses_and_gradients_match_oracle_autograd():
         if cos < worst[0]:
             worst = (cos, rel, k)
         # a few 1e-3 of the leaky-ReLU branches and L1 signs differ between an fp16 forward and the fp32 oracle (each flips
-        # that element's gradient); the decoder's own adjoints are pinned to cos >= 0.999 with identical inputs above
-        assert cos >= 0.99 and rel <= 0.15, (k, cos, rel)
+        # that element's gradient): measured worst case cos 0.9999 / 1.4 % relative RMS over the 106 tensors
+        assert cos >= 0.999 and rel <= 0.05, (k, cos, rel)
     print(f'{n} gradient tensors; worst cos {worst[0]:.5f} (rel {worst[1]:.3e}) at {worst[2]}')
 
 
