@@ -224,6 +224,7 @@ def training_step_record(dev, world, B, steps, timed):
         it[0] += 1
         logs.append(tr.optimize_parameters(it[0]))
     lib = __import__('image_restoration_b200')._lib.lib()
+    torch.cuda.reset_peak_memory_stats(dev)
     step()                                                # first call: packs the frozen decoder, sizes the allocator
     torch.cuda.synchronize()
     n0 = lib.b200ir_launch_count()
