@@ -151,70 +151,89 @@ class ResBlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, ws):
         _need_cuda(x, 'ResBlockFunction')
-        b, h, w, cin = x.shape
-        cout = w2.shape[0]
-        oh, ow = h // 2, w // 2
-        dev = x.device
-        w1p, s1 = pack_equal_conv(w1)
-        w2p, s2 = pack_equal_conv(w2)
-        wsp, ss = pack_equal_conv(ws)
-        e16 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float16)   # noqa: E731
-        t1 = e16(b, h, w, cin)
-        ops.conv_same(x, w1p, t1, 3, bias=b1.detach().float().contiguous(), act=True)()
-        # fir_pad22 writes rows 0..h / columns 0..w; the spare row h+1 and column w+1 only need to be FINITE: the weight
-        # gradient's contraction runs over pixels, and the TMA box of a ragged tile pairs them with zero-filled dy (0 x NaN)
-        p = torch.empty(b, h + 2, w + 2, cin, device=dev, dtype=torch.float16)
-        p[:, h + 1].zero_()
-        p[:, :, w + 1].zero_()
-        ops.fir_pad22(t1, p)
-        y2 = e16(b, oh, ow, cout)
-        ops.conv3x3_s2(p, h, w, w2p, y2, bias=b2.detach().float().contiguous(), act=True)()
-        sk_in = e16(b, oh, ow, cin)
-        ops.fir_down2(x, sk_in)
-        out = e16(b, oh, ow, cout)
-        ops.conv_same(sk_in, wsp, out, 1, res=y2, res_mode=1, res_strides=(cout, ow * cout, oh * ow * cout), res_wh=(ow, oh),
-                      res_scale=ops.INV_SQRT2)()
-        ctx.save_for_backward(x, t1, p, y2, sk_in, w1p, w2, wsp)
-        ctx.scales = (s1, s2, ss)
+        out, saved, scales = resblock_forward(x, w1, b1, w2, b2, ws)
+        ctx.save_for_backward(*saved)
+        ctx.scales = scales
         if ResBlockFunction.debug_saved is not None:      # tests read the leaky-ReLU branches the kernels took
-            ResBlockFunction.debug_saved.update(t1=t1, y2=y2)
+            ResBlockFunction.debug_saved.update(t1=saved[1], y2=saved[3])
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, t1, p, y2, sk_in, w1p, w2, wsp = ctx.saved_tensors
-        s1, s2, ss = ctx.scales
-        b, h, w, cin = x.shape
-        oh, ow, cout = y2.shape[1:]
-        dev = x.device
-        dout = dout.contiguous()
-        need = ctx.needs_input_grad
-        # conv2: the 1 / sqrt 2 of the merge and the sqrt 2 of FusedLeakyReLU cancel
-        dz2, db2 = ops.lrelu_bias_bwd(dout, y2, scale=1.0, want_bias=need[4])
-        dw2 = None
-        if need[3]:
-            dw2 = ops.conv3x3_s2_wgrad(p, h, w, dz2).view(cout, 3, 3, cin).permute(0, 3, 1, 2) * s2
-        # dgrad of the stride-2 conv = conv_transpose2d(dz2, W2, stride 2) -> (h+1) x (w+1), then the FIR adjoint
-        raw = torch.empty(b, h + 2, w + 2, cin, device=dev, dtype=torch.float16)
-        ops.convt_s2_merged(dz2, ops.convt_merged_weight(w2.detach().permute(1, 0, 2, 3), s2), raw, None)()
-        dt1 = torch.empty_like(t1)
-        ops.fir_pad11(raw, dt1)
-        # conv1
-        dz1, db1 = ops.lrelu_bias_bwd(dt1, t1, dz=dt1, want_bias=need[2])
-        dw1 = ops.conv_wgrad(x, dz1).view(cin, 3, 3, cin).permute(0, 3, 1, 2) * s1 if need[1] else None
-        # skip: d(conv1x1 input) with the 1 / sqrt 2 folded into the weights
-        dws = None
-        if need[5]:
-            dws = (ops.conv1x1_wgrad(sk_in, dout) * (ss * ops.INV_SQRT2)).reshape(cout, cin, 1, 1)
-        dx = None
-        if need[0]:
-            dx = torch.empty_like(x)
-            ops.conv_dgrad(dz1, ops.conv_dgrad_weight(w1p, cin), dx)()
-            dsk = torch.empty_like(sk_in)
-            wst = (wsp.float() * ops.INV_SQRT2).t().contiguous().to(torch.float16)          # [cin, cout]
-            ops.conv_same(dout, wst, dsk, 1)()
-            ops.fir_down2_adjoint(dsk, dx, add=dx)
-        return dx, dw1, db1, dw2, db2, dws
+        return resblock_backward(ctx.saved_tensors, ctx.scales, dout, ctx.needs_input_grad)[:6]
+
+
+def resblock_forward(x, w1, b1, w2, b2, ws):
+    """Forward launches of one ResBlock (see ResBlockFunction).  Returns (out, saved, scales) with
+    saved = (x, t1, p, y2, sk_in, w1p, w2, wsp): what the backward pass — and the tangent pass of the R1 penalty (r1.py) — needs."""
+    b, h, w, cin = x.shape
+    cout = w2.shape[0]
+    oh, ow = h // 2, w // 2
+    dev = x.device
+    w1p, s1 = pack_equal_conv(w1)
+    w2p, s2 = pack_equal_conv(w2)
+    wsp, ss = pack_equal_conv(ws)
+    e16 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float16)   # noqa: E731
+    t1 = e16(b, h, w, cin)
+    ops.conv_same(x, w1p, t1, 3, bias=b1.detach().float().contiguous(), act=True)()
+    p = smoothed_buffer(t1)
+    y2 = e16(b, oh, ow, cout)
+    ops.conv3x3_s2(p, h, w, w2p, y2, bias=b2.detach().float().contiguous(), act=True)()
+    sk_in = e16(b, oh, ow, cin)
+    ops.fir_down2(x, sk_in)
+    out = e16(b, oh, ow, cout)
+    ops.conv_same(sk_in, wsp, out, 1, res=y2, res_mode=1, res_strides=(cout, ow * cout, oh * ow * cout), res_wh=(ow, oh),
+                  res_scale=ops.INV_SQRT2)()
+    return out, (x, t1, p, y2, sk_in, w1p, w2.detach(), wsp), (s1, s2, ss)
+
+
+def smoothed_buffer(t1):
+    """fir_pad22(t1) into a fresh [B, h+2, w+2, C] buffer (the input of the stride-2 conv over phase views).  fir_pad22 writes
+    rows 0..h / columns 0..w; the spare row h+1 and column w+1 only need to be FINITE: the weight gradient's contraction runs
+    over pixels, and the TMA box of a ragged tile pairs them with zero-filled dy (0 x NaN)."""
+    b, h, w, c = t1.shape
+    p = torch.empty(b, h + 2, w + 2, c, device=t1.device, dtype=torch.float16)
+    p[:, h + 1].zero_()
+    p[:, :, w + 1].zero_()
+    ops.fir_pad22(t1, p)
+    return p
+
+
+def resblock_backward(saved, scales, dout, need):
+    """Backward launches of one ResBlock; need = (x, w1, b1, w2, b2, ws) flags.  Returns (dx, dw1, db1, dw2, db2, dws, dz1, dz2):
+    the last two are the gradients at the pre-activations of conv1 / conv2, which the R1 penalty pairs with tangents."""
+    x, t1, p, y2, sk_in, w1p, w2, wsp = saved
+    s1, s2, ss = scales
+    b, h, w, cin = x.shape
+    oh, ow, cout = y2.shape[1:]
+    dev = x.device
+    dout = dout.contiguous()
+    # conv2: the 1 / sqrt 2 of the merge and the sqrt 2 of FusedLeakyReLU cancel
+    dz2, db2 = ops.lrelu_bias_bwd(dout, y2, scale=1.0, want_bias=need[4])
+    dw2 = None
+    if need[3]:
+        dw2 = ops.conv3x3_s2_wgrad(p, h, w, dz2).view(cout, 3, 3, cin).permute(0, 3, 1, 2) * s2
+    # dgrad of the stride-2 conv = conv_transpose2d(dz2, W2, stride 2) -> (h+1) x (w+1), then the FIR adjoint
+    raw = torch.empty(b, h + 2, w + 2, cin, device=dev, dtype=torch.float16)
+    ops.convt_s2_merged(dz2, ops.convt_merged_weight(w2.detach().permute(1, 0, 2, 3), s2), raw, None)()
+    dt1 = torch.empty_like(t1)
+    ops.fir_pad11(raw, dt1)
+    # conv1
+    dz1, db1 = ops.lrelu_bias_bwd(dt1, t1, dz=dt1, want_bias=need[2])
+    dw1 = ops.conv_wgrad(x, dz1).view(cin, 3, 3, cin).permute(0, 3, 1, 2) * s1 if need[1] else None
+    # skip: d(conv1x1 input) with the 1 / sqrt 2 folded into the weights
+    dws = None
+    if need[5]:
+        dws = (ops.conv1x1_wgrad(sk_in, dout) * (ss * ops.INV_SQRT2)).reshape(cout, cin, 1, 1)
+    dx = None
+    if need[0]:
+        dx = torch.empty_like(x)
+        ops.conv_dgrad(dz1, ops.conv_dgrad_weight(w1p, cin), dx)()
+        dsk = torch.empty_like(sk_in)
+        wst = (wsp.float() * ops.INV_SQRT2).t().contiguous().to(torch.float16)          # [cin, cout]
+        ops.conv_same(dout, wst, dsk, 1)()
+        ops.fir_down2_adjoint(dsk, dx, add=dx)
+    return dx, dw1, db1, dw2, db2, dws, dz1, dz2
 
 
 def res_block(x, w1, b1, w2, b2, ws):

@@ -417,6 +417,116 @@ __global__ void __launch_bounds__(kTrThreads) softplus_loss_kernel(const __half*
   }
 }
 
+// ------------------------------------------------------------------------------------------ R1 penalty pieces
+// sum of squares of an fp32 array: out[0] += scale * sum x^2   (|grad_x D|^2 of the R1 penalty, losses.py:492-506)
+__global__ void __launch_bounds__(kTrThreads) sum_squares_kernel(const float* __restrict__ x, long long n, float scale,
+                                                                 float* __restrict__ out) {
+  __shared__ float red[kTrThreads / 32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTrThreads) {
+    const float v = __ldcs(x + i);
+    acc = fmaf(v, v, acc);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kTrThreads / 32; ++i) s += red[i];
+    atomicAdd(out, s * scale);
+  }
+}
+
+// Minibatch standard deviation (stylegan2_arch.py:791-801; forward: b200ir_minibatch_stddev), first and second derivative
+// along a tangent t.  Sample b = g * M + m belongs to statistic m; per (m, p, c): mu = mean_g x, sigma = sqrt(var_g x + 1e-8),
+// tbar = mean_g t, dot = sum_g (x_g - mu) t_g.
+//   JVP:  ts[m] = 1 / (C P) * sum_{p,c} dot / (G sigma)
+//   HVP:  q[b][p][c] = a[m] / (C P) * ( (t_g - tbar) / (G sigma) - (x_g - mu) * dot / (G^2 sigma^3) )   (Hessian of a.s times t)
+// One thread per (m, p, 8 channels), the group (<= 8 samples) in registers, as mbstd_bwd_kernel.
+template <bool kHvp>
+__global__ void __launch_bounds__(kTrThreads) mbstd_tangent_kernel(const uint4* __restrict__ x, const uint4* __restrict__ t,
+                                                                   const float* __restrict__ a, float* __restrict__ ts,
+                                                                   uint4* __restrict__ q, int M, int P, int groups, int group) {
+  const long long n = (long long)M * P * groups;
+  const float inv_cp = 1.f / ((float)groups * 8.f * (float)P);
+  const float inv_g = 1.f / (float)group;
+  // JVP partial sums are flushed per thread with one fp32 atomic (the layer runs at 4 x 4r pixels: a few thousand threads)
+  for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
+    const unsigned r = (unsigned)idx / (unsigned)groups;
+    const int g8 = (int)((unsigned)idx - r * (unsigned)groups);
+    const int m = (int)(r / (unsigned)P), p = (int)(r - (unsigned)m * (unsigned)P);
+    float xv[8][8], tv[8][8], mu[8], tb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mu[k] = tb[k] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g < group) {
+        const long long row = ((long long)(g * M + m) * P + p) * groups + g8;
+        tr_unpack(__ldg(x + row), xv[g]);
+        tr_unpack(__ldg(t + row), tv[g]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mu[k] += xv[g][k], tb[k] += tv[g][k];
+      }
+    }
+    float jv = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mu[k] *= inv_g;
+      tb[k] *= inv_g;
+      float var = 0.f, dot = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (g < group) {
+          const float d = xv[g][k] - mu[k];
+          var = fmaf(d, d, var);
+          dot = fmaf(d, tv[g][k], dot);
+        }
+      const float rs = rsqrtf(var * inv_g + 1e-8f);  // 1 / sigma
+      if (kHvp) {
+        const float c1 = rs * inv_g, c2 = dot * inv_g * inv_g * rs * rs * rs;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (g < group) tv[g][k] = (tv[g][k] - tb[k]) * c1 - (xv[g][k] - mu[k]) * c2;
+      } else {
+        jv = fmaf(dot * inv_g, rs, jv);
+      }
+    }
+    if (kHvp) {
+      const float am = __ldg(a + m) * inv_cp;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (g < group) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = tv[g][k] * am;
+          q[((long long)(g * M + m) * P + p) * groups + g8] = tr_pack(o);
+        }
+    } else {
+      atomicAdd(ts + m, jv * inv_cp);
+    }
+  }
+}
+
+// tcat[b][p][:] = [ t[b][p][0..C) | ts[m(b)] | zeros up to c_pad ]: the tangent of b200ir_minibatch_stddev's output
+__global__ void __launch_bounds__(kTrThreads) mbstd_tangent_cat_kernel(const __half* __restrict__ t, const float* __restrict__ ts,
+                                                                       __half* __restrict__ tcat, long long n_pix, int P, int C,
+                                                                       int c_pad, int M) {
+  const int pad_groups = c_pad / 8;
+  const long long n = n_pix * pad_groups;
+  for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
+    const long long pix = idx / pad_groups;
+    const int g8 = (int)(idx - pix * pad_groups);
+    const int b = (int)(pix / P);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g8 * 8 + k;
+      o[k] = c < C ? __half2float(t[pix * C + c]) : (c == C ? ts[b % M] : 0.f);
+    }
+    *reinterpret_cast<uint4*>(tcat + pix * c_pad + g8 * 8) = tr_pack(o);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ weight packing
 __global__ void __launch_bounds__(kTrThreads) pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout,
                                                                   int cin, int kh, int kw, float scale, int mode, int cin_pad) {
@@ -571,6 +681,53 @@ extern "C" int b200ir_softplus_loss(const void* pred, int n, int stride, float s
   softplus_loss_kernel<<<1, kTrThreads, 0, STREAM>>>((const __half*)pred, n, stride, sign, weight / (float)n,
                                                      grad_scale * weight / (float)n, loss, (__half*)dpred);
   return check_launch("softplus_loss");
+}
+
+extern "C" int b200ir_sum_squares(const float* x, int64_t n, float scale, float* out, void* stream) {
+  B200IR_REQUIRE(x && out && n > 0, "sum_squares: bad arguments");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  sum_squares_kernel<<<tr_grid(n, sms, 8), kTrThreads, 0, STREAM>>>(x, n, scale, out);
+  return check_launch("sum_squares");
+}
+
+extern "C" int b200ir_minibatch_stddev_jvp(const void* x, const void* t, float* ts, void* tcat, int B, int P, int C, int c_pad,
+                                           int group, void* stream) {
+  B200IR_REQUIRE(x && t && ts && tcat && B > 0 && P > 0 && C > 0 && C % 8 == 0 && c_pad > C && c_pad % 8 == 0,
+                 "minibatch_stddev_jvp: bad arguments");
+  B200IR_REQUIRE(group >= 1 && group <= 8 && B % group == 0, "minibatch_stddev_jvp: batch %d is not divisible by group %d", B,
+                 group);
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const int M = B / group;
+  const long long n = (long long)M * P * (C / 8);
+  B200IR_REQUIRE(n < (1LL << 31), "minibatch_stddev_jvp: too many elements");
+  if (cudaMemsetAsync(ts, 0, sizeof(float) * M, STREAM) != cudaSuccess) {
+    set_error("minibatch_stddev_jvp: cudaMemsetAsync failed");
+    return 1;
+  }
+  mbstd_tangent_kernel<false><<<tr_grid(n, sms, 8), kTrThreads, 0, STREAM>>>((const uint4*)x, (const uint4*)t, nullptr, ts,
+                                                                            nullptr, M, P, C / 8, group);
+  if (check_launch("minibatch_stddev_jvp")) return 1;
+  const long long n2 = (long long)B * P * (c_pad / 8);
+  mbstd_tangent_cat_kernel<<<tr_grid(n2, sms, 8), kTrThreads, 0, STREAM>>>((const __half*)t, ts, (__half*)tcat, (long long)B * P,
+                                                                          P, C, c_pad, M);
+  return check_launch("minibatch_stddev_jvp(cat)");
+}
+
+extern "C" int b200ir_minibatch_stddev_hvp(const void* x, const void* t, const float* a, void* q, int B, int P, int C, int group,
+                                           void* stream) {
+  B200IR_REQUIRE(x && t && a && q && B > 0 && P > 0 && C > 0 && C % 8 == 0, "minibatch_stddev_hvp: bad arguments");
+  B200IR_REQUIRE(group >= 1 && group <= 8 && B % group == 0, "minibatch_stddev_hvp: batch %d is not divisible by group %d", B,
+                 group);
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const int M = B / group;
+  const long long n = (long long)M * P * (C / 8);
+  B200IR_REQUIRE(n < (1LL << 31), "minibatch_stddev_hvp: too many elements");
+  mbstd_tangent_kernel<true><<<tr_grid(n, sms, 8), kTrThreads, 0, STREAM>>>((const uint4*)x, (const uint4*)t, a, nullptr,
+                                                                           (uint4*)q, M, P, C / 8, group);
+  return check_launch("minibatch_stddev_hvp");
 }
 
 extern "C" int b200ir_pack_weights(const float* w, void* out, int cout, int cin, int kh, int kw, float scale, int mode,

@@ -756,3 +756,46 @@ def pack_weights(w, scale, mode=0, cin_pad=0):
     check(_lib.lib().b200ir_pack_weights(_ptr(w), _ptr(out), cout, cin, kh, kw, float(scale), mode, cin_pad, _stream()),
           'pack_weights')
     return out
+
+
+def sum_squares(x, scale, out):
+    _req(x, torch.float32, 'x')
+    check(_lib.lib().b200ir_sum_squares(_ptr(x), x.numel(), float(scale), _ptr(out), _stream()), 'sum_squares')
+
+
+def minibatch_stddev(x, group):
+    """b200ir_minibatch_stddev: x NHWC fp16 [B,h,w,C] -> [B,h,w,c_pad] = concat(x, group statistic, zero padding)."""
+    b, h, w, c = x.shape
+    c_pad = (c + 1 + 15) // 16 * 16
+    out = torch.zeros(b, h, w, c_pad, device=x.device, dtype=torch.float16)
+    s_buf = torch.empty(b // group, device=x.device, dtype=torch.float32)
+    check(_lib.lib().b200ir_minibatch_stddev(_ptr(x), _ptr(s_buf), _ptr(out), b, h * w, c, c_pad, group, _stream()),
+          'minibatch_stddev')
+    return out
+
+
+def minibatch_stddev_bwd(x, dcat, ds, dx, group):
+    b, h, w, c = x.shape
+    check(_lib.lib().b200ir_minibatch_stddev_bwd(_ptr(x), _ptr(dcat), _ptr(ds), _ptr(dx), b, h * w, c, dcat.shape[3], group,
+                                                 _stream()), 'minibatch_stddev_bwd')
+
+
+def minibatch_stddev_jvp(x, t, group):
+    """Tangent of minibatch_stddev's output along t (the tangent of x): [B,h,w,c_pad]."""
+    b, h, w, c = x.shape
+    c_pad = (c + 1 + 15) // 16 * 16
+    tcat = torch.empty(b, h, w, c_pad, device=x.device, dtype=torch.float16)
+    ts = torch.empty(b // group, device=x.device, dtype=torch.float32)
+    check(_lib.lib().b200ir_minibatch_stddev_jvp(_ptr(x), _ptr(t), _ptr(ts), _ptr(tcat), b, h * w, c, c_pad, group, _stream()),
+          'minibatch_stddev_jvp')
+    return tcat
+
+
+def minibatch_stddev_hvp(x, t, a, group):
+    """Hessian of (a . statistic)(x) times t: NHWC fp16 [B,h,w,C]; a fp32 [B / group]."""
+    b, h, w, c = x.shape
+    q = torch.empty_like(x)
+    _req(a, torch.float32, 'a')
+    check(_lib.lib().b200ir_minibatch_stddev_hvp(_ptr(x), _ptr(t), _ptr(a), _ptr(q), b, h * w, c, group, _stream()),
+          'minibatch_stddev_hvp')
+    return q

@@ -366,15 +366,16 @@ def construct_img_pyramid(gt, levels):
 class GFPGANTrainer:
     """optimize_parameters of GFPGANModel (gfpgan_model.py:494-691) for the plate options: pixel L1 (weight 0.1), image
     pyramid L1 (weight 1), GAN 'wgan_softplus' (weight 0.1), net_d logistic loss; Adam lr 2e-3 betas (0, 0.99) for both
-    networks; EMA decay 0.5 ** (32 / 10000).  Perceptual / identity / facial-component terms and the R1 penalty are
-    not part of this step (VGG19 weights are not available offline; R1 needs a double backward).
+    networks; EMA decay 0.5 ** (32 / 10000); R1 penalty on the real batch every net_d_reg_every iterations (r1.py).  The
+    perceptual / identity / facial-component terms are not part of this step (VGG19 / ArcFace weights are not available
+    offline; the component discriminators are off for plates).
 
     net_g: image_restoration_b200.GFPGANv1OCR (fix_decoder=True) on the device; net_d: image_restoration_b200.disc.StyleGAN2Discriminator;
     net_g_ema: optional second GFPGANv1OCR that receives the EMA of the trainable parameters."""
 
     def __init__(self, net_g, net_d, net_g_ema=None, lr_g=2e-3, lr_d=2e-3, betas=(0.0, 0.99), pix_weight=0.1, pyramid_weight=1.0,
                  gan_weight=0.1, ema_decay=0.5 ** (32 / (10 * 1000)), loss_scale=None, group=None, net_d_iters=1,
-                 net_d_init_iters=0):
+                 net_d_init_iters=0, r1_reg_weight=10.0, net_d_reg_every=16):
         from .grad_sync import GradAllReducer
         from .optim import FlatAdam
         import torch.distributed as dist
@@ -382,6 +383,7 @@ class GFPGANTrainer:
         self.pix_weight, self.pyramid_weight, self.gan_weight = pix_weight, pyramid_weight, gan_weight
         self.ema_decay, self.loss_scale = ema_decay, loss_scale
         self.net_d_iters, self.net_d_init_iters = net_d_iters, net_d_init_iters
+        self.r1_reg_weight, self.net_d_reg_every = r1_reg_weight, net_d_reg_every
         self.g_params = [p for p in net_g.parameters() if p.requires_grad]
         self.d_params = list(net_d.parameters())
         ema_params = None
@@ -460,7 +462,7 @@ class GFPGANTrainer:
             self._mark('g_backward')
             self._step(self.opt_g, self.sync_g, S, ema_decay=self.ema_decay if self.net_g_ema is not None else None)
         self._mark('g_allreduce_adam_ema')
-        # ---------------- optimize net_d (:672-691, without the R1 penalty)
+        # ---------------- optimize net_d (:672-691)
         for p in self.d_params:
             p.requires_grad_(True)
         self.opt_d.zero_grad()
@@ -475,6 +477,11 @@ class GFPGANTrainer:
         self._mark('d_forward')
         self._backward(l_d, S)
         self._mark('d_backward')
+        if self.r1_reg_weight > 0 and self.net_d_reg_every > 0 and current_iter % self.net_d_reg_every == 0:   # :683-689
+            from .r1 import r1_penalty_backward
+            log['l_d_r1'] = r1_penalty_backward(self.d_sd, gt, self.r1_reg_weight / 2 * self.net_d_reg_every, grad_out_scale=S,
+                                                stddev_group=getattr(self.net_d, 'stddev_group', 4))
+            self._mark('d_r1')
         self._step(self.opt_d, self.sync_d, S)
         self._mark('d_allreduce_adam')
         self.log = log

@@ -295,6 +295,20 @@ int b200ir_first_conv_dgrad(const void* dz, const float* w, float* dx, int accum
  * kernels: head NHWC fp16 [B][P][cpad] -> rgb fp32 NCHW [B][3][P] (what the reference returns in out_rgbs), and the adjoint. */
 int b200ir_head_to_nchw(const void* head, float* rgb, int B, int64_t P, int cpad, void* stream);
 int b200ir_nchw_to_head(const float* drgb, void* dhead, int B, int64_t P, int cpad, void* stream);
+/* R1 penalty of the discriminator (r1_penalty, basicsr/losses/losses.py:492-506; gfpgan_model.py:683-689): the double
+ * backward is assembled from the primal backward signals and a forward-mode (tangent) pass along v = grad_x sum D(x), see
+ * image_restoration_b200/r1.py.  These are its three non-GEMM pieces:
+ * sum_squares: out[0] += scale * sum_i x[i]^2  (fp32; the penalty's value);
+ * minibatch_stddev_jvp: tangent of b200ir_minibatch_stddev's output along t (NHWC fp16 [B][P][C], the tangent of its input x):
+ *   tcat [B][P][c_pad] = [ t | ts[m] | 0 ],  ts[m] = 1/(C P) sum_{p,c} sum_g (x_g - mu) t_g / (G sigma)   (ts: fp32 [B/group] work);
+ * minibatch_stddev_hvp: q = Hessian of (a . s)(x) times t, a fp32 [B/group] = d f / d s[m]:
+ *   q[b][p][c] = a[m]/(C P) * ((t_g - tbar)/(G sigma) - (x_g - mu) * dot/(G^2 sigma^3)),  dot = sum_g (x_g - mu) t_g. */
+int b200ir_sum_squares(const float* x, int64_t n, float scale, float* out, void* stream);
+int b200ir_minibatch_stddev_jvp(const void* x, const void* t, float* ts, void* tcat, int B, int P, int C, int c_pad, int group,
+                                void* stream);
+int b200ir_minibatch_stddev_hvp(const void* x, const void* t, const float* a, void* q, int B, int P, int C, int group,
+                                void* stream);
+
 /* L1Loss(loss_weight, reduction='mean') (basicsr/losses/losses.py:81-106; l_g_pix gfpgan_model.py:521, pyramid :532-536)
  * forward + gradient in one pass: loss[0] += weight / n * sum |x - t|;  grad[i] = grad_scale * weight / n * sign(x - t).
  * fp32 arrays; loss is a device scalar the caller zeroes; grad may be NULL. */

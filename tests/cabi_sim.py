@@ -526,6 +526,48 @@ class SimLib:
             TS(dpred, (n,), (stride,), torch.float16).copy_(grad_scale * weight / n * sign * torch.sigmoid(v))
         return 0
 
+    def b200ir_nchw_to_nhwc_pad(self, x, out, B, Cc, H, W, Cpad, sub, mul, unshuffle, stream):
+        self.launches += 1
+        assert unshuffle == 1, 'cabi_sim: pixel_unshuffle variant not simulated'
+        xt = T(x, (B, Cc, H, W), torch.float32)
+        if _addr(sub):
+            xt = xt - T(sub, (Cc,), torch.float32).view(1, Cc, 1, 1)
+        o = T(out, (B, H, W, Cpad), torch.float16)
+        o.zero_()
+        o[..., :Cc].copy_((xt * mul).permute(0, 2, 3, 1).clamp(-65504, 65504))
+        return 0
+
+    def b200ir_sum_squares(self, x, n, scale, out, stream):
+        self.launches += 1
+        T(out, (1,), torch.float32).add_(scale * T(x, (n,), torch.float32).pow(2).sum())
+        return 0
+
+    @staticmethod
+    def _mbstd_stat(x, group):
+        """(a-weighted) statistic of minibatch_stddev as a differentiable torch function of x [B,P,C]: returns s [M]."""
+        B, P, Cc = x.shape
+        g = x.view(group, B // group, P, Cc)
+        return torch.sqrt(g.var(0, unbiased=False) + 1e-8).mean(dim=(1, 2))
+
+    def b200ir_minibatch_stddev_jvp(self, x, t, ts, tcat, B, P, Cc, c_pad, group, stream):
+        self.launches += 1
+        xt, tt = T(x, (B, P, Cc), torch.float16).float(), T(t, (B, P, Cc), torch.float16).float()
+        _, jv = torch.autograd.functional.jvp(lambda v: self._mbstd_stat(v, group), xt, tt)
+        T(ts, (B // group,), torch.float32).copy_(jv)
+        o = T(tcat, (B, P, c_pad), torch.float16)
+        o.zero_()
+        o[..., :Cc].copy_(tt)
+        o[..., Cc].copy_(jv.repeat(group).view(B, 1).expand(B, P))
+        return 0
+
+    def b200ir_minibatch_stddev_hvp(self, x, t, a, q, B, P, Cc, group, stream):
+        self.launches += 1
+        xt, tt = T(x, (B, P, Cc), torch.float16).float(), T(t, (B, P, Cc), torch.float16).float()
+        av = T(a, (B // group,), torch.float32)
+        _, hv = torch.autograd.functional.hvp(lambda v: (self._mbstd_stat(v, group) * av).sum(), xt, tt)
+        T(q, (B, P, Cc), torch.float16).copy_(hv.clamp(-65504, 65504))
+        return 0
+
     def b200ir_pack_weights(self, w, out, cout, cin, kh, kw, scale, mode, cin_pad, stream):
         self.launches += 1
         wt = T(w, (cout, cin, kh, kw), torch.float32) * scale

@@ -215,3 +215,56 @@ def test_flat_adam_step_invalidates_the_forward_engine():
     assert not torch.allclose(y0, y1), 'the engine kept serving the weights packed before the optimiser step'
     a, b = to01(y1.float().cpu()), to01(ref)
     assert (a - b).abs().max().item() <= 2e-2 and psnr01(a, b) >= 45.0
+
+
+def test_r1_penalty_against_torch_double_backward():
+    """r1.r1_penalty_backward on the B200 kernels at the plate geometry against autograd.grad(..., create_graph=True) through
+    the fp32 oracle discriminator (the reference's r1_penalty, losses.py:492-506)."""
+    from image_restoration_b200 import r1
+    from oracle.disc_oracle import discriminator_forward
+    _, netd, _ = _nets(seed=1)
+    B = 4
+    _, gt = _data(B, seed=3)
+    weight = 10 / 2 * 16
+    sd = {k: v.detach().clone().requires_grad_() for k, v in netd.state_dict().items()}
+    x = gt.clone().requires_grad_()
+    pred = discriminator_forward(sd, x)
+    grad_real = torch.autograd.grad(pred.sum(), x, create_graph=True)[0]
+    ref = weight * grad_real.pow(2).view(B, -1).sum(1).mean()
+    ref.backward()
+    params = dict(netd.named_parameters())
+    for p in params.values():
+        p.grad = None
+    S = 1024.0
+    val = r1.r1_penalty_backward(params, gt, weight, grad_out_scale=S)
+    torch.cuda.synchronize()
+    print(f'R1 penalty {val.item():.6f} vs oracle {ref.item():.6f}')
+    assert abs(val.item() - ref.item()) <= 5e-3 * ref.item()
+    worst = (1.0, 0.0, '')
+    for k, p in params.items():
+        gb = sd[k].grad
+        if gb is None or gb.abs().max().item() == 0:
+            assert p.grad is None or p.grad.abs().max().item() <= 1e-7 * S, k
+            continue
+        cos, rel = _stats(p.grad / S, gb)
+        if cos < worst[0]:
+            worst = (cos, rel, k)
+        assert cos >= 0.999 and rel <= 0.05, (k, cos, rel)
+    print(f'R1 gradients: worst cos {worst[0]:.5f} (rel {worst[1]:.3e}) at {worst[2]}')
+
+
+def test_trainer_r1_iteration():
+    """An iteration on which the R1 penalty is due (current_iter % net_d_reg_every == 0): finite, logged, and it changes the
+    discriminator update."""
+    from image_restoration_b200 import train
+    net, netd, _ = _nets(seed=0)
+    net.train()
+    tr = train.GFPGANTrainer(net, netd, net_d_reg_every=2)
+    lq, gt = _data(4, seed=2)
+    for it in (1, 2):
+        tr.feed_data(lq, gt)
+        log = tr.optimize_parameters(it)
+        assert ('l_d_r1' in log) == (it % 2 == 0)
+    torch.cuda.synchronize()
+    assert math.isfinite(log['l_d_r1'].item()) and log['l_d_r1'].item() > 0
+    assert all(torch.isfinite(p).all() for p in netd.parameters())

@@ -269,3 +269,34 @@ def test_trainer_two_rank_gloo_replicas_stay_identical():
     assert gs0 == gs1 and gs0 > 0
     assert log0['l_g_pix'] != log1['l_g_pix']                  # different shards
     assert all(math.isfinite(v) for v in list(log0.values()) + list(log1.values()))
+
+
+def test_r1_penalty_gradients_match_torch_double_backward():
+    """r1.r1_penalty_backward (primal backward signals x tangent pass + the Hessian term of the minibatch standard deviation)
+    against the reference's own formulation: autograd.grad(real_pred.sum(), gt, create_graph=True) -> penalty -> backward
+    (losses.py:492-506, gfpgan_model.py:683-689), on the fp32 oracle discriminator."""
+    from image_restoration_b200 import r1
+    from oracle.disc_oracle import discriminator_forward
+    _, netd = _nets(seed=1)
+    B = 4
+    _, gt = _data(B, seed=3)
+    weight = 10 / 2 * 16                                      # r1_reg_weight / 2 * net_d_reg_every
+    sd = {k: v.detach().clone().requires_grad_() for k, v in netd.state_dict().items()}
+    x = gt.clone().requires_grad_()
+    pred = discriminator_forward(sd, x)
+    grad_real = torch.autograd.grad(pred.sum(), x, create_graph=True)[0]
+    l_d_r1 = weight * grad_real.pow(2).view(B, -1).sum(1).mean() + 0 * pred[0]
+    l_d_r1.sum().backward()
+    params = dict(netd.named_parameters())
+    S = 512.0
+    with cabi_sim.installed():
+        for p in params.values():
+            p.grad = torch.ones_like(p)                       # the penalty's gradient is ADDED to what l_d.backward() left there
+        val = r1.r1_penalty_backward(params, gt, weight, grad_out_scale=S)
+    assert abs(val.item() - l_d_r1.sum().item()) <= 3e-3 * l_d_r1.sum().item(), (val.item(), l_d_r1.sum().item())
+    for k, p in params.items():
+        ga, gb = (p.grad - 1) / S, sd[k].grad
+        if gb.abs().max().item() == 0:                        # biases above the statistic layer: no dependence at all
+            assert ga.abs().max().item() <= 1e-7, k
+            continue
+        _cmp(k, ga, gb, 0.999, 0.05)

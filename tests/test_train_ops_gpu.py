@@ -209,3 +209,33 @@ def test_conv_plan_launch_equals_direct_launch():
     bad.block_n = 48
     assert lib.b200ir_conv_plan_create(C.byref(bad), C.byref(h)) != 0 and not h.value
     lib.b200ir_conv_plan_destroy(None)
+
+
+@pytest.mark.parametrize('B,h,w,C,group', [(8, 4, 12, 512, 4), (4, 4, 12, 64, 4), (6, 3, 5, 32, 2), (2, 4, 4, 24, 2)])
+def test_minibatch_stddev_tangent_kernels_and_sum_squares(B, h, w, C, group):
+    """First and second derivative of the minibatch standard deviation along a tangent (the two non-GEMM pieces of the R1
+    penalty) against torch.autograd.functional.jvp / hvp of the oracle formula (tests/cabi_sim.py)."""
+    from image_restoration_b200 import ops
+    g = torch.Generator().manual_seed(B * C)
+    t = dict(x=rn(B, h, w, C, g=g).half(), t=rn(B, h, w, C, g=g).half(), a=rn(B // group, g=g),
+             sq=rn(B, 3, h, w, g=g), out=torch.zeros(1))
+    res = {}
+
+    def run(d):
+        res['tcat'] = ops.minibatch_stddev_jvp(d['x'], d['t'], group)
+        res['q'] = ops.minibatch_stddev_hvp(d['x'], d['t'], d['a'], group)
+        ops.sum_squares(d['sq'], 0.25, d['out'])
+    gpu = {k: v.cuda() for k, v in t.items()}
+    run(gpu)
+    torch.cuda.synchronize()
+    got = dict(res)
+    cpu = {k: v.clone() for k, v in t.items()}
+    with cabi_sim.installed():
+        run(cpu)
+    c_pad = got['tcat'].shape[3]
+    assert c_pad % 16 == 0 and c_pad > C
+    close('tcat', got['tcat'], res['tcat'])
+    assert (got['tcat'][..., C + 1:] == 0).all()
+    close('stat tangent', got['tcat'][..., C], res['tcat'][..., C], rel=2e-3)
+    close('hvp', got['q'], res['q'], rel=3e-3)
+    close('sum_squares', gpu['out'], cpu['out'], rel=1e-5)
