@@ -202,7 +202,24 @@ def training_step_record(dev, world, B, steps, timed):
     ema = GFPGANv1OCR(**NET_KW).to(dev).eval()
     ema.load_state_dict(net.state_dict())
     netd = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1).to(dev)
-    tr = train.GFPGANTrainer(net, netd, net_g_ema=ema)
+    # perceptual_opt of the training YAMLs (VGG19, conv1_2 .. conv5_4 before ReLU, perceptual 1 / style 50).  The ImageNet
+    # checkpoint is not available offline: seeded random weights of the same architecture (same arithmetic, same cost)
+    from image_restoration_b200 import perceptual
+    gv = torch.Generator().manual_seed(0)
+    vgg_sd, cin, f_vgg, hh, ww = {}, 3, 0.0, H, W
+    for idx, name in enumerate(perceptual.VGG19_NAMES[:35]):
+        if name.startswith('conv'):
+            cout = {'1': 64, '2': 128, '3': 256, '4': 512, '5': 512}[name[4]]
+            vgg_sd[f'features.{idx}.weight'] = torch.randn(cout, cin, 3, 3, generator=gv) * (2.0 / (cout * 9)) ** 0.5
+            vgg_sd[f'features.{idx}.bias'] = torch.randn(cout, generator=gv) * 0.05
+            f_vgg += 2.0 * cout * cin * 9 * hh * ww / 1e9
+            cin = cout
+        elif name.startswith('pool'):
+            hh, ww = hh // 2, ww // 2
+    layer_weights = {'conv1_2': 0.1, 'conv2_2': 0.1, 'conv3_4': 1.0, 'conv4_4': 1.0, 'conv5_4': 1.0}
+    vgg = perceptual.VGG19Features(vgg_sd, list(layer_weights), dev, use_input_norm=True, range_norm=True)
+    tr = train.GFPGANTrainer(net, netd, net_g_ema=ema, perceptual=dict(vgg=vgg, layer_weights=layer_weights,
+                                                                        perceptual_weight=1.0, style_weight=50.0))
     # GT crops and degradation parameters are drawn up front (the reference's DataLoader workers do this on the host, beside
     # the step); the synthesis itself (blur / resize / noise / JPEG / jitter -> lq, img2tensor -> gt) runs inside the step
     rng = np.random.RandomState(int(os.environ.get('RANK', '0')))
@@ -233,6 +250,10 @@ def training_step_record(dev, world, B, steps, timed):
     tr.profile = True
     step()
     phases = tr.phase_ms()
+    # an iteration on which the R1 penalty is due (every net_d_reg_every = 16 iterations, gfpgan_model.py:683-689)
+    it[0] = 15
+    step()
+    phases_r1 = tr.phase_ms()
     tr.profile = False
     mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     f_d = conv_gflop({k: v for k, v in netd.state_dict().items()}, H, W, 'conv_body.0')
@@ -240,13 +261,17 @@ def training_step_record(dev, world, B, steps, timed):
     f_unet = GEMM_GFLOP_PER_CROP - f_dec
     # net_g forward + U-Net dgrad and wgrad + decoder dgrad; net_d: forward + dgrad in the G step, (forward + dgrad + wgrad)
     # on fake and on real in the D step
-    f_train = GFLOP_PER_CROP + 2 * f_unet + f_dec + 8 * f_d
+    # + the VGG19 of the perceptual loss: forward on output and on gt, input gradient for the output
+    f_train = GFLOP_PER_CROP + 2 * f_unet + f_dec + 8 * f_d + 3 * f_vgg
     last = {k: float(v) for k, v in logs[-1].items()}
     first = {k: float(v) for k, v in logs[0].items()}
-    del tr, net, ema, netd
+    del net, ema, netd, vgg
     torch.cuda.empty_cache()
-    return {'ms': ms, 'batch_per_gpu': B, 'launches_per_step': int(launches), 'phase_ms': phases, 'max_memory_gib': mem_gb,
-            'gflop_per_crop': f_train, 'disc_forward_gflop_per_crop': f_d, 'losses_first_step': first, 'losses_last_step': last}
+    return {'ms': ms, 'batch_per_gpu': B, 'launches_per_step': int(launches), 'phase_ms': phases,
+            'r1_iteration': {'ms_per_step': sum(phases_r1.values()), 'd_r1_ms': phases_r1.get('d_r1'),
+                             'every': tr.net_d_reg_every, 'amortised_ms_per_step': phases_r1.get('d_r1', 0.0) / tr.net_d_reg_every},
+            'max_memory_gib': mem_gb, 'gflop_per_crop': f_train, 'disc_forward_gflop_per_crop': f_d,
+            'vgg19_forward_gflop_per_crop': f_vgg, 'losses_first_step': first, 'losses_last_step': last}
 
 
 def run_reference(args):
@@ -641,11 +666,12 @@ def main():
                 'algorithmic_tflops': cps * training['gflop_per_crop'] / 1e3,
                 'frac_of_tensor_peak': cps / world * training['gflop_per_crop'] / 1e3 / tf_peak,
                 'config': 'BASELINE configs[4]: per step and GPU: fused degradation kernel (training-YAML kernel mix incl. JPEG) '
-                          '-> lq, img2tensor -> gt; net_g forward (return_rgb) + l_g_pix 0.1 + image pyramid 1.0 + l_g_gan 0.1 '
-                          '(wgan_softplus) -> backward (U-Net wgrad/dgrad, frozen StyleGAN2 decoder dgrad, net_d dgrad) -> '
-                          'NCCL all-reduce -> fused Adam + EMA; net_d forward on fake and real -> logistic loss -> backward -> '
-                          'all-reduce -> fused Adam.  Not in the step: perceptual loss (VGG19 weights unavailable offline), R1 '
-                          'penalty (double backward), facial-component / identity terms (off for plates)',
+                          '-> lq, img2tensor -> gt; net_g forward (return_rgb) + l_g_pix 0.1 + image pyramid 1.0 + perceptual 1.0 / '
+                          'style 50 (VGG19 conv1_2..conv5_4, seeded random weights: the ImageNet checkpoint is not available '
+                          'offline) + l_g_gan 0.1 (wgan_softplus) -> backward (U-Net wgrad/dgrad, frozen StyleGAN2 decoder dgrad, '
+                          'net_d dgrad, VGG dgrad) -> NCCL all-reduce -> fused Adam + EMA; net_d forward on fake and real -> '
+                          'logistic loss -> backward -> all-reduce -> fused Adam; R1 penalty every 16th iteration (timed '
+                          'separately: r1_iteration).  Not in the step: facial-component / identity terms (off for plates)',
                 'timing': 'CUDA events, max over ranks; phase_ms from one extra profiled step on rank 0'})
             line['training_step'] = training
         if variants is not None:

@@ -118,6 +118,9 @@ SIGNATURES = {
     'b200ir_first_conv_dgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_head_to_nchw': [_P, _P, _I, _L, _I, _P],
     'b200ir_nchw_to_head': [_P, _P, _I, _L, _I, _P],
+    'b200ir_maxpool2_relu': [_P, _P, _I, _I, _I, _I, _P],
+    'b200ir_maxpool2_relu_bwd': [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_l1_loss_f16': [_P, _P, _L, _F, _F, _P, _P, _P],
     'b200ir_sum_squares': [_P, _L, _F, _P, _P],
     'b200ir_minibatch_stddev_jvp': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_minibatch_stddev_hvp': [_P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -417,6 +417,112 @@ __global__ void __launch_bounds__(kTrThreads) softplus_loss_kernel(const __half*
   }
 }
 
+// ------------------------------------------------------------------------------------------ perceptual loss pieces (VGG19)
+// nn.ReLU + nn.MaxPool2d(2, 2) of the VGG feature extractor (vgg_arch.py:100-125) on a PRE-activation tensor z (the layers the
+// perceptual loss taps are read before their ReLU, losses.py:250-356): out = max(0, max over the 2 x 2 window).
+__global__ void __launch_bounds__(kTrThreads) maxpool2_relu_kernel(const uint4* __restrict__ z, uint4* __restrict__ out,
+                                                                   long long n, int oh, int ow, int groups) {
+  for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
+    const long long pix = idx / groups;
+    const int g = (int)(idx - pix * groups);
+    const int x = (int)(pix % ow);
+    const long long r = pix / ow;
+    const int y = (int)(r % oh);
+    const long long b = r / oh;
+    const long long base = ((b * 2 * oh + 2 * y) * (2 * ow) + 2 * x) * groups + g;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float v[8];
+        tr_unpack(__ldcs(z + base + ((long long)dy * 2 * ow + dx) * groups), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    out[idx] = tr_pack(m);
+  }
+}
+
+// backward: dz = add + (dpool routed to the first maximum of its window, if that maximum is positive); one thread per
+// pooled position and channel group writes the four dz entries of its window.
+__global__ void __launch_bounds__(kTrThreads) maxpool2_relu_bwd_kernel(const uint4* __restrict__ z, const uint4* __restrict__ dpool,
+                                                                       const uint4* __restrict__ add, uint4* __restrict__ dz,
+                                                                       long long n, int oh, int ow, int groups) {
+  for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
+    const long long pix = idx / groups;
+    const int g = (int)(idx - pix * groups);
+    const int x = (int)(pix % ow);
+    const long long r = pix / ow;
+    const int y = (int)(r % oh);
+    const long long b = r / oh;
+    const long long base = ((b * 2 * oh + 2 * y) * (2 * ow) + 2 * x) * groups + g;
+    float v[4][8], d[8];
+    if (dpool != nullptr) {
+      tr_unpack(__ldcs(dpool + idx), d);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tr_unpack(__ldcs(z + base + ((long long)(k >> 1) * 2 * ow + (k & 1)) * groups), v[k]);
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float m = v[0][j];
+      int a = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k][j] > m) m = v[k][j], a = k;   // first maximum in row-major order, as nn.MaxPool2d
+      arg[j] = m > 0.f ? a : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long o = base + ((long long)(k >> 1) * 2 * ow + (k & 1)) * groups;
+      float w[8];
+      if (add != nullptr) {
+        tr_unpack(__ldcs(add + o), w);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] += (arg[j] == k) ? d[j] : 0.f;
+      dz[o] = tr_pack(w);
+    }
+  }
+}
+
+// L1Loss(mean) * weight on fp16 tensors (VGG features): loss[0] += weight / n * sum |x - t|; grad (fp16) = gscale * sign(x - t)
+__global__ void __launch_bounds__(kTrThreads) l1_loss_f16_kernel(const uint4* __restrict__ x, const uint4* __restrict__ t,
+                                                                 long long n8, float lscale, float gscale, float* __restrict__ loss,
+                                                                 uint4* __restrict__ grad) {
+  __shared__ float red[kTrThreads / 32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kTrThreads) {
+    float a[8], b[8], gq[8];
+    tr_unpack(__ldcs(x + i), a);
+    tr_unpack(__ldcs(t + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = a[j] - b[j];
+      acc += fabsf(d);
+      gq[j] = d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f);
+    }
+    if (grad != nullptr) grad[i] = tr_pack(gq);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kTrThreads / 32; ++i) s += red[i];
+    atomicAdd(loss, s * lscale);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ R1 penalty pieces
 // sum of squares of an fp32 array: out[0] += scale * sum x^2   (|grad_x D|^2 of the R1 penalty, losses.py:492-506)
 __global__ void __launch_bounds__(kTrThreads) sum_squares_kernel(const float* __restrict__ x, long long n, float scale,
@@ -681,6 +787,38 @@ extern "C" int b200ir_softplus_loss(const void* pred, int n, int stride, float s
   softplus_loss_kernel<<<1, kTrThreads, 0, STREAM>>>((const __half*)pred, n, stride, sign, weight / (float)n,
                                                      grad_scale * weight / (float)n, loss, (__half*)dpred);
   return check_launch("softplus_loss");
+}
+
+extern "C" int b200ir_maxpool2_relu(const void* z, void* out, int B, int H, int W, int C, void* stream) {
+  B200IR_REQUIRE(z && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0,
+                 "maxpool2_relu: bad arguments (H, W even; C %% 8 == 0)");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_relu_kernel<<<tr_grid(n, sms, 16), kTrThreads, 0, STREAM>>>((const uint4*)z, (uint4*)out, n, H / 2, W / 2, C / 8);
+  return check_launch("maxpool2_relu");
+}
+
+extern "C" int b200ir_maxpool2_relu_bwd(const void* z, const void* dpool, const void* add, void* dz, int B, int H, int W, int C,
+                                        void* stream) {
+  B200IR_REQUIRE(z && dz && (dpool || add) && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0,
+                 "maxpool2_relu_bwd: bad arguments");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_relu_bwd_kernel<<<tr_grid(n, sms, 16), kTrThreads, 0, STREAM>>>((const uint4*)z, (const uint4*)dpool, (const uint4*)add,
+                                                                          (uint4*)dz, n, H / 2, W / 2, C / 8);
+  return check_launch("maxpool2_relu_bwd");
+}
+
+extern "C" int b200ir_l1_loss_f16(const void* x, const void* t, int64_t n, float weight, float grad_scale, float* loss, void* grad,
+                                  void* stream) {
+  B200IR_REQUIRE(x && t && loss && n > 0 && n % 8 == 0, "l1_loss_f16: bad arguments (n %% 8 == 0)");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  l1_loss_f16_kernel<<<tr_grid(n / 8, sms, 8), kTrThreads, 0, STREAM>>>((const uint4*)x, (const uint4*)t, n / 8, weight / (float)n,
+                                                                       grad_scale * weight / (float)n, loss, (uint4*)grad);
+  return check_launch("l1_loss_f16");
 }
 
 extern "C" int b200ir_sum_squares(const float* x, int64_t n, float scale, float* out, void* stream) {

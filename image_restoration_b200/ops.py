@@ -799,3 +799,22 @@ def minibatch_stddev_hvp(x, t, a, group):
     check(_lib.lib().b200ir_minibatch_stddev_hvp(_ptr(x), _ptr(t), _ptr(a), _ptr(q), b, h * w, c, group, _stream()),
           'minibatch_stddev_hvp')
     return q
+
+
+def maxpool2_relu(z, out):
+    b, h, w, c = z.shape
+    check(_lib.lib().b200ir_maxpool2_relu(_ptr(z), _ptr(out), b, h, w, c, _stream()), 'maxpool2_relu')
+
+
+def maxpool2_relu_bwd(z, dpool, add, dz):
+    b, h, w, c = z.shape
+    check(_lib.lib().b200ir_maxpool2_relu_bwd(_ptr(z), _ptr(dpool), _ptr(add), _ptr(dz), b, h, w, c, _stream()),
+          'maxpool2_relu_bwd')
+
+
+def l1_loss_f16(x, t, weight, grad_scale, loss, grad):
+    _req(x, torch.float16, 'x')
+    _req(t, torch.float16, 't')
+    assert x.shape == t.shape
+    check(_lib.lib().b200ir_l1_loss_f16(_ptr(x), _ptr(t), x.numel(), float(weight), float(grad_scale), _ptr(loss), _ptr(grad),
+                                        _stream()), 'l1_loss_f16')

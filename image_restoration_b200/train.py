@@ -366,16 +366,18 @@ def construct_img_pyramid(gt, levels):
 class GFPGANTrainer:
     """optimize_parameters of GFPGANModel (gfpgan_model.py:494-691) for the plate options: pixel L1 (weight 0.1), image
     pyramid L1 (weight 1), GAN 'wgan_softplus' (weight 0.1), net_d logistic loss; Adam lr 2e-3 betas (0, 0.99) for both
-    networks; EMA decay 0.5 ** (32 / 10000); R1 penalty on the real batch every net_d_reg_every iterations (r1.py).  The
-    perceptual / identity / facial-component terms are not part of this step (VGG19 / ArcFace weights are not available
-    offline; the component discriminators are off for plates).
+    networks; EMA decay 0.5 ** (32 / 10000); R1 penalty on the real batch every net_d_reg_every iterations (r1.py); the
+    perceptual + style terms when a VGG19 is supplied (perceptual.py).  The identity / facial-component terms are not part of
+    this step (ArcFace / component discriminators are face-specific and off for plates).
 
     net_g: image_restoration_b200.GFPGANv1OCR (fix_decoder=True) on the device; net_d: image_restoration_b200.disc.StyleGAN2Discriminator;
     net_g_ema: optional second GFPGANv1OCR that receives the EMA of the trainable parameters."""
 
     def __init__(self, net_g, net_d, net_g_ema=None, lr_g=2e-3, lr_d=2e-3, betas=(0.0, 0.99), pix_weight=0.1, pyramid_weight=1.0,
                  gan_weight=0.1, ema_decay=0.5 ** (32 / (10 * 1000)), loss_scale=None, group=None, net_d_iters=1,
-                 net_d_init_iters=0, r1_reg_weight=10.0, net_d_reg_every=16):
+                 net_d_init_iters=0, r1_reg_weight=10.0, net_d_reg_every=16, perceptual=None):
+        """perceptual: None, or dict(vgg=perceptual.VGG19Features, layer_weights={...}, perceptual_weight=1.0, style_weight=50.0)
+        — the `perceptual_opt` of the training YAMLs (gfpgan_model.py:538-545)."""
         from .grad_sync import GradAllReducer
         from .optim import FlatAdam
         import torch.distributed as dist
@@ -384,6 +386,7 @@ class GFPGANTrainer:
         self.ema_decay, self.loss_scale = ema_decay, loss_scale
         self.net_d_iters, self.net_d_init_iters = net_d_iters, net_d_init_iters
         self.r1_reg_weight, self.net_d_reg_every = r1_reg_weight, net_d_reg_every
+        self.perceptual = perceptual
         self.g_params = [p for p in net_g.parameters() if p.requires_grad]
         self.d_params = list(net_d.parameters())
         ema_params = None
@@ -453,6 +456,13 @@ class GFPGANTrainer:
                     l_p = l1_loss(rgb, tgt, self.pyramid_weight, S)
                     log[f'l_p_{2 ** (i + 3)}'] = l_p.detach()
                     total = total + l_p
+            if self.perceptual is not None:                                                         # :538-545
+                from .perceptual import perceptual_loss
+                pc = self.perceptual
+                l_per, lp, ls = perceptual_loss(output, gt, pc['vgg'], pc['layer_weights'], pc.get('perceptual_weight', 1.0),
+                                                pc.get('style_weight', 0.0), S)
+                log['l_g_percep'], log['l_g_style'] = lp.detach(), ls.detach()
+                total = total + l_per
             fake_g_pred = disc_forward_image(self.d_sd, output)                                    # :549-552
             l_g_gan = gan_softplus_loss(fake_g_pred, True, self.gan_weight, S)
             log['l_g_gan'] = l_g_gan.detach()

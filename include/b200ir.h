@@ -295,6 +295,20 @@ int b200ir_first_conv_dgrad(const void* dz, const float* w, float* dx, int accum
  * kernels: head NHWC fp16 [B][P][cpad] -> rgb fp32 NCHW [B][3][P] (what the reference returns in out_rgbs), and the adjoint. */
 int b200ir_head_to_nchw(const void* head, float* rgb, int B, int64_t P, int cpad, void* stream);
 int b200ir_nchw_to_head(const float* drgb, void* dhead, int B, int64_t P, int cpad, void* stream);
+/* Perceptual loss (PerceptualLoss, basicsr/losses/losses.py:250-356 over VGGFeatureExtractor, basicsr/archs/vgg_arch.py:56-160):
+ * the VGG19 convs run on b200ir_conv_igemm (nn.Conv2d 3x3 + bias + ReLU = act 2, slope 0), their input gradients on the same
+ * kernel with adjoint weights, the Gram matrices of the style term on b200ir_conv_wgrad_view; these are the remaining stages.
+ * maxpool2_relu: nn.ReLU + nn.MaxPool2d(2, 2) on a pre-activation tensor z NHWC fp16 [B][H][W][C] -> [B][H/2][W/2][C]
+ *   (the tapped layers are read BEFORE their ReLU, so the conv stores z and this kernel applies both);
+ * maxpool2_relu_bwd: dz = add + dpool routed to the first maximum of each window when it is positive (add: the loss
+ *   gradient at the tapped layer, may be NULL; dpool may be NULL for the top layer);
+ * l1_loss_f16: b200ir_l1_loss on fp16 tensors with an fp16 gradient (n % 8 == 0). */
+int b200ir_maxpool2_relu(const void* z, void* out, int B, int H, int W, int C, void* stream);
+int b200ir_maxpool2_relu_bwd(const void* z, const void* dpool, const void* add, void* dz, int B, int H, int W, int C,
+                             void* stream);
+int b200ir_l1_loss_f16(const void* x, const void* t, int64_t n, float weight, float grad_scale, float* loss, void* grad,
+                       void* stream);
+
 /* R1 penalty of the discriminator (r1_penalty, basicsr/losses/losses.py:492-506; gfpgan_model.py:683-689): the double
  * backward is assembled from the primal backward signals and a forward-mode (tangent) pass along v = grad_x sum D(x), see
  * image_restoration_b200/r1.py.  These are its three non-GEMM pieces:

@@ -537,6 +537,33 @@ class SimLib:
         o[..., :Cc].copy_((xt * mul).permute(0, 2, 3, 1).clamp(-65504, 65504))
         return 0
 
+    def b200ir_maxpool2_relu(self, z, out, B, H, W, Cc, stream):
+        self.launches += 1
+        zt = nchw(T(z, (B, H, W, Cc), torch.float16).float())
+        T(out, (B, H // 2, W // 2, Cc), torch.float16).copy_(nhwc(F.max_pool2d(F.relu(zt), 2, 2)))
+        return 0
+
+    def b200ir_maxpool2_relu_bwd(self, z, dpool, add, dz, B, H, W, Cc, stream):
+        self.launches += 1
+        o = torch.zeros(B, H, W, Cc)
+        if _addr(dpool):
+            with torch.enable_grad():
+                zt = nchw(T(z, (B, H, W, Cc), torch.float16).float()).requires_grad_()
+                F.max_pool2d(F.relu(zt), 2, 2).backward(nchw(T(dpool, (B, H // 2, W // 2, Cc), torch.float16).float()))
+            o = nhwc(zt.grad)
+        if _addr(add):
+            o = o + T(add, (B, H, W, Cc), torch.float16).float()
+        T(dz, (B, H, W, Cc), torch.float16).copy_(o.clamp(-65504, 65504))
+        return 0
+
+    def b200ir_l1_loss_f16(self, x, t, n, weight, grad_scale, loss, grad, stream):
+        self.launches += 1
+        d = T(x, (n,), torch.float16).float() - T(t, (n,), torch.float16).float()
+        T(loss, (1,), torch.float32).add_(weight * d.abs().mean())
+        if _addr(grad):
+            T(grad, (n,), torch.float16).copy_(torch.sign(d) * (grad_scale * weight / n))
+        return 0
+
     def b200ir_sum_squares(self, x, n, scale, out, stream):
         self.launches += 1
         T(out, (1,), torch.float32).add_(scale * T(x, (n,), torch.float32).pow(2).sum())

@@ -239,3 +239,28 @@ def test_minibatch_stddev_tangent_kernels_and_sum_squares(B, h, w, C, group):
     close('stat tangent', got['tcat'][..., C], res['tcat'][..., C], rel=2e-3)
     close('hvp', got['q'], res['q'], rel=3e-3)
     close('sum_squares', gpu['out'], cpu['out'], rel=1e-5)
+
+
+@pytest.mark.parametrize('B,H,W,C', [(3, 16, 48, 64), (2, 6, 10, 512), (2, 128, 384, 64), (5, 2, 2, 24)])
+def test_maxpool2_relu_and_l1_f16(B, H, W, C):
+    """ReLU + MaxPool2d(2, 2) of the VGG feature extractor, its backward (first maximum of the window, only when positive,
+    plus the addend) and the fp16 L1 loss, against torch (tests/cabi_sim.py)."""
+    from image_restoration_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    z = rn(B, H, W, C, g=g).half()
+    z[0, 0, 0] = z[0, 0, 1]                                                                          # an exact tie in one window
+    t = dict(z=z, out=torch.zeros(B, H // 2, W // 2, C).half(), dpool=rn(B, H // 2, W // 2, C, g=g).half(),
+             add=rn(B, H, W, C, g=g).half(), dz=torch.zeros(B, H, W, C).half(), dz2=torch.zeros(B, H, W, C).half(),
+             t2=rn(B, H, W, C, g=g).half(), loss=torch.zeros(1), grad=torch.zeros(B, H, W, C).half())
+
+    def run(d):
+        ops.maxpool2_relu(d['z'], d['out'])
+        ops.maxpool2_relu_bwd(d['z'], d['dpool'], d['add'], d['dz'])
+        ops.maxpool2_relu_bwd(d['z'], d['dpool'], None, d['dz2'])
+        ops.l1_loss_f16(d['z'], d['t2'], 0.1, 4096.0, d['loss'], d['grad'])
+    gpu, cpu = both(run, t)
+    assert torch.equal(gpu['out'].cpu(), cpu['out'])
+    close('dz', gpu['dz'], cpu['dz'], rel=1e-3)
+    assert torch.equal(gpu['dz2'].cpu(), cpu['dz2'])
+    close('l1_f16', gpu['loss'], cpu['loss'], rel=1e-4)
+    close('l1_f16 grad', gpu['grad'], cpu['grad'], rel=1e-3)
