@@ -37,6 +37,7 @@ class ConvDesc(C.Structure):
         ('act_slope', C.c_float), ('res_mul', C.c_float), ('ps_r', C.c_int32),
         ('ps_c', C.c_int32), ('demod_c', C.c_int32), ('use_tap_mask', C.c_int32), ('tap_mask', C.c_uint32 * 8),
         ('corr_top', C.c_void_p), ('corr_bot', C.c_void_p), ('corr_left', C.c_void_p), ('corr_right', C.c_void_p),
+        ('w_per_image', C.c_int32),
     ]
 
 
@@ -118,6 +119,7 @@ SIGNATURES = {
     'b200ir_first_conv_dgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_head_to_nchw': [_P, _P, _I, _L, _I, _P],
     'b200ir_nchw_to_head': [_P, _P, _I, _L, _I, _P],
+    'b200ir_gram_batched': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_maxpool2_relu': [_P, _P, _I, _I, _I, _I, _P],
     'b200ir_maxpool2_relu_bwd': [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     'b200ir_l1_loss_f16': [_P, _P, _L, _F, _F, _P, _P, _P],

@@ -99,6 +99,7 @@ struct alignas(64) ConvParams {
   int rgb_w_px;
   int no_store;
   int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
+  int w_img_rows;    // per-image weights: rows of the weight matrix per image (= cout), 0 = one matrix for all images
 };
 
 struct TileCoord {
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
             uint8_t* sa = ring + stage * stage_bytes;
             mbar_arrive_expect_tx(&s.full_bar[stage], stage_bytes);
             tma_load_4d(sa, &p.tmap_a[view], &s.full_bar[stage], kc * kBlockK, cx, cy, t.b0);
-            if (!p.b_resident) tma_load_2d(sa + a_bytes, &p.tmap_b, &s.full_bar[stage], kb * kBlockK, t.n0);
+            if (!p.b_resident) tma_load_2d(sa + a_bytes, &p.tmap_b, &s.full_bar[stage], kb * kBlockK, t.n0 + t.b0 * p.w_img_rows);
           }
           __syncwarp();
           if (++stage == p.stages) {

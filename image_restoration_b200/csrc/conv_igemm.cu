@@ -158,9 +158,11 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
     cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)d->tile_w, (cuuint32_t)d->tile_h, (cuuint32_t)d->tile_b};
     if (encode_map(&p.tmap_a[v], a.ptr, 4, dims, strides, box, swz, "activation")) return 1;
   }
+  B200IR_REQUIRE(!d->w_per_image || (d->tile_b == 1 && d->row_mode == 0),
+                 "conv_igemm: per-image weights need tile_b = 1 and the generic kernel");
   {
     const int k_total = d->num_taps * d->cin;
-    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->cout};
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->cout * (d->w_per_image ? (cuuint64_t)d->m_b : 1u)};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)d->block_n};
     if (encode_map(&p.tmap_b, d->weight, 2, dims, strides, box, swz, "weight")) return 1;
@@ -214,7 +216,8 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
     const int st_res = (g_smem_optin - 1024 - tail - w_bytes) / a_bytes;
     static int no_res = -1;
     if (no_res < 0) no_res = (getenv("B200IR_NO_RESIDENT") != nullptr) ? 1 : 0;
-    if (!no_res && d->block_n == d->cout && !d->use_tap_mask && st_res >= 3 && d->num_taps * p.k_chunks >= 2) {
+    if (!no_res && d->block_n == d->cout && !d->use_tap_mask && st_res >= 3 && d->num_taps * p.k_chunks >= 2 &&
+        !d->w_per_image) {
       p.b_resident = 1;
       stages = st_res > kMaxStages ? kMaxStages : st_res;
       smem_bytes = w_bytes + stages * a_bytes + tail + 1024;
@@ -278,6 +281,7 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
     p.slope = d->act == 1 ? 0.2f : (d->act == 2 ? d->act_slope : 1.f);
     if (p.epi >= 0 && d->res_mode != 0) p.act_gain *= d->res_scale;
   }
+  p.w_img_rows = d->w_per_image ? d->cout : 0;
   p.out_scale = d->out_scale; p.rgb_w = d->rgb_w; p.rgb_part = d->rgb_part; p.no_store = d->no_store;
   p.rgb_w_px = d->rgb_w_px; p.rgb_plane = (long long)d->rgb_h * d->rgb_w_px;
   p.rgb_image = (long long)d->m_b * 3 * p.rgb_plane;

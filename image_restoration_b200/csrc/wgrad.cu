@@ -43,6 +43,11 @@ struct WgradParams {
   uint32_t tap_mask;   // bit kh * 3 + kw: taps to compute (the others stay zero)
   int num_kh;          // kernel rows with at least one tap in the mask
   int kh_list[3];
+  // output addressing: dw[img * img_stride + co * co_stride + (kh * 3 + kw) * tap_stride + ci].  The weight gradient sums over
+  // the batch (per_image = 0, one image slot); the per-image Gram matrices of the style loss do not (per_image = 1, grid.y = B,
+  // compact [B][cout][cin] output of the single centre tap).
+  int per_image;
+  long long img_stride, co_stride, tap_stride;
 };
 
 // Shared-memory matrix descriptor of an MN-major operand with the 128-byte swizzle (canonical layout, in 16-byte units:
@@ -75,8 +80,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   const uint32_t kw_mask = (p.tap_mask >> (kh * 3)) & 7u;
   const int ci_blk = u % p.ci_blocks;
   const int co_blk = u / p.ci_blocks;
-  const int t0 = (int)((long long)split * p.num_tiles / p.splits);
-  const int t1 = (int)((long long)(split + 1) * p.num_tiles / p.splits);
+  const int img = blockIdx.y;  // 0 unless per_image
+  const int nt = p.per_image ? p.tiles_x * p.tiles_y : p.num_tiles;
+  const int t_base = p.per_image ? img * nt : 0;
+  const int t0 = t_base + (int)((long long)split * nt / p.splits);
+  const int t1 = t_base + (int)((long long)(split + 1) * nt / p.splits);
   if (t0 >= t1) return;  // CTA-uniform
 
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_smem) + 1023) & ~(uintptr_t)1023);
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     const int ci0 = ci_blk * (64 * kNC);
     for (int kw = 0; kw < 3; ++kw) {
       if (!((kw_mask >> kw) & 1u)) continue;
-      float* dst = p.dw + ((long long)co * 9 + kh * 3 + kw) * p.cin + ci0;
+      float* dst = p.dw + (long long)img * p.img_stride + (long long)co * p.co_stride + (long long)(kh * 3 + kw) * p.tap_stride + ci0;
 #pragma unroll
       for (int c16 = 0; c16 < 4 * kNC; ++c16) {
         if (ci0 + c16 * 16 >= p.cin) break;  // warp-uniform: channels past cin were zero-filled by TMA
@@ -190,8 +198,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
 
 using namespace b200ir;
 
-extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, float* dw, int B, int H, int W, int cout,
-                                      uint32_t tap_mask, void* stream) {
+static int wgrad_launch(const b200ir_view* xv, const void* dy, float* dw, int B, int H, int W, int cout, uint32_t tap_mask,
+                        bool per_image, void* stream) {
   B200IR_REQUIRE(xv && xv->ptr && dy && dw && B > 0 && H > 0 && W > 0 && xv->b == B, "conv_wgrad: bad arguments");
   const int cin = xv->c;
   tap_mask &= 0x1FFu;
@@ -233,8 +241,19 @@ extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, flo
   // One wave of CTAs (one per SM: the ring takes the whole shared memory) and at least ~16 pixel tiles per CTA, so that
   // the fixed cost of a CTA -- 128 x N x 3 fp32 atomics into dW -- stays below its MMA time (measured sweep:
   // tools/sweep_wgrad.py; two waves were 20-45 % slower on every layer of the B = 64 step).
-  int splits = sms / units;
-  if (splits > p.num_tiles / 16) splits = p.num_tiles / 16;
+  p.per_image = per_image ? 1 : 0;
+  if (per_image) {  // compact per-image output of the single tap in the mask: [B][cout][cin]
+    p.img_stride = (long long)cout * cin;
+    p.co_stride = cin;
+    p.tap_stride = 0;
+  } else {
+    p.img_stride = 0;
+    p.co_stride = 9LL * cin;
+    p.tap_stride = cin;
+  }
+  const int tiles_cta = per_image ? p.tiles_x * p.tiles_y : p.num_tiles;  // pixel tiles one (block, image) unit owns
+  int splits = per_image ? sms / (units * B) : sms / units;
+  if (splits > tiles_cta / 16) splits = tiles_cta / 16;
   {
     // tuning switch (tools/sweep_wgrad.py), read once: a positive integer forces the split count; 1 = deterministic
     // (one CTA per dW block, no cross-CTA atomics: the fp32 summation order is then fixed run to run)
@@ -246,10 +265,11 @@ extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, flo
     }
     if (forced > 0) splits = forced;
   }
-  if (splits > p.num_tiles) splits = p.num_tiles;
+  if (splits > tiles_cta) splits = tiles_cta;
   if (splits < 1) splits = 1;
   p.splits = splits;
-  if (cudaMemsetAsync(dw, 0, (size_t)cout * 9 * cin * sizeof(float), st) != cudaSuccess) {
+  const size_t dw_bytes = per_image ? (size_t)B * cout * cin * sizeof(float) : (size_t)cout * 9 * cin * sizeof(float);
+  if (cudaMemsetAsync(dw, 0, dw_bytes, st) != cudaSuccess) {
     set_error("conv_wgrad: cudaMemsetAsync failed");
     return 1;
   }
@@ -258,7 +278,7 @@ extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, flo
       set_error("conv_wgrad: cudaFuncSetAttribute failed");
       return 1;
     }
-    kernel<<<units * splits, kWgThreads, smem, st>>>(p);
+    kernel<<<dim3(units * splits, per_image ? B : 1), kWgThreads, smem, st>>>(p);
     return 0;
   };
   if (nc == 2) {
@@ -267,6 +287,21 @@ extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, flo
     if (launch(conv_wgrad_kernel<1>, WgCfg<1>::kStages * WgCfg<1>::kStage + 1024)) return 1;
   }
   return check_launch("conv_wgrad");
+}
+
+extern "C" int b200ir_conv_wgrad_view(const b200ir_view* xv, const void* dy, float* dw, int B, int H, int W, int cout,
+                                      uint32_t tap_mask, void* stream) {
+  return wgrad_launch(xv, dy, dw, B, H, W, cout, tap_mask, false, stream);
+}
+
+extern "C" int b200ir_gram_batched(const void* x, const void* dy, float* out, int B, int H, int W, int cin, int cout,
+                                   void* stream) {
+  B200IR_REQUIRE(x && dy && out && B > 0 && B <= 65535 && H > 0 && W > 0 && cin > 0, "gram_batched: bad arguments");
+  b200ir_view v = {};
+  v.ptr = x;
+  v.c = cin, v.w = W, v.h = H, v.b = B;
+  v.stride_w = cin, v.stride_h = (int64_t)W * cin, v.stride_b = (int64_t)H * W * cin;
+  return wgrad_launch(&v, dy, out, B, H, W, cout, 1u << 4, true, stream);
 }
 
 extern "C" int b200ir_conv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int cin, int cout,

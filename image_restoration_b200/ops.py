@@ -75,14 +75,21 @@ class ConvOp:
                  out_mul_off=(1, 0, 1, 0), bias=None, demod=None, noise=None, noise_gain=None, noise_strides=(0, 0),
                  act=False, res=None, res_mode=0, res_strides=(0, 0, 0), res_wh=(0, 0), res_scale=1.0, block_n=None,
                  tile=None, max_ctas=0, row_mode=0, out_scale=None, rgb_w=None, rgb_part=None, rgb_hw=(0, 0),
-                 no_store=False, act_slope=None, res_mul=0.0, ps_r=0, ps_c=0, demod_c=0, tap_mask=None, corr=None):
+                 no_store=False, act_slope=None, res_mul=0.0, ps_r=0, ps_c=0, demod_c=0, tap_mask=None, corr=None,
+                 w_per_image=False):
         d = ConvDesc()
         assert 1 <= len(views) <= _lib.MAX_VIEWS and 1 <= len(taps) <= _lib.MAX_TAPS
         for i, v in enumerate(views):
             d.a[i] = v
         d.num_views = len(views)
         _req(weight, torch.float16, 'weight')
-        assert weight.shape == (cout, len(taps) * cin), (weight.shape, cout, len(taps), cin)
+        if w_per_image:      # one weight matrix per image: [m_b, cout, taps * cin]; a tile must not span images
+            assert weight.shape == (m_whb[2], cout, len(taps) * cin), (weight.shape, m_whb, cout, len(taps), cin)
+            d.w_per_image = 1
+            tile = tile or pick_tile(m_whb[0], m_whb[1], m_whb[2], max_b=1)
+            assert tile[2] == 1 and not row_mode
+        else:
+            assert weight.shape == (cout, len(taps) * cin), (weight.shape, cout, len(taps), cin)
         d.weight = weight.data_ptr()
         d.cin, d.cout, d.num_taps = cin, cout, len(taps)
         for i, (v, dx, dy) in enumerate(taps):
@@ -213,10 +220,11 @@ def conv_same(x, weight, out, ksize, **kw):
     """Stride-1 'same' conv (k = 1 or 3) of NHWC x [B,H,W,Cin] into NHWC out [B,H,W,Ctot] (channel offset via
     out_c_off).  EqualConv2d / plain ModulatedConv2d / ConvUpLayer conv."""
     b, h, w, cin = x.shape
-    cout = weight.shape[0]
+    cout = weight.shape[-2]            # [cout, K], or [B, cout, K] with w_per_image
     taps = taps_3x3() if ksize == 3 else [(0, 0, 0)]
     oc = out.shape[3] if out is not None else cout
-    if ksize == 3 and 'tile' not in kw and 'row_mode' not in kw and row_mode_ok(b, h, w, cin, cout):
+    if ksize == 3 and 'tile' not in kw and 'row_mode' not in kw and not kw.get('w_per_image') and \
+            row_mode_ok(b, h, w, cin, cout):
         kw.update(tile=(128, 1, 1), row_mode=1, block_n=cout)
     return ConvOp([nhwc_view(x)], weight, cin, cout, taps, (w, h, b), out, (oc, w * oc, h * w * oc), **kw)
 
@@ -818,3 +826,17 @@ def l1_loss_f16(x, t, weight, grad_scale, loss, grad):
     assert x.shape == t.shape
     check(_lib.lib().b200ir_l1_loss_f16(_ptr(x), _ptr(t), x.numel(), float(weight), float(grad_scale), _ptr(loss), _ptr(grad),
                                         _stream()), 'l1_loss_f16')
+
+
+def gram_batched(x, dy=None, out=None):
+    """out[b] = sum over pixels of dy[b,p,:] (x) x[b,p,:] (fp32 [B, cout, cin]); dy = x: the un-normalised Gram matrices of
+    PerceptualLoss._gram_mat for the whole batch in one launch (b200ir_gram_batched)."""
+    dy = x if dy is None else dy
+    b, h, w, cin = x.shape
+    cout = dy.shape[3]
+    _req(x, torch.float16, 'x')
+    _req(dy, torch.float16, 'dy')
+    if out is None:
+        out = torch.empty(b, cout, cin, device=x.device, dtype=torch.float32)
+    check(_lib.lib().b200ir_gram_batched(_ptr(x), _ptr(dy), _ptr(out), b, h, w, cin, cout, _stream()), 'gram_batched')
+    return out

@@ -6,7 +6,7 @@
 
 The VGG19 convs run on b200ir_conv_igemm (nn.Conv2d 3x3 + bias [+ ReLU] in the epilogue), ReLU + MaxPool on
 b200ir_maxpool2_relu, the feature L1 on b200ir_l1_loss_f16, the Gram matrices on the weight-gradient GEMM
-(b200ir_conv_wgrad_view: sum over pixels of f (x) f, one launch per image) and the backward pass — input gradients only, the
+(b200ir_gram_batched: sum over pixels of f (x) f for every image in one launch) and the backward pass — input gradients only, the
 VGG is frozen — on the same conv kernel with adjoint weights.  The input normalisation ((x + 1) / 2 - mean) / std is folded
 into the first conv (a per-channel shift in the layout conversion, a per-channel factor in its weights).
 
@@ -143,12 +143,9 @@ class VGG19Features:
 
 
 def gram_raw(f):
-    """sum_p f[b,p,i] f[b,p,j] per image (the un-normalised Gram matrix of losses.py:343-356): NHWC fp16 [B,h,w,C] -> fp32 [B,C,C]."""
-    B, h, w, C = f.shape
-    out = torch.empty(B, C, C, device=f.device, dtype=F32)
-    for b in range(B):
-        out[b] = ops.conv1x1_wgrad(f[b:b + 1], f[b:b + 1])
-    return out
+    """sum_p f[b,p,i] f[b,p,j] per image (the un-normalised Gram matrix of losses.py:343-356): NHWC fp16 [B,h,w,C] -> fp32
+    [B,C,C], the whole batch in one launch of the weight-gradient GEMM (b200ir_gram_batched)."""
+    return ops.gram_batched(f)
 
 
 class PerceptualLossFunction(torch.autograd.Function):
@@ -186,10 +183,10 @@ class PerceptualLossFunction(torch.autograd.Function):
                 ops.l1_loss(ga, gb, wgt, n / wgt, style, sign)                        # grad = +-1 exactly
                 if want:
                     sm = (sign + sign.transpose(1, 2)).to(F16).contiguous()           # {-2..2}: exact in fp16
-                    f = torch.full((1, C), sv * wgt / n, device=dev, dtype=F32)        # per-element factor, applied in the epilogue
-                    for i in range(B):     # dF_b = f * F_b (S_b + S_b^T) + the L1 term: 1x1 conv with this image's matrix
-                        ops.conv_same(a[i:i + 1], sm[i], grad[i:i + 1], 1, demod=f, res=grad[i:i + 1], res_mode=1,
-                                      res_strides=(C, w * C, h * w * C), res_wh=(w, h), res_scale=1.0, res_mul=1.0)()
+                    f = torch.full((B, C), sv * wgt / n, device=dev, dtype=F32)        # per-element factor, applied in the epilogue
+                    # dF_b = f * F_b (S_b + S_b^T) + the L1 term: ONE 1x1 conv whose matrix differs per image (w_per_image)
+                    ops.conv_same(a, sm, grad, 1, demod=f, res=grad, res_mode=1, res_strides=(C, w * C, h * w * C),
+                                  res_wh=(w, h), res_scale=1.0, res_mul=1.0, w_per_image=True)()
             if want:
                 dfeat[name] = grad
         dx = None

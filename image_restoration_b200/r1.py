@@ -23,7 +23,7 @@ pre-activation (the adjoint of the tangent network is the primal adjoint).  So:
        backward pass (weights and biases).
 
 All activations NHWC fp16; the backward signals and the tangents carry static scales (s1, s2) that are divided out of the fp32
-weight gradients.  torch allocates, packs weights and adds the results into .grad.
+weight gradients (sq: the Hessian term's own scale).  torch allocates, packs weights and adds the results into .grad.
 """
 import math
 
@@ -39,14 +39,14 @@ def _e16(like, *shape):
     return torch.empty(*shape, device=like.device, dtype=F16)
 
 
-def r1_penalty_backward(sd, x, weight, grad_out_scale=1.0, stddev_group=4, s1=256.0, s2=256.0):
+def r1_penalty_backward(sd, x, weight, grad_out_scale=1.0, stddev_group=4, s1=256.0, s2=256.0, sq=4096.0):
     """l_d_r1 = weight * mean_b |grad_x sum D(x)|^2 for the discriminator `sd` (fp32 CUDA parameters under the reference's
     state_dict names) on the real batch x (fp32 NCHW [B,3,H,W]); weight = r1_reg_weight / 2 * net_d_reg_every.
     Adds grad_out_scale * d(l_d_r1)/d(param) to every parameter's .grad (grad_out_scale = the trainer's loss scale, which the
     fused Adam step divides out) and returns the penalty as a 0-dim fp32 tensor."""
     _lib.require_cuda(x, 'r1.r1_penalty_backward')
     with torch.no_grad():
-        return _r1(sd, x.contiguous().float(), float(weight), float(grad_out_scale), stddev_group, float(s1), float(s2))
+        return _r1(sd, x.contiguous().float(), float(weight), float(grad_out_scale), stddev_group, float(s1), float(s2), float(sq))
 
 
 def _add_grad(p, g):
@@ -57,7 +57,7 @@ def _add_grad(p, g):
         p.grad.add_(g)
 
 
-def _r1(sd, x, weight, gscale, stddev_group, s1, s2):
+def _r1(sd, x, weight, gscale, stddev_group, s1, s2, sq):
     dev = x.device
     B, _, H, W = x.shape
     inv = ops.INV_SQRT2
@@ -176,16 +176,18 @@ def _r1(sd, x, weight, gscale, stddev_group, s1, s2):
     dwl2 = ops.conv1x1_wgrad(thid.view(1, 1, B, n1), dscore.view(1, 1, B, 16))[:1] * (k * sl2)
     _add_grad(sd['final_linear.1.weight'], dwl2)
     # ------------------------------------------------------------------ 5. Hessian term of the minibatch standard deviation
-    q = ops.minibatch_stddev_hvp(feat, tfeat, a, group)                  # carries s1 * s2
+    # q is small (a / (C P) times a tangent): a third static scale keeps this pass out of the fp16 subnormals on its way down
+    q = ops.minibatch_stddev_hvp(feat, tfeat, (a * sq).contiguous(), group)          # carries s1 * s2 * sq
+    kq = k / sq
     need_all = (True, True, True, True, True, True)
     d = q
     for pre, saved, scales in reversed(blocks):
         dx, dw1, db1, dw2, db2, dws, _, _ = resblock_backward(saved, scales, d, need_all)
         for name, gr in ((f'{pre}.conv1.0.weight', dw1), (f'{pre}.conv1.1.bias', db1), (f'{pre}.conv2.1.weight', dw2),
                          (f'{pre}.conv2.2.bias', db2), (f'{pre}.skip.1.weight', dws)):
-            _add_grad(sd[name], gr * k)
+            _add_grad(sd[name], gr * kq)
         d = dx
     dzq, dbq = ops.lrelu_bias_bwd(d, y0)
-    _add_grad(sd['conv_body.0.1.bias'], dbq * k)
-    _add_grad(w0, ops.first_conv_wgrad(x, dzq) * (k / math.sqrt(3.0)))
+    _add_grad(sd['conv_body.0.1.bias'], dbq * kq)
+    _add_grad(w0, ops.first_conv_wgrad(x, dzq) * (kq / math.sqrt(3.0)))
     return penalty[0]

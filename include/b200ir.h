@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200IR_ABI_VERSION 1
+#define B200IR_ABI_VERSION 2
 #define B200IR_MAX_TAPS 16
 #define B200IR_MAX_VIEWS 4
 
@@ -139,6 +139,10 @@ typedef struct {
   const float* corr_bot;
   const float* corr_left;
   const float* corr_right;
+  /* w_per_image != 0: every image has its own weight matrix -- weight is fp16 [m_b][cout][num_taps*cin] and image b contracts
+   * with block b (tile_b must be 1).  The style term of the perceptual loss sends dL/dGram_b back through F_b this way
+   * (a 1x1 conv whose matrix differs per image, losses.py:330-356). */
+  int32_t w_per_image;
 } b200ir_conv_desc;
 
 int b200ir_conv_igemm(const b200ir_conv_desc* d, void* stream);
@@ -295,6 +299,12 @@ int b200ir_first_conv_dgrad(const void* dz, const float* w, float* dx, int accum
  * kernels: head NHWC fp16 [B][P][cpad] -> rgb fp32 NCHW [B][3][P] (what the reference returns in out_rgbs), and the adjoint. */
 int b200ir_head_to_nchw(const void* head, float* rgb, int B, int64_t P, int cpad, void* stream);
 int b200ir_nchw_to_head(const float* drgb, void* dhead, int B, int64_t P, int cpad, void* stream);
+/* Per-image Gram-type reduction on the weight-gradient GEMM (b200ir_conv_wgrad_view's kernel without the sum over the batch):
+ * out[b][co][ci] = sum_{y,x} dy[b][y][x][co] * x[b][y][x][ci];  x NHWC fp16 [B][H][W][cin], dy [B][H][W][cout], out fp32
+ * [B][cout][cin], overwritten.  With dy = x this is the un-normalised Gram matrix of PerceptualLoss._gram_mat
+ * (losses.py:343-356), all images in one launch.  cin % 16 == 0, cout % 8 == 0. */
+int b200ir_gram_batched(const void* x, const void* dy, float* out, int B, int H, int W, int cin, int cout, void* stream);
+
 /* Perceptual loss (PerceptualLoss, basicsr/losses/losses.py:250-356 over VGGFeatureExtractor, basicsr/archs/vgg_arch.py:56-160):
  * the VGG19 convs run on b200ir_conv_igemm (nn.Conv2d 3x3 + bias + ReLU = act 2, slope 0), their input gradients on the same
  * kernel with adjoint weights, the Gram matrices of the style term on b200ir_conv_wgrad_view; these are the remaining stages.

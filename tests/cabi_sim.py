@@ -129,7 +129,7 @@ class SimLib:
         self.launches += 1
         cin, cout, nt = d.cin, d.cout, d.num_taps
         mb, mh, mw = d.m_b, d.m_h, d.m_w
-        W = T(d.weight, (cout, nt * cin), torch.float16).float()
+        W = T(d.weight, (mb if d.w_per_image else 1, cout, nt * cin), torch.float16).float()
         views = []
         for v in range(d.num_views):
             a = d.a[v]
@@ -146,8 +146,8 @@ class SimLib:
             b1 = min(mb, vb)
             if y1 > y0 and x1 > x0:
                 A[:b1, y0:y1, x0:x1] = v[:b1, y0 + dy:y1 + dy, x0 + dx:x1 + dx, :cin].float()
-            Wt = W[:, t * cin:(t + 1) * cin]
-            part = A @ Wt.t()
+            Wt = W[:, :, t * cin:(t + 1) * cin]                                   # [mb | 1, cout, cin]
+            part = torch.einsum('bhwi,boi->bhwo', A, Wt.expand(mb, cout, cin))
             if d.use_tap_mask:
                 for j in range(n_tiles):
                     if not (d.tap_mask[j] >> t) & 1:
@@ -535,6 +535,13 @@ class SimLib:
         o = T(out, (B, H, W, Cpad), torch.float16)
         o.zero_()
         o[..., :Cc].copy_((xt * mul).permute(0, 2, 3, 1).clamp(-65504, 65504))
+        return 0
+
+    def b200ir_gram_batched(self, x, dy, out, B, H, W, cin, cout, stream):
+        self.launches += 1
+        xt = T(x, (B, H * W, cin), torch.float16).float()
+        dt = T(dy, (B, H * W, cout), torch.float16).float()
+        T(out, (B, cout, cin), torch.float32).copy_(torch.einsum('bpo,bpi->boi', dt, xt))
         return 0
 
     def b200ir_maxpool2_relu(self, z, out, B, H, W, Cc, stream):

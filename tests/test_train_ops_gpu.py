@@ -264,3 +264,22 @@ def test_maxpool2_relu_and_l1_f16(B, H, W, C):
     assert torch.equal(gpu['dz2'].cpu(), cpu['dz2'])
     close('l1_f16', gpu['loss'], cpu['loss'], rel=1e-4)
     close('l1_f16 grad', gpu['grad'], cpu['grad'], rel=1e-3)
+
+
+@pytest.mark.parametrize('B,h,w,C', [(3, 16, 48, 64), (5, 8, 24, 256), (2, 128, 384, 64), (4, 4, 12, 512), (3, 6, 10, 128)])
+def test_gram_batched_and_per_image_weights(B, h, w, C):
+    """The two batched pieces of the style loss: per-image Gram matrices on the weight-gradient GEMM (no sum over the batch)
+    and the 1x1 conv whose weight matrix differs per image (w_per_image), both against torch (tests/cabi_sim.py)."""
+    from image_restoration_b200 import ops
+    g = torch.Generator().manual_seed(B * C + h)
+    t = dict(f=rn(B, h, w, C, g=g).half(), gram=torch.zeros(B, C, C), sm=torch.randint(-2, 3, (B, C, C), generator=g).half(),
+             scale=torch.full((B, C), 0.37), grad=rn(B, h, w, C, g=g).half())
+
+    def run(d):
+        ops.gram_batched(d['f'], out=d['gram'])
+        ops.conv_same(d['f'], d['sm'], d['grad'], 1, demod=d['scale'], res=d['grad'], res_mode=1, res_strides=(C, w * C, h * w * C),
+                      res_wh=(w, h), res_scale=1.0, res_mul=1.0, w_per_image=True)()
+    gpu, cpu = both(run, t)
+    close('gram', gpu['gram'], cpu['gram'], rel=1e-3)
+    assert torch.allclose(gpu['gram'].cpu(), gpu['gram'].cpu().transpose(1, 2), rtol=1e-4, atol=1e-3 * cpu['gram'].abs().max().item())
+    close('per-image conv', gpu['grad'], cpu['grad'], rel=2e-3)
