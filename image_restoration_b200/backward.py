@@ -33,6 +33,46 @@ def _need_cuda(t, who):
     _lib.require_cuda(t, f'backward.{who}')
 
 
+# A forward pass can be tagged (`with graph_tag('net_d'):`); a later backward pass through those nodes can then be told to
+# leave the parameter gradients out (`with skip_param_grads('net_d'):`).  optimize_parameters runs net_d on the generator's
+# output twice with identical weights — once for l_g_gan (input gradient only) and once for l_d (parameter gradients only,
+# gfpgan_model.py:549-552, :676-681); the trainer runs that forward ONCE and walks its graph twice (train.GFPGANTrainer).
+_TAG = [None]
+_SKIP_PARAM_GRADS = set()
+
+
+class graph_tag:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        self.prev, _TAG[0] = _TAG[0], self.tag
+
+    def __exit__(self, *exc):
+        _TAG[0] = self.prev
+        return False
+
+
+class skip_param_grads:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        _SKIP_PARAM_GRADS.add(self.tag)
+
+    def __exit__(self, *exc):
+        _SKIP_PARAM_GRADS.discard(self.tag)
+        return False
+
+
+def _need(ctx, params):
+    """ctx.needs_input_grad with the parameter positions cleared when this node's tag is in the skip set."""
+    need = ctx.needs_input_grad
+    if getattr(ctx, 'tag', None) in _SKIP_PARAM_GRADS:
+        need = tuple(False if i in params else n for i, n in enumerate(need))
+    return need
+
+
 def pack_equal_conv3x3(weight):
     """EqualConv2d weight fp32 [cout, cin, 3, 3] -> (packed fp16 [cout, 9*cin] with the equalised-lr scale folded in,
     scale).  stylegan2_ocr_arch.py:629-648."""
@@ -57,23 +97,25 @@ class ConvLayer3x3Function(torch.autograd.Function):
         ops.conv_same(x, wp, y, 3, bias=bias.detach().float().contiguous(), act=activate)()
         ctx.save_for_backward(x, y if activate else None, wp)
         ctx.scale = scale
+        ctx.tag = _TAG[0]
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y, wp = ctx.saved_tensors
+        need = _need(ctx, (1, 2))
         b, h, w, cin = x.shape
         cout = wp.shape[0]
         dy = dy.contiguous()
         if y is not None:
-            dz, dbias = ops.lrelu_bias_bwd(dy, y, want_bias=ctx.needs_input_grad[2])
+            dz, dbias = ops.lrelu_bias_bwd(dy, y, want_bias=need[2])
         else:
-            dz, dbias = dy, (ops.lrelu_bias_bwd(dy, None, scale=1.0)[1] if ctx.needs_input_grad[2] else None)
+            dz, dbias = dy, (ops.lrelu_bias_bwd(dy, None, scale=1.0)[1] if need[2] else None)
         dx = dweight = None
-        if ctx.needs_input_grad[1]:
+        if need[1]:
             dw = ops.conv_wgrad(x, dz)                                           # [cout, 9, cin] fp32
             dweight = dw.view(cout, 3, 3, cin).permute(0, 3, 1, 2) * ctx.scale   # reference layout [cout, cin, 3, 3]
-        if ctx.needs_input_grad[0]:
+        if need[0]:
             dx = torch.empty_like(x)
             ops.conv_dgrad(dz, ops.conv_dgrad_weight(wp, cin), dx)()
         return dx, dweight, dbias, None
@@ -101,24 +143,26 @@ class EqualLinearFunction(torch.autograd.Function):
                       act=activate)()
         ctx.save_for_backward(x, wp, y if activate else None)
         ctx.consts = (scale, lr_mul)
+        ctx.tag = _TAG[0]
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, wp, y = ctx.saved_tensors
+        need = _need(ctx, (1, 2))
         scale, lr_mul = ctx.consts
         b, cin = x.shape
         cout = wp.shape[0]
         dy = dy.contiguous()
         dx = dweight = dbias = None
         if y is not None:
-            dy, dbias = ops.lrelu_bias_bwd(dy, y)
-            dbias = dbias * lr_mul
-        elif ctx.needs_input_grad[2]:
+            dy, dbias = ops.lrelu_bias_bwd(dy, y, want_bias=need[2])
+            dbias = dbias * lr_mul if dbias is not None else None
+        elif need[2]:
             dbias = ops.lrelu_bias_bwd(dy, None, scale=1.0)[1] * lr_mul
-        if ctx.needs_input_grad[1]:
+        if need[1]:
             dweight = ops.conv1x1_wgrad(x.view(1, 1, b, cin), dy.view(1, 1, b, cout)) * scale
-        if ctx.needs_input_grad[0]:
+        if need[0]:
             dx = torch.empty_like(x)
             ops.conv_same(dy.view(1, 1, b, cout), wp.t().contiguous(), dx.view(1, 1, b, cin), 1)()
         return dx, dweight, dbias, None, None
@@ -154,13 +198,14 @@ class ResBlockFunction(torch.autograd.Function):
         out, saved, scales = resblock_forward(x, w1, b1, w2, b2, ws)
         ctx.save_for_backward(*saved)
         ctx.scales = scales
+        ctx.tag = _TAG[0]
         if ResBlockFunction.debug_saved is not None:      # tests read the leaky-ReLU branches the kernels took
             ResBlockFunction.debug_saved.update(t1=saved[1], y2=saved[3])
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        return resblock_backward(ctx.saved_tensors, ctx.scales, dout, ctx.needs_input_grad)[:6]
+        return resblock_backward(ctx.saved_tensors, ctx.scales, dout, _need(ctx, (1, 2, 3, 4, 5)))[:6]
 
 
 def resblock_forward(x, w1, b1, w2, b2, ws):
@@ -330,12 +375,13 @@ class FirstConvFunction(torch.autograd.Function):
         ops.first_conv(xc, ws, bias.detach().float().contiguous(), y)
         ctx.save_for_backward(xc, y, ws)
         ctx.scale = scale
+        ctx.tag = _TAG[0]
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, y, ws = ctx.saved_tensors
-        need = ctx.needs_input_grad
+        need = _need(ctx, (1, 2))
         dz, dbias = ops.lrelu_bias_bwd(dy.contiguous(), y, want_bias=need[2])
         dw = (ops.first_conv_wgrad(x, dz) * ctx.scale).view(-1, 3, 1, 1) if need[1] else None
         dx = None

@@ -434,6 +434,12 @@ class GFPGANTrainer:
             opt.step(grad_scale=1.0 / S, ema_decay=ema_decay)
 
     def optimize_parameters(self, current_iter=1):
+        """One iteration of gfpgan_model.py:494-691.  net_d is evaluated on the generator's output ONCE: the reference calls
+        net_d(self.output) for l_g_gan and net_d(self.output.detach()) for l_d with identical weights (optimizer_d steps after
+        both), so the second forward recomputes the first.  Here the graph of that forward is walked twice — input gradient
+        only for the generator (backward.skip_param_grads), parameter gradients only for the discriminator — and the
+        generator's own graph is cut at `output` so that it can be freed after its backward."""
+        from .backward import graph_tag, skip_param_grads
         lq, gt = self.lq, self.gt
         B = lq.shape[0]
         S = self._scale(B)
@@ -441,13 +447,14 @@ class GFPGANTrainer:
         self._marks = []
         self._mark('start')
         # ---------------- optimize net_g (gfpgan_model.py:497-667)
-        for p in self.d_params:
-            p.requires_grad_(False)
         self.opt_g.zero_grad()
+        self.opt_d.zero_grad()
         output, out_rgbs = train_forward(self.net_g, lq, return_rgb=self.pyramid_weight > 0)
         self.output = output.detach()
         self._mark('g_forward')
-        if current_iter % self.net_d_iters == 0 and current_iter > self.net_d_init_iters:
+        fake_pred = None
+        g_update = current_iter % self.net_d_iters == 0 and current_iter > self.net_d_init_iters
+        if g_update:
             total = l1_loss(output, gt, self.pix_weight, S)                                        # :519-523
             log['l_g_pix'] = total.detach()
             if self.pyramid_weight > 0:                                                             # :531-536
@@ -463,29 +470,36 @@ class GFPGANTrainer:
                                                 pc.get('style_weight', 0.0), S)
                 log['l_g_percep'], log['l_g_style'] = lp.detach(), ls.detach()
                 total = total + l_per
-            fake_g_pred = disc_forward_image(self.d_sd, output)                                    # :549-552
-            l_g_gan = gan_softplus_loss(fake_g_pred, True, self.gan_weight, S)
+            out_leaf = self.output.requires_grad_()                                                 # cut: net_d's graph starts here
+            with graph_tag('net_d'):
+                fake_pred = disc_forward_image(self.d_sd, out_leaf)                                # :549-552
+            l_g_gan = gan_softplus_loss(fake_pred, True, self.gan_weight, S)
             log['l_g_gan'] = l_g_gan.detach()
-            total = total + l_g_gan
             self._mark('g_losses_and_d_forward')
-            self._backward(total, S)
+            with skip_param_grads('net_d'):                                                         # d l_g_gan / d output only
+                l_g_gan.backward(gradient=torch.full_like(l_g_gan, S), retain_graph=True)
+            d_out, out_leaf.grad = out_leaf.grad, None
+            torch.autograd.backward([total, output], [torch.full_like(total, S), d_out])
+            self.output = self.output.detach()
+            del total, output, out_rgbs, d_out
             self._mark('g_backward')
             self._step(self.opt_g, self.sync_g, S, ema_decay=self.ema_decay if self.net_g_ema is not None else None)
+        else:
+            del output, out_rgbs
         self._mark('g_allreduce_adam_ema')
         # ---------------- optimize net_d (:672-691)
-        for p in self.d_params:
-            p.requires_grad_(True)
-        self.opt_d.zero_grad()
-        fake_d_pred = disc_forward_image(self.d_sd, self.output)
+        if fake_pred is None:
+            fake_pred = disc_forward_image(self.d_sd, self.output)
         real_d_pred = disc_forward_image(self.d_sd, gt)
         l_d_real = gan_softplus_loss(real_d_pred, True, 1.0, S)
-        l_d_fake = gan_softplus_loss(fake_d_pred, False, 1.0, S)
+        l_d_fake = gan_softplus_loss(fake_pred, False, 1.0, S)
         l_d = l_d_real + l_d_fake
         log['l_d'] = l_d.detach()
         log['real_score'] = real_d_pred.detach().float().mean()
-        log['fake_score'] = fake_d_pred.detach().float().mean()
+        log['fake_score'] = fake_pred.detach().float().mean()
         self._mark('d_forward')
-        self._backward(l_d, S)
+        torch.autograd.backward([l_d], [torch.full_like(l_d, S)], inputs=self.d_params)
+        del fake_pred, real_d_pred, l_d, l_d_real, l_d_fake
         self._mark('d_backward')
         if self.r1_reg_weight > 0 and self.net_d_reg_every > 0 and current_iter % self.net_d_reg_every == 0:   # :683-689
             from .r1 import r1_penalty_backward
