@@ -259,10 +259,12 @@ def training_step_record(dev, world, B, steps, timed):
     f_d = conv_gflop({k: v for k, v in netd.state_dict().items()}, H, W, 'conv_body.0')
     f_dec = 34.9           # modulated convs of the StyleGAN2 decoder (24.7 plain + 10.2 up-sampling)
     f_unet = GEMM_GFLOP_PER_CROP - f_dec
-    # net_g forward + U-Net dgrad and wgrad + decoder dgrad; net_d: forward + dgrad in the G step, (forward + dgrad + wgrad)
-    # on fake and on real in the D step
+    # net_g forward + U-Net dgrad and wgrad + decoder dgrad; net_d: forward + dgrad on the output (G step), dgrad + wgrad of
+    # that same graph and forward + dgrad + wgrad on the real batch (D step)
     # + the VGG19 of the perceptual loss: forward on output and on gt, input gradient for the output
-    f_train = GFLOP_PER_CROP + 2 * f_unet + f_dec + 8 * f_d + 3 * f_vgg
+    # (the reference evaluates net_d on the generator's output twice with identical weights; the trainer does it once and
+    # walks that graph twice: 7 net_d passes are executed and counted, not 8)
+    f_train = GFLOP_PER_CROP + 2 * f_unet + f_dec + 7 * f_d + 3 * f_vgg
     last = {k: float(v) for k, v in logs[-1].items()}
     first = {k: float(v) for k, v in logs[0].items()}
     del net, ema, netd, vgg
