@@ -57,62 +57,60 @@ __global__ void __launch_bounds__(kBwThreads) lrelu_bias_bwd_kernel(const uint4*
 // skip conv of ResBlock, stylegan2_ocr_arch.py:685-697 with kernel_size = 1): zero-stuffing x2 followed by the same 4-tap
 // FIR, i.e. upfirdn2d(d, k, up = 2, pad = (2, 1)) without UpFirDnUpsample's gain of 4.  Per axis
 //   out[2i] = (3 d[i] + d[i-1]) / 8,   out[2i+1] = (3 d[i] + d[i+1]) / 8,   d = 0 outside.
-// One thread per (input pixel, 8 channels): 3 x 3 neighbourhood in, 2 x 2 outputs (+ optional addend) out.
+// One thread per (OUTPUT pixel, 8 channels): the 2 x 2 input neighbourhood it depends on (L1 / L2 hits: every input is
+// shared by 9 outputs), the optional addend and one 16-byte store.  ~40 registers, so the SM runs at full occupancy; the
+// first version computed a 2 x 2 output patch from a 3 x 3 input patch per thread (~100 registers, 2 CTAs per SM) and was
+// latency-bound at ~40 % of the HBM rate on the training step's largest tensors (torch profiler, B = 256).
 __global__ void __launch_bounds__(kBwThreads) fir_down2_adjoint_kernel(const uint4* __restrict__ d, const uint4* __restrict__ add,
                                                                        uint4* __restrict__ out, int B, int h, int w, int groups) {
-  const long long n = (long long)B * h * w * groups;
+  const int W2 = 2 * w, H2 = 2 * h;
+  const long long n = (long long)B * H2 * W2 * groups;
   for (long long idx = (long long)blockIdx.x * kBwThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kBwThreads) {
-    unsigned r = (unsigned)idx / (unsigned)groups;   // 32-bit index arithmetic: the launcher keeps n below 2^31
-    const int g = (int)((unsigned)idx - r * (unsigned)groups);
-    const unsigned r2 = r / (unsigned)w;
-    const int j = (int)(r - r2 * (unsigned)w);
-    const int b = (int)(r2 / (unsigned)h);
-    const int i = (int)(r2 - (unsigned)b * (unsigned)h);
-    float v[3][3][8];
+    const unsigned r = (unsigned)(idx / groups);     // output pixel index (the launcher keeps B * 2h * 2w below 2^31)
+    const int g = (int)(idx - (long long)r * groups);
+    const unsigned r2 = r / (unsigned)W2;
+    const int X = (int)(r - r2 * (unsigned)W2);
+    const int b = (int)(r2 / (unsigned)H2);
+    const int Y = (int)(r2 - (unsigned)b * (unsigned)H2);
+    const int i = Y >> 1, j = X >> 1;
+    const int ni = (Y & 1) ? i + 1 : i - 1, nj = (X & 1) ? j + 1 : j - 1;   // the neighbour that gets weight 1/8 on this phase
+    const bool vy = ni >= 0 && ni < h, vx = nj >= 0 && nj < w;
+    const uint4* base = d + (long long)b * h * w * groups + g;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 q11 = __ldg(base + ((long long)i * w + j) * groups);
+    const uint4 qn1 = vy ? __ldg(base + ((long long)ni * w + j) * groups) : zero;
+    const uint4 q1n = vx ? __ldg(base + ((long long)i * w + nj) * groups) : zero;
+    const uint4 qnn = (vy && vx) ? __ldg(base + ((long long)ni * w + nj) * groups) : zero;
+    float acc[8];
+    if (add) {
+      const uint4 q = __ldcs(add + idx);
+      const __half2* hq = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int y = i + dy - 1, x = j + dx - 1;
-        uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        if (y >= 0 && y < h && x >= 0 && x < w) q = __ldg(d + (((long long)b * h + y) * w + x) * groups + g);
-        const __half2* hq = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = __half22float2(hq[k]);
-          v[dy][dx][2 * k] = f.x;
-          v[dy][dx][2 * k + 1] = f.y;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(hq[k]);
+        acc[2 * k] = f.x;
+        acc[2 * k + 1] = f.y;
       }
+    } else {
 #pragma unroll
-    for (int py = 0; py < 2; ++py)
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    }
+    const __half2* h11 = reinterpret_cast<const __half2*>(&q11);
+    const __half2* hn1 = reinterpret_cast<const __half2*>(&qn1);
+    const __half2* h1n = reinterpret_cast<const __half2*>(&q1n);
+    const __half2* hnn = reinterpret_cast<const __half2*>(&qnn);
 #pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        const long long o = (((long long)b * 2 * h + 2 * i + py) * (2 * w) + 2 * j + px) * groups + g;
-        float acc[8];
-        if (add) {
-          const uint4 q = __ldcs(add + o);
-          const __half2* hq = reinterpret_cast<const __half2*>(&q);
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = __half22float2(h11[k]), bq = __half22float2(hn1[k]), c = __half22float2(h1n[k]), e = __half22float2(hnn[k]);
+      // same expression (and rounding) as the patch version: (9 v11 + 3 (vn1 + v1n) + vnn) / 64
+      acc[2 * k] += (9.f * a.x + 3.f * (bq.x + c.x) + e.x) * (1.f / 64.f);
+      acc[2 * k + 1] += (9.f * a.y + 3.f * (bq.y + c.y) + e.y) * (1.f / 64.f);
+    }
+    uint4 q;
+    __half2* hq = reinterpret_cast<__half2*>(&q);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 f = __half22float2(hq[k]);
-            acc[2 * k] = f.x;
-            acc[2 * k + 1] = f.y;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        }
-        const int ny = py ? 2 : 0, nx = px ? 2 : 0;  // the neighbour that gets weight 1/8 on this phase
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          acc[k] += (9.f * v[1][1][k] + 3.f * (v[ny][1][k] + v[1][nx][k]) + v[ny][nx][k]) * (1.f / 64.f);
-        uint4 q;
-        __half2* hq = reinterpret_cast<__half2*>(&q);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hq[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
-        __stcs(out + o, q);
-      }
+    for (int k = 0; k < 4; ++k) hq[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+    __stcs(out + idx, q);
   }
 }
 
@@ -299,13 +297,13 @@ extern "C" int b200ir_fir_pad11(const void* in, void* out, int B, int H, int W, 
 }
 
 extern "C" int b200ir_fir_down2_adjoint(const void* d, const void* add, void* out, int B, int h, int w, int C, void* stream) {
-  B200IR_REQUIRE(d && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0 && (long long)B * h * w * (C / 8) < (1LL << 31),
+  B200IR_REQUIRE(d && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0 && (long long)B * h * w * 4 < (1LL << 31),
                  "fir_down2_adjoint: bad arguments");
   const int sms = num_sms();
   if (sms == 0) return 1;
-  const long long n = (long long)B * h * w * (C / 8);
+  const long long n = (long long)B * h * w * 4 * (C / 8);
   long long grid = (n + kBwThreads - 1) / kBwThreads;
-  if (grid > 16LL * sms) grid = 16LL * sms;
+  if (grid > 64LL * sms) grid = 64LL * sms;
   fir_down2_adjoint_kernel<<<(int)grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const uint4*)d, (const uint4*)add, (uint4*)out, B, h, w, C / 8);
   return check_launch("fir_down2_adjoint");

@@ -27,6 +27,12 @@ out = {'source': f'ncu dram__bytes_read.sum + dram__bytes_write.sum over the {le
                  f'B=64 forward ({os.path.basename(path)}), averaged per launch',
        'launches': len(launches), 'dram_bytes_per_launch': (rd + wr) / len(launches),
        'dram_read_bytes_per_step': rd, 'dram_write_bytes_per_step': wr, 'ncu_time_s_per_step': t}
+try:      # the commit the capture was taken from (the working tree gpurun snapshotted)
+    import subprocess
+    out['commit'] = subprocess.check_output(['git', 'rev-parse', '--short', 'HEAD'], text=True,
+                                            cwd=os.path.dirname(os.path.abspath(__file__))).strip()
+except Exception:
+    pass
 print(json.dumps(out, indent=1))
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 json.dump(out, open(os.path.join(root, 'profiles', 'conv_traffic.json'), 'w'), indent=1)
