@@ -72,7 +72,7 @@ __global__ void first_conv_kernel(const float* __restrict__ x, const float* __re
 // bank groups), then the CTA writes its 256 pixels as one contiguous run of 16-byte chunks: full 128-byte lines per
 // warp store instead of 32 partial lines.  Four rounds of 256 pixels per CTA with all input loads issued up front.
 constexpr int kFcPix = 4;  // pixels per thread (rounds of 256 pixels per CTA)
-template <int kCpp>  // 16-byte chunks per pixel = cout / 8: 2, 4 or 8
+template <int kCpp>  // 16-byte chunks per pixel = cout / 8: 2, 4, 8 or 16
 __global__ void __launch_bounds__(kPwThreads) first_conv_staged_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                        const float* __restrict__ bias, __half* __restrict__ out,
                                                                        long long n_pix, int HW, int cout) {
@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(kPwThreads) first_conv_staged_kernel(const flo
   for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * 3 + i] = bias[i];
   __syncthreads();
   constexpr int cpp = kCpp;
-  constexpr int cs = kCpp == 2 ? 1 : (kCpp == 4 ? 2 : 3), gs = 3 - cs;    // shifts: q / cpp, px / (8 / cpp)
+  // shifts: q / cpp, px / (8 / cpp).  cout = 128 (16 chunks, 256 bytes per pixel: the discriminator's first layer): every pixel
+  // starts on the same bank group, the XOR with the low pixel bits spreads a quarter warp over all eight of them
+  constexpr int cs = kCpp == 2 ? 1 : (kCpp == 4 ? 2 : (kCpp == 8 ? 3 : 4)), gs = cs >= 3 ? 0 : 3 - cs;
   const int t = threadIdx.x;
   const int swz = (t >> gs) & (cpp - 1);
   const long long base0 = (long long)blockIdx.x * (kPwThreads * kFcPix);
@@ -960,10 +962,21 @@ extern "C" int b200ir_first_conv(const float* x, const float* w, const float* bi
   B200IR_REQUIRE(x && w && bias && out, "first_conv: null pointer");
   B200IR_REQUIRE(cout % 8 == 0 && cout <= 512, "first_conv: cout=%d", cout);
   const long long n = (long long)B * H * W;
-  if ((cout == 16 || cout == 32 || cout == 64) && n < (1LL << 31)) {
-    const size_t smem = (size_t)kPwThreads * cout * 2 + cout * 4 * sizeof(float);  // <= 33 KB
+  if ((cout == 16 || cout == 32 || cout == 64 || cout == 128) && n < (1LL << 31)) {
+    const size_t smem = (size_t)kPwThreads * cout * 2 + cout * 4 * sizeof(float);  // <= 33 KB (cout = 128: 66 KB, opt-in)
     const int grid = grid_for((n + kFcPix - 1) / kFcPix);
-    if (cout == 16)
+    if (cout == 128) {
+      static bool configured = false;
+      if (!configured) {
+        if (cudaFuncSetAttribute(first_conv_staged_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+          set_error("first_conv: cudaFuncSetAttribute failed");
+          return 1;
+        }
+        configured = true;
+      }
+      first_conv_staged_kernel<16><<<grid, kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
+    } else if (cout == 16)
       first_conv_staged_kernel<2><<<grid, kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
     else if (cout == 32)
       first_conv_staged_kernel<4><<<grid, kPwThreads, smem, STREAM>>>(x, w, bias, (__half*)out, n, H * W, cout);
