@@ -63,15 +63,18 @@ __global__ void __launch_bounds__(kBwThreads) lrelu_bias_bwd_kernel(const uint4*
 // latency-bound at ~40 % of the HBM rate on the training step's largest tensors (torch profiler, B = 256).
 __global__ void __launch_bounds__(kBwThreads) fir_down2_adjoint_kernel(const uint4* __restrict__ d, const uint4* __restrict__ add,
                                                                        uint4* __restrict__ out, int B, int h, int w, int groups) {
+  // grid: x = chunks of one output row's (X, channel group) pairs, y = output rows (b, Y): the index arithmetic per element is
+  // one 32-bit division (a 64-bit division per element made the first per-pixel version ALU-bound at half the HBM rate)
   const int W2 = 2 * w, H2 = 2 * h;
-  const long long n = (long long)B * H2 * W2 * groups;
-  for (long long idx = (long long)blockIdx.x * kBwThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kBwThreads) {
-    const unsigned r = (unsigned)(idx / groups);     // output pixel index (the launcher keeps B * 2h * 2w below 2^31)
-    const int g = (int)(idx - (long long)r * groups);
-    const unsigned r2 = r / (unsigned)W2;
-    const int X = (int)(r - r2 * (unsigned)W2);
-    const int b = (int)(r2 / (unsigned)H2);
-    const int Y = (int)(r2 - (unsigned)b * (unsigned)H2);
+  const unsigned row_elems = (unsigned)W2 * (unsigned)groups;
+  for (unsigned row = blockIdx.y; row < (unsigned)B * (unsigned)H2; row += gridDim.y) {
+    const int b = (int)(row / (unsigned)H2);
+    const int Y = (int)(row - (unsigned)b * (unsigned)H2);
+    const unsigned e = blockIdx.x * kBwThreads + threadIdx.x;
+    if (e >= row_elems) continue;
+    const int X = (int)(e / (unsigned)groups);
+    const int g = (int)(e - (unsigned)X * (unsigned)groups);
+    const long long idx = (long long)row * row_elems + e;
     const int i = Y >> 1, j = X >> 1;
     const int ni = (Y & 1) ? i + 1 : i - 1, nj = (X & 1) ? j + 1 : j - 1;   // the neighbour that gets weight 1/8 on this phase
     const bool vy = ni >= 0 && ni < h, vx = nj >= 0 && nj < w;
@@ -301,10 +304,10 @@ extern "C" int b200ir_fir_down2_adjoint(const void* d, const void* add, void* ou
                  "fir_down2_adjoint: bad arguments");
   const int sms = num_sms();
   if (sms == 0) return 1;
-  const long long n = (long long)B * h * w * 4 * (C / 8);
-  long long grid = (n + kBwThreads - 1) / kBwThreads;
-  if (grid > 64LL * sms) grid = 64LL * sms;
-  fir_down2_adjoint_kernel<<<(int)grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  const unsigned row_elems = (unsigned)(2 * w) * (unsigned)(C / 8);
+  const long long rows = (long long)B * 2 * h;
+  const dim3 grid((row_elems + kBwThreads - 1) / kBwThreads, (unsigned)(rows < 65535 ? rows : 65535));
+  fir_down2_adjoint_kernel<<<grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const uint4*)d, (const uint4*)add, (uint4*)out, B, h, w, C / 8);
   return check_launch("fir_down2_adjoint");
 }

@@ -75,16 +75,17 @@ __global__ void __launch_bounds__(kTrThreads) sft_mod_kernel(const uint4* __rest
                                                              const float* __restrict__ s_next, uint4* __restrict__ out,
                                                              long long n, long long P, int row_groups) {
   for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
-    const long long pix = idx / row_groups;
-    const int g = (int)(idx - pix * row_groups);
-    const long long b = pix / P;
+    // 32-bit index arithmetic (the launcher keeps n below 2^32): 64-bit divisions per element would make this ALU-bound
+    const unsigned pix = (unsigned)idx / (unsigned)row_groups;
+    const int g = (int)((unsigned)idx - pix * (unsigned)row_groups);
+    const long long b = pix / (unsigned)P;
     float v[8];
     tr_unpack(__ldcs(a + idx), v);
     const int gs = g - (row_groups - sft_groups);
     if (scale != nullptr && gs >= 0) {
       float sc[8], sh[8];
-      tr_unpack(__ldcs(scale + pix * sft_groups + gs), sc);
-      tr_unpack(__ldcs(shift + pix * sft_groups + gs), sh);
+      tr_unpack(__ldcs(scale + (long long)pix * sft_groups + gs), sc);
+      tr_unpack(__ldcs(shift + (long long)pix * sft_groups + gs), sh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
     }
@@ -423,12 +424,12 @@ __global__ void __launch_bounds__(kTrThreads) softplus_loss_kernel(const __half*
 __global__ void __launch_bounds__(kTrThreads) maxpool2_relu_kernel(const uint4* __restrict__ z, uint4* __restrict__ out,
                                                                    long long n, int oh, int ow, int groups) {
   for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
-    const long long pix = idx / groups;
-    const int g = (int)(idx - pix * groups);
-    const int x = (int)(pix % ow);
-    const long long r = pix / ow;
-    const int y = (int)(r % oh);
-    const long long b = r / oh;
+    const unsigned pix = (unsigned)idx / (unsigned)groups;      // 32-bit index arithmetic: the launcher keeps n below 2^32
+    const int g = (int)((unsigned)idx - pix * (unsigned)groups);
+    const unsigned r = pix / (unsigned)ow;
+    const int x = (int)(pix - r * (unsigned)ow);
+    const long long b = r / (unsigned)oh;
+    const int y = (int)(r - (unsigned)b * (unsigned)oh);
     const long long base = ((b * 2 * oh + 2 * y) * (2 * ow) + 2 * x) * groups + g;
     float m[8];
 #pragma unroll
@@ -452,12 +453,12 @@ __global__ void __launch_bounds__(kTrThreads) maxpool2_relu_bwd_kernel(const uin
                                                                        const uint4* __restrict__ add, uint4* __restrict__ dz,
                                                                        long long n, int oh, int ow, int groups) {
   for (long long idx = (long long)blockIdx.x * kTrThreads + threadIdx.x; idx < n; idx += (long long)gridDim.x * kTrThreads) {
-    const long long pix = idx / groups;
-    const int g = (int)(idx - pix * groups);
-    const int x = (int)(pix % ow);
-    const long long r = pix / ow;
-    const int y = (int)(r % oh);
-    const long long b = r / oh;
+    const unsigned pix = (unsigned)idx / (unsigned)groups;      // 32-bit index arithmetic: the launcher keeps n below 2^32
+    const int g = (int)((unsigned)idx - pix * (unsigned)groups);
+    const unsigned r = pix / (unsigned)ow;
+    const int x = (int)(pix - r * (unsigned)ow);
+    const long long b = r / (unsigned)oh;
+    const int y = (int)(r - (unsigned)b * (unsigned)oh);
     const long long base = ((b * 2 * oh + 2 * y) * (2 * ow) + 2 * x) * groups + g;
     float v[4][8], d[8];
     if (dpool != nullptr) {
@@ -676,6 +677,7 @@ extern "C" int b200ir_sft_mod(const void* a, const void* scale, const void* shif
   const int sms = num_sms();
   if (sms == 0) return 1;
   const long long n = (long long)B * P * (C / 8);
+  B200IR_REQUIRE(n < (1LL << 32), "sft_mod: too many elements");
   sft_mod_kernel<<<tr_grid(n, sms, 16), kTrThreads, 0, STREAM>>>((const uint4*)a, (const uint4*)scale, (const uint4*)shift,
                                                                  scale ? c_sft / 8 : 0, s_next, (uint4*)out, n, P, C / 8);
   return check_launch("sft_mod");
@@ -795,6 +797,7 @@ extern "C" int b200ir_maxpool2_relu(const void* z, void* out, int B, int H, int 
   const int sms = num_sms();
   if (sms == 0) return 1;
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  B200IR_REQUIRE(n < (1LL << 32), "maxpool2_relu: too many elements");
   maxpool2_relu_kernel<<<tr_grid(n, sms, 16), kTrThreads, 0, STREAM>>>((const uint4*)z, (uint4*)out, n, H / 2, W / 2, C / 8);
   return check_launch("maxpool2_relu");
 }
@@ -806,6 +809,7 @@ extern "C" int b200ir_maxpool2_relu_bwd(const void* z, const void* dpool, const 
   const int sms = num_sms();
   if (sms == 0) return 1;
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  B200IR_REQUIRE(n < (1LL << 32), "maxpool2_relu_bwd: too many elements");
   maxpool2_relu_bwd_kernel<<<tr_grid(n, sms, 16), kTrThreads, 0, STREAM>>>((const uint4*)z, (const uint4*)dpool, (const uint4*)add,
                                                                           (uint4*)dz, n, H / 2, W / 2, C / 8);
   return check_launch("maxpool2_relu_bwd");
