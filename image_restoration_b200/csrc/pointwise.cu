@@ -162,7 +162,11 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float gr = gg[k] * grad_scale + wd * pp[k];
+    float gr = gg[k] * grad_scale + wd * pp[k];
+    // a non-finite gradient element (an fp16 activation gradient that overflowed under the static loss scale) must not
+    // poison the parameter and its moments for good: it is dropped, the element is left where it is (bit test: this file
+    // builds with fast-math).  GFPGANTrainer counts such elements and lowers its loss scale (train.py).
+    if ((__float_as_uint(gr) & 0x7f800000u) == 0x7f800000u) gr = 0.f;
     mm[k] = b1 * mm[k] + (1.f - b1) * gr;
     vv[k] = b2 * vv[k] + (1.f - b2) * gr * gr;
     const float denom = __fsqrt_rn(vv[k]) * inv_bc2_sqrt + eps;          // IEEE sqrt / divide (the file builds with fast-math)

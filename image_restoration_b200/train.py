@@ -387,6 +387,11 @@ class GFPGANTrainer:
         self.net_d_iters, self.net_d_init_iters = net_d_iters, net_d_init_iters
         self.r1_reg_weight, self.net_d_reg_every = r1_reg_weight, net_d_reg_every
         self.perceptual = perceptual
+        # fp16 activation gradients under a static loss scale can overflow when the losses grow; b200ir_adam_step drops
+        # non-finite gradient elements, and every `check_finite_every` iterations the flat gradients are inspected (one host
+        # sync): if any element was non-finite the loss scale is halved (never raised again: the default leaves ~2^5 headroom)
+        self.check_finite_every = 50
+        self.overflow_events = 0
         self.g_params = [p for p in net_g.parameters() if p.requires_grad]
         self.d_params = list(net_d.parameters())
         ema_params = None
@@ -508,5 +513,12 @@ class GFPGANTrainer:
             self._mark('d_r1')
         self._step(self.opt_d, self.sync_d, S)
         self._mark('d_allreduce_adam')
+        if self.check_finite_every and current_iter % self.check_finite_every == 0:
+            flats = [self.sync_g.flat if self.sync_g is not None else self.opt_g.grad,
+                     self.sync_d.flat if self.sync_d is not None else self.opt_d.grad]
+            if not all(bool(torch.isfinite(f).all()) for f in flats):
+                self.overflow_events += 1
+                self.loss_scale = self._scale(B) / 2.0
+                log['loss_scale_halved_to'] = torch.tensor(self.loss_scale)
         self.log = log
         return log

@@ -238,7 +238,8 @@ int b200ir_minibatch_stddev_bwd(const void* x, const void* dcat, const float* ds
  * when ema != NULL, with the EMA update of BaseModel.model_ema (basicsr/models/base_model.py:50-57):
  *   g = grad * grad_scale + weight_decay * p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2
  *   p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps);  ema = decay * ema + (1 - decay) * p
- * All buffers n fp32 elements, 16-byte aligned; step counts from 1. */
+ * All buffers n fp32 elements, 16-byte aligned; step counts from 1.  A non-finite g (an overflowed fp16 activation
+ * gradient under a static loss scale) is treated as 0 for that element instead of turning p, m and v into NaN. */
 int b200ir_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, float* ema, float ema_decay,
                      void* stream);

@@ -398,6 +398,7 @@ class SimLib:
         p, g = T(param, (n,), torch.float32), T(grad, (n,), torch.float32) * grad_scale
         mt, vt = T(m, (n,), torch.float32), T(v, (n,), torch.float32)
         g = g + wd * p
+        g = torch.where(torch.isfinite(g), g, torch.zeros_like(g))
         mt.mul_(b1).add_(g, alpha=1 - b1)
         vt.mul_(b2).addcmul_(g, g, value=1 - b2)
         p.sub_(lr / (1 - b1 ** step) * mt / (vt.sqrt() / math.sqrt(1 - b2 ** step) + eps))

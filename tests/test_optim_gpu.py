@@ -55,3 +55,33 @@ def test_flat_gradient_buffer_with_world_average():
         assert torch.allclose(q, p, rtol=2e-6, atol=1e-8)
     with pytest.raises(ValueError):
         opt.step(ema_decay=0.99)                            # no EMA copy registered
+
+
+def test_non_finite_gradient_elements_are_dropped():
+    """An overflowed fp16 activation gradient (inf / nan in a few elements) must not turn the parameters and the Adam
+    moments into NaN: those elements are treated as zero gradient, every other element steps exactly as torch.optim.Adam."""
+    import torch
+    from image_restoration_b200.optim import FlatAdam
+    ref_net, net = make_net(), make_net()
+    ref_opt = torch.optim.Adam(ref_net.parameters(), lr=2e-3, betas=(0.0, 0.99))
+    opt = FlatAdam(net.parameters())
+    g = torch.Generator(device='cuda').manual_seed(0)
+    bad = {}
+    for i, (p, q) in enumerate(zip(ref_net.parameters(), net.parameters())):
+        gr = torch.randn(p.shape, device='cuda', generator=g)
+        p.grad = gr.clone()
+        gb = gr.clone()
+        flat = gb.view(-1)
+        flat[0] = float('inf')
+        if flat.numel() > 3:
+            flat[3] = float('nan')
+        p.grad.view(-1)[0] = 0.0
+        if flat.numel() > 3:
+            p.grad.view(-1)[3] = 0.0
+        q.grad = gb
+    ref_opt.step()
+    opt.step()
+    for p, q in zip(ref_net.parameters(), net.parameters()):
+        assert torch.isfinite(q).all()
+        assert torch.allclose(q, p, rtol=2e-6, atol=1e-8)
+    assert torch.isfinite(opt.exp_avg).all() and torch.isfinite(opt.exp_avg_sq).all()
