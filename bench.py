@@ -187,7 +187,7 @@ def sr_arch_records(dev, timed, tf_peak):
     return out
 
 
-def training_step_record(dev, world, B, steps, timed):
+def training_step_record(dev, world, B, steps, timed, fix_decoder=False, brief=False):
     """BASELINE configs[4]: on-device pair synthesis (fused degradation kernel) + GFPGANModel.optimize_parameters (net_g
     update on l_g_pix + image pyramid + l_g_gan, EMA, net_d update) at `B` crops per GPU, NCCL all-reduce of the flat
     gradient buffers when world > 1.  Returns the record for the JSON line (rank-local timings; the caller's `timed` does the
@@ -198,8 +198,9 @@ def training_step_record(dev, world, B, steps, timed):
     from image_restoration_b200 import GFPGANv1OCR, degradation as dg, ops, train
     from image_restoration_b200.disc import StyleGAN2Discriminator
     torch.manual_seed(0)
-    net = GFPGANv1OCR(**NET_KW).to(dev).train()
-    ema = GFPGANv1OCR(**NET_KW).to(dev).eval()
+    kw = dict(NET_KW, fix_decoder=fix_decoder)       # the shipped training YAMLs: fix_decoder false (decoder trained as well)
+    net = GFPGANv1OCR(**kw).to(dev).train()
+    ema = GFPGANv1OCR(**kw).to(dev).eval()
     ema.load_state_dict(net.state_dict())
     netd = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1).to(dev)
     # perceptual_opt of the training YAMLs (VGG19, conv1_2 .. conv5_4 before ReLU, perceptual 1 / style 50).  The ImageNet
@@ -247,6 +248,11 @@ def training_step_record(dev, world, B, steps, timed):
     n0 = lib.b200ir_launch_count()
     ms = timed(step, steps, 1, preroll=0.0) / steps
     launches = (lib.b200ir_launch_count() - n0) // (steps + 1)
+    if brief:
+        mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        del net, ema, netd, vgg, tr
+        torch.cuda.empty_cache()
+        return {'ms': ms, 'launches_per_step': int(launches), 'max_memory_gib': mem_gb}
     tr.profile = True
     step()
     phases = tr.phase_ms()
@@ -264,12 +270,13 @@ def training_step_record(dev, world, B, steps, timed):
     # + the VGG19 of the perceptual loss: forward on output and on gt, input gradient for the output
     # (the reference evaluates net_d on the generator's output twice with identical weights; the trainer does it once and
     # walks that graph twice: 7 net_d passes are executed and counted, not 8)
-    f_train = GFLOP_PER_CROP + 2 * f_unet + f_dec + 7 * f_d + 3 * f_vgg
+    # fix_decoder false: + the decoder's weight gradients (one more pass over its modulated convs)
+    f_train = GFLOP_PER_CROP + 2 * f_unet + (1 if fix_decoder else 2) * f_dec + 7 * f_d + 3 * f_vgg
     last = {k: float(v) for k, v in logs[-1].items()}
     first = {k: float(v) for k, v in logs[0].items()}
     del net, ema, netd, vgg
     torch.cuda.empty_cache()
-    return {'ms': ms, 'batch_per_gpu': B, 'launches_per_step': int(launches), 'phase_ms': phases,
+    return {'ms': ms, 'batch_per_gpu': B, 'fix_decoder': fix_decoder, 'launches_per_step': int(launches), 'phase_ms': phases,
             'r1_iteration': {'ms_per_step': sum(phases_r1.values()), 'd_r1_ms': phases_r1.get('d_r1'),
                              'every': tr.net_d_reg_every, 'amortised_ms_per_step': phases_r1.get('d_r1', 0.0) / tr.net_d_reg_every},
             'max_memory_gib': mem_gb, 'gflop_per_crop': f_train, 'disc_forward_gflop_per_crop': f_d,
@@ -610,7 +617,11 @@ def main():
         pipe.slots.clear()
         eng.plans.clear()
         torch.cuda.empty_cache()
-        training = training_step_record(dev, world, args.train_batch, args.train_steps, timed)
+        training = training_step_record(dev, world, args.train_batch, args.train_steps, timed, fix_decoder=False)
+        frozen = training_step_record(dev, world, args.train_batch, args.train_steps, timed, fix_decoder=True, brief=True)
+        ms_frozen = frozen.pop('ms')
+        training['fix_decoder_true'] = dict(frozen, ms_per_step=ms_frozen, crops_per_s=args.train_batch * world / (ms_frozen / 1e3),
+                                            note='same step with the StyleGAN2 decoder frozen (input gradients only)')
 
     if rank == 0:
         tf_peak, hbm_peak, src = peaks()
@@ -670,7 +681,7 @@ def main():
                 'config': 'BASELINE configs[4]: per step and GPU: fused degradation kernel (training-YAML kernel mix incl. JPEG) '
                           '-> lq, img2tensor -> gt; net_g forward (return_rgb) + l_g_pix 0.1 + image pyramid 1.0 + perceptual 1.0 / '
                           'style 50 (VGG19 conv1_2..conv5_4, seeded random weights: the ImageNet checkpoint is not available '
-                          'offline) + l_g_gan 0.1 (wgan_softplus) -> backward (U-Net wgrad/dgrad, frozen StyleGAN2 decoder dgrad, '
+                          'offline) + l_g_gan 0.1 (wgan_softplus) -> backward (U-Net wgrad/dgrad, StyleGAN2 decoder dgrad + wgrad: fix_decoder false as in training_config/*.yml, '
                           'net_d dgrad, VGG dgrad) -> NCCL all-reduce -> fused Adam + EMA; net_d forward on fake and real -> '
                           'logistic loss -> backward -> all-reduce -> fused Adam; R1 penalty every 16th iteration (timed '
                           'separately: r1_iteration).  Not in the step: facial-component / identity terms (off for plates)',

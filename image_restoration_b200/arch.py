@@ -259,7 +259,7 @@ class GFPGANv1OCR(nn.Module):
                                '(move the module and the input to cuda)')
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training call (GFPGANModel.optimize_parameters, gfpgan_model.py:508): the differentiable path -- U-Net through
-            # the autograd Functions of backward.py, frozen decoder through train.FrozenDecoderFunction.  The inference
+            # the autograd Functions of backward.py, StyleGAN2 decoder through train.DecoderFunction.  The inference
             # engine below runs under no_grad and would hand back tensors without history.
             if save_feat_path is not None or load_feat_path is not None:
                 raise NotImplementedError('save_feat_path / load_feat_path are inference options (call .eval() first)')

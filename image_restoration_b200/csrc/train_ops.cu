@@ -162,12 +162,15 @@ __global__ void __launch_bounds__(kTrThreads) sft_mod_bwd_kernel(const uint4* __
 // ------------------------------------------------------------------------------------------ StyleConv tail, backward
 // a = lrelu(y + gain * noise + bias) * sqrt 2 (saved output);  dz = da * sqrt 2 * (a > 0 ? 1 : 0.2);
 // y reconstructed from a;  dd[b][c] += sum_p dz * y;  out = dz * oscale[b][c] * mul
+// kParams (fix_decoder = false): also db[b][c] += sum_p dz (activate.bias) and dn[b][c] += sum_p dz * noise (StyleConv.weight)
+template <bool kParams>
 __global__ void __launch_bounds__(kTrThreads) style_act_bwd_kernel(const uint4* __restrict__ da, const uint4* __restrict__ a,
                                                                    const float* __restrict__ noise, long long noise_sb,
                                                                    const float* __restrict__ noise_gain,
                                                                    const float* __restrict__ bias,
                                                                    const float* __restrict__ oscale, float mul,
-                                                                   uint4* __restrict__ out, float* __restrict__ dd, long long P,
+                                                                   uint4* __restrict__ out, float* __restrict__ dd,
+                                                                   float* __restrict__ db, float* __restrict__ dn, long long P,
                                                                    int groups, int row_groups) {
   __shared__ float part[kTrThreads][9];
   const int gi = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = kTrThreads / groups;
@@ -180,34 +183,49 @@ __global__ void __launch_bounds__(kTrThreads) style_act_bwd_kernel(const uint4* 
     os[j] = ((oscale != nullptr) ? __ldg(oscale + (b * row_groups + grp) * 8 + j) : 1.f) * mul;
   }
   const float gain = (noise != nullptr) ? __ldg(noise_gain) : 0.f;
-  float acc[8];
+  float acc[8], accb[8], accn[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 8; ++j) acc[j] = accb[j] = accn[j] = 0.f;
   for (long long p = (long long)blockIdx.x * lanes + lane; p < P; p += (long long)gridDim.x * lanes) {
     const long long i = (b * P + p) * row_groups + grp;
     float dv[8], av[8], o[8];
     tr_unpack(__ldcs(da + i), dv);
     tr_unpack(__ldcs(a + i), av);
-    const float nz = (noise != nullptr) ? gain * __ldg(noise + b * noise_sb + p) : 0.f;
+    const float nraw = (noise != nullptr) ? __ldg(noise + b * noise_sb + p) : 0.f;
+    const float nz = gain * nraw;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const bool pos = av[j] > 0.f;
       const float dz = dv[j] * (pos ? kTrSqrt2 : 0.2f * kTrSqrt2);
       const float y = av[j] * (pos ? (1.f / kTrSqrt2) : (1.f / (0.2f * kTrSqrt2))) - nz - bs[j];
       acc[j] = fmaf(dz, y, acc[j]);
+      if (kParams) {
+        accb[j] += dz;
+        accn[j] = fmaf(dz, nraw, accn[j]);
+      }
       o[j] = dz * os[j];
     }
     out[i] = tr_pack(o);
   }
-  if (dd != nullptr) tr_reduce_add(acc, dd + (b * row_groups + (long long)blockIdx.y * groups) * 8, groups, lanes, part);
+  const long long tab = (b * row_groups + (long long)blockIdx.y * groups) * 8;
+  if (dd != nullptr) tr_reduce_add(acc, dd + tab, groups, lanes, part);
+  if (kParams) {
+    __syncthreads();
+    tr_reduce_add(accb, db + tab, groups, lanes, part);
+    __syncthreads();
+    tr_reduce_add(accn, dn + tab, groups, lanes, part);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ ToRGB, backward
 // t[c] = sum_o drgb[b][o][p] * w[o][c];  da (+)= s[b][c] * t;  ds[b][c] += sum_p a * t
+// kParams (fix_decoder = false): also R[b][o][c] += sum_p drgb[b][o][p] * a[b][p][c]  (weight gradient of the 1x1 conv before
+// its modulation: dw[o][c] = sum_b s[b][c] R[b][o][c])
+template <bool kParams>
 __global__ void __launch_bounds__(kTrThreads) to_rgb_bwd_kernel(const float* __restrict__ drgb, const uint4* __restrict__ a,
                                                                 const float* __restrict__ w, const float* __restrict__ s,
                                                                 uint4* __restrict__ da, int accumulate, float* __restrict__ ds,
-                                                                long long P, int groups, int row_groups) {
+                                                                float* __restrict__ R, long long P, int groups, int row_groups) {
   __shared__ float part[kTrThreads][9];
   const int gi = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = kTrThreads / groups;
   const int grp = blockIdx.y * groups + gi;
@@ -221,9 +239,9 @@ __global__ void __launch_bounds__(kTrThreads) to_rgb_bwd_kernel(const float* __r
     w2[j] = __ldg(w + 2 * C + grp * 8 + j);
     sv[j] = (s != nullptr) ? __ldg(s + (b * row_groups + grp) * 8 + j) : 1.f;
   }
-  float acc[8];
+  float acc[8], r0[8], r1[8], r2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 8; ++j) acc[j] = r0[j] = r1[j] = r2[j] = 0.f;
   const float* dr = drgb + b * 3 * P;
   for (long long p = (long long)blockIdx.x * lanes + lane; p < P; p += (long long)gridDim.x * lanes) {
     const long long i = (b * P + p) * row_groups + grp;
@@ -235,6 +253,11 @@ __global__ void __launch_bounds__(kTrThreads) to_rgb_bwd_kernel(const float* __r
       const float t = fmaf(d0, w0[j], fmaf(d1, w1[j], d2 * w2[j]));
       acc[j] = fmaf(av[j], t, acc[j]);
       o[j] = t * sv[j];
+      if (kParams) {
+        r0[j] = fmaf(d0, av[j], r0[j]);
+        r1[j] = fmaf(d1, av[j], r1[j]);
+        r2[j] = fmaf(d2, av[j], r2[j]);
+      }
     }
     if (da != nullptr) {
       if (accumulate) {
@@ -247,6 +270,96 @@ __global__ void __launch_bounds__(kTrThreads) to_rgb_bwd_kernel(const float* __r
     }
   }
   if (ds != nullptr) tr_reduce_add(acc, ds + (b * row_groups + (long long)blockIdx.y * groups) * 8, groups, lanes, part);
+  if (kParams) {
+    float* Rb = R + b * 3 * C + (long long)blockIdx.y * groups * 8;
+    __syncthreads();
+    tr_reduce_add(r0, Rb, groups, lanes, part);
+    __syncthreads();
+    tr_reduce_add(r1, Rb + C, groups, lanes, part);
+    __syncthreads();
+    tr_reduce_add(r2, Rb + 2 * C, groups, lanes, part);
+  }
+}
+
+// out[c] += sum over b and p of x[b][c][p] (fp32 NCHW planes): bias gradient of ToRGB (to_rgb.bias, stylegan2_ocr_arch.py:349)
+__global__ void __launch_bounds__(kTrThreads) plane_sums_kernel(const float* __restrict__ x, float* __restrict__ out, int Cn,
+                                                                long long P) {
+  __shared__ float red[kTrThreads / 32];
+  const long long plane = blockIdx.y;             // b * Cn + c
+  float acc = 0.f;
+  const float* xp = x + plane * P;
+  for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < P; i += (long long)gridDim.x * kTrThreads) acc += xp[i];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sacc = 0.f;
+    for (int i = 0; i < kTrThreads / 32; ++i) sacc += red[i];
+    atomicAdd(out + (plane % Cn), sacc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ decoder parameter gradients
+// (fix_decoder = false).  The per-image tables the pointwise adjoints leave behind are folded over the batch here.
+// out[j] = scale * sum_b in[b][j] * (mul ? mul[b][j % m] : 1): bias gradients (sum of db / ds over the batch), the ToRGB
+// weight (R[b][o][c] weighted by s[b][c]), ConstantInput (g0[b][p][c] weighted by s[b][c], fp16 input), the noise gain.
+template <typename T>
+__global__ void __launch_bounds__(kTrThreads) table_colsum_kernel(const T* __restrict__ in, const float* __restrict__ mul, int m,
+                                                                  float scale, float* __restrict__ out, int B, long long n) {
+  const long long j = (long long)blockIdx.x * kTrThreads + threadIdx.x;
+  if (j >= n) return;
+  const int jm = (mul != nullptr) ? (int)(j % m) : 0;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float v = (float)in[(long long)b * n + j];
+    acc = (mul != nullptr) ? fmaf(v, __ldg(mul + (long long)b * m + jm), acc) : acc + v;
+  }
+  out[j] = scale * acc;
+}
+
+// dw[ci][f] = wscale * sum_b ds[b][ci] * latent[b][lat_idx][f]: weight gradient of a modulation EqualLinear
+// (stylegan2_ocr_arch.py:233-234); one CTA per ci.
+__global__ void __launch_bounds__(kTrThreads) mod_linear_wgrad_kernel(const float* __restrict__ ds, const float* __restrict__ lat,
+                                                                      float wscale, float* __restrict__ dw, int L, int F,
+                                                                      int lat_idx, int B, int cin) {
+  const int ci = blockIdx.x;
+  for (int f = threadIdx.x; f < F; f += kTrThreads) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(__ldg(ds + (long long)b * cin + ci), __ldg(lat + ((long long)b * L + lat_idx) * F + f), acc);
+    dw[(long long)ci * F + f] = wscale * acc;
+  }
+}
+
+// Weight gradient of ModulatedConv2d (stylegan2_ocr_arch.py:239-279) assembled in the reference layout:
+//   dw[co][ci][k] = scale * G[co][k][ci] - scale^2 * W[co][ci][k] * sum_b dd[b][co] d[b][co]^2 s[b][ci]^2
+// G = the tap-major result of the weight-gradient GEMM on (modulated input, dy * d); `transposed`: G is [ci][k][co] (the
+// up-sampling conv, whose GEMM runs with the roles of input and output exchanged).  The second term is the dependence of
+// the demodulation table d on W.  One CTA per co.
+__global__ void __launch_bounds__(kTrThreads) modconv_wgrad_kernel(const float* __restrict__ G, int transposed,
+                                                                   const float* __restrict__ W, const float* __restrict__ s,
+                                                                   const float* __restrict__ dd, const float* __restrict__ d,
+                                                                   float scale, float* __restrict__ dw, int B, int cin, int cout,
+                                                                   int taps) {
+  extern __shared__ float t[];  // [B]
+  const int co = blockIdx.x;
+  for (int b = threadIdx.x; b < B; b += kTrThreads) {
+    const float dv = d[(long long)b * cout + co];
+    t[b] = dd[(long long)b * cout + co] * dv * dv;
+  }
+  __syncthreads();
+  for (int ci = threadIdx.x; ci < cin; ci += kTrThreads) {
+    float m = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float sv = __ldg(s + (long long)b * cin + ci);
+      m = fmaf(t[b], sv * sv, m);
+    }
+    m *= scale * scale;
+    for (int k = 0; k < taps; ++k) {
+      const float g = transposed ? G[((long long)ci * taps + k) * cout + co] : G[((long long)co * taps + k) * cin + ci];
+      const long long o = ((long long)co * cin + ci) * taps + k;
+      dw[o] = scale * g - W[o] * m;
+    }
+  }
 }
 
 // adjoint of upfirdn2d(skip, FIR * 4, up = 2, pad = (2, 1)) on fp32 planes: per axis
@@ -708,10 +821,24 @@ extern "C" int b200ir_style_act_bwd(const void* da, const void* a, const float* 
   const int sms = num_sms();
   if (sms == 0) return 1;
   const TrLayout l = tr_layout(C, P, sms, B);
-  style_act_bwd_kernel<<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(
-      (const uint4*)da, (const uint4*)a, noise, noise_stride_b, noise_gain, bias, oscale, mul, (uint4*)out, dd, P, l.groups,
-      C / 8);
+  style_act_bwd_kernel<false><<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(
+      (const uint4*)da, (const uint4*)a, noise, noise_stride_b, noise_gain, bias, oscale, mul, (uint4*)out, dd, nullptr, nullptr,
+      P, l.groups, C / 8);
   return check_launch("style_act_bwd");
+}
+
+extern "C" int b200ir_style_act_bwd_params(const void* da, const void* a, const float* noise, int64_t noise_stride_b,
+                                           const float* noise_gain, const float* bias, const float* oscale, float mul, void* out,
+                                           float* dd, float* db, float* dn, int B, int64_t P, int C, void* stream) {
+  B200IR_REQUIRE(da && a && out && db && dn && B > 0 && P > 0 && C > 0 && C % 8 == 0, "style_act_bwd_params: bad arguments");
+  B200IR_REQUIRE(noise == nullptr || noise_gain != nullptr, "style_act_bwd_params: noise without gain");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const TrLayout l = tr_layout(C, P, sms, B);
+  style_act_bwd_kernel<true><<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(
+      (const uint4*)da, (const uint4*)a, noise, noise_stride_b, noise_gain, bias, oscale, mul, (uint4*)out, dd, db, dn, P,
+      l.groups, C / 8);
+  return check_launch("style_act_bwd_params");
 }
 
 extern "C" int b200ir_to_rgb_bwd(const float* drgb, const void* a, const float* w, const float* s, void* da, int accumulate,
@@ -720,9 +847,54 @@ extern "C" int b200ir_to_rgb_bwd(const float* drgb, const void* a, const float* 
   const int sms = num_sms();
   if (sms == 0) return 1;
   const TrLayout l = tr_layout(C, P, sms, B);
-  to_rgb_bwd_kernel<<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(drgb, (const uint4*)a, w, s, (uint4*)da, accumulate,
-                                                                           ds, P, l.groups, C / 8);
+  to_rgb_bwd_kernel<false><<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(drgb, (const uint4*)a, w, s, (uint4*)da,
+                                                                                  accumulate, ds, nullptr, P, l.groups, C / 8);
   return check_launch("to_rgb_bwd");
+}
+
+extern "C" int b200ir_to_rgb_bwd_params(const float* drgb, const void* a, const float* w, const float* s, void* da, int accumulate,
+                                        float* ds, float* R, int B, int64_t P, int C, void* stream) {
+  B200IR_REQUIRE(drgb && a && w && R && B > 0 && P > 0 && C > 0 && C % 8 == 0, "to_rgb_bwd_params: bad arguments");
+  const int sms = num_sms();
+  if (sms == 0) return 1;
+  const TrLayout l = tr_layout(C, P, sms, B);
+  to_rgb_bwd_kernel<true><<<dim3(l.grid_x, l.chunks, B), kTrThreads, 0, STREAM>>>(drgb, (const uint4*)a, w, s, (uint4*)da,
+                                                                                 accumulate, ds, R, P, l.groups, C / 8);
+  return check_launch("to_rgb_bwd_params");
+}
+
+extern "C" int b200ir_plane_sums(const float* x, float* out, int B, int Cn, int64_t P, void* stream) {
+  B200IR_REQUIRE(x && out && B > 0 && Cn > 0 && P > 0 && (long long)B * Cn <= 65535, "plane_sums: bad arguments");
+  long long gx = (P + kTrThreads * 8 - 1) / (kTrThreads * 8);
+  if (gx > 64) gx = 64;
+  plane_sums_kernel<<<dim3((unsigned)gx, (unsigned)(B * Cn)), kTrThreads, 0, STREAM>>>(x, out, Cn, P);
+  return check_launch("plane_sums");
+}
+
+extern "C" int b200ir_table_colsum(const void* in, int in_f16, const float* mul, int m, float scale, float* out, int B, int64_t n,
+                                   void* stream) {
+  B200IR_REQUIRE(in && out && B > 0 && n > 0 && (mul == nullptr || m > 0), "table_colsum: bad arguments");
+  const unsigned grid = (unsigned)((n + kTrThreads - 1) / kTrThreads);
+  if (in_f16)
+    table_colsum_kernel<__half><<<grid, kTrThreads, 0, STREAM>>>((const __half*)in, mul, m, scale, out, B, n);
+  else
+    table_colsum_kernel<float><<<grid, kTrThreads, 0, STREAM>>>((const float*)in, mul, m, scale, out, B, n);
+  return check_launch("table_colsum");
+}
+
+extern "C" int b200ir_mod_linear_wgrad(const float* ds, const float* latent, float wscale, float* dw, int L, int F, int lat_idx,
+                                       int B, int cin, void* stream) {
+  B200IR_REQUIRE(ds && latent && dw && B > 0 && cin > 0 && F > 0 && lat_idx >= 0 && lat_idx < L, "mod_linear_wgrad: bad arguments");
+  mod_linear_wgrad_kernel<<<cin, kTrThreads, 0, STREAM>>>(ds, latent, wscale, dw, L, F, lat_idx, B, cin);
+  return check_launch("mod_linear_wgrad");
+}
+
+extern "C" int b200ir_modconv_wgrad(const float* G, int transposed, const float* W, const float* s, const float* dd,
+                                    const float* d, float scale, float* dw, int B, int cin, int cout, int taps, void* stream) {
+  B200IR_REQUIRE(G && W && s && dd && d && dw && B > 0 && B <= 8192 && cin > 0 && cout > 0 && taps > 0,
+                 "modconv_wgrad: bad arguments");
+  modconv_wgrad_kernel<<<cout, kTrThreads, B * sizeof(float), STREAM>>>(G, transposed, W, s, dd, d, scale, dw, B, cin, cout, taps);
+  return check_launch("modconv_wgrad");
 }
 
 extern "C" int b200ir_rgb_up_adjoint(const float* d, float* out, int planes, int h, int w, void* stream) {

@@ -840,3 +840,59 @@ def gram_batched(x, dy=None, out=None):
         out = torch.empty(b, cout, cin, device=x.device, dtype=torch.float32)
     check(_lib.lib().b200ir_gram_batched(_ptr(x), _ptr(dy), _ptr(out), b, h, w, cin, cout, _stream()), 'gram_batched')
     return out
+
+
+def style_act_bwd_params(da, a, noise, noise_gain, bias, oscale, mul, out, dd, db, dn):
+    """style_act_bwd + the per-image reductions for StyleConv.activate.bias (db) and the noise gain (dn): fp32 [B, C], zeroed by the caller."""
+    b, h, w, c = a.shape
+    check(_lib.lib().b200ir_style_act_bwd_params(_ptr(da), _ptr(a), _ptr(noise), h * w, _ptr(noise_gain), _ptr(bias), _ptr(oscale),
+                                                 float(mul), _ptr(out), _ptr(dd), _ptr(db), _ptr(dn), b, h * w, c, _stream()),
+          'style_act_bwd_params')
+
+
+def to_rgb_bwd_params(drgb, a, w, s, da, accumulate, ds, R):
+    """to_rgb_bwd + R[b, o, c] += sum_p drgb[b, o, p] a[b, p, c] (fp32 [B, 3, C], zeroed by the caller)."""
+    b, h, wd, c = a.shape
+    _req(drgb, torch.float32, 'drgb')
+    check(_lib.lib().b200ir_to_rgb_bwd_params(_ptr(drgb), _ptr(a), _ptr(w), _ptr(s), _ptr(da), 1 if accumulate else 0, _ptr(ds),
+                                              _ptr(R), b, h * wd, c, _stream()), 'to_rgb_bwd_params')
+
+
+def plane_sums(x, out):
+    """out[c] += sum over batch and pixels of fp32 NCHW x[b, c, :, :]."""
+    b, c, h, w = x.shape
+    _req(x, torch.float32, 'x')
+    check(_lib.lib().b200ir_plane_sums(_ptr(x), _ptr(out), b, c, h * w, _stream()), 'plane_sums')
+
+
+def table_colsum(tab, out=None, mul=None, scale=1.0):
+    """out[j] = scale * sum_b tab[b, j] * (mul[b, j % m] if mul is given): tab fp32 or fp16 [B, ...], mul fp32 [B, m] -> fp32 [n]."""
+    b = tab.shape[0]
+    n = tab.numel() // b
+    assert tab.is_contiguous() and tab.dtype in (torch.float32, torch.float16)
+    if out is None:
+        out = torch.empty(n, device=tab.device, dtype=torch.float32)
+    m = mul.shape[1] if mul is not None else 0
+    check(_lib.lib().b200ir_table_colsum(_ptr(tab), 1 if tab.dtype == torch.float16 else 0, _ptr(mul), m, float(scale), _ptr(out),
+                                         b, n, _stream()), 'table_colsum')
+    return out
+
+
+def mod_linear_wgrad(ds, latent, wscale, lat_idx):
+    """Weight gradient of a modulation EqualLinear: ds fp32 [B, cin], latent fp32 [B, L, F] -> fp32 [cin, F]."""
+    b, L, f = latent.shape
+    dw = torch.empty(ds.shape[1], f, device=ds.device, dtype=torch.float32)
+    check(_lib.lib().b200ir_mod_linear_wgrad(_ptr(ds), _ptr(latent), float(wscale), _ptr(dw), L, f, lat_idx, b, ds.shape[1],
+                                             _stream()), 'mod_linear_wgrad')
+    return dw
+
+
+def modconv_wgrad(G, transposed, w_raw, s, dd, d, scale):
+    """ModulatedConv2d weight gradient in the reference layout [cout, cin, kh, kw] (see include/b200ir.h)."""
+    cout, cin, kh, kw = w_raw.shape
+    _req(w_raw, torch.float32, 'w_raw')
+    _req(G, torch.float32, 'G')
+    dw = torch.empty_like(w_raw)
+    check(_lib.lib().b200ir_modconv_wgrad(_ptr(G), 1 if transposed else 0, _ptr(w_raw), _ptr(s), _ptr(dd), _ptr(d), float(scale),
+                                          _ptr(dw), s.shape[0], cin, cout, kh * kw, _stream()), 'modconv_wgrad')
+    return dw

@@ -1,11 +1,12 @@
 """The training step on the B200 kernels (BASELINE config 5): GFPGANModel.optimize_parameters
-(basicsr/models/gfpgan_model.py:494-691) for the plate configs (`fix_decoder: true`): one net_g update on
+(basicsr/models/gfpgan_model.py:494-691) for the plate configs (`fix_decoder` true or false): one net_g update on
 l_g_pix + image-pyramid + l_g_gan, the EMA, one net_d update on the logistic loss — data-parallel with one NCCL all-reduce of
 the flat gradient buffer per network (base_model.py:62-76).
 
     train_forward(net, lq)          differentiable GFPGANv1OCR.forward(lq, return_rgb=True): U-Net through backward.unet_forward,
-                                    the frozen StyleGAN2 decoder through FrozenDecoderFunction (input gradients only)
-    FrozenDecoderFunction           StyleGAN2OCRGeneratorSFT.forward (gfpganv1_ocr_arch.py:50-136) w.r.t. style code and SFT conditions
+                                    the StyleGAN2 decoder through DecoderFunction
+    DecoderFunction                 StyleGAN2OCRGeneratorSFT.forward (gfpganv1_ocr_arch.py:50-136) w.r.t. style code and SFT conditions,
+                                    and w.r.t. the decoder's own parameters when they require grad (fix_decoder=False)
     l1_loss / gan_softplus_loss     L1Loss(mean) / GANLoss('wgan_softplus') (losses/losses.py:81-106, 404-470), value + gradient in one pass
     disc_forward_image              network_d on an fp32 NCHW image, with the input gradient the generator needs
     GFPGANTrainer                   feed_data / optimize_parameters / model_ema, mirrors GFPGANModel for these options
@@ -32,15 +33,21 @@ class DecoderState:
     convs.  Built once per (module, decoder parameter versions)."""
 
     def __init__(self, net):
-        if any(p.requires_grad for p in net.stylegan_decoder.parameters()):
-            raise NotImplementedError('the training path implements fix_decoder=True (every plate config of SURVEY.md §8): the '
-                                      'StyleGAN2 decoder gets input gradients only')
+        # fix_decoder=False (the shipped training YAMLs): the decoder's own parameters get gradients as well
+        self.trainable = any(p.requires_grad for p in net.stylegan_decoder.parameters())
+        self.param_names = [n for n, _ in net.stylegan_decoder.named_parameters()]
         if not net.input_is_latent:
             raise NotImplementedError('training path: input_is_latent=False (style MLP) is not differentiated')
         dev = next(net.parameters()).device
         self.dev = dev
         sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith('stylegan_decoder.')}
         pack_decoder(self, net, lambda k: sd[k].to(dev), lambda k: sd[k].to(dev).float().contiguous(), train=True)
+        if self.trainable:      # fp32 weights in the reference layout: the demodulation's dependence on W needs them
+            D = 'stylegan_decoder'
+            self.sc1['w_raw'] = sd[f'{D}.style_conv1.modulated_conv.weight'][0].float()
+            for j, c in enumerate(self.sconv):
+                c['w_raw'] = sd[f'{D}.style_convs.{j}.modulated_conv.weight'][0].float()
+            self.const_raw = sd[f'{D}.constant_input.weight'][0].float()
         self.different_w, self.sft_half, self.nf = net.different_w, net.sft_half, net.num_style_feat
         self.H, self.W = net.input_height, net.input_width
         self.ratio = int(self.W / self.H)
@@ -69,9 +76,10 @@ def _convt_merged(cout, B, h, w):
     return cout <= 128 or B * h * w < 40000
 
 
-class FrozenDecoderFunction(torch.autograd.Function):
+class DecoderFunction(torch.autograd.Function):
     """image = stylegan_decoder([style_code], conditions) (gfpganv1_ocr_arch.py:387-391, 50-136) with gradients for the style
-    code and the SFT conditions; the decoder's own parameters are frozen.
+    code and the SFT conditions, and — when the decoder is trainable (fix_decoder=False, the shipped training YAMLs) — for
+    every decoder parameter on the path (the style MLP is unused with input_is_latent=True: no gradient, as in the reference).
 
     forward : existing forward kernels, but every StyleConv keeps its un-modulated output `a` (post-activation, pre-SFT) —
               the inference plan fuses SFT and the next modulation into the producer and keeps neither;
@@ -80,8 +88,13 @@ class FrozenDecoderFunction(torch.autograd.Function):
               views (adjoint of conv_transpose2d + FIR), then demod_bwd + mod_linear_bwd into d(latent)."""
 
     @staticmethod
-    def forward(ctx, st, noises, style_code, *conds):
+    def forward(ctx, st, noises, n_conds, style_code, *rest):
+        """rest = the n_conds SFT condition tensors, then (fix_decoder=False) the decoder's parameters in named_parameters()
+        order — passed only so that autograd routes their gradients; the arithmetic uses the packed copies in `st`."""
         _lib.require_cuda(style_code, 'train.FrozenDecoderFunction')
+        conds = rest[:n_conds]
+        ctx.n_conds, ctx.n_params = n_conds, len(rest) - n_conds
+        keep = st.trainable          # the weight gradients need every conv's modulated input
         dev = style_code.device
         B = style_code.shape[0]
         L = st.L
@@ -118,6 +131,7 @@ class FrozenDecoderFunction(torch.autograd.Function):
         h, w = 4, 4 * st.ratio
         xs = e16(B, h, w, st.sc1['cin'])
         ops.modulate_const(st.const, s_sc1, xs)
+        xs_in0 = xs if keep else None
         a0 = e16(B, h, w, st.sc1['cout'])
         ops.conv_same(xs, st.sc1['w'], a0, 3, bias=st.sc1['bias'], demod=d_sc1, noise=nz[0], noise_gain=st.sc1['gain'],
                       noise_strides=(h * w, w), act=True)()
@@ -135,6 +149,7 @@ class FrozenDecoderFunction(torch.autograd.Function):
             else:
                 for pi, (py, px) in enumerate(ops.CONVT_PHASES):
                     ops.convt_s2_phase(xs, c1['w_phase'][pi], py, px, raw, demod=d_conv[2 * lvl])()
+            xs_up = xs if keep else None
             a1 = e16(B, h2, w2, cout)
             ops.upfir_act(raw, a1, nz[2 * lvl + 1], h2 * w2, c1['gain'], c1['bias'], None, None, 0, None)
             del raw
@@ -144,6 +159,7 @@ class FrozenDecoderFunction(torch.autograd.Function):
             a2 = e16(B, h2, w2, c2['cout'])
             ops.conv_same(xs2, c2['w'], a2, 3, bias=c2['bias'], demod=d_conv[2 * lvl + 1], noise=nz[2 * lvl + 2],
                           noise_gain=c2['gain'], noise_strides=(h2 * w2, w2), act=True)()
+            xs_keep = xs2 if keep else None
             del xs2
             last = lvl == L - 1
             nskip = e32(B, 3, h2, w2)
@@ -151,9 +167,10 @@ class FrozenDecoderFunction(torch.autograd.Function):
             ops.to_rgb(a2, st.rgbs[lvl]['w'], s_rgb[lvl], st.rgbs[lvl]['bias'], skip, nskip,
                        s_next=None if last else s_conv[2 * lvl + 2], xs_out=xs)
             skip = nskip
-            acts.append((a1, a2, sc, sh))
+            acts.append((a1, a2, sc, sh, xs_up, xs_keep))
             h, w = h2, w2
-        ctx.st, ctx.nz, ctx.acts, ctx.a0 = st, nz, acts, a0
+        ctx.st, ctx.nz, ctx.acts, ctx.a0, ctx.xs_in0 = st, nz, acts, a0, xs_in0
+        ctx.latent = latent if keep else None
         ctx.tables = (s_sc1, d_sc1, s_rgb1, s_conv, d_conv, s_rgb)
         ctx.lat_shape = latent.shape
         ctx.code_shape, ctx.code_dtype = style_code.shape, style_code.dtype
@@ -174,37 +191,80 @@ class FrozenDecoderFunction(torch.autograd.Function):
         dskip = d_image.contiguous().float()
         d_conds = [None] * (2 * L)
         g_next = None           # gradient w.r.t. the modulated input of the conv that consumed this level's a2 (next level's conv1)
-        nxt = None              # (layer, s, d, dd, lat index) of that conv: its style gradient needs this level's a2
+        nxt = None              # (layer, s, d, dd, lat index, name) of that conv: its style gradient needs this level's a2
+        train_p = st.trainable  # fix_decoder=False: parameter gradients as well, keyed by the decoder's parameter names
+        pg = {}
+        latent = ctx.latent
 
-        def style_grad(layer, s, d, dd, ds, li):
+        def mod_param_grads(name, ds, li):
+            """modulation EqualLinear of a ModulatedConv2d (stylegan2_ocr_arch.py:233-234, lr_mul 1): weight and bias."""
+            pg[f'{name}.modulated_conv.modulation.weight'] = ops.mod_linear_wgrad(ds, latent, wscale, lat(li))
+            pg[f'{name}.modulated_conv.modulation.bias'] = ops.table_colsum(ds)
+
+        def style_grad(layer, s, d, dd, ds, li, name):
             ops.demod_bwd(ds, s, dd, d, layer['wsq'], layer['scale2'])
+            ops.mod_linear_bwd(ds, layer['mod_w'], wscale, dlat, lat(li))
+            if train_p:
+                mod_param_grads(name, ds, li)
+
+        def act_bwd(name, layer, da, a, noise, d, mul, dd):
+            """noise + FusedLeakyReLU backward in place (da becomes dy * d * mul); with parameters also activate.bias and the
+            noise gain StyleConv.weight (stylegan2_ocr_arch.py:316-333)."""
+            if not train_p:
+                ops.style_act_bwd(da, a, noise, layer['gain'], layer['bias'], d, mul, da, dd)
+                return
+            C = a.shape[3]
+            db, dn = z32(B, C), z32(B, C)
+            ops.style_act_bwd_params(da, a, noise, layer['gain'], layer['bias'], d, mul, da, dd, db, dn)
+            pg[f'{name}.activate.bias'] = ops.table_colsum(db)
+            pg[f'{name}.weight'] = ops.table_colsum(ops.table_colsum(dn).view(C, 1))
+
+        def conv_weight_grad(name, layer, G, transposed, s, dd, d):
+            pg[f'{name}.modulated_conv.weight'] = ops.modconv_wgrad(G, transposed, layer['w_raw'], s, dd, d,
+                                                                    math.sqrt(layer['scale2'])).unsqueeze(0)
+
+        def rgb_bwd(name, layer, a, s, da, li):
+            """ToRGB (modulated 1x1 conv without demodulation + bias, stylegan2_ocr_arch.py:357-374) at the current dskip."""
+            C = a.shape[3]
+            ds = z32(B, C)
+            if train_p:
+                R = z32(B, 3, C)
+                ops.to_rgb_bwd_params(dskip, a, layer['w'], s, da, False, ds, R)
+                pg[f'{name}.modulated_conv.weight'] = ops.table_colsum(R, mul=s, scale=1.0 / math.sqrt(C)).view(1, 3, C, 1, 1)
+                bias = z32(3)
+                ops.plane_sums(dskip, bias)
+                pg[f'{name}.bias'] = bias.view(1, 3, 1, 1)
+                mod_param_grads(name, ds, li)
+            else:
+                ops.to_rgb_bwd(dskip, a, layer['w'], s, da, False, ds)
             ops.mod_linear_bwd(ds, layer['mod_w'], wscale, dlat, lat(li))
 
         for lvl in range(L - 1, -1, -1):
-            a1, a2, sc, sh = acts[lvl]
+            a1, a2, sc, sh, xs_up, xs2 = acts[lvl]
             c1, c2 = st.sconv[2 * lvl], st.sconv[2 * lvl + 1]
+            n1, n2 = f'style_convs.{2 * lvl}', f'style_convs.{2 * lvl + 1}'
             i = 1 + 2 * lvl
             _, h2, w2, C = a2.shape
             # ---- ToRGB (modulated 1x1, no demod) + skip up-sampling
             da2 = e16(B, h2, w2, C)
-            ds = z32(B, C)
-            ops.to_rgb_bwd(dskip, a2, st.rgbs[lvl]['w'], s_rgb[lvl], da2, False, ds)
-            ops.mod_linear_bwd(ds, st.rgbs[lvl]['mod_w'], wscale, dlat, lat(i + 2))
+            rgb_bwd(f'to_rgbs.{lvl}', st.rgbs[lvl], a2, s_rgb[lvl], da2, i + 2)
             dprev = torch.empty(B, 3, h2 // 2, w2 // 2, device=dev, dtype=F32)
             ops.rgb_up_adjoint(dskip, dprev)
             dskip = dprev
             # ---- the next level's conv1 read a2 * s
             if g_next is not None:
-                layer, s, d, dd, li = nxt
+                layer, s, d, dd, li, name = nxt
                 ds = z32(B, C)
                 ops.sft_mod_bwd(g_next, a2, None, None, s, da2, True, None, None, ds)
-                style_grad(layer, s, d, dd, ds, li)
+                style_grad(layer, s, d, dd, ds, li, name)
             # ---- conv2: a2 = act(conv(xs2) * d + noise + bias)
             dd2 = z32(B, C)
-            ops.style_act_bwd(da2, a2, nz[2 * lvl + 2], c2['gain'], c2['bias'], d_conv[2 * lvl + 1], 1.0, da2, dd2)
+            act_bwd(n2, c2, da2, a2, nz[2 * lvl + 2], d_conv[2 * lvl + 1], 1.0, dd2)
+            if train_p:
+                conv_weight_grad(n2, c2, ops.conv_wgrad(xs2, da2), False, s_conv[2 * lvl + 1], dd2, d_conv[2 * lvl + 1])
             g2 = e16(B, h2, w2, c2['cin'])
             ops.conv_same(da2, c2['w_dgrad'], g2, 3)()
-            del da2
+            del da2, xs2
             # ---- SFT + modulation between conv1 and conv2
             C1 = a1.shape[3]
             da1 = e16(B, h2, w2, C1)
@@ -212,38 +272,57 @@ class FrozenDecoderFunction(torch.autograd.Function):
             ds = z32(B, C1)
             ops.sft_mod_bwd(g2, a1, sc, sh, s_conv[2 * lvl + 1], da1, False, dsc, dsh, ds)
             del g2
-            style_grad(c2, s_conv[2 * lvl + 1], d_conv[2 * lvl + 1], dd2, ds, i + 1)
+            style_grad(c2, s_conv[2 * lvl + 1], d_conv[2 * lvl + 1], dd2, ds, i + 1, n2)
             d_conds[2 * lvl], d_conds[2 * lvl + 1] = dsc, dsh
             # ---- conv1 (up-sampling): a1 = act(FIR4(convT(xs) * d) + noise + bias)
             dd1 = z32(B, C1)
-            ops.style_act_bwd(da1, a1, nz[2 * lvl + 1], c1['gain'], c1['bias'], d_conv[2 * lvl], 4.0, da1, dd1)
+            act_bwd(n1, c1, da1, a1, nz[2 * lvl + 1], d_conv[2 * lvl], 4.0, dd1)
             draw = e16(B, h2 + 2, w2 + 2, C1)        # fir_pad22 fills the (h2+1) x (w2+1) region the stride-2 conv reads
+            if train_p:                              # the weight gradient contracts over whole pixel tiles: spare row / column finite
+                draw[:, h2 + 1].zero_()
+                draw[:, :, w2 + 1].zero_()
             ops.fir_pad22(da1, draw)
             del da1
+            if train_p:   # conv_transpose2d's weight gradient = the stride-2 conv's with input and output exchanged: [cin][9][cout]
+                conv_weight_grad(n1, c1, ops.conv3x3_s2_wgrad(draw, h2, w2, xs_up), True, s_conv[2 * lvl], dd1, d_conv[2 * lvl])
             g_next = e16(B, h2 // 2, w2 // 2, c1['cin'])
             ops.conv3x3_s2(draw, h2, w2, c1['w_dgrad'], g_next)()
             del draw
-            nxt = (c1, s_conv[2 * lvl], d_conv[2 * lvl], dd1, i)
+            nxt = (c1, s_conv[2 * lvl], d_conv[2 * lvl], dd1, i, n1)
         # ---- style_conv1 + to_rgb1 on the constant input
         _, h, w, C = a0.shape
         da0 = e16(B, h, w, C)
-        ds = z32(B, C)
-        ops.to_rgb_bwd(dskip, a0, st.rgb1['w'], s_rgb1, da0, False, ds)
-        ops.mod_linear_bwd(ds, st.rgb1['mod_w'], wscale, dlat, lat(1))
+        rgb_bwd('to_rgb1', st.rgb1, a0, s_rgb1, da0, 1)
         if g_next is not None:
-            layer, s, d, dd, li = nxt
+            layer, s, d, dd, li, name = nxt
             ds = z32(B, C)
             ops.sft_mod_bwd(g_next, a0, None, None, s, da0, True, None, None, ds)
-            style_grad(layer, s, d, dd, ds, li)
+            style_grad(layer, s, d, dd, ds, li, name)
         dd0 = z32(B, C)
-        ops.style_act_bwd(da0, a0, nz[0], st.sc1['gain'], st.sc1['bias'], d_sc1, 1.0, da0, dd0)
+        act_bwd('style_conv1', st.sc1, da0, a0, nz[0], d_sc1, 1.0, dd0)
+        if train_p:
+            conv_weight_grad('style_conv1', st.sc1, ops.conv_wgrad(ctx.xs_in0, da0), False, s_sc1, dd0, d_sc1)
         g0 = e16(B, h, w, st.sc1['cin'])
         ops.conv_same(da0, st.sc1['w_dgrad'], g0, 3)()
         ds = z32(B, st.sc1['cin'])
         ops.sft_mod_bwd(g0, st.const, None, None, None, None, False, None, None, ds, a_broadcast=True)
-        style_grad(st.sc1, s_sc1, d_sc1, dd0, ds, 0)
+        style_grad(st.sc1, s_sc1, d_sc1, dd0, ds, 0, 'style_conv1')
+        if train_p:       # ConstantInput (stylegan2_ocr_arch.py:287-301): x' = const * s, so d(const)[c][p] = sum_b s[b][c] g0[b][p][c]
+            cin = st.sc1['cin']
+            pg['constant_input.weight'] = ops.table_colsum(g0, mul=s_sc1).view(h, w, cin).permute(2, 0, 1).unsqueeze(0).contiguous()
         d_code = dlat.reshape(ctx.code_shape).to(ctx.code_dtype)
-        return (None, None, d_code) + tuple(d_conds)
+        d_params = tuple(pg.get(n) for n in st.param_names[:ctx.n_params]) if ctx.n_params else ()
+        return (None, None, None, d_code) + tuple(d_conds) + d_params
+
+
+FrozenDecoderFunction = DecoderFunction      # the name of the fix_decoder=True-only version
+
+
+def decoder_apply(net, st, noises, style_code, conds):
+    """stylegan_decoder([style_code], conds) through DecoderFunction; with fix_decoder=False the decoder's parameters are
+    handed to autograd as inputs (in named_parameters() order) so that their gradients land in .grad."""
+    params = [p for _, p in net.stylegan_decoder.named_parameters()] if st.trainable else []
+    return DecoderFunction.apply(st, noises, len(conds), style_code, *conds, *params)
 
 
 # ------------------------------------------------------------------------------------------ heads / losses
@@ -326,7 +405,7 @@ def gan_softplus_loss(pred, target_is_real, weight=1.0, grad_scale=1.0):
 
 # ------------------------------------------------------------------------------------------ networks
 def train_forward(net, x, return_rgb=True, randomize_noise=True, noise=None):
-    """Differentiable GFPGANv1OCR.forward (gfpganv1_ocr_arch.py:341-393) for training with fix_decoder=True: returns
+    """Differentiable GFPGANv1OCR.forward (gfpganv1_ocr_arch.py:341-393) for training: returns
     (image fp32 NCHW [B,3,H,W], out_rgbs: list of fp32 NCHW toRGB heads) with autograd history on the trainable parameters.
     noise: optional list of 2L+1 tensors [B|1,1,h,w]; else fresh N(0,1) planes when randomize_noise (the reference's training
     default, gfpgan_model.py:508) or the registered noise buffers."""
@@ -341,7 +420,7 @@ def train_forward(net, x, return_rgb=True, randomize_noise=True, noise=None):
             noise = [torch.randn(B, 1, n.shape[2], n.shape[3], device=x.device, dtype=F32) for n in st.stored_noise]
         else:
             noise = st.stored_noise
-    image = FrozenDecoderFunction.apply(st, noise, style_code, *conds)
+    image = decoder_apply(net, st, noise, style_code, conds)
     out_rgbs = [HeadToNchwFunction.apply(r) for r in res[2]] if return_rgb else []
     return image, out_rgbs
 
@@ -370,7 +449,7 @@ class GFPGANTrainer:
     perceptual + style terms when a VGG19 is supplied (perceptual.py).  The identity / facial-component terms are not part of
     this step (ArcFace / component discriminators are face-specific and off for plates).
 
-    net_g: image_restoration_b200.GFPGANv1OCR (fix_decoder=True) on the device; net_d: image_restoration_b200.disc.StyleGAN2Discriminator;
+    net_g: image_restoration_b200.GFPGANv1OCR (fix_decoder True or False) on the device; net_d: image_restoration_b200.disc.StyleGAN2Discriminator;
     net_g_ema: optional second GFPGANv1OCR that receives the EMA of the trainable parameters."""
 
     def __init__(self, net_g, net_d, net_g_ema=None, lr_g=2e-3, lr_d=2e-3, betas=(0.0, 0.99), pix_weight=0.1, pyramid_weight=1.0,

@@ -280,6 +280,34 @@ int b200ir_style_act_bwd(const void* da, const void* a, const float* noise, int6
  *   t = sum_o drgb[b][o][p] * w[o][c];   da (+)= s * t;   ds[b][c] += sum_p a * t. */
 int b200ir_to_rgb_bwd(const float* drgb, const void* a, const float* w, const float* s, void* da, int accumulate, float* ds,
                       int B, int64_t P, int C, void* stream);
+/* fix_decoder = false (the shipped training YAMLs train the StyleGAN2 decoder too): the same two kernels with the extra
+ * per-image reductions the decoder's own parameters need --
+ *   style_act_bwd_params: db[b][c] += sum_p dz (StyleConv.activate.bias), dn[b][c] += sum_p dz * noise (StyleConv.weight, the
+ *     noise gain; stylegan2_ocr_arch.py:316-333), fp32 [B][C], caller zeroes;
+ *   to_rgb_bwd_params: R[b][o][c] += sum_p drgb[b][o][p] * a[b][p][c] (fp32 [B][3][C], caller zeroes): the 1x1 weight gradient
+ *     before its modulation, dw[o][c] = sum_b s[b][c] R[b][o][c] / sqrt(C);
+ *   plane_sums: out[c] += sum_{b,p} x[b][c][p] over fp32 NCHW planes (ToRGB.bias). */
+int b200ir_style_act_bwd_params(const void* da, const void* a, const float* noise, int64_t noise_stride_b,
+                                const float* noise_gain, const float* bias, const float* oscale, float mul, void* out, float* dd,
+                                float* db, float* dn, int B, int64_t P, int C, void* stream);
+int b200ir_to_rgb_bwd_params(const float* drgb, const void* a, const float* w, const float* s, void* da, int accumulate, float* ds,
+                             float* R, int B, int64_t P, int C, void* stream);
+int b200ir_plane_sums(const float* x, float* out, int B, int Cn, int64_t P, void* stream);
+/* Folding the per-image tables over the batch into parameter gradients (fix_decoder = false):
+ *   table_colsum: out[j] = scale * sum_b in[b][j] * (mul ? mul[b][j % m] : 1), in fp32 or fp16 [B][n] (in_f16), mul fp32 [B][m]
+ *     -- activate.bias / modulation.bias / noise gain (plain sums), ToRGB weight (R weighted by s), ConstantInput (the gradient
+ *     of the modulated constant, NHWC fp16, weighted by s; stylegan2_ocr_arch.py:287-301);
+ *   mod_linear_wgrad: dw[ci][f] = wscale * sum_b ds[b][ci] * latent[b][lat_idx][f] (modulation EqualLinear weight, :233-234);
+ *   modconv_wgrad: dw[co][ci][k] = scale * G - scale^2 * W[co][ci][k] * sum_b dd[b][co] d[b][co]^2 s[b][ci]^2 in the reference
+ *     layout [cout][cin][taps]; G = b200ir_conv_wgrad's tap-major result [cout][taps][cin] on (modulated input, dy * d), or
+ *     [cin][taps][cout] when `transposed` (the up-sampling conv: its GEMM runs with input and output roles exchanged). The second
+ *     term is the weight's path through the demodulation table (:253-257). */
+int b200ir_table_colsum(const void* in, int in_f16, const float* mul, int m, float scale, float* out, int B, int64_t n,
+                        void* stream);
+int b200ir_mod_linear_wgrad(const float* ds, const float* latent, float wscale, float* dw, int L, int F, int lat_idx, int B,
+                            int cin, void* stream);
+int b200ir_modconv_wgrad(const float* G, int transposed, const float* W, const float* s, const float* dd, const float* d,
+                         float scale, float* dw, int B, int cin, int cout, int taps, void* stream);
 /* Adjoint of UpFirDnUpsample on the RGB skip (upfirdn2d(skip, FIR*4, up=2, pad=(2,1)), stylegan2_ocr_arch.py:43-69):
  * d fp32 [planes][2h][2w] -> out fp32 [planes][h][w]. */
 int b200ir_rgb_up_adjoint(const float* d, float* out, int planes, int h, int w, void* stream);

@@ -472,6 +472,51 @@ class SimLib:
             dt.copy_(((dt.float() + o) if accumulate else o).clamp(-65504, 65504))
         return 0
 
+    def b200ir_style_act_bwd_params(self, da, a, noise, noise_sb, noise_gain, bias, oscale, mul, out, dd, db, dn, B, P, Cc, stream):
+        dv, av = T(da, (B, P, Cc), torch.float16).float(), T(a, (B, P, Cc), torch.float16).float()
+        dz = dv * torch.where(av > 0, SQRT2, 0.2 * SQRT2)
+        T(db, (B, Cc), torch.float32).add_(dz.sum(1))
+        if _addr(noise):
+            T(dn, (B, Cc), torch.float32).add_((dz * TS(noise, (B, P), (noise_sb, 1), torch.float32).unsqueeze(-1)).sum(1))
+        return self.b200ir_style_act_bwd(da, a, noise, noise_sb, noise_gain, bias, oscale, mul, out, dd, B, P, Cc, stream)
+
+    def b200ir_to_rgb_bwd_params(self, drgb, a, w, s, da, accumulate, ds, R, B, P, Cc, stream):
+        d = T(drgb, (B, 3, P), torch.float32)
+        av = T(a, (B, P, Cc), torch.float16).float()
+        T(R, (B, 3, Cc), torch.float32).add_(torch.einsum('bop,bpc->boc', d, av))
+        return self.b200ir_to_rgb_bwd(drgb, a, w, s, da, accumulate, ds, B, P, Cc, stream)
+
+    def b200ir_plane_sums(self, x, out, B, Cn, P, stream):
+        self.launches += 1
+        T(out, (Cn,), torch.float32).add_(T(x, (B, Cn, P), torch.float32).sum(dim=(0, 2)))
+        return 0
+
+    def b200ir_table_colsum(self, tab, in_f16, mul, m, scale, out, B, n, stream):
+        self.launches += 1
+        t = T(tab, (B, n), torch.float16 if in_f16 else torch.float32).float()
+        if _addr(mul):
+            t = (t.view(B, n // m, m) * T(mul, (B, 1, m), torch.float32)).view(B, n)
+        T(out, (n,), torch.float32).copy_(scale * t.sum(0))
+        return 0
+
+    def b200ir_mod_linear_wgrad(self, ds, latent, wscale, dw, L, F_, lat_idx, B, cin, stream):
+        self.launches += 1
+        lat = T(latent, (B, L, F_), torch.float32)[:, lat_idx]
+        T(dw, (cin, F_), torch.float32).copy_(wscale * T(ds, (B, cin), torch.float32).t() @ lat)
+        return 0
+
+    def b200ir_modconv_wgrad(self, G, transposed, W, s, dd, d, scale, dw, B, cin, cout, taps, stream):
+        self.launches += 1
+        if transposed:
+            g = T(G, (cin, taps, cout), torch.float32).permute(2, 0, 1)
+        else:
+            g = T(G, (cout, taps, cin), torch.float32).permute(0, 2, 1)
+        dv = T(d, (B, cout), torch.float32)
+        t = T(dd, (B, cout), torch.float32) * dv * dv
+        m = scale * scale * (t.t() @ T(s, (B, cin), torch.float32).pow(2))
+        T(dw, (cout, cin, taps), torch.float32).copy_(scale * g - T(W, (cout, cin, taps), torch.float32) * m.unsqueeze(-1))
+        return 0
+
     def b200ir_rgb_up_adjoint(self, d, out, planes, h, w, stream):
         self.launches += 1
         with torch.enable_grad():

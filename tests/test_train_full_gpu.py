@@ -69,7 +69,7 @@ def test_decoder_input_gradients_strict():
     st = train.decoder_state(net)
     code_a = code.clone().requires_grad_()
     conds_a = [c.clone().requires_grad_() for c in conds]
-    img = train.FrozenDecoderFunction.apply(st, noises, code_a, *conds_a)
+    img = train.decoder_apply(net, st, noises, code_a, conds_a)
     img.backward(cot)
     torch.cuda.synchronize()
     err = (img.detach() - img_r.detach()).abs().max().item()
@@ -82,6 +82,42 @@ def test_decoder_input_gradients_strict():
         cos, rel = _stats(ca.grad.float().permute(0, 3, 1, 2), cr.grad)
         print(f'd(cond {i}): cos {cos:.6f} rel rms {rel:.3e}')
         assert cos >= 0.999 and rel <= 0.05, i
+
+
+def test_trainable_decoder_parameter_gradients():
+    """fix_decoder=False (training_config/*.yml): every decoder parameter's gradient from DecoderFunction on the kernels against
+    autograd through the oracle's stylegan_decoder (same case as tests/test_train_host_cpu.py runs on the simulator)."""
+    from image_restoration_b200 import train
+    from tests.test_train_host_cpu import _oracle_decoder_param_grads, _trainable_decoder_case
+    net, code, conds, noises, cot = _trainable_decoder_case('cpu')
+    img_r, dcode_r, pgrads = _oracle_decoder_param_grads(net, code, conds, noises, cot)       # fp32 on the host (no TF32)
+    img_r, dcode_r = img_r.cuda(), dcode_r.cuda()
+    pgrads = {k: (v.cuda() if v is not None else None) for k, v in pgrads.items()}
+    net = net.cuda()
+    code, conds, noises, cot = code.cuda(), [c.cuda() for c in conds], [n.cuda() for n in noises], cot.cuda()
+    st = train.decoder_state(net)
+    assert st.trainable
+    code_a = code.clone().requires_grad_()
+    conds_a = [c.clone().requires_grad_() for c in conds]
+    img = train.decoder_apply(net, st, noises, code_a, conds_a)
+    img.backward(cot)
+    torch.cuda.synchronize()
+    assert (img.detach() - img_r).abs().max().item() <= 2e-2 * img_r.abs().max().item()
+    cos, rel = _stats(code_a.grad.float(), dcode_r)
+    assert cos >= 0.999 and rel <= 0.05
+    worst = (1.0, 0.0)
+    for n, p in net.stylegan_decoder.named_parameters():
+        gr = pgrads[f'stylegan_decoder.{n}']
+        if gr is None:
+            assert p.grad is None and n.startswith('style_mlp'), n
+            continue
+        assert p.grad is not None and p.grad.shape == p.shape, n
+        cos, rel = _stats(p.grad, gr)
+        # scalar noise gains: a sum of dz * noise that cancels to ~1 / sqrt(n) of its terms (see the CPU test)
+        assert cos >= 0.999 and rel <= (0.15 if p.numel() == 1 else 0.05), (n, cos, rel)
+        if p.numel() > 1:
+            worst = (min(worst[0], cos), max(worst[1], rel))
+    print(f'decoder parameter gradients vs oracle autograd: worst cos {worst[0]:.5f}, worst rel rms {worst[1]:.3e}')
 
 
 def test_generator_losses_and_gradients_match_oracle_autograd():

@@ -142,7 +142,7 @@ def test_decoder_function_gradients_strict():
         st = train.decoder_state(net)
         code_a = code.clone().requires_grad_()
         conds_a = [c.clone().requires_grad_() for c in conds]
-        img = train.FrozenDecoderFunction.apply(st, noises, code_a, *conds_a)
+        img = train.decoder_apply(net, st, noises, code_a, conds_a)
         img.backward(cot)
     assert (img.detach() - img_r.detach()).abs().max().item() <= 1e-2 * img_r.abs().max().item()
     cos, rel = _cmp('d_style_code', code_a.grad.float(), code_r.grad, 0.999, 0.05)
@@ -150,6 +150,79 @@ def test_decoder_function_gradients_strict():
     for i, (ca, cr) in enumerate(zip(conds_a, conds_r)):
         cos, rel = _cmp(f'd_cond{i}', ca.grad.float().permute(0, 3, 1, 2), cr.grad, 0.999, 0.05)
         print(f'd(cond {i}): cos {cos:.6f} rel {rel:.3e}')
+
+
+def _trainable_decoder_case(dev):
+    """Inputs of the fix_decoder=False checks (also used by tests/test_train_full_gpu.py): net with a trainable decoder whose
+    noise gains / biases are non-trivial, fp16-rounded style code and conditions, noise planes and a cotangent."""
+    from image_restoration_b200 import GFPGANv1OCR
+    torch.manual_seed(4)
+    net = GFPGANv1OCR(input_width=W, input_height=H, decoder_load_path=None, fix_decoder=False, **KW)
+    with torch.no_grad():
+        for n, p in net.stylegan_decoder.named_parameters():
+            if n.endswith('.weight') and p.numel() == 1:
+                p.fill_(0.3)
+            if n.endswith('activate.bias') or n.endswith('to_rgb1.bias') or '.to_rgbs.' in n and n.endswith('.bias'):
+                p.normal_(0, 0.1)
+    net = net.to(dev)
+    L = net.log_size - 2
+    g = torch.Generator().manual_seed(9)
+    B = 3
+    sdn = net.state_dict()
+    code = (0.5 * torch.randn(B, 2 * L + 2, KW['num_style_feat'], generator=g)).half().to(dev)
+    conds = []
+    for lvl in range(L):
+        h, w = 8 * 2 ** lvl, 24 * 2 ** lvl
+        c = sdn[f'condition_scale.{lvl}.2.weight'].shape[0]
+        conds += [(1 + 0.3 * torch.randn(B, h, w, c, generator=g)).half().to(dev), (0.3 * torch.randn(B, h, w, c, generator=g)).half().to(dev)]
+    noises = [torch.randn(B, 1, *sdn[f'stylegan_decoder.noises.noise{j}'].shape[2:], generator=g).to(dev) for j in range(2 * L + 1)]
+    cot = torch.randn(B, 3, H, W, generator=g).to(dev)
+    return net, code, conds, noises, cot
+
+
+def _oracle_decoder_param_grads(net, code, conds, noises, cot):
+    from oracle.gfpgan_ocr_oracle import OcrNetConfig, stylegan_decoder
+    cfg = OcrNetConfig(input_width=W, input_height=H, **KW)
+    sd = {k: v.detach().float().clone() for k, v in net.state_dict().items()}
+    names = [f'stylegan_decoder.{n}' for n, _ in net.stylegan_decoder.named_parameters()]
+    for k in names:
+        sd[k].requires_grad_()
+    code_r = code.float().requires_grad_()
+    conds_r = [c.float().permute(0, 3, 1, 2).contiguous().requires_grad_() for c in conds]
+    img_r = stylegan_decoder(sd, cfg, code_r, conds_r, noises)
+    (img_r * cot).sum().backward()
+    return img_r.detach(), code_r.grad, {k: sd[k].grad for k in names}
+
+
+def test_trainable_decoder_parameter_gradients():
+    """fix_decoder=False (every shipped training YAML, training_config/*.yml `fix_decoder: false`): DecoderFunction also returns
+    the gradient of every decoder parameter on the path — modulated conv weights (direct term + their path through the
+    demodulation), modulation linears, noise gains, activation biases, ToRGB weights / biases, the constant input — against
+    autograd through oracle.stylegan_decoder; the unused style MLP gets none, as in the reference."""
+    from image_restoration_b200 import train
+    net, code, conds, noises, cot = _trainable_decoder_case('cpu')
+    img_r, dcode_r, pgrads = _oracle_decoder_param_grads(net, code, conds, noises, cot)
+    with cabi_sim.installed():
+        st = train.decoder_state(net)
+        assert st.trainable
+        code_a = code.clone().requires_grad_()
+        conds_a = [c.clone().requires_grad_() for c in conds]
+        img = train.decoder_apply(net, st, noises, code_a, conds_a)
+        img.backward(cot)
+    assert (img.detach() - img_r).abs().max().item() <= 1e-2 * img_r.abs().max().item()
+    _cmp('d_style_code', code_a.grad.float(), dcode_r, 0.999, 0.05)
+    seen = 0
+    for n, p in net.stylegan_decoder.named_parameters():
+        gr = pgrads[f'stylegan_decoder.{n}']
+        if gr is None:
+            assert p.grad is None and n.startswith('style_mlp'), n
+            continue
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == p.dtype, n
+        # the noise gains are scalars: sum over every element of dz * noise with noise ~ N(0, 1) independent of dz, a sum that
+        # cancels to ~1 / sqrt(n) of its terms, so the ~1e-3 of flipped leaky-ReLU branches shows up amplified
+        cos, rel = _cmp(n, p.grad, gr, 0.999, 0.15 if p.numel() == 1 else 0.05)
+        seen += 1
+    assert seen == 2 + 5 * (2 * (net.log_size - 2) + 1) + 4 * (net.log_size - 1) - 1, seen
 
 
 def test_trainer_steps_match_a_torch_reference_loop():
@@ -221,6 +294,35 @@ def test_trainer_steps_match_a_torch_reference_loop():
     dec = 0.5 ** (32 / (10 * 1000))
     k0 = g_names[0]
     assert not torch.equal(dict(ema.named_parameters())[k0], dict(net.named_parameters())[k0])
+
+
+def test_trainer_updates_a_trainable_decoder():
+    """GFPGANTrainer with fix_decoder=False (training_config/*.yml): the decoder's parameters are part of optimizer_g, their
+    packed copies are rebuilt after every step (FlatAdam bumps the parameter versions), the unused style MLP stays put."""
+    from image_restoration_b200 import GFPGANv1OCR, train
+    from image_restoration_b200.disc import StyleGAN2Discriminator
+    torch.manual_seed(6)
+    net = GFPGANv1OCR(input_width=W, input_height=H, decoder_load_path=None, fix_decoder=False, **KW)
+    netd = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1)
+    lq, gt = _data(2, seed=8)
+    before = {k: v.detach().clone() for k, v in net.named_parameters()}
+    with cabi_sim.installed():
+        tr = train.GFPGANTrainer(net, netd)
+        assert len(tr.g_params) == len(list(net.parameters()))
+        losses = []
+        for it in range(2):
+            tr.feed_data(lq, gt)
+            st0 = train.decoder_state(net)
+            log = tr.optimize_parameters(it + 1)
+            assert train.decoder_state(net) is not st0                 # repacked from the updated weights
+            losses.append(float(log['l_g_pix']))
+    assert all(math.isfinite(v) for v in losses)
+    for k, p in net.named_parameters():
+        moved = (p.detach() - before[k]).abs().max().item()
+        if 'style_mlp' in k:
+            assert moved == 0.0, k
+        else:
+            assert 0.0 < moved <= 2.5 * 2 * 2e-3, (k, moved)           # two Adam steps of at most ~lr each
 
 
 def _ddp_worker(rank, world, port, q):

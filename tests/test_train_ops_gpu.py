@@ -108,6 +108,67 @@ def test_to_rgb_bwd_and_skip_adjoint(B, h, w, C):
     close('rgb_up_adjoint', gpu['out'], cpu['out'], rel=1e-5)
 
 
+@pytest.mark.parametrize('B,h,w,C', [(3, 16, 48, 64), (2, 8, 24, 512), (2, 5, 7, 32)])
+def test_decoder_parameter_reductions(B, h, w, C):
+    """fix_decoder=False: the *_params variants of the pointwise adjoints (activate.bias, noise gain, ToRGB weight partials) and
+    plane_sums, against the simulator; their primary outputs must equal the plain variants'."""
+    from image_restoration_b200 import ops
+    g = torch.Generator().manual_seed(C + 2)
+    a = rn(B, h, w, C, g=g)
+    a = torch.where(a.abs() < 0.02, torch.full_like(a, 0.05), a).half()
+    t = dict(da=rn(B, h, w, C, g=g).half(), a=a, nz=rn(B, 1, h, w, g=g), gain=torch.tensor([0.3]), bias=0.1 * rn(C, g=g),
+             osc=1 + 0.3 * rn(B, C, g=g), out=torch.zeros(B, h, w, C).half(), dd=torch.zeros(B, C), db=torch.zeros(B, C),
+             dn=torch.zeros(B, C), out0=torch.zeros(B, h, w, C).half(), dd0=torch.zeros(B, C))
+
+    def run(d):
+        ops.style_act_bwd_params(d['da'], d['a'], d['nz'], d['gain'], d['bias'], d['osc'], 4.0, d['out'], d['dd'], d['db'], d['dn'])
+        ops.style_act_bwd(d['da'], d['a'], d['nz'], d['gain'], d['bias'], d['osc'], 4.0, d['out0'], d['dd0'])
+    gpu, cpu = both(run, t)
+    assert torch.equal(gpu['out'], gpu['out0'])
+    close('dd', gpu['dd'], gpu['dd0'].cpu(), rel=1e-5)
+    for k in ('out', 'dd', 'db', 'dn'):
+        close(k, gpu[k], cpu[k], rel=3e-3)
+    t = dict(drgb=rn(B, 3, h, w, g=g), a=rn(B, h, w, C, g=g).half(), w=rn(3, C, g=g) / math.sqrt(C), s=1 + 0.5 * rn(B, C, g=g),
+             da=torch.zeros(B, h, w, C).half(), ds=torch.zeros(B, C), R=torch.zeros(B, 3, C), bias=torch.zeros(3))
+
+    def run2(d):
+        ops.to_rgb_bwd_params(d['drgb'], d['a'], d['w'], d['s'], d['da'], False, d['ds'], d['R'])
+        ops.plane_sums(d['drgb'], d['bias'])
+    gpu, cpu = both(run2, t)
+    for k in ('da', 'ds', 'R', 'bias'):
+        close(k, gpu[k], cpu[k], rel=3e-3)
+
+
+def test_decoder_parameter_folds():
+    """table_colsum (fp32 / fp16 input, with and without the per-image weights), mod_linear_wgrad, modconv_wgrad (both
+    GEMM-result layouts) against the simulator."""
+    from image_restoration_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, cin, cout, L, Fd = 5, 96, 40, 6, 256
+    t = dict(tab=rn(B, 3, cin, g=g), s=1 + 0.5 * rn(B, cin, g=g), g0=rn(B, 4, 12, cin, g=g).half(), ds=rn(B, cin, g=g),
+             lat=rn(B, L, Fd, g=g), G=rn(cout, 9, cin, g=g), Gt=rn(cin, 9, cout, g=g), W=rn(cout, cin, 3, 3, g=g),
+             dd=rn(B, cout, g=g), d=torch.rand(B, cout, generator=g) + 0.5)
+    res = {}
+
+    def run(d):
+        res['plain'] = ops.table_colsum(d['ds'])
+        res['rgb'] = ops.table_colsum(d['tab'], mul=d['s'], scale=0.25)
+        res['const'] = ops.table_colsum(d['g0'], mul=d['s'])
+        res['total'] = ops.table_colsum(res['plain'].view(cin, 1))
+        res['mod_w'] = ops.mod_linear_wgrad(d['ds'], d['lat'], 1.0 / math.sqrt(Fd), 4)
+        res['dw'] = ops.modconv_wgrad(d['G'], False, d['W'], d['s'], d['dd'], d['d'], 1.0 / math.sqrt(cin * 9))
+        res['dwt'] = ops.modconv_wgrad(d['Gt'], True, d['W'], d['s'], d['dd'], d['d'], 1.0 / math.sqrt(cin * 9))
+    gpu = {k: v.cuda() for k, v in t.items()}
+    run(gpu)
+    torch.cuda.synchronize()
+    got = dict(res)
+    with cabi_sim.installed():
+        run(t)
+    assert got['const'].shape == (4 * 12 * cin,) and got['dw'].shape == (cout, cin, 3, 3)
+    for k in got:
+        close(k, got[k], res[k], rel=1e-4)
+
+
 def test_style_tables_backward():
     from image_restoration_b200 import ops
     g = torch.Generator().manual_seed(9)

@@ -1,5 +1,6 @@
 """Training loop on the B200 kernels: the `train_pipeline` of basicsr/train.py for the plate configs
-(training_config/train_gfpgan_v4_*_license_*.yml with fix_decoder: true), one process per GPU.
+(training_config/train_gfpgan_v4_*_license_*.yml; --fix-decoder freezes the StyleGAN2 decoder, the YAMLs train it), one
+process per GPU.
 
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 tools/train_plates.py --iters 200 --batch 256 --out /tmp/exp
 
@@ -53,6 +54,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='crops per GPU')
     ap.add_argument('--val-freq', type=int, default=25)
     ap.add_argument('--out', default='')
+    ap.add_argument('--fix-decoder', action='store_true', help='freeze the StyleGAN2 decoder (the training YAMLs train it)')
     args = ap.parse_args()
     world, rank, local = int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
@@ -60,8 +62,9 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(0)                                   # identical replicas
-    net_g = GFPGANv1OCR(**NET_KW).to(dev).train()
-    net_g_ema = GFPGANv1OCR(**NET_KW).to(dev).eval()
+    kw = dict(NET_KW, fix_decoder=args.fix_decoder)
+    net_g = GFPGANv1OCR(**kw).to(dev).train()
+    net_g_ema = GFPGANv1OCR(**kw).to(dev).eval()
     net_g_ema.load_state_dict(net_g.state_dict())
     net_d = StyleGAN2Discriminator(input_width=W, input_height=H, channel_multiplier=1).to(dev)
     trainer = train.GFPGANTrainer(net_g, net_d, net_g_ema=net_g_ema)
