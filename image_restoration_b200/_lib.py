@@ -116,6 +116,7 @@ SIGNATURES = {
     'b200ir_style_act_bwd_params': [_P, _P, _P, _L, _P, _P, _P, _F, _P, _P, _P, _P, _I, _L, _I, _P],
     'b200ir_to_rgb_bwd_params': [_P, _P, _P, _P, _P, _I, _P, _P, _I, _L, _I, _P],
     'b200ir_plane_sums': [_P, _P, _I, _I, _L, _P],
+    'b200ir_wgrad_unfold': [_P, _P, _I, _I, _I, _P],
     'b200ir_table_colsum': [_P, _I, _P, _I, _F, _P, _I, _L, _P],
     'b200ir_mod_linear_wgrad': [_P, _P, _F, _P, _I, _I, _I, _I, _I, _P],
     'b200ir_modconv_wgrad': [_P, _I, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],

@@ -362,6 +362,34 @@ __global__ void __launch_bounds__(kTrThreads) modconv_wgrad_kernel(const float* 
   }
 }
 
+// Low-channel weight gradients run on pixel-folded views (ops.conv_wgrad): f horizontally adjacent pixels of x and dy are read as
+// f * C channels of one pixel, so a 32 -> 32 layer becomes a 128 -> 128 GEMM over a quarter of the pixels (the tensor pipe
+// charges a full 128 x 64 tile whatever the channel count).  G[(s_o, co)][kh][kw'][(s_i, ci)] then holds every pair of
+// sub-pixels; the original tap kw collects the pairs with f * (kw' - 1) + s_i - s_o = kw - 1.
+__global__ void __launch_bounds__(kTrThreads) wgrad_unfold_kernel(const float* __restrict__ G, float* __restrict__ dw, int f,
+                                                                  int cin, int cout) {
+  const int n = cout * 9 * cin;
+  const int idx = blockIdx.x * kTrThreads + threadIdx.x;
+  if (idx >= n) return;
+  const int ci = idx % cin, tap = (idx / cin) % 9, co = idx / (9 * cin);
+  const int kh = tap / 3, d = tap % 3 - 1;
+  const long long ldg = 9LL * f * cin;      // elements per folded output channel
+  float acc = 0.f;
+  for (int so = 0; so < f; ++so) {
+    const int t = so + d;
+    int dp, si;
+    if (t >= 0 && t < f) {
+      dp = 0, si = t;
+    } else if (t == f) {
+      dp = 1, si = 0;
+    } else {
+      dp = -1, si = f - 1;
+    }
+    acc += G[(long long)(so * cout + co) * ldg + (long long)(kh * 3 + dp + 1) * f * cin + si * cin + ci];
+  }
+  dw[idx] = acc;
+}
+
 // adjoint of upfirdn2d(skip, FIR * 4, up = 2, pad = (2, 1)) on fp32 planes: per axis
 //   out[k] = .25 d[2k-1] + .75 d[2k] + .75 d[2k+1] + .25 d[2k+2]   (d = 0 outside)
 __global__ void __launch_bounds__(kTrThreads) rgb_up_adjoint_kernel(const float* __restrict__ d, float* __restrict__ out,
@@ -895,6 +923,13 @@ extern "C" int b200ir_modconv_wgrad(const float* G, int transposed, const float*
                  "modconv_wgrad: bad arguments");
   modconv_wgrad_kernel<<<cout, kTrThreads, B * sizeof(float), STREAM>>>(G, transposed, W, s, dd, d, scale, dw, B, cin, cout, taps);
   return check_launch("modconv_wgrad");
+}
+
+extern "C" int b200ir_wgrad_unfold(const float* G, float* dw, int f, int cin, int cout, void* stream) {
+  B200IR_REQUIRE(G && dw && f >= 1 && f <= 8 && cin > 0 && cout > 0, "wgrad_unfold: bad arguments");
+  const int n = cout * 9 * cin;
+  wgrad_unfold_kernel<<<(n + kTrThreads - 1) / kTrThreads, kTrThreads, 0, STREAM>>>(G, dw, f, cin, cout);
+  return check_launch("wgrad_unfold");
 }
 
 extern "C" int b200ir_rgb_up_adjoint(const float* d, float* out, int planes, int h, int w, void* stream) {

@@ -7,6 +7,7 @@ upfirdn2d / fused_leaky_relu — see include/b200ir.h for file:line).
 import ctypes as C
 import functools
 import math
+import os
 
 import torch
 
@@ -564,8 +565,32 @@ def conv_wgrad(x, dy, dw=None):
     assert tuple(dy.shape[:3]) == (b, h, w) and x.dtype == torch.float16 and dy.dtype == torch.float16
     if dw is None:
         dw = torch.empty(cout, 9, cin, device=x.device, dtype=torch.float32)
+    f = wgrad_fold(cin, cout, w)
+    if f > 1 and x.is_contiguous() and dy.is_contiguous():
+        # low-channel layers: f adjacent pixels read as f * C channels (a free view of NHWC), GEMM on the folded shapes, then
+        # the tap blocks are collected (b200ir_wgrad_unfold)
+        G = torch.empty(f * cout, 9, f * cin, device=x.device, dtype=torch.float32)
+        check(_lib.lib().b200ir_conv_wgrad(_ptr(x), _ptr(dy), _ptr(G), b, h, w // f, f * cin, f * cout, _stream()), 'conv_wgrad')
+        check(_lib.lib().b200ir_wgrad_unfold(_ptr(G), _ptr(dw), f, cin, cout, _stream()), 'wgrad_unfold')
+        return dw
     check(_lib.lib().b200ir_conv_wgrad(_ptr(x), _ptr(dy), _ptr(dw), b, h, w, cin, cout, _stream()), 'conv_wgrad')
     return dw
+
+
+_WGRAD_FOLD = int(os.environ.get('B200IR_WGRAD_FOLD', '1'))        # 0: never fold (A/B switch of tools/time_wgrad_lowc.py)
+
+
+def wgrad_fold(cin, cout, w):
+    """Pixel-fold factor of conv_wgrad.  The weight-gradient GEMM pays for a 128 (cout) x 64 (cin) tile whatever the channel
+    counts, so 32 -> 32 runs as 128 -> 128 over a quarter of the pixels (1 / f of the folded result is kept): measured at
+    B = 256, 128x384: 32->32 1882 -> 698 us, 32->64 1994 -> 1036 us, 64->32 2075 -> 1158 us, 64->64 1893 -> 1321 us."""
+    if _WGRAD_FOLD == 0:
+        return 1
+    if cin == 32 and cout == 32 and w % 4 == 0:
+        return 4
+    if (cin, cout) in ((32, 64), (64, 32), (64, 64)) and w % 2 == 0:
+        return 2
+    return 1
 
 
 def conv_dgrad_weight(weight, cin):

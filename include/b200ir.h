@@ -302,6 +302,10 @@ int b200ir_plane_sums(const float* x, float* out, int B, int Cn, int64_t P, void
  *     layout [cout][cin][taps]; G = b200ir_conv_wgrad's tap-major result [cout][taps][cin] on (modulated input, dy * d), or
  *     [cin][taps][cout] when `transposed` (the up-sampling conv: its GEMM runs with input and output roles exchanged). The second
  *     term is the weight's path through the demodulation table (:253-257). */
+/* Weight gradient of a low-channel 3x3 conv computed on pixel-folded views: b200ir_conv_wgrad is called with x, dy read as
+ * [B][H][W/f][f*C] (f horizontally adjacent pixels = f*C channels) and returns G fp32 [f*cout][9][f*cin]; this folds G back to
+ * dw fp32 [cout][9][cin]: tap (kh, kw) = sum of the blocks (s_o, s_i, kw') with f * (kw' - 1) + s_i - s_o = kw - 1. */
+int b200ir_wgrad_unfold(const float* G, float* dw, int f, int cin, int cout, void* stream);
 int b200ir_table_colsum(const void* in, int in_f16, const float* mul, int m, float scale, float* out, int B, int64_t n,
                         void* stream);
 int b200ir_mod_linear_wgrad(const float* ds, const float* latent, float wscale, float* dw, int L, int F, int lat_idx, int B,

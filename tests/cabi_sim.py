@@ -387,6 +387,18 @@ class SimLib:
         v = View(_addr(x), cin, W, H, B, cin, W * cin, H * W * cin)
         return self.b200ir_conv_wgrad_view(v, dy, dw, B, H, W, cout, 0x1FF, stream)
 
+    def b200ir_wgrad_unfold(self, G, dw, f, cin, cout, stream):
+        self.launches += 1
+        g = T(G, (f, cout, 3, 3, f, cin), torch.float32)            # [s_o, co, kh, kw', s_i, ci]
+        out = T(dw, (cout, 3, 3, cin), torch.float32)
+        out.zero_()
+        for d in (-1, 0, 1):
+            for so in range(f):
+                t = so + d
+                dp, si = (0, t) if 0 <= t < f else ((1, 0) if t == f else (-1, f - 1))
+                out[:, :, d + 1] += g[so, :, :, dp + 1, si]
+        return 0
+
     def b200ir_first_conv_wgrad(self, x, dz, dw, B, H, W, cout, stream):
         self.launches += 1
         T(dw, (cout, 3), torch.float32).copy_(torch.einsum('bhwc,bkhw->ck', T(dz, (B, H, W, cout), torch.float16).float(),

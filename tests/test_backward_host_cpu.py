@@ -3,6 +3,8 @@
 weight gradient, checked against torch's own conv gradients on the CPU."""
 import math
 
+import pytest
+
 import torch
 import torch.nn.functional as F
 
@@ -104,3 +106,23 @@ def test_training_functions_have_no_cpu_path():
         backward.MinibatchStddevFunction.apply(x, 1)
     with pytest.raises(RuntimeError):
         backward.AddFunction.apply(x, x)
+
+
+@pytest.mark.parametrize('cin,cout,w,f', [(32, 32, 24, 4), (32, 64, 10, 2), (64, 64, 12, 2)])
+def test_wgrad_pixel_fold_algebra(cin, cout, w, f, monkeypatch):
+    """ops.conv_wgrad on pixel-folded views (low-channel layers) + b200ir_wgrad_unfold == the direct weight gradient, through the
+    C-ABI simulator: checks the view arithmetic and the tap-block bookkeeping above the ABI."""
+    from image_restoration_b200 import ops
+    from tests import cabi_sim
+    g = torch.Generator().manual_seed(cin + cout + w)
+    B, h = 2, 5
+    x = torch.randn(B, h, w, cin, generator=g).half()
+    dy = torch.randn(B, h, w, cout, generator=g).half()
+    with cabi_sim.installed():
+        monkeypatch.setattr(ops, '_WGRAD_FOLD', 1)
+        assert ops.wgrad_fold(cin, cout, w) == f
+        folded = ops.conv_wgrad(x, dy)
+        monkeypatch.setattr(ops, '_WGRAD_FOLD', 0)
+        direct = ops.conv_wgrad(x, dy)
+    assert folded.shape == direct.shape == (cout, 9, cin)
+    assert (folded - direct).abs().max().item() <= 1e-4 * direct.abs().max().item()

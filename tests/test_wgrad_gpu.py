@@ -64,3 +64,21 @@ def test_wgrad_3x3_stride2(B, H, W, cin, cout):
     err, scale = (got - ref).abs().max().item(), ref.abs().max().item()
     print(f'wgrad 3x3 s2 B{B} {H}x{W} {cin}->{cout}: max err {err:.3e} of {scale:.3e}')
     assert err <= 1e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize('fold', [0, 1])
+@pytest.mark.parametrize('B,H,W,cin,cout', [(2, 16, 48, 32, 32), (1, 9, 20, 32, 64), (2, 8, 24, 64, 64), (1, 16, 40, 64, 32),
+                                              (1, 8, 18, 32, 32)])
+def test_wgrad_pixel_fold_modes(B, H, W, cin, cout, fold, monkeypatch):
+    """Low-channel layers on pixel-folded views (ops.wgrad_fold + b200ir_wgrad_unfold): every fold mode gives the same weight
+    gradient as torch (mode 0 = no folding; W = 18 is not a multiple of 4, so 32 -> 32 stays unfolded there)."""
+    from image_restoration_b200 import ops
+    monkeypatch.setattr(ops, '_WGRAD_FOLD', fold)
+    torch.manual_seed(W + cin)
+    x = torch.randn(B, cin, H, W, device='cuda').half()
+    dy = torch.randn(B, cout, H, W, device='cuda').half()
+    ref = torch.nn.grad.conv2d_weight(x.float(), (cout, cin, 3, 3), dy.float(), padding=1).permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    got = ops.conv_wgrad(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous())
+    torch.cuda.synchronize()
+    err, scale = (got - ref).abs().max().item(), ref.abs().max().item()
+    assert err <= 1e-3 * scale, (fold, ops.wgrad_fold(cin, cout, W), err, scale)
