@@ -54,7 +54,7 @@ class DegradeCrop(C.Structure):
     """b200ir_degrade_crop (include/b200ir.h); numpy view: DEGRADE_CROP_DTYPE."""
     _fields_ = [('blur_mode', C.c_int32), ('ksize', C.c_int32), ('blur_f64', C.c_int32), ('lr_w', C.c_int32), ('lr_h', C.c_int32),
                 ('jpeg_quality', C.c_int32), ('gray', C.c_int32), ('jitter', C.c_float * 3), ('bilateral_sigma', C.c_float), ('cj_count', C.c_int32),
-                ('cj_order', C.c_int32 * 4), ('cj_factor', C.c_float * 4), ('cj_one_minus', C.c_float * 4)]
+                ('cj_order', C.c_int32 * 4), ('cj_factor', C.c_float * 4), ('cj_one_minus', C.c_float * 4), ('mask_mode', C.c_int32)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -137,6 +137,7 @@ SIGNATURES = {
     'b200ir_softplus_loss': [_P, _I, _I, _F, _F, _F, _P, _P, _P],
     'b200ir_degrade': [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     'b200ir_degrade_full': [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_degrade_full_masked': [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64, 'b200ir_conv_plan_destroy': None}
 

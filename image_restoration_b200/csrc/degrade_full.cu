@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(kDfThreads, 1)
 degrade_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ gt_f32, const double* __restrict__ taps_all,
                     int kmax,
                     const b200ir_degrade_crop* __restrict__ crops, const float* __restrict__ noise, int lr_wmax,
-                    int lr_hmax, float* __restrict__ out, float* __restrict__ lr_out, int H, int W, int bgr2rgb) {
+                    int lr_hmax, float* __restrict__ out, float* __restrict__ lr_out, int H, int W, int bgr2rgb,
+                    const uint8_t* __restrict__ mask) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_nnz;
   const int b = blockIdx.x;
@@ -592,6 +593,7 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ gt
       cj_mean = s_mean;
     }
   }
+  const uint8_t* mask_b = (mask != nullptr && cp.mask_mode != 0) ? mask + (size_t)b * H * W : nullptr;
   for (int it = tid; it < H * W; it += kDfThreads) {
     float v[3];
     pixel(it, v);
@@ -602,10 +604,17 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ gt
       v[1] = g;
       v[0] = bl;
     }
+    // random_mask (ffhq_degradation_dataset.py:153-187, :299-303) on the clamped image: the regular / half kinds set the masked
+    // pixels to 1.0; the irregular kind first takes np.array(img * 255.0, uint8) of the WHOLE image (truncation) and draws 255
+    const bool masked = mask_b != nullptr && mask_b[it] != 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float t = fminf(fmaxf(v[c], 0.f), 1.f);
-      t = fminf(fmaxf(rintf(__fmul_rn(t, 255.f)), 0.f), 255.f);
+      if (cp.mask_mode == 2)
+        t = truncf(__fmul_rn(t, 255.f));
+      else
+        t = fminf(fmaxf(rintf(__fmul_rn(t, 255.f)), 0.f), 255.f);
+      if (masked) t = 255.f;
       t = __fdiv_rn(t, 255.f);
       t = __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);
       const int co = bgr2rgb ? 2 - c : c;
@@ -625,10 +634,23 @@ __global__ void gt_to_u8_kernel(const float* __restrict__ f, uint8_t* __restrict
 
 using namespace b200ir;
 
+extern "C" int b200ir_degrade_full_masked(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
+                                          const b200ir_degrade_crop* crops, const float* noise, int lr_wmax, int lr_hmax,
+                                          const uint8_t* mask, float* out, float* lr_out, int B, int H, int W, int bgr2rgb,
+                                          void* stream);
+
 extern "C" int b200ir_degrade_full(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
                                    const b200ir_degrade_crop* crops,
                                    const float* noise, int lr_wmax, int lr_hmax, float* out, float* lr_out, int B, int H,
                                    int W, int bgr2rgb, void* stream) {
+  return b200ir_degrade_full_masked(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, nullptr, out, lr_out, B, H, W,
+                                    bgr2rgb, stream);
+}
+
+extern "C" int b200ir_degrade_full_masked(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
+                                          const b200ir_degrade_crop* crops, const float* noise, int lr_wmax, int lr_hmax,
+                                          const uint8_t* mask, float* out, float* lr_out, int B, int H, int W, int bgr2rgb,
+                                          void* stream) {
   B200IR_REQUIRE(gt && taps && crops && out, "degrade_full: null pointer");
   B200IR_REQUIRE(B > 0 && H > 1 && W > 1 && kmax > 0 && (kmax & 1) && lr_wmax > 0 && lr_hmax > 0,
                  "degrade_full: bad sizes (kmax must be odd)");
@@ -652,11 +674,11 @@ extern "C" int b200ir_degrade_full(uint8_t* gt, const float* gt_f32, const doubl
   if (stage) {
     cudaFuncSetAttribute(degrade_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
     degrade_full_kernel<true><<<B, kDfThreads, staged, st>>>(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
-                                                            H, W, bgr2rgb);
+                                                            H, W, bgr2rgb, mask);
   } else {
     cudaFuncSetAttribute(degrade_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
     degrade_full_kernel<false><<<B, kDfThreads, base, st>>>(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
-                                                           H, W, bgr2rgb);
+                                                           H, W, bgr2rgb, mask);
   }
   return check_launch("degrade_full");
 }

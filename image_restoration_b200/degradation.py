@@ -415,6 +415,67 @@ def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=
     return 2, k, desc
 
 
+def random_mask_draw(H, W, py_random=None, np_random=np.random):
+    """The draws of FFHQDegradationDataset.random_mask (ffhq_degradation_dataset.py:95-187) for an H x W image, with the same
+    calls in the same order.  Returns (mask_mode, mask uint8 [H, W]): mode 1 = regular rectangles / half masks (masked pixels
+    become 1.0), mode 2 = irregular mask (lines, circles, ellipses rasterised by the reference's own cv2 calls; the image is
+    also truncated to the 8-bit grid, see include/b200ir.h).  The reference indexes its shapes with size[0] = H for x and
+    size[1] = W for y (:121-141); that is kept."""
+    import random as _random
+    rnd = py_random or _random
+    mask = np.zeros((H, W), dtype=np.uint8)
+    if rnd.random() > 0.3:
+        if rnd.random() > 0.5:                                   # random_regular_mask (:95-110)
+            n_mask = rnd.randint(1, 5)
+            limx, limy = H - H / (n_mask + 1), W - W / (n_mask + 1)
+            for _ in range(n_mask):
+                x, y = rnd.randint(0, int(limx)), rnd.randint(0, int(limy))
+                range_x = x + rnd.randint(int(H / (n_mask + 7)), int(H - x))
+                range_y = y + rnd.randint(int(W / (n_mask + 7)), int(W - y))
+                mask[int(x):int(range_x), int(y):int(range_y)] = 1
+            return 1, mask
+        if H < 64 or W < 64:                                     # random_irregular_mask (:112-151)
+            raise Exception('Width and Height of mask must be at least 64!')
+        import cv2
+        max_width = 20
+        for _ in range(rnd.randint(16, 64)):
+            model = rnd.random()
+            if model < 0.6:
+                x1, x2 = rnd.randint(1, H), rnd.randint(1, H)
+                y1, y2 = rnd.randint(1, W), rnd.randint(1, W)
+                cv2.line(mask, (x1, y1), (x2, y2), 255, rnd.randint(4, max_width))
+            elif 0.6 < model < 0.8:
+                x1, y1 = rnd.randint(1, H), rnd.randint(1, W)
+                cv2.circle(mask, (x1, y1), rnd.randint(4, max_width), 255, -1)
+            elif model > 0.8:
+                x1, y1 = rnd.randint(1, H), rnd.randint(1, W)
+                s1, s2 = rnd.randint(1, H), rnd.randint(1, W)
+                a1, a2, a3 = rnd.randint(3, 180), rnd.randint(3, 180), rnd.randint(3, 180)
+                cv2.ellipse(mask, (x1, y1), (s1, s2), a1, a2, a3, 255, rnd.randint(4, max_width))
+        return 2, (mask == 255).astype(np.uint8)
+    half_h, half_w = int(H / 2), int(W / 2)                      # half masks (:163-186)
+    if rnd.random() > 0.5:
+        start = np_random.uniform(0.0, 7 / 8)
+        end = np_random.uniform(start, 1.0)
+        if end - start > 0.5:
+            end -= 0.5
+        if rnd.random() > 0.5:
+            mask[int(start * half_h):int(end * half_h), :] = 1
+        else:
+            mask[:, int(start * half_w):int(end * half_w)] = 1
+    else:
+        tmp = rnd.random()
+        if tmp > 0.75:
+            mask[:half_h] = 1
+        elif tmp > 0.50:
+            mask[half_h:] = 1
+        elif tmp > 0.25:
+            mask[:, :half_w] = 1
+        else:
+            mask[:, half_w:] = 1
+    return 1, mask
+
+
 def sample_params(B, H, W, opt, py_random=None, np_random=np.random, torch_generator=None):
     """Per-crop random draws of __getitem__ for the stages b200ir_degrade_full runs, in the reference's order: blur
     kind + kernel, scale, noise sigma (+ the gray-noise coin) + noise field, JPEG quality, colour-jitter coin / shifts,
@@ -422,10 +483,9 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random, torch_gener
     from torch's global generator, as the reference does).  opt carries the dataset options of the training YAML (kernel_list, kernel_prob, blur_kernel_size,
     blur_sigma, downsample_range, noise_range, jpeg_range, color_jitter_prob, color_jitter_shift, gray_prob).
     Returns a dict of host arrays ready for degrade_full_batch."""
-    if opt.get('random_mask'):
-        raise NotImplementedError('random_mask (ffhq_degradation_dataset.py:153-186) has no B200 implementation')
     ks = opt['blur_kernel_size']
     modes, kernels, sizes, noises, quality, jitter, gray, desc, bsigma, cj = [], [], [], [], [], [], [], [], [], []
+    mask_modes, masks = [], []
     for _ in range(B):
         m, k, d = random_mixed_kernel(opt['kernel_list'], opt['kernel_prob'], ks, opt['blur_sigma'], opt['blur_sigma'],
                                       (-math.pi, math.pi), pad_kernel=True, pad_kernel_size=ks, py_random=py_random,
@@ -462,6 +522,10 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random, torch_gener
                     f = torch.tensor(1.0).uniform_(ranges[fn_id][0], ranges[fn_id][1], generator=torch_generator).item()
                     steps.append((fn_id, f))
         cj.append(steps)
+        if opt.get('random_mask'):              # :299-303, after color_jitter_pt
+            mm, mk = random_mask_draw(H, W, py_random=py_random, np_random=np_random)
+            mask_modes.append(mm)
+            masks.append(mk)
     lr_wmax, lr_hmax = max(s[0] for s in sizes), max(s[1] for s in sizes)
     nz = None
     if any(n is not None for n in noises):
@@ -470,11 +534,12 @@ def sample_params(B, H, W, opt, py_random=None, np_random=np.random, torch_gener
             if n is not None:
                 nz[b, :n.shape[0], :n.shape[1]] = n
     return dict(modes=modes, kernels=kernels, sizes=sizes, noise=nz, quality=quality, jitter=jitter, gray=gray,
-                bilateral_sigma=bsigma, color_jitter_pt=cj, desc=desc)
+                bilateral_sigma=bsigma, color_jitter_pt=cj, desc=desc,
+                mask_modes=mask_modes or None, masks=np.stack(masks) if masks else None)
 
 
 def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=None, gray=None, bilateral_sigma=None,
-                      color_jitter_pt=None, dev='cuda', **_unused):
+                      color_jitter_pt=None, dev='cuda', mask_modes=None, masks=None, **_unused):
     """Device-side parameter block of a batch for b200ir_degrade_full (taps, per-crop records, noise): build once per
     batch of draws, reuse across launches.  Arguments as returned by sample_params."""
     B = len(modes)
@@ -498,16 +563,26 @@ def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=No
         c.cj_count = len(steps)
         for i, (op, f) in enumerate(steps):     # torchvision's _blend: ratio and (1.0 - ratio) become float32 scalars
             c.cj_order[i], c.cj_factor[i], c.cj_one_minus[i] = int(op), float(f), float(1.0 - float(f))
+        c.mask_mode = int(mask_modes[b]) if mask_modes is not None else 0
+        if c.mask_mode not in (0, 1, 2):
+            raise ValueError('mask_mode must be 0, 1 or 2')
     lr_wmax, lr_hmax = max(s[0] for s in sizes), max(s[1] for s in sizes)
     if noise is not None:
         noise = torch.as_tensor(noise, dtype=torch.float32).to(dev).contiguous()
         assert tuple(noise.shape) == (B, lr_hmax, lr_wmax, 3)
+    mask_t = None
+    if mask_modes is not None and any(int(m) for m in mask_modes):
+        if masks is None:
+            raise ValueError('mask_modes given without masks')
+        mask_t = torch.as_tensor(np.asarray(masks), dtype=torch.uint8).to(dev).contiguous()
+        assert mask_t.dim() == 3 and mask_t.shape[0] == B, 'masks: uint8 [B, H, W]'
     return dict(crops=torch.frombuffer(bytearray(bytes(crops)), dtype=torch.uint8).to(dev),
-                taps=torch.from_numpy(taps).to(dev), kmax=kmax, noise=noise, lr_wmax=lr_wmax, lr_hmax=lr_hmax, n=B)
+                taps=torch.from_numpy(taps).to(dev), kmax=kmax, noise=noise, lr_wmax=lr_wmax, lr_hmax=lr_hmax, n=B, mask=mask_t)
 
 
 def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, quality=None, jitter=None, gray=None,
-                       bilateral_sigma=None, color_jitter_pt=None, bgr2rgb=True, return_lr=False, packed=None, **_unused):
+                       bilateral_sigma=None, color_jitter_pt=None, bgr2rgb=True, return_lr=False, packed=None, mask_modes=None,
+                       masks=None, **_unused):
     """One launch of b200ir_degrade_full over a batch (see include/b200ir.h).  gt_u8: uint8 CUDA tensor [B,H,W,3] in
     the reference's channel order (BGR), or a float32 CUDA tensor [B,H,W,3] in [0,1] (the reference's img_gt after
     cv2.resize, not on the 8-bit grid: filter2D kinds then work on the float values as the reference does); the other arguments as returned by sample_params (or packed= the result of
@@ -522,16 +597,19 @@ def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, 
     if gt_u8.dtype == torch.float32:
         gt_f32, gt_u8 = gt_u8, torch.empty(B, H, W, 3, device=dev, dtype=torch.uint8)   # scratch the launch fills
     pk = packed if packed is not None else pack_degrade_full(modes, kernels, sizes, noise, quality, jitter, gray,
-                                                             bilateral_sigma, color_jitter_pt, dev)
+                                                             bilateral_sigma, color_jitter_pt, dev, mask_modes, masks)
     assert pk['n'] == B
+    mask_t = pk.get('mask')
+    if mask_t is not None and tuple(mask_t.shape) != (B, H, W):
+        raise ValueError(f'masks must be uint8 [B, H, W] = {(B, H, W)}, got {tuple(mask_t.shape)}')
     out = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
     lr = torch.zeros(B, pk['lr_hmax'], pk['lr_wmax'], 3, device=dev, dtype=torch.float32) if return_lr else None
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)  # noqa: E731
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.lib().b200ir_degrade_full(p(gt_u8), p(gt_f32), p(pk['taps']), pk['kmax'], p(pk['crops']), p(pk['noise']),
-                                                  pk['lr_wmax'], pk['lr_hmax'], p(out), p(lr), B, H, W,
-                                                  1 if bgr2rgb else 0, st), 'b200ir_degrade_full')
+        _lib.check(_lib.lib().b200ir_degrade_full_masked(p(gt_u8), p(gt_f32), p(pk['taps']), pk['kmax'], p(pk['crops']),
+                                                         p(pk['noise']), pk['lr_wmax'], pk['lr_hmax'], p(mask_t), p(out), p(lr),
+                                                         B, H, W, 1 if bgr2rgb else 0, st), 'b200ir_degrade_full')
     return (out, lr) if return_lr else out
 
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200IR_ABI_VERSION 2
+#define B200IR_ABI_VERSION 3   /* 3: b200ir_degrade_crop.mask_mode (appended), b200ir_degrade_full_masked */
 #define B200IR_MAX_TAPS 16
 #define B200IR_MAX_VIEWS 4
 
@@ -550,8 +550,11 @@ int b200ir_degrade(const uint8_t* gt, const double* taps, const int32_t* ksize, 
  * normalize (:307-311).
  * Random draws stay on the host (image_restoration_b200.degradation.sample_params mirrors the reference's order of
  * random / np.random calls); this entry point is deterministic in its arguments.
- * Not covered (host fallback does not exist either -- callers must not select them): random_mask,
- * the 'pyblur_motion' / 'random_cover' / 'bicubic' kinds.
+ * random_mask (:153-187, :299-303; `random_mask: true` in the dataset options) is the mask argument of
+ * b200ir_degrade_full_masked: the shapes are drawn on the host with the reference's own calls (random rectangles / halves,
+ * cv2.line / circle / ellipse), the kernel applies them.
+ * Not covered: the 'bicubic' kind; 'pyblur_motion' / 'random_cover' call RandomMotion / RandomCover, which the reference's
+ * pyblur package does not define (pyblur/pyblur/__init__.py) -- they raise NameError in the reference itself.
  */
 typedef struct b200ir_degrade_crop {
   int32_t blur_mode;    /* 0 none; 1 'pyblur': scipy convolve2d on the uint8 image, fill 255, truncated to uint8;
@@ -574,6 +577,10 @@ typedef struct b200ir_degrade_crop {
   int32_t cj_order[4];   /* the drawn order: 0 brightness, 1 contrast, 2 saturation, 3 hue */
   float cj_factor[4];    /* the factor of each step as float32 (hue: the shift) */
   float cj_one_minus[4]; /* (float)(1.0 - factor), the second blend weight as torchvision's _blend evaluates it */
+  int32_t mask_mode;     /* random_mask (ffhq_degradation_dataset.py:153-187, :299-303), needs the mask argument of
+                            b200ir_degrade_full_masked: 0 off; 1 regular / half masks: masked pixels become 1.0; 2 irregular
+                            mask: the whole image goes through np.array(img * 255.0, uint8) (truncation) and the drawn pixels
+                            become 255 */
 } b200ir_degrade_crop;
 
 /* gt uint8 [B][H][W][3] (channel order B,G,R as the reference holds images).  gt_f32 (optional): the float image
@@ -587,6 +594,10 @@ typedef struct b200ir_degrade_crop {
 int b200ir_degrade_full(uint8_t* gt, const float* gt_f32, const double* taps, int kmax, const b200ir_degrade_crop* crops,
                         const float* noise, int lr_wmax, int lr_hmax, float* out, float* lr_out, int B, int H, int W,
                         int bgr2rgb, void* stream);
+/* The same with random_mask: mask uint8 [B][H][W] (non-zero = masked; rows of crops with mask_mode 0 are ignored), or NULL. */
+int b200ir_degrade_full_masked(uint8_t* gt, const float* gt_f32, const double* taps, int kmax, const b200ir_degrade_crop* crops,
+                               const float* noise, int lr_wmax, int lr_hmax, const uint8_t* mask, float* out, float* lr_out,
+                               int B, int H, int W, int bgr2rgb, void* stream);
 
 #ifdef __cplusplus
 }

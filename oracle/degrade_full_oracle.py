@@ -208,6 +208,22 @@ def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, g
     return up, lr
 
 
+def apply_random_mask(up, mask_mode, mask):
+    """FFHQDegradationDataset.random_mask applied to the image of __getitem__ (ffhq_degradation_dataset.py:299-303) once its
+    shapes are drawn (degradation.random_mask_draw mirrors the draws): tensor2img(out_type=float32) clamps to [0, 1]; the
+    regular / half kinds (:95-110, :163-186) write 1.0 into the masked pixels; the irregular kind (:112-151) takes
+    np.array(img * 255.0, dtype=np.uint8) of the whole image, draws 255 and returns mask.astype('float32') / 255.0."""
+    img = np.clip(up, 0, 1).astype(np.float32)
+    if mask_mode == 2:
+        m = np.array(img * 255.0, dtype=np.uint8)
+        m[np.asarray(mask) != 0] = 255
+        return m.astype('float32') / 255.0
+    if mask_mode == 1:
+        img = img.copy()
+        img[np.asarray(mask) != 0] = 1.0
+    return img
+
+
 def lq_tensor(up, bgr2rgb=True):
     """Tail of __getitem__: 8-bit grid, normalise with mean = std = 0.5, HWC -> CHW (numpy float32)."""
     x = np.clip(np.rint(np.clip(up, 0, 1) * np.float32(255.)), 0, 255) / np.float32(255.)
@@ -218,6 +234,8 @@ def lq_tensor(up, bgr2rgb=True):
 
 
 def degrade_full(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, gray=0, bgr2rgb=True, exact_blur=True,
-                 lib_jpeg=False, bilateral_sigma=0.0, cj=None):
+                 lib_jpeg=False, bilateral_sigma=0.0, cj=None, mask_mode=0, mask=None):
     up, lr = lq_image(gt_u8, mode, kernel, lr_size, noise, quality, jitter, gray, exact_blur, lib_jpeg, bilateral_sigma, cj)
+    if mask_mode:
+        up = apply_random_mask(up, mask_mode, mask)
     return lq_tensor(up, bgr2rgb), lr

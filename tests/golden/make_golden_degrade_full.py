@@ -60,18 +60,27 @@ def reference_lq(deg, DS, gt, opt):
         t = DS.color_jitter_pt(t, opt.get('brightness', (0.5, 1.5)), opt.get('contrast', (0.5, 1.5)),
                                opt.get('saturation', (0, 1.5)), opt.get('hue', (-0.1, 0.1)))
     t = t.clamp(0, 1)                                             # tensor2img(out_type=float32) / img2tensor round trip (:299-303)
+    if opt.get('random_mask'):                                    # :299-303: tensor2img -> random_mask -> img2tensor
+        img = np.ascontiguousarray(t.numpy().transpose(1, 2, 0)[..., ::-1])
+        img = DS.random_mask(img)
+        t = torch.from_numpy(np.ascontiguousarray(img[..., ::-1].transpose(2, 0, 1))).float()
     t = torch.clamp((t * 255.0).round(), 0, 255) / 255.
     return ((t - 0.5) / 0.5).numpy()
 
 
 def main():
     deg, DS = ref_import.load_reference_degradations()
+    if len(sys.argv) > 1 and sys.argv[1] == 'mask':     # random_mask: true (regular / irregular / half masks), 14 small crops
+        make(deg, DS, 'degrade_full_mask.npz', 64, 192, 14, 5000, np.random.default_rng(11), float_gt=False,
+             opt=dict(OPT, random_mask=True))
+        return
     make(deg, DS, 'degrade_full.npz', 128, 384, 20, 1000, np.random.default_rng(7), float_gt=False)
     # GT images that are not on the 8-bit grid: the dataset resizes every image to the network size (:230)
     make(deg, DS, 'degrade_full_floatgt.npz', 64, 192, 12, 3000, np.random.default_rng(9), float_gt=True)
 
 
-def make(deg, DS, fname, H, W, N, seed0, rng, float_gt):
+def make(deg, DS, fname, H, W, N, seed0, rng, float_gt, opt=None):
+    opt = opt or OPT
     gts, outs, seeds = [], [], []
     for i in range(N):
         gt = smooth_crop(rng, H, W)
@@ -83,14 +92,14 @@ def make(deg, DS, fname, H, W, N, seed0, rng, float_gt):
         random.seed(seed)
         np.random.seed(seed)
         torch.manual_seed(seed)
-        outs.append(reference_lq(deg, DS, gt, OPT))
+        outs.append(reference_lq(deg, DS, gt, opt))
         gts.append(gt)
         seeds.append(seed)
     # parameters the host mirror draws from the same seeds (stored so the GPU box needs no reference)
     recs = []
     for gt, seed in zip(gts, seeds):
         pr, nr = random.Random(seed), np.random.RandomState(seed)
-        recs.append(D.sample_params(1, H, W, OPT, py_random=pr, np_random=nr,
+        recs.append(D.sample_params(1, H, W, opt, py_random=pr, np_random=nr,
                                     torch_generator=torch.Generator().manual_seed(seed)))
     kmax = 29
     taps = np.zeros((N, kmax, kmax), np.float64)
@@ -102,7 +111,11 @@ def make(deg, DS, fname, H, W, N, seed0, rng, float_gt):
     noise = np.zeros((N, lh.max(), lw.max(), 3), np.float32)
     for i, r in enumerate(recs):
         noise[i, :lh[i], :lw[i]] = r['noise'][0]
-    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', fname), gt=np.stack(gts),
+    extra = {}
+    if opt.get('random_mask'):
+        extra = dict(mask_modes=np.array([r['mask_modes'][0] for r in recs]), masks=np.stack([r['masks'][0] for r in recs]))
+        print('mask modes', extra['mask_modes'].tolist(), 'masked fraction', [round(float(m.mean()), 3) for m in extra['masks']])
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', fname), gt=np.stack(gts), **extra,
                         out_u8=np.rint((np.stack(outs) * 0.5 + 0.5) * 255).astype(np.uint8), seeds=np.array(seeds),
                         modes=np.array([r['modes'][0] for r in recs]), taps=taps,
                         ksize=np.array([r['kernels'][0].shape[0] for r in recs]),

@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, n), f'{n} declared in b200ir.h but not exported'
         assert n in _lib.SIGNATURES, f'{n} has no ctypes signature'
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.b200ir_abi_version() == 2
+    assert lib.b200ir_abi_version() == 3
 
 
 def test_struct_layout_matches_c(tmp_path):

@@ -120,8 +120,9 @@ def test_kernel_builders_known_answers():
     assert D.average_kernel(5).dtype == np.float32 and np.allclose(D.average_kernel(5), 0.04)
     with pytest.raises(NotImplementedError):
         D.random_mixed_kernel(['bicubic'], [1.0], 21)
-    with pytest.raises(NotImplementedError):
-        D.sample_params(1, 32, 64, dict(blur_kernel_size=21, random_mask=True))
+    for kind in ('pyblur_motion', 'random_cover'):      # RandomMotion / RandomCover are undefined in the reference's pyblur
+        with pytest.raises(NotImplementedError):
+            D.random_mixed_kernel([kind], [1.0], 21)
 
 
 @pytest.mark.skipif(not ref_import.available(), reason='/root/reference not present')
@@ -195,3 +196,38 @@ def test_explicit_resize_is_bit_exact_against_cv2():
         img = rng.random((h, w, 3)).astype(np.float32)
         ref = cv2.resize(img, (W, H), interpolation=cv2.INTER_LINEAR)
         assert np.array_equal(dfo.resize_linear(img, (W, H)), ref), (h, w, H, W)
+
+
+def test_random_mask_oracle_reproduces_golden_reference_outputs():
+    """`random_mask: true`: tests/golden/degrade_full_mask.npz holds the REFERENCE's outputs (its own random_mask, regular /
+    irregular / half kinds) and the shapes the host mirror drew from the same seeds; oracle(mirror's shapes) == reference."""
+    g = np.load(os.path.join(os.path.dirname(GOLD), 'degrade_full_mask.npz'))
+    assert {1, 2} <= set(int(m) for m in g['mask_modes'])
+    for i in range(len(g['seeds'])):
+        c = golden_case(g, i)
+        lib, _ = dfo.degrade_full(c['gt'], c['mode'], c['kernel'], c['lr_size'], c['noise'], c['quality'], c['jitter'],
+                                  c['gray'], exact_blur=False, bilateral_sigma=c['bsigma'], cj=c['cj'],
+                                  mask_mode=int(g['mask_modes'][i]), mask=g['masks'][i])
+        assert np.array_equal(to_u8(lib), g['out_u8'][i].astype(np.int32)), (i, int(g['mask_modes'][i]))
+        m = g['masks'][i] != 0
+        assert (g['out_u8'][i][:, m] == 255).all()                      # masked pixels are white in the reference's output
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='/root/reference not present')
+def test_random_mask_draws_equal_reference():
+    """degradation.random_mask_draw against FFHQDegradationDataset.random_mask itself, same seeds: applying the mirrored
+    shapes to the same image gives the reference's image (all three kinds occur in 40 draws)."""
+    _, DS = ref_import.load_reference_degradations()
+    rng = np.random.default_rng(3)
+    H, W = 64, 160
+    seen = set()
+    for seed in range(40):
+        img = rng.random((H, W, 3)).astype(np.float32)
+        random.seed(seed)
+        np.random.seed(seed)
+        ref = DS.random_mask(img.copy())
+        mode, mask = D.random_mask_draw(H, W, py_random=random.Random(seed), np_random=np.random.RandomState(seed))
+        got = dfo.apply_random_mask(img, mode, mask)
+        assert np.array_equal(got, np.asarray(ref, dtype=np.float32)), (seed, mode)
+        seen.add((mode, bool(mask.any())))
+    assert {m for m, _ in seen} == {1, 2}

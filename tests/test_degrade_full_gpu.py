@@ -186,3 +186,54 @@ def test_synthesize_pairs_feeds_the_network():
     net = GFPGANv1OCR(decoder_load_path=None, fix_decoder=True, **kw).eval().cuda()
     out, _ = net(lq, return_rgb=False, randomize_noise=False)
     assert out.shape == (8, 3, 128, 384) and torch.isfinite(out).all()
+
+
+def test_random_mask_golden_reference_outputs():
+    """`random_mask: true` (ffhq_degradation_dataset.py:153-187, :299-303): the kernel applies the shapes the host mirror drew;
+    against the reference's own outputs (tests/golden/degrade_full_mask.npz) and, bit for bit, against the oracle."""
+    from image_restoration_b200 import degradation as D
+    g, kernels, sizes, cj = golden_batch('degrade_full_mask.npz')
+    n = len(kernels)
+    out = D.degrade_full_batch(torch.from_numpy(g['gt']).cuda(), [int(m) for m in g['modes']], kernels, sizes, noise=g['noise'],
+                               quality=[int(q) for q in g['quality']], jitter=g['jitter'], gray=[int(x) for x in g['gray']],
+                               bilateral_sigma=[float(x) for x in g['bsigma']], color_jitter_pt=cj,
+                               mask_modes=[int(m) for m in g['mask_modes']], masks=g['masks'])
+    torch.cuda.synchronize()
+    out = out.cpu().numpy()
+    exact = 0
+    for i in range(n):
+        lw, lh = sizes[i]
+        diff = np.abs(to_u8(out[i]) - g['out_u8'][i].astype(np.int32))
+        m = g['masks'][i] != 0
+        assert (to_u8(out[i])[:, m] == 255).all(), i
+        assert (diff > 0).mean() < 0.02 and diff.max() <= 6, (i, str(g['kinds'][i]), (diff > 0).mean(), diff.max())
+        exact += int(diff.max() == 0)
+        ref, _ = dfo.degrade_full(g['gt'][i], int(g['modes'][i]), kernels[i], sizes[i], g['noise'][i, :lh, :lw],
+                                  int(g['quality'][i]), g['jitter'][i], int(g['gray'][i]), exact_blur=True,
+                                  bilateral_sigma=float(g['bsigma'][i]), cj=cj[i], mask_mode=int(g['mask_modes'][i]),
+                                  mask=g['masks'][i])
+        if not any(op == 1 for op, _ in cj[i]):
+            assert np.array_equal(out[i], ref), (i, int(g['mask_modes'][i]))
+    assert exact >= n // 3, exact
+
+
+def test_random_mask_through_synthesize_pairs():
+    """sample_params draws masks when the dataset options say `random_mask: true`; rows with mask_mode 0 are untouched."""
+    import random as pyrandom
+    from image_restoration_b200 import degradation as D
+    rng = np.random.RandomState(5)
+    gt = torch.from_numpy(rng.randint(0, 256, (6, 64, 192, 3)).astype(np.uint8)).cuda()
+    opt = dict(blur_kernel_size=21, kernel_list=['iso', 'pyblur'], kernel_prob=[0.5, 0.5], blur_sigma=[0.1, 10],
+               downsample_range=[4.0, 12.0], noise_range=[0, 20], jpeg_range=[30, 100], random_mask=True)
+    pair, prm = D.synthesize_pairs(gt, opt, py_random=pyrandom.Random(1), np_random=np.random.RandomState(1))
+    assert prm['masks'].shape == (6, 64, 192) and len(prm['mask_modes']) == 6
+    lq = pair['lq'].cpu().numpy()
+    for b in range(6):
+        m = prm['masks'][b] != 0
+        assert m.any() and (lq[b][:, m] == 1.0).all()
+    prm2 = dict(prm, mask_modes=[0] * 6)
+    plain = D.degrade_full_batch(gt, **{k: v for k, v in prm2.items() if k != 'masks'}).cpu().numpy()
+    for b in range(6):
+        if prm['mask_modes'][b] == 1:
+            keep = prm['masks'][b] == 0
+            assert np.array_equal(lq[b][:, keep], plain[b][:, keep]), b
