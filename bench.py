@@ -308,7 +308,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
             'warmup': min(args.warmup, 2), 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': f'GFPGANv1OCR forward, 3x{H}x{W} crops, batch {args.batch}/GPU (sampled: '
+            'config': {'workload': f'GFPGANv1OCR forward, 3x{H}x{W} crops, batch {args.batch or 64}/GPU (sampled: '
                                    f'{sample_b} crop per step on CPU)', 'timing': 'host wall clock'},
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                              'sample': f'{steps} steps of B={sample_b} crop, fp32 oracle port of the reference forward'},
@@ -322,7 +322,8 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--batch', type=int, default=0, help='micro-batch per launch plan (default: 64 = BASELINE configs[1] at N = 1; '
+                    '128 for the sharded configs[2] at N > 1, where the batch per GPU is 512 .. 2048: +2 %% over 64)')
     ap.add_argument('--total', type=int, default=4096, help='N > 1: crops per step over all GPUs (BASELINE configs[2])')
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -344,7 +345,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     warmup = max(args.warmup, 3)
-    B = args.batch
+    B = args.batch or (64 if world == 1 else 128)
     # crops this rank processes per step: one micro-batch at N = 1, its shard of --total at N > 1
     if world > 1:
         lo, hi = shard_bounds(args.total, rank, world)

@@ -407,9 +407,12 @@ def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=
     elif kind == 'bilateral':       # bilateral_blur (degradations.py:358-361): sigma = random.randint(150, 250)
         sigma = py_random.randint(150, 250)
         return 4, bilateral_space_kernel(kernel_size, sigma), ('bilateral', kernel_size, sigma)
+    elif kind in ('pyblur_motion', 'random_cover'):
+        raise NotImplementedError(f"blur kind '{kind}' cannot run in the reference either: degradations.py:369-377 calls "
+                                  "RandomMotion / RandomCover, which its pyblur package does not define")
     else:
         raise NotImplementedError(f"blur kind '{kind}' has no B200 implementation (supported: "
-                                  f"{FILTER2D_KINDS + ('pyblur',)})")
+                                  f"{FILTER2D_KINDS + ('pyblur', 'median', 'bilateral')})")
     if pad_kernel:
         k = _pad_to(k, pad_kernel_size)
     return 2, k, desc

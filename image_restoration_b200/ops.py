@@ -236,6 +236,8 @@ def conv3x3_s2(p, h, w, weight, out, **kw):
     b, hp, wp, c = p.shape
     assert hp == h + 2 and wp == w + 2 and h % 2 == 0 and w % 2 == 0
     cout = weight.shape[0]
+    if c == 32 and _S2_FOLD:       # 64-byte pixel rows: the pixel-folded form is faster (118 -> 87 us at B=64, 128x384, 32->64;
+        return conv3x3_s2_folded(p, h, w, s2_fold_weight(weight, c), out, **kw)   # 64 channels and up: slower, tools/time_conv_s2.py)
     views = []
     for py in range(2):
         for px in range(2):
@@ -244,6 +246,34 @@ def conv3x3_s2(p, h, w, weight, out, **kw):
     taps = [((kh % 2) * 2 + (kw % 2), kw // 2, kh // 2) for kh in range(3) for kw in range(3)]
     oh, ow = h // 2, w // 2
     return ConvOp(views, weight, c, cout, taps, (ow, oh, b), out, (cout, ow * cout, oh * ow * cout), **kw)
+
+
+_S2_FOLD = os.environ.get('B200IR_S2_FOLD', '1') != '0'
+
+
+def s2_fold_weight(weight, cin):
+    """Packed weights [cout, 9*cin] (tap-major) of the stride-2 conv -> [cout, 6 * 2*cin] for conv3x3_s2_folded: taps
+    (kh, kw' = 0): pixel pair (kw 0 | kw 1), (kh, kw' = 1): (kw 2 | zeros)."""
+    cout = weight.shape[0]
+    w = weight.view(cout, 3, 3, cin)
+    out = torch.zeros(cout, 3, 2, 2, cin, device=weight.device, dtype=weight.dtype)
+    out[:, :, 0, 0], out[:, :, 0, 1], out[:, :, 1, 0] = w[:, :, 0], w[:, :, 1], w[:, :, 2]
+    return out.reshape(cout, 12 * cin).contiguous()
+
+
+def conv3x3_s2_folded(p, h, w, weight_folded, out, **kw):
+    """conv3x3_s2 on a pixel-folded view of p: horizontally adjacent pixel pairs are read as 2*C channels of one pixel
+    ([B,H+2,(W+2)/2,2C], a free view), which turns the stride-2 sampling along x into a dense stride-1 conv with two taps per
+    kernel row (the third kw shares a pixel pair with a zero block); rows keep their stride-2 phase views.  Dense TMA boxes with
+    128-byte rows for C = 32 instead of element-strided ones, at 4/3 of the MMA work."""
+    b, hp, wp, c = p.shape
+    assert hp == h + 2 and wp == w + 2 and h % 2 == 0 and w % 2 == 0
+    cout = weight_folded.shape[0]
+    assert weight_folded.shape[1] == 12 * c
+    views = [View(p.data_ptr() + 2 * py * wp * c, 2 * c, wp // 2, hp // 2, b, 2 * c, 2 * wp * c, hp * wp * c) for py in range(2)]
+    taps = [(kh % 2, kx, kh // 2) for kh in range(3) for kx in range(2)]
+    oh, ow = h // 2, w // 2
+    return ConvOp(views, weight_folded, 2 * c, cout, taps, (ow, oh, b), out, (cout, ow * cout, oh * ow * cout), **kw)
 
 
 CONVT_PHASES = [(py, px) for py in range(2) for px in range(2)]

@@ -37,11 +37,20 @@ def timeit(op):
     return e0.elapsed_time(e1) / 10 * 1e3
 
 
-for (H, W, cin, cout) in [(128, 384, 32, 64), (64, 192, 64, 256), (32, 96, 256, 256), (16, 48, 256, 256), (8, 24, 256, 256)]:
+for (H, W, cin, cout) in [(128, 384, 32, 64), (64, 192, 64, 256), (128, 384, 128, 256), (32, 96, 256, 256), (16, 48, 256, 256), (8, 24, 256, 256)]:
     p = torch.randn(B, H + 2, W + 2, cin, device=dev).half()
     w = (torch.randn(cout, 9 * cin, device=dev) / math.sqrt(9 * cin)).half()
     bias = torch.zeros(cout, device=dev)
     out = torch.empty(B, H // 2, W // 2, cout, device=dev, dtype=torch.float16)
+    ops._S2_FOLD = False
     a = ops.conv3x3_s2(p, H, W, w, out, bias=bias, act=True)
     b = s2_deint(p, H, W, w, out, bias=bias, act=True)
-    print(f'{H}x{W} {cin}->{cout}: strided views {timeit(a):.1f} us   deinterleaved {timeit(b):.1f} us   tile={a.desc.tile_w, a.desc.tile_h, a.desc.tile_b}')
+    out2 = torch.empty_like(out)
+    c = ops.conv3x3_s2_folded(p, H, W, ops.s2_fold_weight(w, cin), out2, bias=bias, act=True)
+    a()
+    c()
+    torch.cuda.synchronize()
+    err = (out.float() - out2.float()).abs().max().item()
+    print(f'{H}x{W} {cin}->{cout}: strided views {timeit(a):.1f} us   deinterleaved {timeit(b):.1f} us   pixel-folded '
+          f'{timeit(c):.1f} us (max diff {err:.2e})   tile={a.desc.tile_w, a.desc.tile_h, a.desc.tile_b} / '
+          f'{c.desc.tile_w, c.desc.tile_h, c.desc.tile_b}')
