@@ -422,6 +422,18 @@ def main():
             dist.barrier()
         return ms
 
+    def graphed(fn):
+        """fn's launches captured in a CUDA graph; returns its replay.  The forward step itself is a graph replay: timing a
+        group of its kernels through per-launch Python / ctypes calls would charge the small pyramid levels (10-20 us kernels)
+        with host launch time the step never pays."""
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        torch.cuda.synchronize()
+        return g.replay
+
     # clocks take a few hundred ms to settle after the idle -> busy transition: untimed pre-roll before the W warm-ups
     t_pre = time.time()
     while time.time() - t_pre < 1.5:
@@ -476,7 +488,7 @@ def main():
     def conv_only():
         for op in conv_ops:
             op()
-    ms_conv = timed(conv_only, args.steps, warmup, preroll=0.3)
+    ms_conv = timed(graphed(conv_only), args.steps, warmup, preroll=0.3)
     n_conv_ops = len(conv_ops)
     conv_alg_bytes = 0          # algorithmic bytes of the conv launches: input once + output once + weights, fp16
     for op in conv_ops:
@@ -497,10 +509,10 @@ def main():
             def run_group(g=group):
                 for op in g:
                     op()
-            ms = timed(run_group, args.steps, 3, preroll=0.05) / args.steps
+            ms = timed(graphed(run_group), args.steps, 3, preroll=0.05) / args.steps
             nbytes = sum(op.nbytes for op in group)
             big = max(group, key=lambda op: op.nbytes)        # the largest launch of the kind, alone
-            ms_big = timed(big, args.steps, 3, preroll=0.05) / args.steps
+            ms_big = timed(graphed(big), args.steps, 3, preroll=0.05) / args.steps
             pw_report.append({'kernel': name, 'launches_per_step': len(group), 'algorithmic_mb_per_step': nbytes / 1e6,
                               'ms_per_step': ms, 'achieved_gbs': nbytes / ms / 1e6,
                               'largest_launch': {'algorithmic_mb': big.nbytes / 1e6, 'ms': ms_big,
@@ -651,6 +663,8 @@ def main():
                        'parallelism': f'dp{world} (independent shards, no collective)',
                        'l2': 'working set per forward >> 126 MB L2 (activations ~GBs at batch 64); no explicit flush',
                        'executor': 'CUDA graph replay of the launch plan',
+                       'kernel_group_timing': 'roofline / memory_bound_kernels: the launches of one step of that kind captured in '
+                                              'a CUDA graph and replayed back to back on one stream (CUDA events around the replays)',
                        'timing': 'CUDA events, max over ranks; >= 0.5 s untimed pre-roll after the barrier, immediately '
                                  'before the first event'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': crops_per_step * 3 * H * W * 4,

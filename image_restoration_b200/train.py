@@ -446,8 +446,9 @@ class GFPGANTrainer:
     """optimize_parameters of GFPGANModel (gfpgan_model.py:494-691) for the plate options: pixel L1 (weight 0.1), image
     pyramid L1 (weight 1), GAN 'wgan_softplus' (weight 0.1), net_d logistic loss; Adam lr 2e-3 betas (0, 0.99) for both
     networks; EMA decay 0.5 ** (32 / 10000); R1 penalty on the real batch every net_d_reg_every iterations (r1.py); the
-    perceptual + style terms when a VGG19 is supplied (perceptual.py).  The identity / facial-component terms are not part of
-    this step (ArcFace / component discriminators are face-specific and off for plates).
+    perceptual + style terms when a VGG19 is supplied (perceptual.py).  The identity / component terms are not part of this
+    step: the reference never executes them (gfpgan_model.py:70-74 hard-codes use_facial_disc = False and get_roi_regions is
+    `pass`; network_identity is commented out in every training YAML).
 
     net_g: image_restoration_b200.GFPGANv1OCR (fix_decoder True or False) on the device; net_d: image_restoration_b200.disc.StyleGAN2Discriminator;
     net_g_ema: optional second GFPGANv1OCR that receives the EMA of the trainable parameters."""
