@@ -99,6 +99,7 @@ struct alignas(64) ConvParams {
   int rgb_w_px;
   int no_store;
   int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
+  int epi_pipe;      // fast epilogues without global operands: keep the next chunk's TMEM load in flight (host heuristic)
   int w_img_rows;    // per-image weights: rows of the weight matrix per image (= cout), 0 = one matrix for all images
 };
 
@@ -447,98 +448,149 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
   if (p.dbg_skip_epi) return;
   const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
   const float ag = p.act_gain, slope = p.slope;
+  const bool act = slope != 1.f;  // slope 1: no activation (max(v, v)); saves two instructions per element
+  const int block_n = p.block_n;
   float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-    uint32_t raw[16];
-    tmem_ld16(taddr + c0, raw);
-    float4 bs[4], dm[4];
+  // pixel-shuffle store (transposed conv, folded ConvUpLayer): sub-pixel base and channel of the current chunk, advanced
+  // by 16 channels per chunk instead of recomputing the phase split of n0 + c0 every time
+  const int ps_r = p.ps_r, ps_c = p.ps_c;
+  int ps_ch = 0, ps_t = 0;
+  const __half* ps_base = r.out;
+  if (ps_r) {
+    ps_t = (p.ps_shift >= 0) ? (n0 >> p.ps_shift) : (n0 / ps_c);
+    ps_ch = n0 - ps_t * ps_c;
+    const int ty = ps_t / ps_r;
+    ps_base = r.out + (long long)ty * p.out_sy + (long long)(ps_t - ty * ps_r) * p.out_sx;
+  }
+  // everything after the accumulator chunk has arrived: scale / bias / activation / residual / ToRGB / store
+  auto finish = [&](int c0, const uint32_t (&raw)[16], const uint4 (&ra)[2], const uint4 (&rb)[2], const uint4 (&rc)[2],
+                    const uint4 (&rd)[2]) {
+    if (valid) {
+      float4 bs[4], dm[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bs[j] = lds_f4(s_bias + (c0 + 4 * j) * 4);
-    if (F & F_DEMOD) {
+      for (int j = 0; j < 4; ++j) bs[j] = lds_f4(s_bias + (c0 + 4 * j) * 4);
+      if (F & F_DEMOD) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dm[j] = lds_f4(s_demod + (c0 + 4 * j) * 4);
-    } else {
+        for (int j = 0; j < 4; ++j) dm[j] = lds_f4(s_demod + (c0 + 4 * j) * 4);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dm[j] = make_float4(ag, ag, ag, ag);
-    }
-    uint4 ra[2], rb[2], rc[2], rd[2];
-    if ((F & (F_RES1 | F_RES2)) && valid) {
-      ra[0] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0));
-      ra[1] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0) + 1);
-      if (F & F_RES2) {
-        rb[0] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0));
-        rb[1] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0) + 1);
-        rc[0] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0));
-        rc[1] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0) + 1);
-        rd[0] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0));
-        rd[1] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0) + 1);
+        for (int j = 0; j < 4; ++j) dm[j] = make_float4(ag, ag, ag, ag);
       }
-    }
-    tmem_ld_wait16(raw);
-    if (!valid) continue;
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), dm[j].x, bs[j].x + nz);
-      v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), dm[j].y, bs[j].y + nz);
-      v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), dm[j].z, bs[j].z + nz);
-      v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), dm[j].w, bs[j].w + nz);
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
-    if (F & F_RES1) {
-      float f[16];
-      unpack_half8(ra[0], f);
-      unpack_half8(ra[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
-    }
-    if (F & F_RES2) {
-      float f[16];
-      unpack_half8(ra[0], f); unpack_half8(ra[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
-      unpack_half8(rb[0], f); unpack_half8(rb[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w01, v[j]);
-      unpack_half8(rc[0], f); unpack_half8(rc[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w10, v[j]);
-      unpack_half8(rd[0], f); unpack_half8(rd[1], f + 8);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w11, v[j]);
-    }
-    if (F & F_RGB) {
+      float v[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 w0 = lds_f4(s_aux + (aux_stride + c0 + 4 * j) * 4);
-        const float4 w1 = lds_f4(s_aux + (2 * aux_stride + c0 + 4 * j) * 4);
-        const float4 w2 = lds_f4(s_aux + (3 * aux_stride + c0 + 4 * j) * 4);
-        rgb0 = fmaf(v[4 * j], w0.x, rgb0); rgb1 = fmaf(v[4 * j], w1.x, rgb1); rgb2 = fmaf(v[4 * j], w2.x, rgb2);
-        rgb0 = fmaf(v[4 * j + 1], w0.y, rgb0); rgb1 = fmaf(v[4 * j + 1], w1.y, rgb1); rgb2 = fmaf(v[4 * j + 1], w2.y, rgb2);
-        rgb0 = fmaf(v[4 * j + 2], w0.z, rgb0); rgb1 = fmaf(v[4 * j + 2], w1.z, rgb1); rgb2 = fmaf(v[4 * j + 2], w2.z, rgb2);
-        rgb0 = fmaf(v[4 * j + 3], w0.w, rgb0); rgb1 = fmaf(v[4 * j + 3], w1.w, rgb1); rgb2 = fmaf(v[4 * j + 3], w2.w, rgb2);
+        v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), dm[j].x, bs[j].x + nz);
+        v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), dm[j].y, bs[j].y + nz);
+        v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), dm[j].z, bs[j].z + nz);
+        v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), dm[j].w, bs[j].w + nz);
       }
-      if (!(F & F_NOSTORE)) {
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+      }
+      if (F & F_RES1) {
+        float f[16];
+        unpack_half8(ra[0], f);
+        unpack_half8(ra[1], f + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
+      }
+      if (F & F_RES2) {
+        float f[16];
+        unpack_half8(ra[0], f); unpack_half8(ra[1], f + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
+        unpack_half8(rb[0], f); unpack_half8(rb[1], f + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w01, v[j]);
+        unpack_half8(rc[0], f); unpack_half8(rc[1], f + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w10, v[j]);
+        unpack_half8(rd[0], f); unpack_half8(rd[1], f + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w11, v[j]);
+      }
+      if (F & F_RGB) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 s4 = lds_f4(s_aux + (c0 + 4 * j) * 4);
-          v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+          const float4 w0 = lds_f4(s_aux + (aux_stride + c0 + 4 * j) * 4);
+          const float4 w1 = lds_f4(s_aux + (2 * aux_stride + c0 + 4 * j) * 4);
+          const float4 w2 = lds_f4(s_aux + (3 * aux_stride + c0 + 4 * j) * 4);
+          rgb0 = fmaf(v[4 * j], w0.x, rgb0); rgb1 = fmaf(v[4 * j], w1.x, rgb1); rgb2 = fmaf(v[4 * j], w2.x, rgb2);
+          rgb0 = fmaf(v[4 * j + 1], w0.y, rgb0); rgb1 = fmaf(v[4 * j + 1], w1.y, rgb1); rgb2 = fmaf(v[4 * j + 1], w2.y, rgb2);
+          rgb0 = fmaf(v[4 * j + 2], w0.z, rgb0); rgb1 = fmaf(v[4 * j + 2], w1.z, rgb1); rgb2 = fmaf(v[4 * j + 2], w2.z, rgb2);
+          rgb0 = fmaf(v[4 * j + 3], w0.w, rgb0); rgb1 = fmaf(v[4 * j + 3], w1.w, rgb1); rgb2 = fmaf(v[4 * j + 3], w2.w, rgb2);
+        }
+        if (!(F & F_NOSTORE)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 s4 = lds_f4(s_aux + (c0 + 4 * j) * 4);
+            v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+          }
         }
       }
-    }
-    if (!(F & F_NOSTORE)) {
-      uint32_t pk[8];
+      if (!(F & F_NOSTORE)) {
+        uint32_t pk[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        __half2 h = f2h2_sat(v[2 * j], v[2 * j + 1]);
-        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        for (int j = 0; j < 8; ++j) {
+          __half2 h = f2h2_sat(v[2 * j], v[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        const __half* op = ps_r ? ps_base + ps_ch : r.out + c0;
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]),
+                     "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                     : "memory");
       }
-      const __half* op = r.out + c0 + (p.ps_r ? ps_offset(p, n0, c0) : 0);
-      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]),
-                   "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                   : "memory");
+    }
+    if (ps_r) {  // next chunk: 16 channels on, next sub-pixel when the channel block is complete
+      ps_ch += 16;
+      if (ps_ch >= ps_c) {
+        ps_ch = 0;
+        ++ps_t;
+        const int ty = ps_t / ps_r;
+        ps_base = r.out + (long long)ty * p.out_sy + (long long)(ps_t - ty * ps_r) * p.out_sx;
+      }
+    }
+  };
+  if ((F & (F_RES1 | F_RES2)) || !p.epi_pipe) {
+    // residual variants: the residual row(s) of a chunk are fetched from global memory while its TMEM load is in flight
+#pragma unroll 1
+    for (int c0 = 0; c0 < block_n; c0 += 16) {
+      uint32_t raw[16];
+      tmem_ld16(taddr + c0, raw);
+      uint4 ra[2], rb[2], rc[2], rd[2];
+      if ((F & (F_RES1 | F_RES2)) && valid) {
+        ra[0] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0));
+        ra[1] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0) + 1);
+        if (F & F_RES2) {
+          rb[0] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0));
+          rb[1] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0) + 1);
+          rc[0] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0));
+          rc[1] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0) + 1);
+          rd[0] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0));
+          rd[1] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0) + 1);
+        }
+      }
+      tmem_ld_wait16(raw);
+      finish(c0, raw, ra, rb, rc, rd);
+    }
+  } else {
+    // no global operands: the TMEM load of chunk k + 1 is in flight while chunk k is scaled, activated and stored (two
+    // register buffers; tcgen05.wait::ld covers every outstanding load, so the next one is issued right after the wait)
+    uint32_t raw_a[16], raw_b[16];
+    const uint4 none[2] = {};
+    tmem_ld16(taddr, raw_a);
+#pragma unroll 1
+    for (int c0 = 0; c0 < block_n; c0 += 32) {
+      tmem_ld_wait16(raw_a);
+      const bool second = c0 + 16 < block_n;
+      if (second) tmem_ld16(taddr + c0 + 16, raw_b);
+      finish(c0, raw_a, none, none, none, none);
+      if (second) {
+        tmem_ld_wait16(raw_b);
+        if (c0 + 32 < block_n) tmem_ld16(taddr + c0 + 32, raw_a);
+        finish(c0 + 16, raw_b, none, none, none, none);
+      }
     }
   }
   if ((F & F_RGB) && valid) {

@@ -249,7 +249,10 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
     static int dbg = -1;
     if (dbg < 0) dbg = (getenv("B200IR_DBG_SKIP_EPI") != nullptr) ? atoi(getenv("B200IR_DBG_SKIP_EPI")) : 0;
     p.dbg_skip_epi = dbg;
-
+    // B200IR_EPI_PIPE: 0 / 1 force the pipelined TMEM loads of the fast epilogues off / on (A/B switch, tools/time_plan_ops.py)
+    static int pipe = -2;
+    if (pipe == -2) pipe = (getenv("B200IR_EPI_PIPE") != nullptr) ? atoi(getenv("B200IR_EPI_PIPE")) : -1;
+    p.epi_pipe = pipe >= 0 ? pipe : 1;
   }
   // ---- specialised epilogue selection
   {
