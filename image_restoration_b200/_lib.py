@@ -137,7 +137,7 @@ SIGNATURES = {
     'b200ir_softplus_loss': [_P, _I, _I, _F, _F, _F, _P, _P, _P],
     'b200ir_degrade': [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
     'b200ir_degrade_full': [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
-    'b200ir_degrade_full_masked': [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P],
+    'b200ir_degrade_full_ex': [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'b200ir_last_error': C.c_char_p, 'b200ir_launch_count': C.c_uint64, 'b200ir_conv_plan_destroy': None}
 

@@ -293,7 +293,7 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ gt
                     int kmax,
                     const b200ir_degrade_crop* __restrict__ crops, const float* __restrict__ noise, int lr_wmax,
                     int lr_hmax, float* __restrict__ out, float* __restrict__ lr_out, int H, int W, int bgr2rgb,
-                    const uint8_t* __restrict__ mask) {
+                    const uint8_t* __restrict__ mask, const uint8_t* __restrict__ alt) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_nnz;
   const int b = blockIdx.x;
@@ -314,9 +314,12 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ gt
   int* s_cb = reinterpret_cast<int*>(smem + lay.cbp);
   int* s_cr = reinterpret_cast<int*>(smem + lay.crp);
   uint8_t* s_gt = smem + lay.gt;
-  const uint8_t* g_img = gt + (size_t)b * H * W * 3;
-  const float* g_imgf = gt_f32 != nullptr ? gt_f32 + (size_t)b * H * W * 3 : nullptr;  // float GT: used where the
-                                                                                       // reference keeps float values
+  // blur_mode 5 ('bicubic'): the Pillow round trip was evaluated by pil_bicubic_kernel into `alt`; from here on the crop is a
+  // no-blur crop whose source is that uint8 image (np.array(blur2, float32) / 255.0, degradations.py:379-385)
+  const bool pre_blurred = mode == 5 && alt != nullptr;
+  const uint8_t* g_img = (pre_blurred ? alt : gt) + (size_t)b * H * W * 3;
+  const float* g_imgf = (gt_f32 != nullptr && !pre_blurred) ? gt_f32 + (size_t)b * H * W * 3 : nullptr;  // float GT: used
+                                                                                  // where the reference keeps float values
 
   // ---- set-up: compacted taps (one warp, kernel order), resize taps, u8/255 table, quantisation tables, GT staging
   if (tid < 32) {
@@ -349,7 +352,7 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ gt
   const uint8_t* img = kStage ? s_gt : g_img;
   const int n_nz = s_nnz;
   const int rad = (ksz - 1) >> 1;
-  const bool do_blur = mode != 0 && ksz > 0 && (n_nz > 0 || mode == 3);
+  const bool do_blur = mode != 0 && mode != 5 && ksz > 0 && (n_nz > 0 || mode == 3);
 
   // ---- 1. blur at the 2x2 source pixels of every LR pixel (4 lanes per LR pixel), down-resize, noise, clip
   {
@@ -623,6 +626,149 @@ degrade_full_kernel(const uint8_t* __restrict__ gt, const float* __restrict__ gt
   }
 }
 
+// ---------------------------------------------------------------------------------------------- 'bicubic' kind
+// degradations.bicubic (degradations.py:379-385): Image.fromarray(uint8 image) -> torchvision Resize((h // 4, w // 4), BICUBIC)
+// -> Resize((h, w), BICUBIC), i.e. two Pillow ImagingResample calls on an 8-bit RGB image.  Pillow's 8-bit path is integer
+// arithmetic (src/libImaging/Resample.c): per output index the window [xmin, xmin + n) and the coefficients
+// (int)(+-0.5 + w / sum(w) * 2^22) of the Keys cubic (a = -0.5) evaluated in double, support 2 * max(scale, 1); horizontal pass
+// first, every pass rounds with + 2^21 >> 22 and clamps to [0, 255].  The coefficient tables are built here, in fp64 with
+// explicitly rounded operations (the same IEEE sequence as the C code), so the result is Pillow's bit for bit.
+struct PilAxis {
+  int xmin, n, off;  // window start, length, offset of its coefficients
+};
+__device__ __forceinline__ double pil_cubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(a + 2.0, x), a + 3.0), x), x), 1.0);
+  if (x < 2.0) return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), a);
+  return 0.0;
+}
+// precompute_coeffs + normalize_coeffs_8bpc for one output index (one thread)
+__device__ void pil_axis_coeffs(int in_size, int out_size, int xx, int ksize, PilAxis* ax, int* kk) {
+  const double scale = __ddiv_rn((double)(float)in_size, (double)out_size);
+  const double fscale = scale < 1.0 ? 1.0 : scale;
+  const double support = __dmul_rn(2.0, fscale);
+  const double center = __dmul_rn((double)xx + 0.5, scale);
+  const double ss = __ddiv_rn(1.0, fscale);
+  int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  const int n = xmax - xmin;
+  double ww = 0.0;
+  for (int x = 0; x < n; ++x) ww = __dadd_rn(ww, pil_cubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss)));
+  int* k = kk + xx * ksize;
+  for (int x = 0; x < ksize; ++x) {
+    int c = 0;
+    if (x < n) {
+      double w = pil_cubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+      if (ww != 0.0) w = __ddiv_rn(w, ww);
+      c = (w < 0) ? (int)__dadd_rn(-0.5, __dmul_rn(w, 4194304.0)) : (int)__dadd_rn(0.5, __dmul_rn(w, 4194304.0));
+    }
+    k[x] = c;
+  }
+  ax[xx].xmin = xmin;
+  ax[xx].n = n;
+  ax[xx].off = xx * ksize;
+}
+__host__ __device__ inline int pil_ksize(int in_size, int out_size) {
+  const double scale = (double)(float)in_size / (double)out_size;
+  const double support = 2.0 * (scale < 1.0 ? 1.0 : scale);
+  int c = (int)support;
+  if ((double)c < support) ++c;  // ceil
+  return c * 2 + 1;
+}
+__device__ __forceinline__ uint8_t pil_clip8(int v) { return (uint8_t)min(max(v >> 22, 0), 255); }
+
+constexpr int kPilThreads = 512;
+// one CTA per crop; crops whose blur_mode is not 5 leave at once.  src / dst uint8 [B][H][W][3]
+__global__ void __launch_bounds__(kPilThreads) pil_bicubic_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                  const b200ir_degrade_crop* __restrict__ crops, int H, int W) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (crops[b].blur_mode != 5) return;
+  extern __shared__ __align__(16) uint8_t psm[];
+  const int h4 = H / 4, w4 = W / 4;
+  const int kdw = pil_ksize(W, w4), kdh = pil_ksize(H, h4), kuw = pil_ksize(w4, W), kuh = pil_ksize(h4, H);
+  // tables: [down W | down H | up W | up H]
+  PilAxis* a_dw = reinterpret_cast<PilAxis*>(psm);
+  PilAxis* a_dh = a_dw + w4;
+  PilAxis* a_uw = a_dh + h4;
+  PilAxis* a_uh = a_uw + W;
+  int* k_dw = reinterpret_cast<int*>(a_uh + H);
+  int* k_dh = k_dw + w4 * kdw;
+  int* k_uw = k_dh + h4 * kdh;
+  int* k_uh = k_uw + W * kuw;
+  uint8_t* t_a = reinterpret_cast<uint8_t*>(k_uh + H * kuh);   // [H][w4][3]  horizontal pass of the down-scaling
+  uint8_t* t_s = t_a + (size_t)H * w4 * 3;                     // [h4][w4][3] the low-resolution image
+  uint8_t* t_b = t_s + (size_t)h4 * w4 * 3;                    // [h4][W][3]  horizontal pass of the up-scaling
+  for (int i = tid; i < w4; i += kPilThreads) pil_axis_coeffs(W, w4, i, kdw, a_dw, k_dw);
+  for (int i = tid; i < h4; i += kPilThreads) pil_axis_coeffs(H, h4, i, kdh, a_dh, k_dh);
+  for (int i = tid; i < W; i += kPilThreads) pil_axis_coeffs(w4, W, i, kuw, a_uw, k_uw);
+  for (int i = tid; i < H; i += kPilThreads) pil_axis_coeffs(h4, H, i, kuh, a_uh, k_uh);
+  __syncthreads();
+  const uint8_t* img = src + (size_t)b * H * W * 3;
+  uint8_t* o = dst + (size_t)b * H * W * 3;
+  for (int it = tid; it < H * w4; it += kPilThreads) {  // H x W -> H x w4
+    const int y = it / w4, xx = it - y * w4;
+    const PilAxis ax = a_dw[xx];
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+    const uint8_t* p = img + ((size_t)y * W + ax.xmin) * 3;
+    for (int x = 0; x < ax.n; ++x) {
+      const int c = k_dw[ax.off + x];
+      s0 += p[3 * x] * c; s1 += p[3 * x + 1] * c; s2 += p[3 * x + 2] * c;
+    }
+    uint8_t* q = t_a + (size_t)it * 3;
+    q[0] = pil_clip8(s0); q[1] = pil_clip8(s1); q[2] = pil_clip8(s2);
+  }
+  __syncthreads();
+  for (int it = tid; it < h4 * w4; it += kPilThreads) {  // H x w4 -> h4 x w4
+    const int yy = it / w4, x = it - yy * w4;
+    const PilAxis ax = a_dh[yy];
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+    for (int y = 0; y < ax.n; ++y) {
+      const int c = k_dh[ax.off + y];
+      const uint8_t* p = t_a + ((size_t)(ax.xmin + y) * w4 + x) * 3;
+      s0 += p[0] * c; s1 += p[1] * c; s2 += p[2] * c;
+    }
+    uint8_t* q = t_s + (size_t)it * 3;
+    q[0] = pil_clip8(s0); q[1] = pil_clip8(s1); q[2] = pil_clip8(s2);
+  }
+  __syncthreads();
+  for (int it = tid; it < h4 * W; it += kPilThreads) {  // h4 x w4 -> h4 x W
+    const int y = it / W, xx = it - y * W;
+    const PilAxis ax = a_uw[xx];
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+    const uint8_t* p = t_s + ((size_t)y * w4 + ax.xmin) * 3;
+    for (int x = 0; x < ax.n; ++x) {
+      const int c = k_uw[ax.off + x];
+      s0 += p[3 * x] * c; s1 += p[3 * x + 1] * c; s2 += p[3 * x + 2] * c;
+    }
+    uint8_t* q = t_b + (size_t)it * 3;
+    q[0] = pil_clip8(s0); q[1] = pil_clip8(s1); q[2] = pil_clip8(s2);
+  }
+  __syncthreads();
+  for (int it = tid; it < H * W; it += kPilThreads) {  // h4 x W -> H x W
+    const int yy = it / W, x = it - yy * W;
+    const PilAxis ax = a_uh[yy];
+    int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+    for (int y = 0; y < ax.n; ++y) {
+      const int c = k_uh[ax.off + y];
+      const uint8_t* p = t_b + ((size_t)(ax.xmin + y) * W + x) * 3;
+      s0 += p[0] * c; s1 += p[1] * c; s2 += p[2] * c;
+    }
+    uint8_t* q = o + (size_t)it * 3;
+    q[0] = pil_clip8(s0); q[1] = pil_clip8(s1); q[2] = pil_clip8(s2);
+  }
+}
+
+static size_t pil_smem_bytes(int H, int W) {
+  const int h4 = H / 4, w4 = W / 4;
+  const size_t tabs = (size_t)(w4 + h4 + W + H) * sizeof(PilAxis) +
+                      ((size_t)w4 * pil_ksize(W, w4) + (size_t)h4 * pil_ksize(H, h4) + (size_t)W * pil_ksize(w4, W) +
+                       (size_t)H * pil_ksize(h4, H)) * sizeof(int);
+  return tabs + (size_t)H * w4 * 3 + (size_t)h4 * w4 * 3 + (size_t)h4 * W * 3 + 16;
+}
+
 // np.array(img * 255.0, dtype=np.uint8) of random_pyblur / median_blur / bilateral_blur (degradations.py:353-366):
 // fp32 product, truncation toward zero.
 __global__ void gt_to_u8_kernel(const float* __restrict__ f, uint8_t* __restrict__ u, size_t n) {
@@ -634,23 +780,23 @@ __global__ void gt_to_u8_kernel(const float* __restrict__ f, uint8_t* __restrict
 
 using namespace b200ir;
 
-extern "C" int b200ir_degrade_full_masked(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
-                                          const b200ir_degrade_crop* crops, const float* noise, int lr_wmax, int lr_hmax,
-                                          const uint8_t* mask, float* out, float* lr_out, int B, int H, int W, int bgr2rgb,
-                                          void* stream);
+extern "C" int b200ir_degrade_full_ex(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
+                                      const b200ir_degrade_crop* crops, const float* noise, int lr_wmax, int lr_hmax,
+                                      const uint8_t* mask, uint8_t* bicubic_scratch, float* out, float* lr_out, int B, int H,
+                                      int W, int bgr2rgb, void* stream);
 
 extern "C" int b200ir_degrade_full(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
                                    const b200ir_degrade_crop* crops,
                                    const float* noise, int lr_wmax, int lr_hmax, float* out, float* lr_out, int B, int H,
                                    int W, int bgr2rgb, void* stream) {
-  return b200ir_degrade_full_masked(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, nullptr, out, lr_out, B, H, W,
-                                    bgr2rgb, stream);
+  return b200ir_degrade_full_ex(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, nullptr, nullptr, out, lr_out, B, H, W,
+                                bgr2rgb, stream);
 }
 
-extern "C" int b200ir_degrade_full_masked(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
-                                          const b200ir_degrade_crop* crops, const float* noise, int lr_wmax, int lr_hmax,
-                                          const uint8_t* mask, float* out, float* lr_out, int B, int H, int W, int bgr2rgb,
-                                          void* stream) {
+extern "C" int b200ir_degrade_full_ex(uint8_t* gt, const float* gt_f32, const double* taps, int kmax,
+                                      const b200ir_degrade_crop* crops, const float* noise, int lr_wmax, int lr_hmax,
+                                      const uint8_t* mask, uint8_t* bicubic_scratch, float* out, float* lr_out, int B, int H,
+                                      int W, int bgr2rgb, void* stream) {
   B200IR_REQUIRE(gt && taps && crops && out, "degrade_full: null pointer");
   B200IR_REQUIRE(B > 0 && H > 1 && W > 1 && kmax > 0 && (kmax & 1) && lr_wmax > 0 && lr_hmax > 0,
                  "degrade_full: bad sizes (kmax must be odd)");
@@ -666,19 +812,28 @@ extern "C" int b200ir_degrade_full_masked(uint8_t* gt, const float* gt_f32, cons
     gt_to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gt_f32, gt, n);
     if (check_launch("degrade_full(gt -> uint8)")) return 1;
   }
+  if (bicubic_scratch != nullptr) {  // crops of the 'bicubic' kind (blur_mode 5): Pillow round trip of the uint8 image
+    B200IR_REQUIRE(H >= 8 && W >= 8, "degrade_full: the bicubic kind needs an image of at least 8x8");
+    const size_t psm = pil_smem_bytes(H, W);
+    B200IR_REQUIRE(psm <= (size_t)smem_optin, "degrade_full: bicubic intermediates of a %dx%d image do not fit shared memory", H, W);
+    cudaFuncSetAttribute(pil_bicubic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+    pil_bicubic_kernel<<<B, kPilThreads, psm, st>>>(gt, bicubic_scratch, crops, H, W);
+    if (check_launch("degrade_full(bicubic)")) return 1;
+  }
   const size_t base = df_layout(kmax, lr_wmax, lr_hmax, H, W, false).total;
   const size_t staged = df_layout(kmax, lr_wmax, lr_hmax, H, W, true).total;
   B200IR_REQUIRE(base <= (size_t)smem_optin, "degrade_full: low-resolution image %dx%d does not fit shared memory",
                  lr_wmax, lr_hmax);
-  const bool stage = staged <= (size_t)smem_optin && (H * W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(gt) & 15) == 0;
+  const bool stage = staged <= (size_t)smem_optin && (H * W * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(gt) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(bicubic_scratch) & 15) == 0;
   if (stage) {
     cudaFuncSetAttribute(degrade_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged);
     degrade_full_kernel<true><<<B, kDfThreads, staged, st>>>(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
-                                                            H, W, bgr2rgb, mask);
+                                                            H, W, bgr2rgb, mask, bicubic_scratch);
   } else {
     cudaFuncSetAttribute(degrade_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
     degrade_full_kernel<false><<<B, kDfThreads, base, st>>>(gt, gt_f32, taps, kmax, crops, noise, lr_wmax, lr_hmax, out, lr_out,
-                                                           H, W, bgr2rgb, mask);
+                                                           H, W, bgr2rgb, mask, bicubic_scratch);
   }
   return check_launch("degrade_full");
 }

@@ -277,7 +277,7 @@ def random_degradation_params(B, H, W, downsample_range=(4, 12), noise_range=(0,
 # reference run draw for draw.
 FILTER2D_KINDS = ('iso', 'aniso', 'generalized_iso', 'generalized_aniso', 'plateau_iso', 'plateau_aniso', 'motion',
                   'average')
-UNSUPPORTED_KINDS = ('pyblur_motion', 'random_cover', 'bicubic')
+UNSUPPORTED_KINDS = ('pyblur_motion', 'random_cover')     # undefined in the reference itself (RandomMotion / RandomCover)
 
 
 def mesh_axis(kernel_size):
@@ -365,7 +365,8 @@ def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=
                         np_random=np.random, betag_range=(0.5, 8), betap_range=(0.5, 8)):
     """The kernel random_mixed_kernels would apply (degradations.py:419-523), drawn with the same calls in the same
     order.  Returns (blur_mode, kernel, description): blur_mode 2 = cv2.filter2D kinds, 1 = 'pyblur', 3 = 'median'
-    (kernel: zeros, only its size is used), 4 = 'bilateral' (kernel: the space weights; description carries sigma)."""
+    (kernel: zeros, only its size is used), 4 = 'bilateral' (kernel: the space weights; description carries sigma), 5 = 'bicubic'
+    (kernel unused)."""
     import random as _random
     py_random = py_random or _random
     kind = py_random.choices(kernel_list, kernel_prob)[0]
@@ -407,12 +408,14 @@ def random_mixed_kernel(kernel_list, kernel_prob, kernel_size=21, sigma_x_range=
     elif kind == 'bilateral':       # bilateral_blur (degradations.py:358-361): sigma = random.randint(150, 250)
         sigma = py_random.randint(150, 250)
         return 4, bilateral_space_kernel(kernel_size, sigma), ('bilateral', kernel_size, sigma)
+    elif kind == 'bicubic':         # bicubic (degradations.py:379-385): Pillow x1/4 and back, evaluated on the device
+        return 5, np.zeros((kernel_size, kernel_size), np.float32), ('bicubic',)
     elif kind in ('pyblur_motion', 'random_cover'):
         raise NotImplementedError(f"blur kind '{kind}' cannot run in the reference either: degradations.py:369-377 calls "
                                   "RandomMotion / RandomCover, which its pyblur package does not define")
     else:
         raise NotImplementedError(f"blur kind '{kind}' has no B200 implementation (supported: "
-                                  f"{FILTER2D_KINDS + ('pyblur', 'median', 'bilateral')})")
+                                  f"{FILTER2D_KINDS + ('pyblur', 'median', 'bilateral', 'bicubic')})")
     if pad_kernel:
         k = _pad_to(k, pad_kernel_size)
     return 2, k, desc
@@ -580,7 +583,8 @@ def pack_degrade_full(modes, kernels, sizes, noise=None, quality=None, jitter=No
         mask_t = torch.as_tensor(np.asarray(masks), dtype=torch.uint8).to(dev).contiguous()
         assert mask_t.dim() == 3 and mask_t.shape[0] == B, 'masks: uint8 [B, H, W]'
     return dict(crops=torch.frombuffer(bytearray(bytes(crops)), dtype=torch.uint8).to(dev),
-                taps=torch.from_numpy(taps).to(dev), kmax=kmax, noise=noise, lr_wmax=lr_wmax, lr_hmax=lr_hmax, n=B, mask=mask_t)
+                taps=torch.from_numpy(taps).to(dev), kmax=kmax, noise=noise, lr_wmax=lr_wmax, lr_hmax=lr_hmax, n=B, mask=mask_t,
+                has_bicubic=any(int(m) == 5 for m in modes))
 
 
 def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, quality=None, jitter=None, gray=None,
@@ -606,13 +610,14 @@ def degrade_full_batch(gt_u8, modes=None, kernels=None, sizes=None, noise=None, 
     if mask_t is not None and tuple(mask_t.shape) != (B, H, W):
         raise ValueError(f'masks must be uint8 [B, H, W] = {(B, H, W)}, got {tuple(mask_t.shape)}')
     out = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
+    scratch = torch.empty(B, H, W, 3, device=dev, dtype=torch.uint8) if pk.get('has_bicubic') else None   # 'bicubic' crops
     lr = torch.zeros(B, pk['lr_hmax'], pk['lr_wmax'], 3, device=dev, dtype=torch.float32) if return_lr else None
     p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)  # noqa: E731
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.lib().b200ir_degrade_full_masked(p(gt_u8), p(gt_f32), p(pk['taps']), pk['kmax'], p(pk['crops']),
-                                                         p(pk['noise']), pk['lr_wmax'], pk['lr_hmax'], p(mask_t), p(out), p(lr),
-                                                         B, H, W, 1 if bgr2rgb else 0, st), 'b200ir_degrade_full')
+        _lib.check(_lib.lib().b200ir_degrade_full_ex(p(gt_u8), p(gt_f32), p(pk['taps']), pk['kmax'], p(pk['crops']),
+                                                     p(pk['noise']), pk['lr_wmax'], pk['lr_hmax'], p(mask_t), p(scratch), p(out),
+                                                     p(lr), B, H, W, 1 if bgr2rgb else 0, st), 'b200ir_degrade_full')
     return (out, lr) if return_lr else out
 
 

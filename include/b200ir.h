@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200IR_ABI_VERSION 3   /* 3: b200ir_degrade_crop.mask_mode (appended), b200ir_degrade_full_masked */
+#define B200IR_ABI_VERSION 3   /* 3: b200ir_degrade_crop.mask_mode (appended), blur_mode 5, b200ir_degrade_full_ex */
 #define B200IR_MAX_TAPS 16
 #define B200IR_MAX_VIEWS 4
 
@@ -551,10 +551,10 @@ int b200ir_degrade(const uint8_t* gt, const double* taps, const int32_t* ksize, 
  * Random draws stay on the host (image_restoration_b200.degradation.sample_params mirrors the reference's order of
  * random / np.random calls); this entry point is deterministic in its arguments.
  * random_mask (:153-187, :299-303; `random_mask: true` in the dataset options) is the mask argument of
- * b200ir_degrade_full_masked: the shapes are drawn on the host with the reference's own calls (random rectangles / halves,
+ * b200ir_degrade_full_ex: the shapes are drawn on the host with the reference's own calls (random rectangles / halves,
  * cv2.line / circle / ellipse), the kernel applies them.
- * Not covered: the 'bicubic' kind; 'pyblur_motion' / 'random_cover' call RandomMotion / RandomCover, which the reference's
- * pyblur package does not define (pyblur/pyblur/__init__.py) -- they raise NameError in the reference itself.
+ * Not covered: 'pyblur_motion' / 'random_cover' call RandomMotion / RandomCover, which the reference's pyblur package does
+ * not define (pyblur/pyblur/__init__.py) -- they raise NameError in the reference itself.
  */
 typedef struct b200ir_degrade_crop {
   int32_t blur_mode;    /* 0 none; 1 'pyblur': scipy convolve2d on the uint8 image, fill 255, truncated to uint8;
@@ -563,7 +563,10 @@ typedef struct b200ir_degrade_crop {
                            >= 11x11, so its result differs in the last bits);
                            3 'median': cv2.medianBlur(uint8 image, ksize), BORDER_REPLICATE (degradations.py:353-355);
                            4 'bilateral': cv2.bilateralFilter(uint8 image, ksize, sigma, sigma) (degradations.py:358-361);
-                             taps = the space weights exp(-r^2 / (2 sigma^2)) inside the radius, zero outside */
+                             taps = the space weights exp(-r^2 / (2 sigma^2)) inside the radius, zero outside;
+                           5 'bicubic': torchvision Resize((h // 4, w // 4), BICUBIC) and back on the PIL image
+                             (degradations.py:379-385) = Pillow's 8-bit ImagingResample twice, restated as the same integer
+                             arithmetic (needs bicubic_scratch of b200ir_degrade_full_ex; taps unused) */
   int32_t ksize;        /* odd extent of the kernel inside its kmax x kmax block */
   int32_t blur_f64;     /* blur_mode 1 only: 1 = the reference's convolve2d ran in float64 (box / disk / line kernels are
                            float64 under NumPy 2), 0 = in float32 (psf kernels).  The kernel reproduces scipy's summation
@@ -578,7 +581,7 @@ typedef struct b200ir_degrade_crop {
   float cj_factor[4];    /* the factor of each step as float32 (hue: the shift) */
   float cj_one_minus[4]; /* (float)(1.0 - factor), the second blend weight as torchvision's _blend evaluates it */
   int32_t mask_mode;     /* random_mask (ffhq_degradation_dataset.py:153-187, :299-303), needs the mask argument of
-                            b200ir_degrade_full_masked: 0 off; 1 regular / half masks: masked pixels become 1.0; 2 irregular
+                            b200ir_degrade_full_ex: 0 off; 1 regular / half masks: masked pixels become 1.0; 2 irregular
                             mask: the whole image goes through np.array(img * 255.0, uint8) (truncation) and the drawn pixels
                             become 255 */
 } b200ir_degrade_crop;
@@ -594,10 +597,12 @@ typedef struct b200ir_degrade_crop {
 int b200ir_degrade_full(uint8_t* gt, const float* gt_f32, const double* taps, int kmax, const b200ir_degrade_crop* crops,
                         const float* noise, int lr_wmax, int lr_hmax, float* out, float* lr_out, int B, int H, int W,
                         int bgr2rgb, void* stream);
-/* The same with random_mask: mask uint8 [B][H][W] (non-zero = masked; rows of crops with mask_mode 0 are ignored), or NULL. */
-int b200ir_degrade_full_masked(uint8_t* gt, const float* gt_f32, const double* taps, int kmax, const b200ir_degrade_crop* crops,
-                               const float* noise, int lr_wmax, int lr_hmax, const uint8_t* mask, float* out, float* lr_out,
-                               int B, int H, int W, int bgr2rgb, void* stream);
+/* The same with random_mask and the 'bicubic' kind: mask uint8 [B][H][W] (non-zero = masked; rows of crops with mask_mode 0
+ * are ignored), or NULL; bicubic_scratch uint8 [B][H][W][3], caller-owned, required when any crop has blur_mode 5 (the Pillow
+ * round trip of those crops is written there by a first launch and read by the main one), else NULL. */
+int b200ir_degrade_full_ex(uint8_t* gt, const float* gt_f32, const double* taps, int kmax, const b200ir_degrade_crop* crops,
+                           const float* noise, int lr_wmax, int lr_hmax, const uint8_t* mask, uint8_t* bicubic_scratch,
+                           float* out, float* lr_out, int B, int H, int W, int bgr2rgb, void* stream);
 
 #ifdef __cplusplus
 }

@@ -189,6 +189,14 @@ def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, g
         blur = (bilateral_u8(gt_u8, k, bilateral_sigma) if exact_blur
                 else cv2.bilateralFilter(gt_u8, k, bilateral_sigma, bilateral_sigma))
         img = blur.astype(np.float32) / np.float32(255.)
+    elif mode == 5:     # bicubic (degradations.py:379-385): Pillow round trip of np.array(img * 255.0, uint8)
+        if exact_blur:
+            blur = pil_bicubic_roundtrip(gt_u8)
+        else:
+            from PIL import Image
+            pil = Image.fromarray(gt_u8)
+            blur = np.asarray(pil.resize((W // 4, H // 4), Image.BICUBIC).resize((W, H), Image.BICUBIC))
+        img = np.array(blur, dtype=np.float32) / 255.0
     lr = cv2.resize(img, tuple(lr_size), interpolation=cv2.INTER_LINEAR)
     if noise is not None:
         lr = np.clip(lr + noise, 0, 1)
@@ -206,6 +214,73 @@ def lq_image(gt_u8, mode, kernel, lr_size, noise=None, quality=0, jitter=None, g
     if cj:
         up = color_jitter_pt(up, cj)
     return up, lr
+
+
+# ---- 'bicubic' kind (degradations.py:379-385): Pillow's 8-bit ImagingResample (src/libImaging/Resample.c) restated.
+_PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def _pil_bicubic_filter(x):
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_bicubic_tables(in_size, out_size):
+    """precompute_coeffs + normalize_coeffs_8bpc for the bicubic filter (support 2): per output index (xmin, n) and the
+    fixed-point coefficients (int)(+-0.5 + w / sum(w) * 2^22); all in double, in Pillow's order of operations."""
+    import math
+    scale = float(np.float32(in_size) - np.float32(0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int64)
+    kk = np.zeros((out_size, ksize), np.int64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [_pil_bicubic_filter((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x, v in enumerate(w):
+            if ww != 0.0:
+                v = v / ww
+            kk[xx, x] = int(-0.5 + v * (1 << _PIL_PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << _PIL_PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def _pil_resample_axis(img, out_size, axis):
+    bounds, kk = pil_bicubic_tables(img.shape[axis], out_size)
+    src = np.moveaxis(img, axis, 0).astype(np.int64)
+    out = np.zeros((out_size,) + src.shape[1:], np.int64)
+    for xx in range(out_size):
+        xmin, n = bounds[xx]
+        acc = np.full(src.shape[1:], 1 << (_PIL_PRECISION_BITS - 1), np.int64)
+        for x in range(n):
+            acc = acc + src[xmin + x] * int(kk[xx, x])
+        out[xx] = np.clip(acc >> _PIL_PRECISION_BITS, 0, 255)
+    return np.moveaxis(out, 0, axis).astype(np.uint8)
+
+
+def pil_bicubic_resize(img_u8, h, w):
+    """Image.fromarray(img).resize((w, h), BICUBIC) on a uint8 HWC image: horizontal pass first, then vertical."""
+    t = _pil_resample_axis(img_u8, w, 1) if w != img_u8.shape[1] else img_u8
+    return _pil_resample_axis(t, h, 0) if h != img_u8.shape[0] else t
+
+
+def pil_bicubic_roundtrip(img_u8):
+    """degradations.bicubic on the uint8 image: x 1/4 and back to the original size."""
+    h, w = img_u8.shape[:2]
+    return pil_bicubic_resize(pil_bicubic_resize(img_u8, h // 4, w // 4), h, w)
 
 
 def apply_random_mask(up, mask_mode, mask):

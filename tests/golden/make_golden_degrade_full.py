@@ -74,6 +74,10 @@ def main():
         make(deg, DS, 'degrade_full_mask.npz', 64, 192, 14, 5000, np.random.default_rng(11), float_gt=False,
              opt=dict(OPT, random_mask=True))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'bicubic':  # the 'bicubic' kind (Pillow x1/4 and back), float GT off the 8-bit grid
+        make(deg, DS, 'degrade_full_bicubic.npz', 64, 192, 8, 7000, np.random.default_rng(13), float_gt=True,
+             opt=dict(OPT, kernel_list=['bicubic', 'iso'], kernel_prob=[0.75, 0.25]))
+        return
     make(deg, DS, 'degrade_full.npz', 128, 384, 20, 1000, np.random.default_rng(7), float_gt=False)
     # GT images that are not on the 8-bit grid: the dataset resizes every image to the network size (:230)
     make(deg, DS, 'degrade_full_floatgt.npz', 64, 192, 12, 3000, np.random.default_rng(9), float_gt=True)

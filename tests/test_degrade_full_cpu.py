@@ -45,7 +45,7 @@ def test_golden_covers_every_stage():
     assert g['gray'].any() and (g['jitter'] != 0).any() and (g['quality'] > 0).all() and (g['cj_n'] == 4).sum() >= 4
 
 
-@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz'])
+@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz', 'degrade_full_bicubic.npz'])
 def test_oracle_reproduces_golden_reference_outputs(fname):
     g = np.load(os.path.join(os.path.dirname(GOLD), fname))
     for i in range(len(g['seeds'])):
@@ -57,7 +57,7 @@ def test_oracle_reproduces_golden_reference_outputs(fname):
         exact, _ = dfo.degrade_full(c['gt'], c['mode'], c['kernel'], c['lr_size'], c['noise'], c['quality'], c['jitter'],
                                     c['gray'], exact_blur=True, bilateral_sigma=c['bsigma'], cj=c['cj'])
         diff = np.abs(to_u8(exact) - g['out_u8'][i].astype(np.int32))
-        if c['mode'] in (1, 3):  # pyblur: the explicit summation tree is scipy's; median: integer -> identical
+        if c['mode'] in (1, 3, 5):  # pyblur: the explicit summation tree is scipy's; median / bicubic: integer -> identical
             assert diff.max() == 0, (i, diff.max())
         else:
             assert (diff > 0).mean() < 0.02 and diff.max() <= 6, (i, str(g['kinds'][i]), (diff > 0).mean(), diff.max())
@@ -118,8 +118,7 @@ def test_kernel_builders_known_answers():
     assert k.shape == (21, 21) and abs(k.sum() - 1) < 1e-12 and k.argmax() == 10 * 21 + 10 and np.allclose(k, k.T)
     assert np.count_nonzero(D.motion_kernel(7, True)[3]) == 7 and np.count_nonzero(D.motion_kernel(7, False)[:, 3]) == 7
     assert D.average_kernel(5).dtype == np.float32 and np.allclose(D.average_kernel(5), 0.04)
-    with pytest.raises(NotImplementedError):
-        D.random_mixed_kernel(['bicubic'], [1.0], 21)
+    assert D.random_mixed_kernel(['bicubic'], [1.0], 21)[0] == 5
     for kind in ('pyblur_motion', 'random_cover'):      # RandomMotion / RandomCover are undefined in the reference's pyblur
         with pytest.raises(NotImplementedError):
             D.random_mixed_kernel([kind], [1.0], 21)
@@ -231,3 +230,23 @@ def test_random_mask_draws_equal_reference():
         assert np.array_equal(got, np.asarray(ref, dtype=np.float32)), (seed, mode)
         seen.add((mode, bool(mask.any())))
     assert {m for m, _ in seen} == {1, 2}
+
+
+def test_pil_bicubic_restatement_is_bit_exact_against_pillow():
+    """oracle.pil_bicubic_resize (Pillow's 8-bit ImagingResample restated: double-precision coefficient tables, 22-bit fixed
+    point, horizontal pass first) against PIL itself, down- and up-scaling, odd sizes included; and the whole 'bicubic' kind
+    against the reference's degradations.bicubic."""
+    from PIL import Image
+    rng = np.random.default_rng(2)
+    for (h, w) in [(128, 384), (64, 192), (50, 70), (214, 214), (37, 91)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        small = dfo.pil_bicubic_resize(img, h // 4, w // 4)
+        assert np.array_equal(small, np.asarray(Image.fromarray(img).resize((w // 4, h // 4), Image.BICUBIC)))
+        back = dfo.pil_bicubic_resize(small, h, w)
+        assert np.array_equal(back, np.asarray(Image.fromarray(small).resize((w, h), Image.BICUBIC)))
+    if ref_import.available():
+        deg, _ = ref_import.load_reference_degradations()
+        img = rng.random((64, 192, 3)).astype(np.float32)
+        ref = deg.bicubic(img)
+        got = np.array(dfo.pil_bicubic_roundtrip(np.array(img * 255.0, dtype=np.uint8)), dtype=np.float32) / 255.0
+        assert np.array_equal(got, ref)

@@ -47,7 +47,7 @@ def golden_batch(fname='degrade_full.npz'):
     return g, kernels, sizes, cj
 
 
-@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz'])
+@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz', 'degrade_full_bicubic.npz'])
 def test_golden_reference_outputs(fname):
     """degrade_full_floatgt.npz: GT images off the 8-bit grid (the dataset's cv2.resize), passed as float32."""
     g, kernels, sizes, cj = golden_batch(fname)
@@ -58,7 +58,7 @@ def test_golden_reference_outputs(fname):
         diff = np.abs(to_u8(out[i]) - g['out_u8'][i].astype(np.int32))
         if any(op == 1 for op, _ in cj[i]):   # contrast: torch's fp32 mean of the gray image vs the kernel's fp64 sum
             assert diff.max() <= 1 and (diff > 0).mean() < 1e-3, (i, (diff > 0).mean(), diff.max())
-        elif int(g['modes'][i]) in (1, 3):    # pyblur / median crops: every stage restated bit-exactly -> the reference's output
+        elif int(g['modes'][i]) in (1, 3, 5):  # pyblur / median / bicubic crops: every stage restated bit-exactly -> the reference's output
             assert diff.max() == 0, (i, str(g['kinds'][i]), (diff > 0).mean(), diff.max())
         else:                             # filter2D crops: OpenCV's DFT blur vs the direct sum; bilateral: fp32 sums inside
                                           # OpenCV's SIMD code (see the CPU tests)
@@ -67,7 +67,7 @@ def test_golden_reference_outputs(fname):
     assert exact >= len(kernels) // 2, exact
 
 
-@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz'])
+@pytest.mark.parametrize('fname', ['degrade_full.npz', 'degrade_full_floatgt.npz', 'degrade_full_bicubic.npz'])
 def test_golden_against_oracle_stage_by_stage(fname):
     g, kernels, sizes, cj = golden_batch(fname)
     out, lr = run_gpu(g['gt'], [int(m) for m in g['modes']], kernels, sizes, g['noise'], [int(q) for q in g['quality']],
@@ -237,3 +237,27 @@ def test_random_mask_through_synthesize_pairs():
         if prm['mask_modes'][b] == 1:
             keep = prm['masks'][b] == 0
             assert np.array_equal(lq[b][:, keep], plain[b][:, keep]), b
+
+
+@pytest.mark.parametrize('H,W', [(128, 384), (64, 192), (40, 72)])
+def test_bicubic_kind_uint8_gt(H, W):
+    """'bicubic' crops mixed with other kinds on a uint8 GT batch: identical to the oracle (Pillow's integer arithmetic), the
+    caller's GT tensor is left untouched (the round trip goes through the scratch buffer)."""
+    from image_restoration_b200 import degradation as D
+    rng = np.random.RandomState(H + W)
+    B = 5
+    gt = rng.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
+    modes = [5, 0, 5, 2, 5]
+    kernels = [np.zeros((21, 21), np.float32), np.zeros((21, 21), np.float32), np.zeros((21, 21), np.float32),
+               D.bivariate_Gaussian(21, 2.0, 2.0, 0, isotropic=True).astype(np.float64), np.zeros((21, 21), np.float32)]
+    sizes = [(W // 4, H // 4), (W // 5, H // 5), (W // 7, H // 7), (W // 4, H // 4), (W // 9 + 2, H // 9 + 2)]
+    gt_d = torch.from_numpy(gt).cuda()
+    out, lr = D.degrade_full_batch(gt_d, modes, kernels, sizes, quality=[0, 0, 60, 0, 0], return_lr=True)
+    torch.cuda.synchronize()
+    assert torch.equal(gt_d.cpu(), torch.from_numpy(gt))
+    out = out.cpu().numpy()
+    for b in range(B):
+        ref, ref_lr = dfo.degrade_full(gt[b], modes[b], kernels[b], sizes[b], quality=[0, 0, 60, 0, 0][b], exact_blur=True)
+        lw, lh = sizes[b]
+        assert np.array_equal(lr[b, :lh, :lw].cpu().numpy(), ref_lr), (b, modes[b])
+        assert np.array_equal(out[b], ref), (b, modes[b])
