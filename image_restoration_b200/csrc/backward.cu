@@ -117,6 +117,76 @@ __global__ void __launch_bounds__(kBwThreads) fir_down2_adjoint_kernel(const uin
   }
 }
 
+// Tiled variant for the large tensors of the training step: a CTA stages the (8 + 2) x (16 + 2) input pixels x 64 channels its
+// 16 x 32 output tile depends on in shared memory once (the per-pixel kernel above reads every input 16 times through L1 / L2
+// and ran at ~3.3 TB/s of algorithmic traffic on [256, 128, 384, 128]: L2-bandwidth-bound), then every thread produces 16
+// outputs: four 16-byte shared-memory reads, the optional addend, one 16-byte store.  Same expression and rounding per output.
+// GP = channel groups (of 8) per CTA: 8, or 4 for 32-channel tensors (then the tile is twice as wide: all 256 threads busy).
+constexpr int kFdTi = 8;
+template <int GP>
+__global__ void __launch_bounds__(kBwThreads) fir_down2_adjoint_tiled_kernel(const uint4* __restrict__ d, const uint4* __restrict__ add,
+                                                                             uint4* __restrict__ out, int h, int w, int groups,
+                                                                             int chunks) {
+  constexpr int kFdTj = 128 / GP;
+  __shared__ uint4 tile[(kFdTi + 2) * (kFdTj + 2) * GP];
+  const int chunk = blockIdx.x % chunks, tj = blockIdx.x / chunks, ti = blockIdx.y, b = blockIdx.z;
+  const int g0 = chunk * GP, ng = min(GP, groups - g0);
+  const int i0 = ti * kFdTi - 1, j0 = tj * kFdTj - 1;      // input coordinates of tile[0][0]
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const uint4* db = d + (long long)b * h * w * groups + g0;
+  for (int e = threadIdx.x; e < (kFdTi + 2) * (kFdTj + 2) * GP; e += kBwThreads) {
+    const int g = e % GP, pix = e / GP;
+    const int r = pix / (kFdTj + 2), c = pix - r * (kFdTj + 2);
+    const int i = i0 + r, j = j0 + c;
+    tile[e] = (g < ng && i >= 0 && i < h && j >= 0 && j < w) ? __ldg(db + ((long long)i * w + j) * groups + g) : zero;
+  }
+  __syncthreads();
+  const int g = threadIdx.x % GP, xl = threadIdx.x / GP;   // 2 * kFdTj output columns x GP channel groups per output row
+  if (g >= ng) return;
+  const int X = tj * 2 * kFdTj + xl;
+  if (X >= 2 * w) return;
+  const int jl = (xl >> 1) + 1, njl = (xl & 1) ? jl + 1 : jl - 1;
+  const long long img = (long long)b * 4 * h * w * groups;
+#pragma unroll 4
+  for (int yl = 0; yl < 2 * kFdTi; ++yl) {
+    const int Y = ti * 2 * kFdTi + yl;
+    if (Y >= 2 * h) break;
+    const int il = (yl >> 1) + 1, nil = (yl & 1) ? il + 1 : il - 1;
+    const uint4 q11 = tile[(il * (kFdTj + 2) + jl) * GP + g], qn1 = tile[(nil * (kFdTj + 2) + jl) * GP + g];
+    const uint4 q1n = tile[(il * (kFdTj + 2) + njl) * GP + g], qnn = tile[(nil * (kFdTj + 2) + njl) * GP + g];
+    const long long idx = img + ((long long)Y * 2 * w + X) * groups + g0 + g;
+    float acc[8];
+    if (add) {
+      const uint4 q = __ldcs(add + idx);
+      const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(hq[k]);
+        acc[2 * k] = f.x;
+        acc[2 * k + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    }
+    const __half2* h11 = reinterpret_cast<const __half2*>(&q11);
+    const __half2* hn1 = reinterpret_cast<const __half2*>(&qn1);
+    const __half2* h1n = reinterpret_cast<const __half2*>(&q1n);
+    const __half2* hnn = reinterpret_cast<const __half2*>(&qnn);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = __half22float2(h11[k]), bq = __half22float2(hn1[k]), c = __half22float2(h1n[k]), e = __half22float2(hnn[k]);
+      acc[2 * k] += (9.f * a.x + 3.f * (bq.x + c.x) + e.x) * (1.f / 64.f);
+      acc[2 * k + 1] += (9.f * a.y + 3.f * (bq.y + c.y) + e.y) * (1.f / 64.f);
+    }
+    uint4 q;
+    __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hq[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+    __stcs(out + idx, q);
+  }
+}
+
 // Adjoint of b200ir_bilinear_up2 (F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) of ConvUpLayer,
 // gfpganv1_ocr_arch.py:190): per axis hi[2i] = .75 lo[i] + .25 lo[max(i-1, 0)], hi[2i+1] = .75 lo[i] + .25 lo[min(i+1, n-1)],
 // so  dlo[i] = sum_t (.25, .75, .75, .25)[t] * dhi[clamp(2i - 1 + t, 0, 2n - 1)]  (the clamp returns the border rows'
@@ -304,6 +374,19 @@ extern "C" int b200ir_fir_down2_adjoint(const void* d, const void* add, void* ou
                  "fir_down2_adjoint: bad arguments");
   const int sms = num_sms();
   if (sms == 0) return 1;
+  const int groups = C / 8;
+  if (h >= kFdTi && w >= 32 && B <= 65535 && (h + kFdTi - 1) / kFdTi <= 65535) {   // large levels: shared-memory tiles
+    const int gp = (groups % 8 == 0) ? 8 : 4;
+    const int tj = 128 / gp, chunks = (groups + gp - 1) / gp;
+    const dim3 grid((unsigned)(((w + tj - 1) / tj) * chunks), (unsigned)((h + kFdTi - 1) / kFdTi), (unsigned)B);
+    if (gp == 8)
+      fir_down2_adjoint_tiled_kernel<8><<<grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+          (const uint4*)d, (const uint4*)add, (uint4*)out, h, w, groups, chunks);
+    else
+      fir_down2_adjoint_tiled_kernel<4><<<grid, kBwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+          (const uint4*)d, (const uint4*)add, (uint4*)out, h, w, groups, chunks);
+    return check_launch("fir_down2_adjoint");
+  }
   const unsigned row_elems = (unsigned)(2 * w) * (unsigned)(C / 8);
   const long long rows = (long long)B * 2 * h;
   const dim3 grid((row_elems + kBwThreads - 1) / kBwThreads, (unsigned)(rows < 65535 ? rows : 65535));
