@@ -49,7 +49,10 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}')
         objs.append(obj)
-    cmd = [nvcc, '-shared', '-o', LIB, *objs, '-lcudart_static', '-ldl', '-lrt', '-lpthread']
+    # shared CUDA runtime: the process already holds torch's libcudart.so.12 (one runtime instance instead of a second, static
+    # one inside this library); the rpath covers a host program that loads the library without torch
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), 'lib64')
+    cmd = [nvcc, '-shared', '--cudart', 'shared', '-o', LIB, *objs, '-Xlinker', f'-rpath={cuda_lib}', '-ldl', '-lrt', '-lpthread']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
