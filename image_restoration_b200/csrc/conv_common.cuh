@@ -101,6 +101,11 @@ struct alignas(64) ConvParams {
   int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
   int epi_pipe;      // fast epilogues without global operands: keep the next chunk's TMEM load in flight (host heuristic)
   int w_img_rows;    // per-image weights: rows of the weight matrix per image (= cout), 0 = one matrix for all images
+  // CTA pairs (conv_igemm_kernel<.., kPair = true>): two CTAs share one 256 x block_n MMA per K step
+  CUtensorMap tmap_b2;  // weight tile of block_n / 2 rows (each CTA of a pair stages half of B)
+  int pair;             // 1: launched as clusters of two
+  int pair_tiles;       // ceil(M-tiles / 2) * tiles_n work items of a pair
+  uint32_t idesc_pair;  // instruction descriptor with M = 256
 };
 
 struct TileCoord {
@@ -792,6 +797,7 @@ __device__ __forceinline__ KernelSmem carve_smem(uint8_t* smem_raw, uint32_t dat
   return s;
 }
 
+template <bool kPair = false>
 __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const KernelSmem& s, int nslots, int warp) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < nslots; ++i) {
@@ -800,7 +806,7 @@ __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const K
     }
     for (int i = 0; i < p.acc_stages; ++i) {
       mbar_init(&s.tmem_full[i], 1);
-      mbar_init(&s.tmem_empty[i], 128);
+      mbar_init(&s.tmem_empty[i], kPair ? 256 : 128);   // pair: the epilogue threads of both CTAs release the leader's MMA
     }
     mbar_init(s.w_bar, 1);
     fence_barrier_init();
@@ -809,9 +815,15 @@ __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const K
   if (p.bias_c <= kMaxBias || p.bias == nullptr)
     for (int i = threadIdx.x; i < min(p.bias_c, kMaxBias); i += blockDim.x)
       s.bias[i] = (p.bias != nullptr) ? p.bias[i] * p.act_gain : 0.f;
+  if (kPair) cluster_sync_all();  // the peer's barriers exist before any remote arrive, multicast commit or pair TMA load
   if (warp == 1) {
-    tmem_alloc(s.tmem_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(s.tmem_slot, p.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(s.tmem_slot, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -819,37 +831,55 @@ __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const K
   return *s.tmem_slot;
 }
 
+template <bool kPair = false>
 __device__ __forceinline__ void kernel_epilogue(const ConvParams& p, uint32_t tmem_base, int warp) {
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal it or read its tiles
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (kPair) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
 // ================================================================================================ generic tiles
-template <int kBlockK, int EPI>
+// kPair: clusters of two CTAs (the two SMs of a TPC) work on two vertically adjacent M-tiles of the same N-tile with ONE
+// tcgen05.mma.cta_group::2 (M = 256) per K step, issued by the leader (cluster rank 0): each CTA stages its own 128 A rows and
+// half of the B tile, so the weight traffic per CTA (L2 -> shared memory and shared memory -> tensor core) halves -- the
+// operand fetch, not the tensor pipe, paces the N = 128 layers.  Barriers: the leader's full barrier counts
+// the bytes of both CTAs' loads, its commits arrive on both CTAs' empty / accumulator-full barriers, and the epilogue threads
+// of both CTAs release the leader's accumulator-empty barrier.  Weights are never resident in this variant.
+template <int kBlockK, int EPI, bool kPair = false>
 __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kGroups = EpiCfg<EPI>::kGroups;
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t row_bytes = kBlockK * 2;
   constexpr uint32_t a_bytes = kBlockM * row_bytes;
   constexpr int k_steps = kBlockK / 16;
-  const uint32_t b_bytes = p.block_n * row_bytes;
-  const uint32_t stage_bytes = p.b_resident ? a_bytes : a_bytes + b_bytes;
-  const uint32_t w_bytes = p.b_resident ? p.num_taps * p.k_chunks * b_bytes : 0u;  // resident weights sit in front
+  const uint32_t b_bytes = (kPair ? p.block_n / 2 : p.block_n) * row_bytes;
+  const uint32_t stage_bytes = (!kPair && p.b_resident) ? a_bytes : a_bytes + b_bytes;
+  const uint32_t w_bytes = (!kPair && p.b_resident) ? p.num_taps * p.k_chunks * b_bytes : 0u;  // resident weights sit in front
   const KernelSmem s = carve_smem(smem_raw, w_bytes + p.stages * stage_bytes);
   uint8_t* const ring = s.base + w_bytes;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t tmem_base = kernel_prologue(p, s, p.stages, warp);
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  // work items: tiles, or (pair of M-tiles, N-tile) items of which this CTA takes the M-tile of its rank
+  const int item0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_items = kPair ? p.pair_tiles : p.num_tiles;
+  auto tile_of = [&](int item) {
+    return kPair ? (2 * (item / p.tiles_n) + (int)rank) * p.tiles_n + item % p.tiles_n : item;
+  };
+  const uint32_t tmem_base = kernel_prologue<kPair>(p, s, p.stages, warp);
   if (warp == 0) {
     // ---------------- TMA producer
     if (lane == 0) {
       for (int v = 0; v < B200IR_MAX_VIEWS; ++v) tma_prefetch_desc(&p.tmap_a[v]);
       tma_prefetch_desc(&p.tmap_b);
-      if (p.b_resident) {  // one N-tile: every CTA needs the same weights for every tile, load them once
+      if (kPair) tma_prefetch_desc(&p.tmap_b2);
+      if (!kPair && p.b_resident) {  // one N-tile: every CTA needs the same weights for every tile, load them once
         mbar_arrive_expect_tx(s.w_bar, w_bytes);
         for (int kb = 0; kb < p.num_taps * p.k_chunks; ++kb)
           tma_load_2d(s.base + kb * b_bytes, &p.tmap_b, s.w_bar, kb * kBlockK, 0);
@@ -858,7 +888,8 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int item = item0; item < num_items; item += item_step) {
+      const int tile = tile_of(item);
       const TileCoord t = decode_tile(p, tile);
       const uint32_t mask = p.tap_mask[(tile % p.tiles_n) & 7];
       int kb = 0;
@@ -874,9 +905,17 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
           mbar_wait_parked(&s.empty_bar[stage], phase ^ 1u);
           if (elect_one()) {
             uint8_t* sa = ring + stage * stage_bytes;
-            mbar_arrive_expect_tx(&s.full_bar[stage], stage_bytes);
-            tma_load_4d(sa, &p.tmap_a[view], &s.full_bar[stage], kc * kBlockK, cx, cy, t.b0);
-            if (!p.b_resident) tma_load_2d(sa + a_bytes, &p.tmap_b, &s.full_bar[stage], kb * kBlockK, t.n0 + t.b0 * p.w_img_rows);
+            if (kPair) {
+              // the leader's barrier of this stage collects the bytes of both CTAs (its own arrive announces them all)
+              if (rank == 0) mbar_arrive_expect_tx(&s.full_bar[stage], 2 * stage_bytes);
+              const uint32_t bar = mapa_rank(smem_u32(&s.full_bar[stage]), 0);
+              tma_load_4d_pair(sa, &p.tmap_a[view], bar, kc * kBlockK, cx, cy, t.b0);
+              tma_load_2d_pair(sa + a_bytes, &p.tmap_b2, bar, kb * kBlockK, t.n0 + (int)rank * (p.block_n / 2));
+            } else {
+              mbar_arrive_expect_tx(&s.full_bar[stage], stage_bytes);
+              tma_load_4d(sa, &p.tmap_a[view], &s.full_bar[stage], kc * kBlockK, cx, cy, t.b0);
+              if (!p.b_resident) tma_load_2d(sa + a_bytes, &p.tmap_b, &s.full_bar[stage], kb * kBlockK, t.n0 + t.b0 * p.w_img_rows);
+            }
           }
           __syncwarp();
           if (++stage == p.stages) {
@@ -886,20 +925,21 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer
+  } else if (warp == 1 && (!kPair || rank == 0)) {
+    // ---------------- MMA issuer (pair: the leader CTA only)
     const uint32_t hi = desc_hi_word(row_bytes);
     const uint32_t base_lo = smem_u32(ring) >> 4;
     const uint32_t w_lo = smem_u32(s.base) >> 4;
     const uint32_t stage_lo = stage_bytes >> 4;
-    if (p.b_resident) {
+    if (!kPair && p.b_resident) {
       mbar_wait(s.w_bar, 0);
       tc_fence_after();
     }
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int item = item0; item < num_items; item += item_step, ++it) {
+      const int tile = tile_of(item);
       const int acc = it & (p.acc_stages - 1);
       mbar_wait(&s.tmem_empty[acc], ((it >> p.acc_shift) & 1) ^ 1u);
       tc_fence_after();
@@ -911,12 +951,20 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
         if (elect_one()) {
           const uint32_t a_lo = base_lo + stage * stage_lo;
           // resident weights: every tap is executed (no tap mask), so the k-block index is the running kb
-          const uint32_t b_lo = p.b_resident ? w_lo + kb * (b_bytes >> 4) : a_lo + (a_bytes >> 4);
+          const uint32_t b_lo = (!kPair && p.b_resident) ? w_lo + kb * (b_bytes >> 4) : a_lo + (a_bytes >> 4);
+          if (kPair) {
 #pragma unroll
-          for (int k = 0; k < k_steps; ++k)
-            umma_f16(tmem_d, desc64(a_lo + 2 * k, hi), desc64(b_lo + 2 * k, hi), p.idesc, (k > 0 || kb > 0) ? 1u : 0u);
-          umma_commit(&s.empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&s.tmem_full[acc]);
+            for (int k = 0; k < k_steps; ++k)
+              umma_f16_pair(tmem_d, desc64(a_lo + 2 * k, hi), desc64(b_lo + 2 * k, hi), p.idesc_pair, (k > 0 || kb > 0) ? 1u : 0u);
+            umma_commit_pair(&s.empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_pair(&s.tmem_full[acc]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < k_steps; ++k)
+              umma_f16(tmem_d, desc64(a_lo + 2 * k, hi), desc64(b_lo + 2 * k, hi), p.idesc, (k > 0 || kb > 0) ? 1u : 0u);
+            umma_commit(&s.empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit(&s.tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -925,7 +973,7 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
         }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ---------------- epilogue: two groups of 4 warps drain alternate tiles; TMEM lane quarter = warp % 4
     const int q = warp & 3;
     const int group = (warp - 2) >> 2;
@@ -940,8 +988,9 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
     // a group may wait at most one phase ahead on an accumulator's mbarrier, so no more groups than accumulator stages
     // take part (block_n = 256 has two stages: the third group idles there, those layers are main-loop bound anyway)
     const int ngroups = min(kGroups, p.acc_stages);
-    for (int tile = (group < ngroups) ? blockIdx.x + group * gridDim.x : p.num_tiles; tile < p.num_tiles;
-         tile += ngroups * gridDim.x, it += ngroups) {
+    for (int item = (group < ngroups) ? item0 + group * item_step : num_items; item < num_items;
+         item += ngroups * item_step, it += ngroups) {
+      const int tile = tile_of(item);
       const int acc = it & (p.acc_stages - 1);
       const TileCoord t = decode_tile(p, tile);
       const int x = t.x0 + xx, y = t.y0 + yy, b = t.b0 + bi;
@@ -990,10 +1039,11 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
       epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, y, b, t.n0, valid, gain, s_bias, s_dm,
                         g_dm, s_aux, tab_n);
       tc_fence_before();
-      mbar_arrive(&s.tmem_empty[acc]);
+      if (kPair && rank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(&s.tmem_empty[acc]), 0));
+      else mbar_arrive(&s.tmem_empty[acc]);
     }
   }
-  kernel_epilogue(p, tmem_base, warp);
+  kernel_epilogue<kPair>(p, tmem_base, warp);
 }
 
 // ================================================================================================ row mode
@@ -1225,6 +1275,37 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(c
 // ------------------------------------------------------------------------------------------ launch (per EPI)
 // Defined as a template here, explicitly instantiated once per EPI in conv_epi*.cu; conv_igemm.cu calls through
 // launch_conv_variant's extern declarations.
+template <int EPI>
+static int launch_pair(const ConvParams& p, int grid, int smem_bytes, int smem_max, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<64, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e != cudaSuccess) {
+      set_error("conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)EpiCfg<EPI>::kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<64, EPI, true>, p);
+  if (e != cudaSuccess) {
+    set_error("conv_igemm (CTA pairs): %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return check_launch("conv_igemm(pair)");
+}
+
 template <int kBlockK, int EPI, bool ROW>
 static int launch_one(const ConvParams& p, int grid, int smem_bytes, int smem_max, cudaStream_t st) {
   static bool configured = false;
@@ -1260,6 +1341,7 @@ static int launch_one(const ConvParams& p, int grid, int smem_bytes, int smem_ma
 template <int EPI>
 int launch_conv_variant(const ConvParams& p, int block_k, bool row, int grid, int smem_bytes, int smem_max,
                         cudaStream_t st) {
+  if (p.pair && !row && block_k == 64) return launch_pair<EPI>(p, grid, smem_bytes, smem_max, st);
   if (row) {
     if (block_k == 64) return launch_one<64, EPI, true>(p, grid, smem_bytes, smem_max, st);
     if (block_k == 32) return launch_one<32, EPI, true>(p, grid, smem_bytes, smem_max, st);

@@ -379,6 +379,32 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
 
   int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
+  // ---- CTA pairs (cta_group::2): streamed-weight layers with N-tiles of 128 / 256 columns and enough M-tiles for every
+  // pair; B200IR_CTA_PAIR=0 keeps every layer on single CTAs (A/B switch)
+  {
+    static int pair_env = -1;
+    if (pair_env < 0) pair_env = (getenv("B200IR_CTA_PAIR") != nullptr) ? atoi(getenv("B200IR_CTA_PAIR")) : 1;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    if (pair_env && !p.b_resident && p.block_k == 64 && d->block_n >= 128 && d->block_n % 16 == 0 && !d->w_per_image &&
+        d->max_ctas <= 0 && m_tiles >= g_num_sms && g_num_sms >= 2) {
+      const int k_total = d->num_taps * d->cin;
+      cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->cout};
+      cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+      cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)(d->block_n / 2)};
+      if (encode_map(&p.tmap_b2, d->weight, 2, dims, strides, box, swz, "weight(pair)")) return 1;
+      p.pair = 1;
+      p.pair_tiles = ((m_tiles + 1) / 2) * p.tiles_n;
+      p.idesc_pair = make_idesc_f16(2 * kBlockM, d->block_n, false);
+      const int row_b = p.block_k * 2;
+      const int stage_pair = kBlockM * row_b + (d->block_n / 2) * row_b;
+      int st_pair = (g_smem_optin - 1024 - kTailBytes) / stage_pair;
+      if (st_pair > kMaxStages) st_pair = kMaxStages;
+      p.stages = st_pair;
+      smem_bytes = st_pair * stage_pair + kTailBytes + 1024;
+      const int pairs = g_num_sms / 2 < p.pair_tiles ? g_num_sms / 2 : p.pair_tiles;
+      grid = 2 * pairs;
+    }
+  }
   L.row = false;
   L.grid = grid;
   L.smem_bytes = smem_bytes;

@@ -550,3 +550,44 @@ def test_fp16_stores_saturate_instead_of_overflowing(cin, cout, H, W):
     assert torch.equal(got, ref.clamp(-65504, 65504).half().float()) or \
         (got - ref.clamp(-65504, 65504)).abs().max().item() <= 1e-2 * 65504
     assert (got.abs() == 65504).any()
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout,kind', [(8, 32, 96, 256, 256, 'plain'), (7, 36, 96, 256, 512, 'plain'),
+                                                 (4, 64, 192, 128, 128, 'mod'), (6, 32, 96, 128, 64, 'convt'),
+                                                 (8, 32, 96, 256, 256, 'res')])
+def test_conv_cta_pair_matches_single_cta(B, H, W, cin, cout, kind):
+    """Layers with streamed weights, N-tiles of 128 / 256 columns and at least one M-tile per SM run on CTA pairs
+    (tcgen05.mma.cta_group::2, M = 256: each CTA stages its own A rows and half of the weight tile).  Same K order per
+    accumulator, so the result must equal the single-CTA kernel's bit for bit (max_ctas > 0 keeps a launch on single CTAs);
+    (7, 36, 96) has an odd number of M-tiles: the last pair works with an out-of-range second tile."""
+    import math
+    from image_restoration_b200 import ops
+    g = torch.Generator().manual_seed(B * H + cin)
+    x = torch.randn(B, H, W, cin, generator=g).half().cuda()
+    outs = []
+    for max_ctas in (0, 148):
+        if kind == 'convt':
+            wt = torch.randn(cout, cin, 3, 3, generator=torch.Generator().manual_seed(1)) / math.sqrt(cin * 9)
+            raw = torch.zeros(B, 2 * H + 2, 2 * W + 2, cout, device='cuda', dtype=torch.float16)
+            demod = (1 + 0.1 * torch.randn(B, cout, generator=torch.Generator().manual_seed(2))).cuda()
+            op = ops.convt_s2_merged(x, ops.convt_merged_weight(wt.cuda(), 1.0), raw, demod)
+            op.desc.max_ctas = max_ctas
+            op()
+            outs.append(raw)
+            continue
+        w = (torch.randn(cout, 9 * cin, generator=torch.Generator().manual_seed(3)) / math.sqrt(9 * cin)).half().cuda()
+        bias = (0.1 * torch.randn(cout, generator=torch.Generator().manual_seed(4))).cuda()
+        out = torch.zeros(B, H, W, cout, device='cuda', dtype=torch.float16)
+        kw = dict(bias=bias, act=True, max_ctas=max_ctas)
+        if kind == 'mod':
+            kw.update(demod=(1 + 0.1 * torch.randn(B, cout, generator=torch.Generator().manual_seed(5))).cuda(),
+                      noise=torch.randn(B, 1, H, W, generator=torch.Generator().manual_seed(6)).cuda(),
+                      noise_gain=torch.full((1,), 0.3).cuda(), noise_strides=(H * W, W))
+        if kind == 'res':
+            res = torch.randn(B, H, W, cout, generator=torch.Generator().manual_seed(7)).half().cuda()
+            kw.update(res=res, res_mode=1, res_strides=(cout, W * cout, H * W * cout), res_wh=(W, H), res_scale=ops.INV_SQRT2)
+        ops.conv_same(x, w, out, 3, **kw)()
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert outs[0].float().abs().max().item() > 0.1
+    assert torch.equal(outs[0], outs[1])
