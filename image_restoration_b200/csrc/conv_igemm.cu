@@ -379,14 +379,15 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
 
   int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-  // ---- CTA pairs (cta_group::2): streamed-weight layers with N-tiles of 128 / 256 columns and enough M-tiles for every
-  // pair; B200IR_CTA_PAIR=0 keeps every layer on single CTAs (A/B switch)
+  // ---- CTA pairs (cta_group::2): streamed-weight layers with N-tiles of 128 / 256 columns and at least one work item (two
+  // M-tiles of one N-tile) per pair of SMs -- with fewer, single CTAs spread the tiles over more SMs (measured: 256 -> 256 at
+  // 8x24 / 4x12 lose 2 us as pairs, 512 -> 4x512 at 9x25 gains 12 us); B200IR_CTA_PAIR=0 keeps every layer on single CTAs
   {
     static int pair_env = -1;
     if (pair_env < 0) pair_env = (getenv("B200IR_CTA_PAIR") != nullptr) ? atoi(getenv("B200IR_CTA_PAIR")) : 1;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     if (pair_env && !p.b_resident && p.block_k == 64 && d->block_n >= 128 && d->block_n % 16 == 0 && !d->w_per_image &&
-        d->max_ctas <= 0 && m_tiles >= g_num_sms && g_num_sms >= 2) {
+        d->max_ctas <= 0 && m_tiles >= 2 && g_num_sms >= 2 && ((m_tiles + 1) / 2) * p.tiles_n >= g_num_sms / 2) {
       const int k_total = d->num_taps * d->cin;
       cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->cout};
       cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
