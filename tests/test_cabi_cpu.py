@@ -69,6 +69,7 @@ def test_sass_is_blackwell_native():
     sass = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
     if not sass:
         pytest.skip('cuobjdump unavailable')
-    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG'):
+    # UTCHMMA.2CTA / UTCBAR.2CTA.MULTICAST: the CTA-pair conv kernel (tcgen05.mma.cta_group::2 + multicast commit)
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UTCHMMA.2CTA', 'UTCBAR.2CTA.MULTICAST', 'UTMALDG.4D.2CTA'):
         assert mnemonic in sass, mnemonic
     assert 'HMMA.16816' not in sass          # no legacy mma.sync path
