@@ -100,6 +100,8 @@ struct alignas(64) ConvParams {
   int no_store;
   int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
   int epi_pipe;      // fast epilogues without global operands: keep the next chunk's TMEM load in flight (host heuristic)
+  int epi_split;     // 256-column accumulators (two ring stages): every tile is drained as two 128-column halves and the
+                     // half-tiles go round-robin over all three epilogue groups (otherwise the third group idles)
   int w_img_rows;    // per-image weights: rows of the weight matrix per image (= cout), 0 = one matrix for all images
   // CTA pairs (conv_igemm_kernel<.., kPair = true>): two CTAs share one 256 x block_n MMA per K step
   CUtensorMap tmap_b2;  // weight tile of block_n / 2 rows (each CTA of a pair stages half of B)
@@ -447,14 +449,14 @@ template <int F>
 __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
                                               uint32_t full_phase, const FastRow& r, bool valid, float gain,
                                               uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride,
-                                              int n0) {
+                                              int n0, int c_begin, int c_end) {
   mbar_wait_parked(full_bar, full_phase);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
   const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
   const float ag = p.act_gain, slope = p.slope;
   const bool act = slope != 1.f;  // slope 1: no activation (max(v, v)); saves two instructions per element
-  const int block_n = p.block_n;
+  const int block_n = c_end;      // columns [c_begin, c_end) of the tile (the whole tile unless the epilogue is split)
   float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
   // pixel-shuffle store (transposed conv, folded ConvUpLayer): sub-pixel base and channel of the current chunk, advanced
   // by 16 channels per chunk instead of recomputing the phase split of n0 + c0 every time
@@ -462,8 +464,9 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
   int ps_ch = 0, ps_t = 0;
   const __half* ps_base = r.out;
   if (ps_r) {
-    ps_t = (p.ps_shift >= 0) ? (n0 >> p.ps_shift) : (n0 / ps_c);
-    ps_ch = n0 - ps_t * ps_c;
+    const int nb = n0 + c_begin;
+    ps_t = (p.ps_shift >= 0) ? (nb >> p.ps_shift) : (nb / ps_c);
+    ps_ch = nb - ps_t * ps_c;
     const int ty = ps_t / ps_r;
     ps_base = r.out + (long long)ty * p.out_sy + (long long)(ps_t - ty * ps_r) * p.out_sx;
   }
@@ -560,7 +563,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
   if ((F & (F_RES1 | F_RES2)) || !p.epi_pipe) {
     // residual variants: the residual row(s) of a chunk are fetched from global memory while its TMEM load is in flight
 #pragma unroll 1
-    for (int c0 = 0; c0 < block_n; c0 += 16) {
+    for (int c0 = c_begin; c0 < block_n; c0 += 16) {
       uint32_t raw[16];
       tmem_ld16(taddr + c0, raw);
       uint4 ra[2], rb[2], rc[2], rd[2];
@@ -584,9 +587,9 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
     // register buffers; tcgen05.wait::ld covers every outstanding load, so the next one is issued right after the wait)
     uint32_t raw_a[16], raw_b[16];
     const uint4 none[2] = {};
-    tmem_ld16(taddr, raw_a);
+    tmem_ld16(taddr + c_begin, raw_a);
 #pragma unroll 1
-    for (int c0 = 0; c0 < block_n; c0 += 32) {
+    for (int c0 = c_begin; c0 < block_n; c0 += 32) {
       tmem_ld_wait16(raw_a);
       const bool second = c0 + 16 < block_n;
       if (second) tmem_ld16(taddr + c0 + 16, raw_b);
@@ -619,7 +622,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
 // (gfpganv1_ocr_arch.py:224, 1x1 conv commuted to low resolution) is sampled bilinearly for that pixel.
 __device__ __forceinline__ void epilogue_upfold(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
                                                 uint32_t full_phase, int x, int y, int b, int n0, bool valid,
-                                                uint32_t s_bias) {
+                                                uint32_t s_bias, int c_begin, int c_end) {
   mbar_wait_parked(full_bar, full_phase);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
@@ -628,7 +631,7 @@ __device__ __forceinline__ void epilogue_upfold(const ConvParams& p, uint32_t ta
   __half* out_b = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_sb + p.out_c_off;
   const __half* res_b = p.res + (long long)b * p.res_sb;
 #pragma unroll 1
-  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
     uint32_t raw[16];
     tmem_ld16(taddr + c0, raw);
     const int n = n0 + c0;
@@ -726,13 +729,14 @@ __device__ __forceinline__ void epilogue_upfold(const ConvParams& p, uint32_t ta
 template <int EPI>
 __device__ __forceinline__ void epilogue_one(const ConvParams& p, uint32_t taddr, uint64_t* full_bar, uint32_t full_phase,
                                              int x, int y, int b, int n0, bool valid, float gain, uint32_t s_bias,
-                                             uint32_t s_dm, const float* g_dm, uint32_t s_aux, int aux_stride) {
+                                             uint32_t s_dm, const float* g_dm, uint32_t s_aux, int aux_stride, int c_begin,
+                                             int c_end) {
   if constexpr (EPI >= 0 && (epi_profile_flags(EPI < 0 ? 0 : EPI) & F_UPFOLD) != 0) {
-    epilogue_upfold(p, taddr, full_bar, full_phase, x, y, b, n0, valid, s_bias);
+    epilogue_upfold(p, taddr, full_bar, full_phase, x, y, b, n0, valid, s_bias, c_begin, c_end);
   } else if constexpr (EPI >= 0) {
     constexpr int F = epi_profile_flags(EPI);
     const FastRow fr = fast_setup<F>(p, x, y, b, n0, valid);
-    epilogue_fast<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride, n0);
+    epilogue_fast<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride, n0, c_begin, c_end);
   } else {
     const EpiRow r = epi_setup(p, x, y, b, n0, valid, gain);
     epilogue_tile(p, taddr, full_bar, full_phase, r, valid, gain, s_bias, p.bias + n0, s_dm, g_dm, s_aux, aux_stride, 0, 16,
@@ -806,7 +810,8 @@ __device__ __forceinline__ uint32_t kernel_prologue(const ConvParams& p, const K
     }
     for (int i = 0; i < p.acc_stages; ++i) {
       mbar_init(&s.tmem_full[i], 1);
-      mbar_init(&s.tmem_empty[i], kPair ? 256 : 128);   // pair: the epilogue threads of both CTAs release the leader's MMA
+      // pair: the epilogue threads of both CTAs release the leader's MMA; split epilogue: two groups drain one tile
+      mbar_init(&s.tmem_empty[i], (kPair ? 256 : 128) * (p.epi_split ? 2 : 1));
     }
     mbar_init(s.w_bar, 1);
     fence_barrier_init();
@@ -987,9 +992,16 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
     int last_key = -1;
     // a group may wait at most one phase ahead on an accumulator's mbarrier, so no more groups than accumulator stages
     // take part (block_n = 256 has two stages: the third group idles there, those layers are main-loop bound anyway)
-    const int ngroups = min(kGroups, p.acc_stages);
-    for (int item = (group < ngroups) ? item0 + group * item_step : num_items; item < num_items;
-         item += ngroups * item_step, it += ngroups) {
+    const bool split = kGroups == 3 && p.epi_split;
+    const int ngroups = split ? 3 : min(kGroups, p.acc_stages);
+    // unit u of this group: a tile (u = it), or half a tile when the epilogue is split (u = 2 * it + half)
+    const int my_items = (num_items > item0) ? (num_items - item0 + item_step - 1) / item_step : 0;
+    const int units = split ? 2 * my_items : my_items;
+    for (int u = (group < ngroups) ? group : units; u < units; u += ngroups) {
+      it = split ? (u >> 1) : u;
+      const int c_begin = split ? (u & 1) * (p.block_n >> 1) : 0;
+      const int c_end = split ? c_begin + (p.block_n >> 1) : p.block_n;
+      const int item = item0 + it * item_step;
       const int tile = tile_of(item);
       const int acc = it & (p.acc_stages - 1);
       const TileCoord t = decode_tile(p, tile);
@@ -1037,7 +1049,7 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1) conv_igemm_kernel(co
       const uint32_t s_bias = (p.bias_c <= kMaxBias) ? smem_u32(s.bias + t.n0 % p.bias_c)
                                                      : (p.bias == nullptr ? smem_u32(s.bias + t.n0 % kMaxBias) : 0u);
       epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, y, b, t.n0, valid, gain, s_bias, s_dm,
-                        g_dm, s_aux, tab_n);
+                        g_dm, s_aux, tab_n, c_begin, c_end);
       tc_fence_before();
       if (kPair && rank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(&s.tmem_empty[acc]), 0));
       else mbar_arrive(&s.tmem_empty[acc]);
@@ -1262,7 +1274,7 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(c
         const int acc = it & (p.acc_stages - 1);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
         epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, w.y0 + j, w.b, 0, valid, gain,
-                          smem_u32(s.bias), s_dm, nullptr, s_aux, p.block_n);
+                          smem_u32(s.bias), s_dm, nullptr, s_aux, p.block_n, 0, p.block_n);
         tc_fence_before();
         mbar_arrive(&s.tmem_empty[acc]);
       }

@@ -283,6 +283,14 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
                    "32-byte aligned output and all four correction buffers");
     p.slope = d->act == 1 ? 0.2f : (d->act == 2 ? d->act_slope : 1.f);
     if (p.epi >= 0 && d->res_mode != 0) p.act_gain *= d->res_scale;
+    // 256-column tiles have two accumulator stages, i.e. two busy epilogue groups: the residual epilogues (global gathers
+    // per chunk: latency-bound) drain each tile as two halves over all three groups.  Measured (B200IR_EPI_SPLIT=0/1 in one
+    // box): folded ConvUpLayer 237 -> 219 us, 256 -> 256 + bilinear residual 192 -> 182, 64 -> 256 stride 2 100 -> 92;
+    // the demodulation-only epilogues of the transposed convs get slower when split (250 -> 273 us), so they are not
+    static int split_env = -1;
+    if (split_env < 0) split_env = (getenv("B200IR_EPI_SPLIT") != nullptr) ? atoi(getenv("B200IR_EPI_SPLIT")) : 1;
+    p.epi_split = (split_env && p.epi >= 0 && p.acc_stages == 2 && d->block_n == 256 && (flags & (F_RES1 | F_RES2)) &&
+                   !(flags & F_RGB)) ? 1 : 0;
   }
   p.w_img_rows = d->w_per_image ? d->cout : 0;
   p.out_scale = d->out_scale; p.rgb_w = d->rgb_w; p.rgb_part = d->rgb_part; p.no_store = d->no_store;
