@@ -445,7 +445,122 @@ __device__ __forceinline__ FastRow fast_setup(const ConvParams& p, int x, int y,
 
 // fp16 NHWC output with 32-byte aligned rows, bias (and demod / aux tables) in shared memory, gains pre-folded:
 //   v = acc * (demod*g | g) + (bias*g + noise*gain*g);  v = max(v, slope*v);  v += res * w (w carries the residual scale)
+// The epilogue as the two-CTAs-per-SM row kernels use it: one TMEM load per chunk, whole tile, no pipelining state (60-72
+// registers; see epilogue_fast for the general form).
 template <int F>
+__device__ __forceinline__ void epilogue_fast_lean(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
+                                              uint32_t full_phase, const FastRow& r, bool valid, float gain,
+                                              uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride,
+                                              int n0) {
+  mbar_wait_parked(full_bar, full_phase);
+  tc_fence_after();
+  if (p.dbg_skip_epi) return;
+  const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
+  const float ag = p.act_gain, slope = p.slope;
+  float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+    uint32_t raw[16];
+    tmem_ld16(taddr + c0, raw);
+    float4 bs[4], dm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bs[j] = lds_f4(s_bias + (c0 + 4 * j) * 4);
+    if (F & F_DEMOD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = lds_f4(s_demod + (c0 + 4 * j) * 4);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dm[j] = make_float4(ag, ag, ag, ag);
+    }
+    uint4 ra[2], rb[2], rc[2], rd[2];
+    if ((F & (F_RES1 | F_RES2)) && valid) {
+      ra[0] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0));
+      ra[1] = __ldg(reinterpret_cast<const uint4*>(r.r00 + c0) + 1);
+      if (F & F_RES2) {
+        rb[0] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0));
+        rb[1] = __ldg(reinterpret_cast<const uint4*>(r.r01 + c0) + 1);
+        rc[0] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0));
+        rc[1] = __ldg(reinterpret_cast<const uint4*>(r.r10 + c0) + 1);
+        rd[0] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0));
+        rd[1] = __ldg(reinterpret_cast<const uint4*>(r.r11 + c0) + 1);
+      }
+    }
+    tmem_ld_wait16(raw);
+    if (!valid) continue;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), dm[j].x, bs[j].x + nz);
+      v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), dm[j].y, bs[j].y + nz);
+      v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), dm[j].z, bs[j].z + nz);
+      v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), dm[j].w, bs[j].w + nz);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+    if (F & F_RES1) {
+      float f[16];
+      unpack_half8(ra[0], f);
+      unpack_half8(ra[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
+    }
+    if (F & F_RES2) {
+      float f[16];
+      unpack_half8(ra[0], f); unpack_half8(ra[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w00, v[j]);
+      unpack_half8(rb[0], f); unpack_half8(rb[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w01, v[j]);
+      unpack_half8(rc[0], f); unpack_half8(rc[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w10, v[j]);
+      unpack_half8(rd[0], f); unpack_half8(rd[1], f + 8);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(f[j], r.w11, v[j]);
+    }
+    if (F & F_RGB) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w0 = lds_f4(s_aux + (aux_stride + c0 + 4 * j) * 4);
+        const float4 w1 = lds_f4(s_aux + (2 * aux_stride + c0 + 4 * j) * 4);
+        const float4 w2 = lds_f4(s_aux + (3 * aux_stride + c0 + 4 * j) * 4);
+        rgb0 = fmaf(v[4 * j], w0.x, rgb0); rgb1 = fmaf(v[4 * j], w1.x, rgb1); rgb2 = fmaf(v[4 * j], w2.x, rgb2);
+        rgb0 = fmaf(v[4 * j + 1], w0.y, rgb0); rgb1 = fmaf(v[4 * j + 1], w1.y, rgb1); rgb2 = fmaf(v[4 * j + 1], w2.y, rgb2);
+        rgb0 = fmaf(v[4 * j + 2], w0.z, rgb0); rgb1 = fmaf(v[4 * j + 2], w1.z, rgb1); rgb2 = fmaf(v[4 * j + 2], w2.z, rgb2);
+        rgb0 = fmaf(v[4 * j + 3], w0.w, rgb0); rgb1 = fmaf(v[4 * j + 3], w1.w, rgb1); rgb2 = fmaf(v[4 * j + 3], w2.w, rgb2);
+      }
+      if (!(F & F_NOSTORE)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 s4 = lds_f4(s_aux + (c0 + 4 * j) * 4);
+          v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+        }
+      }
+    }
+    if (!(F & F_NOSTORE)) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __half2 h = f2h2_sat(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      const __half* op = r.out + c0 + (p.ps_r ? ps_offset(p, n0, c0) : 0);
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op), "r"(pk[0]), "r"(pk[1]),
+                   "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                   : "memory");
+    }
+  }
+  if ((F & F_RGB) && valid) {
+    r.rgb[0] = rgb0;
+    r.rgb[p.rgb_plane] = rgb1;
+    r.rgb[2 * p.rgb_plane] = rgb2;
+  }
+}
+
+// kAllowPipe = false compiles the pipelined variant out: its second TMEM register buffer costs ~25 registers, and the
+// row kernel's two-CTAs-per-SM configuration (cout <= 32, profiles 0 / 1) only fits with <= 73 registers per thread.
+template <int F, bool kAllowPipe = true>
 __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
                                               uint32_t full_phase, const FastRow& r, bool valid, float gain,
                                               uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride,
@@ -560,7 +675,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
       }
     }
   };
-  if ((F & (F_RES1 | F_RES2)) || !p.epi_pipe) {
+  if ((F & (F_RES1 | F_RES2)) || !kAllowPipe || !p.epi_pipe) {
     // residual variants: the residual row(s) of a chunk are fetched from global memory while its TMEM load is in flight
 #pragma unroll 1
     for (int c0 = c_begin; c0 < block_n; c0 += 16) {
@@ -582,7 +697,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
       tmem_ld_wait16(raw);
       finish(c0, raw, ra, rb, rc, rd);
     }
-  } else {
+  } else if constexpr (kAllowPipe) {
     // no global operands: the TMEM load of chunk k + 1 is in flight while chunk k is scaled, activated and stored (two
     // register buffers; tcgen05.wait::ld covers every outstanding load, so the next one is issued right after the wait)
     uint32_t raw_a[16], raw_b[16];
@@ -726,7 +841,7 @@ __device__ __forceinline__ void epilogue_upfold(const ConvParams& p, uint32_t ta
 // template constants) or -1 for the run-time generic one.  Every (block_k, EPI) pair is its own kernel, compiled in its
 // own translation unit (conv_epi*.cu): with all variants inlined behind a switch the register allocator spilled
 // loop-carried state of the tile loops (a local-memory load per tile showed up as the second largest stall).
-template <int EPI>
+template <int EPI, bool kAllowPipe = true>
 __device__ __forceinline__ void epilogue_one(const ConvParams& p, uint32_t taddr, uint64_t* full_bar, uint32_t full_phase,
                                              int x, int y, int b, int n0, bool valid, float gain, uint32_t s_bias,
                                              uint32_t s_dm, const float* g_dm, uint32_t s_aux, int aux_stride, int c_begin,
@@ -736,7 +851,10 @@ __device__ __forceinline__ void epilogue_one(const ConvParams& p, uint32_t taddr
   } else if constexpr (EPI >= 0) {
     constexpr int F = epi_profile_flags(EPI);
     const FastRow fr = fast_setup<F>(p, x, y, b, n0, valid);
-    epilogue_fast<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride, n0, c_begin, c_end);
+    if constexpr (kAllowPipe)
+      epilogue_fast<F, true>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride, n0, c_begin, c_end);
+    else
+      epilogue_fast_lean<F>(p, taddr, full_bar, full_phase, fr, valid, gain, s_bias, s_dm, s_aux, aux_stride, n0);
   } else {
     const EpiRow r = epi_setup(p, x, y, b, n0, valid, gain);
     epilogue_tile(p, taddr, full_bar, full_phase, r, valid, gain, s_bias, p.bias + n0, s_dm, g_dm, s_aux, aux_stride, 0, 16,
@@ -1273,8 +1391,10 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(c
         if (it % ngroups != group) continue;
         const int acc = it & (p.acc_stages - 1);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-        epilogue_one<EPI>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x, w.y0 + j, w.b, 0, valid, gain,
-                          smem_u32(s.bias), s_dm, nullptr, s_aux, p.block_n, 0, p.block_n);
+        // 32-channel inputs with the plain profiles may run two CTAs per SM (build_conv_launch: `dual`): keep them lean
+        epilogue_one<EPI, !(kBlockK == 32 && (EPI == 0 || EPI == 1))>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x,
+                                                                     w.y0 + j, w.b, 0, valid, gain, smem_u32(s.bias), s_dm,
+                                                                     nullptr, s_aux, p.block_n, 0, p.block_n);
         tc_fence_before();
         mbar_arrive(&s.tmem_empty[acc]);
       }
