@@ -11,10 +11,13 @@ StyleGAN2OCRGeneratorSFT.forward (:50-136); identities used (v
   * bilinear x2 commutes with the 1x1 skip conv of ResUpBlock; FIR-then-sample commutes with the 1x1 skip of ResBlock.
 """
 import math
+import os
 
 import torch
 
 from . import ops
+
+_SFT_SPLIT = os.environ.get('B200IR_SFT_SPLIT', '1') != '0'    # 0: merged 64-channel hidden tensor of the 32-channel SFT heads
 
 F16 = torch.float16
 F32 = torch.float32
@@ -296,20 +299,35 @@ class _Plan:
                 steps.wait(f'up_sl{i}')
                 steps.append(ops.conv_same(u, d['w2'], feat, 3, bias=d['b2'], act=True, res=sl, res_mode=2,
                                            res_strides=(cout, w * cout, h * w * cout), res_wh=(w, h), res_scale=inv))
-            hid = e16(B, h2, w2, 2 * cout)
-            steps.append(ops.conv_same(feat, d['wh0'], hid, 3, bias=d['bh0'], act=True))
             c_sft = d['wsc'].shape[0]
             sc, sh = e16(B, h2, w2, c_sft), e16(B, h2, w2, c_sft)
-            steps.rec(f'up_hid{i}')
-            for half, wk, bk, dst in ((0, 'wsc', 'bsc', sc), (1, 'wsh', 'bsh', sh)):
-                v = ops.View(hid.data_ptr() + 2 * half * cout, cout, w2, h2, B, 2 * cout, w2 * 2 * cout,
-                             h2 * w2 * 2 * cout)
-                rk = dict(tile=(128, 1, 1), row_mode=1, block_n=c_sft) if ops.row_mode_ok(B, h2, w2, cout, c_sft) else {}
-                if half == 1:                      # the shift head runs beside the scale head
-                    steps.lane = 2
-                    steps.wait(f'up_hid{i}')
-                steps.append(ops.ConvOp([v], d[wk], cout, c_sft, ops.taps_3x3(), (w2, h2, B), dst,
-                                        (c_sft, w2 * c_sft, h2 * w2 * c_sft), bias=d[bk], **rk))
+            if cout < 64 and _SFT_SPLIT:
+                # 32-channel heads: a merged 64-channel hidden tensor would make each output conv read 64-byte half rows (the
+                # whole 128-byte line is fetched: 115 us against 79 us for a contiguous 32-channel input, B = 64 at 128x384),
+                # and two 32 -> 32 launches (two CTAs per SM in the row kernel) beat one 32 -> 64 launch (2 x 79 vs 181 us):
+                # each head is its own chain of two convs, the shift head on lane 2 beside the scale head
+                steps.rec(f'up_feat{i}')
+                for half, wk, bk, dst in ((0, 'wsc', 'bsc', sc), (1, 'wsh', 'bsh', sh)):
+                    if half == 1:
+                        steps.lane = 2
+                        steps.wait(f'up_feat{i}')
+                    hid_h = e16(B, h2, w2, cout)
+                    steps.append(ops.conv_same(feat, d['wh0'][half * cout:(half + 1) * cout], hid_h, 3,
+                                               bias=d['bh0'][half * cout:(half + 1) * cout], act=True))
+                    steps.append(ops.conv_same(hid_h, d[wk], dst, 3, bias=d[bk]))
+            else:
+                hid = e16(B, h2, w2, 2 * cout)
+                steps.append(ops.conv_same(feat, d['wh0'], hid, 3, bias=d['bh0'], act=True))
+                steps.rec(f'up_hid{i}')
+                for half, wk, bk, dst in ((0, 'wsc', 'bsc', sc), (1, 'wsh', 'bsh', sh)):
+                    v = ops.View(hid.data_ptr() + 2 * half * cout, cout, w2, h2, B, 2 * cout, w2 * 2 * cout,
+                                 h2 * w2 * 2 * cout)
+                    rk = dict(tile=(128, 1, 1), row_mode=1, block_n=c_sft) if ops.row_mode_ok(B, h2, w2, cout, c_sft) else {}
+                    if half == 1:                      # the shift head runs beside the scale head
+                        steps.lane = 2
+                        steps.wait(f'up_hid{i}')
+                    steps.append(ops.ConvOp([v], d[wk], cout, c_sft, ops.taps_3x3(), (w2, h2, B), dst,
+                                            (c_sft, w2 * c_sft, h2 * w2 * c_sft), bias=d[bk], **rk))
             steps.rec(f'up_sh{i}')
             steps.lane = 0
             steps.wait(f'up_sh{i}')
