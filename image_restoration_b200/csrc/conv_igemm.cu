@@ -356,6 +356,21 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
         p.row_R = R;
         p.row_chunks = (d->m_h + R - 1) / R;
         p.row_items = d->m_b * p.tiles_w * p.row_chunks;
+        {
+          // balanced alternative: equal row ranges per CTA, cut at (image, segment) boundaries; a CTA then pays its rows
+          // plus two halo rows per (partial) pair it touches.  Taken when that is at least 3 % shorter than the uniform grid
+          // (64 x 192 levels at batch 64: 128 whole-image items on 148 SMs -> 59 instead of 66 row times).
+          static int bal_env = -1;
+          if (bal_env < 0) bal_env = (getenv("B200IR_ROW_BALANCED") != nullptr) ? atoi(getenv("B200IR_ROW_BALANCED")) : 1;
+          const int ctas = (d->max_ctas > 0 && d->max_ctas < row_ctas) ? d->max_ctas : row_ctas;
+          const long long total = (long long)d->m_b * p.tiles_w * d->m_h;
+          const long long rows_cta = (total + ctas - 1) / ctas;
+          const long long pairs_cta = (rows_cta + d->m_h - 1) / d->m_h + 1;
+          const long long cost_bal = rows_cta + 2 * pairs_cta;
+          const long long items_u = (long long)p.row_items;
+          const long long cost_uni = ((items_u + ctas - 1) / ctas) * (R + 2);
+          p.row_balanced = (bal_env && total >= 4LL * ctas && cost_bal * 100 < cost_uni * 97) ? 1 : 0;
+        }
         // too little parallelism at small batch: generic tiles are faster (row_mode == 2 forces the variant: tests)
         row_ok = (long long)d->m_b * p.tiles_w * d->m_h >= 16LL * g_num_sms || d->row_mode == 2;
         p.row_slots = slots;
@@ -371,7 +386,7 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
             while ((1 << p.acc_shift) < p.acc_stages) ++p.acc_shift;
             p.tmem_cols = 256;
           }
-          int grid_r = p.row_items < row_ctas ? p.row_items : row_ctas;
+          int grid_r = (p.row_items < row_ctas && !p.row_balanced) ? p.row_items : row_ctas;
           if (d->max_ctas > 0 && grid_r > d->max_ctas) grid_r = d->max_ctas;
           L.row = true;
           L.grid = grid_r;
