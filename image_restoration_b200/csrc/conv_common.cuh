@@ -1397,6 +1397,9 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(c
     const float gain = (p.noise != nullptr) ? __ldg(p.noise_gain) * p.act_gain : 0.f;
     const int ngroups = min(kGroups, p.acc_stages);  // see conv_igemm_kernel (the ring has 8 or 16 stages here)
     int it = 0;
+    int mine = (group < ngroups) ? group : 0x7fffffff;  // next output row this group drains (rows go round the groups;
+                                                        // a running counter: `it % ngroups` was a run-time division
+                                                        // per row and warp, ~12 % of the kernel's instructions)
     RowItem w;
     for (RowIter iter(p); iter.next(p, w);) {
       const int x = w.seg * 128 + row;
@@ -1421,7 +1424,8 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(c
         if (p.smem_aux) s_aux = smem_u32(tab + p.block_n);
       }
       for (int j = 0; j < w.rows_out; ++j, ++it) {
-        if (it % ngroups != group) continue;
+        if (it != mine) continue;
+        mine += ngroups;
         const int acc = it & (p.acc_stages - 1);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
         // 32-channel inputs with the plain profiles may run two CTAs per SM (build_conv_launch: `dual`): keep them lean

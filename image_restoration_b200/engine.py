@@ -17,7 +17,8 @@ import torch
 
 from . import ops
 
-_SFT_SPLIT = os.environ.get('B200IR_SFT_SPLIT', '1') != '0'    # 0: merged 64-channel hidden tensor of the 32-channel SFT heads
+# SFT heads with at most this many channels run as two chains of two convs (0: always one merged hidden tensor)
+_SFT_SPLIT = int(os.environ.get('B200IR_SFT_SPLIT', '64'))
 
 F16 = torch.float16
 F32 = torch.float32
@@ -301,11 +302,13 @@ class _Plan:
                                            res_strides=(cout, w * cout, h * w * cout), res_wh=(w, h), res_scale=inv))
             c_sft = d['wsc'].shape[0]
             sc, sh = e16(B, h2, w2, c_sft), e16(B, h2, w2, c_sft)
-            if cout < 64 and _SFT_SPLIT:
+            if cout <= _SFT_SPLIT:
                 # 32-channel heads: a merged 64-channel hidden tensor would make each output conv read 64-byte half rows (the
                 # whole 128-byte line is fetched: 115 us against 79 us for a contiguous 32-channel input, B = 64 at 128x384),
                 # and two 32 -> 32 launches (two CTAs per SM in the row kernel) beat one 32 -> 64 launch (2 x 79 vs 181 us):
-                # each head is its own chain of two convs, the shift head on lane 2 beside the scale head
+                # each head is its own chain of two convs, the shift head on lane 2 beside the scale head.  64-channel heads
+                # (64 x 192): four row-kernel launches of ~70 us against 157 us (merged 64 -> 128, generic kernel) + 2 x 72 us,
+                # 7.36 -> 7.32 ms per step (three alternating runs each)
                 steps.rec(f'up_feat{i}')
                 for half, wk, bk, dst in ((0, 'wsc', 'bsc', sc), (1, 'wsh', 'bsh', sh)):
                     if half == 1:
