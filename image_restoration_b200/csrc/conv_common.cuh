@@ -100,6 +100,7 @@ struct alignas(64) ConvParams {
   int rgb_w_px;
   int no_store;
   int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
+  int epi_wait_ns;   // back-off of the epilogue's accumulator-full wait (env B200IR_EPI_WAIT_NS; 0 = parked try_wait)
   int epi_pipe;      // fast epilogues without global operands: keep the next chunk's TMEM load in flight (host heuristic)
   int epi_split;     // 256-column accumulators (two ring stages): every tile is drained as two 128-column halves and the
                      // half-tiles go round-robin over all three epilogue groups (otherwise the third group idles)
@@ -228,7 +229,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                                               uint32_t full_phase, EpiRow r, bool valid, float gain, uint32_t s_bias,
                                               const float* g_bias, uint32_t s_demod, const float* g_demod,
                                               uint32_t s_aux, int aux_stride, int c_begin, int c_step, int n0) {
-  mbar_wait_parked(full_bar, full_phase);
+  mbar_wait_backoff(full_bar, full_phase, p.epi_wait_ns);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
   r.nz *= gain;  // the noise load was issued in epi_setup, long before this first use
@@ -453,7 +454,7 @@ __device__ __forceinline__ void epilogue_fast_lean(const ConvParams& p, uint32_t
                                               uint32_t full_phase, const FastRow& r, bool valid, float gain,
                                               uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride,
                                               int n0) {
-  mbar_wait_parked(full_bar, full_phase);
+  mbar_wait_backoff(full_bar, full_phase, p.epi_wait_ns);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
   const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
@@ -566,7 +567,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
                                               uint32_t full_phase, const FastRow& r, bool valid, float gain,
                                               uint32_t s_bias, uint32_t s_demod, uint32_t s_aux, int aux_stride,
                                               int n0, int c_begin, int c_end) {
-  mbar_wait_parked(full_bar, full_phase);
+  mbar_wait_backoff(full_bar, full_phase, p.epi_wait_ns);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
   const float nz = (F & F_NOISE) ? r.nz * gain : 0.f;
@@ -739,7 +740,7 @@ __device__ __forceinline__ void epilogue_fast(const ConvParams& p, uint32_t tadd
 __device__ __forceinline__ void epilogue_upfold(const ConvParams& p, uint32_t taddr, uint64_t* full_bar,
                                                 uint32_t full_phase, int x, int y, int b, int n0, bool valid,
                                                 uint32_t s_bias, int c_begin, int c_end) {
-  mbar_wait_parked(full_bar, full_phase);
+  mbar_wait_backoff(full_bar, full_phase, p.epi_wait_ns);
   tc_fence_after();
   if (p.dbg_skip_epi) return;
   const float ag = p.act_gain, slope = p.slope;

@@ -253,6 +253,9 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
     static int pipe = -2;
     if (pipe == -2) pipe = (getenv("B200IR_EPI_PIPE") != nullptr) ? atoi(getenv("B200IR_EPI_PIPE")) : -1;
     p.epi_pipe = pipe >= 0 ? pipe : 1;
+    static int wait_ns = -1;
+    if (wait_ns < 0) wait_ns = (getenv("B200IR_EPI_WAIT_NS") != nullptr) ? atoi(getenv("B200IR_EPI_WAIT_NS")) : 0;
+    p.epi_wait_ns = wait_ns;
   }
   // ---- specialised epilogue selection
   {

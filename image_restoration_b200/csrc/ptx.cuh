@@ -77,6 +77,17 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
   } while (!ok);
 }
 
+// Epilogue wait with a fixed back-off: ns > 0 polls every ~ns nanoseconds (nanosleep does not wake on barrier traffic; the
+// parked form above re-issues its four-instruction loop at every mbarrier event of the CTA, ~40 times per accumulator wait
+// in the row kernel); ns = 0 is the parked form.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (ns == 0) {
+    mbar_wait_parked(bar, parity);
+    return;
+  }
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
