@@ -100,6 +100,7 @@ struct alignas(64) ConvParams {
   int rgb_w_px;
   int no_store;
   int dbg_skip_epi;  // profiling aid (env B200IR_DBG_SKIP_EPI): epilogue only recycles the accumulators
+  int row_peek;      // row kernel: the MMA warp peeks at the next row's barriers inside its MMA sequence (env B200IR_ROW_PEEK)
   int epi_wait_ns;   // back-off of the epilogue's accumulator-full wait (env B200IR_EPI_WAIT_NS; 0 = parked try_wait)
   int epi_pipe;      // fast epilogues without global operands: keep the next chunk's TMEM load in flight (host heuristic)
   int epi_split;     // 256-column accumulators (two ring stages): every tile is drained as two 128-column halves and the
@@ -1310,40 +1311,64 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(c
     int slot = 0;                                // ring slot of (current input row, kc 0)
     uint32_t phase = 0;
     int it_base = 0;                             // output rows issued before this item
+    // The scalar work between the last MMA of one input row and the first MMA of the next (two barrier polls, slot
+    // arithmetic, election) is not hidden by the tensor pipe once its short queue has drained, and the issuing thread is
+    // what bounds these layers.  So the common row peeks at the NEXT row's barriers (non-blocking test_wait) in the middle
+    // of its own MMA sequence, while the kw = 0 MMAs are still executing; the next iteration then skips the polls.
+    bool pf_full = false, pf_empty = false;
+    const int peek = p.row_peek;
     RowItem w;
     for (RowIter iter(p); iter.next(p, w);) {
       for (int i = 0; i < w.rows_out + 2; ++i) {
         const int row_slot = slot;
         for (int kc = 0; kc < kc_n; ++kc) {  // this input row has landed (all its k-chunks)
-          mbar_wait(&s.full_bar[slot], phase);
+          if (!pf_full) mbar_wait(&s.full_bar[slot], phase);
+          pf_full = false;
           if (++slot == nslots) {
             slot = 0;
             phase ^= 1u;
           }
         }
         const bool fresh = i < w.rows_out;  // output row i receives its first contribution (kh = 0) from this input row
-        if (fresh) {
+        if (fresh && !pf_empty) {
           const int it = it_base + i;
           mbar_wait(&s.tmem_empty[it & (ring - 1)], ((it >> p.acc_shift) & 1) ^ 1u);
         }
+        pf_empty = false;
         tc_fence_after();
         const int sa = (it_base + i - 2) & (ring - 1);
         if (kc_n == 1 && i >= 2 && fresh && sa <= ring - 3) {
+          const uint32_t d = tmem_base + sa * bn;
+          const uint32_t a_lo = ring_lo + row_slot * slot_lo;
           if (elect_one()) {
-            const uint32_t d = tmem_base + sa * bn;
-            const uint32_t a_lo = ring_lo + row_slot * slot_lo;
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
+            for (int k = 0; k < k_steps; ++k) {
+              const uint64_t a_desc = desc64(a_lo + 2 * k, hi);
+              const uint32_t b_lo = w_lo + 2 * k;
+              if (k == 0) {
+                umma_f16_fixed<true>(d, a_desc, desc64(b_lo, hi), id2);
+                umma_f16_fixed<false>(d + 2 * bn, a_desc, desc64(b_lo + 2 * wtile_lo, hi), id1);
+              } else {
+                umma_f16_fixed<true>(d, a_desc, desc64(b_lo, hi), id3);
+              }
+            }
+          }
+          __syncwarp();
+          if (peek) {  // slot / phase already point at the next input row
+            pf_full = mbar_test_wait(&s.full_bar[slot], phase);
+            if (i + 1 < w.rows_out) {
+              const int it1 = it_base + i + 1;
+              pf_empty = mbar_test_wait(&s.tmem_empty[it1 & (ring - 1)], ((it1 >> p.acc_shift) & 1) ^ 1u);
+            }
+          }
+          if (elect_one()) {
+#pragma unroll
+            for (int kw = 1; kw < 3; ++kw) {
 #pragma unroll
               for (int k = 0; k < k_steps; ++k) {
                 const uint64_t a_desc = desc64(a_lo + kw * px_lo + 2 * k, hi);
                 const uint32_t b_lo = w_lo + kw * 3 * wtile_lo + 2 * k;
-                if (kw == 0 && k == 0) {
-                  umma_f16_fixed<true>(d, a_desc, desc64(b_lo, hi), id2);
-                  umma_f16_fixed<false>(d + 2 * bn, a_desc, desc64(b_lo + 2 * wtile_lo, hi), id1);
-                } else {
-                  umma_f16_fixed<true>(d, a_desc, desc64(b_lo, hi), id3);
-                }
+                umma_f16_fixed<true>(d, a_desc, desc64(b_lo, hi), id3);
               }
             }
             umma_commit(&s.empty_bar[row_slot]);

@@ -256,6 +256,9 @@ static int build_conv_launch(const b200ir_conv_desc* d, ConvLaunch& L) {
     static int wait_ns = -1;
     if (wait_ns < 0) wait_ns = (getenv("B200IR_EPI_WAIT_NS") != nullptr) ? atoi(getenv("B200IR_EPI_WAIT_NS")) : 0;
     p.epi_wait_ns = wait_ns;
+    static int peek = -1;
+    if (peek < 0) peek = (getenv("B200IR_ROW_PEEK") != nullptr) ? atoi(getenv("B200IR_ROW_PEEK")) : 1;
+    p.row_peek = peek;
   }
   // ---- specialised epilogue selection
   {
