@@ -343,6 +343,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--train-batch', type=int, default=256, help='crops per GPU of the training-step record (0 = skip)')
     ap.add_argument('--train-steps', type=int, default=3)
+    ap.add_argument('--preroll', type=float, default=0.5, help='seconds of untimed steps right before the timed region')
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary records (degradation, tiling, training ...)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -456,10 +457,10 @@ def main():
         torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
-    ms_total = timed(step_resident, args.steps, warmup)
+    ms_total = timed(step_resident, args.steps, warmup, preroll=args.preroll)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
-    ms_e2e = timed(step_e2e, args.steps, warmup)
+    ms_e2e = timed(step_e2e, args.steps, warmup, preroll=args.preroll)
     pipe.drain()
 
     # parity of the benchmarked configuration itself: 4 crops of the batch against the CPU oracle (the checker, not the
