@@ -460,7 +460,11 @@ def main():
     ms_total = timed(step_resident, args.steps, warmup, preroll=args.preroll)
     sampler.stop_flag.set()
     sampler.join(timeout=2)
+    sampler_e2e = ClockSampler(local)        # the two legs run seconds apart: each gets its own clock record
+    sampler_e2e.start()
     ms_e2e = timed(step_e2e, args.steps, warmup, preroll=args.preroll)
+    sampler_e2e.stop_flag.set()
+    sampler_e2e.join(timeout=2)
     pipe.drain()
 
     # parity of the benchmarked configuration itself: 4 crops of the batch against the CPU oracle (the checker, not the
@@ -677,7 +681,11 @@ def main():
                                  'before the first event'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': crops_per_step * 3 * H * W * 4,
                     'd2h_bytes_per_step': crops_per_step * 3 * H * W * 4, 'ms_per_step': ms_e2e / args.steps,
-                    'bytes': 'whole job (all ranks), fp32 NCHW in and out'},
+                    'bytes': 'whole job (all ranks), fp32 NCHW in and out',
+                    'clocks': sampler_e2e.summary(),
+                    'note': 'same API call per micro-batch as the resident leg plus the H2D / D2H copies on their own streams '
+                            '(hidden behind the kernels); the legs are timed seconds apart and the power-capped SM clock '
+                            'drifts by 1-2 % in between, so e2e may read slightly above value'},
             'gpu_launches': int(launches_per_mb * mbs_per_step * args.steps * world),
             'launches_per_step': int(launches_per_mb * mbs_per_step * world),
             'launches_per_micro_batch': int(launches_per_mb),
