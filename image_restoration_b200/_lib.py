@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libb200ir.so')
+# B200IR_LIB: another build of the same library (A/B of two builds inside one GPU box; tools/ab_env.sh)
+LIB_PATH = os.environ.get('B200IR_LIB') or os.path.join(HERE, 'libb200ir.so')
 
 MAX_TAPS = 16
 MAX_VIEWS = 4

@@ -1239,8 +1239,12 @@ struct RowIter {
   }
 };
 
+// The instantiations the host may run as two CTAs per SM (build_conv_launch: `dual`) are held to the register budget of
+// two resident CTAs by their launch bounds (66 / 76 registers without it after the barrier peek: the residual profile no
+// longer fitted twice).
 template <int kBlockK, int EPI>
-__global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, (kBlockK <= 32 && (EPI == 0 || EPI == 1)) ? 2 : 1)
+conv_row_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kGroups = EpiCfg<EPI>::kRowGroups;
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t row_bytes = kBlockK * 2;
@@ -1455,7 +1459,7 @@ __global__ void __launch_bounds__(EpiCfg<EPI>::kRowThreads, 1) conv_row_kernel(c
         const int acc = it & (p.acc_stages - 1);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
         // 32-channel inputs with the plain profiles may run two CTAs per SM (build_conv_launch: `dual`): keep them lean
-        epilogue_one<EPI, !(kBlockK == 32 && (EPI == 0 || EPI == 1))>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x,
+        epilogue_one<EPI, !(kBlockK <= 32 && (EPI == 0 || EPI == 1))>(p, taddr, &s.tmem_full[acc], (it >> p.acc_shift) & 1, x,
                                                                      w.y0 + j, w.b, 0, valid, gain, smem_u32(s.bias), s_dm,
                                                                      nullptr, s_aux, p.block_n, 0, p.block_n);
         tc_fence_before();
