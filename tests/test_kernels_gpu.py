@@ -415,7 +415,7 @@ def test_conv_fused_to_rgb_and_next_modulation(B, H, W, C, no_store, with_skip):
     (1, 128, 384, 32, 32, 'plain'), (2, 64, 192, 64, 64, 'plain'), (3, 40, 200, 32, 64, 'plain'),
     (1, 128, 384, 64, 32, 'res2'), (2, 16, 130, 16, 16, 'plain'), (2, 9, 128, 64, 64, 'modrgb'),
     (2, 33, 256, 64, 64, 'modrgb'), (1, 1, 128, 32, 32, 'plain'), (2, 2, 140, 64, 32, 'plain'),
-    (5, 24, 384, 128, 64, 'plain'),
+    (5, 24, 384, 128, 64, 'plain'), (2, 40, 256, 32, 32, 'res1'), (3, 17, 130, 32, 16, 'res1'),
 ])
 def test_row_sliding_conv_forced(B, H, W, cin, cout, kind):
     """The row-sliding conv variant (one MMA of N = 3*cout per input row and kw tap, accumulator ring in TMEM), forced
@@ -437,6 +437,10 @@ def test_row_sliding_conv_forced(B, H, W, cin, cout, kind):
                   res_wh=(W // 2, H // 2), res_scale=1 / math.sqrt(2))
         ref = (F.leaky_relu(y + bias[None, :, None, None], 0.2) * math.sqrt(2) +
                F.interpolate(nchw32(lo), scale_factor=2, mode='bilinear', align_corners=False)) / math.sqrt(2)
+    elif kind == 'res1':      # same-resolution residual (the two-CTAs-per-SM instantiation of the residual profile)
+        rr = nhwc16(torch.randn(B, cout, H, W, device=DEV))
+        kw.update(res=rr, res_mode=1, res_strides=(cout, W * cout, H * W * cout), res_wh=(W, H), res_scale=1 / math.sqrt(2))
+        ref = (F.leaky_relu(y + bias[None, :, None, None], 0.2) * math.sqrt(2) + nchw32(rr)) / math.sqrt(2)
     elif kind == 'modrgb':
         demod = torch.rand(B, cout, device=DEV) + 0.5
         noise = torch.randn(B, 1, H, W, device=DEV)
