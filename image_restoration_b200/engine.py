@@ -411,7 +411,7 @@ class _Plan:
             raw = z16(B, h2 + 2, w2 + 2, cout)
             # merged form: N = 256 MMAs for the 64/128-channel levels and one launch for the small ones; the 512-channel
             # levels with enough tiles run faster as four exact-work phase GEMMs (tools/time_convt.py)
-            if eng.convt_merged and (cout <= 128 or B * h * w < 40000 or eng.convt_merged_all):
+            if eng.convt_merged and (cout <= eng.convt_merged_maxc or B * h * w < 40000 or eng.convt_merged_all):
                 # one implicit GEMM for the whole stride-2 transposed conv (phases = column blocks)
                 steps.append(ops.convt_s2_merged(xs, c1['w_merged'], raw, d_conv[2 * lvl]))
             else:
@@ -516,6 +516,7 @@ class OcrEngine:
         import os
         self.convt_merged = os.environ.get('B200IR_CONVT_MERGED', '1') != '0'
         self.convt_merged_all = os.environ.get('B200IR_CONVT_MERGED', '1') == '2'   # experiment: merged form at every level
+        self.convt_merged_maxc = int(os.environ.get('B200IR_CONVT_MERGED_MAXC', '128'))   # large levels: merged up to this cout
         self.upfold = os.environ.get('B200IR_UPFOLD', '1') != '0'
         self.upfold_all = os.environ.get('B200IR_UPFOLD', '1') == '2'     # experiment: fold every ConvUpLayer
 
